@@ -1,0 +1,776 @@
+/*
+ * reflexiv_oracle.c -- CPU restatement of Reflexiv's k-mer counting and
+ * reflexible contig extension.  TEST INFRASTRUCTURE ONLY (see the header).
+ *
+ * Citations are relative to
+ *   /root/reference/src/main/java/uni/bielefeld/cmg/reflexiv/
+ * ("DSMain" = pipeline/ReflexivDSMain.java, "Counter" =
+ * pipeline/ReflexivDataFrameCounter.java, "Counter64" =
+ * pipeline/ReflexivDataFrameCounter64.java).
+ *
+ * Where the reference's result depends on the arrival order Spark's shuffle
+ * happens to deliver (fork groups with >= 3 members, equal-count ties in the
+ * left fork filter, cycles, budget flags), this file fixes ONE realisable
+ * order and says so at the spot ("CANONICAL ORDER").  libreflexiv_cuda matches
+ * the same choices; DESIGN.md lists them.
+ */
+#define _GNU_SOURCE
+#include "reflexiv_oracle.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+
+static inline u128 mk128(uint64_t hi, uint64_t lo) { return ((u128)hi << 64) | lo; }
+static inline u128 mask_bases(int nb) { return nb >= 64 ? ~(u128)0 : (((u128)1 << (2 * nb)) - 1); }
+
+/* nucleotideValue: A=0 C=1 G=2, everything else (T, N, lower case ...) = 3.
+ * Counter:513-525, DSMain:4010-4022. */
+static inline unsigned base_code(unsigned char c) {
+    return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : 3u;
+}
+
+static u128 revcomp(u128 x, int k) {
+    /* DSKmerReverseComplementLong, DSMain:3857-3863 */
+    u128 r = 0;
+    for (int i = 0; i < k; i++) {
+        r = (r << 2) | ((x & 3) ^ 3);
+        x >>= 2;
+    }
+    return r;
+}
+
+void orc_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------ */
+/* A1 / A1': FASTQ line filters                                              */
+/* ------------------------------------------------------------------------ */
+
+static int is_atcgn(char a) { /* checkSeq, Counter:270-289 */
+    return a == 'A' || a == 'T' || a == 'C' || a == 'G' || a == 'N';
+}
+
+int64_t orc_fastq_reads(const char *txt, size_t n, int mode, uint64_t **starts_out, uint32_t **lens_out) {
+    size_t cap = 1024, cnt = 0;
+    uint64_t *starts = (uint64_t *)malloc(cap * sizeof(uint64_t));
+    uint32_t *lens = (uint32_t *)malloc(cap * sizeof(uint32_t));
+    int line_mark = 0;         /* DSFastqFilterWithQual.lineMark, DSMain:4050 */
+    uint64_t pend_start = 0;   /* the sequence line of the unit being assembled */
+    uint32_t pend_len = 0;
+    size_t pos = 0;
+    while (pos < n) {
+        /* spark.read().text(): one record per line, line terminator stripped
+         * (Hadoop LineRecordReader: \n, \r\n).  A final line without a
+         * terminator is still a record. */
+        const char *nl = (const char *)memchr(txt + pos, '\n', n - pos);
+        size_t end = nl ? (size_t)(nl - txt) : n;
+        size_t len = end - pos;
+        if (len > 0 && txt[pos + len - 1] == '\r') len--;
+        const char *s = txt + pos;
+        int emit = 0;
+        uint64_t e_start = 0;
+        uint32_t e_len = 0;
+        if (mode == ORC_FASTQ_RUN) {
+            /* DSMain:4051-4071 -- branch order matters */
+            if (line_mark == 2) {
+                line_mark = 3;
+            } else if (line_mark == 3) {
+                line_mark = 4;
+                emit = 1; e_start = pend_start; e_len = pend_len; /* units[1], DSMain:3964-3965 */
+            } else if (len > 0 && s[0] == '@') {
+                line_mark = 1;
+            } else if (line_mark == 1) {
+                line_mark = 2;
+                pend_start = pos; pend_len = (uint32_t)len;
+            }
+        } else if (mode == ORC_FASTQ_COUNTER) {
+            /* DSFastqFilterOnlySeq, Counter:247-266 */
+            if (len > 20 && s[0] != '@' && s[0] != '+' && is_atcgn(s[0]) && is_atcgn(s[4]) &&
+                is_atcgn(s[9]) && is_atcgn(s[14]) && is_atcgn(s[19])) {
+                emit = 1; e_start = pos; e_len = (uint32_t)len;
+            }
+        } else {
+            emit = 1; e_start = pos; e_len = (uint32_t)len;
+        }
+        if (emit) {
+            if (cnt == cap) {
+                cap *= 2;
+                starts = (uint64_t *)realloc(starts, cap * sizeof(uint64_t));
+                lens = (uint32_t *)realloc(lens, cap * sizeof(uint32_t));
+            }
+            starts[cnt] = e_start; lens[cnt] = e_len; cnt++;
+        }
+        pos = end + 1;
+    }
+    *starts_out = starts;
+    *lens_out = lens;
+    return (int64_t)cnt;
+}
+
+/* ------------------------------------------------------------------------ */
+/* A2 + A3 + A4: canonical k-mer extraction, counting, coverage filter       */
+/* ------------------------------------------------------------------------ */
+
+/* Does the reference keep this read?  k<=31: Counter:471 / DSMain:3968
+ * ("readLength - k - endClip <= 1" drops reads of length k and k+1);
+ * k>31: Counter64:410 ("readLength - k - endClip + 1 <= 0"). */
+static inline int read_is_kept(int64_t len, int k, int front_clip, int end_clip) {
+    if (front_clip > len) return 0;
+    if (k <= 31) return !(len - k - end_clip <= 1);
+    return !(len - k - end_clip + 1 <= 0);
+}
+
+static inline int64_t read_kmer_count(int64_t len, int k, int front_clip, int end_clip) {
+    if (!read_is_kept(len, k, front_clip, end_clip)) return 0;
+    int64_t m = len - end_clip - front_clip - k + 1;
+    return m > 0 ? m : 0;
+}
+
+/* splitmix64 finaliser: only used to spread keys over CPU partitions. */
+static inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+static void radix_sort_u64(uint64_t *a, uint64_t *tmp, size_t n, int key_bits) {
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        size_t hist[256] = {0};
+        for (size_t i = 0; i < n; i++) hist[(a[i] >> shift) & 255]++;
+        size_t sum = 0, single = 0;
+        for (int b = 0; b < 256; b++) { size_t c = hist[b]; if (c == n) single = 1; hist[b] = sum; sum += c; }
+        if (single) continue;
+        for (size_t i = 0; i < n; i++) tmp[hist[(a[i] >> shift) & 255]++] = a[i];
+        memcpy(a, tmp, n * sizeof(uint64_t));
+    }
+}
+
+static void radix_sort_u128(u128 *a, u128 *tmp, size_t n, int key_bits) {
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        size_t hist[256] = {0};
+        for (size_t i = 0; i < n; i++) hist[(unsigned)(a[i] >> shift) & 255]++;
+        size_t sum = 0, single = 0;
+        for (int b = 0; b < 256; b++) { size_t c = hist[b]; if (c == n) single = 1; hist[b] = sum; sum += c; }
+        if (single) continue;
+        for (size_t i = 0; i < n; i++) tmp[hist[(unsigned)(a[i] >> shift) & 255]++] = a[i];
+        memcpy(a, tmp, n * sizeof(u128));
+    }
+}
+
+#define ORC_PARTS 256
+
+typedef struct { u128 key; uint32_t count; } kc_t;
+
+static int kc_cmp(const void *a, const void *b) {
+    u128 x = ((const kc_t *)a)->key, y = ((const kc_t *)b)->key;
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+
+/* The rolling extractor of Counter:477-508 (k<=31) and, for k>31, the
+ * multi-slot one of Counter64:417-650 restated on one 128-bit integer:
+ *   fwd = ((fwd << 2) | v) & mask ; rc = (rc >> 2) | ((v ^ 3) << 2(k-1))
+ * emit min(fwd, rc) once k bases are in (Counter:501-506; Counter64:652-687
+ * compares base by base = numeric order of equal-length 2-bit strings,
+ * forward on a tie).  Calls sink(key) for every instance. */
+#define EXTRACT_READ(seq, len, k, fc, ec, KT, SINK)                                   \
+    do {                                                                              \
+        KT fwd = 0, rc = 0;                                                           \
+        const KT msk = (KT)mask_bases(k);                                             \
+        for (int64_t i_ = (fc); i_ < (int64_t)(len) - (ec); i_++) {                   \
+            KT v = (KT)base_code((unsigned char)(seq)[i_]);                           \
+            fwd = ((fwd << 2) | v) & msk;                                             \
+            rc = (rc >> 2) | ((v ^ 3) << (2 * ((k)-1)));                              \
+            if (i_ - (fc) >= (k)-1) { KT key_ = fwd < rc ? fwd : rc; SINK(key_); }    \
+        }                                                                             \
+    } while (0)
+
+int64_t orc_count_kmers(const char *txt, const uint64_t *starts, const uint32_t *lens, int64_t n_reads,
+                        int k, int front_clip, int end_clip, int64_t min_count, int64_t max_count,
+                        int n_threads, uint64_t **keys_hi, uint64_t **keys_lo, uint32_t **counts,
+                        int64_t *n_instances, int64_t *n_distinct) {
+    if (k < 1 || k > 63) return -1;
+    if (n_threads < 1) n_threads = 1;
+#ifndef _OPENMP
+    n_threads = 1;
+#endif
+    const int wide = k > 31;
+    const size_t ksz = wide ? sizeof(u128) : sizeof(uint64_t);
+
+    /* Pass 1: per (thread, partition) instance counts -> exact buffers.  This
+     * mirrors the reference's shape: map side emits every instance, a hash
+     * shuffle groups equal keys, a per-partition aggregate counts them
+     * (groupBy("value").count(), Counter:198-200). */
+    size_t *tp_count = (size_t *)calloc((size_t)n_threads * ORC_PARTS, sizeof(size_t));
+#define SINK_COUNT64(key) my[mix64(key) >> 56]++
+#define SINK_COUNT128(key) my[mix64((uint64_t)(key) ^ mix64((uint64_t)((key) >> 64))) >> 56]++
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+    for (int t = 0; t < n_threads; t++) {
+        size_t *my = tp_count + (size_t)t * ORC_PARTS;
+        int64_t lo = n_reads * t / n_threads, hi = n_reads * (t + 1) / n_threads;
+        for (int64_t r = lo; r < hi; r++) {
+            if (!read_is_kept(lens[r], k, front_clip, end_clip)) continue;
+            const char *seq = txt + starts[r];
+            if (!wide) EXTRACT_READ(seq, lens[r], k, front_clip, end_clip, uint64_t, SINK_COUNT64);
+            else EXTRACT_READ(seq, lens[r], k, front_clip, end_clip, u128, SINK_COUNT128);
+        }
+    }
+    /* partition-major layout: part p = [thread 0 | thread 1 | ...] */
+    size_t *tp_off = (size_t *)malloc(((size_t)n_threads * ORC_PARTS + 1) * sizeof(size_t));
+    size_t part_off[ORC_PARTS + 1];
+    size_t total = 0;
+    for (int p = 0; p < ORC_PARTS; p++) {
+        part_off[p] = total;
+        for (int t = 0; t < n_threads; t++) {
+            tp_off[(size_t)t * ORC_PARTS + p] = total;
+            total += tp_count[(size_t)t * ORC_PARTS + p];
+        }
+    }
+    part_off[ORC_PARTS] = total;
+    *n_instances = (int64_t)total;
+
+    char *buf = (char *)malloc((total ? total : 1) * ksz);
+    char *tmp = (char *)malloc((total ? total : 1) * ksz);
+#define SINK_PUT64(key) ((uint64_t *)buf)[my[mix64(key) >> 56]++] = (key)
+#define SINK_PUT128(key) ((u128 *)buf)[my[mix64((uint64_t)(key) ^ mix64((uint64_t)((key) >> 64))) >> 56]++] = (key)
+#pragma omp parallel for schedule(static, 1) num_threads(n_threads)
+    for (int t = 0; t < n_threads; t++) {
+        size_t *my = tp_off + (size_t)t * ORC_PARTS;
+        int64_t lo = n_reads * t / n_threads, hi = n_reads * (t + 1) / n_threads;
+        for (int64_t r = lo; r < hi; r++) {
+            if (!read_is_kept(lens[r], k, front_clip, end_clip)) continue;
+            const char *seq = txt + starts[r];
+            if (!wide) EXTRACT_READ(seq, lens[r], k, front_clip, end_clip, uint64_t, SINK_PUT64);
+            else EXTRACT_READ(seq, lens[r], k, front_clip, end_clip, u128, SINK_PUT128);
+        }
+    }
+    free(tp_count);
+    free(tp_off);
+
+    /* Pass 2: per-partition sort + run-length count + coverage filter (A4). */
+    kc_t *part_out[ORC_PARTS];
+    size_t part_n[ORC_PARTS];
+    size_t part_distinct[ORC_PARTS];
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+    for (int p = 0; p < ORC_PARTS; p++) {
+        size_t lo = part_off[p], n = part_off[p + 1] - lo;
+        part_out[p] = NULL; part_n[p] = 0; part_distinct[p] = 0;
+        if (n == 0) continue;
+        size_t cap = 1024, m = 0, distinct = 0;
+        kc_t *out = (kc_t *)malloc(cap * sizeof(kc_t));
+        if (!wide) {
+            uint64_t *a = (uint64_t *)buf + lo;
+            radix_sort_u64(a, (uint64_t *)tmp + lo, n, 2 * k);
+            for (size_t i = 0; i < n;) {
+                size_t j = i + 1;
+                while (j < n && a[j] == a[i]) j++;
+                int64_t c = (int64_t)(j - i);
+                distinct++;
+                if (c >= min_count && c <= max_count) {
+                    if (m == cap) { cap *= 2; out = (kc_t *)realloc(out, cap * sizeof(kc_t)); }
+                    out[m].key = a[i]; out[m].count = (uint32_t)c; m++;
+                }
+                i = j;
+            }
+        } else {
+            u128 *a = (u128 *)buf + lo;
+            radix_sort_u128(a, (u128 *)tmp + lo, n, 2 * k);
+            for (size_t i = 0; i < n;) {
+                size_t j = i + 1;
+                while (j < n && a[j] == a[i]) j++;
+                int64_t c = (int64_t)(j - i);
+                distinct++;
+                if (c >= min_count && c <= max_count) {
+                    if (m == cap) { cap *= 2; out = (kc_t *)realloc(out, cap * sizeof(kc_t)); }
+                    out[m].key = a[i]; out[m].count = (uint32_t)c; m++;
+                }
+                i = j;
+            }
+        }
+        part_out[p] = out; part_n[p] = m; part_distinct[p] = distinct;
+    }
+    free(buf);
+    free(tmp);
+
+    size_t m_total = 0, d_total = 0;
+    for (int p = 0; p < ORC_PARTS; p++) { m_total += part_n[p]; d_total += part_distinct[p]; }
+    *n_distinct = (int64_t)d_total;
+    kc_t *all = (kc_t *)malloc((m_total ? m_total : 1) * sizeof(kc_t));
+    size_t w = 0;
+    for (int p = 0; p < ORC_PARTS; p++) {
+        if (part_n[p]) memcpy(all + w, part_out[p], part_n[p] * sizeof(kc_t));
+        w += part_n[p];
+        free(part_out[p]);
+    }
+    /* Row order of the reference's CSV is partition dependent (A5); the
+     * oracle returns rows sorted by key so tables compare directly. */
+    qsort(all, m_total, sizeof(kc_t), kc_cmp);
+    *keys_hi = (uint64_t *)malloc((m_total ? m_total : 1) * sizeof(uint64_t));
+    *keys_lo = (uint64_t *)malloc((m_total ? m_total : 1) * sizeof(uint64_t));
+    *counts = (uint32_t *)malloc((m_total ? m_total : 1) * sizeof(uint32_t));
+    for (size_t i = 0; i < m_total; i++) {
+        (*keys_hi)[i] = (uint64_t)(all[i].key >> 64);
+        (*keys_lo)[i] = (uint64_t)all[i].key;
+        (*counts)[i] = all[i].count;
+    }
+    free(all);
+    return (int64_t)m_total;
+}
+
+/* ------------------------------------------------------------------------ */
+/* A6 + A7 + A8: both orientations, right fork filter, left fork filter      */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+    u128 key;      /* oriented k-mer */
+    int32_t left;  /* count until the left filter overwrites it, then flag */
+    int32_t right; /* count until the right filter overwrites it, then flag */
+} okmer_t;
+
+static int ok_cmp_key(const void *a, const void *b) {
+    u128 x = ((const okmer_t *)a)->key, y = ((const okmer_t *)b)->key;
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+
+static int g_rot_k; /* qsort has no context argument; single-threaded use only */
+static inline u128 rot_key(u128 key, int k) {
+    /* sort key of the reflected record: (k-1)-suffix, then first base.
+     * DSReflectedSubKmerExtractionFromForward, DSMain:3661-3685, followed by
+     * sort("k-1"), DSMain:244.  CANONICAL ORDER: rows that share a suffix are
+     * visited in ascending first-base order. */
+    return ((key & mask_bases(k - 1)) << 2) | (key >> (2 * (k - 1)));
+}
+static int ok_cmp_rot(const void *a, const void *b) {
+    u128 x = rot_key(((const okmer_t *)a)->key, g_rot_k), y = rot_key(((const okmer_t *)b)->key, g_rot_k);
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+
+int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const uint32_t *counts,
+                        int64_t n, int k, int min_error_cov, uint64_t **o_hi, uint64_t **o_lo,
+                        int32_t **o_left, int32_t **o_right, int64_t *stats) {
+    if (k < 2 || k > 63) return -1;
+    const int E = min_error_cov;
+    const int sub = k - 1; /* param.subKmerSize */
+    int64_t st[8] = {0};
+    /* A6: DSKmerReverseComplementLong (DSMain:3849-3869) emits the k-mer and
+     * its reverse complement (twice the same row for a palindrome, even k),
+     * DSForwardSubKmerExtraction (DSMain:3625-3644) sets left = right = count. */
+    okmer_t *a = (okmer_t *)malloc((size_t)(n > 0 ? 2 * n : 1) * sizeof(okmer_t));
+    for (int64_t i = 0; i < n; i++) {
+        u128 key = mk128(keys_hi[i], keys_lo[i]);
+        a[2 * i].key = key;
+        a[2 * i + 1].key = revcomp(key, k);
+        a[2 * i].left = a[2 * i].right = a[2 * i + 1].left = a[2 * i + 1].right = (int32_t)counts[i];
+    }
+    int64_t m = 2 * n;
+    /* sort("k-1") on the (k-1)-prefix, DSMain:232.  CANONICAL ORDER: rows that
+     * share a prefix are visited in ascending last-base order (full key order). */
+    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
+
+    /* A7 right fork filter: DSFilterForkSubKmerWithErrorCorrection
+     * (DSMain:3431-3483) when minErrorCoverage != 0, DSFilterForkSubKmer
+     * (DSMain:3375-3417) when it is 0 (DSMain:233-239). */
+    int64_t w = 0;
+    for (int64_t i = 0; i < m;) {
+        int64_t j = i + 1;
+        u128 prefix = a[i].key >> 2;
+        while (j < m && (a[j].key >> 2) == prefix) j++;
+        okmer_t cur = a[i];
+        cur.right = E ? -1 - cur.left : -1;
+        if (j - i >= 2) st[0]++;
+        if (j - i >= 3) st[1]++;
+        for (int64_t x = i + 1; x < j; x++) {
+            int cx = a[x].left, cc = cur.left;
+            if (cx > cc) {
+                int flag = sub;
+                if (E && cc <= E && cx >= 2 * cc) flag = -1 - cx;
+                cur = a[x]; cur.right = flag;
+            } else if (cx == cc) {
+                st[2]++;
+                if ((a[x].key & 3) > (cur.key & 3)) cur = a[x];
+                cur.right = sub;
+            } else {
+                if (E && cx <= E && cc >= 2 * cx) cur.right = -1 - cc;
+                else cur.right = sub;
+            }
+        }
+        a[w++] = cur;
+        i = j;
+    }
+    m = w;
+
+    /* A8: re-key on the suffix (DSMain:3661-3685), sort, left fork filter
+     * DSFilterForkReflectedSubKmerWithErrorCorrection (DSMain:3550-3616) /
+     * DSFilterForkReflectedSubKmer (DSMain:3489-3541). */
+    g_rot_k = k;
+    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_rot);
+    const u128 sufmask = mask_bases(k - 1);
+    w = 0;
+    for (int64_t i = 0; i < m;) {
+        int64_t j = i + 1;
+        u128 suffix = a[i].key & sufmask;
+        while (j < m && (a[j].key & sufmask) == suffix) j++;
+        okmer_t cur = a[i];
+        int H = cur.left; /* HighCoverLastCoverage */
+        cur.left = E ? -1 - H : -1;
+        if (j - i >= 2) st[3]++;
+        if (j - i >= 3) st[4]++;
+        for (int64_t x = i + 1; x < j; x++) {
+            int cx = a[x].left;
+            if (cx > H) {
+                int flag = sub;
+                if (E && H <= E && cx >= 2 * H) flag = -1 - cx;
+                H = cx;
+                cur = a[x]; cur.left = flag;
+            } else if (cx == H) {
+                st[5]++;
+                /* DSMain:3573-3578: the stored row's extension (4|base) is
+                 * shifted one base too far, so "4|base" is compared with 1
+                 * and the arriving row always wins. */
+                uint64_t ext_x = 4u | (uint64_t)(a[x].key >> (2 * (k - 1)));
+                uint64_t ext_c = 4u | (uint64_t)(cur.key >> (2 * (k - 1)));
+                uint64_t first_x = ext_x >> (2 * (1 - 1));
+                uint64_t first_c = ext_c >> (2 * 1);
+                if (first_x > first_c) cur = a[x];
+                cur.left = sub;
+            } else {
+                if (E && cx <= E && H >= 2 * cx) { /* stored row re-emitted unchanged, DSMain:3591-3596 */ }
+                else cur.left = sub;
+            }
+        }
+        a[w++] = cur;
+        i = j;
+    }
+    m = w;
+    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
+    *o_hi = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
+    *o_lo = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
+    *o_left = (int32_t *)malloc((size_t)(m ? m : 1) * sizeof(int32_t));
+    *o_right = (int32_t *)malloc((size_t)(m ? m : 1) * sizeof(int32_t));
+    for (int64_t i = 0; i < m; i++) {
+        (*o_hi)[i] = (uint64_t)(a[i].key >> 64);
+        (*o_lo)[i] = (uint64_t)a[i].key;
+        (*o_left)[i] = a[i].left;
+        (*o_right)[i] = a[i].right;
+        if (a[i].left >= 0) st[6]++;
+        if (a[i].right >= 0) st[7]++;
+    }
+    free(a);
+    if (stats) memcpy(stats, st, sizeof(st));
+    return m;
+}
+
+/* ------------------------------------------------------------------------ */
+/* A9 + A10: extension                                                       */
+/* ------------------------------------------------------------------------ */
+
+void orc_contigs_free(orc_contigs *c) {
+    free(c->offsets); free(c->bases); free(c->left); free(c->right);
+    memset(c, 0, sizeof(*c));
+}
+
+typedef struct {
+    size_t n, cap_n, nb, cap_b;
+    orc_contigs *c;
+} cbuild_t;
+
+static void cb_init(cbuild_t *b, orc_contigs *c) {
+    memset(c, 0, sizeof(*c));
+    b->n = 0; b->cap_n = 16; b->nb = 0; b->cap_b = 4096; b->c = c;
+    c->offsets = (uint64_t *)malloc((b->cap_n + 1) * sizeof(uint64_t));
+    c->left = (int32_t *)malloc(b->cap_n * sizeof(int32_t));
+    c->right = (int32_t *)malloc(b->cap_n * sizeof(int32_t));
+    c->bases = (char *)malloc(b->cap_b);
+    c->offsets[0] = 0;
+}
+
+static char *cb_begin(cbuild_t *b, size_t len, int32_t left, int32_t right) {
+    orc_contigs *c = b->c;
+    if (b->n == b->cap_n) {
+        b->cap_n *= 2;
+        c->offsets = (uint64_t *)realloc(c->offsets, (b->cap_n + 1) * sizeof(uint64_t));
+        c->left = (int32_t *)realloc(c->left, b->cap_n * sizeof(int32_t));
+        c->right = (int32_t *)realloc(c->right, b->cap_n * sizeof(int32_t));
+    }
+    while (b->nb + len > b->cap_b) { b->cap_b *= 2; c->bases = (char *)realloc(c->bases, b->cap_b); }
+    char *dst = c->bases + b->nb;
+    c->left[b->n] = left; c->right[b->n] = right;
+    b->nb += len; b->n++;
+    c->offsets[b->n] = b->nb;
+    c->n_contigs = (int64_t)b->n;
+    return dst;
+}
+
+/* DSKmerToContig, DSMain:743-771: drop if both flags <= -10^7, keep if
+ * length >= minContig. */
+static inline int contig_kept(int64_t len, int32_t left, int32_t right, int min_contig) {
+    if (left <= -10000000 && right <= -10000000) return 0;
+    return len >= min_contig;
+}
+
+static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+
+/* lower_bound on sorted keys */
+static int64_t lb_key(const u128 *keys, int64_t n, u128 x) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (keys[mid] < x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+/* A junction X -> Y (suffix(X) == prefix(Y)) is joined by the scan of
+ * DSExtendReflexivKmer*.call (DSMain:3069-3075 / 1809-1815) when the forward
+ * record's left flag and the reflected record's right flag are both negative
+ * or both non-negative.  Clauses 3/4 (budget >= 0 against a clean end,
+ * DSMain:3077-3084) depend on how long the partner already is when Spark
+ * happens to co-present the pair.  CANONICAL ORDER: unconditional joins run
+ * to the fixed point first; the mixed-sign junctions are left open and
+ * counted (n_budget_junctions / n_budget_admissible). */
+static inline int junction_joins(int32_t x_right, int32_t y_left) {
+    return (y_left < 0 && x_right < 0) || (y_left >= 0 && x_right >= 0);
+}
+
+static int assemble_canonical(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
+                              int k, int min_contig, orc_contigs *out) {
+    const u128 sufmask = mask_bases(k - 1);
+    int64_t *succ = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
+    int64_t *pred = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
+    for (int64_t i = 0; i < n; i++) pred[i] = -1;
+    int bad = 0;
+    for (int64_t i = 0; i < n; i++) {
+        u128 lo = (keys[i] & sufmask) << 2;
+        int64_t p = lb_key(keys, n, lo);
+        succ[i] = -1;
+        if (p < n && (keys[p] >> 2) == (lo >> 2)) {
+            if (p + 1 < n && (keys[p + 1] >> 2) == (lo >> 2)) bad = 1; /* out-degree > 1: not a filter output */
+            succ[i] = p;
+        }
+    }
+    for (int64_t i = 0; i < n && !bad; i++) {
+        if (succ[i] >= 0) {
+            if (pred[succ[i]] >= 0) bad = 1; /* in-degree > 1 */
+            pred[succ[i]] = i;
+        }
+    }
+    if (bad) { free(succ); free(pred); return -2; }
+    /* keep only joining junctions */
+    int64_t budget = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (succ[i] >= 0 && !junction_joins(right[i], left[succ[i]])) {
+            budget++;
+            pred[succ[i]] = -1;
+            succ[i] = -(2 + succ[i]); /* remember the open junction for the admissibility count */
+        }
+    }
+    cbuild_t cb; cb_init(&cb, out);
+    out->n_budget_junctions = budget;
+    char *seen = (char *)calloc((size_t)(n ? n : 1), 1);
+    int64_t *chain_len = (int64_t *)calloc((size_t)(n ? n : 1), sizeof(int64_t)); /* indexed by head and by tail */
+    /* chains, in ascending order of head key */
+    for (int64_t h = 0; h < n; h++) {
+        if (pred[h] >= 0) continue;
+        int64_t cnt = 0, t = h;
+        for (int64_t x = h; x >= 0; x = succ[x] >= 0 ? succ[x] : -1) { seen[x] = 1; cnt++; t = x; }
+        chain_len[h] = cnt; chain_len[t] = cnt;
+        int64_t len = cnt + k - 1;
+        if (!contig_kept(len, left[h], right[t], min_contig)) continue;
+        char *dst = cb_begin(&cb, (size_t)len, left[h], right[t]);
+        for (int b = 0; b < k; b++) dst[b] = ACGT[(unsigned)(keys[h] >> (2 * (k - 1 - b))) & 3];
+        int64_t pos = k;
+        for (int64_t x = succ[h]; x >= 0; x = succ[x] >= 0 ? succ[x] : -1) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
+    }
+    /* cycles: every junction joins.  The reference ends with one record whose
+     * two ends are the same (k-1)-mer; where it is cut is arrival-order
+     * dependent.  CANONICAL ORDER: start at the smallest k-mer of the cycle. */
+    for (int64_t s = 0; s < n; s++) {
+        if (seen[s]) continue;
+        /* s is the smallest index (= smallest key) of its cycle because we scan ascending */
+        int64_t cnt = 0;
+        for (int64_t x = s; !seen[x]; x = succ[x]) { seen[x] = 1; cnt++; }
+        out->n_cycles++;
+        int64_t len = cnt + k - 1;
+        int64_t t = pred[s];
+        if (!contig_kept(len, left[s], right[t], min_contig)) continue;
+        char *dst = cb_begin(&cb, (size_t)len, left[s], right[t]);
+        for (int b = 0; b < k; b++) dst[b] = ACGT[(unsigned)(keys[s] >> (2 * (k - 1 - b))) & 3];
+        int64_t pos = k;
+        for (int64_t x = succ[s]; x != s; x = succ[x]) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
+    }
+    /* open junctions where clause 3/4 would still fire on the finished fragments */
+    for (int64_t i = 0; i < n; i++) {
+        if (succ[i] <= -2) {
+            int64_t y = -(succ[i] + 2);
+            int64_t r_ext = chain_len[i], f_ext = chain_len[y]; /* |ext| = k-mers in the fragment */
+            if (left[y] >= 0 && left[y] - r_ext >= 0) out->n_budget_admissible++;
+            else if (right[i] >= 0 && right[i] - f_ext >= 0) out->n_budget_admissible++;
+        }
+    }
+    free(seen); free(chain_len); free(succ); free(pred);
+    return 0;
+}
+
+/* ---- pass-by-pass simulation of the reference's extension loop ---------- */
+
+typedef struct {
+    u128 sub;      /* sort key: first (marker 1) or last (marker 2) k-1 bases */
+    int marker;    /* 1 forward, 2 reflected */
+    int32_t left, right;
+    uint32_t len;  /* bases in seq = (k-1) + |extension| */
+    uint8_t *seq;  /* base codes */
+} rrec_t;
+
+static u128 seq_sub(const rrec_t *r, int k) {
+    u128 s = 0;
+    const uint8_t *p = r->marker == 1 ? r->seq : r->seq + (r->len - (uint32_t)(k - 1));
+    for (int i = 0; i < k - 1; i++) s = (s << 2) | p[i];
+    return s;
+}
+
+typedef struct { rrec_t *v; size_t n, cap; } rvec_t;
+static void rv_push(rvec_t *v, rrec_t r) {
+    if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 1024; v->v = (rrec_t *)realloc(v->v, v->cap * sizeof(rrec_t)); }
+    v->v[v->n++] = r;
+}
+
+/* singleKmerRandomizer, DSMain:3153-3226 / 3705-3788: the toggle decides on
+ * which end the record is keyed for the next sort, then flips. */
+static void randomize(rvec_t *out, rrec_t r, int *toggle, int k) {
+    if (r.marker != *toggle) { r.marker = *toggle; r.sub = seq_sub(&r, k); }
+    rv_push(out, r);
+    *toggle = (*toggle == 1) ? 2 : 1;
+}
+
+/* reflexivExtend, DSMain:3237-3325 (and 2077-2514): merged = R.ext + sub + F.ext */
+static void extend(rvec_t *out, rrec_t F, rrec_t R, int bubble, int *toggle, int k) {
+    rrec_t m;
+    m.len = R.len + F.len - (uint32_t)(k - 1);
+    m.seq = (uint8_t *)malloc(m.len);
+    memcpy(m.seq, R.seq, R.len);
+    memcpy(m.seq + R.len, F.seq + (k - 1), F.len - (uint32_t)(k - 1));
+    if (bubble < 0) { m.left = R.left; m.right = F.right; }
+    else if (F.left > 0) { m.left = bubble; m.right = F.right; }
+    else { m.left = R.left; m.right = bubble; }
+    m.marker = *toggle;
+    m.sub = seq_sub(&m, k);
+    free(F.seq); free(R.seq);
+    rv_push(out, m);
+    *toggle = (*toggle == 2) ? 1 : 2;
+}
+
+static int rrec_cmp(const void *a, const void *b) {
+    const rrec_t *x = (const rrec_t *)a, *y = (const rrec_t *)b;
+    if (x->sub != y->sub) return x->sub < y->sub ? -1 : 1;
+    /* Spark's sort is not stable; ties (one forward + one reflected record on
+     * the same key) merge identically in either order.  Fix forward-first. */
+    return x->marker - y->marker;
+}
+
+/* One mapPartitions(DSExtendReflexivKmer*) pass over one sorted partition,
+ * DSMain:3040-3147 / 1776-1888. */
+static void extension_pass(rvec_t *in, rvec_t *out, int k) {
+    int toggle = 2; /* randomReflexivMarker, fresh per task */
+    int have = 0;
+    rrec_t held;
+    memset(&held, 0, sizeof(held));
+    for (size_t i = 0; i < in->n; i++) {
+        rrec_t s = in->v[i];
+        if (!have) { held = s; have = 1; continue; } /* lineMarker==1 or tmp list empty */
+        if (s.sub == held.sub) {
+            if (s.marker != held.marker) {
+                rrec_t F = s.marker == 1 ? s : held, R = s.marker == 1 ? held : s;
+                int f_ext = (int)F.len - (k - 1), r_ext = (int)R.len - (k - 1);
+                if (F.left < 0 && R.right < 0) { extend(out, F, R, -1, &toggle, k); have = 0; }
+                else if (F.left >= 0 && R.right >= 0) { extend(out, F, R, -1, &toggle, k); have = 0; }
+                else if (F.left >= 0 && F.left - r_ext >= 0) { extend(out, F, R, F.left - r_ext, &toggle, k); have = 0; }
+                else if (R.right >= 0 && R.right - f_ext >= 0) { extend(out, F, R, R.right - f_ext, &toggle, k); have = 0; }
+                else randomize(out, s, &toggle, k);
+            } else {
+                randomize(out, s, &toggle, k);
+            }
+        } else {
+            randomize(out, held, &toggle, k); /* tmpKmerRandomizer */
+            held = s;
+        }
+    }
+    if (have) randomize(out, held, &toggle, k);
+    in->n = 0;
+}
+
+static int assemble_refsim(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
+                           int k, int min_contig, int min_iter, int max_iter, orc_contigs *out) {
+    rvec_t a = {0}, b = {0};
+    /* Output of the left fork filter: reflected records (suffix, 2, 4|firstBase),
+     * in suffix order (DSMain:3661-3685, 244). */
+    okmer_t *o = (okmer_t *)malloc((size_t)(n ? n : 1) * sizeof(okmer_t));
+    for (int64_t i = 0; i < n; i++) { o[i].key = keys[i]; o[i].left = left[i]; o[i].right = right[i]; }
+    g_rot_k = k;
+    qsort(o, (size_t)n, sizeof(okmer_t), ok_cmp_rot);
+    /* DSkmerRandomReflection, DSMain:3688-3792 */
+    int toggle = 2;
+    for (int64_t i = 0; i < n; i++) {
+        rrec_t r;
+        r.len = (uint32_t)k;
+        r.seq = (uint8_t *)malloc((size_t)k);
+        for (int j = 0; j < k; j++) r.seq[j] = (uint8_t)((o[i].key >> (2 * (k - 1 - j))) & 3);
+        r.marker = 2; r.left = o[i].left; r.right = o[i].right;
+        r.sub = seq_sub(&r, k);
+        randomize(&a, r, &toggle, k);
+    }
+    free(o);
+    /* DSMain:261-326 */
+    int iterations = 0;
+    int64_t passes = 0;
+    qsort(a.v, a.n, sizeof(rrec_t), rrec_cmp);
+    extension_pass(&a, &b, k); passes++;
+    for (int i = 1; i < 4; i++) {
+        iterations++;
+        qsort(b.v, b.n, sizeof(rrec_t), rrec_cmp);
+        extension_pass(&b, &a, k); passes++;
+        rvec_t t = a; a = b; b = t;
+    }
+    qsort(b.v, b.n, sizeof(rrec_t), rrec_cmp);
+    iterations++;
+    extension_pass(&b, &a, k); passes++; /* DSExtendReflexivKmerToArrayFirstTime */
+    int64_t contig_number = 0;
+    while (iterations <= max_iter) {
+        iterations++;
+        if (iterations >= min_iter && iterations % 3 == 0) {
+            int64_t cur = (int64_t)a.n;
+            if (contig_number == cur) break;
+            contig_number = cur;
+        }
+        qsort(a.v, a.n, sizeof(rrec_t), rrec_cmp);
+        extension_pass(&a, &b, k); passes++;
+        rvec_t t = a; a = b; b = t;
+    }
+    /* DSBinaryReflexivKmerArrayToString + DSKmerToContig, DSMain:855-900, 743-771 */
+    cbuild_t cb; cb_init(&cb, out);
+    out->n_passes = passes;
+    for (size_t i = 0; i < a.n; i++) {
+        rrec_t *r = &a.v[i];
+        if (contig_kept(r->len, r->left, r->right, min_contig)) {
+            char *dst = cb_begin(&cb, r->len, r->left, r->right);
+            for (uint32_t j = 0; j < r->len; j++) dst[j] = ACGT[r->seq[j]];
+        }
+        free(r->seq);
+    }
+    free(a.v); free(b.v);
+    return 0;
+}
+
+int orc_assemble(const uint64_t *o_hi, const uint64_t *o_lo, const int32_t *o_left, const int32_t *o_right,
+                 int64_t n, int k, int min_contig, int mode, int min_iter, int max_iter, orc_contigs *out) {
+    if (k < 2 || k > 63) return -1;
+    u128 *keys = (u128 *)malloc((size_t)(n ? n : 1) * sizeof(u128));
+    for (int64_t i = 0; i < n; i++) keys[i] = mk128(o_hi[i], o_lo[i]);
+    for (int64_t i = 1; i < n; i++) if (!(keys[i - 1] < keys[i])) { free(keys); return -3; } /* sorted, unique */
+    int rc = mode == ORC_ASM_REFSIM
+                 ? assemble_refsim(keys, o_left, o_right, n, k, min_contig, min_iter, max_iter, out)
+                 : assemble_canonical(keys, o_left, o_right, n, k, min_contig, out);
+    free(keys);
+    return rc;
+}
