@@ -1,0 +1,181 @@
+/*
+ * reflexiv_cuda.h -- C ABI of libreflexiv_cuda, the B200 (sm_100a) implementation of Reflexiv's
+ * k-mer counting + de Bruijn contig-extension path.
+ *
+ * The reference (rhinempi/Reflexiv) has no FFI: the path is a chain of Spark Dataset stages inside
+ *   src/main/java/uni/bielefeld/cmg/reflexiv/pipeline/ReflexivDataFrameCounter.java:139-236   (`reflexiv counter`)
+ *   src/main/java/uni/bielefeld/cmg/reflexiv/pipeline/ReflexivDSMain.java:123-357            (`reflexiv run`)
+ * This header is the seam a Java driver (JNI / Panama FFM) binds instead of those
+ * stages.  Each entry point names the reference stage(s) it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every call returns RFX_OK (0) or a negative rfx_status; rfx_last_error() gives the message;
+ *     the library never throws, exits or falls back to the CPU;
+ *   - host buffers are caller owned and not retained; results are copied into caller buffers;
+ *   - one context per driver thread, calls are blocking, the context owns its CUDA stream;
+ *   - k-mers are 2 bits per base (A=0 C=1 G=2 T=3, every other character counts as T exactly as
+ *     nucleotideValue() does), first base most significant.
+ */
+#ifndef REFLEXIV_CUDA_H
+#define REFLEXIV_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rfx_ctx rfx_ctx;
+
+typedef enum {
+    RFX_OK = 0,
+    RFX_E_INVALID = -1,     /* bad argument / unsupported parameter value */
+    RFX_E_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    RFX_E_NOMEM = -3,       /* device allocation failed */
+    RFX_E_STATE = -4,       /* call out of order (e.g. rfx_assemble before rfx_count) */
+    RFX_E_CAPACITY = -5,    /* an internal table overflowed; raise table_capacity */
+    RFX_E_GRAPH = -6,       /* k-mer set violates the in/out-degree <= 1 invariant after the fork filters */
+    RFX_E_UNSUPPORTED = -7  /* reference behaviour undefined for this option */
+} rfx_status;
+
+/* FASTQ line filter, selects which reference reader is mirrored */
+enum {
+    RFX_FASTQ_RUN = 0,     /* 4-line state machine: DSFastqFilterWithQual, ReflexivDSMain.java:4048-4072 */
+    RFX_FASTQ_COUNTER = 1, /* stateless heuristic:  DSFastqFilterOnlySeq, ReflexivDataFrameCounter.java:243-289 */
+    RFX_FASTQ_LINE = 2     /* -infmt line: every line is a read, ReflexivDataFrameCounter.java:184 */
+};
+
+/* The parameter block every reference operator closes over: util/DefaultParam.java:54-141. */
+typedef struct {
+    int32_t struct_size;        /* sizeof(rfx_params), for ABI evolution */
+    int32_t kmer_size;          /* -kmer          (31)        1..63 */
+    int32_t min_kmer_coverage;  /* -cover         (2)  */
+    int32_t max_kmer_coverage;  /* -maxcov        (10000000) */
+    int32_t min_error_coverage; /* -error         (8 = 4 * default cover; NOT updated by -cover, Parameter.java:479-487) */
+    int32_t min_contig;         /* -mincontig     (500) */
+    int32_t front_clip;         /* -clipf         (0) */
+    int32_t end_clip;           /* -clipe         (0) */
+    int32_t bubble;             /* 1 = fork filters on (default); -bubble clears it -> RFX_E_UNSUPPORTED in rfx_assemble */
+    int32_t min_iter;           /* -miniter       (15)  accepted; the extension runs to its fixed point */
+    int32_t max_iter;           /* -maxiter       (150) accepted */
+    int32_t partitions;         /* -partition     (0)   accepted, no numerical effect */
+    int32_t shuffle_partitions; /* -partitionredu (200) accepted, no numerical effect */
+    int32_t counter_mode;       /* 1 = `reflexiv counter` filter rule (ReflexivDataFrameCounter.java:202-210):
+                                   lower bound only if cover > 1, upper only if maxcov < 10000000;
+                                   0 = `reflexiv run` rule (ReflexivDSMain.java:211-216): always both */
+    int32_t fastq_mode;         /* RFX_FASTQ_* */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t minimizer_len;      /* 0 = auto.  super-k-mer minimiser length (<= 16) */
+    int32_t reserved0;
+    int64_t table_capacity;     /* 0 = auto.  rows reserved for the filtered (k-mer, count) table */
+    int64_t bin_target_kmers;   /* 0 = auto.  k-mer instances per counting bin */
+} rfx_params;
+
+typedef struct {
+    uint64_t n_reads;        /* sequence lines accepted by the FASTQ filter */
+    uint64_t n_bases;        /* bases kept after clipping / minimum-length rule */
+    uint64_t n_instances;    /* k-mer instances extracted (A2) */
+    uint64_t n_distinct;     /* distinct canonical k-mers before the coverage filter (A3) */
+    uint64_t n_rows;         /* rows after the coverage filter (A4) */
+    uint64_t n_records;      /* super-k-mer records */
+    uint64_t n_bins;
+    uint64_t n_bin_splits;   /* counting bins that had to be re-run in sub-classes */
+    uint64_t n_oriented;     /* oriented k-mers surviving both fork filters (A7, A8) */
+    uint64_t n_budget_junctions;   /* junctions left open because exactly one flag is >= 0 */
+    uint64_t n_budget_admissible;  /* ... of which a clause-3/4 merge would still be admissible */
+    uint64_t n_cycles;
+    uint64_t n_contigs;
+    uint64_t n_contig_bases;
+    uint64_t kernel_launches;  /* kernels launched by this context since creation */
+    float ms_parse;    /* K1: line split + FASTQ filter + 2-bit encode */
+    float ms_partition;/* K2: minimiser binning into super-k-mer records */
+    float ms_count;    /* K3+K4: per-bin counting + coverage filter */
+    float ms_graph;    /* K5: both orientations, fork filters, neighbour links */
+    float ms_extend;   /* K6: list ranking */
+    float ms_contigs;  /* K7: contig gather */
+} rfx_stats_t;
+
+int rfx_params_default(rfx_params* p);
+
+int rfx_create(rfx_ctx** out, const rfx_params* p);
+void rfx_destroy(rfx_ctx* ctx);
+const char* rfx_last_error(const rfx_ctx* ctx); /* ctx may be NULL: error of the last failed rfx_create */
+int rfx_reset(rfx_ctx* ctx);                     /* forget reads and results, keep device buffers */
+
+/* ---- input ----------------------------------------------------------------------------------
+ * replaces spark.read().text + DSFastqFilterWithQual / DSFastqFilterOnlySeq
+ * (ReflexivDSMain.java:188-195, ReflexivDataFrameCounter.java:178-188).
+ * `buf` is decompressed FASTQ text in host memory; may be called repeatedly, every call must end on a
+ * line boundary and (RFX_FASTQ_RUN) on a record boundary. */
+int rfx_push_fastq(rfx_ctx* ctx, const uint8_t* buf, size_t len);
+/* same, `d_buf` is a CUDA device pointer on the context's device (used when the text is already in HBM) */
+int rfx_push_fastq_device(rfx_ctx* ctx, const uint8_t* d_buf, size_t len);
+/* already-split reads: ASCII bases, read i = bases[offsets[i] .. offsets[i+1]) (host memory) */
+int rfx_push_reads(rfx_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads);
+
+/* ---- counting ------------------------------------------------------------------------------
+ * replaces ReverseComplementKmerBinaryExtractionFromDataset(64) + groupBy("value").count() + coverage filter
+ * (ReflexivDataFrameCounter.java:195-210, ReflexivDataFrameCounter64.java:197-212, ReflexivDSMain.java:204-216). */
+int rfx_count(rfx_ctx* ctx);
+int rfx_counts_size(rfx_ctx* ctx, uint64_t* n_rows, int32_t* words_per_key);
+/* keys: n_rows * words_per_key uint64, laid out exactly like the reference's key column so that
+ * DSBinaryKmerToString (ReflexivDataFrameCounter.java:405-428, Counter64.java:340-369) decodes them:
+ * k <= 31 one word, right aligned; k > 31: k/32+1 words, 32 bases per word, the last word holds k%32
+ * bases right aligned.  Row order is unspecified (as in the reference). */
+int rfx_counts_copy(rfx_ctx* ctx, uint64_t* keys, uint32_t* counts);
+/* `KMER,count\n` rows (the reference's CSV part-file content, A5).  Call with out == NULL to get the size. */
+int rfx_counts_csv(rfx_ctx* ctx, char* out, uint64_t cap, uint64_t* n_bytes);
+/* load an existing filtered table instead of counting (the -kmerc seam, ReflexivDSMain.java:362-713);
+ * keys in the layout rfx_counts_copy produces */
+int rfx_load_counts(rfx_ctx* ctx, const uint64_t* keys, const uint32_t* counts, uint64_t n_rows);
+
+/* ---- assembly ------------------------------------------------------------------------------
+ * replaces DSKmerReverseComplementLong .. DSExtendReflexivKmerToArrayLoop .. DSKmerToContig
+ * (ReflexivDSMain.java:221-338). */
+int rfx_assemble(rfx_ctx* ctx);
+int rfx_contigs_size(rfx_ctx* ctx, uint64_t* n_contigs, uint64_t* total_bases);
+/* bases: total_bases chars ACGT; offsets: n_contigs+1; left/right: the two flags printed in the header
+ * ">Contig-<len>-(<left>,<right>)-<idx>" (DSKmerToContig, ReflexivDSMain.java:743-771).
+ * Every contig appears on both strands, order unspecified (as in the reference). */
+int rfx_contigs_copy(rfx_ctx* ctx, char* bases, uint64_t* offsets, int32_t* left, int32_t* right);
+/* surviving oriented k-mers with their fork-filter flags (the Count_<k>_sorted content) */
+int rfx_oriented_size(rfx_ctx* ctx, uint64_t* n);
+int rfx_oriented_copy(rfx_ctx* ctx, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right);
+
+int rfx_stats(rfx_ctx* ctx, rfx_stats_t* out);
+
+/* ---- sharded counting (one context per GPU; the caller moves records between GPUs) ------------
+ * Bins are laid out shard-major: with B bins in total, shard s owns bins [s*B/n, (s+1)*B/n) and its
+ * records are one contiguous device slice.  Sender: rfx_partition(ctx, n, B) then rfx_shard_records()
+ * for every s.  The caller exchanges the slices (NCCL all-to-all over NVLink: this replaces the
+ * groupBy hash shuffle, ReflexivDataFrameCounter.java:198-200).  Receiver: rfx_begin_shard(ctx, s, n, B),
+ * rfx_load_records_device() for every received slice, then rfx_count() re-bins and counts them.
+ * B (n_bins_total) must be the same on every rank and a multiple of n; 0 = let the library choose
+ * (single-process use only). */
+int rfx_partition(rfx_ctx* ctx, int32_t n_shards, uint32_t n_bins_total);
+int rfx_shard_records(rfx_ctx* ctx, int32_t shard, const void** d_ptr, uint64_t* n_bytes);
+int rfx_begin_shard(rfx_ctx* ctx, int32_t shard_id, int32_t n_shards, uint32_t n_bins_total);
+int rfx_load_records_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes);
+int rfx_record_bytes(rfx_ctx* ctx, int32_t* bytes_per_record);
+
+/* ---- synthetic data (host, deterministic) ----------------------------------------- */
+int64_t rfx_synth_genome(uint8_t* out, int64_t n_bases, uint64_t seed);
+/* FASTQ text of pairs [first_pair, first_pair+n_pairs): mate 1 records then mate 2 records.
+ * Returns bytes written, or the required capacity when out == NULL. */
+int64_t rfx_synth_fastq(const uint8_t* genome, int64_t genome_len, int64_t first_pair, int64_t n_pairs,
+                        int32_t read_len, int32_t frag_len, double error_rate, uint64_t seed_reads,
+                        uint64_t seed_errors, uint8_t* out, int64_t cap);
+
+/* ---- debug / test access to intermediate device state (copies to host) ----------------------- */
+int rfx_debug_reads(rfx_ctx* ctx, uint64_t* n_reads, uint64_t* total_words, uint32_t* lens /*n_reads or NULL*/,
+                    uint64_t* word_offsets /*n_reads or NULL*/, uint64_t* words /*total_words or NULL*/);
+int rfx_debug_records(rfx_ctx* ctx, uint64_t* n_records, uint32_t* n_bins, uint64_t* bin_offsets /*n_bins+1 or NULL*/,
+                      uint64_t* records /* n_records * words or NULL */);
+
+const char* rfx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REFLEXIV_CUDA_H */

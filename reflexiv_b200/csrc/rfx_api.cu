@@ -1,0 +1,484 @@
+// rfx_api.cu -- the C ABI of libreflexiv_cuda (include/reflexiv_cuda.h): context life cycle,
+// host <-> device copies, result layout conversion.  No compute lives here except small formatting
+// kernels (CSV rows, oriented k-mer export).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "rfx_internal.h"
+#include "rfx_scan.cuh"
+
+namespace rfx {
+
+static thread_local std::string g_create_error;
+
+int ctx_fail(Ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep) {
+    if (bytes <= b.cap) return RFX_OK;
+    size_t want = bytes;
+    if (keep && b.cap) want = bytes > b.cap * 2 ? bytes : b.cap * 2;  // appended buffers grow geometrically
+    want = (want + 255) & ~(size_t)255;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx_fail(c, RFX_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+    if (b.p) {
+        if (c && c->stream) cudaStreamSynchronize(c->stream);
+        if (keep && b.cap) cudaMemcpy(p, b.p, b.cap, cudaMemcpyDeviceToDevice);
+        cudaFree(b.p);
+    }
+    b.p = p;
+    b.cap = want;
+    return RFX_OK;
+}
+
+void devbuf_free(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static void free_all(Ctx* c) {
+    DevBuf* all[] = {&c->text, &c->line_start, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
+                     &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->anc[0],
+                     &c->anc[1], &c->dist[0], &c->dist[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records};
+    for (DevBuf* b : all) devbuf_free(*b);
+}
+
+// ---- CSV rows: "KMER,count\n" (DSBinaryKmerToString + write().csv, ReflexivDataFrameCounter.java:405-428, 222-233)
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
+    uint32_t d = 1;
+    while (v >= 10) { v /= 10; d++; }
+    return d;
+}
+struct CsvIn {
+    const uint32_t* counts;
+    int k;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)k + 2 + dec_digits(counts[i]); }
+};
+template <class KT> struct CsvOut {
+    const KT* keys;
+    const uint32_t* counts;
+    int k;
+    char* out;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t excl, uint64_t len) const {
+        char* p = out + excl;
+        const KT key = keys[i];
+        for (int j = 0; j < k; j++) p[j] = "ACGT"[(uint32_t)(key >> (2 * (k - 1 - j))) & 3u];
+        p[k] = ',';
+        uint32_t v = counts[i];
+        for (int j = (int)len - 2; j > k; j--) { p[j] = (char)('0' + v % 10); v /= 10; }
+        p[len - 1] = '\n';
+    }
+};
+
+// ---- oriented k-mer export ----
+struct AliveIn {
+    const uint8_t* alive;
+    __device__ __forceinline__ uint64_t operator()(uint64_t x) const { return (alive[x] & 2) ? 1 : 0; }
+};
+template <class KT> struct OrientedOut {
+    const KT* keys;
+    int k;
+    const int32_t* lflag;
+    const int32_t* rflag;
+    uint64_t* hi;
+    uint64_t* lo;
+    int32_t* left;
+    int32_t* right;
+    __device__ __forceinline__ void operator()(uint64_t x, uint64_t excl, uint64_t v) const {
+        if (!v) return;
+        KT key = keys[x >> 1];
+        if (x & 1) key = revcomp(key, k);
+        const u128 wide = (u128)key;
+        hi[excl] = (uint64_t)(wide >> 64);
+        lo[excl] = (uint64_t)wide;
+        left[excl] = lflag[x];
+        right[excl] = rflag[x];
+    }
+};
+
+static int derive(Ctx* c) {
+    const rfx_params& p = c->prm;
+    if (p.kmer_size < 1 || p.kmer_size > 63) return ctx_fail(c, RFX_E_INVALID, "kmer_size %d outside 1..63", p.kmer_size);
+    if (p.front_clip < 0 || p.end_clip < 0) return ctx_fail(c, RFX_E_INVALID, "negative clip");
+    c->k = p.kmer_size;
+    c->wide = c->k > 31;
+    c->recw = rec_words_for_k(c->k);
+    c->max_nk = (uint32_t)rec_max_kmers(c->recw, c->k);
+    int m = p.minimizer_len > 0 ? p.minimizer_len : 11;
+    if (m > 16) m = 16;
+    if (m > c->k) m = c->k;
+    c->m = m;
+    return RFX_OK;
+}
+
+}  // namespace rfx
+
+using namespace rfx;
+
+extern "C" {
+
+const char* rfx_version(void) { return "reflexiv_cuda 0.1 (sm_100a)"; }
+
+int rfx_params_default(rfx_params* p) {
+    if (!p) return RFX_E_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = (int32_t)sizeof(rfx_params);
+    p->kmer_size = 31;            // DefaultParam.java:78
+    p->min_kmer_coverage = 2;     // :104
+    p->max_kmer_coverage = 10000000;  // :105
+    p->min_error_coverage = 8;    // :106 (4 * minKmerCoverage at construction)
+    p->min_contig = 500;          // :108
+    p->bubble = 1;                // :109
+    p->min_iter = 15;             // :116
+    p->max_iter = 150;            // :115
+    p->partitions = 0;            // :114
+    p->shuffle_partitions = 200;  // :123
+    p->fastq_mode = RFX_FASTQ_RUN;
+    return RFX_OK;
+}
+
+int rfx_create(rfx_ctx** out, const rfx_params* p) {
+    if (!out || !p) return ctx_fail(nullptr, RFX_E_INVALID, "rfx_create: null argument");
+    if (p->struct_size != (int32_t)sizeof(rfx_params)) return ctx_fail(nullptr, RFX_E_INVALID, "rfx_create: rfx_params size mismatch");
+    rfx_ctx* c = new rfx_ctx();
+    c->prm = *p;
+    int rc = derive(c);
+    if (rc != RFX_OK) { g_create_error = c->err; delete c; return rc; }
+    cudaError_t e = cudaSetDevice(p->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e != cudaSuccess) {
+        // no CPU fallback: without a usable CUDA device the library refuses to create a context
+        rc = ctx_fail(nullptr, RFX_E_CUDA, "rfx_create: CUDA device %d unusable: %s", p->device, cudaGetErrorString(e));
+        delete c;
+        return rc;
+    }
+    rc = devbuf_reserve(c, c->dstat, DS_NSLOTS * sizeof(uint64_t));
+    if (rc != RFX_OK) { g_create_error = c->err; rfx_destroy(c); return rc; }
+    *out = c;
+    return RFX_OK;
+}
+
+void rfx_destroy(rfx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_all(c);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* rfx_last_error(const rfx_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int rfx_reset(rfx_ctx* c) {
+    if (!c) return RFX_E_INVALID;
+    c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
+    c->n_records = 0; c->n_bins = 0; c->have_records = false;
+    c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
+    c->have_contigs = false;
+    c->rx_bytes = 0; c->shard_id = -1;
+    for (float& m : c->ms) m = 0;
+    return RFX_OK;
+}
+
+int rfx_push_fastq_device(rfx_ctx* c, const uint8_t* d_buf, size_t len) {
+    if (!c || (!d_buf && len)) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    return stage_parse_fastq(c, d_buf, len);
+}
+
+int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
+    if (!c || (!buf && len)) return RFX_E_INVALID;
+    if (len == 0) return RFX_OK;
+    cudaSetDevice(c->prm.device);
+    RFX_TRY(devbuf_reserve(c, c->text, len + 64));
+    RFX_CUDA(c, cudaMemcpyAsync(c->text.p, buf, len, cudaMemcpyHostToDevice, c->stream));
+    RFX_CUDA(c, cudaMemsetAsync(c->text.as<uint8_t>() + len, 0, 64, c->stream));
+    return rfx_push_fastq_device(c, c->text.as<uint8_t>(), len);
+}
+
+int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {
+    if (!c || !offsets || (!bases && n_reads && offsets[n_reads])) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    return stage_push_reads(c, bases, offsets, n_reads);
+}
+
+int rfx_partition(rfx_ctx* c, int32_t n_shards, uint32_t n_bins_total) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    c->forced_bins = n_bins_total;
+    return stage_partition(c, n_shards);
+}
+
+int rfx_count(rfx_ctx* c) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    if (c->shard_id >= 0) RFX_TRY(stage_rebin(c));
+    else if (!c->have_records) RFX_TRY(stage_partition(c, 1));
+    return stage_count(c);
+}
+
+int rfx_counts_size(rfx_ctx* c, uint64_t* n_rows, int32_t* words_per_key) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "no count table");
+    if (n_rows) *n_rows = c->n_rows;
+    if (words_per_key) *words_per_key = c->k <= 31 ? 1 : c->k / 32 + 1;
+    return RFX_OK;
+}
+
+int rfx_counts_copy(rfx_ctx* c, uint64_t* keys, uint32_t* counts) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "no count table");
+    cudaSetDevice(c->prm.device);
+    const uint64_t n = c->n_rows;
+    if (n == 0) return RFX_OK;
+    if (counts) RFX_CUDA(c, cudaMemcpyAsync(counts, c->counts.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (keys) {
+        if (!c->wide) {
+            RFX_CUDA(c, cudaMemcpyAsync(keys, c->keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            // internal: one right-aligned 2k-bit integer.  reference (Counter64.java:417-440): k/32+1 words,
+            // 32 bases per word, the last word holds k%32 bases right aligned.
+            std::vector<u128> tmp(n);
+            RFX_CUDA(c, cudaMemcpyAsync(tmp.data(), c->keys.p, n * sizeof(u128), cudaMemcpyDeviceToHost, c->stream));
+            RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+            const int res = c->k - 32;
+            const uint64_t resmask = res ? (uint64_t)(((u128)1 << (2 * res)) - 1) : 0;
+            for (uint64_t i = 0; i < n; i++) {
+                keys[2 * i] = (uint64_t)(tmp[i] >> (2 * res));
+                keys[2 * i + 1] = (uint64_t)tmp[i] & resmask;
+            }
+        }
+    }
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RFX_OK;
+}
+
+int rfx_load_counts(rfx_ctx* c, const uint64_t* keys, const uint32_t* counts, uint64_t n_rows) {
+    if (!c || (n_rows && (!keys || !counts))) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    const size_t ksz = c->wide ? sizeof(u128) : sizeof(uint64_t);
+    RFX_TRY(devbuf_reserve(c, c->keys, (n_rows + 1) * ksz));
+    RFX_TRY(devbuf_reserve(c, c->counts, (n_rows + 1) * sizeof(uint32_t)));
+    if (n_rows) {
+        if (!c->wide) {
+            RFX_CUDA(c, cudaMemcpyAsync(c->keys.p, keys, n_rows * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+        } else {
+            std::vector<u128> tmp(n_rows);
+            const int res = c->k - 32;
+            for (uint64_t i = 0; i < n_rows; i++) tmp[i] = ((u128)keys[2 * i] << (2 * res)) | keys[2 * i + 1];
+            RFX_CUDA(c, cudaMemcpyAsync(c->keys.p, tmp.data(), n_rows * sizeof(u128), cudaMemcpyHostToDevice, c->stream));
+            RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        RFX_CUDA(c, cudaMemcpyAsync(c->counts.p, counts, n_rows * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_rows = n_rows;
+    c->table_cap = n_rows + 1;
+    c->have_counts = true;
+    c->have_contigs = false;
+    return RFX_OK;
+}
+
+int rfx_counts_csv(rfx_ctx* c, char* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!c || !n_bytes) return RFX_E_INVALID;
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "no count table");
+    cudaSetDevice(c->prm.device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n_rows;
+    if (n == 0) { *n_bytes = 0; return RFX_OK; }
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n) * sizeof(uint64_t)));
+    plan.bind(n, c->scan_ws.as<uint64_t>());
+    CsvIn in{c->counts.as<uint32_t>(), c->k};
+    scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 2 * plan.levels;
+    uint64_t total = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&total, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    *n_bytes = total;
+    if (!out) return RFX_OK;
+    if (cap < total) return ctx_fail(c, RFX_E_INVALID, "rfx_counts_csv: buffer of %llu bytes, need %llu", (unsigned long long)cap, (unsigned long long)total);
+    DevBuf txt;
+    RFX_TRY(devbuf_reserve(c, txt, total + 16));
+    if (!c->wide) scan_apply(plan, in, CsvOut<uint64_t>{c->keys.as<uint64_t>(), c->counts.as<uint32_t>(), c->k, txt.as<char>()}, OpAddU64{}, (uint64_t)0, st);
+    else scan_apply(plan, in, CsvOut<u128>{c->keys.as<u128>(), c->counts.as<uint32_t>(), c->k, txt.as<char>()}, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 1;
+    cudaError_t e = cudaMemcpyAsync(out, txt.p, total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    devbuf_free(txt);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rfx_counts_csv: %s", cudaGetErrorString(e));
+    return RFX_OK;
+}
+
+int rfx_assemble(rfx_ctx* c) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    return stage_graph(c);
+}
+
+int rfx_contigs_size(rfx_ctx* c, uint64_t* n_contigs, uint64_t* total_bases) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no contigs (call rfx_assemble)");
+    if (n_contigs) *n_contigs = c->n_contigs;
+    if (total_bases) *total_bases = c->n_contig_bases;
+    return RFX_OK;
+}
+
+int rfx_contigs_copy(rfx_ctx* c, char* bases, uint64_t* offsets, int32_t* left, int32_t* right) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no contigs (call rfx_assemble)");
+    cudaSetDevice(c->prm.device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n_contigs;
+    if (offsets) RFX_CUDA(c, cudaMemcpyAsync(offsets, c->ctg_off.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    if (n) {
+        if (bases) RFX_CUDA(c, cudaMemcpyAsync(bases, c->ctg_bases.p, c->n_contig_bases, cudaMemcpyDeviceToHost, st));
+        if (left) RFX_CUDA(c, cudaMemcpyAsync(left, c->ctg_left.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (right) RFX_CUDA(c, cudaMemcpyAsync(right, c->ctg_right.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    return RFX_OK;
+}
+
+int rfx_oriented_size(rfx_ctx* c, uint64_t* n) {
+    if (!c || !n) return RFX_E_INVALID;
+    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no graph (call rfx_assemble)");
+    *n = c->n_oriented;
+    return RFX_OK;
+}
+
+int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right) {
+    if (!c || !keys_hi || !keys_lo || !left || !right) return RFX_E_INVALID;
+    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no graph (call rfx_assemble)");
+    cudaSetDevice(c->prm.device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows, m = c->n_oriented;
+    if (m == 0) return RFX_OK;
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n) * sizeof(uint64_t)));
+    plan.bind(n, c->scan_ws.as<uint64_t>());
+    AliveIn in{c->alive.as<uint8_t>()};
+    scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
+    DevBuf tmp;
+    RFX_TRY(devbuf_reserve(c, tmp, m * 24 + 64));
+    uint64_t* d_hi = tmp.as<uint64_t>();
+    uint64_t* d_lo = d_hi + m;
+    int32_t* d_l = reinterpret_cast<int32_t*>(d_lo + m);
+    int32_t* d_r = d_l + m;
+    if (!c->wide)
+        scan_apply(plan, in, OrientedOut<uint64_t>{c->keys.as<uint64_t>(), c->k, c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
+    else
+        scan_apply(plan, in, OrientedOut<u128>{c->keys.as<u128>(), c->k, c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 2 * plan.levels + 1;
+    cudaMemcpyAsync(keys_hi, d_hi, m * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(keys_lo, d_lo, m * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(left, d_l, m * 4, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(right, d_r, m * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    devbuf_free(tmp);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rfx_oriented_copy: %s", cudaGetErrorString(e));
+    return RFX_OK;
+}
+
+int rfx_stats(rfx_ctx* c, rfx_stats_t* s) {
+    if (!c || !s) return RFX_E_INVALID;
+    memset(s, 0, sizeof(*s));
+    s->n_reads = c->n_reads; s->n_bases = c->n_bases; s->n_instances = c->n_instances; s->n_distinct = c->n_distinct;
+    s->n_rows = c->n_rows; s->n_records = c->n_records; s->n_bins = c->n_bins; s->n_bin_splits = c->n_bin_splits;
+    s->n_oriented = c->n_oriented; s->n_budget_junctions = c->n_budget; s->n_budget_admissible = c->n_budget_adm;
+    s->n_cycles = c->n_cycles; s->n_contigs = c->n_contigs; s->n_contig_bases = c->n_contig_bases;
+    s->kernel_launches = c->launches;
+    s->ms_parse = c->ms[0]; s->ms_partition = c->ms[1]; s->ms_count = c->ms[2];
+    s->ms_graph = c->ms[3]; s->ms_extend = c->ms[4]; s->ms_contigs = c->ms[5];
+    return RFX_OK;
+}
+
+// ---- sharded counting ---------------------------------------------------------------------------
+int rfx_record_bytes(rfx_ctx* c, int32_t* bytes_per_record) {
+    if (!c || !bytes_per_record) return RFX_E_INVALID;
+    *bytes_per_record = c->recw * 8;
+    return RFX_OK;
+}
+
+int rfx_shard_records(rfx_ctx* c, int32_t shard, const void** d_ptr, uint64_t* n_bytes) {
+    if (!c || !d_ptr || !n_bytes) return RFX_E_INVALID;
+    if (!c->have_records) return ctx_fail(c, RFX_E_STATE, "rfx_shard_records: call rfx_partition first");
+    if (shard < 0 || shard >= c->n_shards) return ctx_fail(c, RFX_E_INVALID, "shard %d outside 0..%d", shard, c->n_shards - 1);
+    cudaSetDevice(c->prm.device);
+    const uint32_t bps = c->n_bins / (uint32_t)c->n_shards;
+    uint64_t lo = 0, hi = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&lo, c->bin_off.as<uint64_t>() + (uint64_t)shard * bps, 8, cudaMemcpyDeviceToHost, c->stream));
+    RFX_CUDA(c, cudaMemcpyAsync(&hi, c->bin_off.as<uint64_t>() + (uint64_t)(shard + 1) * bps, 8, cudaMemcpyDeviceToHost, c->stream));
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    *d_ptr = c->records.as<uint64_t>() + lo * c->recw;
+    *n_bytes = (hi - lo) * c->recw * 8;
+    return RFX_OK;
+}
+
+int rfx_begin_shard(rfx_ctx* c, int32_t shard_id, int32_t n_shards, uint32_t n_bins_total) {
+    if (!c || n_shards < 1 || shard_id < 0 || shard_id >= n_shards || n_bins_total == 0 || n_bins_total % (uint32_t)n_shards)
+        return c ? ctx_fail(c, RFX_E_INVALID, "rfx_begin_shard: bad shard geometry") : RFX_E_INVALID;
+    c->shard_id = shard_id; c->n_shards = n_shards; c->forced_bins = n_bins_total;
+    c->rx_bytes = 0;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    return RFX_OK;
+}
+
+int rfx_load_records_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes) {
+    if (!c || (!d_records && n_bytes)) return RFX_E_INVALID;
+    if (c->shard_id < 0) return ctx_fail(c, RFX_E_STATE, "rfx_load_records_device: call rfx_begin_shard first");
+    if (n_bytes % (uint64_t)(c->recw * 8)) return ctx_fail(c, RFX_E_INVALID, "record bytes not a multiple of %d", c->recw * 8);
+    cudaSetDevice(c->prm.device);
+    RFX_TRY(devbuf_reserve(c, c->rx_records, c->rx_bytes + n_bytes + 16, true));
+    if (n_bytes) RFX_CUDA(c, cudaMemcpyAsync(c->rx_records.as<uint8_t>() + c->rx_bytes, d_records, n_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->rx_bytes += n_bytes;
+    return RFX_OK;
+}
+
+// ---- debug ---------------------------------------------------------------------------------------
+int rfx_debug_reads(rfx_ctx* c, uint64_t* n_reads, uint64_t* total_words, uint32_t* lens, uint64_t* word_offsets, uint64_t* words) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    if (n_reads) *n_reads = c->n_reads;
+    if (total_words) *total_words = c->n_words;
+    if (lens && c->n_reads) RFX_CUDA(c, cudaMemcpy(lens, c->rd_len.p, c->n_reads * 4, cudaMemcpyDeviceToHost));
+    if (word_offsets && c->n_reads) RFX_CUDA(c, cudaMemcpy(word_offsets, c->rd_woff.p, c->n_reads * 8, cudaMemcpyDeviceToHost));
+    if (words && c->n_words) RFX_CUDA(c, cudaMemcpy(words, c->packed.p, c->n_words * 8, cudaMemcpyDeviceToHost));
+    return RFX_OK;
+}
+
+int rfx_debug_records(rfx_ctx* c, uint64_t* n_records, uint32_t* n_bins, uint64_t* bin_offsets, uint64_t* records) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_records) return ctx_fail(c, RFX_E_STATE, "no records");
+    cudaSetDevice(c->prm.device);
+    if (n_records) *n_records = c->n_records;
+    if (n_bins) *n_bins = c->n_bins;
+    if (bin_offsets) RFX_CUDA(c, cudaMemcpy(bin_offsets, c->bin_off.p, ((size_t)c->n_bins + 1) * 8, cudaMemcpyDeviceToHost));
+    if (records && c->n_records) RFX_CUDA(c, cudaMemcpy(records, c->records.p, c->n_records * c->recw * 8, cudaMemcpyDeviceToHost));
+    return RFX_OK;
+}
+
+}  // extern "C"

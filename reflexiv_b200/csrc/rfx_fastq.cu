@@ -1,0 +1,350 @@
+// rfx_fastq.cu -- K1: FASTQ line split, the reference's line filters, 2-bit encoder.
+//
+// Replaces (paths relative to /root/reference/src/main/java/uni/bielefeld/cmg/reflexiv/pipeline/):
+//   spark.read().text + DSFastqFilterWithQual        ReflexivDSMain.java:188-195, 4048-4072
+//   DSFastqFilterOnlySeq                              ReflexivDataFrameCounter.java:243-289
+//   nucleotideValue + the clip / minimum-length rule  ReflexivDataFrameCounter.java:471, 513-525
+//
+// Device data flow (all in HBM):
+//   text bytes --newline scan--> line_start[] --filter scan--> seq_flag[] --sum scan--> read table
+//   (source offset, effective length, word offset) --warp-cooperative encoder--> packed 2-bit reads.
+#include "rfx_internal.h"
+#include "rfx_scan.cuh"
+
+namespace rfx {
+
+// ------------------------------------------------------------------------------------------
+// newline scan: element = one 16-byte aligned chunk of the text
+// ------------------------------------------------------------------------------------------
+struct TextView {
+    const uint8_t* aligned;  // text pointer rounded down to 16 bytes
+    uint32_t delta;          // text - aligned
+    uint64_t len;
+};
+
+__device__ __forceinline__ uint32_t newline_mask16(const TextView& tv, uint64_t chunk) {
+    const uint4 v = *reinterpret_cast<const uint4*>(tv.aligned + chunk * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mask = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au);                    // 0xff in every byte that is '\n'
+        uint32_t m4 = (((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu;  // movemask: one bit per byte
+        mask |= m4 << (4 * q);
+    }
+    // drop bytes outside [0, len)
+    const int64_t p0 = (int64_t)(chunk * 16) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
+    if (p0 < 0) mask &= 0xffffu << (uint32_t)(-p0);
+    const int64_t over = p0 + 16 - (int64_t)tv.len;
+    if (over > 0) mask &= over >= 16 ? 0u : (0xffffu >> (uint32_t)over);
+    return mask & 0xffffu;
+}
+
+struct NewlineIn {
+    TextView tv;
+    __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const { return __popc(newline_mask16(tv, chunk)); }
+};
+struct NewlineOut {
+    TextView tv;
+    uint64_t* line_start;  // line_start[0] = 0 is written by the caller
+    __device__ __forceinline__ void operator()(uint64_t chunk, uint64_t excl, uint64_t v) const {
+        if (!v) return;
+        uint32_t mask = newline_mask16(tv, chunk);
+        const int64_t p0 = (int64_t)(chunk * 16) - (int64_t)tv.delta;
+        uint64_t idx = excl + 1;
+        while (mask) {
+            int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            line_start[idx++] = (uint64_t)(p0 + j) + 1;
+        }
+    }
+};
+
+__global__ void finish_lines_kernel(const uint8_t* text, uint64_t len, const uint64_t* n_newlines, uint64_t* line_start,
+                                    uint64_t* out /* [0] = n_lines */) {
+    uint64_t n = *n_newlines;
+    line_start[0] = 0;
+    if (len > 0 && text[len - 1] != '\n') {  // final line without terminator is still a record
+        line_start[n + 1] = len + 1;
+        n += 1;
+    }
+    out[0] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// line filters
+// ------------------------------------------------------------------------------------------
+struct Lines {
+    const uint8_t* text;
+    const uint64_t* start;  // n_lines + 1
+    uint64_t n_lines;
+    uint32_t gap;  // 1: lines separated by '\n' (FASTQ text); 0: back-to-back reads (rfx_push_reads)
+    __device__ __forceinline__ uint64_t len(uint64_t i) const {
+        uint64_t s = start[i], e = start[i + 1] - gap;
+        uint64_t l = e - s;
+        if (gap && l > 0 && text[e - 1] == '\r') l--;
+        return l;
+    }
+};
+
+// DSFastqFilterWithQual as a scan of state-transition functions.  State = lineMark in {0..4},
+// a function is 5 x 3 bits.  '@' line: 0->1 1->1 2->3 3->4 4->1 ; other line: 0->0 1->2 2->3 3->4 4->4
+// (branch order of ReflexivDSMain.java:4051-4071: lineMark 2 and 3 consume any line blindly).
+constexpr uint32_t FN_AT = 1u | (1u << 3) | (3u << 6) | (4u << 9) | (1u << 12);
+constexpr uint32_t FN_OTHER = 0u | (2u << 3) | (3u << 6) | (4u << 9) | (4u << 12);
+constexpr uint32_t FN_IDENT = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
+
+struct OpCompose {  // (f then g)
+    __device__ __forceinline__ uint32_t operator()(uint32_t f, uint32_t g) const {
+        uint32_t r = 0;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            uint32_t fs = (f >> (3 * s)) & 7u;
+            r |= ((g >> (3 * fs)) & 7u) << (3 * s);
+        }
+        return r;
+    }
+};
+
+struct LineFnIn {
+    Lines L;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
+        return (L.len(i) > 0 && L.text[L.start[i]] == '@') ? FN_AT : FN_OTHER;
+    }
+};
+struct LineFnOut {
+    Lines L;
+    uint8_t* seq_flag;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t excl, uint32_t fn) const {
+        const uint32_t state_before = excl & 7u;  // prefix function applied to lineMark = 0
+        // the sequence line is the one that moves lineMark 1 -> 2; the unit is emitted only when the
+        // two following lines exist (lineMark 3 -> 4)
+        seq_flag[i] = (state_before == 1u && fn == FN_OTHER && i + 2 < L.n_lines) ? 1 : 0;
+    }
+};
+
+__device__ __forceinline__ bool is_atcgn(uint8_t a) { return a == 'A' || a == 'T' || a == 'C' || a == 'G' || a == 'N'; }
+
+__global__ void flag_lines_kernel(Lines L, int mode, uint8_t* seq_flag) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint8_t f = 1;
+        if (mode == RFX_FASTQ_COUNTER) {  // ReflexivDataFrameCounter.java:247-266
+            const uint64_t l = L.len(i);
+            const uint8_t* s = L.text + L.start[i];
+            f = (l > 20 && s[0] != '@' && s[0] != '+' && is_atcgn(s[0]) && is_atcgn(s[4]) && is_atcgn(s[9]) &&
+                 is_atcgn(s[14]) && is_atcgn(s[19]))
+                    ? 1 : 0;
+        }
+        seq_flag[i] = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// read table: a = reads, b = packed words, c = bases kept, d = k-mer instances
+// ------------------------------------------------------------------------------------------
+struct U64x4 {
+    uint64_t a, b, c, d;
+};
+__device__ __forceinline__ U64x4 shfl_up_any(U64x4 v, int s) {
+    U64x4 r;
+    r.a = __shfl_up_sync(0xffffffffu, v.a, s); r.b = __shfl_up_sync(0xffffffffu, v.b, s);
+    r.c = __shfl_up_sync(0xffffffffu, v.c, s); r.d = __shfl_up_sync(0xffffffffu, v.d, s);
+    return r;
+}
+__device__ __forceinline__ U64x4 shfl_idx_any(U64x4 v, int l) {
+    U64x4 r;
+    r.a = __shfl_sync(0xffffffffu, v.a, l); r.b = __shfl_sync(0xffffffffu, v.b, l);
+    r.c = __shfl_sync(0xffffffffu, v.c, l); r.d = __shfl_sync(0xffffffffu, v.d, l);
+    return r;
+}
+struct OpAddU64x4 {
+    __device__ __forceinline__ U64x4 operator()(U64x4 x, U64x4 y) const { return U64x4{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
+};
+
+struct ReadIn {
+    Lines L;
+    const uint8_t* seq_flag;  // nullptr: every line is a read
+    int k, fc, ec;
+    __device__ __forceinline__ U64x4 operator()(uint64_t i) const {
+        if (seq_flag && !seq_flag[i]) return U64x4{0, 0, 0, 0};
+        const uint32_t e = effective_read_len((int64_t)L.len(i), k, fc, ec);
+        return U64x4{1, (uint64_t)((e + 31u) >> 5), e, e ? (uint64_t)(e - (uint32_t)k + 1u) : 0u};
+    }
+};
+struct ReadOut {
+    Lines L;
+    uint64_t read_base, word_base;
+    int fc;
+    uint64_t* rd_src;
+    uint32_t* rd_len;
+    uint64_t* rd_woff;
+    __device__ __forceinline__ void operator()(uint64_t i, U64x4 excl, U64x4 v) const {
+        if (!v.a) return;
+        const uint64_t r = excl.a;
+        rd_src[r] = L.start[i] + (uint64_t)fc;
+        rd_len[read_base + r] = (uint32_t)v.c;
+        rd_woff[read_base + r] = word_base + excl.b;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// warp-cooperative 2-bit encoder: a lane turns 4 ASCII bases into one byte with SIMD-in-register
+// compares, 8 lanes assemble a 64-bit word with xor shuffles, a warp writes 4 words per step.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) encode_reads_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ rd_src,
+                                                            const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff,
+                                                            uint64_t n_new, uint64_t read_base, uint64_t* __restrict__ packed) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp0; r < n_new; r += n_warps) {
+        const uint32_t elen = rd_len[read_base + r];
+        if (!elen) continue;
+        const uint64_t src = rd_src[r];
+        uint64_t* dst = packed + rd_woff[read_base + r];
+        const uint32_t n_words = (elen + 31u) >> 5;
+        for (uint32_t wbase = 0; wbase < n_words; wbase += 4) {
+            const uint32_t b0 = wbase * 32u + 4u * (uint32_t)lane;
+            uint32_t cb = 0;
+            if (b0 < elen) {
+                const uint32_t nvalid = min(4u, elen - b0);
+                const uintptr_t a = (uintptr_t)(text + src + b0);
+                const uint32_t* p32 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                const uint32_t mis = (uint32_t)(a & 3);
+                const uint32_t lo = p32[0];
+                const uint32_t hi = (mis + nvalid > 4u) ? p32[1] : 0u;
+                const uint32_t w = __funnelshift_r(lo, hi, mis * 8u);  // bytes a..a+3, first base in the low byte
+                const uint32_t mA = __vcmpeq4(w, 0x41414141u), mC = __vcmpeq4(w, 0x43434343u), mG = __vcmpeq4(w, 0x47474747u);
+                const uint32_t codes = (~(mA | mC) & 0x02020202u) | (~(mA | mG) & 0x01010101u);
+                cb = (codes * 0x40100401u) >> 24;            // first base -> bits 7..6
+                cb &= (0xff00u >> (2u * nvalid)) & 0xffu;    // clear the bases past the end of the read
+            }
+            uint64_t word = (uint64_t)cb << (56 - 8 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            const uint32_t wi = wbase + (uint32_t)(lane >> 3);
+            if ((lane & 7) == 0 && wi < n_words) dst[wi] = word;
+        }
+    }
+}
+
+__global__ void offsets_to_u64_kernel(const uint64_t* in, uint64_t n, uint64_t* out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+static unsigned grid_for(uint64_t n, int block, unsigned cap = 148 * 16) {
+    uint64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    return (unsigned)(g > cap ? cap : g);
+}
+
+// Builds the read table for `n_lines` lines and appends the packed reads to the context.
+static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* seq_flag) {
+    cudaStream_t st = c->stream;
+    ScanPlan<U64x4> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<U64x4>::workspace_elems(L.n_lines) * sizeof(U64x4)));
+    plan.bind(L.n_lines, c->scan_ws.as<U64x4>());
+    ReadIn in{L, seq_flag, c->k, c->prm.front_clip, c->prm.end_clip};
+    scan_prepare(plan, in, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
+    c->launches += 2 * plan.levels;
+    U64x4 tot;
+    RFX_CUDA(c, cudaMemcpyAsync(&tot, plan.total, sizeof(tot), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    const uint64_t n_new = tot.a, w_new = tot.b;
+    if (n_new == 0) return RFX_OK;
+    DevBuf rd_src;
+    RFX_TRY(devbuf_reserve(c, rd_src, n_new * sizeof(uint64_t)));
+    int rc = RFX_OK;
+    do {
+        if ((rc = devbuf_reserve(c, c->rd_len, (c->n_reads + n_new) * sizeof(uint32_t), true)) != RFX_OK) break;
+        if ((rc = devbuf_reserve(c, c->rd_woff, (c->n_reads + n_new) * sizeof(uint64_t), true)) != RFX_OK) break;
+        if ((rc = devbuf_reserve(c, c->packed, (c->n_words + w_new + 8) * sizeof(uint64_t), true)) != RFX_OK) break;
+        ReadOut out{L, c->n_reads, c->n_words, c->prm.front_clip, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
+        scan_apply(plan, in, out, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
+        encode_reads_kernel<<<grid_for(n_new * 32, 256, 148 * 8), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
+                                                                                c->rd_woff.as<uint64_t>(), n_new, c->n_reads,
+                                                                                c->packed.as<uint64_t>());
+        // padding words after the last read: packed_window() may look one word ahead
+        cudaMemsetAsync(c->packed.as<uint64_t>() + c->n_words + w_new, 0, 8 * sizeof(uint64_t), st);
+        c->launches += 2;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "encode failed: %s", cudaGetErrorString(e)); break; }
+        c->n_reads += n_new;
+        c->n_words += w_new;
+        c->n_bases += tot.c;
+        c->n_instances += tot.d;
+    } while (0);
+    devbuf_free(rd_src);
+    return rc;
+}
+
+int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
+    if (len == 0) return RFX_OK;
+    cudaStream_t st = c->stream;
+    stage_begin(c);
+    TextView tv;
+    tv.delta = (uint32_t)((uintptr_t)d_text & 15);
+    tv.aligned = d_text - tv.delta;
+    tv.len = len;
+    const uint64_t n_chunks = (len + tv.delta + 15) / 16;
+
+    // 1. newline scan
+    ScanPlan<uint64_t> nl;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n_chunks) * sizeof(uint64_t)));
+    nl.bind(n_chunks, c->scan_ws.as<uint64_t>());
+    scan_prepare(nl, NewlineIn{tv}, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 2 * nl.levels;
+    uint64_t n_newlines = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&n_newlines, nl.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    RFX_TRY(devbuf_reserve(c, c->line_start, (n_newlines + 2) * sizeof(uint64_t)));
+    uint64_t* ls = c->line_start.as<uint64_t>();
+    scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, ls}, OpAddU64{}, (uint64_t)0, st);
+    finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, c->dstat.as<uint64_t>() + DS_NSLOTS - 1);
+    c->launches += 2;
+    uint64_t n_lines = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&n_lines, c->dstat.as<uint64_t>() + DS_NSLOTS - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    if (n_lines == 0) { c->ms[0] += stage_end(c); return RFX_OK; }
+
+    // 2. which lines are reads
+    Lines L{d_text, ls, n_lines, 1u};
+    RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines));
+    const uint8_t* flags = c->seq_flag.as<uint8_t>();
+    if (c->prm.fastq_mode == RFX_FASTQ_RUN) {
+        ScanPlan<uint32_t> fs;
+        RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
+        fs.bind(n_lines, c->scan_ws.as<uint32_t>());
+        scan_prepare(fs, LineFnIn{L}, OpCompose{}, FN_IDENT, st);
+        scan_apply(fs, LineFnIn{L}, LineFnOut{L, c->seq_flag.as<uint8_t>()}, OpCompose{}, FN_IDENT, st);
+        c->launches += 2 * fs.levels + 1;
+    } else if (c->prm.fastq_mode == RFX_FASTQ_COUNTER) {
+        flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint8_t>());
+        c->launches += 1;
+    } else {
+        flags = nullptr;
+    }
+    // 3. read table + encode
+    int rc = append_reads(c, d_text, L, flags);
+    c->ms[0] += stage_end(c);
+    return rc;
+}
+
+int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads) {
+    if (n_reads == 0) return RFX_OK;
+    cudaStream_t st = c->stream;
+    const uint64_t total = h_offsets[n_reads];
+    RFX_TRY(devbuf_reserve(c, c->text, total + 64));
+    RFX_TRY(devbuf_reserve(c, c->line_start, (n_reads + 1) * sizeof(uint64_t)));
+    RFX_CUDA(c, cudaMemcpyAsync(c->text.p, h_bases, total, cudaMemcpyHostToDevice, st));
+    RFX_CUDA(c, cudaMemsetAsync(c->text.as<uint8_t>() + total, 0, 64, st));
+    RFX_CUDA(c, cudaMemcpyAsync(c->line_start.p, h_offsets, (n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    stage_begin(c);
+    Lines L{c->text.as<uint8_t>(), c->line_start.as<uint64_t>(), n_reads, 0u};
+    int rc = append_reads(c, c->text.as<uint8_t>(), L, nullptr);
+    c->ms[0] += stage_end(c);
+    return rc;
+}
+
+}  // namespace rfx

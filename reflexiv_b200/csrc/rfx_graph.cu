@@ -1,0 +1,454 @@
+// rfx_graph.cu -- K5 (both orientations, fork filters, neighbour links), K6 (list ranking of the unitig
+// chains), K7 (contig gather).
+//
+// Replaces, in ReflexivDSMain.java (paths relative to .../reflexiv/pipeline/):
+//   DSKmerReverseComplementLong :3849-3869        both orientations of every kept k-mer
+//   DSForwardSubKmerExtraction :3625-3644 + sort + DSFilterForkSubKmer(WithErrorCorrection) :3375-3483
+//   DSReflectedSubKmerExtractionFromForward :3661-3685 + sort + DSFilterForkReflectedSubKmer(...) :3489-3616
+//   DSkmerRandomReflection :3688-3792, DSExtendReflexivKmer :3011-3362, ...ToArrayFirstTime :2559-3004,
+//   ...ToArrayLoop :1746-2551 and the driver loop :261-326   (>= 18 global sorts in the reference)
+//   DSBinaryReflexivKmerArrayToString :855-900, DSKmerToContig :743-771
+//
+// Data layout in HBM: the filtered table (keys[], counts[]) is the only copy of the k-mers.  An
+// oriented k-mer is an id  oid = 2*row + strand  (strand 1 = reverse complement of keys[row]); every
+// per-node array (flags, links, ranks) is indexed by oid.  A 32-bit open-addressing index (ht[]) maps a
+// canonical k-mer to its row; neighbours are found by probing the 4 possible extensions.
+//
+// After the two fork filters every (k-1)-mer has at most one surviving out-edge and one in-edge, so
+// the reference's sort-and-merge iteration converges to the maximal paths of that graph; pointer
+// jumping computes (head, rank) for every node in O(log n) rounds instead.
+#include "rfx_internal.h"
+#include "rfx_scan.cuh"
+
+namespace rfx {
+
+template <class KT> struct Graph {
+    const KT* keys;
+    const uint32_t* counts;
+    uint64_t n_rows;
+    uint32_t* ht;
+    uint64_t ht_mask;
+    int k;
+
+    __device__ __forceinline__ uint32_t lookup(KT canon) const {
+        uint64_t slot = key_hash(canon) & ht_mask;
+        while (true) {
+            const uint32_t v = ht[slot];
+            if (v == NONE32) return NONE32;
+            if (keys[v] == canon) return v;
+            slot = (slot + 1) & ht_mask;
+        }
+    }
+    __device__ __forceinline__ KT oriented(uint32_t oid) const {
+        const KT key = keys[oid >> 1];
+        return (oid & 1u) ? revcomp(key, k) : key;
+    }
+    // oriented id of the oriented k-mer Z, NONE32 if its canonical form is not in the table
+    __device__ __forceinline__ uint32_t find(KT Z, uint32_t* cnt) const {
+        const KT zc = revcomp(Z, k);
+        const bool fwd = !(zc < Z);
+        const uint32_t r = lookup(fwd ? Z : zc);
+        if (r == NONE32) return NONE32;
+        *cnt = counts[r];
+        return 2u * r + (fwd ? 0u : 1u);
+    }
+};
+
+template <class KT> __global__ void ht_build_kernel(Graph<KT> G) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G.n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t slot = key_hash(G.keys[r]) & G.ht_mask;
+        while (atomicCAS(&G.ht[slot], NONE32, (uint32_t)r) != NONE32) slot = (slot + 1) & G.ht_mask;
+    }
+}
+
+// A7.  alive bit0 = survives the right fork filter.
+template <class KT>
+__global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ alive, int32_t* __restrict__ rflag) {
+    const uint64_t n = 2 * G.n_rows;
+    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(oid >> 1);
+        const KT key = G.keys[row];
+        const KT rc = revcomp(key, G.k);
+        if ((oid & 1u) && rc == key) { alive[oid] = 0; rflag[oid] = 0; continue; }  // palindrome: one node, not two
+        const KT X = (oid & 1u) ? rc : key;
+        const KT prefix = X >> 2;
+        const uint32_t myb = (uint32_t)X & 3u;
+        uint32_t cnt[4];
+        bool dup[4];
+#pragma unroll
+        for (uint32_t b = 0; b < 4; b++) {
+            if (b == myb) { cnt[b] = G.counts[row]; dup[b] = (rc == key); }
+            else {
+                const KT Z = (prefix << 2) | (KT)b;
+                const KT zc = revcomp(Z, G.k);
+                const uint32_t r = G.lookup(zc < Z ? zc : Z);
+                cnt[b] = r == NONE32 ? 0u : G.counts[r];
+                dup[b] = (Z == zc);
+            }
+        }
+        const ForkResult res = right_fork(cnt, dup, E, G.k - 1);
+        alive[oid] = (res.winner == (int)myb) ? 1 : 0;
+        rflag[oid] = res.flag;
+    }
+}
+
+// A8.  alive bit1 = survives both filters.
+template <class KT>
+__global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* __restrict__ lflag) {
+    const uint64_t n = 2 * G.n_rows;
+    const int top = 2 * (G.k - 1);
+    const KT sufmask = mask_bases<KT>(G.k - 1);
+    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+        lflag[oid] = 0;
+        if (!(alive[oid] & 1)) continue;
+        const KT X = G.oriented((uint32_t)oid);
+        const KT suffix = X & sufmask;
+        const uint32_t mya = (uint32_t)(X >> top) & 3u;
+        uint32_t cnt[4];
+#pragma unroll
+        for (uint32_t a = 0; a < 4; a++) {
+            if (a == mya) cnt[a] = G.counts[oid >> 1];
+            else {
+                uint32_t cz = 0;
+                const uint32_t oz = G.find(((KT)a << top) | suffix, &cz);
+                cnt[a] = (oz != NONE32 && (alive[oz] & 1)) ? cz : 0u;
+            }
+        }
+        const ForkResult res = left_fork(cnt, E, G.k - 1);
+        if (res.winner == (int)mya) { alive[oid] = 3; lflag[oid] = res.flag; }
+    }
+}
+
+// Neighbour links.  succ/pred are preset to NONE32.
+template <class KT>
+__global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag,
+                            uint32_t* __restrict__ succ, uint32_t* pred, uint32_t* __restrict__ open_next, unsigned long long* dstat) {
+    const uint64_t n = 2 * G.n_rows;
+    const KT sufmask = mask_bases<KT>(G.k - 1);
+    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[oid] & 2)) continue;
+        const KT X = G.oriented((uint32_t)oid);
+        const KT suffix = X & sufmask;
+        uint32_t next = NONE32;
+        int n_cand = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < 4; b++) {
+            uint32_t cz;
+            const uint32_t oy = G.find((suffix << 2) | (KT)b, &cz);
+            if (oy != NONE32 && (alive[oy] & 2)) { next = oy; n_cand++; }
+        }
+        if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
+        if (next == NONE32) continue;
+        if (junction_joins(rflag[oid], lflag[next])) {
+            if (next == (uint32_t)oid) { atomicAdd(&dstat[DS_CYCLES], 1ull); continue; }  // 1-cycle: a record never merges with itself
+            succ[oid] = next;
+            if (atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+        } else {
+            open_next[oid] = next;
+            atomicAdd(&dstat[DS_BUDGET], 1ull);
+        }
+    }
+}
+
+// ---- K6: pointer jumping towards the head ------------------------------------------------------
+__global__ void rank_init_kernel(uint64_t n, const uint32_t* __restrict__ pred, uint32_t* __restrict__ anc, uint32_t* __restrict__ dist) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = pred[x];
+        anc[x] = p == NONE32 ? (uint32_t)x : p;
+        dist[x] = p == NONE32 ? 0u : 1u;
+    }
+}
+__global__ void rank_step_kernel(uint64_t n, const uint32_t* __restrict__ anc_in, const uint32_t* __restrict__ dist_in,
+                                 uint32_t* __restrict__ anc_out, uint32_t* __restrict__ dist_out, unsigned long long* dstat) {
+    bool changed = false;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = anc_in[x];
+        const uint32_t aa = anc_in[a];
+        dist_out[x] = dist_in[x] + (a == (uint32_t)x ? 0u : dist_in[a]);
+        anc_out[x] = aa;
+        changed |= (aa != a);
+    }
+    if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_CHANGED], 1ull);
+}
+// nodes whose final ancestor is not a true head (pred == NONE) sit on a cycle
+__global__ void cycle_mark_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint32_t* __restrict__ anc,
+                                  uint32_t* __restrict__ lab, uint32_t* __restrict__ ptr, unsigned long long* dstat) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const bool cyc = (alive[x] & 2) && pred[x] != NONE32 && pred[anc[x]] != NONE32;
+        lab[x] = cyc ? (uint32_t)x : NONE32;
+        ptr[x] = cyc ? pred[x] : NONE32;
+        if (cyc) atomicAdd(&dstat[DS_CYCLE_NODES], 1ull);
+    }
+}
+template <class KT>
+__global__ void cycle_min_step_kernel(Graph<KT> G, const uint32_t* __restrict__ lab_in, const uint32_t* __restrict__ ptr_in,
+                                      uint32_t* __restrict__ lab_out, uint32_t* __restrict__ ptr_out) {
+    const uint64_t n = 2 * G.n_rows;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = ptr_in[x];
+        if (p == NONE32) { lab_out[x] = NONE32; ptr_out[x] = NONE32; continue; }
+        const uint32_t la = lab_in[x], lb = lab_in[p];
+        lab_out[x] = (la == lb || G.oriented(la) < G.oriented(lb)) ? la : lb;
+        ptr_out[x] = ptr_in[p];
+    }
+}
+// CANONICAL ORDER: a cycle is opened in front of its smallest oriented k-mer (oracle: assemble_canonical)
+__global__ void cycle_cut_kernel(uint64_t n, const uint32_t* __restrict__ lab, uint32_t* succ, uint32_t* pred, unsigned long long* dstat) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (lab[x] == (uint32_t)x) {
+            const uint32_t p = pred[x];
+            succ[p] = NONE32;
+            pred[x] = NONE32;
+            atomicAdd(&dstat[DS_CYCLES], 1ull);
+        }
+    }
+}
+
+__global__ void tails_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ succ, const uint32_t* __restrict__ anc,
+                             const uint32_t* __restrict__ dist, uint32_t* __restrict__ chain_len, uint32_t* __restrict__ tail_of) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        if ((alive[x] & 2) && succ[x] == NONE32) {
+            const uint32_t h = anc[x];
+            chain_len[h] = dist[x] + 1u;
+            tail_of[h] = (uint32_t)x;
+        }
+    }
+}
+
+__global__ void budget_admissible_kernel(uint64_t n, const uint32_t* __restrict__ open_next, const int32_t* __restrict__ lflag,
+                                         const int32_t* __restrict__ rflag, const uint32_t* __restrict__ dist, const uint32_t* __restrict__ chain_len,
+                                         unsigned long long* dstat) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = open_next[x];
+        if (y == NONE32) continue;
+        const int64_t r_ext = (int64_t)dist[x] + 1, f_ext = (int64_t)chain_len[y];
+        if ((lflag[y] >= 0 && lflag[y] - r_ext >= 0) || (rflag[x] >= 0 && rflag[x] - f_ext >= 0)) atomicAdd(&dstat[DS_BUDGET_ADM], 1ull);
+    }
+}
+
+// ---- K7: contigs ----------------------------------------------------------------------------------
+struct ContigIn {
+    const uint8_t* alive;
+    const uint32_t* pred;
+    const uint32_t* chain_len;
+    const uint32_t* tail_of;
+    const int32_t* lflag;
+    const int32_t* rflag;
+    int k, min_contig;
+    __device__ __forceinline__ U64x3 operator()(uint64_t x) const {
+        if (!(alive[x] & 2)) return U64x3{0, 0, 0};
+        if (pred[x] != NONE32) return U64x3{0, 0, 1};
+        const uint64_t len = (uint64_t)chain_len[x] + (uint64_t)k - 1;
+        // DSKmerToContig, ReflexivDSMain.java:749-754
+        const bool keep = !(lflag[x] <= -10000000 && rflag[tail_of[x]] <= -10000000) && len >= (uint64_t)min_contig;
+        return keep ? U64x3{1, len, 1} : U64x3{0, 0, 1};
+    }
+};
+struct ContigOut {
+    const uint32_t* tail_of;
+    const int32_t* lflag;
+    const int32_t* rflag;
+    uint32_t* ctg_idx;
+    uint64_t* ctg_off;
+    int32_t* ctg_left;
+    int32_t* ctg_right;
+    __device__ __forceinline__ void operator()(uint64_t x, U64x3 excl, U64x3 v) const {
+        ctg_idx[x] = v.a ? (uint32_t)excl.a : NONE32;
+        if (v.a) {
+            ctg_off[excl.a] = excl.b;
+            ctg_left[excl.a] = lflag[x];
+            ctg_right[excl.a] = rflag[tail_of[x]];
+        }
+    }
+};
+
+template <class KT>
+__global__ void gather_contigs_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ anc, const uint32_t* __restrict__ dist,
+                                      const uint32_t* __restrict__ ctg_idx, const uint64_t* __restrict__ ctg_off, char* __restrict__ out) {
+    const uint64_t n = 2 * G.n_rows;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2)) continue;
+        const uint32_t h = anc[x];
+        const uint32_t ci = ctg_idx[h];
+        if (ci == NONE32) continue;
+        const KT X = G.oriented((uint32_t)x);
+        char* dst = out + ctg_off[ci];
+        dst[(uint64_t)(G.k - 1) + dist[x]] = "ACGT"[(uint32_t)X & 3u];
+        if (h == (uint32_t)x)
+            for (int j = 0; j < G.k - 1; j++) dst[j] = "ACGT"[(uint32_t)(X >> (2 * (G.k - 1 - j))) & 3u];
+    }
+}
+
+__global__ void set_u64_kernel(uint64_t* p, const U64x3* tot) { *p = tot->b; }
+
+static unsigned grid_n(uint64_t n) {
+    uint64_t g = (n + 255) / 256;
+    if (g < 1) g = 1;
+    return (unsigned)(g > 148u * 16u ? 148u * 16u : g);
+}
+
+template <class KT> static int graph_impl(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const uint64_t n_rows = c->n_rows, n = 2 * n_rows;
+    unsigned long long* dstat = c->dstat.as<unsigned long long>();
+    uint64_t h[DS_NSLOTS];
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+    c->n_oriented = c->n_budget = c->n_budget_adm = c->n_cycles = c->n_contigs = c->n_contig_bases = 0;
+    if (n_rows == 0) {
+        RFX_TRY(devbuf_reserve(c, c->ctg_off, sizeof(uint64_t)));
+        RFX_CUDA(c, cudaMemsetAsync(c->ctg_off.p, 0, sizeof(uint64_t), st));
+        c->have_contigs = true;
+        return RFX_OK;
+    }
+    if (n >= 0xffffffffull) return ctx_fail(c, RFX_E_CAPACITY, "more than 2^31 rows: oriented ids do not fit 32 bits");
+
+    // ---- K5 ----
+    stage_begin(c);
+    uint64_t ht_cap = 1024;
+    while (ht_cap < 2 * n_rows) ht_cap <<= 1;
+    c->ht_cap = ht_cap;
+    RFX_TRY(devbuf_reserve(c, c->ht, ht_cap * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->rflag, n * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->lflag, n * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->alive, n));
+    RFX_TRY(devbuf_reserve(c, c->succ, n * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->pred, n * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->tail_of, n * sizeof(uint32_t)));  // doubles as open_next until the tails pass
+    for (int i = 0; i < 2; i++) {
+        RFX_TRY(devbuf_reserve(c, c->anc[i], n * sizeof(uint32_t)));
+        RFX_TRY(devbuf_reserve(c, c->dist[i], n * sizeof(uint32_t)));
+    }
+    RFX_TRY(devbuf_reserve(c, c->chain_len, n * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->ctg_idx, n * sizeof(uint32_t)));
+    DevBuf open_next;  // separate from tail_of: both are live in the admissibility pass
+    RFX_TRY(devbuf_reserve(c, open_next, n * sizeof(uint32_t)));
+    int rc = RFX_OK;
+    do {
+        Graph<KT> G{c->keys.as<KT>(), c->counts.as<uint32_t>(), n_rows, c->ht.as<uint32_t>(), ht_cap - 1, c->k};
+        cudaMemsetAsync(c->ht.p, 0xff, ht_cap * sizeof(uint32_t), st);
+        cudaMemsetAsync(c->succ.p, 0xff, n * sizeof(uint32_t), st);
+        cudaMemsetAsync(c->pred.p, 0xff, n * sizeof(uint32_t), st);
+        cudaMemsetAsync(open_next.p, 0xff, n * sizeof(uint32_t), st);
+        cudaMemsetAsync(c->chain_len.p, 0, n * sizeof(uint32_t), st);
+        cudaMemsetAsync(c->tail_of.p, 0xff, n * sizeof(uint32_t), st);
+        const int E = c->prm.min_error_coverage;
+        uint8_t* alive = c->alive.as<uint8_t>();
+        int32_t* lflag = c->lflag.as<int32_t>();
+        int32_t* rflag = c->rflag.as<int32_t>();
+        uint32_t* succ = c->succ.as<uint32_t>();
+        uint32_t* pred = c->pred.as<uint32_t>();
+        ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G);
+        right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, rflag);
+        left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, lflag);
+        link_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, open_next.as<uint32_t>(), dstat);
+        c->launches += 4;
+        cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "graph kernels failed: %s", cudaGetErrorString(e)); break; }
+        c->ms[3] += stage_end(c);
+        if (h[DS_GRAPH_ERR]) { rc = ctx_fail(c, RFX_E_GRAPH, "fork filters left a (k-1)-mer with degree > 1 (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]); break; }
+        c->n_budget = h[DS_BUDGET];
+
+        // ---- K6 ----
+        stage_begin(c);
+        int limit = 2;
+        while ((1ull << limit) < n + 1) limit++;
+        limit += 2;
+        int cur = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            cur = 0;
+            rank_init_kernel<<<grid_n(n), 256, 0, st>>>(n, pred, c->anc[0].as<uint32_t>(), c->dist[0].as<uint32_t>());
+            c->launches++;
+            for (int round = 0; round < limit; round++) {
+                cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st);
+                rank_step_kernel<<<grid_n(n), 256, 0, st>>>(n, c->anc[cur].as<uint32_t>(), c->dist[cur].as<uint32_t>(), c->anc[cur ^ 1].as<uint32_t>(),
+                                                            c->dist[cur ^ 1].as<uint32_t>(), dstat);
+                c->launches++;
+                cur ^= 1;
+                uint64_t changed = 0;
+                cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+                e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) break;
+                if (!changed) break;
+            }
+            if (e != cudaSuccess) break;
+            if (attempt == 1) break;
+            // cycles: every junction of a closed path joins, no node is a head
+            RFX_TRY(devbuf_reserve(c, c->cmin[0], 2 * n * sizeof(uint32_t)));
+            RFX_TRY(devbuf_reserve(c, c->cmin[1], 2 * n * sizeof(uint32_t)));
+            uint32_t* lab[2] = {c->cmin[0].as<uint32_t>(), c->cmin[1].as<uint32_t>()};
+            uint32_t* ptr[2] = {lab[0] + n, lab[1] + n};
+            cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st);
+            cycle_mark_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, c->anc[cur].as<uint32_t>(), lab[0], ptr[0], dstat);
+            c->launches++;
+            uint64_t cyc_nodes = 0;
+            cudaMemcpyAsync(&cyc_nodes, dstat + DS_CYCLE_NODES, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess || cyc_nodes == 0) break;
+            int b = 0;
+            for (int round = 0; round < limit; round++) {
+                cycle_min_step_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, lab[b], ptr[b], lab[b ^ 1], ptr[b ^ 1]);
+                c->launches++;
+                b ^= 1;
+            }
+            cycle_cut_kernel<<<grid_n(n), 256, 0, st>>>(n, lab[b], succ, pred, dstat);
+            c->launches++;
+        }
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "list ranking failed: %s", cudaGetErrorString(e)); break; }
+        uint32_t* anc = c->anc[cur].as<uint32_t>();
+        uint32_t* dist = c->dist[cur].as<uint32_t>();
+        tails_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, succ, anc, dist, c->chain_len.as<uint32_t>(), c->tail_of.as<uint32_t>());
+        budget_admissible_kernel<<<grid_n(n), 256, 0, st>>>(n, open_next.as<uint32_t>(), lflag, rflag, dist, c->chain_len.as<uint32_t>(), dstat);
+        c->launches += 2;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "chain kernels failed: %s", cudaGetErrorString(e)); break; }
+        c->ms[4] += stage_end(c);
+
+        // ---- K7 ----
+        stage_begin(c);
+        ScanPlan<U64x3> plan;
+        if ((rc = devbuf_reserve(c, c->scan_ws, ScanPlan<U64x3>::workspace_elems(n) * sizeof(U64x3))) != RFX_OK) break;
+        plan.bind(n, c->scan_ws.as<U64x3>());
+        ContigIn in{alive, pred, c->chain_len.as<uint32_t>(), c->tail_of.as<uint32_t>(), lflag, rflag, c->k, c->prm.min_contig};
+        scan_prepare(plan, in, OpAddU64x3{}, U64x3{0, 0, 0}, st);
+        c->launches += 2 * plan.levels;
+        U64x3 tot;
+        cudaMemcpyAsync(&tot, plan.total, sizeof(tot), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "contig scan failed: %s", cudaGetErrorString(e)); break; }
+        if ((rc = devbuf_reserve(c, c->ctg_off, (tot.a + 1) * sizeof(uint64_t))) != RFX_OK) break;
+        if ((rc = devbuf_reserve(c, c->ctg_left, (tot.a + 1) * sizeof(int32_t))) != RFX_OK) break;
+        if ((rc = devbuf_reserve(c, c->ctg_right, (tot.a + 1) * sizeof(int32_t))) != RFX_OK) break;
+        if ((rc = devbuf_reserve(c, c->ctg_bases, tot.b + 16)) != RFX_OK) break;
+        ContigOut out{c->tail_of.as<uint32_t>(), lflag, rflag, c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_left.as<int32_t>(),
+                      c->ctg_right.as<int32_t>()};
+        scan_apply(plan, in, out, OpAddU64x3{}, U64x3{0, 0, 0}, st);
+        set_u64_kernel<<<1, 1, 0, st>>>(c->ctg_off.as<uint64_t>() + tot.a, plan.total);
+        gather_contigs_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, anc, dist, c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>());
+        c->launches += 3;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "contig gather failed: %s", cudaGetErrorString(e)); break; }
+        c->ms[5] += stage_end(c);
+        c->n_contigs = tot.a;
+        c->n_contig_bases = tot.b;
+        c->n_oriented = tot.c;
+        c->n_budget_adm = h[DS_BUDGET_ADM];
+        c->n_cycles = h[DS_CYCLES];
+        c->have_contigs = true;
+    } while (0);
+    devbuf_free(open_next);
+    return rc;
+}
+
+int stage_graph(Ctx* c) {
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "rfx_assemble: no count table (call rfx_count or rfx_load_counts first)");
+    if (!c->prm.bubble)
+        return ctx_fail(c, RFX_E_UNSUPPORTED,
+                        "-bubble: with the fork filters off the reference feeds marker-less extensions into DSkmerRandomReflection "
+                        "(ReflexivDSMain.java:3634 vs 3716) and its output is undefined");
+    if (c->k < 2) return ctx_fail(c, RFX_E_INVALID, "assembly needs k >= 2");
+    return c->wide ? graph_impl<u128>(c) : graph_impl<uint64_t>(c);
+}
+
+}  // namespace rfx

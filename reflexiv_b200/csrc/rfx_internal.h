@@ -1,0 +1,146 @@
+// rfx_internal.h -- context layout and host-side helpers shared by the .cu files of libreflexiv_cuda.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/reflexiv_cuda.h"
+#include "rfx_core.h"
+
+namespace rfx {
+
+// growable device buffer; contents are NOT preserved on growth unless keep == true
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Ctx;
+int ctx_fail(Ctx* c, int code, const char* fmt, ...);
+int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep = false);
+void devbuf_free(DevBuf& b);
+
+#define RFX_CUDA(c, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return ctx_fail((c), RFX_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                            cudaGetErrorString(e_));                                               \
+    } while (0)
+#define RFX_TRY(expr)                 \
+    do {                              \
+        int rc_ = (expr);             \
+        if (rc_ != RFX_OK) return rc_; \
+    } while (0)
+
+struct StageTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+struct Ctx {
+    rfx_params prm;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // derived
+    int k = 31;
+    bool wide = false;  // k > 31: 128-bit keys
+    int recw = 2;       // 64-bit words per super-k-mer record
+    int m = 13;         // minimiser length
+    uint32_t max_nk = 26;
+
+    // ---- reads (packed 2-bit) ----
+    DevBuf text;        // staging for host FASTQ text
+    DevBuf line_start;  // u64[n_lines + 1]
+    DevBuf seq_flag;    // u8[n_lines]
+    DevBuf scan_ws;     // scan workspace
+    DevBuf rd_len;      // u32[n_reads]   effective length (0 = contributes nothing)
+    DevBuf rd_woff;     // u64[n_reads]   first word in `packed`
+    DevBuf packed;      // u64[n_words + pad]
+    uint64_t n_reads = 0, n_words = 0, n_bases = 0, n_instances = 0;
+
+    // ---- super-k-mer records ----
+    DevBuf bin_off;     // u64[n_bins + 1]
+    DevBuf bin_cursor;  // u64[n_bins]
+    DevBuf records;     // u64[n_records * recw]
+    uint32_t n_bins = 0;
+    int32_t n_shards = 1;
+    uint64_t n_records = 0;
+    bool have_records = false;
+    uint32_t forced_bins = 0;  // total bin count imposed by the caller (sharded runs), 0 = choose
+    // records received from other shards (rfx_begin_shard / rfx_load_records_device)
+    DevBuf rx_records;
+    uint64_t rx_bytes = 0;
+    int32_t shard_id = -1;
+
+    // ---- filtered count table ----
+    DevBuf keys;        // KT[table_cap]  right-aligned canonical k-mers
+    DevBuf counts;      // u32[table_cap]
+    DevBuf dstat;       // u64[16] device-side counters
+    uint64_t table_cap = 0, n_rows = 0, n_distinct = 0, n_bin_splits = 0;
+    bool have_counts = false;
+
+    // ---- de Bruijn graph over oriented k-mers (id = 2*row + strand) ----
+    DevBuf ht;          // u32[ht_cap] row index or 0xffffffff
+    uint64_t ht_cap = 0;
+    DevBuf rflag, lflag;  // i32[2*n_rows]
+    DevBuf alive;         // u8[2*n_rows]  bit0: survives right filter, bit1: survives both
+    DevBuf succ, pred;    // u32[2*n_rows]
+    DevBuf anc[2], dist[2];
+    DevBuf cmin[2];
+    DevBuf chain_len;     // u32[2*n_rows] at heads
+    DevBuf tail_of;       // u32[2*n_rows] at heads
+    DevBuf ctg_idx;       // u32[2*n_rows] at heads: contig index or NONE
+    DevBuf ctg_off;       // u64[n_contigs + 1]
+    DevBuf ctg_left, ctg_right;  // i32[n_contigs]
+    DevBuf ctg_bases;     // char[total]
+    uint64_t n_oriented = 0, n_budget = 0, n_budget_adm = 0, n_cycles = 0, n_contigs = 0, n_contig_bases = 0;
+    bool have_contigs = false;
+
+    float ms[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// device-side counter slots in Ctx::dstat
+enum {
+    DS_OUT_CURSOR = 0,
+    DS_DISTINCT = 1,
+    DS_INSTANCES = 2,
+    DS_OVERFLOW = 3,
+    DS_SPLITS = 4,
+    DS_BUDGET = 5,
+    DS_BUDGET_ADM = 6,
+    DS_GRAPH_ERR = 7,
+    DS_CHANGED = 8,
+    DS_CYCLE_NODES = 9,
+    DS_CYCLES = 10,
+    DS_ORIENTED = 11,
+    DS_NSLOTS = 16
+};
+
+static const uint32_t NONE32 = 0xffffffffu;
+
+// stage entry points (each in its own .cu)
+int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len);
+int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);
+int stage_partition(Ctx* c, int n_shards);
+int stage_rebin(Ctx* c);
+int stage_count(Ctx* c);
+int stage_graph(Ctx* c);
+
+inline void stage_begin(Ctx* c) { cudaEventRecord(c->ev0, c->stream); }
+inline float stage_end(Ctx* c) {
+    float ms = 0;
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    return ms;
+}
+
+}  // namespace rfx
+
+struct rfx_ctx : rfx::Ctx {};

@@ -1,0 +1,210 @@
+// rfx_partition.cu -- K2: rolling minimiser scan of the packed reads, super-k-mer records binned by
+// canonical minimiser.
+//
+// This is the device-side replacement of the map side of
+//   ReverseComplementKmerBinaryExtractionFromDataset + groupBy("value") hash shuffle
+//   (ReflexivDataFrameCounter.java:195-200, ReflexivDSMain.java:204-209):
+// instead of materialising every k-mer instance as an 8/16-byte key and shuffling it, consecutive
+// k-mers that share a minimiser bin travel together as one 16/32-byte record (about 1.5 B per k-mer
+// instance), and all instances of one canonical k-mer are guaranteed to land in one bin because the
+// bin is a function of the strand-symmetric minimiser of the k-mer.
+//
+// Two launches of one kernel: (1) histogram of records per bin, (2) scatter.  One thread walks one
+// read (rfx_core.h: bin_scan_read); the sliding-minimum ring lives in shared memory, interleaved by
+// lane so the 32 reads of a warp never bank-conflict.
+#include "rfx_internal.h"
+#include "rfx_scan.cuh"
+
+namespace rfx {
+
+constexpr int PART_THREADS = 128;
+
+// what a thread does with each run of k-mers that share a bin
+template <int RECW, bool SCATTER> struct EmitRecord {
+    const uint64_t* rd;
+    unsigned long long* bin_cursor;
+    uint64_t* records;
+    RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) const {
+#if defined(__CUDA_ARCH__)
+        const unsigned long long slot = atomicAdd(&bin_cursor[bin], 1ull);
+        if (SCATTER) {
+            uint64_t rec[RECW];
+            rec_build<RECW>(rd, first_kmer, n_k, rec);
+            uint64_t* dst = records + slot * RECW;
+#pragma unroll
+            for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(rec[i], rec[i + 1]);
+        }
+#else
+        (void)bin; (void)first_kmer; (void)n_k;
+#endif
+    }
+};
+
+template <int RECW, bool SCATTER>
+__global__ void __launch_bounds__(PART_THREADS)
+    partition_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff,
+                     uint64_t n_reads, BinParams P, unsigned long long* __restrict__ bin_cursor, uint64_t* __restrict__ records) {
+    extern __shared__ uint32_t ring_smem[];  // [2*w][PART_THREADS]
+    uint32_t* ring = ring_smem + threadIdx.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * PART_THREADS + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * PART_THREADS) {
+        const uint32_t len = rd_len[r];
+        if (len < (uint32_t)P.k) continue;
+        const uint64_t* rd = packed + rd_woff[r];
+        bin_scan_read(rd, len, P, ring, (uint32_t)PART_THREADS, EmitRecord<RECW, SCATTER>{rd, bin_cursor, records});
+    }
+}
+
+// bin ids are laid out shard-major: bin b belongs to shard b / bins_per_shard, so every shard's
+// records are one contiguous slice of the record array (what the all-to-all sends).
+struct BinCountIn {
+    const unsigned long long* cnt;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return cnt[i]; }
+};
+struct BinOffsetOut {
+    uint64_t* off;
+    unsigned long long* cursor;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t excl, uint64_t) const {
+        off[i] = excl;
+        cursor[i] = excl;
+    }
+};
+
+__global__ void set_last_offset_kernel(uint64_t* off, uint64_t n_bins, const uint64_t* total) { off[n_bins] = *total; }
+
+static uint32_t choose_bins(Ctx* c, int n_shards) {
+    if (c->forced_bins) return c->forced_bins;
+    uint64_t target = c->prm.bin_target_kmers > 0 ? (uint64_t)c->prm.bin_target_kmers : 16384;
+    uint64_t nb = (c->n_instances + target - 1) / target;
+    if (nb < 64) nb = 64;
+    if (nb > (1u << 24)) nb = 1u << 24;
+    // multiple of the shard count so every shard owns the same number of bins
+    nb = (nb + n_shards - 1) / n_shards * n_shards;
+    return (uint32_t)nb;
+}
+
+int stage_partition(Ctx* c, int n_shards) {
+    cudaStream_t st = c->stream;
+    if (n_shards < 1) return ctx_fail(c, RFX_E_INVALID, "n_shards must be >= 1");
+    stage_begin(c);
+    c->n_shards = n_shards;
+    c->n_bins = choose_bins(c, n_shards);
+    if (c->n_bins % (uint32_t)n_shards) return ctx_fail(c, RFX_E_INVALID, "n_bins_total %u is not a multiple of n_shards %d", c->n_bins, n_shards);
+    BinParams P;
+    P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
+    RFX_TRY(devbuf_reserve(c, c->bin_off, ((size_t)c->n_bins + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->bin_cursor, (size_t)c->n_bins * sizeof(uint64_t)));
+    RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, (size_t)c->n_bins * sizeof(uint64_t), st));
+    const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);
+    unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
+    if (grid < 1) grid = 1;
+    if (grid > 148u * 32u) grid = 148u * 32u;
+    auto* cursor = c->bin_cursor.as<unsigned long long>();
+    if (c->n_reads) {
+        if (c->recw == 2) {
+            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            partition_kernel<2, false><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, nullptr);
+        } else {
+            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            partition_kernel<4, false><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, nullptr);
+        }
+        c->launches++;
+    }
+    // exclusive scan of the per-bin record counts -> bin offsets (+ scatter cursors)
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(c->n_bins) * sizeof(uint64_t)));
+    plan.bind(c->n_bins, c->scan_ws.as<uint64_t>());
+    scan_prepare(plan, BinCountIn{cursor}, OpAddU64{}, (uint64_t)0, st);
+    uint64_t n_records = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&n_records, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    scan_apply(plan, BinCountIn{cursor}, BinOffsetOut{c->bin_off.as<uint64_t>(), cursor}, OpAddU64{}, (uint64_t)0, st);
+    set_last_offset_kernel<<<1, 1, 0, st>>>(c->bin_off.as<uint64_t>(), c->n_bins, plan.total);
+    c->launches += 2 * plan.levels + 2;
+    RFX_TRY(devbuf_reserve(c, c->records, (n_records * c->recw + 2) * sizeof(uint64_t)));
+    if (c->n_reads && n_records) {
+        if (c->recw == 2)
+            partition_kernel<2, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
+        else
+            partition_kernel<4, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
+        c->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "partition failed: %s", cudaGetErrorString(e));
+    c->n_records = n_records;
+    c->have_records = true;
+    c->ms[1] += stage_end(c);
+    return RFX_OK;
+}
+
+// ---- receiving side of a sharded run: group received records by (local) bin ----------------------
+template <int RECW, bool SCATTER>
+__global__ void rebin_kernel(const uint64_t* __restrict__ rx, uint64_t n_rec, BinParams P, uint32_t bin_base, uint32_t n_local,
+                             unsigned long long* __restrict__ bin_cursor, uint64_t* __restrict__ records, unsigned long long* dstat) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t rec[RECW];
+#pragma unroll
+        for (int i = 0; i < RECW; i += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(rx + r * RECW + i);
+            rec[i] = v.x; rec[i + 1] = v.y;
+        }
+        const uint32_t bin = rec_first_bin<RECW>(rec, P) - bin_base;
+        if (bin >= n_local) { atomicExch(&dstat[DS_GRAPH_ERR], 3ull); continue; }  // record sent to the wrong shard
+        const unsigned long long slot = atomicAdd(&bin_cursor[bin], 1ull);
+        if (SCATTER) {
+#pragma unroll
+            for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(records + slot * RECW + i) = make_ulonglong2(rec[i], rec[i + 1]);
+        }
+    }
+}
+
+int stage_rebin(Ctx* c) {
+    cudaStream_t st = c->stream;
+    stage_begin(c);
+    const uint32_t bps = c->forced_bins / (uint32_t)c->n_shards;
+    const uint64_t n_rec = c->rx_bytes / (uint64_t)(c->recw * 8);
+    BinParams P;
+    P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->forced_bins; P.max_nk = c->max_nk;
+    c->n_bins = bps;
+    RFX_TRY(devbuf_reserve(c, c->bin_off, ((size_t)bps + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->bin_cursor, (size_t)bps * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->records, (n_rec * c->recw + 2) * sizeof(uint64_t)));
+    RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, (size_t)bps * sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+    auto* cursor = c->bin_cursor.as<unsigned long long>();
+    auto* dstat = c->dstat.as<unsigned long long>();
+    const uint32_t base = (uint32_t)c->shard_id * bps;
+    unsigned grid = (unsigned)((n_rec + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 148u * 16u) grid = 148u * 16u;
+    if (n_rec) {
+        if (c->recw == 2) rebin_kernel<2, false><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, nullptr, dstat);
+        else rebin_kernel<4, false><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, nullptr, dstat);
+        c->launches++;
+    }
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(bps) * sizeof(uint64_t)));
+    plan.bind(bps, c->scan_ws.as<uint64_t>());
+    scan_prepare(plan, BinCountIn{cursor}, OpAddU64{}, (uint64_t)0, st);
+    scan_apply(plan, BinCountIn{cursor}, BinOffsetOut{c->bin_off.as<uint64_t>(), cursor}, OpAddU64{}, (uint64_t)0, st);
+    set_last_offset_kernel<<<1, 1, 0, st>>>(c->bin_off.as<uint64_t>(), bps, plan.total);
+    c->launches += 2 * plan.levels + 2;
+    if (n_rec) {
+        if (c->recw == 2) rebin_kernel<2, true><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, c->records.as<uint64_t>(), dstat);
+        else rebin_kernel<4, true><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, c->records.as<uint64_t>(), dstat);
+        c->launches++;
+    }
+    uint64_t err = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&err, dstat + DS_GRAPH_ERR, 8, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rebin failed: %s", cudaGetErrorString(e));
+    if (err) return ctx_fail(c, RFX_E_INVALID, "received a record whose bin is not owned by shard %d", c->shard_id);
+    c->n_records = n_rec;
+    c->n_instances = 0;  // unknown on the receiving side; rfx_count fills it in
+    c->have_records = true;
+    c->ms[1] += stage_end(c);
+    return RFX_OK;
+}
+
+}  // namespace rfx

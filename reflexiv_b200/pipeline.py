@@ -1,0 +1,357 @@
+"""Host-side mirror of the reference's pipeline entry points on top of libreflexiv_cuda.
+
+* ``ReflexivContext``                    one rfx_ctx (one GPU): push reads, count, assemble, fetch results
+* ``Pipelines.reflexivDSCounterPipe``    <- pipeline/Pipelines.java:148-152 -> ReflexivDataFrameCounter.assembly() (:139-236)
+* ``Pipelines.reflexivDSMainPipe``       <- pipeline/Pipelines.java:90-98   -> ReflexivDSMain.assembly() (:123-357)
+                                            and assemblyFromKmer() (:362-713) when -kmerc is given
+
+Same output trees as the reference: ``<out>/Count_<k>/part-*.csv[.gz]`` + ``_SUCCESS`` (rows ``KMER,count``) and
+``<out>/part-NNNNN`` contig files (``>Contig-<len>-(<left>,<right>)-<idx>`` + sequence wrapped at 100).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import gzip
+import os
+import uuid
+from typing import Iterable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import RfxError, RfxParams, RfxStats, load_library
+from .params import DefaultParam
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        return np.ascontiguousarray(buf, dtype=np.uint8)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+class ReflexivContext:
+    """One libreflexiv_cuda context.  All heavy lifting happens in the library; this class only moves
+    numpy buffers across the C ABI."""
+
+    def __init__(self, param: Optional[DefaultParam] = None, *, counter_mode: bool = False, fastq_mode: Optional[int] = None,
+                 device: int = 0, minimizer_len: int = 0, table_capacity: int = 0, bin_target_kmers: int = 0):
+        self.L = load_library()
+        param = param or DefaultParam()
+        p = RfxParams()
+        self._check(self.L.rfx_params_default(C.byref(p)), None)
+        p.kmer_size = param.kmerSize
+        p.min_kmer_coverage = param.minKmerCoverage
+        p.max_kmer_coverage = param.maxKmerCoverage
+        p.min_error_coverage = param.minErrorCoverage
+        p.min_contig = param.minContig
+        p.front_clip = param.frontClip
+        p.end_clip = param.endClip
+        p.bubble = 1 if param.bubble else 0
+        p.min_iter = param.minimumIteration
+        p.max_iter = param.maximumIteration
+        p.partitions = param.partitions
+        p.shuffle_partitions = param.shufflePartition
+        p.counter_mode = 1 if counter_mode else 0
+        if fastq_mode is None:
+            # `run` uses the 4-line state machine; `counter` the heuristic, or every line with -infmt line
+            fastq_mode = _lib.FASTQ_RUN if not counter_mode else (_lib.FASTQ_LINE if param.inputFormat == "line" else _lib.FASTQ_COUNTER)
+        p.fastq_mode = fastq_mode
+        p.device = device
+        p.minimizer_len = minimizer_len
+        p.table_capacity = table_capacity
+        p.bin_target_kmers = bin_target_kmers
+        self.params = p
+        self.k = param.kmerSize
+        self._ctx = C.c_void_p()
+        rc = self.L.rfx_create(C.byref(self._ctx), C.byref(p))
+        if rc != 0:
+            raise RfxError(rc, (self.L.rfx_last_error(None) or b"").decode())
+
+    # ---- plumbing ----
+    def _check(self, rc: int, ctx):
+        if rc != 0:
+            raise RfxError(rc, (self.L.rfx_last_error(ctx) or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            self.L.rfx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._check(self.L.rfx_reset(self._ctx), self._ctx)
+
+    # ---- input ----
+    def push_fastq(self, text):
+        a = _as_u8(text)
+        self._check(self.L.rfx_push_fastq(self._ctx, a.ctypes.data, a.size), self._ctx)
+
+    def push_fastq_device(self, dev_ptr: int, n_bytes: int):
+        self._check(self.L.rfx_push_fastq_device(self._ctx, dev_ptr, n_bytes), self._ctx)
+
+    def push_reads(self, bases, offsets):
+        b = _as_u8(bases)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._check(self.L.rfx_push_reads(self._ctx, b.ctypes.data, o.ctypes.data, len(o) - 1), self._ctx)
+
+    # ---- counting ----
+    def count(self):
+        self._check(self.L.rfx_count(self._ctx), self._ctx)
+        return self.stats()
+
+    def counts(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(keys uint64[n_rows, words_per_key] in the reference's key layout, counts uint32[n_rows]); row order unspecified."""
+        n, w = C.c_uint64(), C.c_int32()
+        self._check(self.L.rfx_counts_size(self._ctx, C.byref(n), C.byref(w)), self._ctx)
+        keys = np.empty((n.value, w.value), dtype=np.uint64)
+        cnt = np.empty(n.value, dtype=np.uint32)
+        self._check(self.L.rfx_counts_copy(self._ctx, keys.ctypes.data, cnt.ctypes.data), self._ctx)
+        return keys, cnt
+
+    def counts_csv(self) -> bytes:
+        n = C.c_uint64()
+        self._check(self.L.rfx_counts_csv(self._ctx, None, 0, C.byref(n)), self._ctx)
+        buf = np.empty(n.value, dtype=np.uint8)
+        self._check(self.L.rfx_counts_csv(self._ctx, buf.ctypes.data, buf.size, C.byref(n)), self._ctx)
+        return buf.tobytes()
+
+    def load_counts(self, keys: np.ndarray, counts: np.ndarray):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        self._check(self.L.rfx_load_counts(self._ctx, keys.ctypes.data, counts.ctypes.data, len(counts)), self._ctx)
+
+    # ---- assembly ----
+    def assemble(self):
+        self._check(self.L.rfx_assemble(self._ctx), self._ctx)
+        return self.stats()
+
+    def contigs(self):
+        """[(sequence, left_flag, right_flag)], both strands of every contig, order unspecified."""
+        n, tot = C.c_uint64(), C.c_uint64()
+        self._check(self.L.rfx_contigs_size(self._ctx, C.byref(n), C.byref(tot)), self._ctx)
+        bases = np.empty(tot.value, dtype=np.uint8)
+        offs = np.empty(n.value + 1, dtype=np.uint64)
+        left = np.empty(n.value, dtype=np.int32)
+        right = np.empty(n.value, dtype=np.int32)
+        self._check(self.L.rfx_contigs_copy(self._ctx, bases.ctypes.data, offs.ctypes.data, left.ctypes.data, right.ctypes.data), self._ctx)
+        blob = bases.tobytes()
+        return [(blob[int(offs[i]):int(offs[i + 1])].decode(), int(left[i]), int(right[i])) for i in range(n.value)]
+
+    def oriented(self):
+        """Oriented k-mers that survive both fork filters: (keys_hi, keys_lo, left, right)."""
+        n = C.c_uint64()
+        self._check(self.L.rfx_oriented_size(self._ctx, C.byref(n)), self._ctx)
+        hi = np.empty(n.value, dtype=np.uint64)
+        lo = np.empty(n.value, dtype=np.uint64)
+        le = np.empty(n.value, dtype=np.int32)
+        ri = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self.L.rfx_oriented_copy(self._ctx, hi.ctypes.data, lo.ctypes.data, le.ctypes.data, ri.ctypes.data), self._ctx)
+        return hi, lo, le, ri
+
+    def stats(self) -> dict:
+        s = RfxStats()
+        self._check(self.L.rfx_stats(self._ctx, C.byref(s)), self._ctx)
+        return s.as_dict()
+
+    # ---- sharded counting ----
+    def record_bytes(self) -> int:
+        n = C.c_int32()
+        self._check(self.L.rfx_record_bytes(self._ctx, C.byref(n)), self._ctx)
+        return n.value
+
+    def partition(self, n_shards: int, n_bins_total: int = 0):
+        self._check(self.L.rfx_partition(self._ctx, n_shards, n_bins_total), self._ctx)
+
+    def shard_records(self, shard: int) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.L.rfx_shard_records(self._ctx, shard, C.byref(p), C.byref(n)), self._ctx)
+        return (p.value or 0), n.value
+
+    def begin_shard(self, shard_id: int, n_shards: int, n_bins_total: int):
+        self._check(self.L.rfx_begin_shard(self._ctx, shard_id, n_shards, n_bins_total), self._ctx)
+
+    def load_records_device(self, dev_ptr: int, n_bytes: int):
+        self._check(self.L.rfx_load_records_device(self._ctx, dev_ptr, n_bytes), self._ctx)
+
+    # ---- debug ----
+    def debug_reads(self):
+        n, w = C.c_uint64(), C.c_uint64()
+        self._check(self.L.rfx_debug_reads(self._ctx, C.byref(n), C.byref(w), None, None, None), self._ctx)
+        lens = np.empty(n.value, dtype=np.uint32)
+        woff = np.empty(n.value, dtype=np.uint64)
+        words = np.empty(w.value, dtype=np.uint64)
+        self._check(self.L.rfx_debug_reads(self._ctx, C.byref(n), C.byref(w), lens.ctypes.data, woff.ctypes.data, words.ctypes.data), self._ctx)
+        return lens, woff, words
+
+    def debug_records(self):
+        n, nb = C.c_uint64(), C.c_uint32()
+        self._check(self.L.rfx_debug_records(self._ctx, C.byref(n), C.byref(nb), None, None), self._ctx)
+        offs = np.empty(nb.value + 1, dtype=np.uint64)
+        recs = np.empty((n.value, self.record_bytes() // 8), dtype=np.uint64)
+        self._check(self.L.rfx_debug_records(self._ctx, C.byref(n), C.byref(nb), offs.ctypes.data, recs.ctypes.data), self._ctx)
+        return offs, recs
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers shared by the pipelines
+# ------------------------------------------------------------------------------------------------------
+
+def decode_keys(keys: np.ndarray, k: int) -> List[str]:
+    """DSBinaryKmerToString (Counter.java:405-428, Counter64.java:340-369) for a key matrix in the reference layout."""
+    out = []
+    if k <= 31:
+        for v in keys[:, 0].tolist():
+            out.append("".join("ACGT"[(v >> (2 * (k - 1 - i))) & 3] for i in range(k)))
+    else:
+        res = k % 32
+        for row in keys.tolist():
+            s = []
+            for i in range(k // 32 * 32):
+                s.append("ACGT"[(row[i // 32] >> (2 * (31 - i % 32))) & 3])
+            for i in range(k // 32 * 32, k):
+                s.append("ACGT"[(row[i // 32] >> (2 * (res - 1 - i % 32))) & 3])
+            out.append("".join(s))
+    return out
+
+
+def keys_to_int(keys: np.ndarray, k: int) -> List[int]:
+    """Reference key layout -> one Python int per k-mer (right-aligned 2k bits)."""
+    if k <= 31:
+        return [int(v) for v in keys[:, 0]]
+    res = k % 32
+    return [(int(r[0]) << (2 * res)) | int(r[1]) for r in keys]
+
+
+def encode_kmer_rows(kmers: Iterable[str], k: int) -> np.ndarray:
+    """KmerBinarizer (DSMain.java:3872-3948): ACGT strings -> key matrix in the reference layout."""
+    code = {"A": 0, "C": 1, "G": 2}
+    w = 1 if k <= 31 else k // 32 + 1
+    rows = []
+    for s in kmers:
+        v = 0
+        for ch in s:
+            v = (v << 2) | code.get(ch, 3)
+        if k <= 31:
+            rows.append([v])
+        else:
+            res = k % 32
+            rows.append([(v >> (2 * res)) & 0xFFFFFFFFFFFFFFFF, v & ((1 << (2 * res)) - 1)])
+    return np.array(rows, dtype=np.uint64).reshape(-1, w)
+
+
+def format_contig(seq: str, left: int, right: int, idx: int) -> str:
+    """DSKmerToContig + changeLine + TagRowContigID (DSMain.java:743-794, 717-725)."""
+    body = "\n".join(seq[i:i + 100] for i in range(0, len(seq), 100))
+    return f">Contig-{len(seq)}-({left},{right})-{idx}\n{body}"
+
+
+def read_input_text(pattern: str) -> bytes:
+    """spark.read().text(glob): every matching file, .gz inflated on the host (zlib), concatenated in path order."""
+    paths = sorted(glob.glob(pattern)) or ([pattern] if os.path.exists(pattern) else [])
+    if not paths:
+        raise FileNotFoundError(f"Input path does not exist: {pattern}")
+    chunks = []
+    for p in paths:
+        if os.path.isdir(p):
+            for q in sorted(os.listdir(p)):
+                if q.startswith(("_", ".")):
+                    continue
+                chunks.append(_read_one(os.path.join(p, q)))
+        else:
+            chunks.append(_read_one(p))
+    return b"".join(c if c.endswith(b"\n") or not c else c + b"\n" for c in chunks)
+
+
+def _read_one(path: str) -> bytes:
+    if path.endswith(".4mc"):
+        raise RfxError(_lib.RFX_E_UNSUPPORTED, f"{path}: 4mc input needs hadoop-4mc; decompress first or use gzip/plain text")
+    if path.endswith(".gz"):
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def parse_count_csv(text: bytes, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """KmerBinarizer input forms: `KMER,count` and the legacy `(KMER,count)`; counts of >= 10 digits clamp to 10^9
+    (DSMain.java:3895-3910)."""
+    kmers, counts = [], []
+    for line in text.decode().splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith("("):
+            line = line[1:-1]
+        a, b = line.split(",")
+        kmers.append(a)
+        counts.append(1_000_000_000 if len(b) >= 10 else int(b))
+    return encode_kmer_rows(kmers, k), np.array(counts, dtype=np.uint32)
+
+
+class Pipelines:
+    """pipeline/Pipelines.java: one method per workflow."""
+
+    def __init__(self, param: DefaultParam, device: int = 0):
+        self.param = param
+        self.device = device
+
+    def reflexivDSCounterPipe(self) -> dict:
+        p = self.param
+        text = read_input_text(p.inputFqPath)
+        with ReflexivContext(p, counter_mode=True, device=self.device) as ctx:
+            ctx.push_fastq(text)
+            st = ctx.count()
+            csv = ctx.counts_csv()
+        out_dir = os.path.join(p.outputPath, f"Count_{p.kmerSize}")
+        os.makedirs(out_dir, exist_ok=True)  # SaveMode.Overwrite, Counter.java:224-231
+        for f in os.listdir(out_dir):
+            os.remove(os.path.join(out_dir, f))
+        name = f"part-00000-{uuid.uuid4()}-c000.csv"
+        if p.gzip:
+            with gzip.open(os.path.join(out_dir, name + ".gz"), "wb") as f:
+                f.write(csv)
+        else:
+            with open(os.path.join(out_dir, name), "wb") as f:
+                f.write(csv)
+        open(os.path.join(out_dir, "_SUCCESS"), "w").close()
+        return st
+
+    def reflexivDSMainPipe(self) -> dict:
+        p = self.param
+        from_kmer = p.inputKmerPath is not None
+        out_dir = os.path.join(p.outputPath, f"Assemble_{p.kmerSize}") if from_kmer else p.outputPath  # DSMain.java:706-710 / 354
+        if os.path.exists(out_dir):
+            raise FileExistsError(f"Output directory {out_dir} already exists")  # Hadoop FileAlreadyExistsException
+        with ReflexivContext(p, counter_mode=False, device=self.device) as ctx:
+            if from_kmer:
+                keys, counts = parse_count_csv(read_input_text(p.inputKmerPath), p.kmerSize)
+                keep = (counts >= p.minKmerCoverage) & (counts <= p.maxKmerCoverage)  # DSMain.java:405-412
+                ctx.load_counts(keys[keep], counts[keep])
+            else:
+                ctx.push_fastq(read_input_text(p.inputFqPath))
+                ctx.count()
+            st = ctx.assemble()
+            contigs = ctx.contigs()
+        os.makedirs(out_dir)
+        data = "".join(format_contig(s, l, r, i) + "\n" for i, (s, l, r) in enumerate(contigs)).encode()
+        if p.gzip and from_kmer:
+            with gzip.open(os.path.join(out_dir, "part-00000.gz"), "wb") as f:
+                f.write(data)
+        else:
+            with open(os.path.join(out_dir, "part-00000"), "wb") as f:
+                f.write(data)
+        open(os.path.join(out_dir, "_SUCCESS"), "w").close()
+        return st

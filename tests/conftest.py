@@ -1,0 +1,76 @@
+import gzip
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def example_text() -> bytes:
+    """BASELINE config 1: the reference's example/paired_dat{1,2}.fq.gz, inflated, concatenated in glob order."""
+    return b"".join(gzip.open(os.path.join(GOLDEN, f)).read() for f in ("paired_dat1.fq.gz", "paired_dat2.fq.gz"))
+
+
+@pytest.fixture(scope="session")
+def golden() -> dict:
+    return json.load(open(os.path.join(GOLDEN, "example_k31.json")))
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import orc as o
+    o.lib()
+    return o
+
+
+@pytest.fixture(scope="session")
+def hostemu():
+    import ctypes as C
+    d = os.path.join(ROOT, "tests", "hostemu")
+    subprocess.run(["make", "-s", "-C", d], check=True)
+    L = C.CDLL(os.path.join(d, "libhostemu.so"))
+    P, I64, U32, I = C.c_void_p, C.c_int64, C.c_uint32, C.c_int
+    sig = {
+        "emu_pack_reads": (I64, [P, P, P, I64, I, I, I, P, P, P]),
+        "emu_partition": (I64, [P, I64, P, P, I64, I, I, U32]),
+        "emu_partition_fetch": (None, [P, P]),
+        "emu_count_records": (I64, [P, P, I64, I, I, U32, P]),
+        "emu_count_fetch": (None, [P, P, P]),
+        "emu_bins_bruteforce": (I64, [P, U32, I, I, U32, P]),
+        "emu_fork_filter": (I64, [P, P, P, I64, I, I]),
+        "emu_fork_fetch": (None, [P, P, P, P]),
+        "emu_revcomp64": (C.c_uint64, [C.c_uint64, I]),
+        "emu_revcomp128": (None, [C.c_uint64, C.c_uint64, I, P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    return L
+
+
+@pytest.fixture(scope="session")
+def rfxlib():
+    """libreflexiv_cuda.so, built in tree if missing (nvcc cross-compiles without a GPU)."""
+    from reflexiv_b200 import _lib
+    if not os.path.exists(_lib.lib_path()):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "reflexiv_b200", "csrc"), "../libreflexiv_cuda.so"], check=True)
+    return _lib.load_library()
+
+
+def make_reads(seed: int, genome_len: int, n_pairs: int, read_len: int = 100, err: float = 0.0, frag: int = 250) -> np.ndarray:
+    """Small synthetic FASTQ through the library's host generator."""
+    from reflexiv_b200 import synth
+    g = synth.genome(genome_len, seed)
+    return synth.fastq(g, n_pairs, read_len=read_len, frag_len=frag, error_rate=err, seed_reads=seed + 1, seed_errors=seed + 2)

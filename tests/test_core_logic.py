@@ -1,0 +1,155 @@
+"""Host-side checks of the arithmetic the CUDA kernels are built from (reflexiv_b200/csrc/rfx_core.h), driven by
+tests/hostemu/hostemu.cpp and compared with the oracle.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import make_reads
+
+
+def _pack(hostemu, txt, starts, lens, k, fc=0, ec=0):
+    a = np.frombuffer(bytes(txt), dtype=np.uint8)
+    n = len(starts)
+    elen = np.zeros(n, np.uint32)
+    woff = np.zeros(n, np.uint64)
+    nw = hostemu.emu_pack_reads(a.ctypes.data, starts.ctypes.data, lens.ctypes.data, C.c_int64(n), k, fc, ec, elen.ctypes.data, woff.ctypes.data, None)
+    words = np.zeros(nw + 8, np.uint64)
+    hostemu.emu_pack_reads(a.ctypes.data, starts.ctypes.data, lens.ctypes.data, C.c_int64(n), k, fc, ec, elen.ctypes.data, woff.ctypes.data, words.ctypes.data)
+    return elen, woff, words
+
+
+def _records(hostemu, elen, woff, words, k, m, n_bins):
+    n = hostemu.emu_partition(words.ctypes.data, C.c_int64(len(words)), elen.ctypes.data, woff.ctypes.data, C.c_int64(len(elen)), k, m, C.c_uint32(n_bins))
+    recw = 2 if k <= 31 else 4
+    recs = np.zeros((n, recw), np.uint64)
+    bins = np.zeros(n, np.uint32)
+    hostemu.emu_partition_fetch(recs.ctypes.data, bins.ctypes.data)
+    return recs, bins
+
+
+def _count_records(hostemu, recs, bins, k, m, n_bins):
+    bad = C.c_int64(0)
+    d = hostemu.emu_count_records(recs.ctypes.data, bins.ctypes.data, C.c_int64(len(recs)), k, m, C.c_uint32(n_bins), C.addressof(bad))
+    hi = np.zeros(d, np.uint64); lo = np.zeros(d, np.uint64); cnt = np.zeros(d, np.uint32)
+    hostemu.emu_count_fetch(hi.ctypes.data, lo.ctypes.data, cnt.ctypes.data)
+    return hi, lo, cnt, bad.value
+
+
+@pytest.mark.parametrize("k,m", [(31, 11), (31, 15), (21, 9), (15, 15), (61, 11), (33, 16), (5, 5)])
+def test_records_reproduce_the_kmer_multiset(orc, hostemu, example_text, k, m):
+    txt = example_text[:400_000]
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    ref = orc.count_kmers(txt, starts, lens, k)
+    elen, woff, words = _pack(hostemu, txt, starts, lens, k)
+    n_bins = 96
+    recs, bins = _records(hostemu, elen, woff, words, k, m, n_bins)
+    hi, lo, cnt, bad = _count_records(hostemu, recs, bins, k, m, n_bins)
+    assert bad == 0                                   # every record's first k-mer maps to the record's bin
+    assert np.array_equal(hi, ref["keys_hi"]) and np.array_equal(lo, ref["keys_lo"]) and np.array_equal(cnt, ref["counts"])
+    nk = recs[:, 0] >> np.uint64(48)
+    recw = recs.shape[1]
+    assert nk.min() >= 1 and nk.max() <= (recw * 64 - 16) // 2 - k + 1
+    assert int(nk.sum()) == ref["n_instances"]
+    assert bins.max() < n_bins
+
+
+@pytest.mark.parametrize("k,m", [(31, 11), (25, 7), (61, 13)])
+def test_sliding_minimum_equals_brute_force(orc, hostemu, k, m):
+    """van Herk on-the-fly window minimum vs recomputing the minimiser of every k-mer from scratch, and the
+    strand symmetry that makes the bin a function of the canonical k-mer."""
+    rng = np.random.default_rng(k * 100 + m)
+    n_bins = 1000
+    for length in (k, k + 1, k + 7, 100, 151, 300):
+        seq = "".join("ACGT"[i] for i in rng.integers(0, 4, length))
+        for s in (seq, orc.revcomp_str(seq)):
+            txt = s.encode() + b"\n"
+            st = np.array([0], np.uint64); ln = np.array([length], np.uint32)
+            # pack with the k > 31 rule so reads of length k are kept for every k here
+            elen, woff, words = _pack(hostemu, txt, st, ln, max(k, 33) if length - k <= 1 else k)
+            elen[0] = length
+            brute = np.zeros(length - k + 1, np.uint32)
+            hostemu.emu_bins_bruteforce(words.ctypes.data, C.c_uint32(length), k, m, C.c_uint32(n_bins), brute.ctypes.data)
+            recs, bins = _records(hostemu, elen, woff, words, k, m, n_bins)
+            nk = (recs[:, 0] >> np.uint64(48)).astype(np.int64)
+            expanded = np.repeat(bins, nk)
+            assert np.array_equal(expanded, brute)
+            if s is seq:
+                fwd_bins = brute
+            else:
+                assert np.array_equal(brute, fwd_bins[::-1])   # k-mer i of the reverse strand is k-mer n-1-i
+
+
+def test_packing_matches_clip_and_length_rules(orc, hostemu):
+    txt = b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTAC\nACGTACG\n" + b"N" * 40 + b"\n"
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_LINE)
+    for k, fc, ec in ((7, 0, 0), (7, 3, 2), (5, 1, 0), (33, 0, 0), (33, 5, 5)):
+        elen, woff, words = _pack(hostemu, txt, starts, lens, k, fc, ec)
+        ref = orc.count_kmers(txt, starts, lens, k, fc, ec)
+        inst = int(sum(max(0, int(e) - k + 1) for e in elen))
+        assert inst == ref["n_instances"]
+        recs, bins = _records(hostemu, elen, woff, words, k, min(k, 11), 64)
+        hi, lo, cnt, bad = _count_records(hostemu, recs, bins, k, min(k, 11), 64)
+        assert bad == 0 and np.array_equal(lo, ref["keys_lo"]) and np.array_equal(hi, ref["keys_hi"]) and np.array_equal(cnt, ref["counts"])
+
+
+def test_revcomp_bit_tricks(orc, hostemu):
+    rng = np.random.default_rng(1)
+    for nb in (1, 2, 5, 15, 16, 30, 31, 32):
+        for _ in range(20):
+            s = "".join("ACGT"[i] for i in rng.integers(0, 4, nb))
+            v = int("".join(format("ACGT".index(c), "02b") for c in s), 2)
+            r = int("".join(format("ACGT".index(c), "02b") for c in orc.revcomp_str(s)), 2)
+            assert hostemu.emu_revcomp64(v, nb) == r
+    for nb in (33, 40, 61, 63, 64):
+        s = "".join("ACGT"[i] for i in rng.integers(0, 4, nb))
+        v = int("".join(format("ACGT".index(c), "02b") for c in s), 2)
+        r = int("".join(format("ACGT".index(c), "02b") for c in orc.revcomp_str(s)), 2)
+        oh, ol = C.c_uint64(), C.c_uint64()
+        hostemu.emu_revcomp128(C.c_uint64(v >> 64), C.c_uint64(v & (2**64 - 1)), nb, C.addressof(oh), C.addressof(ol))
+        assert (oh.value << 64) | ol.value == r
+
+
+def _emu_fork(hostemu, cnt, k, E):
+    n = hostemu.emu_fork_filter(cnt["keys_hi"].ctypes.data, cnt["keys_lo"].ctypes.data, cnt["counts"].ctypes.data, C.c_int64(len(cnt["counts"])), k, E)
+    hi = np.zeros(n, np.uint64); lo = np.zeros(n, np.uint64); le = np.zeros(n, np.int32); ri = np.zeros(n, np.int32)
+    hostemu.emu_fork_fetch(hi.ctypes.data, lo.ctypes.data, le.ctypes.data, ri.ctypes.data)
+    order = np.lexsort((lo, hi))
+    return hi[order], lo[order], le[order], ri[order]
+
+
+@pytest.mark.parametrize("k,E,cover,err", [(31, 8, 2, 0.01), (31, 0, 2, 0.01), (21, 8, 1, 0.02), (15, 8, 1, 0.03), (41, 8, 2, 0.01), (12, 8, 1, 0.02)])
+def test_fork_filters_per_group_formulation(orc, hostemu, k, E, cover, err):
+    """The GPU evaluates each (k-1)-mer group from its four candidate neighbours (right_fork / left_fork in rfx_core.h);
+    the oracle sorts and scans like the reference.  Both must keep the same oriented k-mers with the same flags,
+    including real forks (repeats), ties and, for even k, palindromes."""
+    from reflexiv_b200 import synth
+    g = synth.genome(3000, 7 + k)
+    g[1500:1900] = g[200:600]          # a repeat -> real forks
+    g[2500:2520] = np.frombuffer(b"ACGT" * 5, np.uint8)  # low-complexity / palindromic stretch
+    txt = synth.fastq(g, 900, read_len=100, frag_len=250, error_rate=err, seed_reads=3, seed_errors=4)
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    cnt = orc.count_kmers(txt, starts, lens, k, min_count=cover)
+    ref = orc.fork_filter(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], k, E)
+    hi, lo, le, ri = _emu_fork(hostemu, cnt, k, E)
+    assert np.array_equal(hi, ref["keys_hi"]) and np.array_equal(lo, ref["keys_lo"])
+    assert np.array_equal(le, ref["left"]) and np.array_equal(ri, ref["right"])
+    if k == 31 and E == 8:
+        assert ref["stats"]["right_forks"] > 0
+
+
+def test_canonical_assembly_vs_pass_simulation_on_clean_data(orc):
+    """Error-free reads, no repeats: no budget flag survives, so the fixed point is order independent.  The
+    reference's pass simulation may stop before it (its stopping rule only compares record counts three passes
+    apart, DSMain.java:297-311), so its contigs must be substrings of the fixed-point contigs and together cover
+    them."""
+    txt = make_reads(11, 6000, 2400, read_len=100, err=0.0)
+    a = orc.run_pipeline(txt, k=31, cover=2, min_contig=31, mode=orc.ASM_CANONICAL)
+    b = orc.run_pipeline(txt, k=31, cover=2, min_contig=31, mode=orc.ASM_REFSIM)
+    assert a["asm"]["n_budget_junctions"] == 0
+    fix = a["asm"]["contigs"]
+    assert max(len(c) for c in fix) > 5000
+    for c in b["asm"]["contigs"]:
+        assert any(c in f for f in fix)
+    # same k-mer content: (#bases - (k-1)) summed over contigs = number of oriented k-mers
+    assert sum(len(c) - 30 for c in fix) == sum(len(c) - 30 for c in b["asm"]["contigs"]) == len(a["forks"]["left"])

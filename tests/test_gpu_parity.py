@@ -1,0 +1,354 @@
+"""GPU parity tests: every stage of libreflexiv_cuda, through the C ABI, against the CPU oracle on identical inputs.
+Bit-exact everywhere (integer / byte work).  Run with `pytest -m gpu` on a B200."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import make_reads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import reflexiv_b200 as R
+    R.load_library()
+    return R
+
+
+def _sorted_table(R, ctx, k):
+    keys, cnt = ctx.counts()
+    ints = np.array(R.pipeline.keys_to_int(keys, k), dtype=object)
+    order = np.argsort(ints) if len(ints) else np.array([], dtype=np.int64)
+    return [int(x) for x in ints[order]], cnt[order]
+
+
+def _oracle_table(orc, txt, k, mode, fc=0, ec=0, minc=1, maxc=2**62):
+    s, l = orc.fastq_reads(txt, mode)
+    c = orc.count_kmers(txt, s, l, k, fc, ec, minc, maxc)
+    ints = [(int(h) << 64) | int(lo) for h, lo in zip(c["keys_hi"], c["keys_lo"])]
+    return ints, c["counts"], c, (s, l)
+
+
+def _param(R, **kw):
+    return R.DefaultParam(**kw)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K1: FASTQ filters + 2-bit encoder
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("k,fc,ec", [(31, 0, 0), (21, 3, 5), (61, 0, 0)])
+def test_k1_reads_and_packing(R, orc, hostemu, example_text, mode, k, fc, ec):
+    txt = example_text[:300_000]
+    txt = txt[:txt.rfind(b"\n@NODE")] + b"\n"
+    if mode == 2:
+        txt = b"\n".join(txt.split(b"\n")[1::4]) + b"\nACGTNNNNNACGT\n\nAC"  # sequence lines only, ragged tail
+    s, l = orc.fastq_reads(txt, mode)
+    a = np.frombuffer(txt, dtype=np.uint8)
+    elen = np.zeros(len(s), np.uint32); woff = np.zeros(len(s), np.uint64)
+    nw = hostemu.emu_pack_reads(a.ctypes.data, s.ctypes.data, l.ctypes.data, len(s), k, fc, ec, elen.ctypes.data, woff.ctypes.data, None)
+    words = np.zeros(nw + 1, np.uint64)
+    hostemu.emu_pack_reads(a.ctypes.data, s.ctypes.data, l.ctypes.data, len(s), k, fc, ec, elen.ctypes.data, woff.ctypes.data, words.ctypes.data)
+    with R.ReflexivContext(_param(R, kmerSize=k, frontClip=fc, endClip=ec), fastq_mode=mode) as ctx:
+        ctx.push_fastq(txt)
+        g_len, g_woff, g_words = ctx.debug_reads()
+        st = ctx.stats()
+    assert st["n_reads"] == len(s)
+    assert np.array_equal(g_len, elen)
+    assert np.array_equal(g_woff, woff)
+    assert np.array_equal(g_words, words[:nw])
+    assert st["n_bases"] == int(elen.sum())
+
+
+def test_k1_state_machine_edge_cases(R, orc):
+    txt = (b"garbage before the first record\n"
+           b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n@IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+           b"@r2\nTTTTACGTACGTACGTACGTACGAACGTACGTACGT\n+r2\n+IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
+           b"@r3\n@r3b\nACGTNNNNACGTACGTACGTACGTACGTACGTACGT\r\n+\r\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\r\n"
+           b"\n@r4\nGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGGG\n+\n")  # last unit lacks its quality line
+    for tail in (b"", b"IIII", b"IIII\n", b"IIII\n@r5\nACGT"):
+        t = txt + tail
+        s, l = orc.fastq_reads(t, orc.FASTQ_RUN)
+        with R.ReflexivContext(_param(R, kmerSize=15)) as ctx:
+            ctx.push_fastq(t)
+            g_len, _, _ = ctx.debug_reads()
+        assert g_len.tolist() == l.tolist()
+    with R.ReflexivContext(_param(R, kmerSize=15)) as ctx:
+        ctx.push_fastq(b"")
+        ctx.push_fastq(b"\n\n\n")
+        assert ctx.stats()["n_reads"] == 0
+        st = ctx.count()
+        assert st["n_rows"] == 0 and st["n_instances"] == 0
+        assert ctx.assemble()["n_contigs"] == 0 and ctx.contigs() == []
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K2: super-k-mer records
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,m", [(31, 0), (31, 15), (21, 9), (61, 0), (33, 16)])
+def test_k2_records_hold_exactly_the_kmer_instances(R, orc, hostemu, example_text, k, m):
+    txt = example_text
+    ints, counts, c, _ = _oracle_table(orc, txt, k, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=k), minimizer_len=m) as ctx:
+        ctx.push_fastq(txt)
+        ctx.partition(1)
+        offs, recs = ctx.debug_records()
+        st = ctx.stats()
+        mm = m if m else 11
+        n_bins = st["n_bins"]
+    nk = (recs[:, 0] >> np.uint64(48)).astype(np.int64)
+    assert int(nk.sum()) == c["n_instances"] == st["n_instances"]
+    assert offs[0] == 0 and offs[-1] == len(recs) and np.all(np.diff(offs.astype(np.int64)) >= 0)
+    bins = np.repeat(np.arange(n_bins, dtype=np.uint32), np.diff(offs.astype(np.int64)))
+    bad = C.c_int64(0)
+    d = hostemu.emu_count_records(recs.ctypes.data, bins.ctypes.data, len(recs), k, mm, n_bins, C.addressof(bad))
+    hi = np.zeros(d, np.uint64); lo = np.zeros(d, np.uint64); cnt = np.zeros(d, np.uint32)
+    hostemu.emu_count_fetch(hi.ctypes.data, lo.ctypes.data, cnt.ctypes.data)
+    assert bad.value == 0
+    assert np.array_equal(hi, c["keys_hi"]) and np.array_equal(lo, c["keys_lo"]) and np.array_equal(cnt, c["counts"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K3 + K4: counting + coverage filter
+# ---------------------------------------------------------------------------------------------------------
+def test_count_table_golden_digests(R, example_text, golden):
+    """BASELINE config 1 through the C ABI: the digests of SURVEY 8c / tests/golden."""
+    for cov in (1, 2, 3):
+        with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=cov)) as ctx:
+            ctx.push_fastq(example_text)
+            st = ctx.count()
+            csv = ctx.counts_csv()
+        g = golden["oracle"]
+        assert (st["n_reads"], st["n_instances"], st["n_distinct"]) == (g["n_reads"], g["n_instances"], g["n_distinct"])
+        assert st["n_rows"] == g[f"count_ge{cov}"]["rows"]
+        rows = sorted(csv.decode().splitlines())
+        assert hashlib.sha256(("\n".join(rows) + "\n").encode()).hexdigest() == g[f"count_ge{cov}"]["sha256_sorted_csv"]
+
+
+@pytest.mark.parametrize("k", [5, 15, 21, 31, 32, 33, 47, 61, 63])
+def test_counts_match_oracle_all_k(R, orc, example_text, k):
+    txt = example_text[:600_000]
+    txt = txt[:txt.rfind(b"\n@NODE")] + b"\n"
+    ints, counts, c, _ = _oracle_table(orc, txt, k, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1)) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, k)
+    assert st["n_instances"] == c["n_instances"] and st["n_distinct"] == c["n_distinct"]
+    assert g_ints == ints
+    assert np.array_equal(g_counts, counts)
+
+
+@pytest.mark.parametrize("counter_mode,cover,maxcov", [(False, 2, 10_000_000), (False, 3, 20), (True, 1, 10_000_000), (True, 2, 30), (True, 0, 5)])
+def test_coverage_filter_rules(R, orc, example_text, counter_mode, cover, maxcov):
+    """A4: `run` always applies both bounds; `counter` only applies cover if > 1 and maxcov if < 10^7."""
+    if counter_mode:
+        lo = cover if cover > 1 else 1
+        hi = maxcov if maxcov < 10_000_000 else 2**62
+    else:
+        lo, hi = cover, maxcov
+    mode = orc.FASTQ_COUNTER if counter_mode else orc.FASTQ_RUN
+    ints, counts, c, _ = _oracle_table(orc, example_text, 31, mode, minc=max(lo, 1), maxc=hi)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=cover, maxKmerCoverage=maxcov), counter_mode=counter_mode) as ctx:
+        ctx.push_fastq(example_text)
+        ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 31)
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
+def test_bin_overflow_splitting_is_exact(R, orc):
+    """Low coverage + few bins: bins hold far more distinct k-mers than the shared-memory table, so classes are split."""
+    txt = make_reads(21, 400_000, 3000, read_len=150, err=0.0, frag=400)
+    ints, counts, c, _ = _oracle_table(orc, txt, 31, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1), bin_target_kmers=200_000) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 31)
+    assert st["n_bin_splits"] > 0
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+    txt = make_reads(22, 200_000, 1500, read_len=150, err=0.0, frag=400)
+    ints, counts, c, _ = _oracle_table(orc, txt, 61, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=61, minKmerCoverage=1), bin_target_kmers=200_000) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 61)
+    assert st["n_bin_splits"] > 0
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
+def test_push_reads_and_repeated_push(R, orc, example_text):
+    s, l = orc.fastq_reads(example_text, orc.FASTQ_RUN)
+    seqs = [example_text[int(a):int(a) + int(b)] for a, b in zip(s, l)]
+    ints, counts, c, _ = _oracle_table(orc, example_text, 31, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
+        half = len(seqs) // 2
+        for part in (seqs[:half], seqs[half:]):
+            offs = np.concatenate([[0], np.cumsum([len(x) for x in part])]).astype(np.uint64)
+            ctx.push_reads(b"".join(part), offs)
+        ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 31)
+        assert g_ints == ints and np.array_equal(g_counts, counts)
+        # reset + FASTQ text pushed in two record-aligned pieces
+        ctx.reset()
+        cut = example_text.find(b"\n@NODE", len(example_text) // 2) + 1
+        ctx.push_fastq(example_text[:cut])
+        ctx.push_fastq(example_text[cut:])
+        ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 31)
+        assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K5: fork filters ; K6/K7: extension and contigs
+# ---------------------------------------------------------------------------------------------------------
+def _oracle_run(orc, txt, k, cover, E=8, min_contig=500):
+    return orc.run_pipeline(txt, k=k, cover=cover, min_error_cov=E, min_contig=min_contig)
+
+
+def _check_assembly(R, orc, txt, k, cover, E=8, min_contig=500):
+    ref = _oracle_run(orc, txt, k, cover, E, min_contig)
+    with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=cover, minErrorCoverage=E, minContig=min_contig)) as ctx:
+        ctx.push_fastq(txt)
+        ctx.count()
+        st = ctx.assemble()
+        hi, lo, le, ri = ctx.oriented()
+        contigs = ctx.contigs()
+    order = np.lexsort((lo, hi))
+    f = ref["forks"]
+    assert np.array_equal(hi[order], f["keys_hi"]) and np.array_equal(lo[order], f["keys_lo"])
+    assert np.array_equal(le[order], f["left"]) and np.array_equal(ri[order], f["right"])
+    a = ref["asm"]
+    assert st["n_oriented"] == len(f["left"])
+    assert (st["n_budget_junctions"], st["n_budget_admissible"], st["n_cycles"]) == (a["n_budget_junctions"], a["n_budget_admissible"], a["n_cycles"])
+    got = sorted((s, l, r) for s, l, r in contigs)
+    exp = sorted(zip(a["contigs"], a["left"].tolist(), a["right"].tolist()))
+    assert got == exp
+    return ref, st
+
+
+def test_docs_golden_contig_on_gpu(R, orc, example_text, golden):
+    """The reference's documented answer: `reflexiv run -kmer 31 -cover 3` on example/ -> 2 x 4558 bp, documented prefix."""
+    ref, st = _check_assembly(R, orc, example_text, 31, 3)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=3)) as ctx:
+        ctx.push_fastq(example_text)
+        ctx.count()
+        ctx.assemble()
+        contigs = [c for c, _, _ in ctx.contigs()]
+    assert sorted(len(c) for c in contigs) == [4558, 4558]
+    assert sum(c.startswith(golden["documented"]["prefix_1200"]) for c in contigs) == 1
+    cs = orc.canonical_contig_set(contigs)
+    assert [hashlib.sha256(x.encode()).hexdigest() for x in cs] == golden["oracle"]["contigs_cover3"]["canonical_sha256"]
+
+
+@pytest.mark.parametrize("k,cover,E,err", [(31, 2, 8, 0.0), (31, 2, 8, 0.01), (31, 2, 0, 0.01), (21, 1, 8, 0.02), (41, 2, 8, 0.01), (61, 2, 8, 0.005), (24, 1, 8, 0.01)])
+def test_assembly_matches_oracle(R, orc, k, cover, E, err):
+    from reflexiv_b200 import synth
+    g = synth.genome(30_000, 100 + k)
+    g[12000:12800] = g[3000:3800]    # repeat: real forks, budget junctions
+    g[20000:20040] = np.frombuffer(b"AT" * 20, np.uint8)  # palindromic low-complexity stretch (cycles for even k)
+    txt = synth.fastq(g, 6000, read_len=150, frag_len=400, error_rate=err, seed_reads=5, seed_errors=6)
+    ref, st = _check_assembly(R, orc, txt, k, cover, E, min_contig=100)
+    assert st["n_contigs"] >= 2
+
+
+def test_cycles_and_tiny_graphs(R, orc):
+    def fq(seqs):
+        return "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
+    rng = np.random.default_rng(3)
+    circ = "".join("ACGT"[i] for i in rng.integers(0, 4, 300))
+    reads = [(circ + circ)[i:i + 120] for i in range(0, 300, 7)] * 3          # a circular genome: one cycle per strand
+    _check_assembly(R, orc, fq(reads), 31, 2, min_contig=50)
+    _check_assembly(R, orc, fq(["A" * 100] * 3), 31, 2, min_contig=10)       # homopolymer: 1-cycle
+    _check_assembly(R, orc, fq(["ACGT" * 30] * 3), 16, 2, min_contig=10)     # period-4 cycle, even k, palindromes
+    _check_assembly(R, orc, fq([circ[:33]] * 2), 31, 2, min_contig=10)       # three k-mers
+
+
+def test_load_counts_seam(R, orc, example_text):
+    """-kmerc: assemble from a (k-mer, count) table instead of reads (ReflexivDSMain.assemblyFromKmer)."""
+    ref = _oracle_run(orc, example_text, 31, 2)
+    c = ref["counts"]
+    keys = c["keys_lo"].reshape(-1, 1)
+    with R.ReflexivContext(_param(R, kmerSize=31)) as ctx:
+        ctx.load_counts(keys, c["counts"])
+        ctx.assemble()
+        got = sorted(s for s, _, _ in ctx.contigs())
+    assert got == sorted(ref["asm"]["contigs"])
+
+
+def test_error_paths(R, example_text):
+    with R.ReflexivContext(_param(R, kmerSize=31)) as ctx:
+        with pytest.raises(R.RfxError) as e:
+            ctx.assemble()
+        assert e.value.code == R._lib.RFX_E_STATE
+    with R.ReflexivContext(_param(R, kmerSize=31, bubble=False)) as ctx:
+        ctx.push_fastq(example_text)
+        ctx.count()
+        with pytest.raises(R.RfxError) as e:
+            ctx.assemble()
+        assert e.value.code == R._lib.RFX_E_UNSUPPORTED
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1), table_capacity=100) as ctx:
+        ctx.push_fastq(example_text)
+        with pytest.raises(R.RfxError) as e:
+            ctx.count()
+        assert e.value.code == R._lib.RFX_E_CAPACITY
+
+
+def test_pipelines_write_reference_output_trees(R, orc, example_text, tmp_path, golden):
+    import gzip
+    from conftest import GOLDEN
+    out = tmp_path / "result"
+    p = R.Parameter(["-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(out), "-kmer", "31", "-cover", "3"]).importCommandLine()
+    R.Pipelines(p).reflexivDSMainPipe()
+    text = (out / "part-00000").read_text()
+    assert (out / "_SUCCESS").exists()
+    recs = text.strip().split(">")[1:]
+    assert len(recs) == 2
+    for i, r in enumerate(recs):
+        head, *lines = r.split("\n")
+        assert head == f"Contig-4558-(-4,-4)-{i}"
+        assert all(len(x) == 100 for x in lines[:-1]) and len("".join(lines)) == 4558
+    with pytest.raises(FileExistsError):
+        R.Pipelines(p).reflexivDSMainPipe()
+    cout = tmp_path / "counts"
+    pc = R.ParameterOfCounter(["-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(cout), "-kmer", "31", "-cover", "2", "-gzip"]).importCommandLine()
+    R.Pipelines(pc).reflexivDSCounterPipe()
+    d = cout / "Count_31"
+    parts = [f for f in os.listdir(d) if f.startswith("part-")]
+    assert len(parts) == 1 and parts[0].endswith(".csv.gz") and (d / "_SUCCESS").exists()
+    rows = sorted(gzip.open(d / parts[0]).read().decode().splitlines())
+    assert hashlib.sha256(("\n".join(rows) + "\n").encode()).hexdigest() == golden["oracle"]["count_ge2"]["sha256_sorted_csv"]
+    # and back in through -kmerc
+    p2 = R.Parameter(["-kmerc", str(d / "part*.csv.gz"), "-outfile", str(tmp_path / "asm"), "-kmer", "31"]).importCommandLine()
+    R.Pipelines(p2).reflexivDSMainPipe()
+    assert (tmp_path / "asm" / "Assemble_31" / "part-00000").read_text().startswith(">Contig-4575-(-3,-3)-0\n")
+
+
+def test_full_size_properties_config2_slice(R, orc):
+    """Size-independent properties at a larger scale (a 1/8 slice of BASELINE config 2): the sum of counts equals the
+    number of k-mer instances, the table has no duplicates, error-free 100x reads reproduce every genome k-mer with
+    the right multiplicity bound, and the contigs are substrings of the genome."""
+    from reflexiv_b200 import synth
+    G = 575_000
+    g = synth.genome(G)
+    n_pairs = synth.n_pairs_for(G, 100.0)
+    txt = synth.fastq(g, n_pairs)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        keys, cnt = ctx.counts()
+        assert st["n_reads"] == 2 * n_pairs and st["n_instances"] == 2 * n_pairs * 120
+        assert int(cnt.astype(np.int64).sum()) == st["n_instances"]
+        assert len(np.unique(keys[:, 0])) == len(keys) == st["n_distinct"]
+        st = ctx.assemble()
+        contigs = [c for c, _, _ in ctx.contigs()]
+    gs = bytes(g).decode()
+    grc = orc.revcomp_str(gs)
+    assert st["n_contigs"] >= 2 and sum(len(c) for c in contigs) > 1.9 * 0.99 * G
+    for c in contigs[:40]:
+        assert c in gs or c in grc
