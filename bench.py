@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Reflexiv hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...            (one rank per GPU, NCCL)
+
+Workload (BASELINE.json configs[1]): synthetic E. coli-size genome (4.6 Mbp), 150 bp paired reads at 100x coverage,
+k = 31, full `reflexiv run` path: FASTQ text -> 2-bit reads -> canonical k-mer count table -> coverage filter ->
+fork filters -> contig extension -> contig bases.  A step is one pass over the whole read set.  At N > 1 every rank
+holds the same amount of reads (weak scaling: genome and read set grow with N), records are exchanged with one NCCL
+all-to-all, shards count locally, the shard tables are all-gathered and the graph stages run replicated.
+
+`value`   k-mer instances per second over the whole step, inputs (FASTQ text) resident in HBM.
+`e2e`     same metric through the public API with host buffers: H2D of the FASTQ text from pinned memory and D2H of
+          the contigs inside the timed region.
+`roofline` the dominant kernel against the measured HBM copy bandwidth, algorithmic bytes per SURVEY 8(d).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GENOME_LEN = 4_600_000
+COVERAGE = 100.0
+READ_LEN = 150
+K = 31
+METRIC = "canonical k-mers counted/sec (full reflexiv run path: count + contig extension)"
+UNIT = "k-mers/s"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_inputs(rank: int, world: int):
+    """This rank's FASTQ text: pairs [rank*P, (rank+1)*P) of a genome of world * 4.6 Mbp."""
+    import numpy as np
+    from reflexiv_b200 import synth
+    g = synth.genome(GENOME_LEN * world)
+    pairs = synth.n_pairs_for(GENOME_LEN, COVERAGE, READ_LEN)
+    txt = synth.fastq(g, pairs, read_len=READ_LEN, frag_len=400, first_pair=rank * pairs)
+    return txt, 2 * pairs
+
+
+def cpu_reference_run(sample_reads: int = 1_000_000, threads: int = 0):
+    """The reference's algorithm on the host cores (oracle: extract -> hash-partition -> per-partition aggregate ->
+    filter -> fork filters -> sort + merge passes), on a bounded sample of the same workload."""
+    import numpy as np
+    from oracle import orc
+    from reflexiv_b200 import synth
+    threads = threads or os.cpu_count() or 1
+    # sample = the reads of a 1/x genome at the same coverage, so the k-mer spectrum is that of the workload
+    frac_genome = max(20_000, int(GENOME_LEN * sample_reads / (2 * synth.n_pairs_for(GENOME_LEN, COVERAGE, READ_LEN))))
+    g = synth.genome(frac_genome)
+    pairs = synth.n_pairs_for(frac_genome, COVERAGE, READ_LEN)
+    txt = synth.fastq(g, pairs, read_len=READ_LEN, frag_len=400)
+    t0 = time.perf_counter()
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    cnt = orc.count_kmers(txt, starts, lens, K, 0, 0, 2, 10_000_000, threads)
+    t1 = time.perf_counter()
+    ff = orc.fork_filter(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], K, 8)
+    asm = orc.assemble(ff["keys_hi"], ff["keys_lo"], ff["left"], ff["right"], K, 500, orc.ASM_REFSIM)
+    t2 = time.perf_counter()
+    n_inst = cnt["n_instances"]
+    return {"value": n_inst / (t2 - t0), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{2 * pairs} reads x {READ_LEN} bp ({n_inst} k-mers) of a {frac_genome} bp genome at {COVERAGE:.0f}x, k={K}; "
+                      f"count {t1 - t0:.2f}s ({threads} threads) + fork filters and {asm['n_passes']} sort+merge passes {t2 - t1:.2f}s (1 thread); "
+                      "CPU restatement of the reference algorithm, the JVM/Spark reference cannot run in this image",
+            "count_stage_kmers_per_s": n_inst / (t1 - t0), "reads_per_s": 2 * pairs / (t2 - t0), "seconds": t2 - t0}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, args.warmup) - 1 + max(1, args.steps)):
+        vals.append(cpu_reference_run())
+    vals = vals[-max(1, args.steps):]
+    best = sorted(vals, key=lambda r: r["value"])[len(vals) // 2]
+    line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"configs[1] sample: synthetic {GENOME_LEN} bp genome, {READ_LEN} bp paired reads at {COVERAGE:.0f}x, k={K}, full run path",
+                       "note": best["sample"]},
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--minimizer", type=int, default=0)
+    ap.add_argument("--bin-target", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import reflexiv_b200 as R
+    from reflexiv_b200 import sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libreflexiv_cuda has no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    args.warmup = max(args.warmup, 3)
+
+    txt, n_reads = make_inputs(rank, world)
+    n_bytes = len(txt)
+    pinned = torch.empty(n_bytes + 64, dtype=torch.uint8, pin_memory=True)
+    pinned[:n_bytes] = torch.from_numpy(txt)
+    pinned[n_bytes:] = 0
+    d_text = torch.zeros(n_bytes + 64, dtype=torch.uint8, device=device)
+    d_text[:n_bytes].copy_(pinned[:n_bytes])
+    torch.cuda.synchronize()
+    host_view = pinned.numpy()[:n_bytes]
+
+    param = R.DefaultParam(kmerSize=K)
+    ctx = R.ReflexivContext(param, device=local, minimizer_len=args.minimizer, bin_target_kmers=args.bin_target)
+    n_inst_rank = n_reads * (READ_LEN - K + 1)
+    n_bins_total = sharded.choose_total_bins(n_inst_rank * world, world, args.bin_target or 16384)
+
+    def step(from_host: bool):
+        ctx.reset()
+        if from_host:
+            ctx.push_fastq(host_view)
+        else:
+            ctx.push_fastq_device(d_text.data_ptr(), n_bytes)
+        if world == 1:
+            ctx.count()
+        else:
+            sharded.sharded_count(ctx, torch, dist, device, n_bins_total)
+            sharded.gather_tables(ctx, torch, dist, device)
+        st = ctx.assemble()
+        if from_host:
+            contigs = ctx.contigs()
+            return st, sum(len(c[0]) for c in contigs) + 16 * len(contigs) + 8
+        return st, 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(n_steps: int, from_host: bool):
+        barrier()
+        launches0 = ctx.stats()["kernel_launches"]
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        stats, d2h = [], 0
+        for _ in range(n_steps):
+            st, d2h = step(from_host)
+            stats.append(st)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), stats, ctx.stats()["kernel_launches"] - launches0, d2h
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_dev, stats, launches, _ = timed(args.steps, False)
+    clocks = sampler.stop()
+    step(True)
+    t_e2e, stats_e2e, _, d2h_bytes = timed(args.steps, True)
+
+    def med(key, ss=stats):
+        v = sorted(s[key] for s in ss)
+        return v[len(v) // 2]
+
+    st = stats[-1]
+    total_inst = n_inst_rank * world
+    ms_step = t_dev / args.steps * 1e3
+    value = total_inst / (t_dev / args.steps)
+    e2e_value = total_inst / (t_e2e / args.steps)
+    stage_ms = {k: med(k) for k in ("ms_parse", "ms_partition", "ms_count", "ms_graph", "ms_extend", "ms_contigs")}
+    kern_ms = {k: med(k) for k in ("ms_kernel_bin_histogram", "ms_kernel_bin_scatter", "ms_kernel_count")}
+
+    # roofline of the dominant counting-path kernel.  Algorithmic bytes of the counting stage:
+    #   B_count = sum(read_len) + 16 * N * W + (8 * W + 4) * D'   (W = 1 word per key for k = 31)
+    # The counting stage is three launches (bin histogram, bin scatter, per-bin count); each kernel is charged the
+    # whole B_count of its shard, so `frac` is a lower bound for every one of them.
+    peak, peak_src = hbm_peak()
+    inst_local = st["n_instances"] if world == 1 else n_inst_rank
+    b_count = n_reads * READ_LEN + 16 * inst_local + 12 * (st["n_rows"] if world == 1 else st["n_rows"] // world)
+    dom = max(kern_ms, key=kern_ms.get)
+    dom_ms = kern_ms[dom]
+    count_path_ms = sum(kern_ms.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": b_count / (dom_ms * 1e-3) / 1e9 if dom_ms else None, "peak": peak, "unit": "GB/s",
+                "frac": (b_count / (dom_ms * 1e-3) / 1e9 / peak) if dom_ms else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_count, "kernel_ms": kern_ms,
+                "counting_stage": {"ms": count_path_ms, "kmers_per_s": inst_local / (count_path_ms * 1e-3) if count_path_ms else None,
+                                   "achieved_gbs": b_count / (count_path_ms * 1e-3) / 1e9 if count_path_ms else None,
+                                   "frac": b_count / (count_path_ms * 1e-3) / 1e9 / peak if count_path_ms else None}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(dom)
+        except Exception:
+            pass
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"configs[1]: synthetic {GENOME_LEN * world} bp genome, {n_reads * world} x {READ_LEN} bp paired reads at {COVERAGE:.0f}x, "
+                                   f"k={K}, cover 2, full run path (FASTQ text -> counts -> fork filters -> contigs)",
+                       "l2_policy": f"inputs larger than L2: {n_bytes / 1e6:.0f} MB of FASTQ text per GPU per step, nothing reused across steps",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: minimiser-bin shards, NCCL all-to-all of super-k-mer records, replicated graph stage",
+                       "timing": "host clock around blocking C-ABI calls bracketed by barrier + cuda synchronize, max over ranks; per-stage and per-kernel times from CUDA events on the library's stream"},
+            "reads_per_s": n_reads * world / (t_dev / args.steps),
+            "stage_ms": stage_ms, "result": {k: st[k] for k in ("n_reads", "n_instances", "n_distinct", "n_rows", "n_records", "n_bins", "n_bin_splits",
+                                                              "n_oriented", "n_contigs", "n_contig_bases", "n_budget_junctions", "n_cycles")},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clocks}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = {k: v for k, v in cpu_reference_run().items() if k in ("value", "unit", "cores", "kind", "sample", "count_stage_kmers_per_s", "reads_per_s")}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,11 @@ typedef struct {
     float ms_graph;    /* K5: both orientations, fork filters, neighbour links */
     float ms_extend;   /* K6: list ranking */
     float ms_contigs;  /* K7: contig gather */
+    /* single-kernel durations of the last rfx_count (CUDA events around the launch only) */
+    float ms_kernel_bin_histogram; /* partition_kernel<.., false> */
+    float ms_kernel_bin_scatter;   /* partition_kernel<.., true>  */
+    float ms_kernel_count;         /* count_bins_*_kernel         */
+    float reserved1;
 } rfx_stats_t;
 
 int rfx_params_default(rfx_params* p);
@@ -158,6 +163,12 @@ int rfx_shard_records(rfx_ctx* ctx, int32_t shard, const void** d_ptr, uint64_t*
 int rfx_begin_shard(rfx_ctx* ctx, int32_t shard_id, int32_t n_shards, uint32_t n_bins_total);
 int rfx_load_records_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes);
 int rfx_record_bytes(rfx_ctx* ctx, int32_t* bytes_per_record);
+/* The filtered table as device pointers (valid until the next rfx_count / rfx_load_* / rfx_reset): keys are
+ * key_bytes (8 for k <= 31, 16 for k > 31) little-endian right-aligned 2k-bit integers, i.e. the library's internal
+ * layout, NOT the reference slot layout of rfx_counts_copy.  Used to move shard tables between GPUs. */
+int rfx_counts_device(rfx_ctx* ctx, const void** d_keys, const uint32_t** d_counts, uint64_t* n_rows, int32_t* key_bytes);
+/* Replace (append == 0) or extend (append != 0) the table from device memory in that same layout. */
+int rfx_load_counts_device(rfx_ctx* ctx, const void* d_keys, const uint32_t* d_counts, uint64_t n_rows, int32_t append);
 
 /* ---- synthetic data (host, deterministic) ----------------------------------------- */
 int64_t rfx_synth_genome(uint8_t* out, int64_t n_bases, uint64_t seed);

@@ -30,7 +30,8 @@ class RfxStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_reads", "n_bases", "n_instances", "n_distinct", "n_rows", "n_records", "n_bins", "n_bin_splits", "n_oriented",
         "n_budget_junctions", "n_budget_admissible", "n_cycles", "n_contigs", "n_contig_bases", "kernel_launches")] + [
-        (n, C.c_float) for n in ("ms_parse", "ms_partition", "ms_count", "ms_graph", "ms_extend", "ms_contigs")]
+        (n, C.c_float) for n in ("ms_parse", "ms_partition", "ms_count", "ms_graph", "ms_extend", "ms_contigs",
+                                 "ms_kernel_bin_histogram", "ms_kernel_bin_scatter", "ms_kernel_count", "reserved1")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -64,6 +65,8 @@ SYMBOLS = {
     "rfx_begin_shard": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32]),
     "rfx_load_records_device": (C.c_int, [_P, _P, C.c_uint64]),
     "rfx_record_bytes": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "rfx_counts_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
+    "rfx_load_counts_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32]),
     "rfx_synth_genome": (C.c_int64, [_P, C.c_int64, C.c_uint64]),
     "rfx_synth_fastq": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_uint64,
                                     C.c_uint64, _P, C.c_int64]),

@@ -164,6 +164,7 @@ int rfx_create(rfx_ctx** out, const rfx_params* p) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->evk[i]);
     if (e != cudaSuccess) {
         // no CPU fallback: without a usable CUDA device the library refuses to create a context
         rc = ctx_fail(nullptr, RFX_E_CUDA, "rfx_create: CUDA device %d unusable: %s", p->device, cudaGetErrorString(e));
@@ -183,6 +184,7 @@ void rfx_destroy(rfx_ctx* c) {
     free_all(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 6; i++) if (c->evk[i]) cudaEventDestroy(c->evk[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -412,6 +414,7 @@ int rfx_stats(rfx_ctx* c, rfx_stats_t* s) {
     s->kernel_launches = c->launches;
     s->ms_parse = c->ms[0]; s->ms_partition = c->ms[1]; s->ms_count = c->ms[2];
     s->ms_graph = c->ms[3]; s->ms_extend = c->ms[4]; s->ms_contigs = c->ms[5];
+    s->ms_kernel_bin_histogram = c->ms_kernel[0]; s->ms_kernel_bin_scatter = c->ms_kernel[1]; s->ms_kernel_count = c->ms_kernel[2];
     return RFX_OK;
 }
 
@@ -455,6 +458,35 @@ int rfx_load_records_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes)
     if (n_bytes) RFX_CUDA(c, cudaMemcpyAsync(c->rx_records.as<uint8_t>() + c->rx_bytes, d_records, n_bytes, cudaMemcpyDeviceToDevice, c->stream));
     RFX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->rx_bytes += n_bytes;
+    return RFX_OK;
+}
+
+int rfx_counts_device(rfx_ctx* c, const void** d_keys, const uint32_t** d_counts, uint64_t* n_rows, int32_t* key_bytes) {
+    if (!c) return RFX_E_INVALID;
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "no count table");
+    if (d_keys) *d_keys = c->keys.p;
+    if (d_counts) *d_counts = c->counts.as<uint32_t>();
+    if (n_rows) *n_rows = c->n_rows;
+    if (key_bytes) *key_bytes = c->wide ? 16 : 8;
+    return RFX_OK;
+}
+
+int rfx_load_counts_device(rfx_ctx* c, const void* d_keys, const uint32_t* d_counts, uint64_t n_rows, int32_t append) {
+    if (!c || (n_rows && (!d_keys || !d_counts))) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    const size_t ksz = c->wide ? 16 : 8;
+    const uint64_t base = (append && c->have_counts) ? c->n_rows : 0;
+    RFX_TRY(devbuf_reserve(c, c->keys, (base + n_rows + 1) * ksz, base > 0));
+    RFX_TRY(devbuf_reserve(c, c->counts, (base + n_rows + 1) * sizeof(uint32_t), base > 0));
+    if (n_rows) {
+        RFX_CUDA(c, cudaMemcpyAsync(c->keys.as<uint8_t>() + base * ksz, d_keys, n_rows * ksz, cudaMemcpyDeviceToDevice, c->stream));
+        RFX_CUDA(c, cudaMemcpyAsync(c->counts.as<uint32_t>() + base, d_counts, n_rows * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->n_rows = base + n_rows;
+    c->table_cap = c->n_rows + 1;
+    c->have_counts = true;
+    c->have_contigs = false;
     return RFX_OK;
 }
 

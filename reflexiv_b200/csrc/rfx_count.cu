@@ -346,6 +346,7 @@ int stage_count(Ctx* c) {
     A.dstat = c->dstat.as<unsigned long long>();
     A.out_cap = cap;
     if (c->n_records) {
+        cudaEventRecord(c->evk[4], st);
         if (!c->wide) {
             const size_t smem = (size_t)CAP_NARROW * 12;
             RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -357,6 +358,7 @@ int stage_count(Ctx* c) {
             unsigned grid = c->n_bins < 148u * 2u * 8u ? c->n_bins : 148u * 2u * 8u;
             count_bins_wide_kernel<4, CAP_WIDE><<<grid, CNT_THREADS, smem, st>>>(A);
         }
+        cudaEventRecord(c->evk[5], st);
         c->launches++;
     }
     uint64_t h[DS_NSLOTS];
@@ -364,6 +366,8 @@ int stage_count(Ctx* c) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count kernel failed: %s", cudaGetErrorString(e));
     c->ms[2] += stage_end(c);
+    c->ms_kernel[2] = 0;
+    if (c->n_records) cudaEventElapsedTime(&c->ms_kernel[2], c->evk[4], c->evk[5]);
     if (h[DS_OVERFLOW] == 2) return ctx_fail(c, RFX_E_CAPACITY, "a counting bin could not be split further");
     if (h[DS_OVERFLOW] == 1 || h[DS_OUT_CURSOR] > cap)
         return ctx_fail(c, RFX_E_CAPACITY, "filtered table needs %llu rows, capacity %llu: raise table_capacity",

@@ -102,7 +102,9 @@ struct Ctx {
     bool have_contigs = false;
 
     float ms[6] = {0, 0, 0, 0, 0, 0};
+    float ms_kernel[3] = {0, 0, 0};  // histogram, scatter, count: last launch only
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // device-side counter slots in Ctx::dstat

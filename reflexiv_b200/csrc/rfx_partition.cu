@@ -100,6 +100,7 @@ int stage_partition(Ctx* c, int n_shards) {
     if (grid > 148u * 32u) grid = 148u * 32u;
     auto* cursor = c->bin_cursor.as<unsigned long long>();
     if (c->n_reads) {
+        cudaEventRecord(c->evk[0], st);
         if (c->recw == 2) {
             RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -109,6 +110,7 @@ int stage_partition(Ctx* c, int n_shards) {
             RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             partition_kernel<4, false><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, nullptr);
         }
+        cudaEventRecord(c->evk[1], st);
         c->launches++;
     }
     // exclusive scan of the per-bin record counts -> bin offsets (+ scatter cursors)
@@ -124,14 +126,19 @@ int stage_partition(Ctx* c, int n_shards) {
     c->launches += 2 * plan.levels + 2;
     RFX_TRY(devbuf_reserve(c, c->records, (n_records * c->recw + 2) * sizeof(uint64_t)));
     if (c->n_reads && n_records) {
+        cudaEventRecord(c->evk[2], st);
         if (c->recw == 2)
             partition_kernel<2, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
         else
             partition_kernel<4, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
+        cudaEventRecord(c->evk[3], st);
         c->launches++;
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "partition failed: %s", cudaGetErrorString(e));
+    c->ms_kernel[0] = c->ms_kernel[1] = 0;
+    if (c->n_reads) cudaEventElapsedTime(&c->ms_kernel[0], c->evk[0], c->evk[1]);
+    if (c->n_reads && n_records) cudaEventElapsedTime(&c->ms_kernel[1], c->evk[2], c->evk[3]);
     c->n_records = n_records;
     c->have_records = true;
     c->ms[1] += stage_end(c);

@@ -186,6 +186,15 @@ class ReflexivContext:
     def load_records_device(self, dev_ptr: int, n_bytes: int):
         self._check(self.L.rfx_load_records_device(self._ctx, dev_ptr, n_bytes), self._ctx)
 
+    def counts_device(self):
+        """(keys device pointer, counts device pointer, n_rows, key_bytes) of the filtered table in HBM."""
+        pk, pc, n, kb = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_int32()
+        self._check(self.L.rfx_counts_device(self._ctx, C.byref(pk), C.byref(pc), C.byref(n), C.byref(kb)), self._ctx)
+        return (pk.value or 0), (pc.value or 0), n.value, kb.value
+
+    def load_counts_device(self, keys_ptr: int, counts_ptr: int, n_rows: int, append: bool = False):
+        self._check(self.L.rfx_load_counts_device(self._ctx, keys_ptr, counts_ptr, n_rows, 1 if append else 0), self._ctx)
+
     # ---- debug ----
     def debug_reads(self):
         n, w = C.c_uint64(), C.c_uint64()

@@ -1,0 +1,101 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for the exchanges.
+
+The counting path shards by minimiser bin: every rank bins its own reads into super-k-mer records
+laid out shard-major, one all-to-all moves each shard's slice to its owner (this is the step that replaces Spark's
+groupBy hash shuffle, ReflexivDataFrameCounter.java:198-200), the owner re-bins and counts locally.  Shard tables are
+disjoint, so their concatenation is the global table; no reduction collective is involved.
+
+`exchange_bytes` is backend agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n_bytes: int):
+        self.__cuda_array_interface__ = {"shape": (n_bytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def device_view(torch, ptr: int, n_bytes: int, device):
+    if n_bytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevView(ptr, n_bytes), device=device)
+
+
+def shard_of_bin(bin_id: int, n_bins_total: int, n_shards: int) -> int:
+    """Bins are shard-major: shard s owns bins [s*B/n, (s+1)*B/n)."""
+    return bin_id // (n_bins_total // n_shards)
+
+
+def choose_total_bins(global_instances: int, n_shards: int, target_per_bin: int = 16384, lo: int = 64, hi: int = 1 << 24) -> int:
+    """Same rule as the library's single-process choice (rfx_partition.cu: choose_bins), on the GLOBAL instance count,
+    rounded up to a multiple of the shard count so that every rank computes the same number."""
+    nb = max(lo, min(hi, -(-global_instances // target_per_bin)))
+    return -(-nb // n_shards) * n_shards
+
+
+def exchange_bytes(torch, dist, send, send_sizes: Sequence[int], group=None) -> Tuple[object, List[int]]:
+    """All-to-all of variable-size byte slices.  `send` is one uint8 tensor holding the slices for rank 0, 1, ...
+    back to back.  Returns (recv tensor, recv sizes)."""
+    world = dist.get_world_size(group)
+    assert len(send_sizes) == world and sum(send_sizes) == send.numel()
+    s = torch.tensor(list(send_sizes), dtype=torch.int64, device=send.device)
+    r = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(r, s, group=group)
+    recv_sizes = [int(x) for x in r.tolist()]
+    recv = torch.empty(sum(recv_sizes), dtype=torch.uint8, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_sizes, input_split_sizes=list(send_sizes), group=group)
+    return recv, recv_sizes
+
+
+def gather_varlen(torch, dist, local, group=None):
+    """all_gather of 1-D tensors of different lengths (same dtype); returns the concatenation in rank order."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.empty(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(sizes) if sizes else 0
+    pad = torch.zeros(mx, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    bufs = [torch.empty(mx, dtype=local.dtype, device=local.device) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)]), sizes
+
+
+def _sync(torch, device):
+    """The library runs on its own stream and its calls block; torch work that produced its inputs must be done."""
+    if getattr(device, "type", str(device)) != "cpu" and torch.cuda.is_available():
+        torch.cuda.current_stream(device).synchronize()
+
+
+def sharded_count(ctx, torch, dist, device, n_bins_total: int, group=None) -> dict:
+    """Counting across the ranks of `group`; on return `ctx` holds this rank's shard of the global table."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ctx.partition(world, n_bins_total)
+    slices = [ctx.shard_records(s) for s in range(world)]
+    base = slices[0][0]
+    total = sum(n for _, n in slices)
+    send = device_view(torch, base, total, device)
+    recv, _ = exchange_bytes(torch, dist, send, [n for _, n in slices], group)
+    _sync(torch, device)
+    ctx.begin_shard(rank, world, n_bins_total)
+    ctx.load_records_device(recv.data_ptr() if recv.numel() else 0, recv.numel())
+    del recv
+    return ctx.count()
+
+
+def gather_tables(ctx, torch, dist, device, group=None) -> dict:
+    """Replicates the global (k-mer, count) table on every rank (all_gather of the disjoint shard tables) so the
+    graph stages can run; returns the context stats."""
+    pk, pc, n, kb = ctx.counts_device()
+    keys = device_view(torch, pk, n * kb, device)
+    cnts = device_view(torch, pc, n * 4, device)
+    all_keys, sizes = gather_varlen(torch, dist, keys.clone(), group)
+    all_cnts, _ = gather_varlen(torch, dist, cnts.clone(), group)
+    n_all = sum(sizes) // kb
+    _sync(torch, device)
+    ctx.load_counts_device(all_keys.data_ptr() if n_all else 0, all_cnts.data_ptr() if n_all else 0, n_all, append=False)
+    return ctx.stats()

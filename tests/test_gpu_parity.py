@@ -310,7 +310,7 @@ def test_pipelines_write_reference_output_trees(R, orc, example_text, tmp_path, 
     recs = text.strip().split(">")[1:]
     assert len(recs) == 2
     for i, r in enumerate(recs):
-        head, *lines = r.split("\n")
+        head, *lines = r.strip().split("\n")
         assert head == f"Contig-4558-(-4,-4)-{i}"
         assert all(len(x) == 100 for x in lines[:-1]) and len("".join(lines)) == 4558
     with pytest.raises(FileExistsError):
