@@ -95,8 +95,8 @@ typedef struct {
     float ms_extend;   /* K6: list ranking */
     float ms_contigs;  /* K7: contig gather */
     /* single-kernel durations of the last rfx_count (CUDA events around the launch only) */
-    float ms_kernel_bin_histogram; /* partition_kernel<.., false> */
-    float ms_kernel_bin_scatter;   /* partition_kernel<.., true>  */
+    float ms_kernel_bin_histogram; /* bin_scan_kernel: minimiser scan, run descriptors, bin histogram */
+    float ms_kernel_bin_scatter;   /* emit_records_kernel: super-k-mer records into bins */
     float ms_kernel_count;         /* count_bins_*_kernel         */
     float reserved1;
 } rfx_stats_t;

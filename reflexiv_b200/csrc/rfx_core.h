@@ -151,7 +151,7 @@ template <class KT, int RECW, class F> RFX_HD void rec_foreach_kmer(const uint64
 
 // ---------------------------------------------------------------------------------------------
 // minimiser binning of one read (pass 1).  One thread walks one read.
-//   m-mer hash      h(j) = fmix32(min(mmer, revcomp(mmer)))            (m <= 16)
+//   m-mer hash      h(j) = mmer_hash(min(mmer, revcomp(mmer)))         (m <= 16)
 //   k-mer minimiser      = min over its w = k - m + 1 m-mers of h      (strand symmetric)
 //   bin                  = fmix32(minimiser ^ salt) * n_bins >> 32
 // Consecutive k-mers of equal bin form one super-k-mer run; runs are cut at max_nk k-mers.
@@ -169,6 +169,14 @@ struct BinParams {
     uint32_t max_nk;  // k-mers per record
 };
 
+// Order of the m-mers inside a k-mer: two multiplies and a fold are enough to make "smallest hash" an arbitrary,
+// strand-symmetric choice; the bin is re-mixed separately below.
+RFX_HD uint32_t mmer_hash(uint32_t canon_mmer) {
+    uint32_t h = (canon_mmer ^ 0x3c6ef372u) * 0x9E3779B1u;
+    h ^= h >> 15;
+    return h * 0x85ebca6bu;
+}
+
 RFX_HD uint32_t bin_of_minimizer(uint32_t hmin, uint32_t n_bins) {
     return (uint32_t)(((uint64_t)fmix32(hmin ^ 0x9e3779b9u) * n_bins) >> 32);
 }
@@ -182,52 +190,61 @@ template <class Emit> RFX_HD void bin_scan_read(const uint64_t* rd, uint32_t len
     const int mtop = 2 * (m - 1);
     uint32_t mf = 0, mr = 0;
     uint64_t cur = 0;
-    uint32_t blk = 0;        // which half of the ring the current block writes
-    int pib = 0;             // position in block of the m-mer being produced
-    uint32_t pmin = 0xffffffffu;  // prefix minimum of the current block
-    uint32_t run_bin = 0, run_start = 0;
-    bool in_run = false;
-    for (uint32_t e = 0; e < len; e++) {
+    uint32_t e = 0;
+    for (; e + 1 < (uint32_t)m; e++) {  // the first m-1 bases complete no m-mer
         if ((e & 31u) == 0) cur = rd[e >> 5];
-        uint32_t v = (uint32_t)(cur >> 62);
+        const uint32_t v = (uint32_t)(cur >> 62);
         cur <<= 2;
         mf = ((mf << 2) | v) & mmask;
         mr = (mr >> 2) | ((v ^ 3u) << mtop);
-        if (e + 1 < (uint32_t)m) continue;
-        // m-mer j = e - m + 1 is complete
-        uint32_t h = fmix32(mf < mr ? mf : mr);
-        ring[(blk * (uint32_t)w + (uint32_t)pib) * rs] = h;
+    }
+    uint32_t* blk_cur = ring;                       // block being filled
+    uint32_t* blk_prev = ring + (uint32_t)w * rs;   // previous block, already turned into suffix minima
+    int pib = 0;                                    // position in block of the m-mer being produced
+    uint32_t pmin = 0xffffffffu;                    // prefix minimum of the current block
+    uint32_t prev_h = 0, run_bin = 0, run_start = 0;
+    const uint32_t n_mmers = len - (uint32_t)m + 1u;
+    for (uint32_t j = 0; j < n_mmers; j++, e++) {
+        if ((e & 31u) == 0) cur = rd[e >> 5];
+        const uint32_t v = (uint32_t)(cur >> 62);
+        cur <<= 2;
+        mf = ((mf << 2) | v) & mmask;
+        mr = (mr >> 2) | ((v ^ 3u) << mtop);
+        const uint32_t h = mmer_hash(mf < mr ? mf : mr);
+        blk_cur[(uint32_t)pib * rs] = h;
         pmin = h < pmin ? h : pmin;
-        const uint32_t j = e + 1 - (uint32_t)m;
         if (j + 1 >= (uint32_t)w) {
             // k-mer i = j - w + 1 is complete: its m-mers are i .. j
             const uint32_t i = j + 1 - (uint32_t)w;
             uint32_t hmin = pmin;
-            if (pib != w - 1) {
-                // window starts inside the previous block at offset pib + 1
-                uint32_t s = ring[((blk ^ 1u) * (uint32_t)w + (uint32_t)pib + 1u) * rs];
-                hmin = s < hmin ? s : hmin;
+            if (pib != w - 1) {  // window starts inside the previous block at offset pib + 1
+                const uint32_t sfx = blk_prev[(uint32_t)(pib + 1) * rs];
+                hmin = sfx < hmin ? sfx : hmin;
             }
-            const uint32_t bin = bin_of_minimizer(hmin, P.n_bins);
-            if (!in_run) { in_run = true; run_bin = bin; run_start = i; }
-            else if (bin != run_bin || i - run_start == P.max_nk) {
-                emit(run_bin, run_start, i - run_start);
-                run_bin = bin; run_start = i;
+            if (i == 0) {
+                prev_h = hmin; run_bin = bin_of_minimizer(hmin, P.n_bins);
+            } else {
+                uint32_t bin = run_bin;
+                if (hmin != prev_h) { prev_h = hmin; bin = bin_of_minimizer(hmin, P.n_bins); }  // same minimiser, same bin
+                if (bin != run_bin || i - run_start == P.max_nk) {
+                    emit(run_bin, run_start, i - run_start);
+                    run_bin = bin; run_start = i;
+                }
             }
         }
         if (++pib == w) {
-            // block finished: turn its h values into suffix minima, start the next block
+            // block finished: turn its h values into suffix minima, swap the two halves of the ring
             uint32_t sm = 0xffffffffu;
             for (int t = w - 1; t >= 0; t--) {
-                uint32_t idx = (blk * (uint32_t)w + (uint32_t)t) * rs;
-                uint32_t x = ring[idx];
+                const uint32_t x = blk_cur[(uint32_t)t * rs];
                 sm = x < sm ? x : sm;
-                ring[idx] = sm;
+                blk_cur[(uint32_t)t * rs] = sm;
             }
-            blk ^= 1u; pib = 0; pmin = 0xffffffffu;
+            uint32_t* tmp = blk_cur; blk_cur = blk_prev; blk_prev = tmp;
+            pib = 0; pmin = 0xffffffffu;
         }
     }
-    if (in_run) emit(run_bin, run_start, len - (uint32_t)k + 1u - run_start);
+    emit(run_bin, run_start, len - (uint32_t)k + 1u - run_start);
 }
 
 // Bin of a record = bin of its first k-mer (every k-mer of a record shares it).  Used by the receiving
@@ -254,7 +271,7 @@ template <int RECW> RFX_HD uint32_t rec_first_bin(const uint64_t* rec, const Bin
         mf = ((mf << 2) | v) & mmask;
         mr = (mr >> 2) | ((v ^ 3u) << mtop);
         if (t + 1 >= m) {
-            const uint32_t h = fmix32(mf < mr ? mf : mr);
+            const uint32_t h = mmer_hash(mf < mr ? mf : mr);
             hmin = h < hmin ? h : hmin;
         }
     }

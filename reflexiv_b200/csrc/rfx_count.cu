@@ -35,38 +35,40 @@ struct CountArgs {
 // ---------------------------------------------------------------------------------------------
 // k <= 31
 // ---------------------------------------------------------------------------------------------
-template <int CAP> struct InsertNarrow {
-    unsigned long long* keys;
-    uint32_t* cnts;
-    uint32_t* n_distinct;
-    volatile uint32_t* overflow;
-    uint32_t cls_mask, cls_val;
-    RFX_HD void operator()(uint64_t key) const {
-#if defined(__CUDA_ARCH__)
-        const uint64_t h = key_hash(key);
-        if (((uint32_t)(h >> 40) & cls_mask) != cls_val) return;
-        uint32_t slot = (uint32_t)h & (CAP - 1);
-        for (int probe = 0; probe < CAP; probe++) {
-            unsigned long long cur = keys[slot];
-            if (cur != key) {
-                if (cur != ~0ull) { slot = (slot + 1) & (CAP - 1); continue; }
-                cur = atomicCAS(&keys[slot], ~0ull, (unsigned long long)key);
-                if (cur == ~0ull) {
-                    if (atomicAdd(n_distinct, 1u) >= (uint32_t)(CAP * 3 / 4)) *overflow = 1u;
-                } else if (cur != key) { slot = (slot + 1) & (CAP - 1); continue; }
-            }
-            atomicAdd(&cnts[slot], 1u);
-            return;
-        }
-        *overflow = 1u;
-#else
-        (void)key;
-#endif
-    }
-};
+// Cheap 2 x 32-bit mix of a <= 62-bit key: slot bits from `h`, sub-class bits from an independent second product.
+__device__ __forceinline__ uint32_t narrow_hash(uint64_t key) {
+    uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+__device__ __forceinline__ uint32_t narrow_class(uint64_t key, uint32_t h) { return ((h ^ (uint32_t)(key >> 32)) * 0x27D4EB2Fu) >> 8; }
 
+template <int CAP>
+__device__ __forceinline__ void insert_narrow(unsigned long long* keys, uint32_t* cnts, uint32_t* n_distinct, volatile uint32_t* overflow,
+                                              uint64_t key, uint32_t h) {
+    uint32_t slot = h & (CAP - 1);
+    for (int probe = 0; probe < CAP; probe++) {
+        unsigned long long cur = keys[slot];
+        if (cur != key) {
+            if (cur != ~0ull) { slot = (slot + 1) & (CAP - 1); continue; }
+            cur = atomicCAS(&keys[slot], ~0ull, (unsigned long long)key);
+            if (cur == ~0ull) {
+                if (atomicAdd(n_distinct, 1u) >= (uint32_t)(CAP * 3 / 4)) *overflow = 1u;
+            } else if (cur != key) { slot = (slot + 1) & (CAP - 1); continue; }
+        }
+        atomicAdd(&cnts[slot], 1u);
+        return;
+    }
+    *overflow = 1u;
+}
+
+// A warp takes 32 records at a time (one coalesced 16-byte load per lane), prefix-sums their k-mer counts and then
+// walks the flattened (record, k-mer) space 32 k-mers per step: every lane finds its source record with a 5-step
+// shuffle binary search, fetches the record words by shuffle and cuts its k-mer straight out of the 2-bit stream
+// (no per-base rolling through the k-1 leading bases, all lanes busy whatever the record lengths are).
 template <int RECW, int CAP>
 __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArgs A) {
+    static_assert(RECW == 2, "k <= 31 uses 16-byte records");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     uint32_t* cnts = reinterpret_cast<uint32_t*>(keys + CAP);
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
     __shared__ uint32_t s_warp_tot[CNT_THREADS / 32];
     __shared__ unsigned long long s_out_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = A.k;
+    const int kshift = 64 - 2 * k;
 
     for (uint32_t bin = blockIdx.x; bin < A.n_bins; bin += gridDim.x) {
         const uint64_t beg = A.bin_off[bin], end = A.bin_off[bin + 1];
@@ -89,23 +93,52 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; }
             for (int i = tid; i < CAP; i += CNT_THREADS) { keys[i] = ~0ull; cnts[i] = 0; }
             __syncthreads();
-            InsertNarrow<CAP> ins{keys, cnts, &s_distinct, &s_overflow, (1u << depth) - 1u, cval};
-            for (uint64_t r = beg + tid; r < end; r += CNT_THREADS) {
-                if (*(volatile uint32_t*)&s_overflow) break;
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
-                uint64_t rec[RECW];
-                rec[0] = v.x; rec[1] = v.y;
-                rec_foreach_kmer<uint64_t, RECW>(rec, A.k, ins);
+            const uint32_t cshift = 24u - depth;  // class = top `depth` bits of a 24-bit second hash
+            for (uint64_t base = beg + (uint64_t)warp * 32; base < end; base += CNT_THREADS) {
+                if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
+                const uint64_t r = base + lane;
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                if (r < end) v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
+                const uint32_t nk = (uint32_t)(v.x >> 48);
+                uint32_t pi = nk;  // inclusive prefix of k-mer counts over the warp's 32 records
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
+                const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
+                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                    const uint32_t t = t0 + lane;
+                    uint32_t s = 0;  // number of records whose inclusive prefix is <= t  ==  source record of k-mer t
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
+                        if (pv <= t) s += step;
+                    }
+                    s &= 31;
+                    const uint64_t w0 = __shfl_sync(0xffffffffu, v.x, s), w1 = __shfl_sync(0xffffffffu, v.y, s);
+                    const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
+                    if (t < total) {
+                        const uint32_t off = t - (pis - (uint32_t)(w0 >> 48));  // k-mer index inside the record
+                        const uint32_t b = 16u + 2u * off;                      // first bit of the k-mer in the 128-bit stream
+                        uint64_t hi;
+                        if (b < 64u) hi = (w0 << b) | (w1 >> (64u - b));
+                        else hi = w1 << (b - 64u);
+                        const uint64_t fwd = hi >> kshift;
+                        const uint64_t rc = revcomp(fwd, k);
+                        const uint64_t key = fwd < rc ? fwd : rc;
+                        const uint32_t h = narrow_hash(key);
+                        if (depth == 0 || (narrow_class(key, h) >> cshift) == cval)
+                            insert_narrow<CAP>(keys, cnts, &s_distinct, &s_overflow, key, h);
+                    }
+                }
             }
             __syncthreads();
             if (s_overflow) {
                 // too many distinct k-mers for the table: split this class in two by the next hash bit
                 if (tid == 0) {
-                    if (depth >= 24 || s_sp + 2 > CNT_STACK) {
+                    if (depth >= 22 || s_sp + 2 > CNT_STACK) {
                         atomicExch(&A.dstat[DS_OVERFLOW], 2ull);
                     } else {
-                        s_stack_val[s_sp] = cval; s_stack_depth[s_sp] = depth + 1; s_sp++;
-                        s_stack_val[s_sp] = cval | (1u << depth); s_stack_depth[s_sp] = depth + 1; s_sp++;
+                        s_stack_val[s_sp] = cval << 1; s_stack_depth[s_sp] = depth + 1; s_sp++;
+                        s_stack_val[s_sp] = (cval << 1) | 1u; s_stack_depth[s_sp] = depth + 1; s_sp++;
                         atomicAdd(&A.dstat[DS_SPLITS], 1ull);
                     }
                 }

@@ -253,7 +253,7 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* s
     RFX_CUDA(c, cudaStreamSynchronize(st));
     const uint64_t n_new = tot.a, w_new = tot.b;
     if (n_new == 0) return RFX_OK;
-    DevBuf rd_src;
+    DevBuf& rd_src = c->rd_src;
     RFX_TRY(devbuf_reserve(c, rd_src, n_new * sizeof(uint64_t)));
     int rc = RFX_OK;
     do {
@@ -262,7 +262,7 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* s
         if ((rc = devbuf_reserve(c, c->packed, (c->n_words + w_new + 8) * sizeof(uint64_t), true)) != RFX_OK) break;
         ReadOut out{L, c->n_reads, c->n_words, c->prm.front_clip, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
         scan_apply(plan, in, out, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
-        encode_reads_kernel<<<grid_for(n_new * 32, 256, 148 * 8), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
+        encode_reads_kernel<<<grid_for(n_new * 32, 256, 148 * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
                                                                                 c->rd_woff.as<uint64_t>(), n_new, c->n_reads,
                                                                                 c->packed.as<uint64_t>());
         // padding words after the last read: packed_window() may look one word ahead
@@ -275,7 +275,6 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* s
         c->n_bases += tot.c;
         c->n_instances += tot.d;
     } while (0);
-    devbuf_free(rd_src);
     return rc;
 }
 

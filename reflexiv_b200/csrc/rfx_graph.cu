@@ -151,30 +151,34 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
 }
 
 // ---- K6: pointer jumping towards the head ------------------------------------------------------
-__global__ void rank_init_kernel(uint64_t n, const uint32_t* __restrict__ pred, uint32_t* __restrict__ anc, uint32_t* __restrict__ dist) {
+// One 64-bit word per node: low half = current ancestor, high half = distance to it, so a jump costs one random
+// 8-byte read.  Double buffered (Jacobi), so every round is deterministic.
+__device__ __forceinline__ uint64_t ad_pack(uint32_t anc, uint32_t dist) { return (uint64_t)anc | ((uint64_t)dist << 32); }
+
+__global__ void rank_init_kernel(uint64_t n, const uint32_t* __restrict__ pred, uint64_t* __restrict__ ad) {
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t p = pred[x];
-        anc[x] = p == NONE32 ? (uint32_t)x : p;
-        dist[x] = p == NONE32 ? 0u : 1u;
+        ad[x] = p == NONE32 ? ad_pack((uint32_t)x, 0u) : ad_pack(p, 1u);
     }
 }
-__global__ void rank_step_kernel(uint64_t n, const uint32_t* __restrict__ anc_in, const uint32_t* __restrict__ dist_in,
-                                 uint32_t* __restrict__ anc_out, uint32_t* __restrict__ dist_out, unsigned long long* dstat) {
+__global__ void rank_step_kernel(uint64_t n, const uint64_t* __restrict__ ad_in, uint64_t* __restrict__ ad_out, unsigned long long* dstat) {
     bool changed = false;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = anc_in[x];
-        const uint32_t aa = anc_in[a];
-        dist_out[x] = dist_in[x] + (a == (uint32_t)x ? 0u : dist_in[a]);
-        anc_out[x] = aa;
+        const uint64_t mine = ad_in[x];
+        const uint32_t a = (uint32_t)mine;
+        if (a == (uint32_t)x) { ad_out[x] = mine; continue; }
+        const uint64_t up = ad_in[a];
+        const uint32_t aa = (uint32_t)up;
+        ad_out[x] = ad_pack(aa, (uint32_t)(mine >> 32) + (uint32_t)(up >> 32));
         changed |= (aa != a);
     }
     if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_CHANGED], 1ull);
 }
 // nodes whose final ancestor is not a true head (pred == NONE) sit on a cycle
-__global__ void cycle_mark_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint32_t* __restrict__ anc,
+__global__ void cycle_mark_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint64_t* __restrict__ ad,
                                   uint32_t* __restrict__ lab, uint32_t* __restrict__ ptr, unsigned long long* dstat) {
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
-        const bool cyc = (alive[x] & 2) && pred[x] != NONE32 && pred[anc[x]] != NONE32;
+        const bool cyc = (alive[x] & 2) && pred[x] != NONE32 && pred[(uint32_t)ad[x]] != NONE32;
         lab[x] = cyc ? (uint32_t)x : NONE32;
         ptr[x] = cyc ? pred[x] : NONE32;
         if (cyc) atomicAdd(&dstat[DS_CYCLE_NODES], 1ull);
@@ -204,24 +208,25 @@ __global__ void cycle_cut_kernel(uint64_t n, const uint32_t* __restrict__ lab, u
     }
 }
 
-__global__ void tails_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ succ, const uint32_t* __restrict__ anc,
-                             const uint32_t* __restrict__ dist, uint32_t* __restrict__ chain_len, uint32_t* __restrict__ tail_of) {
+__global__ void tails_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ succ, const uint64_t* __restrict__ ad,
+                             uint32_t* __restrict__ chain_len, uint32_t* __restrict__ tail_of) {
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         if ((alive[x] & 2) && succ[x] == NONE32) {
-            const uint32_t h = anc[x];
-            chain_len[h] = dist[x] + 1u;
+            const uint64_t v = ad[x];
+            const uint32_t h = (uint32_t)v;
+            chain_len[h] = (uint32_t)(v >> 32) + 1u;
             tail_of[h] = (uint32_t)x;
         }
     }
 }
 
 __global__ void budget_admissible_kernel(uint64_t n, const uint32_t* __restrict__ open_next, const int32_t* __restrict__ lflag,
-                                         const int32_t* __restrict__ rflag, const uint32_t* __restrict__ dist, const uint32_t* __restrict__ chain_len,
+                                         const int32_t* __restrict__ rflag, const uint64_t* __restrict__ ad, const uint32_t* __restrict__ chain_len,
                                          unsigned long long* dstat) {
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t y = open_next[x];
         if (y == NONE32) continue;
-        const int64_t r_ext = (int64_t)dist[x] + 1, f_ext = (int64_t)chain_len[y];
+        const int64_t r_ext = (int64_t)(ad[x] >> 32) + 1, f_ext = (int64_t)chain_len[y];
         if ((lflag[y] >= 0 && lflag[y] - r_ext >= 0) || (rflag[x] >= 0 && rflag[x] - f_ext >= 0)) atomicAdd(&dstat[DS_BUDGET_ADM], 1ull);
     }
 }
@@ -263,17 +268,18 @@ struct ContigOut {
 };
 
 template <class KT>
-__global__ void gather_contigs_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ anc, const uint32_t* __restrict__ dist,
+__global__ void gather_contigs_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const uint64_t* __restrict__ ad,
                                       const uint32_t* __restrict__ ctg_idx, const uint64_t* __restrict__ ctg_off, char* __restrict__ out) {
     const uint64_t n = 2 * G.n_rows;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         if (!(alive[x] & 2)) continue;
-        const uint32_t h = anc[x];
+        const uint64_t v = ad[x];
+        const uint32_t h = (uint32_t)v;
         const uint32_t ci = ctg_idx[h];
         if (ci == NONE32) continue;
         const KT X = G.oriented((uint32_t)x);
         char* dst = out + ctg_off[ci];
-        dst[(uint64_t)(G.k - 1) + dist[x]] = "ACGT"[(uint32_t)X & 3u];
+        dst[(uint64_t)(G.k - 1) + (uint32_t)(v >> 32)] = "ACGT"[(uint32_t)X & 3u];
         if (h == (uint32_t)x)
             for (int j = 0; j < G.k - 1; j++) dst[j] = "ACGT"[(uint32_t)(X >> (2 * (G.k - 1 - j))) & 3u];
     }
@@ -314,13 +320,10 @@ template <class KT> static int graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->succ, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->pred, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->tail_of, n * sizeof(uint32_t)));  // doubles as open_next until the tails pass
-    for (int i = 0; i < 2; i++) {
-        RFX_TRY(devbuf_reserve(c, c->anc[i], n * sizeof(uint32_t)));
-        RFX_TRY(devbuf_reserve(c, c->dist[i], n * sizeof(uint32_t)));
-    }
+    for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, c->ad[i], n * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->chain_len, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_idx, n * sizeof(uint32_t)));
-    DevBuf open_next;  // separate from tail_of: both are live in the admissibility pass
+    DevBuf& open_next = c->open_next;  // separate from tail_of: both are live in the admissibility pass
     RFX_TRY(devbuf_reserve(c, open_next, n * sizeof(uint32_t)));
     int rc = RFX_OK;
     do {
@@ -357,14 +360,16 @@ template <class KT> static int graph_impl(Ctx* c) {
         int cur = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             cur = 0;
-            rank_init_kernel<<<grid_n(n), 256, 0, st>>>(n, pred, c->anc[0].as<uint32_t>(), c->dist[0].as<uint32_t>());
+            rank_init_kernel<<<grid_n(n), 256, 0, st>>>(n, pred, c->ad[0].as<uint64_t>());
             c->launches++;
-            for (int round = 0; round < limit; round++) {
+            // the host looks at the "changed" flag only every 4 rounds (extra rounds are idempotent)
+            for (int round = 0; round < limit;) {
                 cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st);
-                rank_step_kernel<<<grid_n(n), 256, 0, st>>>(n, c->anc[cur].as<uint32_t>(), c->dist[cur].as<uint32_t>(), c->anc[cur ^ 1].as<uint32_t>(),
-                                                            c->dist[cur ^ 1].as<uint32_t>(), dstat);
-                c->launches++;
-                cur ^= 1;
+                for (int q = 0; q < 4 && round < limit; q++, round++) {
+                    rank_step_kernel<<<grid_n(n), 256, 0, st>>>(n, c->ad[cur].as<uint64_t>(), c->ad[cur ^ 1].as<uint64_t>(), dstat);
+                    c->launches++;
+                    cur ^= 1;
+                }
                 uint64_t changed = 0;
                 cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
                 e = cudaStreamSynchronize(st);
@@ -379,7 +384,7 @@ template <class KT> static int graph_impl(Ctx* c) {
             uint32_t* lab[2] = {c->cmin[0].as<uint32_t>(), c->cmin[1].as<uint32_t>()};
             uint32_t* ptr[2] = {lab[0] + n, lab[1] + n};
             cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st);
-            cycle_mark_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, c->anc[cur].as<uint32_t>(), lab[0], ptr[0], dstat);
+            cycle_mark_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, c->ad[cur].as<uint64_t>(), lab[0], ptr[0], dstat);
             c->launches++;
             uint64_t cyc_nodes = 0;
             cudaMemcpyAsync(&cyc_nodes, dstat + DS_CYCLE_NODES, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
@@ -395,10 +400,9 @@ template <class KT> static int graph_impl(Ctx* c) {
             c->launches++;
         }
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "list ranking failed: %s", cudaGetErrorString(e)); break; }
-        uint32_t* anc = c->anc[cur].as<uint32_t>();
-        uint32_t* dist = c->dist[cur].as<uint32_t>();
-        tails_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, succ, anc, dist, c->chain_len.as<uint32_t>(), c->tail_of.as<uint32_t>());
-        budget_admissible_kernel<<<grid_n(n), 256, 0, st>>>(n, open_next.as<uint32_t>(), lflag, rflag, dist, c->chain_len.as<uint32_t>(), dstat);
+        const uint64_t* ad = c->ad[cur].as<uint64_t>();
+        tails_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, succ, ad, c->chain_len.as<uint32_t>(), c->tail_of.as<uint32_t>());
+        budget_admissible_kernel<<<grid_n(n), 256, 0, st>>>(n, open_next.as<uint32_t>(), lflag, rflag, ad, c->chain_len.as<uint32_t>(), dstat);
         c->launches += 2;
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "chain kernels failed: %s", cudaGetErrorString(e)); break; }
@@ -425,7 +429,7 @@ template <class KT> static int graph_impl(Ctx* c) {
                       c->ctg_right.as<int32_t>()};
         scan_apply(plan, in, out, OpAddU64x3{}, U64x3{0, 0, 0}, st);
         set_u64_kernel<<<1, 1, 0, st>>>(c->ctg_off.as<uint64_t>() + tot.a, plan.total);
-        gather_contigs_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, anc, dist, c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>());
+        gather_contigs_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, ad, c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>());
         c->launches += 3;
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "contig gather failed: %s", cudaGetErrorString(e)); break; }
@@ -437,7 +441,6 @@ template <class KT> static int graph_impl(Ctx* c) {
         c->n_cycles = h[DS_CYCLES];
         c->have_contigs = true;
     } while (0);
-    devbuf_free(open_next);
     return rc;
 }
 

@@ -58,6 +58,7 @@ struct Ctx {
     DevBuf line_start;  // u64[n_lines + 1]
     DevBuf seq_flag;    // u8[n_lines]
     DevBuf scan_ws;     // scan workspace
+    DevBuf rd_src;      // u64[new reads] text offset of each read of the current push (scratch)
     DevBuf rd_len;      // u32[n_reads]   effective length (0 = contributes nothing)
     DevBuf rd_woff;     // u64[n_reads]   first word in `packed`
     DevBuf packed;      // u64[n_words + pad]
@@ -67,6 +68,8 @@ struct Ctx {
     DevBuf bin_off;     // u64[n_bins + 1]
     DevBuf bin_cursor;  // u64[n_bins]
     DevBuf records;     // u64[n_records * recw]
+    DevBuf run_desc;    // u32[slots][n_reads]  (bin << 8 | n_kmers) per run, read-interleaved
+    DevBuf rd_runs;     // u32[n_reads] runs per read
     uint32_t n_bins = 0;
     int32_t n_shards = 1;
     uint64_t n_records = 0;
@@ -90,7 +93,8 @@ struct Ctx {
     DevBuf rflag, lflag;  // i32[2*n_rows]
     DevBuf alive;         // u8[2*n_rows]  bit0: survives right filter, bit1: survives both
     DevBuf succ, pred;    // u32[2*n_rows]
-    DevBuf anc[2], dist[2];
+    DevBuf ad[2];         // u64[2*n_rows] packed (ancestor, distance) for pointer jumping, double buffered
+    DevBuf open_next;     // u32[2*n_rows] successor across a junction that stays open
     DevBuf cmin[2];
     DevBuf chain_len;     // u32[2*n_rows] at heads
     DevBuf tail_of;       // u32[2*n_rows] at heads
@@ -121,6 +125,7 @@ enum {
     DS_CYCLE_NODES = 9,
     DS_CYCLES = 10,
     DS_ORIENTED = 11,
+    DS_SPILL = 12,
     DS_NSLOTS = 16
 };
 

@@ -19,40 +19,127 @@ namespace rfx {
 
 constexpr int PART_THREADS = 128;
 
-// what a thread does with each run of k-mers that share a bin
-template <int RECW, bool SCATTER> struct EmitRecord {
-    const uint64_t* rd;
-    unsigned long long* bin_cursor;
-    uint64_t* records;
-    RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) const {
+// Pass 1 (the only pass that walks the bases): every run of k-mers that share a bin becomes one 32-bit descriptor
+// (bin << 8 | n_kmers) plus a 16-bit start position, both in read-interleaved arrays (slot i of read r at
+// [i * stride + r]: coalesced across the reads of a warp), and bumps its bin's record count.  A read with more runs
+// than descriptor slots (or longer than 65535 k-mers) only counts its extra runs (spill_cnt); pass 2 re-scans such reads.
+struct EmitDesc {
+    uint32_t* desc;  // already offset by the read index
+    uint16_t* pos;   // same layout: first k-mer of the run
+    uint64_t stride;
+    uint32_t max_slots;
+    uint32_t* bin_cnt;
+    uint32_t* spill_cnt;
+    uint32_t n;        // runs seen
+    uint32_t stored;   // runs that got a descriptor (always a prefix of the read's runs)
+    RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
 #if defined(__CUDA_ARCH__)
-        const unsigned long long slot = atomicAdd(&bin_cursor[bin], 1ull);
-        if (SCATTER) {
-            uint64_t rec[RECW];
-            rec_build<RECW>(rd, first_kmer, n_k, rec);
-            uint64_t* dst = records + slot * RECW;
-#pragma unroll
-            for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(rec[i], rec[i + 1]);
+        if (n < max_slots && first_kmer < 65536u) {
+            atomicAdd(&bin_cnt[bin], 1u);  // result unused: compiles to a fire-and-forget RED
+            desc[(uint64_t)n * stride] = (bin << 8) | n_k;
+            pos[(uint64_t)n * stride] = (uint16_t)first_kmer;
+            stored++;
+        } else {
+            atomicAdd(&spill_cnt[bin], 1u);
         }
+        n++;
 #else
         (void)bin; (void)first_kmer; (void)n_k;
 #endif
     }
 };
 
-template <int RECW, bool SCATTER>
 __global__ void __launch_bounds__(PART_THREADS)
-    partition_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff,
-                     uint64_t n_reads, BinParams P, unsigned long long* __restrict__ bin_cursor, uint64_t* __restrict__ records) {
+    bin_scan_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
+                    BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
+                    uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
     extern __shared__ uint32_t ring_smem[];  // [2*w][PART_THREADS]
     uint32_t* ring = ring_smem + threadIdx.x;
     for (uint64_t r = (uint64_t)blockIdx.x * PART_THREADS + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * PART_THREADS) {
         const uint32_t len = rd_len[r];
-        if (len < (uint32_t)P.k) continue;
-        const uint64_t* rd = packed + rd_woff[r];
-        bin_scan_read(rd, len, P, ring, (uint32_t)PART_THREADS, EmitRecord<RECW, SCATTER>{rd, bin_cursor, records});
+        EmitDesc em{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u};
+        if (len >= (uint32_t)P.k) bin_scan_read(packed + rd_woff[r], len, P, ring, (uint32_t)PART_THREADS, em);
+        const bool spill = em.n > em.stored;
+        rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
+        if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
     }
 }
+
+// re-scan of a read with more runs than descriptor slots: runs [max_slots, n) go behind the ranked records of their bin
+template <int RECW> struct EmitSpill {
+    const uint64_t* rd;
+    const uint64_t* bin_off;
+    const uint32_t* bin_cnt;
+    uint32_t* spill_cur;
+    uint64_t* records;
+    uint32_t max_slots;
+    uint32_t n;
+    RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
+#if defined(__CUDA_ARCH__)
+        const bool stored = n < max_slots && first_kmer < 65536u;  // same test as pass 1
+        n++;
+        if (stored) return;
+        const uint64_t slot = bin_off[bin] + bin_cnt[bin] + atomicAdd(&spill_cur[bin], 1u);
+        uint64_t rec[RECW];
+        rec_build<RECW>(rd, first_kmer, n_k, rec);
+        uint64_t* dst = records + slot * RECW;
+#pragma unroll
+        for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(rec[i], rec[i + 1]);
+#else
+        (void)bin; (void)first_kmer; (void)n_k;
+#endif
+    }
+};
+
+// Pass 2: per-record work only.  One thread per descriptor slot (reads x slots threads, so tens of millions of
+// independent atomics + 16/32-byte stores are in flight): claim a place in the bin, cut the record out of the read.
+template <int RECW>
+__global__ void __launch_bounds__(256)
+    emit_records_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ rd_woff, uint64_t n_reads, const uint64_t* __restrict__ bin_off,
+                        uint32_t* __restrict__ cursor, const uint32_t* __restrict__ desc, const uint16_t* __restrict__ pos, uint64_t stride,
+                        uint32_t max_slots, const uint32_t* __restrict__ rd_runs, uint64_t* __restrict__ records) {
+    const uint64_t total = (uint64_t)max_slots * stride;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = idx % stride;
+        const uint32_t i = (uint32_t)(idx / stride);
+        if (r >= n_reads || i >= (rd_runs[r] & 0x7fffffffu)) continue;
+        const uint32_t d = desc[idx];
+        const uint32_t first = pos[idx];
+        const uint32_t bin = d >> 8;
+        const uint64_t slot = bin_off[bin] + atomicAdd(&cursor[bin], 1u);
+        uint64_t rec[RECW];
+        rec_build<RECW>(packed + rd_woff[r], first, d & 255u, rec);
+        uint64_t* dst = records + slot * RECW;
+#pragma unroll
+        for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec[q], rec[q + 1]);
+    }
+}
+
+// reads that did not fit their descriptor slots: re-scan, emit the runs pass 1 could not store
+template <int RECW>
+__global__ void __launch_bounds__(PART_THREADS)
+    emit_spill_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
+                      BinParams P, const uint64_t* __restrict__ bin_off, const uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cur,
+                      uint32_t max_slots, const uint32_t* __restrict__ rd_runs, uint64_t* __restrict__ records) {
+    extern __shared__ uint32_t ring_smem[];
+    for (uint64_t r = (uint64_t)blockIdx.x * PART_THREADS + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * PART_THREADS) {
+        if (!(rd_runs[r] >> 31)) continue;
+        const uint32_t len = rd_len[r];
+        const uint64_t* rd = packed + rd_woff[r];
+        EmitSpill<RECW> sp{rd, bin_off, bin_cnt, spill_cur, records, max_slots, 0u};
+        bin_scan_read(rd, len, P, ring_smem + threadIdx.x, (uint32_t)PART_THREADS, sp);
+    }
+}
+
+struct BinCount2In {
+    const uint32_t* cnt;
+    const uint32_t* spill;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)cnt[i] + spill[i]; }
+};
+struct BinOffset2Out {
+    uint64_t* off;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t excl, uint64_t) const { off[i] = excl; }
+};
 
 // bin ids are laid out shard-major: bin b belongs to shard b / bins_per_shard, so every shard's
 // records are one contiguous slice of the record array (what the all-to-all sends).
@@ -91,48 +178,77 @@ int stage_partition(Ctx* c, int n_shards) {
     if (c->n_bins % (uint32_t)n_shards) return ctx_fail(c, RFX_E_INVALID, "n_bins_total %u is not a multiple of n_shards %d", c->n_bins, n_shards);
     BinParams P;
     P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
-    RFX_TRY(devbuf_reserve(c, c->bin_off, ((size_t)c->n_bins + 1) * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, c->bin_cursor, (size_t)c->n_bins * sizeof(uint64_t)));
-    RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, (size_t)c->n_bins * sizeof(uint64_t), st));
+    // descriptor slots per read: twice the expected number of runs (a run is about (w+1)/2 k-mers), 8..64
+    const uint64_t avg_nk = c->n_reads ? c->n_instances / c->n_reads : 0;
+    uint64_t slots = 2 * (avg_nk / (uint64_t)((P.w + 1) / 2 + 1) + 1) + 4;
+    if (slots < 8) slots = 8;
+    if (slots > 64) slots = 64;
+    const uint64_t stride = (c->n_reads + 31) & ~(uint64_t)31;
+    const size_t nb = c->n_bins;
+    RFX_TRY(devbuf_reserve(c, c->bin_off, (nb + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->bin_cursor, nb * 4 * sizeof(uint32_t)));  // ranked count | spill count | cursor | spill cursor
+    RFX_TRY(devbuf_reserve(c, c->run_desc, (size_t)(slots * stride + 64) * (sizeof(uint32_t) + sizeof(uint16_t))));
+    RFX_TRY(devbuf_reserve(c, c->rd_runs, (size_t)(c->n_reads + 1) * sizeof(uint32_t)));
+    RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, nb * 4 * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_SPILL, 0, sizeof(uint64_t), st));
+    uint32_t* bin_cnt = c->bin_cursor.as<uint32_t>();
+    uint32_t* spill_cnt = bin_cnt + nb;
+    uint32_t* cursor = spill_cnt + nb;
+    uint32_t* spill_cur = cursor + nb;
+    uint32_t* desc = c->run_desc.as<uint32_t>();
+    uint16_t* pos = reinterpret_cast<uint16_t*>(desc + slots * stride + 32);
     const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);
     unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
     if (grid < 1) grid = 1;
-    if (grid > 148u * 32u) grid = 148u * 32u;
-    auto* cursor = c->bin_cursor.as<unsigned long long>();
+    if (grid > 148u * 64u) grid = 148u * 64u;
     if (c->n_reads) {
+        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaEventRecord(c->evk[0], st);
-        if (c->recw == 2) {
-            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            partition_kernel<2, false><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, nullptr);
-        } else {
-            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RFX_CUDA(c, cudaFuncSetAttribute(partition_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            partition_kernel<4, false><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, nullptr);
-        }
+        bin_scan_kernel<<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, bin_cnt,
+                                                          spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                          c->dstat.as<unsigned long long>());
         cudaEventRecord(c->evk[1], st);
         c->launches++;
     }
-    // exclusive scan of the per-bin record counts -> bin offsets (+ scatter cursors)
+    // exclusive scan of the per-bin record counts -> bin offsets
     ScanPlan<uint64_t> plan;
     RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(c->n_bins) * sizeof(uint64_t)));
     plan.bind(c->n_bins, c->scan_ws.as<uint64_t>());
-    scan_prepare(plan, BinCountIn{cursor}, OpAddU64{}, (uint64_t)0, st);
-    uint64_t n_records = 0;
+    scan_prepare(plan, BinCount2In{bin_cnt, spill_cnt}, OpAddU64{}, (uint64_t)0, st);
+    uint64_t n_records = 0, spill = 0;
     RFX_CUDA(c, cudaMemcpyAsync(&n_records, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaMemcpyAsync(&spill, c->dstat.as<uint64_t>() + DS_SPILL, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     RFX_CUDA(c, cudaStreamSynchronize(st));
-    scan_apply(plan, BinCountIn{cursor}, BinOffsetOut{c->bin_off.as<uint64_t>(), cursor}, OpAddU64{}, (uint64_t)0, st);
+    scan_apply(plan, BinCount2In{bin_cnt, spill_cnt}, BinOffset2Out{c->bin_off.as<uint64_t>()}, OpAddU64{}, (uint64_t)0, st);
     set_last_offset_kernel<<<1, 1, 0, st>>>(c->bin_off.as<uint64_t>(), c->n_bins, plan.total);
     c->launches += 2 * plan.levels + 2;
     RFX_TRY(devbuf_reserve(c, c->records, (n_records * c->recw + 2) * sizeof(uint64_t)));
     if (c->n_reads && n_records) {
+        const uint64_t total = slots * stride;
+        unsigned g2 = (unsigned)((total + 255) / 256 > 148u * 256u ? 148u * 256u : (total + 255) / 256);
         cudaEventRecord(c->evk[2], st);
         if (c->recw == 2)
-            partition_kernel<2, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
+            emit_records_kernel<2><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
+                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>());
         else
-            partition_kernel<4, true><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, cursor, c->records.as<uint64_t>());
-        cudaEventRecord(c->evk[3], st);
+            emit_records_kernel<4><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
+                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>());
         c->launches++;
+        if (spill) {
+            if (c->recw == 2) {
+                RFX_CUDA(c, cudaFuncSetAttribute(emit_spill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                emit_spill_kernel<2><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
+                                                                       c->bin_off.as<uint64_t>(), bin_cnt, spill_cur, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                                       c->records.as<uint64_t>());
+            } else {
+                RFX_CUDA(c, cudaFuncSetAttribute(emit_spill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                emit_spill_kernel<4><<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
+                                                                       c->bin_off.as<uint64_t>(), bin_cnt, spill_cur, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                                       c->records.as<uint64_t>());
+            }
+            c->launches++;
+        }
+        cudaEventRecord(c->evk[3], st);
     }
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "partition failed: %s", cudaGetErrorString(e));

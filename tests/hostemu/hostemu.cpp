@@ -121,7 +121,7 @@ int64_t emu_bins_bruteforce(const uint64_t* rd, uint32_t len, int k, int m, uint
             uint32_t mf = 0;
             for (int t = 0; t < m; t++) mf = ((mf << 2) | packed_base(rd, j + t)) & mmask;
             uint32_t mr = (uint32_t)revcomp((uint64_t)mf, m);
-            uint32_t h = fmix32(mf < mr ? mf : mr);
+            uint32_t h = mmer_hash(mf < mr ? mf : mr);
             hmin = h < hmin ? h : hmin;
         }
         out[i] = bin_of_minimizer(hmin, n_bins);

@@ -172,13 +172,30 @@ def test_bin_overflow_splitting_is_exact(R, orc):
         g_ints, g_counts = _sorted_table(R, ctx, 31)
     assert st["n_bin_splits"] > 0
     assert g_ints == ints and np.array_equal(g_counts, counts)
-    txt = make_reads(22, 200_000, 1500, read_len=150, err=0.0, frag=400)
+    txt = make_reads(22, 400_000, 4000, read_len=150, err=0.0, frag=400)
     ints, counts, c, _ = _oracle_table(orc, txt, 61, orc.FASTQ_RUN)
     with R.ReflexivContext(_param(R, kmerSize=61, minKmerCoverage=1), bin_target_kmers=200_000) as ctx:
         ctx.push_fastq(txt)
         st = ctx.count()
         g_ints, g_counts = _sorted_table(R, ctx, 61)
     assert st["n_bin_splits"] > 0
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
+@pytest.mark.parametrize("k", [31, 61])
+def test_long_and_ragged_reads(R, orc, k):
+    """Reads far longer than the descriptor slots of the binning pass (spill path), mixed with short and empty ones."""
+    rng = np.random.default_rng(9)
+    g = "".join("ACGT"[i] for i in rng.integers(0, 4, 20_000))
+    seqs = [g[a:a + n] for a, n in ((0, 5000), (3000, 4000), (100, k), (200, k + 1), (300, k + 2), (400, 150), (9000, 11000), (0, 0), (5, 3))]
+    seqs += [orc.revcomp_str(g[a:a + 700]) for a in range(0, 19000, 450)]
+    txt = ("\n".join(seqs) + "\n").encode()
+    ints, counts, c, _ = _oracle_table(orc, txt, k, orc.FASTQ_LINE)
+    with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1), fastq_mode=2) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, k)
+    assert st["n_instances"] == c["n_instances"]
     assert g_ints == ints and np.array_equal(g_counts, counts)
 
 
