@@ -114,7 +114,9 @@ int rfx_reset(rfx_ctx* ctx);                     /* forget reads and results, ke
  * `buf` is decompressed FASTQ text in host memory; may be called repeatedly, every call must end on a
  * line boundary and (RFX_FASTQ_RUN) on a record boundary. */
 int rfx_push_fastq(rfx_ctx* ctx, const uint8_t* buf, size_t len);
-/* same, `d_buf` is a CUDA device pointer on the context's device (used when the text is already in HBM) */
+/* same, `d_buf` is a CUDA device pointer on the context's device (used when the text is already in HBM).
+ * The parser reads whole 64-byte aligned chunks: the allocation must extend to the next 64-byte boundary behind
+ * d_buf + len (always true for a cudaMalloc'ed buffer). */
 int rfx_push_fastq_device(rfx_ctx* ctx, const uint8_t* d_buf, size_t len);
 /* already-split reads: ASCII bases, read i = bases[offsets[i] .. offsets[i+1]) (host memory) */
 int rfx_push_reads(rfx_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads);

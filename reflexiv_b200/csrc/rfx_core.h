@@ -114,10 +114,19 @@ RFX_HD int rec_words_for_k(int k) { return k <= 31 ? 2 : 4; }
 RFX_HD int rec_max_bases(int recw) { return (recw * 64 - 16) / 2; }
 RFX_HD int rec_max_kmers(int recw, int k) { return rec_max_bases(recw) - k + 1; }
 
-template <int RECW> RFX_HD void rec_build(const uint64_t* read_words, uint32_t base_pos, uint32_t n_k, uint64_t* out) {
+// `k` is needed to zero the bits behind the last base, so that equal super-k-mers are equal bit patterns
+// (the counting kernel de-duplicates whole records before it touches k-mers).
+template <int RECW> RFX_HD void rec_build(const uint64_t* read_words, uint32_t base_pos, uint32_t n_k, int k, uint64_t* out) {
     out[0] = ((uint64_t)n_k << 48) | (packed_window(read_words, base_pos) >> 16);
 #pragma unroll
     for (int i = 1; i < RECW; i++) out[i] = packed_window(read_words, (uint64_t)base_pos + 32u * i - 8u);
+    const uint32_t used = 16u + 2u * (n_k + (uint32_t)k - 1u);  // header + bases, in bits from the top of word 0
+#pragma unroll
+    for (int i = 0; i < RECW; i++) {
+        const uint32_t lo = 64u * i;
+        if (used <= lo) out[i] = 0;
+        else if (used < lo + 64u) out[i] &= ~0ull << (lo + 64u - used);
+    }
 }
 
 // Visit every canonical k-mer of a record.  Same rolling update as the reference extractor

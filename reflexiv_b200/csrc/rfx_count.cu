@@ -43,9 +43,22 @@ __device__ __forceinline__ uint32_t narrow_hash(uint64_t key) {
 }
 __device__ __forceinline__ uint32_t narrow_class(uint64_t key, uint32_t h) { return ((h ^ (uint32_t)(key >> 32)) * 0x27D4EB2Fu) >> 8; }
 
+// 64-bit hash of a whole 16-byte record, built from 32-bit multiplies.  Only speed depends on its quality: equal
+// hashes are confirmed against the stored record before anything is counted.
+__device__ __forceinline__ uint64_t record_hash(uint64_t w0, uint64_t w1) {
+    const uint32_t a = (uint32_t)w0, b = (uint32_t)(w0 >> 32), c = (uint32_t)w1, d = (uint32_t)(w1 >> 32);
+    uint32_t h1 = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du ^ d * 0x27D4EB2Fu;
+    uint32_t h2 = a * 0x165667B1u ^ b * 0xD3A2646Cu ^ c * 0xFD7046C5u ^ d * 0xB55A4F09u;
+    h1 ^= h1 >> 15; h1 *= 0x2C1B3C6Du; h1 ^= h1 >> 13;
+    h2 ^= h2 >> 16; h2 *= 0x7FEB352Du; h2 ^= h2 >> 15;
+    const uint64_t h = ((uint64_t)h2 << 32) | h1;
+    return h == ~0ull ? 0x5bd1e9955bd1e995ull : h;
+}
+
+// adds `mult` occurrences of one canonical k-mer to the shared-memory table
 template <int CAP>
 __device__ __forceinline__ void insert_narrow(unsigned long long* keys, uint32_t* cnts, uint32_t* n_distinct, volatile uint32_t* overflow,
-                                              uint64_t key, uint32_t h) {
+                                              uint64_t key, uint32_t h, uint32_t mult) {
     uint32_t slot = h & (CAP - 1);
     for (int probe = 0; probe < CAP; probe++) {
         unsigned long long cur = keys[slot];
@@ -56,23 +69,57 @@ __device__ __forceinline__ void insert_narrow(unsigned long long* keys, uint32_t
                 if (atomicAdd(n_distinct, 1u) >= (uint32_t)(CAP * 3 / 4)) *overflow = 1u;
             } else if (cur != key) { slot = (slot + 1) & (CAP - 1); continue; }
         }
-        atomicAdd(&cnts[slot], 1u);
+        atomicAdd(&cnts[slot], mult);
         return;
     }
     *overflow = 1u;
 }
 
-// A warp takes 32 records at a time (one coalesced 16-byte load per lane), prefix-sums their k-mer counts and then
-// walks the flattened (record, k-mer) space 32 k-mers per step: every lane finds its source record with a 5-step
-// shuffle binary search, fetches the record words by shuffle and cuts its k-mer straight out of the 2-bit stream
-// (no per-base rolling through the k-1 leading bases, all lanes busy whatever the record lengths are).
-template <int RECW, int CAP>
+struct NarrowTable {
+    unsigned long long* keys;
+    uint32_t* cnts;
+    uint32_t* n_distinct;
+    volatile uint32_t* overflow;
+    uint32_t depth, cval;
+};
+
+template <int CAP> struct DirectInsert {  // rare path: a record whose 64-bit hash collided with a different record
+    NarrowTable T;
+    RFX_HD void operator()(uint64_t key) const {
+#if defined(__CUDA_ARCH__)
+        const uint32_t h = narrow_hash(key);
+        if (T.depth == 0 || (narrow_class(key, h) >> (24u - T.depth)) == T.cval) insert_narrow<CAP>(T.keys, T.cnts, T.n_distinct, T.overflow, key, h, 1u);
+#else
+        (void)key;
+#endif
+    }
+};
+
+// One CTA per minimiser bin.  The bin's records are taken in chunks of RCAP*3/4:
+//   A1  every thread hashes its records whole (16 bytes) into a shared-memory record table: identical super-k-mers --
+//       the same genome window seen by many reads -- collapse into one entry with a multiplicity;
+//   A2  every thread checks that the entry it counted into really holds its record (a 64-bit hash collision sends the
+//       record down a direct path instead), so the collapse is exact;
+//   B   the distinct records are expanded: a warp takes 32 table slots, prefix-sums their k-mer counts and walks the
+//       flattened (record, k-mer) space 32 k-mers per step -- 5-step shuffle binary search for the source record, record
+//       words fetched by shuffle, the k-mer cut straight out of the 2-bit stream, brev-based reverse complement -- and
+//       adds the record's multiplicity to the canonical k-mer's slot of the k-mer table (64-bit atomicCAS + atomicAdd).
+// At 100x coverage phase B sees about one k-mer in eight; the rest of the instances cost one record-level insert per
+// ~10 k-mers.  K4: only rows inside the coverage bounds leave shared memory (block-scan compaction).
+template <int RECW, int CAP, int RCAP>
 __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArgs A) {
     static_assert(RECW == 2, "k <= 31 uses 16-byte records");
+    constexpr int CHUNK = RCAP * 3 / 4;
+    static_assert(CHUNK % CNT_THREADS == 0, "chunk must be a whole number of records per thread");
+    constexpr int PER_THREAD = CHUNK / CNT_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    uint32_t* cnts = reinterpret_cast<uint32_t*>(keys + CAP);
-    __shared__ uint32_t s_distinct, s_overflow, s_sp;
+    ulonglong2* rrec = reinterpret_cast<ulonglong2*>(keys + CAP);
+    unsigned long long* rhash = reinterpret_cast<unsigned long long*>(rrec + RCAP);
+    uint32_t* cnts = reinterpret_cast<uint32_t*>(rhash + RCAP);
+    uint32_t* rmult = cnts + CAP;
+    uint16_t* ulist = reinterpret_cast<uint16_t*>(rmult + RCAP);  // slots of the distinct records of the chunk, in claim order
+    __shared__ uint32_t s_distinct, s_overflow, s_sp, s_nuniq;
     __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
     __shared__ uint32_t s_warp_tot[CNT_THREADS / 32];
     __shared__ unsigned long long s_out_base;
@@ -92,43 +139,94 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             __syncthreads();
             if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; }
             for (int i = tid; i < CAP; i += CNT_THREADS) { keys[i] = ~0ull; cnts[i] = 0; }
-            __syncthreads();
             const uint32_t cshift = 24u - depth;  // class = top `depth` bits of a 24-bit second hash
-            for (uint64_t base = beg + (uint64_t)warp * 32; base < end; base += CNT_THREADS) {
-                if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
-                const uint64_t r = base + lane;
-                ulonglong2 v = make_ulonglong2(0ull, 0ull);
-                if (r < end) v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
-                const uint32_t nk = (uint32_t)(v.x >> 48);
-                uint32_t pi = nk;  // inclusive prefix of k-mer counts over the warp's 32 records
+            const NarrowTable T{keys, cnts, &s_distinct, &s_overflow, depth, cval};
+            for (uint64_t cbeg = beg; cbeg < end; cbeg += CHUNK) {
+                for (int i = tid; i < RCAP; i += CNT_THREADS) { rhash[i] = ~0ull; rmult[i] = 0; }
+                if (tid == 0) s_nuniq = 0;
+                __syncthreads();
+                if (s_overflow) break;
+                const uint64_t cend = cbeg + CHUNK < end ? cbeg + CHUNK : end;
+                // ---- A1: collapse identical records ----
+                uint32_t myslot[PER_THREAD];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
-                const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
-                for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                    const uint32_t t = t0 + lane;
-                    uint32_t s = 0;  // number of records whose inclusive prefix is <= t  ==  source record of k-mer t
-#pragma unroll
-                    for (int step = 16; step; step >>= 1) {
-                        const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
-                        if (pv <= t) s += step;
-                    }
-                    s &= 31;
-                    const uint64_t w0 = __shfl_sync(0xffffffffu, v.x, s), w1 = __shfl_sync(0xffffffffu, v.y, s);
-                    const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
-                    if (t < total) {
-                        const uint32_t off = t - (pis - (uint32_t)(w0 >> 48));  // k-mer index inside the record
-                        const uint32_t b = 16u + 2u * off;                      // first bit of the k-mer in the 128-bit stream
-                        uint64_t hi;
-                        if (b < 64u) hi = (w0 << b) | (w1 >> (64u - b));
-                        else hi = w1 << (b - 64u);
-                        const uint64_t fwd = hi >> kshift;
-                        const uint64_t rc = revcomp(fwd, k);
-                        const uint64_t key = fwd < rc ? fwd : rc;
-                        const uint32_t h = narrow_hash(key);
-                        if (depth == 0 || (narrow_class(key, h) >> cshift) == cval)
-                            insert_narrow<CAP>(keys, cnts, &s_distinct, &s_overflow, key, h);
+                for (int j = 0; j < PER_THREAD; j++) {
+                    const uint64_t r = cbeg + (uint64_t)j * CNT_THREADS + tid;
+                    myslot[j] = 0xffffffffu;
+                    if (r < cend) {
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
+                        const uint64_t h = record_hash(v.x, v.y);
+                        uint32_t slot = (uint32_t)(h >> 20) & (RCAP - 1);
+                        while (true) {  // at most CHUNK < RCAP entries: an empty slot always exists
+                            unsigned long long cur = rhash[slot];
+                            if (cur == ~0ull) {
+                                cur = atomicCAS(&rhash[slot], ~0ull, (unsigned long long)h);
+                                if (cur == ~0ull) { rrec[slot] = v; ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)slot; break; }
+                            }
+                            if (cur == h) break;
+                            slot = (slot + 1) & (RCAP - 1);
+                        }
+                        atomicAdd(&rmult[slot], 1u);
+                        myslot[j] = slot;
                     }
                 }
+                __syncthreads();
+                // ---- A2: confirm (records are re-read: L1/L2 hits) ----
+#pragma unroll
+                for (int j = 0; j < PER_THREAD; j++) {
+                    if (myslot[j] != 0xffffffffu) {
+                        const uint64_t r = cbeg + (uint64_t)j * CNT_THREADS + tid;
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
+                        const ulonglong2 t = rrec[myslot[j]];
+                        if (t.x != v.x || t.y != v.y) {
+                            atomicSub(&rmult[myslot[j]], 1u);
+                            uint64_t rec[RECW] = {v.x, v.y};
+                            rec_foreach_kmer<uint64_t, RECW>(rec, k, DirectInsert<CAP>{T});
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- B: expand the distinct records ----
+                const int n_uniq = (int)s_nuniq;
+                for (int ubase = warp * 32; ubase < n_uniq; ubase += CNT_THREADS) {
+                    if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
+                    const int u = ubase + lane;
+                    uint32_t mult = 0;
+                    ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                    if (u < n_uniq) { const int slot = ulist[u]; mult = rmult[slot]; if (mult) v = rrec[slot]; }
+                    const uint32_t nk = mult ? (uint32_t)(v.x >> 48) : 0u;
+                    uint32_t pi = nk;  // inclusive prefix of k-mer counts over the warp's 32 table slots
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
+                    const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
+                    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+                        const uint32_t t = t0 + lane;
+                        uint32_t s = 0;  // number of slots whose inclusive prefix is <= t  ==  source slot of k-mer t
+#pragma unroll
+                        for (int step = 16; step; step >>= 1) {
+                            const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
+                            if (pv <= t) s += step;
+                        }
+                        s &= 31;
+                        const uint64_t w0 = __shfl_sync(0xffffffffu, v.x, s), w1 = __shfl_sync(0xffffffffu, v.y, s);
+                        const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
+                        const uint32_t ms = __shfl_sync(0xffffffffu, mult, s);
+                        if (t < total) {
+                            const uint32_t off = t - (pis - (uint32_t)(w0 >> 48));  // k-mer index inside the record
+                            const uint32_t b = 16u + 2u * off;                      // first bit of the k-mer in the 128-bit stream
+                            uint64_t hi;
+                            if (b < 64u) hi = (w0 << b) | (w1 >> (64u - b));
+                            else hi = w1 << (b - 64u);
+                            const uint64_t fwd = hi >> kshift;
+                            const uint64_t rc = revcomp(fwd, k);
+                            const uint64_t key = fwd < rc ? fwd : rc;
+                            const uint32_t h = narrow_hash(key);
+                            if (depth == 0 || (narrow_class(key, h) >> cshift) == cval)
+                                insert_narrow<CAP>(keys, cnts, &s_distinct, &s_overflow, key, h, ms);
+                        }
+                    }
+                }
+                __syncthreads();
             }
             __syncthreads();
             if (s_overflow) {
@@ -340,7 +438,8 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs 
     }
 }
 
-constexpr int CAP_NARROW = 4096;  // 4096 * (8 + 4) B = 48 KB  -> 4 CTAs / SM
+constexpr int CAP_NARROW = 2048;   // k-mer table: 2048 * (8 + 4) B = 24 KB
+constexpr int RCAP_NARROW = 1024;  // record table: 1024 * (16 + 8 + 4 + 2) B = 30 KB   -> 54 KB / CTA, 4 CTAs / SM
 constexpr int CAP_WIDE = 4096;    // 4096 * (16 + 4 + 4) B = 96 KB -> 2 CTAs / SM
 
 int stage_count(Ctx* c) {
@@ -381,10 +480,10 @@ int stage_count(Ctx* c) {
     if (c->n_records) {
         cudaEventRecord(c->evk[4], st);
         if (!c->wide) {
-            const size_t smem = (size_t)CAP_NARROW * 12;
-            RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t smem = (size_t)CAP_NARROW * 12 + (size_t)RCAP_NARROW * 30;
+            RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             unsigned grid = c->n_bins < 148u * 4u * 8u ? c->n_bins : 148u * 4u * 8u;
-            count_bins_narrow_kernel<2, CAP_NARROW><<<grid, CNT_THREADS, smem, st>>>(A);
+            count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW><<<grid, CNT_THREADS, smem, st>>>(A);
         } else {
             const size_t smem = (size_t)CAP_WIDE * 24;
             RFX_CUDA(c, cudaFuncSetAttribute(count_bins_wide_kernel<4, CAP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

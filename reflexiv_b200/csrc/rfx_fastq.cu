@@ -14,56 +14,68 @@
 namespace rfx {
 
 // ------------------------------------------------------------------------------------------
-// newline scan: element = one 16-byte aligned chunk of the text
+// newline scan: element = one 64-byte aligned chunk of the text
 // ------------------------------------------------------------------------------------------
 struct TextView {
-    const uint8_t* aligned;  // text pointer rounded down to 16 bytes
+    const uint8_t* aligned;  // text pointer rounded down to 64 bytes
     uint32_t delta;          // text - aligned
     uint64_t len;
 };
 
-__device__ __forceinline__ uint32_t newline_mask16(const TextView& tv, uint64_t chunk) {
-    const uint4 v = *reinterpret_cast<const uint4*>(tv.aligned + chunk * 16);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t mask = 0;
+// newline positions of one 64-byte aligned chunk as a 64-bit mask
+__device__ __forceinline__ uint64_t newline_mask64(const TextView& tv, uint64_t chunk) {
+    const uint4* p = reinterpret_cast<const uint4*>(tv.aligned + chunk * 64);
+    uint64_t mask = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au);                    // 0xff in every byte that is '\n'
-        uint32_t m4 = (((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu;  // movemask: one bit per byte
-        mask |= m4 << (4 * q);
+    for (int part = 0; part < 4; part++) {
+        const uint4 v = p[part];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t m16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au);                          // 0xff in every byte that is '\n'
+            m16 |= ((((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);  // movemask: one bit per byte
+        }
+        mask |= (uint64_t)m16 << (16 * part);
     }
     // drop bytes outside [0, len)
-    const int64_t p0 = (int64_t)(chunk * 16) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
-    if (p0 < 0) mask &= 0xffffu << (uint32_t)(-p0);
-    const int64_t over = p0 + 16 - (int64_t)tv.len;
-    if (over > 0) mask &= over >= 16 ? 0u : (0xffffu >> (uint32_t)over);
-    return mask & 0xffffu;
+    const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
+    if (p0 < 0) mask &= ~0ull << (uint32_t)(-p0);
+    const int64_t over = p0 + 64 - (int64_t)tv.len;
+    if (over > 0) mask &= over >= 64 ? 0ull : (~0ull >> (uint32_t)over);
+    return mask;
 }
 
 struct NewlineIn {
     TextView tv;
-    __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const { return __popc(newline_mask16(tv, chunk)); }
+    __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const { return __popcll(newline_mask64(tv, chunk)); }
 };
 struct NewlineOut {
     TextView tv;
-    uint64_t* line_start;  // line_start[0] = 0 is written by the caller
+    const uint8_t* text;
+    uint64_t* line_start;  // line_start[0] = 0 is written by finish_lines_kernel
+    uint8_t* line_at;      // 1 if the line starts with '@'
     __device__ __forceinline__ void operator()(uint64_t chunk, uint64_t excl, uint64_t v) const {
         if (!v) return;
-        uint32_t mask = newline_mask16(tv, chunk);
-        const int64_t p0 = (int64_t)(chunk * 16) - (int64_t)tv.delta;
+        uint64_t mask = newline_mask64(tv, chunk);
+        const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;
         uint64_t idx = excl + 1;
         while (mask) {
-            int j = __ffs(mask) - 1;
+            const int j = __ffsll((long long)mask) - 1;
             mask &= mask - 1;
-            line_start[idx++] = (uint64_t)(p0 + j) + 1;
+            const uint64_t next = (uint64_t)(p0 + j) + 1;  // the line after this newline starts here
+            line_start[idx] = next;
+            line_at[idx] = (next < tv.len && text[next] == '@') ? 1 : 0;
+            idx++;
         }
     }
 };
 
-__global__ void finish_lines_kernel(const uint8_t* text, uint64_t len, const uint64_t* n_newlines, uint64_t* line_start,
+__global__ void finish_lines_kernel(const uint8_t* text, uint64_t len, const uint64_t* n_newlines, uint64_t* line_start, uint8_t* line_at,
                                     uint64_t* out /* [0] = n_lines */) {
     uint64_t n = *n_newlines;
     line_start[0] = 0;
+    line_at[0] = (len > 0 && text[0] == '@') ? 1 : 0;
     if (len > 0 && text[len - 1] != '\n') {  // final line without terminator is still a record
         line_start[n + 1] = len + 1;
         n += 1;
@@ -107,19 +119,17 @@ struct OpCompose {  // (f then g)
 };
 
 struct LineFnIn {
-    Lines L;
-    __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
-        return (L.len(i) > 0 && L.text[L.start[i]] == '@') ? FN_AT : FN_OTHER;
-    }
+    const uint8_t* line_at;  // written next to line_start by the newline pass: no random text access here
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return line_at[i] ? FN_AT : FN_OTHER; }
 };
 struct LineFnOut {
-    Lines L;
+    uint64_t n_lines;
     uint8_t* seq_flag;
     __device__ __forceinline__ void operator()(uint64_t i, uint32_t excl, uint32_t fn) const {
         const uint32_t state_before = excl & 7u;  // prefix function applied to lineMark = 0
         // the sequence line is the one that moves lineMark 1 -> 2; the unit is emitted only when the
         // two following lines exist (lineMark 3 -> 4)
-        seq_flag[i] = (state_before == 1u && fn == FN_OTHER && i + 2 < L.n_lines) ? 1 : 0;
+        seq_flag[i] = (state_before == 1u && fn == FN_OTHER && i + 2 < n_lines) ? 1 : 0;
     }
 };
 
@@ -194,17 +204,26 @@ struct ReadOut {
 __global__ void __launch_bounds__(256) encode_reads_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ rd_src,
                                                             const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff,
                                                             uint64_t n_new, uint64_t read_base, uint64_t* __restrict__ packed) {
-    const int lane = threadIdx.x & 31;
+    // four reads per warp: an 8-lane group owns one read and produces one 64-bit word (8 lanes x 4 bases) per step
+    const int lane = threadIdx.x & 31, q = lane & 7, grp = lane >> 3;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t r = warp0; r < n_new; r += n_warps) {
-        const uint32_t elen = rd_len[read_base + r];
-        if (!elen) continue;
-        const uint64_t src = rd_src[r];
-        uint64_t* dst = packed + rd_woff[read_base + r];
+    for (uint64_t r0 = warp0 * 4; r0 < n_new; r0 += n_warps * 4) {
+        const uint64_t r = r0 + grp;
+        uint32_t elen = 0;
+        uint64_t src = 0;
+        uint64_t* dst = packed;
+        if (r < n_new) {
+            elen = rd_len[read_base + r];
+            src = rd_src[r];
+            dst = packed + rd_woff[read_base + r];
+        }
         const uint32_t n_words = (elen + 31u) >> 5;
-        for (uint32_t wbase = 0; wbase < n_words; wbase += 4) {
-            const uint32_t b0 = wbase * 32u + 4u * (uint32_t)lane;
+        uint32_t max_words = n_words;  // warp-uniform trip count: the shuffles below need every lane
+        max_words = max(max_words, __shfl_xor_sync(0xffffffffu, max_words, 8));
+        max_words = max(max_words, __shfl_xor_sync(0xffffffffu, max_words, 16));
+        for (uint32_t wi = 0; wi < max_words; wi++) {
+            const uint32_t b0 = wi * 32u + 4u * (uint32_t)q;
             uint32_t cb = 0;
             if (b0 < elen) {
                 const uint32_t nvalid = min(4u, elen - b0);
@@ -219,12 +238,11 @@ __global__ void __launch_bounds__(256) encode_reads_kernel(const uint8_t* __rest
                 cb = (codes * 0x40100401u) >> 24;            // first base -> bits 7..6
                 cb &= (0xff00u >> (2u * nvalid)) & 0xffu;    // clear the bases past the end of the read
             }
-            uint64_t word = (uint64_t)cb << (56 - 8 * (lane & 7));
+            uint64_t word = (uint64_t)cb << (56 - 8 * q);
             word |= __shfl_xor_sync(0xffffffffu, word, 1);
             word |= __shfl_xor_sync(0xffffffffu, word, 2);
             word |= __shfl_xor_sync(0xffffffffu, word, 4);
-            const uint32_t wi = wbase + (uint32_t)(lane >> 3);
-            if ((lane & 7) == 0 && wi < n_words) dst[wi] = word;
+            if (q == 0 && wi < n_words) dst[wi] = word;
         }
     }
 }
@@ -262,7 +280,7 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* s
         if ((rc = devbuf_reserve(c, c->packed, (c->n_words + w_new + 8) * sizeof(uint64_t), true)) != RFX_OK) break;
         ReadOut out{L, c->n_reads, c->n_words, c->prm.front_clip, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
         scan_apply(plan, in, out, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
-        encode_reads_kernel<<<grid_for(n_new * 32, 256, 148 * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
+        encode_reads_kernel<<<grid_for(n_new * 8, 256, 148 * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
                                                                                 c->rd_woff.as<uint64_t>(), n_new, c->n_reads,
                                                                                 c->packed.as<uint64_t>());
         // padding words after the last read: packed_window() may look one word ahead
@@ -283,10 +301,10 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
     cudaStream_t st = c->stream;
     stage_begin(c);
     TextView tv;
-    tv.delta = (uint32_t)((uintptr_t)d_text & 15);
-    tv.aligned = d_text - tv.delta;
     tv.len = len;
-    const uint64_t n_chunks = (len + tv.delta + 15) / 16;
+    tv.delta = (uint32_t)((uintptr_t)d_text & 63);
+    tv.aligned = d_text - tv.delta;
+    const uint64_t n_chunks = (len + tv.delta + 63) / 64;
 
     // 1. newline scan
     ScanPlan<uint64_t> nl;
@@ -298,9 +316,11 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
     RFX_CUDA(c, cudaMemcpyAsync(&n_newlines, nl.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     RFX_CUDA(c, cudaStreamSynchronize(st));
     RFX_TRY(devbuf_reserve(c, c->line_start, (n_newlines + 2) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->line_at, n_newlines + 2));
     uint64_t* ls = c->line_start.as<uint64_t>();
-    scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, ls}, OpAddU64{}, (uint64_t)0, st);
-    finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, c->dstat.as<uint64_t>() + DS_NSLOTS - 1);
+    uint8_t* lat = c->line_at.as<uint8_t>();
+    scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, d_text, ls, lat}, OpAddU64{}, (uint64_t)0, st);
+    finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, lat, c->dstat.as<uint64_t>() + DS_NSLOTS - 1);
     c->launches += 2;
     uint64_t n_lines = 0;
     RFX_CUDA(c, cudaMemcpyAsync(&n_lines, c->dstat.as<uint64_t>() + DS_NSLOTS - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
@@ -315,8 +335,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
         ScanPlan<uint32_t> fs;
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
         fs.bind(n_lines, c->scan_ws.as<uint32_t>());
-        scan_prepare(fs, LineFnIn{L}, OpCompose{}, FN_IDENT, st);
-        scan_apply(fs, LineFnIn{L}, LineFnOut{L, c->seq_flag.as<uint8_t>()}, OpCompose{}, FN_IDENT, st);
+        scan_prepare(fs, LineFnIn{lat}, OpCompose{}, FN_IDENT, st);
+        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines, c->seq_flag.as<uint8_t>()}, OpCompose{}, FN_IDENT, st);
         c->launches += 2 * fs.levels + 1;
     } else if (c->prm.fastq_mode == RFX_FASTQ_COUNTER) {
         flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint8_t>());

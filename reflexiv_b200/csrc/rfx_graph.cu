@@ -174,6 +174,57 @@ __global__ void rank_step_kernel(uint64_t n, const uint64_t* __restrict__ ad_in,
     }
     if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_CHANGED], 1ull);
 }
+// ---- K6 (work-efficient variant): rank through a sample of splitters ------------------------------------------
+// Heads and one node in 16 (hash of the id) are splitters.  Each splitter walks its successors up to the next
+// splitter, stamping (owner, offset) on the way: every node is touched once.  Only the splitter list (n/16 entries,
+// L2 resident) goes through pointer jumping; a last pass adds the offsets.  ~2 random accesses per node instead of
+// one per node per round.
+__device__ __forceinline__ bool is_random_splitter(uint32_t x) { return (fmix32(x ^ 0xa5a5a5a5u) & 15u) == 0u; }
+
+__global__ void splitter_select_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, uint32_t* __restrict__ spl_id,
+                                       uint32_t* __restrict__ spl_node, uint64_t* __restrict__ sp_ad, unsigned long long* dstat) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t id = NONE32;
+        if ((alive[x] & 2) && (pred[x] == NONE32 || is_random_splitter((uint32_t)x))) {
+            id = (uint32_t)atomicAdd(&dstat[DS_NSPL], 1ull);
+            spl_node[id] = (uint32_t)x;
+            sp_ad[id] = ad_pack(id, 0u);
+        }
+        spl_id[x] = id;
+    }
+}
+__global__ void splitter_walk_kernel(uint64_t m, const uint32_t* __restrict__ spl_node, const uint32_t* __restrict__ succ,
+                                     const uint32_t* __restrict__ spl_id, uint64_t* __restrict__ loc, uint64_t* sp_ad) {
+    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m; id += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = spl_node[id];
+        uint32_t off = 0;
+        loc[x] = ad_pack((uint32_t)id, 0u);
+        uint32_t y = succ[x];
+        while (y != NONE32) {
+            // a node with a predecessor is a splitter iff its id hashes to one (heads are never walked into)
+            if (is_random_splitter(y)) { sp_ad[spl_id[y]] = ad_pack((uint32_t)id, off + 1u); break; }  // my segment ends in front of it
+            off++;
+            loc[y] = ad_pack((uint32_t)id, off);
+            y = succ[y];
+        }
+    }
+}
+__global__ void rank_finalize_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint64_t* __restrict__ loc,
+                                     const uint64_t* __restrict__ sp_ad, const uint32_t* __restrict__ spl_node, uint64_t* __restrict__ ad,
+                                     unsigned long long* dstat) {
+    bool on_cycle = false;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t l = loc[x];
+        if (!(alive[x] & 2)) { ad[x] = ad_pack((uint32_t)x, 0u); continue; }
+        if (l == ~0ull) { ad[x] = ad_pack((uint32_t)x, 0u); on_cycle = true; continue; }  // never reached: cycle without a splitter
+        const uint64_t v = sp_ad[(uint32_t)l];
+        const uint32_t head = spl_node[(uint32_t)v];
+        ad[x] = ad_pack(head, (uint32_t)(v >> 32) + (uint32_t)(l >> 32));
+        if ((l >> 32) == 0) on_cycle |= pred[head] != NONE32;  // splitters check that their chain's head really is one
+    }
+    if (__any_sync(0xffffffffu, on_cycle) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_CYCLE_NODES], 1ull);
+}
+
 // nodes whose final ancestor is not a true head (pred == NONE) sit on a cycle
 __global__ void cycle_mark_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint64_t* __restrict__ ad,
                                   uint32_t* __restrict__ lab, uint32_t* __restrict__ ptr, unsigned long long* dstat) {
@@ -320,7 +371,11 @@ template <class KT> static int graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->succ, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->pred, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->tail_of, n * sizeof(uint32_t)));  // doubles as open_next until the tails pass
-    for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, c->ad[i], n * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->ad[0], n * sizeof(uint64_t)));
+    for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, c->sp_ad[i], n * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->spl_id, n * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->spl_node, n * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->loc, n * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->chain_len, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_idx, n * sizeof(uint32_t)));
     DevBuf& open_next = c->open_next;  // separate from tail_of: both are live in the admissibility pass
@@ -360,23 +415,47 @@ template <class KT> static int graph_impl(Ctx* c) {
         int cur = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
             cur = 0;
-            rank_init_kernel<<<grid_n(n), 256, 0, st>>>(n, pred, c->ad[0].as<uint64_t>());
-            c->launches++;
-            // the host looks at the "changed" flag only every 4 rounds (extra rounds are idempotent)
-            for (int round = 0; round < limit;) {
-                cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st);
-                for (int q = 0; q < 4 && round < limit; q++, round++) {
-                    rank_step_kernel<<<grid_n(n), 256, 0, st>>>(n, c->ad[cur].as<uint64_t>(), c->ad[cur ^ 1].as<uint64_t>(), dstat);
-                    c->launches++;
-                    cur ^= 1;
-                }
-                uint64_t changed = 0;
-                cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            {
+                uint32_t* spl_id = c->spl_id.as<uint32_t>();
+                uint32_t* spl_node = c->spl_node.as<uint32_t>();
+                uint64_t* loc = c->loc.as<uint64_t>();
+                cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st);
+                cudaMemsetAsync(loc, 0xff, n * sizeof(uint64_t), st);
+                splitter_select_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, spl_id, spl_node, c->sp_ad[0].as<uint64_t>(), dstat);
+                uint64_t m = 0;
+                cudaMemcpyAsync(&m, dstat + DS_NSPL, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
                 e = cudaStreamSynchronize(st);
                 if (e != cudaSuccess) break;
-                if (!changed) break;
+                int scur = 0;
+                if (m) {
+                    splitter_walk_kernel<<<grid_n(m), 256, 0, st>>>(m, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
+                    int slimit = 2;
+                    while ((1ull << slimit) < m + 1) slimit++;
+                    slimit += 2;
+                    // the host looks at the "changed" flag only every 4 rounds (extra rounds are idempotent)
+                    for (int round = 0; round < slimit;) {
+                        cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st);
+                        for (int q = 0; q < 4 && round < slimit; q++, round++) {
+                            rank_step_kernel<<<grid_n(m), 256, 0, st>>>(m, c->sp_ad[scur].as<uint64_t>(), c->sp_ad[scur ^ 1].as<uint64_t>(), dstat);
+                            c->launches++;
+                            scur ^= 1;
+                        }
+                        uint64_t changed = 0;
+                        cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+                        e = cudaStreamSynchronize(st);
+                        if (e != cudaSuccess) break;
+                        if (!changed) break;
+                    }
+                    if (e != cudaSuccess) break;
+                }
+                cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st);
+                rank_finalize_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, loc, c->sp_ad[scur].as<uint64_t>(), spl_node, c->ad[0].as<uint64_t>(), dstat);
+                c->launches += 3;
+                uint64_t any_cycle = 0;
+                cudaMemcpyAsync(&any_cycle, dstat + DS_CYCLE_NODES, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+                e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess || !any_cycle) break;
             }
-            if (e != cudaSuccess) break;
             if (attempt == 1) break;
             // cycles: every junction of a closed path joins, no node is a head
             RFX_TRY(devbuf_reserve(c, c->cmin[0], 2 * n * sizeof(uint32_t)));

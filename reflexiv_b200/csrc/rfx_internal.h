@@ -56,6 +56,7 @@ struct Ctx {
     // ---- reads (packed 2-bit) ----
     DevBuf text;        // staging for host FASTQ text
     DevBuf line_start;  // u64[n_lines + 1]
+    DevBuf line_at;     // u8[n_lines + 1] line starts with '@'
     DevBuf seq_flag;    // u8[n_lines]
     DevBuf scan_ws;     // scan workspace
     DevBuf rd_src;      // u64[new reads] text offset of each read of the current push (scratch)
@@ -95,6 +96,10 @@ struct Ctx {
     DevBuf succ, pred;    // u32[2*n_rows]
     DevBuf ad[2];         // u64[2*n_rows] packed (ancestor, distance) for pointer jumping, double buffered
     DevBuf open_next;     // u32[2*n_rows] successor across a junction that stays open
+    DevBuf spl_id;        // u32[2*n_rows] splitter index of a node, NONE if it is not a splitter
+    DevBuf spl_node;      // u32[2*n_rows] node of a splitter
+    DevBuf loc;           // u64[2*n_rows] (owning splitter, offset from it)
+    DevBuf sp_ad[2];      // u64[2*n_rows] packed (ancestor, distance) over the splitter list
     DevBuf cmin[2];
     DevBuf chain_len;     // u32[2*n_rows] at heads
     DevBuf tail_of;       // u32[2*n_rows] at heads
@@ -126,6 +131,7 @@ enum {
     DS_CYCLES = 10,
     DS_ORIENTED = 11,
     DS_SPILL = 12,
+    DS_NSPL = 13,
     DS_NSLOTS = 16
 };
 

@@ -74,6 +74,7 @@ template <int RECW> struct EmitSpill {
     uint64_t* records;
     uint32_t max_slots;
     uint32_t n;
+    int k;
     RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
 #if defined(__CUDA_ARCH__)
         const bool stored = n < max_slots && first_kmer < 65536u;  // same test as pass 1
@@ -81,7 +82,7 @@ template <int RECW> struct EmitSpill {
         if (stored) return;
         const uint64_t slot = bin_off[bin] + bin_cnt[bin] + atomicAdd(&spill_cur[bin], 1u);
         uint64_t rec[RECW];
-        rec_build<RECW>(rd, first_kmer, n_k, rec);
+        rec_build<RECW>(rd, first_kmer, n_k, k, rec);
         uint64_t* dst = records + slot * RECW;
 #pragma unroll
         for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(rec[i], rec[i + 1]);
@@ -97,7 +98,7 @@ template <int RECW>
 __global__ void __launch_bounds__(256)
     emit_records_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ rd_woff, uint64_t n_reads, const uint64_t* __restrict__ bin_off,
                         uint32_t* __restrict__ cursor, const uint32_t* __restrict__ desc, const uint16_t* __restrict__ pos, uint64_t stride,
-                        uint32_t max_slots, const uint32_t* __restrict__ rd_runs, uint64_t* __restrict__ records) {
+                        uint32_t max_slots, const uint32_t* __restrict__ rd_runs, uint64_t* __restrict__ records, int k) {
     const uint64_t total = (uint64_t)max_slots * stride;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t r = idx % stride;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256)
         const uint32_t bin = d >> 8;
         const uint64_t slot = bin_off[bin] + atomicAdd(&cursor[bin], 1u);
         uint64_t rec[RECW];
-        rec_build<RECW>(packed + rd_woff[r], first, d & 255u, rec);
+        rec_build<RECW>(packed + rd_woff[r], first, d & 255u, k, rec);
         uint64_t* dst = records + slot * RECW;
 #pragma unroll
         for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec[q], rec[q + 1]);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(PART_THREADS)
         if (!(rd_runs[r] >> 31)) continue;
         const uint32_t len = rd_len[r];
         const uint64_t* rd = packed + rd_woff[r];
-        EmitSpill<RECW> sp{rd, bin_off, bin_cnt, spill_cur, records, max_slots, 0u};
+        EmitSpill<RECW> sp{rd, bin_off, bin_cnt, spill_cur, records, max_slots, 0u, P.k};
         bin_scan_read(rd, len, P, ring_smem + threadIdx.x, (uint32_t)PART_THREADS, sp);
     }
 }
@@ -229,10 +230,10 @@ int stage_partition(Ctx* c, int n_shards) {
         cudaEventRecord(c->evk[2], st);
         if (c->recw == 2)
             emit_records_kernel<2><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
-                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>());
+                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>(), c->k);
         else
             emit_records_kernel<4><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
-                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>());
+                                                       stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(), c->records.as<uint64_t>(), c->k);
         c->launches++;
         if (spill) {
             if (c->recw == 2) {

@@ -42,12 +42,13 @@ int64_t emu_pack_reads(const uint8_t* text, const uint64_t* starts, const uint32
 struct EmitVec {
     const uint64_t* rd;
     int recw;
+    int k;
     std::vector<uint64_t>* recs;
     std::vector<uint32_t>* bins;
     void operator()(uint32_t bin, uint32_t first, uint32_t nk) const {
         uint64_t rec[4] = {0, 0, 0, 0};
-        if (recw == 2) rec_build<2>(rd, first, nk, rec);
-        else rec_build<4>(rd, first, nk, rec);
+        if (recw == 2) rec_build<2>(rd, first, nk, k, rec);
+        else rec_build<4>(rd, first, nk, k, rec);
         for (int i = 0; i < recw; i++) recs->push_back(rec[i]);
         bins->push_back(bin);
     }
@@ -68,7 +69,7 @@ int64_t emu_partition(const uint64_t* words, int64_t n_words_padded, const uint3
     std::vector<uint32_t> ring(2 * P.w);
     for (int64_t r = 0; r < n; r++) {
         if (elen[r] < (uint32_t)k) continue;
-        bin_scan_read(words + woff[r], elen[r], P, ring.data(), 1u, EmitVec{words + woff[r], recw, &g_recs, &g_bins});
+        bin_scan_read(words + woff[r], elen[r], P, ring.data(), 1u, EmitVec{words + woff[r], recw, k, &g_recs, &g_bins});
     }
     return (int64_t)g_bins.size();
 }
