@@ -216,6 +216,18 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), stats, ctx.stats()["kernel_launches"] - launches0, d2h
 
+    # raw pinned-host -> device copy rate of this box (what bounds the end-to-end path)
+    h2d_ev0, h2d_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scratch = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+    scratch.copy_(pinned[:n_bytes], non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_ev0.record()
+    scratch.copy_(pinned[:n_bytes], non_blocking=True)
+    h2d_ev1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = n_bytes / (h2d_ev0.elapsed_time(h2d_ev1) * 1e-3) / 1e9
+    del scratch
+
     for _ in range(args.warmup):
         step(False)
     sampler = ClockSampler(local)
@@ -272,7 +284,9 @@ def main():
             "stage_ms": stage_ms, "result": {k: st[k] for k in ("n_reads", "n_instances", "n_distinct", "n_rows", "n_records", "n_bins", "n_bin_splits",
                                                               "n_oriented", "n_contigs", "n_contig_bases", "n_budget_junctions", "n_cycles")},
             "roofline": roofline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e / args.steps * 1e3,
+                    "h2d_gbs_raw_copy": h2d_gbs, "h2d_ms_raw_copy": n_bytes / h2d_gbs / 1e6,
+                    "note": "FASTQ text uploaded in 96 MB chunks on a copy stream while the previous chunk is parsed"},
             "gpu_launches": launches, "clocks": clocks}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_run().items() if k in ("value", "unit", "cores", "kind", "sample", "count_stage_kmers_per_s", "reads_per_s")}

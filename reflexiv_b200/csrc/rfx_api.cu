@@ -2,6 +2,7 @@
 // host <-> device copies, result layout conversion.  No compute lives here except small formatting
 // kernels (CSV rows, oriented k-mer export).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -165,6 +166,8 @@ int rfx_create(rfx_ctx** out, const rfx_params* p) {
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->evk[i]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->copy_done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         // no CPU fallback: without a usable CUDA device the library refuses to create a context
         rc = ctx_fail(nullptr, RFX_E_CUDA, "rfx_create: CUDA device %d unusable: %s", p->device, cudaGetErrorString(e));
@@ -185,6 +188,8 @@ void rfx_destroy(rfx_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 6; i++) if (c->evk[i]) cudaEventDestroy(c->evk[i]);
+    for (int i = 0; i < 2; i++) if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -206,17 +211,53 @@ int rfx_push_fastq_device(rfx_ctx* c, const uint8_t* d_buf, size_t len) {
     if (!c || (!d_buf && len)) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
     c->have_records = false; c->have_counts = false; c->have_contigs = false;
-    return stage_parse_fastq(c, d_buf, len);
+    return stage_parse_fastq(c, d_buf, len, true, false);
 }
 
+// Host text is uploaded in chunks of whole lines on a copy stream while the compute stream parses and encodes the
+// previous chunk (PCIe is the bound of the end-to-end path: 1 GB of FASTQ per 3 M reads).  The FASTQ state machine's
+// lineMark is carried from chunk to chunk on the device, so chunking never changes which lines are reads.
 int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     if (!c || (!buf && len)) return RFX_E_INVALID;
     if (len == 0) return RFX_OK;
     cudaSetDevice(c->prm.device);
-    RFX_TRY(devbuf_reserve(c, c->text, len + 64));
-    RFX_CUDA(c, cudaMemcpyAsync(c->text.p, buf, len, cudaMemcpyHostToDevice, c->stream));
-    RFX_CUDA(c, cudaMemsetAsync(c->text.as<uint8_t>() + len, 0, 64, c->stream));
-    return rfx_push_fastq_device(c, c->text.as<uint8_t>(), len);
+    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    RFX_TRY(devbuf_reserve(c, c->text, len + 128));
+    uint8_t* d_text = c->text.as<uint8_t>();
+    // chunk boundaries: just behind a newline; the last chunk keeps at least two lines
+    size_t target = (size_t)96 << 20;
+    if (const char* e = getenv("RFX_FASTQ_CHUNK_BYTES")) { const long long v = atoll(e); if (v >= 64) target = (size_t)v; }  // tests force many chunks
+    std::vector<size_t> cuts;
+    cuts.push_back(0);
+    size_t last_ok = len;
+    {   // position just behind the third-last newline: no earlier chunk may end after it
+        size_t p = len, seen = 0;
+        while (p > 0 && seen < 3) { p--; if (buf[p] == '\n') seen++; }
+        last_ok = seen == 3 ? p + 1 : 0;
+    }
+    while (len - cuts.back() > target + target / 2) {
+        size_t want = cuts.back() + target;
+        if (want > last_ok) break;
+        const void* nl = memchr(buf + want, '\n', last_ok > want ? last_ok - want : 0);
+        if (!nl) break;
+        const size_t cut = (size_t)((const uint8_t*)nl - buf) + 1;
+        if (cut > last_ok || cut <= cuts.back()) break;
+        cuts.push_back(cut);
+    }
+    cuts.push_back(len);
+    const size_t n_chunks = cuts.size() - 1;
+    RFX_CUDA(c, cudaMemsetAsync(d_text + len, 0, 128, c->copy_stream));
+    RFX_CUDA(c, cudaMemcpyAsync(d_text, buf, cuts[1], cudaMemcpyHostToDevice, c->copy_stream));
+    RFX_CUDA(c, cudaEventRecord(c->copy_done[0], c->copy_stream));
+    for (size_t i = 0; i < n_chunks; i++) {
+        if (i + 1 < n_chunks) {
+            RFX_CUDA(c, cudaMemcpyAsync(d_text + cuts[i + 1], buf + cuts[i + 1], cuts[i + 2] - cuts[i + 1], cudaMemcpyHostToDevice, c->copy_stream));
+            RFX_CUDA(c, cudaEventRecord(c->copy_done[(i + 1) & 1], c->copy_stream));
+        }
+        RFX_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[i & 1], 0));
+        RFX_TRY(stage_parse_fastq(c, d_text + cuts[i], cuts[i + 1] - cuts[i], i == 0, i + 1 < n_chunks));
+    }
+    return RFX_OK;
 }
 
 int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {

@@ -123,15 +123,20 @@ struct LineFnIn {
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return line_at[i] ? FN_AT : FN_OTHER; }
 };
 struct LineFnOut {
-    uint64_t n_lines;
+    uint64_t n_lines;  // lines known to exist from the start of this chunk on (the chunk's own, +2 if more text follows)
     uint8_t* seq_flag;
+    const unsigned long long* state_in;  // lineMark at the start of the chunk
     __device__ __forceinline__ void operator()(uint64_t i, uint32_t excl, uint32_t fn) const {
-        const uint32_t state_before = excl & 7u;  // prefix function applied to lineMark = 0
+        const uint32_t state_before = (excl >> (3u * (uint32_t)*state_in)) & 7u;  // prefix function applied to the carried lineMark
         // the sequence line is the one that moves lineMark 1 -> 2; the unit is emitted only when the
         // two following lines exist (lineMark 3 -> 4)
         seq_flag[i] = (state_before == 1u && fn == FN_OTHER && i + 2 < n_lines) ? 1 : 0;
     }
 };
+
+__global__ void fq_state_update_kernel(const uint32_t* total_fn, unsigned long long* state) {
+    *state = (*total_fn >> (3u * (uint32_t)*state)) & 7u;
+}
 
 __device__ __forceinline__ bool is_atcgn(uint8_t a) { return a == 'A' || a == 'T' || a == 'C' || a == 'G' || a == 'N'; }
 
@@ -296,9 +301,13 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* s
     return rc;
 }
 
-int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
-    if (len == 0) return RFX_OK;
+// One chunk of FASTQ text (whole lines).  `first_chunk` resets the carried lineMark; `more_follows` promises that at
+// least two more lines come after this chunk, so a unit that starts in its last lines is known to complete.
+int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chunk, bool more_follows) {
     cudaStream_t st = c->stream;
+    unsigned long long* fq_state = c->dstat.as<unsigned long long>() + DS_FQ_STATE;
+    if (first_chunk) RFX_CUDA(c, cudaMemsetAsync(fq_state, 0, sizeof(uint64_t), st));
+    if (len == 0) return RFX_OK;
     stage_begin(c);
     TextView tv;
     tv.len = len;
@@ -336,7 +345,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len) {
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
         fs.bind(n_lines, c->scan_ws.as<uint32_t>());
         scan_prepare(fs, LineFnIn{lat}, OpCompose{}, FN_IDENT, st);
-        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines, c->seq_flag.as<uint8_t>()}, OpCompose{}, FN_IDENT, st);
+        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines + (more_follows ? 2u : 0u), c->seq_flag.as<uint8_t>(), fq_state}, OpCompose{}, FN_IDENT, st);
+        fq_state_update_kernel<<<1, 1, 0, st>>>(fs.total, fq_state);
         c->launches += 2 * fs.levels + 1;
     } else if (c->prm.fastq_mode == RFX_FASTQ_COUNTER) {
         flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint8_t>());

@@ -43,6 +43,8 @@ struct StageTimer {
 struct Ctx {
     rfx_params prm;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of the next FASTQ chunk overlaps the parse of the current one
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
     std::string err;
     uint64_t launches = 0;
 
@@ -132,13 +134,14 @@ enum {
     DS_ORIENTED = 11,
     DS_SPILL = 12,
     DS_NSPL = 13,
+    DS_FQ_STATE = 14,  // lineMark carried between the chunks of one rfx_push_fastq call
     DS_NSLOTS = 16
 };
 
 static const uint32_t NONE32 = 0xffffffffu;
 
 // stage entry points (each in its own .cu)
-int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len);
+int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chunk = true, bool more_follows = false);
 int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);
 int stage_partition(Ctx* c, int n_shards);
 int stage_rebin(Ctx* c);

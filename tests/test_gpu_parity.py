@@ -88,6 +88,26 @@ def test_k1_state_machine_edge_cases(R, orc):
         assert ctx.assemble()["n_contigs"] == 0 and ctx.contigs() == []
 
 
+def test_chunked_upload_carries_the_fastq_state(R, orc, example_text, monkeypatch):
+    """rfx_push_fastq uploads big inputs in chunks cut at arbitrary newlines (here: every ~3 KB, so chunks start in
+    the middle of records, on '+' lines and on quality lines that begin with '@'); the carried lineMark must make
+    that invisible."""
+    monkeypatch.setenv("RFX_FASTQ_CHUNK_BYTES", "3000")
+    for txt in (example_text, example_text[:100_003], example_text + b"@tail\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n"):
+        s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
+        with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
+            ctx.push_fastq(txt)
+            g_len, _, _ = ctx.debug_reads()
+            assert ctx.stats()["n_reads"] == len(s)
+            assert np.array_equal(g_len, np.where(l.astype(np.int64) - 31 > 1, l, 0).astype(np.uint32))
+    ints, counts, c, _ = _oracle_table(orc, example_text, 31, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
+        ctx.push_fastq(example_text)
+        ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, 31)
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # K2: super-k-mer records
 # ---------------------------------------------------------------------------------------------------------
@@ -369,3 +389,36 @@ def test_full_size_properties_config2_slice(R, orc):
     assert st["n_contigs"] >= 2 and sum(len(c) for c in contigs) > 1.9 * 0.99 * G
     for c in contigs[:40]:
         assert c in gs or c in grc
+
+
+def test_reflexiv_binary_matches_documented_run(R, tmp_path, golden):
+    """The C++ `reflexiv` driver (csrc/reflexiv_main.cpp) with the command line of docs/example.html:303, Spark options
+    included: same output tree as the reference, contig of the documented length and prefix on both strands."""
+    import gzip
+    import subprocess
+    from conftest import GOLDEN, ROOT
+    exe = os.path.join(ROOT, "reflexiv_b200", "reflexiv")
+    assert os.path.exists(exe), "build() must produce the reflexiv binary"
+    out = tmp_path / "result"
+    r = subprocess.run([exe, "run", "--driver-memory", "3G", "--executor-memory", "3G", "-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"),
+                        "-outfile", str(out), "-kmer", "31", "-cover", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Reflexiv" in r.stdout and (out / "_SUCCESS").exists()
+    recs = (out / "part-00000").read_text().strip().split(">")[1:]
+    seqs = ["".join(x.strip().split("\n")[1:]) for x in recs]
+    assert [x.split("\n")[0] for x in recs] == ["Contig-4558-(-4,-4)-0", "Contig-4558-(-4,-4)-1"]
+    assert sum(s.startswith(golden["documented"]["prefix_1200"]) for s in seqs) == 1
+    # counter command, gzip output, then assembly from the counts (-kmerc)
+    cout = tmp_path / "c"
+    r = subprocess.run([exe, "counter", "-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(cout), "-kmer", "31", "-cover", "2", "-gzip"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    parts = [f for f in os.listdir(cout / "Count_31") if f.startswith("part-")]
+    rows = sorted(gzip.open(cout / "Count_31" / parts[0]).read().decode().splitlines())
+    assert hashlib.sha256(("\n".join(rows) + "\n").encode()).hexdigest() == golden["oracle"]["count_ge2"]["sha256_sorted_csv"]
+    r = subprocess.run([exe, "run", "-kmerc", str(cout / "Count_31" / "part*"), "-outfile", str(tmp_path / "a"), "-kmer", "31"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "a" / "Assemble_31" / "part-00000").read_text().startswith(">Contig-4575-(-3,-3)-0\n")
+    # reference behaviour on bad options: message, exit code 0, nothing written
+    r = subprocess.run([exe, "run", "-fastq", "x", "-outfile", str(tmp_path / "z"), "-nosuch"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Parameter settings incorrect" in r.stdout and not (tmp_path / "z").exists()
