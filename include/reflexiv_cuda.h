@@ -164,6 +164,13 @@ int rfx_partition(rfx_ctx* ctx, int32_t n_shards, uint32_t n_bins_total);
 int rfx_shard_records(rfx_ctx* ctx, int32_t shard, const void** d_ptr, uint64_t* n_bytes);
 int rfx_begin_shard(rfx_ctx* ctx, int32_t shard_id, int32_t n_shards, uint32_t n_bins_total);
 int rfx_load_records_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes);
+/* Faster receive path: a sender's slice is already grouped by bin, so if its bin offsets travel with it the receiver
+ * needs no re-binning at all -- rfx_count walks every bin as the concatenation of one segment per sender.
+ * rfx_shard_bin_offsets: device pointer to the B/n + 1 record offsets (sender-absolute) of shard `shard`.
+ * rfx_load_segment_device: append one received slice together with the offsets its sender exported.
+ * Do not mix with rfx_load_records_device inside one rfx_begin_shard. */
+int rfx_shard_bin_offsets(rfx_ctx* ctx, int32_t shard, const uint64_t** d_offsets, uint32_t* n_offsets);
+int rfx_load_segment_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes, const uint64_t* d_bin_offsets);
 int rfx_record_bytes(rfx_ctx* ctx, int32_t* bytes_per_record);
 /* The filtered table as device pointers (valid until the next rfx_count / rfx_load_* / rfx_reset): keys are
  * key_bytes (8 for k <= 31, 16 for k > 31) little-endian right-aligned 2k-bit integers, i.e. the library's internal

@@ -65,6 +65,8 @@ SYMBOLS = {
     "rfx_begin_shard": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32]),
     "rfx_load_records_device": (C.c_int, [_P, _P, C.c_uint64]),
     "rfx_record_bytes": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "rfx_shard_bin_offsets": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_uint32)]),
+    "rfx_load_segment_device": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "rfx_counts_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "rfx_load_counts_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32]),
     "rfx_synth_genome": (C.c_int64, [_P, C.c_int64, C.c_uint64]),

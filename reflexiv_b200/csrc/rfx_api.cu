@@ -56,7 +56,7 @@ static void free_all(Ctx* c) {
     DevBuf* all[] = {&c->text, &c->line_start, &c->line_at, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
                      &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->ad[0],
                      &c->ad[1], &c->open_next, &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
-                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs};
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base};
     for (DevBuf* b : all) devbuf_free(*b);
 }
 
@@ -202,7 +202,7 @@ int rfx_reset(rfx_ctx* c) {
     c->n_records = 0; c->n_bins = 0; c->have_records = false;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
     c->have_contigs = false;
-    c->rx_bytes = 0; c->shard_id = -1;
+    c->rx_bytes = 0; c->shard_id = -1; c->n_seg = 0;
     for (float& m : c->ms) m = 0;
     return RFX_OK;
 }
@@ -277,7 +277,8 @@ int rfx_partition(rfx_ctx* c, int32_t n_shards, uint32_t n_bins_total) {
 int rfx_count(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    if (c->shard_id >= 0) RFX_TRY(stage_rebin(c));
+    if (c->shard_id >= 0 && c->n_seg > 0) RFX_TRY(stage_adopt_segments(c));
+    else if (c->shard_id >= 0) RFX_TRY(stage_rebin(c));
     else if (!c->have_records) RFX_TRY(stage_partition(c, 1));
     return stage_count(c);
 }
@@ -485,7 +486,7 @@ int rfx_begin_shard(rfx_ctx* c, int32_t shard_id, int32_t n_shards, uint32_t n_b
     if (!c || n_shards < 1 || shard_id < 0 || shard_id >= n_shards || n_bins_total == 0 || n_bins_total % (uint32_t)n_shards)
         return c ? ctx_fail(c, RFX_E_INVALID, "rfx_begin_shard: bad shard geometry") : RFX_E_INVALID;
     c->shard_id = shard_id; c->n_shards = n_shards; c->forced_bins = n_bins_total;
-    c->rx_bytes = 0;
+    c->rx_bytes = 0; c->n_seg = 0;
     c->have_records = false; c->have_counts = false; c->have_contigs = false;
     return RFX_OK;
 }
@@ -528,6 +529,36 @@ int rfx_load_counts_device(rfx_ctx* c, const void* d_keys, const uint32_t* d_cou
     c->table_cap = c->n_rows + 1;
     c->have_counts = true;
     c->have_contigs = false;
+    return RFX_OK;
+}
+
+int rfx_shard_bin_offsets(rfx_ctx* c, int32_t shard, const uint64_t** d_offsets, uint32_t* n_offsets) {
+    if (!c || !d_offsets || !n_offsets) return RFX_E_INVALID;
+    if (!c->have_records) return ctx_fail(c, RFX_E_STATE, "rfx_shard_bin_offsets: call rfx_partition first");
+    if (shard < 0 || shard >= c->n_shards) return ctx_fail(c, RFX_E_INVALID, "shard %d outside 0..%d", shard, c->n_shards - 1);
+    const uint32_t bps = c->n_bins / (uint32_t)c->n_shards;
+    *d_offsets = c->bin_off.as<uint64_t>() + (uint64_t)shard * bps;
+    *n_offsets = bps + 1;
+    return RFX_OK;
+}
+
+int rfx_load_segment_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes, const uint64_t* d_bin_offsets) {
+    if (!c || (!d_records && n_bytes) || !d_bin_offsets) return RFX_E_INVALID;
+    if (c->shard_id < 0) return ctx_fail(c, RFX_E_STATE, "rfx_load_segment_device: call rfx_begin_shard first");
+    if (c->n_seg >= 64) return ctx_fail(c, RFX_E_INVALID, "more than 64 segments");
+    if (c->n_seg == 0 && c->rx_bytes) return ctx_fail(c, RFX_E_STATE, "do not mix rfx_load_records_device and rfx_load_segment_device");
+    if (n_bytes % (uint64_t)(c->recw * 8)) return ctx_fail(c, RFX_E_INVALID, "record bytes not a multiple of %d", c->recw * 8);
+    cudaSetDevice(c->prm.device);
+    const uint32_t bps = c->forced_bins / (uint32_t)c->n_shards;
+    RFX_TRY(devbuf_reserve(c, c->rx_records, c->rx_bytes + n_bytes + 16, true));
+    RFX_TRY(devbuf_reserve(c, c->seg_off, (size_t)(c->n_seg + 1) * (bps + 1) * sizeof(uint64_t), true));
+    if (n_bytes) RFX_CUDA(c, cudaMemcpyAsync(c->rx_records.as<uint8_t>() + c->rx_bytes, d_records, n_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    RFX_CUDA(c, cudaMemcpyAsync(c->seg_off.as<uint64_t>() + (size_t)c->n_seg * (bps + 1), d_bin_offsets, (size_t)(bps + 1) * sizeof(uint64_t),
+                                cudaMemcpyDeviceToDevice, c->stream));
+    RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->seg_base_host[c->n_seg] = c->rx_bytes / (uint64_t)(c->recw * 8);
+    c->n_seg++;
+    c->rx_bytes += n_bytes;
     return RFX_OK;
 }
 

@@ -22,7 +22,11 @@ constexpr int CNT_STACK = 48;
 
 struct CountArgs {
     const uint64_t* records;
-    const uint64_t* bin_off;
+    // bin b = concatenation over segments s of records[seg_base[s] + off_s[b] - off_s[0] .. seg_base[s] + off_s[b+1] - off_s[0])
+    // with off_s = seg_off + s * (n_bins + 1).  A local partition is one segment with base 0.
+    const uint64_t* seg_off;
+    const uint64_t* seg_base;
+    int n_seg;
     uint32_t n_bins;
     int k;
     uint32_t min_count, max_count;
@@ -128,8 +132,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
     const int kshift = 64 - 2 * k;
 
     for (uint32_t bin = blockIdx.x; bin < A.n_bins; bin += gridDim.x) {
-        const uint64_t beg = A.bin_off[bin], end = A.bin_off[bin + 1];
-        if (beg == end) continue;
+        __syncthreads();  // every thread has left the previous bin's class loop before the stack is re-armed
         if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
         __syncthreads();
         while (true) {
@@ -141,6 +144,9 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             for (int i = tid; i < CAP; i += CNT_THREADS) { keys[i] = ~0ull; cnts[i] = 0; }
             const uint32_t cshift = 24u - depth;  // class = top `depth` bits of a 24-bit second hash
             const NarrowTable T{keys, cnts, &s_distinct, &s_overflow, depth, cval};
+            for (int seg = 0; seg < A.n_seg; seg++) {
+            const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
+            const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
             for (uint64_t cbeg = beg; cbeg < end; cbeg += CHUNK) {
                 for (int i = tid; i < RCAP; i += CNT_THREADS) { rhash[i] = ~0ull; rmult[i] = 0; }
                 if (tid == 0) s_nuniq = 0;
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
                     }
                 }
                 __syncthreads();
+            }
             }
             __syncthreads();
             if (s_overflow) {
@@ -353,8 +360,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (uint32_t bin = blockIdx.x; bin < A.n_bins; bin += gridDim.x) {
-        const uint64_t beg = A.bin_off[bin], end = A.bin_off[bin + 1];
-        if (beg == end) continue;
+        __syncthreads();  // every thread has left the previous bin's class loop before the stack is re-armed
         if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
         __syncthreads();
         while (true) {
@@ -367,6 +373,9 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs 
             __syncthreads();
             const uint32_t cmask = (1u << depth) - 1u;
             InsertWide<CAP> ins{tags, keys, &s_distinct, &s_overflow, cmask, cval};
+            for (int seg = 0; seg < A.n_seg; seg++) {
+            const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
+            const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
             for (uint64_t r = beg + tid; r < end; r += CNT_THREADS) {
                 if (*(volatile uint32_t*)&s_overflow) break;
                 uint64_t rec[RECW];
@@ -377,9 +386,13 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs 
                 }
                 rec_foreach_kmer<u128, RECW>(rec, A.k, ins);
             }
+            }
             __syncthreads();
             if (!s_overflow) {
                 CountWide<CAP> cnt{tags, keys, cnts, &s_overflow, cmask, cval};
+                for (int seg = 0; seg < A.n_seg; seg++) {
+                const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
+                const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
                 for (uint64_t r = beg + tid; r < end; r += CNT_THREADS) {
                     if (*(volatile uint32_t*)&s_overflow) break;
                     uint64_t rec[RECW];
@@ -389,6 +402,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs 
                         rec[i] = v.x; rec[i + 1] = v.y;
                     }
                     rec_foreach_kmer<u128, RECW>(rec, A.k, cnt);
+                }
                 }
                 __syncthreads();
             }
@@ -469,8 +483,15 @@ int stage_count(Ctx* c) {
     c->table_cap = cap;
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
     CountArgs A;
-    A.records = c->records.as<uint64_t>();
-    A.bin_off = c->bin_off.as<uint64_t>();
+    const bool segmented = c->shard_id >= 0 && c->n_seg > 0;
+    if (!segmented) {  // one segment: the locally partitioned (or re-binned) records
+        RFX_TRY(devbuf_reserve(c, c->seg_base, 64 * sizeof(uint64_t)));
+        RFX_CUDA(c, cudaMemsetAsync(c->seg_base.p, 0, sizeof(uint64_t), st));
+    }
+    A.records = segmented ? c->rx_records.as<uint64_t>() : c->records.as<uint64_t>();
+    A.seg_off = segmented ? c->seg_off.as<uint64_t>() : c->bin_off.as<uint64_t>();
+    A.seg_base = c->seg_base.as<uint64_t>();
+    A.n_seg = segmented ? c->n_seg : 1;
     A.n_bins = c->n_bins;
     A.k = c->k;
     A.min_count = minc; A.max_count = maxc;

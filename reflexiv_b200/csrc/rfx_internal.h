@@ -82,6 +82,11 @@ struct Ctx {
     DevBuf rx_records;
     uint64_t rx_bytes = 0;
     int32_t shard_id = -1;
+    // per-sender segments (rfx_load_segment_device): record base in rx_records + the sender's bin offsets
+    DevBuf seg_off;       // u64[n_seg][bps + 1]
+    DevBuf seg_base;      // u64[n_seg]
+    uint64_t seg_base_host[64];
+    int32_t n_seg = 0;
 
     // ---- filtered count table ----
     DevBuf keys;        // KT[table_cap]  right-aligned canonical k-mers
@@ -145,6 +150,7 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
 int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);
 int stage_partition(Ctx* c, int n_shards);
 int stage_rebin(Ctx* c);
+int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);
 int stage_graph(Ctx* c);
 

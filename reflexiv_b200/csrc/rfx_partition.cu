@@ -331,4 +331,40 @@ int stage_rebin(Ctx* c) {
     return RFX_OK;
 }
 
+// Receiving side, fast path: every sender's slice arrived grouped by bin together with its bin offsets, so the
+// received buffer is used as is; rfx_count walks bin b as the concatenation of segment(s, b) over the senders s.
+__global__ void check_segments_kernel(const uint64_t* seg_off, int n_seg, uint32_t bps, const uint64_t* seg_base, uint64_t total_records,
+                                      unsigned long long* dstat) {
+    // offsets must be monotone and the segments must tile the received records exactly
+    uint64_t expect = 0;
+    for (int s = 0; s < n_seg; s++) {
+        const uint64_t* o = seg_off + (size_t)s * (bps + 1);
+        if (seg_base[s] != expect) atomicExch(&dstat[DS_GRAPH_ERR], 4ull);
+        for (uint32_t b = threadIdx.x; b < bps; b += blockDim.x)
+            if (o[b + 1] < o[b]) atomicExch(&dstat[DS_GRAPH_ERR], 4ull);
+        expect += o[bps] - o[0];
+    }
+    if (expect != total_records) atomicExch(&dstat[DS_GRAPH_ERR], 4ull);
+}
+
+int stage_adopt_segments(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const uint32_t bps = c->forced_bins / (uint32_t)c->n_shards;
+    const uint64_t n_rec = c->rx_bytes / (uint64_t)(c->recw * 8);
+    RFX_TRY(devbuf_reserve(c, c->seg_base, 64 * sizeof(uint64_t)));
+    RFX_CUDA(c, cudaMemcpyAsync(c->seg_base.p, c->seg_base_host, (size_t)c->n_seg * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_GRAPH_ERR, 0, sizeof(uint64_t), st));
+    check_segments_kernel<<<1, 256, 0, st>>>(c->seg_off.as<uint64_t>(), c->n_seg, bps, c->seg_base.as<uint64_t>(), n_rec, c->dstat.as<unsigned long long>());
+    c->launches++;
+    uint64_t err = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&err, c->dstat.as<uint64_t>() + DS_GRAPH_ERR, 8, cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    if (err) return ctx_fail(c, RFX_E_INVALID, "received segments do not tile the record buffer");
+    c->n_bins = bps;
+    c->n_records = n_rec;
+    c->n_instances = 0;  // unknown on the receiving side; rfx_count fills it in
+    c->have_records = true;
+    return RFX_OK;
+}
+
 }  // namespace rfx

@@ -149,6 +149,21 @@ class ReflexivContext:
         blob = bases.tobytes()
         return [(blob[int(offs[i]):int(offs[i + 1])].decode(), int(left[i]), int(right[i])) for i in range(n.value)]
 
+    def contigs_raw(self, out=None):
+        """Contigs as flat arrays (bases uint8[total], offsets uint64[n+1], left int32[n], right int32[n]): the D2H read
+        without building Python strings.  `out` may carry preallocated (e.g. pinned) arrays of sufficient size."""
+        n, tot = C.c_uint64(), C.c_uint64()
+        self._check(self.L.rfx_contigs_size(self._ctx, C.byref(n), C.byref(tot)), self._ctx)
+        if out is not None and out[0].size >= tot.value and out[1].size >= n.value + 1 and out[2].size >= n.value:
+            bases, offs, left, right = out
+        else:
+            bases = np.empty(tot.value, dtype=np.uint8)
+            offs = np.empty(n.value + 1, dtype=np.uint64)
+            left = np.empty(n.value, dtype=np.int32)
+            right = np.empty(n.value, dtype=np.int32)
+        self._check(self.L.rfx_contigs_copy(self._ctx, bases.ctypes.data, offs.ctypes.data, left.ctypes.data, right.ctypes.data), self._ctx)
+        return bases[:tot.value], offs[:n.value + 1], left[:n.value], right[:n.value]
+
     def oriented(self):
         """Oriented k-mers that survive both fork filters: (keys_hi, keys_lo, left, right)."""
         n = C.c_uint64()
@@ -185,6 +200,14 @@ class ReflexivContext:
 
     def load_records_device(self, dev_ptr: int, n_bytes: int):
         self._check(self.L.rfx_load_records_device(self._ctx, dev_ptr, n_bytes), self._ctx)
+
+    def shard_bin_offsets(self, shard: int) -> Tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint32()
+        self._check(self.L.rfx_shard_bin_offsets(self._ctx, shard, C.byref(p), C.byref(n)), self._ctx)
+        return (p.value or 0), n.value
+
+    def load_segment_device(self, rec_ptr: int, n_bytes: int, offsets_ptr: int):
+        self._check(self.L.rfx_load_segment_device(self._ctx, rec_ptr, n_bytes, offsets_ptr), self._ctx)
 
     def counts_device(self):
         """(keys device pointer, counts device pointer, n_rows, key_bytes) of the filtered table in HBM."""

@@ -71,18 +71,34 @@ def _sync(torch, device):
         torch.cuda.current_stream(device).synchronize()
 
 
-def sharded_count(ctx, torch, dist, device, n_bins_total: int, group=None) -> dict:
-    """Counting across the ranks of `group`; on return `ctx` holds this rank's shard of the global table."""
+def sharded_count(ctx, torch, dist, device, n_bins_total: int, group=None, rebin: bool = False) -> dict:
+    """Counting across the ranks of `group`; on return `ctx` holds this rank's shard of the global table.
+    Every sender's slice is already grouped by bin, so its bin offsets travel with it (a second, tiny all-to-all) and
+    the owner counts the received buffer in place; `rebin=True` exercises the general path that re-derives the bins."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     ctx.partition(world, n_bins_total)
     slices = [ctx.shard_records(s) for s in range(world)]
     base = slices[0][0]
     total = sum(n for _, n in slices)
     send = device_view(torch, base, total, device)
-    recv, _ = exchange_bytes(torch, dist, send, [n for _, n in slices], group)
+    recv, recv_sizes = exchange_bytes(torch, dist, send, [n for _, n in slices], group)
+    off_ptr, n_off = ctx.shard_bin_offsets(0)
+    offs_send = device_view(torch, off_ptr, (world * (n_off - 1) + 1) * 8, device).view(torch.int64)
+    # shard s needs offsets [s*bps, (s+1)*bps]: bps + 1 values, neighbours share one
+    bps = n_off - 1
+    idx = (torch.arange(world, device=device).unsqueeze(1) * bps + torch.arange(n_off, device=device).unsqueeze(0)).reshape(-1)
+    offs_out = offs_send[idx].contiguous()
+    offs_in = torch.empty_like(offs_out)
+    dist.all_to_all_single(offs_in, offs_out, group=group)
     _sync(torch, device)
     ctx.begin_shard(rank, world, n_bins_total)
-    ctx.load_records_device(recv.data_ptr() if recv.numel() else 0, recv.numel())
+    if rebin:
+        ctx.load_records_device(recv.data_ptr() if recv.numel() else 0, recv.numel())
+    else:
+        pos = 0
+        for j in range(world):
+            ctx.load_segment_device(recv.data_ptr() + pos if recv_sizes[j] else 0, recv_sizes[j], offs_in[j * n_off:(j + 1) * n_off].data_ptr())
+            pos += recv_sizes[j]
     del recv
     return ctx.count()
 

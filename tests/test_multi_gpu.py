@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, k, out_dir):
+def _worker(rank, world, port, k, rebin, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -36,7 +36,7 @@ def _worker(rank, world, port, k, out_dir):
     inst = torch.tensor([ctx.stats()["n_instances"]], dtype=torch.int64, device=device)
     dist.all_reduce(inst)
     n_bins_total = sharded.choose_total_bins(int(inst.item()), world, 4096)
-    st = sharded.sharded_count(ctx, torch, dist, device, n_bins_total)
+    st = sharded.sharded_count(ctx, torch, dist, device, n_bins_total, rebin=rebin)
     keys, cnt = ctx.counts()
     np.save(os.path.join(out_dir, f"keys_{rank}.npy"), keys)
     np.save(os.path.join(out_dir, f"cnt_{rank}.npy"), cnt)
@@ -50,8 +50,8 @@ def _worker(rank, world, port, k, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k", [31, 61])
-def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k):
+@pytest.mark.parametrize("k,rebin", [(31, False), (61, False), (31, True)])
+def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin):
     import torch
     import torch.multiprocessing as mp
     from conftest import make_reads
@@ -60,8 +60,8 @@ def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k):
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(world, 4)
-    port = 29700 + os.getpid() % 1000 + k
-    mp.spawn(_worker, args=(world, port, k, str(tmp_path)), nprocs=world, join=True)
+    port = 29700 + os.getpid() % 1000 + k + (7 if rebin else 0)
+    mp.spawn(_worker, args=(world, port, k, rebin, str(tmp_path)), nprocs=world, join=True)
     txt = bytes(make_reads(31, 60_000, 12_000, read_len=150, err=0.005, frag=400))
     ref = orc.run_pipeline(txt, k=k, cover=2, min_contig=200)
     c = ref["counts"]
