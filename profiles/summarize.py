@@ -44,7 +44,11 @@ def kernel(path):
         print("kernel:", vals[hdr.index("Kernel Name")][:100])
         for i, h in enumerate(hdr):
             if h in KEYS:
-                print(f"  {h:75s} {vals[i]:>18s} {units[i]}")
+                v, u = vals[i], units[i]
+                if u in ("Gbyte", "Kbyte", "byte", "Tbyte"):  # normalise to Mbyte so summaries compare
+                    v = f"{float(v.replace(',', '')) * {'Tbyte': 1e6, 'Gbyte': 1e3, 'Kbyte': 1e-3, 'byte': 1e-6}[u]:.6f}"
+                    u = "Mbyte"
+                print(f"  {h:75s} {v:>18s} {u}")
             elif "warp_issue_stalled" in h and h.endswith("per_warp_active.pct") and vals[i] and float(vals[i]) > 3:
                 print(f"  {h:75s} {vals[i]:>18s} %")
 

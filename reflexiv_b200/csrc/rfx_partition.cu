@@ -49,19 +49,119 @@ struct EmitDesc {
     }
 };
 
+// The 32 reads of a warp advance in lock step, one base per iteration.  The per-base work (roll the m-mer, hash it,
+// sliding minimum) is branch free; what happens only about once per ten k-mers -- the minimiser changes -- is merely
+// queued (position + minimiser hash, a few instructions on the few lanes concerned) in a lane-interleaved
+// shared-memory queue.  The queues are drained by the whole warp together (at the end of the reads, or when one fills
+// up): bin lookup, run cutting and descriptor emission then run with most lanes busy instead of ~3 of 32.
+// Semantics are exactly those of bin_scan_read() (rfx_core.h), which the host harness and the spill pass still use.
+constexpr int SCAN_Q = 20;  // queued minimiser changes per read between two drains
+
+struct RunState {
+    uint32_t run_bin, run_start;
+    bool have;
+};
+
+__device__ __forceinline__ void emit_run(EmitDesc& em, uint32_t bin, uint32_t first, uint32_t n_k, uint32_t max_nk) {
+    while (n_k > max_nk) { em(bin, first, max_nk); first += max_nk; n_k -= max_nk; }  // same cuts as the streaming rule
+    em(bin, first, n_k);
+}
+
+// FIXED: the default geometry (k = 31, m = 11, w = 21) as compile-time constants, so masks, shifts and the block
+// length fold into immediates; any other (k, m) takes the run-time version of the same code.
+template <bool FIXED>
 __global__ void __launch_bounds__(PART_THREADS)
     bin_scan_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
                     BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
                     uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
-    extern __shared__ uint32_t ring_smem[];  // [2*w][PART_THREADS]
-    uint32_t* ring = ring_smem + threadIdx.x;
-    for (uint64_t r = (uint64_t)blockIdx.x * PART_THREADS + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * PART_THREADS) {
-        const uint32_t len = rd_len[r];
+    extern __shared__ uint32_t scan_smem[];
+    const int k = FIXED ? 31 : P.k, m = FIXED ? 11 : P.m, w = FIXED ? 21 : P.w;
+    uint32_t* ring = scan_smem + threadIdx.x;                                   // [2*w][PART_THREADS]
+    uint32_t* qh = scan_smem + 2 * w * PART_THREADS + threadIdx.x;              // [SCAN_Q][PART_THREADS] minimiser hash
+    uint32_t* qp = qh + SCAN_Q * PART_THREADS;                                  // [SCAN_Q][PART_THREADS] k-mer index
+    const uint32_t mmask = (m >= 16) ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+    const int mtop = 2 * (m - 1);
+    const uint32_t rs = PART_THREADS;
+    for (uint64_t base = (uint64_t)blockIdx.x * PART_THREADS; base < n_reads; base += (uint64_t)gridDim.x * PART_THREADS) {
+        const uint64_t r = base + threadIdx.x;
+        uint32_t len = r < n_reads ? rd_len[r] : 0u;
+        if (len < (uint32_t)k) len = 0;
+        const uint64_t* rd = packed + (r < n_reads ? rd_woff[r] : 0ull);
+        uint32_t maxlen = len;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
         EmitDesc em{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u};
-        if (len >= (uint32_t)P.k) bin_scan_read(packed + rd_woff[r], len, P, ring, (uint32_t)PART_THREADS, em);
-        const bool spill = em.n > em.stored;
-        rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
-        if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
+        RunState rst{0u, 0u, false};
+        uint32_t mf = 0, mr = 0, qn = 0, prev_h = 0;
+        uint64_t cur = 0;
+        uint32_t* blk_cur = ring;
+        uint32_t* blk_prev = ring + (uint32_t)w * rs;
+        int pib = 0;
+        uint32_t pmin = 0xffffffffu;
+        auto drain = [&]() {
+            uint32_t maxq = qn;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, d));
+            for (uint32_t t = 0; t < maxq; t++) {
+                if (t < qn) {
+                    const uint32_t i = qp[t * rs];
+                    const uint32_t bin = bin_of_minimizer(qh[t * rs], P.n_bins);
+                    if (!rst.have) { rst.have = true; rst.run_bin = bin; rst.run_start = i; }
+                    else if (bin != rst.run_bin) {
+                        emit_run(em, rst.run_bin, rst.run_start, i - rst.run_start, P.max_nk);
+                        rst.run_bin = bin; rst.run_start = i;
+                    }
+                }
+            }
+            qn = 0;
+        };
+        for (uint32_t e = 0; e < maxlen; e++) {
+            if (e < len) {
+                if ((e & 31u) == 0) cur = rd[e >> 5];
+                const uint32_t v = (uint32_t)(cur >> 62);
+                cur <<= 2;
+                mf = ((mf << 2) | v) & mmask;
+                mr = (mr >> 2) | ((v ^ 3u) << mtop);
+                if (e + 1 >= (uint32_t)m) {
+                    const uint32_t j = e + 1 - (uint32_t)m;  // m-mer index
+                    const uint32_t h = mmer_hash(mf < mr ? mf : mr);
+                    blk_cur[(uint32_t)pib * rs] = h;
+                    pmin = h < pmin ? h : pmin;
+                    if (j + 1 >= (uint32_t)w) {
+                        uint32_t hmin = pmin;
+                        if (pib != w - 1) {
+                            const uint32_t sfx = blk_prev[(uint32_t)(pib + 1) * rs];
+                            hmin = sfx < hmin ? sfx : hmin;
+                        }
+                        const uint32_t i = j + 1 - (uint32_t)w;  // k-mer index
+                        if (i == 0 || hmin != prev_h) {        // minimiser changed: remember where, decide later
+                            prev_h = hmin;
+                            qh[qn * rs] = hmin;
+                            qp[qn * rs] = i;
+                            qn++;
+                        }
+                    }
+                    if (++pib == w) {
+                        uint32_t sm = 0xffffffffu;
+                        for (int t = w - 1; t >= 0; t--) {
+                            const uint32_t x = blk_cur[(uint32_t)t * rs];
+                            sm = x < sm ? x : sm;
+                            blk_cur[(uint32_t)t * rs] = sm;
+                        }
+                        uint32_t* tmp = blk_cur; blk_cur = blk_prev; blk_prev = tmp;
+                        pib = 0; pmin = 0xffffffffu;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, qn >= (uint32_t)SCAN_Q)) drain();
+        }
+        drain();
+        if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len - (uint32_t)k + 1u - rst.run_start, P.max_nk);
+        if (r < n_reads) {
+            const bool spill = em.n > em.stored;
+            rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
+            if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
+        }
     }
 }
 
@@ -92,27 +192,38 @@ template <int RECW> struct EmitSpill {
     }
 };
 
-// Pass 2: per-record work only.  One thread per descriptor slot (reads x slots threads, so tens of millions of
-// independent atomics + 16/32-byte stores are in flight): claim a place in the bin, cut the record out of the read.
+// Pass 2: per-record work only.  A block owns 32 consecutive reads at a time; its 8 warps take the descriptor slots
+// round robin (lane = read, so descriptor loads are coalesced and the 32 reads' packed words -- 1.3 KB -- are fetched
+// from HBM once and then served by L1 to all 8 warps).  Each thread claims a place in its run's bin with one atomic
+// and cuts the 16/32-byte record out of the read.
 template <int RECW>
 __global__ void __launch_bounds__(256)
     emit_records_kernel(const uint64_t* __restrict__ packed, const uint64_t* __restrict__ rd_woff, uint64_t n_reads, const uint64_t* __restrict__ bin_off,
                         uint32_t* __restrict__ cursor, const uint32_t* __restrict__ desc, const uint16_t* __restrict__ pos, uint64_t stride,
                         uint32_t max_slots, const uint32_t* __restrict__ rd_runs, uint64_t* __restrict__ records, int k) {
-    const uint64_t total = (uint64_t)max_slots * stride;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = idx % stride;
-        const uint32_t i = (uint32_t)(idx / stride);
-        if (r >= n_reads || i >= (rd_runs[r] & 0x7fffffffu)) continue;
-        const uint32_t d = desc[idx];
-        const uint32_t first = pos[idx];
-        const uint32_t bin = d >> 8;
-        const uint64_t slot = bin_off[bin] + atomicAdd(&cursor[bin], 1u);
-        uint64_t rec[RECW];
-        rec_build<RECW>(packed + rd_woff[r], first, d & 255u, k, rec);
-        uint64_t* dst = records + slot * RECW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_tiles = (n_reads + 31) / 32;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t r = tile * 32 + lane;
+        uint32_t n = 0;
+        const uint64_t* rd = packed;
+        if (r < n_reads) { n = rd_runs[r] & 0x7fffffffu; rd = packed + rd_woff[r]; }
+        uint32_t nmax = n;
 #pragma unroll
-        for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec[q], rec[q + 1]);
+        for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
+        for (uint32_t i = warp; i < nmax; i += 8) {
+            if (i >= n) continue;
+            const uint64_t idx = (uint64_t)i * stride + r;
+            const uint32_t d = desc[idx];
+            const uint32_t first = pos[idx];
+            const uint32_t bin = d >> 8;
+            const uint64_t slot = bin_off[bin] + atomicAdd(&cursor[bin], 1u);
+            uint64_t rec[RECW];
+            rec_build<RECW>(rd, first, d & 255u, k, rec);
+            uint64_t* dst = records + slot * RECW;
+#pragma unroll
+            for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec[q], rec[q + 1]);
+        }
     }
 }
 
@@ -198,16 +309,24 @@ int stage_partition(Ctx* c, int n_shards) {
     uint32_t* spill_cur = cursor + nb;
     uint32_t* desc = c->run_desc.as<uint32_t>();
     uint16_t* pos = reinterpret_cast<uint16_t*>(desc + slots * stride + 32);
-    const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);
+    const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring (spill pass)
+    const size_t smem_scan = smem + (size_t)2 * SCAN_Q * PART_THREADS * sizeof(uint32_t);  // + the change queues
     unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
     if (grid < 1) grid = 1;
     if (grid > 148u * 64u) grid = 148u * 64u;
     if (c->n_reads) {
-        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const bool fixed = P.k == 31 && P.m == 11;
+        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         cudaEventRecord(c->evk[0], st);
-        bin_scan_kernel<<<grid, PART_THREADS, smem, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P, bin_cnt,
-                                                          spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                          c->dstat.as<unsigned long long>());
+        if (fixed)
+            bin_scan_kernel<true><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
+                                                                         bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                                         c->dstat.as<unsigned long long>());
+        else
+            bin_scan_kernel<false><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
+                                                                          bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                                          c->dstat.as<unsigned long long>());
         cudaEventRecord(c->evk[1], st);
         c->launches++;
     }
@@ -225,8 +344,8 @@ int stage_partition(Ctx* c, int n_shards) {
     c->launches += 2 * plan.levels + 2;
     RFX_TRY(devbuf_reserve(c, c->records, (n_records * c->recw + 2) * sizeof(uint64_t)));
     if (c->n_reads && n_records) {
-        const uint64_t total = slots * stride;
-        unsigned g2 = (unsigned)((total + 255) / 256 > 148u * 256u ? 148u * 256u : (total + 255) / 256);
+        const uint64_t n_tiles = (c->n_reads + 31) / 32;
+        unsigned g2 = (unsigned)(n_tiles > 148u * 64u ? 148u * 64u : n_tiles);
         cudaEventRecord(c->evk[2], st);
         if (c->recw == 2)
             emit_records_kernel<2><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
