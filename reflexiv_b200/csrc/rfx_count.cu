@@ -13,6 +13,9 @@
 // k > 31 (128-bit keys): the slot is claimed with a 32-bit CAS on a tag word, the 128-bit key is then
 // published, and a second pass over the records verifies every k-mer against the published keys
 // while counting, so two different k-mers can never be merged (details at insert_wide()).
+#include <stdlib.h>
+#include <string.h>
+
 #include "rfx_internal.h"
 
 namespace rfx {
@@ -110,12 +113,12 @@ template <int CAP> struct DirectInsert {  // rare path: a record whose 64-bit ha
 //       adds the record's multiplicity to the canonical k-mer's slot of the k-mer table (64-bit atomicCAS + atomicAdd).
 // At 100x coverage phase B sees about one k-mer in eight; the rest of the instances cost one record-level insert per
 // ~10 k-mers.  K4: only rows inside the coverage bounds leave shared memory (block-scan compaction).
-template <int RECW, int CAP, int RCAP>
-__global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArgs A) {
+template <int RECW, int CAP, int RCAP, int NT>
+__global__ void __launch_bounds__(NT) count_bins_narrow_kernel(CountArgs A) {
     static_assert(RECW == 2, "k <= 31 uses 16-byte records");
     constexpr int CHUNK = RCAP * 3 / 4;
-    static_assert(CHUNK % CNT_THREADS == 0, "chunk must be a whole number of records per thread");
-    constexpr int PER_THREAD = CHUNK / CNT_THREADS;
+    static_assert(CHUNK % NT == 0, "chunk must be a whole number of records per thread");
+    constexpr int PER_THREAD = CHUNK / NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     ulonglong2* rrec = reinterpret_cast<ulonglong2*>(keys + CAP);
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
     uint16_t* ulist = reinterpret_cast<uint16_t*>(rmult + RCAP);  // slots of the distinct records of the chunk, in claim order
     __shared__ uint32_t s_distinct, s_overflow, s_sp, s_nuniq;
     __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
-    __shared__ uint32_t s_warp_tot[CNT_THREADS / 32];
+    __shared__ uint32_t s_warp_tot[NT / 32];
     __shared__ unsigned long long s_out_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = A.k;
@@ -141,14 +144,14 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             const uint32_t depth = s_stack_depth[s_sp - 1], cval = s_stack_val[s_sp - 1];
             __syncthreads();
             if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; }
-            for (int i = tid; i < CAP; i += CNT_THREADS) { keys[i] = ~0ull; cnts[i] = 0; }
+            for (int i = tid; i < CAP; i += NT) { keys[i] = ~0ull; cnts[i] = 0; }
             const uint32_t cshift = 24u - depth;  // class = top `depth` bits of a 24-bit second hash
             const NarrowTable T{keys, cnts, &s_distinct, &s_overflow, depth, cval};
             for (int seg = 0; seg < A.n_seg; seg++) {
             const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
             const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
             for (uint64_t cbeg = beg; cbeg < end; cbeg += CHUNK) {
-                for (int i = tid; i < RCAP; i += CNT_THREADS) { rhash[i] = ~0ull; rmult[i] = 0; }
+                for (int i = tid; i < RCAP; i += NT) { rhash[i] = ~0ull; rmult[i] = 0; }
                 if (tid == 0) s_nuniq = 0;
                 __syncthreads();
                 if (s_overflow) break;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
                 uint32_t myslot[PER_THREAD];
 #pragma unroll
                 for (int j = 0; j < PER_THREAD; j++) {
-                    const uint64_t r = cbeg + (uint64_t)j * CNT_THREADS + tid;
+                    const uint64_t r = cbeg + (uint64_t)j * NT + tid;
                     myslot[j] = 0xffffffffu;
                     if (r < cend) {
                         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
 #pragma unroll
                 for (int j = 0; j < PER_THREAD; j++) {
                     if (myslot[j] != 0xffffffffu) {
-                        const uint64_t r = cbeg + (uint64_t)j * CNT_THREADS + tid;
+                        const uint64_t r = cbeg + (uint64_t)j * NT + tid;
                         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
                         const ulonglong2 t = rrec[myslot[j]];
                         if (t.x != v.x || t.y != v.y) {
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
                 __syncthreads();
                 // ---- B: expand the distinct records ----
                 const int n_uniq = (int)s_nuniq;
-                for (int ubase = warp * 32; ubase < n_uniq; ubase += CNT_THREADS) {
+                for (int ubase = warp * 32; ubase < n_uniq; ubase += NT) {
                     if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
                     const int u = ubase + lane;
                     uint32_t mult = 0;
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             }
             // K4: coverage filter + compaction.  Block-wide exclusive scan of per-thread survivor counts.
             uint32_t mine = 0, inst = 0;
-            for (int i = tid; i < CAP; i += CNT_THREADS) {
+            for (int i = tid; i < CAP; i += NT) {
                 const uint32_t cn = cnts[i];
                 inst += cn;
                 mine += (cn >= A.min_count && cn <= A.max_count && keys[i] != ~0ull) ? 1u : 0u;
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             __syncthreads();
             if (tid == 0) {
                 uint32_t tot = 0;
-                for (int w = 0; w < CNT_THREADS / 32; w++) { uint32_t t = s_warp_tot[w]; s_warp_tot[w] = tot; tot += t; }
+                for (int w = 0; w < NT / 32; w++) { uint32_t t = s_warp_tot[w]; s_warp_tot[w] = tot; tot += t; }
                 s_out_base = tot ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
                 atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)s_distinct);
                 if (s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(CNT_THREADS) count_bins_narrow_kernel(CountArg
             unsigned long long o = s_out_base + s_warp_tot[warp] + (incl - mine);
             if (o + mine <= A.out_cap) {
                 uint64_t* ok = reinterpret_cast<uint64_t*>(A.out_keys);
-                for (int i = tid; i < CAP; i += CNT_THREADS) {
+                for (int i = tid; i < CAP; i += NT) {
                     const uint32_t cn = cnts[i];
                     if (cn >= A.min_count && cn <= A.max_count && keys[i] != ~0ull) { ok[o] = keys[i]; A.out_counts[o] = cn; o++; }
                 }
@@ -502,9 +505,16 @@ int stage_count(Ctx* c) {
         cudaEventRecord(c->evk[4], st);
         if (!c->wide) {
             const size_t smem = (size_t)CAP_NARROW * 12 + (size_t)RCAP_NARROW * 30;
-            RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             unsigned grid = c->n_bins < 148u * 4u * 8u ? c->n_bins : 148u * 4u * 8u;
-            count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW><<<grid, CNT_THREADS, smem, st>>>(A);
+            const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob: "big" = 512 threads, 2048-entry record table
+            if (variant && !strcmp(variant, "big")) {
+                const size_t smem2 = (size_t)CAP_NARROW * 12 + (size_t)2048 * 30;
+                RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, 2048, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                count_bins_narrow_kernel<2, CAP_NARROW, 2048, 512><<<grid, 512, smem2, st>>>(A);
+            } else {
+                RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW, CNT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW, CNT_THREADS><<<grid, CNT_THREADS, smem, st>>>(A);
+            }
         } else {
             const size_t smem = (size_t)CAP_WIDE * 24;
             RFX_CUDA(c, cudaFuncSetAttribute(count_bins_wide_kernel<4, CAP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -211,18 +211,29 @@ __global__ void __launch_bounds__(256)
         uint32_t nmax = n;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, d));
-        for (uint32_t i = warp; i < nmax; i += 8) {
-            if (i >= n) continue;
-            const uint64_t idx = (uint64_t)i * stride + r;
-            const uint32_t d = desc[idx];
-            const uint32_t first = pos[idx];
-            const uint32_t bin = d >> 8;
-            const uint64_t slot = bin_off[bin] + atomicAdd(&cursor[bin], 1u);
-            uint64_t rec[RECW];
-            rec_build<RECW>(rd, first, d & 255u, k, rec);
-            uint64_t* dst = records + slot * RECW;
+        // two runs per thread per step: both descriptor loads, both atomics and both stores are in flight together
+        for (uint32_t i = warp; i < nmax; i += 16) {
+            const uint32_t i2 = i + 8;
+            const bool a = i < n, b = i2 < n;
+            uint32_t d1 = 0, d2 = 0, f1 = 0, f2 = 0;
+            if (a) { const uint64_t idx = (uint64_t)i * stride + r; d1 = desc[idx]; f1 = pos[idx]; }
+            if (b) { const uint64_t idx = (uint64_t)i2 * stride + r; d2 = desc[idx]; f2 = pos[idx]; }
+            uint64_t s1 = 0, s2 = 0;
+            if (a) s1 = bin_off[d1 >> 8] + atomicAdd(&cursor[d1 >> 8], 1u);
+            if (b) s2 = bin_off[d2 >> 8] + atomicAdd(&cursor[d2 >> 8], 1u);
+            uint64_t rec1[RECW], rec2[RECW];
+            if (a) rec_build<RECW>(rd, f1, d1 & 255u, k, rec1);
+            if (b) rec_build<RECW>(rd, f2, d2 & 255u, k, rec2);
+            if (a) {
+                uint64_t* dst = records + s1 * RECW;
 #pragma unroll
-            for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec[q], rec[q + 1]);
+                for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec1[q], rec1[q + 1]);
+            }
+            if (b) {
+                uint64_t* dst = records + s2 * RECW;
+#pragma unroll
+                for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(rec2[q], rec2[q + 1]);
+            }
         }
     }
 }
