@@ -72,13 +72,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_inputs(rank: int, world: int):
+def make_inputs(rank: int, world: int, genome_len: int = GENOME_LEN, error_rate: float = 0.0):
     """This rank's FASTQ text: pairs [rank*P, (rank+1)*P) of a genome of world * 4.6 Mbp."""
     import numpy as np
     from reflexiv_b200 import synth
-    g = synth.genome(GENOME_LEN * world)
-    pairs = synth.n_pairs_for(GENOME_LEN, COVERAGE, READ_LEN)
-    txt = synth.fastq(g, pairs, read_len=READ_LEN, frag_len=400, first_pair=rank * pairs)
+    g = synth.genome(genome_len * world)
+    pairs = synth.n_pairs_for(genome_len, COVERAGE, READ_LEN)
+    txt = synth.fastq(g, pairs, read_len=READ_LEN, frag_len=400, first_pair=rank * pairs, error_rate=error_rate)
     return txt, 2 * pairs
 
 
@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--minimizer", type=int, default=0)
     ap.add_argument("--bin-target", type=int, default=0)
+    ap.add_argument("--k", type=int, default=K, help="informational runs only: the headline config is k=31")
+    ap.add_argument("--error-rate", type=float, default=0.0, help="informational: per-base substitution rate of the synthetic reads")
+    ap.add_argument("--genome", type=int, default=GENOME_LEN, help="informational: genome length per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -161,7 +164,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     args.warmup = max(args.warmup, 3)
 
-    txt, n_reads = make_inputs(rank, world)
+    txt, n_reads = make_inputs(rank, world, args.genome, args.error_rate)
+    kk = args.k
     n_bytes = len(txt)
     pinned = torch.empty(n_bytes + 64, dtype=torch.uint8, pin_memory=True)
     pinned[:n_bytes] = torch.from_numpy(txt)
@@ -171,9 +175,9 @@ def main():
     torch.cuda.synchronize()
     host_view = pinned.numpy()[:n_bytes]
 
-    param = R.DefaultParam(kmerSize=K)
+    param = R.DefaultParam(kmerSize=kk)
     ctx = R.ReflexivContext(param, device=local, minimizer_len=args.minimizer, bin_target_kmers=args.bin_target)
-    n_inst_rank = n_reads * (READ_LEN - K + 1)
+    n_inst_rank = n_reads * (READ_LEN - kk + 1)
     n_bins_total = sharded.choose_total_bins(n_inst_rank * world, world, args.bin_target or 16384)
 
     # pinned landing buffers for the end-to-end result read (contig bases, offsets, flags)
@@ -274,7 +278,8 @@ def main():
     peak, peak_src = hbm_peak()
     inst_local = st["n_instances"] if world == 1 else n_inst_rank
     rows_local = st["n_rows"] if world == 1 else st["n_rows"] // world
-    b_count = n_reads * READ_LEN + 16 * inst_local + 12 * rows_local
+    wkey = 1 if kk <= 31 else 2
+    b_count = n_reads * READ_LEN + 16 * wkey * inst_local + (8 * wkey + 4) * rows_local
     dom = max(kern_ms, key=kern_ms.get)
     count_path_ms = sum(kern_ms.values())
     ach = b_count / (count_path_ms * 1e-3) / 1e9 if count_path_ms else None
@@ -292,8 +297,9 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"configs[1]: synthetic {GENOME_LEN * world} bp genome, {n_reads * world} x {READ_LEN} bp paired reads at {COVERAGE:.0f}x, "
-                                   f"k={K}, cover 2, full run path (FASTQ text -> counts -> fork filters -> contigs)",
+            "config": {"workload": f"configs[1]: synthetic {args.genome * world} bp genome, {n_reads * world} x {READ_LEN} bp paired reads at {COVERAGE:.0f}x, "
+                                   f"k={kk}, cover 2, full run path (FASTQ text -> counts -> fork filters -> contigs)"
+                                   + ("" if (kk, args.error_rate, args.genome) == (K, 0.0, GENOME_LEN) else f" [informational variant: error rate {args.error_rate}]"),
                        "l2_policy": f"inputs larger than L2: {n_bytes / 1e6:.0f} MB of FASTQ text per GPU per step, nothing reused across steps",
                        "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: minimiser-bin shards, NCCL all-to-all of super-k-mer records, replicated graph stage",
                        "timing": "host clock around blocking C-ABI calls bracketed by barrier + cuda synchronize, max over ranks; per-stage and per-kernel times from CUDA events on the library's stream"},
