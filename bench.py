@@ -178,7 +178,7 @@ def main():
     param = R.DefaultParam(kmerSize=kk)
     ctx = R.ReflexivContext(param, device=local, minimizer_len=args.minimizer, bin_target_kmers=args.bin_target)
     n_inst_rank = n_reads * (READ_LEN - kk + 1)
-    n_bins_total = sharded.choose_total_bins(n_inst_rank * world, world, args.bin_target or 16384)
+    n_bins_total = ctx.choose_bins(n_inst_rank * world, world)
 
     # pinned landing buffers for the end-to-end result read (contig bases, offsets, flags)
     out_bases = torch.empty(2 * GENOME_LEN * world + (1 << 20), dtype=torch.uint8, pin_memory=True).numpy()

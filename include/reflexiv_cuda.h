@@ -161,6 +161,9 @@ int rfx_stats(rfx_ctx* ctx, rfx_stats_t* out);
  * B (n_bins_total) must be the same on every rank and a multiple of n; 0 = let the library choose
  * (single-process use only). */
 int rfx_partition(rfx_ctx* ctx, int32_t n_shards, uint32_t n_bins_total);
+/* the library's own choice of B for `global_instances` k-mer instances over n_shards shards (what rfx_count uses in a
+ * single-process run); every rank of a sharded run calls it with the same arguments.  0 on bad arguments. */
+uint32_t rfx_choose_bins(rfx_ctx* ctx, uint64_t global_instances, int32_t n_shards);
 int rfx_shard_records(rfx_ctx* ctx, int32_t shard, const void** d_ptr, uint64_t* n_bytes);
 int rfx_begin_shard(rfx_ctx* ctx, int32_t shard_id, int32_t n_shards, uint32_t n_bins_total);
 int rfx_load_records_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes);

@@ -61,6 +61,7 @@ SYMBOLS = {
     "rfx_oriented_copy": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfx_stats": (C.c_int, [_P, C.POINTER(RfxStats)]),
     "rfx_partition": (C.c_int, [_P, C.c_int32, C.c_uint32]),
+    "rfx_choose_bins": (C.c_uint32, [_P, C.c_uint64, C.c_int32]),
     "rfx_shard_records": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "rfx_begin_shard": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32]),
     "rfx_load_records_device": (C.c_int, [_P, _P, C.c_uint64]),

@@ -274,6 +274,11 @@ int rfx_partition(rfx_ctx* c, int32_t n_shards, uint32_t n_bins_total) {
     return stage_partition(c, n_shards);
 }
 
+uint32_t rfx_choose_bins(rfx_ctx* c, uint64_t global_instances, int32_t n_shards) {
+    if (!c || n_shards < 1) return 0;
+    return choose_bin_count(c, global_instances, n_shards);
+}
+
 int rfx_count(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);

@@ -3,25 +3,39 @@
 // Replaces groupBy("value").count() + filter(count >= min && count <= max)
 //   (ReflexivDataFrameCounter.java:198-210, ReflexivDataFrameCounter64.java:200-212, ReflexivDSMain.java:207-216).
 //
-// One CTA owns one minimiser bin at a time.  Its threads stream the bin's super-k-mer records from
-// HBM (one coalesced 16/32-byte record per thread), unroll them into canonical k-mers with the same
-// rolling update as the reference extractor, and count them in an open-addressing table that lives
-// in shared memory (64-bit atomicCAS claims a slot, 32-bit atomicAdd counts).  Only rows that pass the
-// coverage filter ever reach HBM again.  A bin whose distinct k-mers do not fit the table is re-run
-// in 2, 4, ... sub-classes selected by independent hash bits, so the result is exact for any input.
-//
-// k > 31 (128-bit keys): the slot is claimed with a 32-bit CAS on a tag word, the 128-bit key is then
-// published, and a second pass over the records verifies every k-mer against the published keys
-// while counting, so two different k-mers can never be merged (details at insert_wide()).
+// One CTA owns one minimiser bin at a time (bins are handed out by an atomic ticket, so a heavy bin never
+// holds up a static schedule).  Per bin:
+//   A1  every thread hashes its super-k-mer records whole into a shared-memory tag table: identical records
+//       -- the same genome window seen by many reads -- collapse into one entry with a multiplicity;
+//   A2  every thread checks that the entry it counted into really is its record (compared against the
+//       claimant's record, re-read from L1/L2); a record that lost a tag collision becomes an entry of its
+//       own, so the collapse is exact;
+//   B   the distinct records are expanded: a warp takes 32 entries, prefix-sums their k-mer counts and walks
+//       the flattened (record, k-mer) space 32 k-mers per step -- shuffle binary search for the source record,
+//       record words fetched by shuffle, the k-mer cut straight out of the 2-bit stream, brev-based reverse
+//       complement -- and adds the record's multiplicity to the canonical k-mer's slot of an open-addressing
+//       table in shared memory.
+//         k <= 31: 64-bit atomicCAS claims the slot with the key itself;
+//         k  > 31: a 32-bit tag CAS claims the slot and the claimant publishes the 128-bit key (pass B1);
+//                  after a barrier pass B2 walks the same k-mers again, finds the slot whose FULL key
+//                  matches and counts.  A key swallowed by a tag collision in B1 is not found in B2: the bin
+//                  is re-run in sub-classes (different hash bits separate the pair), so counts stay exact.
+//   K4  only rows inside the coverage bounds leave shared memory.
+// Both tables keep a list of their occupied slots, so clearing and compaction cost what the bin holds, not
+// what the table could hold; that is what lets bins be small (one chunk, few barriers) and the table be
+// sized for noisy reads (one error-carrying k-mer in four is a singleton) at the same time.
+// A bin whose distinct k-mers still do not fit is re-run in 2 or 4 sub-classes chosen by independent hash
+// bits, recursively, so the result is exact for any input.
 #include <stdlib.h>
 #include <string.h>
+
+#include <type_traits>
 
 #include "rfx_internal.h"
 
 namespace rfx {
 
-constexpr int CNT_THREADS = 256;
-constexpr int CNT_STACK = 48;
+constexpr int CNT_STACK = 64;
 
 struct CountArgs {
     const uint64_t* records;
@@ -39,425 +53,551 @@ struct CountArgs {
     unsigned long long out_cap;
 };
 
-// ---------------------------------------------------------------------------------------------
-// k <= 31
-// ---------------------------------------------------------------------------------------------
-// Cheap 2 x 32-bit mix of a <= 62-bit key: slot bits from `h`, sub-class bits from an independent second product.
-__device__ __forceinline__ uint32_t narrow_hash(uint64_t key) {
-    uint32_t h = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
-    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    return h;
-}
-__device__ __forceinline__ uint32_t narrow_class(uint64_t key, uint32_t h) { return ((h ^ (uint32_t)(key >> 32)) * 0x27D4EB2Fu) >> 8; }
+constexpr int MAX_SEG = 64;
 
-// 64-bit hash of a whole 16-byte record, built from 32-bit multiplies.  Only speed depends on its quality: equal
-// hashes are confirmed against the stored record before anything is counted.
-__device__ __forceinline__ uint64_t record_hash(uint64_t w0, uint64_t w1) {
-    const uint32_t a = (uint32_t)w0, b = (uint32_t)(w0 >> 32), c = (uint32_t)w1, d = (uint32_t)(w1 >> 32);
-    uint32_t h1 = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du ^ d * 0x27D4EB2Fu;
-    uint32_t h2 = a * 0x165667B1u ^ b * 0xD3A2646Cu ^ c * 0xFD7046C5u ^ d * 0xB55A4F09u;
-    h1 ^= h1 >> 15; h1 *= 0x2C1B3C6Du; h1 ^= h1 >> 13;
-    h2 ^= h2 >> 16; h2 *= 0x7FEB352Du; h2 ^= h2 >> 15;
-    const uint64_t h = ((uint64_t)h2 << 32) | h1;
-    return h == ~0ull ? 0x5bd1e9955bd1e995ull : h;
+// Hashing.  Every 32-bit word goes through a 32 x 32 -> 64-bit multiply whose halves are folded together ("mum"):
+// the high half carries the word's top bits down, so -- unlike a plain (word * odd) ^ ... chain, where a difference
+// in the top bits of one word can cancel a difference in the top bits of another -- related k-mers (a substitution
+// here, another 16 bases further on) do not collide systematically.  Only speed depends on the quality of these
+// hashes: equal hashes are always confirmed against the full record / key before anything is counted.
+__device__ __forceinline__ uint32_t mum32(uint32_t x, uint32_t c) {
+    const uint64_t p = (uint64_t)x * c;
+    return (uint32_t)p ^ (uint32_t)(p >> 32);
 }
-
-// adds `mult` occurrences of one canonical k-mer to the shared-memory table
-template <int CAP>
-__device__ __forceinline__ void insert_narrow(unsigned long long* keys, uint32_t* cnts, uint32_t* n_distinct, volatile uint32_t* overflow,
-                                              uint64_t key, uint32_t h, uint32_t mult) {
-    uint32_t slot = h & (CAP - 1);
-    for (int probe = 0; probe < CAP; probe++) {
-        unsigned long long cur = keys[slot];
-        if (cur != key) {
-            if (cur != ~0ull) { slot = (slot + 1) & (CAP - 1); continue; }
-            cur = atomicCAS(&keys[slot], ~0ull, (unsigned long long)key);
-            if (cur == ~0ull) {
-                if (atomicAdd(n_distinct, 1u) >= (uint32_t)(CAP * 3 / 4)) *overflow = 1u;
-            } else if (cur != key) { slot = (slot + 1) & (CAP - 1); continue; }
-        }
-        atomicAdd(&cnts[slot], mult);
-        return;
-    }
-    *overflow = 1u;
+__device__ __forceinline__ uint32_t lane_a(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t x = mum32(a ^ 0x9E3779B9u, 0x9E3779B1u) ^ b;
+    x = mum32(x, 0x85EBCA77u) ^ c;
+    x = mum32(x, 0xC2B2AE3Du) ^ d;
+    return mum32(x, 0x27D4EB2Fu);
+}
+__device__ __forceinline__ uint32_t lane_b(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t x = mum32(a ^ 0x7F4A7C15u, 0x2C1B3C6Du) ^ b;
+    x = mum32(x, 0x7FEB352Du) ^ c;
+    x = mum32(x, 0x846CA68Bu) ^ d;
+    return mum32(x, 0x165667B1u);
 }
 
-struct NarrowTable {
-    unsigned long long* keys;
+// slot hash + tag of a whole record (tag 0 = empty slot)
+template <int RECW> __device__ __forceinline__ void record_hash(const uint64_t (&w)[RECW], uint32_t& slot_h, uint32_t& tag) {
+    uint32_t x = lane_a((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
+    if (RECW == 4) x = lane_b((uint32_t)w[2] ^ x, (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
+    const uint64_t p = (uint64_t)x * 0xD3A2646Cu;
+    slot_h = (uint32_t)p ^ (uint32_t)(p >> 32);
+    tag = (uint32_t)(p >> 32) * 0xFD7046C5u | 1u;
+}
+
+// k <= 31: table slot from h; sub-class bits (24) from a second product of the same mixed word
+__device__ __forceinline__ uint32_t narrow_hash(uint64_t key, uint32_t& cls) {
+    const uint32_t x = mum32((uint32_t)key ^ 0x9E3779B9u, 0x9E3779B1u) ^ (uint32_t)(key >> 32);
+    const uint64_t p = (uint64_t)x * 0x85EBCA77u;
+    cls = ((uint32_t)(p >> 32) * 0x27D4EB2Fu) >> 8;
+    return (uint32_t)p ^ (uint32_t)(p >> 32);
+}
+
+// The shared-memory k-mer table of one CTA.
+template <bool WIDE, int CAP> struct KmerTable {
+    static constexpr int KMAX = CAP * 3 / 4;  // distinct k-mers the table accepts before the bin is split
+    unsigned long long* keys;  // narrow: the key, ~0 = empty.   wide: high 64 bits of the key
+    unsigned long long* keys_lo;  // wide only
+    uint32_t* tags;               // wide only: 0 = empty
     uint32_t* cnts;
+    uint16_t* klist;              // occupied slots in claim order
     uint32_t* n_distinct;
     volatile uint32_t* overflow;
-    uint32_t depth, cval;
-};
+    unsigned long long* why;  // DS_OVF_WHY counters
 
-template <int CAP> struct DirectInsert {  // rare path: a record whose 64-bit hash collided with a different record
-    NarrowTable T;
-    RFX_HD void operator()(uint64_t key) const {
-#if defined(__CUDA_ARCH__)
-        const uint32_t h = narrow_hash(key);
-        if (T.depth == 0 || (narrow_class(key, h) >> (24u - T.depth)) == T.cval) insert_narrow<CAP>(T.keys, T.cnts, T.n_distinct, T.overflow, key, h, 1u);
-#else
-        (void)key;
+    __device__ __forceinline__ void flag(int reason) const {
+        if (!*overflow) atomicAdd(&why[reason], 1ull);
+        *overflow = 1u;
+    }
+    __device__ __forceinline__ void note_claim(uint32_t slot) const {
+        const uint32_t i = atomicAdd(n_distinct, 1u);
+        if (i < (uint32_t)KMAX) klist[i] = (uint16_t)slot;
+        else flag(0);
+    }
+    // narrow: claim-or-find with the key itself, then count
+    __device__ __forceinline__ void add(uint64_t key, uint32_t h, uint32_t mult) const {
+        uint32_t slot = h & (CAP - 1);
+        for (int probe = 0; probe < CAP; probe++) {
+            unsigned long long cur = keys[slot];
+            if (cur != key) {
+                if (cur != ~0ull) { slot = (slot + 1) & (CAP - 1); continue; }
+                if (*overflow) return;
+                cur = atomicCAS(&keys[slot], ~0ull, (unsigned long long)key);
+                if (cur == ~0ull) note_claim(slot);
+                else if (cur != key) { slot = (slot + 1) & (CAP - 1); continue; }
+            }
+            atomicAdd(&cnts[slot], mult);
+            return;
+        }
+        flag(3);
+    }
+    // wide, pass B1: claim by tag, publish the key (an equal tag is presumed to be the same key; B2 verifies)
+    __device__ __forceinline__ void claim(u128 key, uint32_t h, uint32_t tag) const {
+        uint32_t slot = h & (CAP - 1);
+        for (int probe = 0; probe < CAP; probe++) {
+            uint32_t cur = tags[slot];
+            if (cur == 0u) {
+                if (*overflow) return;
+                cur = atomicCAS(&tags[slot], 0u, tag);
+                if (cur == 0u) {
+                    keys[slot] = (unsigned long long)(uint64_t)(key >> 64);
+                    keys_lo[slot] = (unsigned long long)(uint64_t)key;
+                    note_claim(slot);
+                    return;
+                }
+            }
+            if (cur == tag) return;
+            slot = (slot + 1) & (CAP - 1);
+        }
+        flag(1);
+    }
+    // wide, pass B2: find the slot whose full key matches, count
+    __device__ __forceinline__ void count(u128 key, uint32_t h, uint32_t tag, uint32_t mult) const {
+        const unsigned long long hi = (uint64_t)(key >> 64), lo = (uint64_t)key;
+        uint32_t slot = h & (CAP - 1);
+        for (int probe = 0; probe < CAP; probe++) {
+            const uint32_t cur = tags[slot];
+            if (cur == 0u) break;
+            if (cur == tag && keys[slot] == hi && keys_lo[slot] == lo) { atomicAdd(&cnts[slot], mult); return; }
+            slot = (slot + 1) & (CAP - 1);
+        }
+#ifdef RFX_DEBUG_COUNT
+        if (!*overflow) {
+            int found = -1;
+            for (int i = 0; i < CAP; i++) if (tags[i] && keys[i] == hi && keys_lo[i] == lo) found = i;
+            int chain = 0; uint32_t s2 = h & (CAP - 1);
+            while (tags[s2] && chain < CAP) { s2 = (s2 + 1) & (CAP - 1); chain++; }
+            printf("MISS key %016llx:%016llx tag %08x start %u chain %d found_at %d tag_there %08x nd %u\n", hi, lo, tag, h & (CAP - 1), chain, found, found >= 0 ? tags[found] : 0u, *n_distinct);
+        }
 #endif
+        flag(2);  // swallowed by a tag collision in B1
     }
 };
 
-// One CTA per minimiser bin.  The bin's records are taken in chunks of RCAP*3/4:
-//   A1  every thread hashes its records whole (16 bytes) into a shared-memory record table: identical super-k-mers --
-//       the same genome window seen by many reads -- collapse into one entry with a multiplicity;
-//   A2  every thread checks that the entry it counted into really holds its record (a 64-bit hash collision sends the
-//       record down a direct path instead), so the collapse is exact;
-//   B   the distinct records are expanded: a warp takes 32 table slots, prefix-sums their k-mer counts and walks the
-//       flattened (record, k-mer) space 32 k-mers per step -- 5-step shuffle binary search for the source record, record
-//       words fetched by shuffle, the k-mer cut straight out of the 2-bit stream, brev-based reverse complement -- and
-//       adds the record's multiplicity to the canonical k-mer's slot of the k-mer table (64-bit atomicCAS + atomicAdd).
-// At 100x coverage phase B sees about one k-mer in eight; the rest of the instances cost one record-level insert per
-// ~10 k-mers.  K4: only rows inside the coverage bounds leave shared memory (block-scan compaction).
-template <int RECW, int CAP, int RCAP, int NT>
-__global__ void __launch_bounds__(NT) count_bins_narrow_kernel(CountArgs A) {
-    static_assert(RECW == 2, "k <= 31 uses 16-byte records");
+// PHASE 0: narrow add.  PHASE 1: wide claim.  PHASE 2: wide count.
+template <bool WIDE, int CAP, int PHASE> struct KmerSink {
+    KmerTable<WIDE, CAP> T;
+    uint32_t depth, cval;
+    __device__ __forceinline__ void operator()(uint64_t key, uint32_t mult) const {
+        uint32_t cls;
+        const uint32_t h = narrow_hash(key, cls);
+        if (depth == 0 || (cls >> (24u - depth)) == cval) T.add(key, h, mult);
+    }
+    __device__ __forceinline__ void operator()(u128 key, uint32_t mult) const {
+        const uint64_t hi = (uint64_t)(key >> 64), lo = (uint64_t)key;
+        // two independent 32-bit lanes: slot = low bits of h1, class = its top bits, tag = h2
+        const uint32_t h1 = lane_a((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+        const uint32_t h2 = lane_b((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+        if (depth != 0 && (h1 >> (32u - depth)) != cval) return;
+        if (PHASE == 1) T.claim(key, h1, h2 | 1u);
+        else T.count(key, h1, h2 | 1u, mult);
+    }
+};
+
+// Warp-cooperative expansion of up to 32 records (one per lane: words w[], nk k-mers, multiplicity mult; nk = 0 for
+// an idle lane) into canonical k-mers: sink(key, mult) is called once per k-mer, 32 k-mers per step.
+template <bool WIDE, class Sink>
+__device__ __forceinline__ void expand_warp(const uint64_t* w, uint32_t nk, uint32_t mult, int k, int lane, const Sink& sink, volatile uint32_t* overflow) {
+    uint32_t pi = nk;  // inclusive prefix of k-mer counts over the warp's 32 records
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
+    const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
+    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        uint32_t s = 0;  // number of records whose inclusive prefix is <= t  ==  source record of k-mer t
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
+            if (pv <= t) s += step;
+        }
+        s &= 31;
+        const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
+        const uint32_t nks = __shfl_sync(0xffffffffu, nk, s);
+        const uint32_t ms = __shfl_sync(0xffffffffu, mult, s);
+        const uint32_t off = t - (pis - nks);  // k-mer index inside the record
+        const uint32_t b = 16u + 2u * off;     // first bit of the k-mer in the record's bit stream
+        if (!WIDE) {
+            const uint64_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
+            if (t < total) {
+                uint64_t hi;
+                if (b < 64u) hi = (w0 << b) | ((w1 >> 1) >> (63u - b));
+                else hi = w1 << (b - 64u);
+                const uint64_t fwd = hi >> (64 - 2 * k);
+                const uint64_t rc = revcomp(fwd, k);
+                sink(fwd < rc ? fwd : rc, ms);
+            }
+        } else {
+            const uint64_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
+            const uint64_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
+            if (t < total) {
+                // 128 bits starting at bit b of the 256-bit stream w0 w1 w2 w3
+                const uint32_t wi = b >> 6, sh = b & 63u;
+                const uint64_t a0 = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
+                const uint64_t a1 = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : 0ull;
+                const uint64_t a2 = wi == 0 ? w2 : wi == 1 ? w3 : 0ull;
+                const uint64_t hi = (a0 << sh) | ((a1 >> 1) >> (63u - sh));
+                const uint64_t lo = (a1 << sh) | ((a2 >> 1) >> (63u - sh));
+                const u128 fwd = (((u128)hi << 64) | lo) >> (128 - 2 * k);
+                const u128 rc = revcomp(fwd, k);
+                sink(fwd < rc ? fwd : rc, ms);  // forward on a tie (Counter64.java:686)
+            }
+        }
+        if (__any_sync(0xffffffffu, *overflow)) break;
+    }
+}
+
+// ---- bulk-copy / mbarrier plumbing (PTX; sm_90+) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+
+constexpr int CNT_STAGES = 2;
+constexpr uint32_t BIN_END = 0xffffffffu;
+
+// what the producer warp hands over per bin
+struct BinDesc {
+    unsigned long long seg_beg[MAX_SEG];  // first record of the bin inside each segment
+    uint32_t seg_pre[MAX_SEG + 1];        // bin-local index of the first record of each segment
+    uint32_t bin;
+};
+
+// issue the bulk copies that bring records [cbeg, cbeg + cn) of the bin into `dst`; one thread
+template <int RECW>
+__device__ __forceinline__ void issue_chunk(const CountArgs& A, const BinDesc& D, int n_seg, uint32_t cbeg, uint32_t cn, uint64_t* dst, uint64_t* bar) {
+    mbar_expect_tx(bar, cn * (uint32_t)(RECW * 8));
+    const uint32_t cend = cbeg + cn;
+    for (int s = 0; s < n_seg; s++) {
+        const uint32_t lo = D.seg_pre[s] > cbeg ? D.seg_pre[s] : cbeg;
+        const uint32_t hi = D.seg_pre[s + 1] < cend ? D.seg_pre[s + 1] : cend;
+        if (lo < hi) bulk_g2s(dst + (size_t)(lo - cbeg) * RECW, A.records + (D.seg_beg[s] + (lo - D.seg_pre[s])) * RECW, (hi - lo) * (uint32_t)(RECW * 8), bar);
+    }
+}
+
+// NT compute threads + one producer warp.  The producer draws bin tickets, reads the bin's segment offsets and
+// bulk-copies its first chunk of records into one of CNT_STAGES shared-memory buffers while the compute warps are
+// still busy with the previous bin; full[]/empty[] mbarriers hand the stages back and forth.
+template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM>
+__global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A) {
+    using KT = typename std::conditional<WIDE, u128, uint64_t>::type;
+    constexpr int RECW = WIDE ? 4 : 2;
     constexpr int CHUNK = RCAP * 3 / 4;
     static_assert(CHUNK % NT == 0, "chunk must be a whole number of records per thread");
     constexpr int PER_THREAD = CHUNK / NT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    ulonglong2* rrec = reinterpret_cast<ulonglong2*>(keys + CAP);
-    unsigned long long* rhash = reinterpret_cast<unsigned long long*>(rrec + RCAP);
-    uint32_t* cnts = reinterpret_cast<uint32_t*>(rhash + RCAP);
-    uint32_t* rmult = cnts + CAP;
-    uint16_t* ulist = reinterpret_cast<uint16_t*>(rmult + RCAP);  // slots of the distinct records of the chunk, in claim order
-    __shared__ uint32_t s_distinct, s_overflow, s_sp, s_nuniq;
+    constexpr int NW = NT / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* rbuf = reinterpret_cast<uint64_t*>(smem_raw);  // [CNT_STAGES][CHUNK * RECW]
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rbuf + (size_t)CNT_STAGES * CHUNK * RECW);
+    unsigned long long* keys_lo = keys + CAP;
+    uint32_t* tags = reinterpret_cast<uint32_t*>(keys + (WIDE ? 2 * CAP : CAP));
+    uint32_t* cnts = tags + (WIDE ? CAP : 0);
+    uint32_t* rtag = cnts + CAP;
+    uint32_t* rmult = rtag + RCAP;
+    uint16_t* ridx = reinterpret_cast<uint16_t*>(rmult + RCAP);
+    uint16_t* ulist = ridx + RCAP;   // [CHUNK] entries of the chunk: slot (< RCAP) or RCAP + record index (a record that lost a tag collision)
+    uint16_t* klist = ulist + CHUNK; // [KMAX]
+    __shared__ uint32_t s_distinct, s_overflow, s_sp, s_nuniq, s_npass, s_cursor, s_early;
     __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
-    __shared__ uint32_t s_warp_tot[NT / 32];
     __shared__ unsigned long long s_out_base;
+    __shared__ BinDesc s_desc[CNT_STAGES];
+    __shared__ __align__(8) uint64_t s_full[CNT_STAGES], s_empty[CNT_STAGES], s_aux;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = A.k;
-    const int kshift = 64 - 2 * k;
+    const int n_seg = A.n_seg;
 
-    for (uint32_t bin = blockIdx.x; bin < A.n_bins; bin += gridDim.x) {
-        __syncthreads();  // every thread has left the previous bin's class loop before the stack is re-armed
-        if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
-        __syncthreads();
+    if (tid == 0) {
+        for (int i = 0; i < CNT_STAGES; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        mbar_init(&s_aux, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp < NW) {
+        for (int i = tid; i < CAP; i += NT) { if (WIDE) tags[i] = 0u; else keys[i] = ~0ull; cnts[i] = 0u; }
+        for (int i = tid; i < RCAP; i += NT) { rtag[i] = 0u; rmult[i] = 0u; }
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ---------------- producer warp ----------------
+        uint32_t it = 0;
         while (true) {
-            __syncthreads();
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(&A.dstat[DS_TICKET], 1ull);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            const bool end = t >= (unsigned long long)A.n_bins;
+            const uint32_t bin = end ? 0u : (uint32_t)t;
+            // per-segment extent of the bin: lanes over segments
+            uint32_t tot = 0;
+            unsigned long long my_beg[(MAX_SEG + 31) / 32];
+            uint32_t my_cnt[(MAX_SEG + 31) / 32], my_pre[(MAX_SEG + 31) / 32];
+#pragma unroll
+            for (int r = 0; r < (MAX_SEG + 31) / 32; r++) {
+                const int sg = r * 32 + lane;
+                my_beg[r] = 0; my_cnt[r] = 0;
+                if (!end && sg < n_seg) {
+                    const uint64_t* so = A.seg_off + (size_t)sg * (A.n_bins + 1);
+                    const uint64_t o0 = so[0], ob = so[bin], oe = so[bin + 1];
+                    my_beg[r] = A.seg_base[sg] + ob - o0;
+                    my_cnt[r] = (uint32_t)(oe - ob);
+                }
+                uint32_t incl = my_cnt[r];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+                my_pre[r] = tot + incl - my_cnt[r];
+                tot += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (!end && tot == 0) continue;  // empty bin: nothing to hand over
+            const int st = (int)(it % CNT_STAGES);
+            if (it >= (uint32_t)CNT_STAGES) mbar_wait(&s_empty[st], ((it / CNT_STAGES) - 1) & 1);
+            BinDesc& D = s_desc[st];
+#pragma unroll
+            for (int r = 0; r < (MAX_SEG + 31) / 32; r++) {
+                const int sg = r * 32 + lane;
+                if (sg < n_seg) { D.seg_beg[sg] = my_beg[r]; D.seg_pre[sg] = my_pre[r]; }
+            }
+            if (lane == 0) { D.seg_pre[n_seg] = tot; D.bin = end ? BIN_END : bin; }
+            __syncwarp();
+            if (lane == 0) {
+                if (end) mbar_arrive(&s_full[st]);
+                else issue_chunk<RECW>(A, D, n_seg, 0u, tot < (uint32_t)CHUNK ? tot : (uint32_t)CHUNK, rbuf + (size_t)st * CHUNK * RECW, &s_full[st]);
+            }
+            if (end) break;
+            it++;
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    const KmerTable<WIDE, CAP> T{keys, keys_lo, tags, cnts, klist, &s_distinct, &s_overflow, A.dstat + DS_OVF_WHY};
+    auto clear_all = [&]() {
+        for (int i = tid; i < CAP; i += NT) { if (WIDE) tags[i] = 0u; else keys[i] = ~0ull; cnts[i] = 0u; }
+        for (int i = tid; i < RCAP; i += NT) { rtag[i] = 0u; rmult[i] = 0u; }
+    };
+    uint32_t aux_phase = 0;
+    for (uint32_t it = 0;; it++) {
+        const int st = (int)(it % CNT_STAGES);
+        mbar_wait(&s_full[st], (it / CNT_STAGES) & 1);
+        const BinDesc& D = s_desc[st];
+        if (D.bin == BIN_END) break;
+        const uint64_t* buf = rbuf + (size_t)st * CHUNK * RECW;
+        const uint32_t n_rec = D.seg_pre[n_seg];
+        bool staged = true;  // the buffer holds chunk 0 of the bin
+        compute_barrier<NT>();  // every thread has left the previous bin's class loop before the stack is re-armed
+        if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
+        while (true) {
+            compute_barrier<NT>();
             if (s_sp == 0) break;
             const uint32_t depth = s_stack_depth[s_sp - 1], cval = s_stack_val[s_sp - 1];
-            __syncthreads();
-            if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; }
-            for (int i = tid; i < CAP; i += NT) { keys[i] = ~0ull; cnts[i] = 0; }
-            const uint32_t cshift = 24u - depth;  // class = top `depth` bits of a 24-bit second hash
-            const NarrowTable T{keys, cnts, &s_distinct, &s_overflow, depth, cval};
-            for (int seg = 0; seg < A.n_seg; seg++) {
-            const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
-            const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
-            for (uint64_t cbeg = beg; cbeg < end; cbeg += CHUNK) {
-                for (int i = tid; i < RCAP; i += NT) { rhash[i] = ~0ull; rmult[i] = 0; }
+            compute_barrier<NT>();
+            if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; s_npass = 0; s_cursor = 0; s_early = 0; }
+            for (uint32_t cbeg = 0; cbeg < n_rec; cbeg += CHUNK) {
+                const uint32_t cn = n_rec - cbeg < (uint32_t)CHUNK ? n_rec - cbeg : (uint32_t)CHUNK;
                 if (tid == 0) s_nuniq = 0;
-                __syncthreads();
+                if (!(staged && cbeg == 0)) {
+                    // later chunks and sub-class re-runs: fetched on demand (every thread is past its reads of the buffer)
+                    compute_barrier<NT>();
+                    if (tid == 0) issue_chunk<RECW>(A, D, n_seg, cbeg, cn, const_cast<uint64_t*>(buf), &s_aux);
+                    mbar_wait(&s_aux, aux_phase);
+                    aux_phase ^= 1u;
+                    staged = false;
+                }
+                compute_barrier<NT>();
                 if (s_overflow) break;
-                const uint64_t cend = cbeg + CHUNK < end ? cbeg + CHUNK : end;
                 // ---- A1: collapse identical records ----
+                uint64_t v[PER_THREAD][RECW];
                 uint32_t myslot[PER_THREAD];
 #pragma unroll
                 for (int j = 0; j < PER_THREAD; j++) {
-                    const uint64_t r = cbeg + (uint64_t)j * NT + tid;
+                    const uint32_t li = (uint32_t)j * NT + tid;  // chunk-local record index
                     myslot[j] = 0xffffffffu;
-                    if (r < cend) {
-                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
-                        const uint64_t h = record_hash(v.x, v.y);
-                        uint32_t slot = (uint32_t)(h >> 20) & (RCAP - 1);
+                    if (li < cn) {
+#pragma unroll
+                        for (int q = 0; q < RECW; q += 2) {
+                            const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
+                            v[j][q] = x.x; v[j][q + 1] = x.y;
+                        }
+                        uint32_t h, tag;
+                        record_hash<RECW>(v[j], h, tag);
+                        uint32_t slot = h & (RCAP - 1);
                         while (true) {  // at most CHUNK < RCAP entries: an empty slot always exists
-                            unsigned long long cur = rhash[slot];
-                            if (cur == ~0ull) {
-                                cur = atomicCAS(&rhash[slot], ~0ull, (unsigned long long)h);
-                                if (cur == ~0ull) { rrec[slot] = v; ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)slot; break; }
+                            uint32_t cur = rtag[slot];
+                            if (cur == 0u) {
+                                cur = atomicCAS(&rtag[slot], 0u, tag);
+                                if (cur == 0u) { ridx[slot] = (uint16_t)li; ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)slot; break; }
                             }
-                            if (cur == h) break;
+                            if (cur == tag) break;
                             slot = (slot + 1) & (RCAP - 1);
                         }
                         atomicAdd(&rmult[slot], 1u);
                         myslot[j] = slot;
                     }
                 }
-                __syncthreads();
-                // ---- A2: confirm (records are re-read: L1/L2 hits) ----
+                compute_barrier<NT>();
+                // ---- A2: confirm against the claimant's record ----
 #pragma unroll
                 for (int j = 0; j < PER_THREAD; j++) {
                     if (myslot[j] != 0xffffffffu) {
-                        const uint64_t r = cbeg + (uint64_t)j * NT + tid;
-                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW);
-                        const ulonglong2 t = rrec[myslot[j]];
-                        if (t.x != v.x || t.y != v.y) {
-                            atomicSub(&rmult[myslot[j]], 1u);
-                            uint64_t rec[RECW] = {v.x, v.y};
-                            rec_foreach_kmer<uint64_t, RECW>(rec, k, DirectInsert<CAP>{T});
+                        const uint32_t li = (uint32_t)j * NT + tid;
+                        const uint32_t ci = ridx[myslot[j]];
+                        if (ci != li) {
+                            bool same = true;
+#pragma unroll
+                            for (int q = 0; q < RECW; q += 2) {
+                                const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)ci * RECW + q);
+                                same = same && x.x == v[j][q] && x.y == v[j][q + 1];
+                            }
+                            if (!same) {
+                                atomicSub(&rmult[myslot[j]], 1u);
+                                ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)(RCAP + li);
+                            }
                         }
                     }
                 }
-                __syncthreads();
-                // ---- B: expand the distinct records ----
+                compute_barrier<NT>();
+                // ---- B: expand the distinct records, spread evenly over the warps ----
                 const int n_uniq = (int)s_nuniq;
-                for (int ubase = warp * 32; ubase < n_uniq; ubase += NT) {
-                    if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
-                    const int u = ubase + lane;
-                    uint32_t mult = 0;
-                    ulonglong2 v = make_ulonglong2(0ull, 0ull);
-                    if (u < n_uniq) { const int slot = ulist[u]; mult = rmult[slot]; if (mult) v = rrec[slot]; }
-                    const uint32_t nk = mult ? (uint32_t)(v.x >> 48) : 0u;
-                    uint32_t pi = nk;  // inclusive prefix of k-mer counts over the warp's 32 table slots
+                int per = (n_uniq + NW - 1) / NW;
+                per = per < 4 ? 4 : per > 32 ? 32 : per;
+#pragma unroll 1
+                for (int pass = 0; pass < (WIDE ? 2 : 1); pass++) {
+                    const bool last = pass == (WIDE ? 1 : 0);
+                    for (int ubase = warp * per; ubase < n_uniq; ubase += NW * per) {
+                        if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
+                        const int u = ubase + lane;
+                        uint32_t mult = 0, nk = 0;
+                        uint64_t w[RECW];
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
-                    const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
-                    for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-                        const uint32_t t = t0 + lane;
-                        uint32_t s = 0;  // number of slots whose inclusive prefix is <= t  ==  source slot of k-mer t
+                        for (int q = 0; q < RECW; q++) w[q] = 0ull;
+                        if (lane < per && u < n_uniq) {
+                            const uint32_t e = ulist[u];
+                            uint32_t li;
+                            if (e < (uint32_t)RCAP) {
+                                mult = rmult[e]; li = ridx[e];
+                                if (last) { rtag[e] = 0u; rmult[e] = 0u; }  // the slot is this lane's alone: leave it clean
+                            } else { mult = 1u; li = e - RCAP; }
+                            if (mult) {
 #pragma unroll
-                        for (int step = 16; step; step >>= 1) {
-                            const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
-                            if (pv <= t) s += step;
+                                for (int q = 0; q < RECW; q += 2) {
+                                    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
+                                    w[q] = x.x; w[q + 1] = x.y;
+                                }
+                                nk = (uint32_t)(w[0] >> 48);
+                            }
                         }
-                        s &= 31;
-                        const uint64_t w0 = __shfl_sync(0xffffffffu, v.x, s), w1 = __shfl_sync(0xffffffffu, v.y, s);
-                        const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
-                        const uint32_t ms = __shfl_sync(0xffffffffu, mult, s);
-                        if (t < total) {
-                            const uint32_t off = t - (pis - (uint32_t)(w0 >> 48));  // k-mer index inside the record
-                            const uint32_t b = 16u + 2u * off;                      // first bit of the k-mer in the 128-bit stream
-                            uint64_t hi;
-                            if (b < 64u) hi = (w0 << b) | (w1 >> (64u - b));
-                            else hi = w1 << (b - 64u);
-                            const uint64_t fwd = hi >> kshift;
-                            const uint64_t rc = revcomp(fwd, k);
-                            const uint64_t key = fwd < rc ? fwd : rc;
-                            const uint32_t h = narrow_hash(key);
-                            if (depth == 0 || (narrow_class(key, h) >> cshift) == cval)
-                                insert_narrow<CAP>(keys, cnts, &s_distinct, &s_overflow, key, h, ms);
-                        }
+                        if (!WIDE) expand_warp<false>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 0>{T, depth, cval}, &s_overflow);
+                        else if (pass == 0) expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 1>{T, depth, cval}, &s_overflow);
+                        else expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 2>{T, depth, cval}, &s_overflow);
                     }
+                    compute_barrier<NT>();
                 }
-                __syncthreads();
+                if (s_overflow && tid == 0 && 2 * (cbeg + cn) <= n_rec) s_early = 1;  // overflowed within the first half
             }
-            }
-            __syncthreads();
+            compute_barrier<NT>();
             if (s_overflow) {
-                // too many distinct k-mers for the table: split this class in two by the next hash bit
+                // too many distinct k-mers for the table: split this class by the next hash bit(s)
+                const uint32_t bits = s_early ? 2u : 1u;
+                compute_barrier<NT>();
                 if (tid == 0) {
-                    if (depth >= 22 || s_sp + 2 > CNT_STACK) {
+                    if (depth + bits > 20 || s_sp + (1u << bits) > CNT_STACK) {
                         atomicExch(&A.dstat[DS_OVERFLOW], 2ull);
                     } else {
-                        s_stack_val[s_sp] = cval << 1; s_stack_depth[s_sp] = depth + 1; s_sp++;
-                        s_stack_val[s_sp] = (cval << 1) | 1u; s_stack_depth[s_sp] = depth + 1; s_sp++;
+                        for (uint32_t c = 0; c < (1u << bits); c++) { s_stack_val[s_sp] = (cval << bits) | c; s_stack_depth[s_sp] = depth + bits; s_sp++; }
                         atomicAdd(&A.dstat[DS_SPLITS], 1ull);
                     }
                 }
+                clear_all();
+                staged = false;
                 continue;
             }
-            // K4: coverage filter + compaction.  Block-wide exclusive scan of per-thread survivor counts.
+            if (n_rec > (uint32_t)CHUNK) staged = false;
+            // ---- K4: coverage filter + compaction over the occupied slots ----
+            const uint32_t nd = s_distinct;
             uint32_t mine = 0, inst = 0;
-            for (int i = tid; i < CAP; i += NT) {
-                const uint32_t cn = cnts[i];
-                inst += cn;
-                mine += (cn >= A.min_count && cn <= A.max_count && keys[i] != ~0ull) ? 1u : 0u;
+            for (uint32_t i = tid; i < nd; i += NT) {
+                const uint32_t c = cnts[klist[i]];
+                inst += c;
+                mine += (c >= A.min_count && c <= A.max_count) ? 1u : 0u;
             }
-            uint32_t incl = mine;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) inst += __shfl_xor_sync(0xffffffffu, inst, d);
-            if (lane == 31) s_warp_tot[warp] = incl;
-            __syncthreads();
+            for (int d = 16; d > 0; d >>= 1) { mine += __shfl_xor_sync(0xffffffffu, mine, d); inst += __shfl_xor_sync(0xffffffffu, inst, d); }
+            if (lane == 0) {
+                if (mine) atomicAdd(&s_npass, mine);
+                if (inst) atomicAdd(&A.dstat[DS_INSTANCES], (unsigned long long)inst);
+            }
+            compute_barrier<NT>();
             if (tid == 0) {
-                uint32_t tot = 0;
-                for (int w = 0; w < NT / 32; w++) { uint32_t t = s_warp_tot[w]; s_warp_tot[w] = tot; tot += t; }
+                const uint32_t tot = s_npass;
                 s_out_base = tot ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
-                atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)s_distinct);
+                atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)nd);
                 if (s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
             }
-            if (lane == 0 && inst) atomicAdd(&A.dstat[DS_INSTANCES], (unsigned long long)inst);
-            __syncthreads();
-            unsigned long long o = s_out_base + s_warp_tot[warp] + (incl - mine);
-            if (o + mine <= A.out_cap) {
-                uint64_t* ok = reinterpret_cast<uint64_t*>(A.out_keys);
-                for (int i = tid; i < CAP; i += NT) {
-                    const uint32_t cn = cnts[i];
-                    if (cn >= A.min_count && cn <= A.max_count && keys[i] != ~0ull) { ok[o] = keys[i]; A.out_counts[o] = cn; o++; }
+            compute_barrier<NT>();
+            const bool room = s_out_base + s_npass <= A.out_cap;
+            for (uint32_t i0 = (uint32_t)warp * 32u; i0 < nd; i0 += NT) {
+                const uint32_t i = i0 + lane;
+                bool keep = false;
+                uint32_t c = 0, slot = 0;
+                if (i < nd) {
+                    slot = klist[i];
+                    c = cnts[slot];
+                    keep = c >= A.min_count && c <= A.max_count;
+                }
+                const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                uint32_t base = 0;
+                if (lane == 0 && ball) base = atomicAdd(&s_cursor, (uint32_t)__popc(ball));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (i < nd) {
+                    if (keep && room) {
+                        const unsigned long long o = s_out_base + base + (uint32_t)__popc(ball & ((1u << lane) - 1u));
+                        if (!WIDE) reinterpret_cast<uint64_t*>(A.out_keys)[o] = keys[slot];
+                        else reinterpret_cast<KT*>(A.out_keys)[o] = ((u128)keys[slot] << 64) | keys_lo[slot];
+                        A.out_counts[o] = c;
+                    }
+                    if (WIDE) tags[slot] = 0u; else keys[slot] = ~0ull;
+                    cnts[slot] = 0u;
                 }
             }
         }
+        // the class loop left through a compute barrier: every thread is done with the stage
+        if (tid == 0) mbar_arrive(&s_empty[st]);
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k in 32..63: 128-bit keys
-//   tags[slot]  : 0 = empty, else 1 | (31-bit fingerprint << 1)     (claimed with a 32-bit CAS)
-//   keys[slot]  : the 128-bit key, written by the claiming thread right after the CAS
-// Pass A inserts (claims + publishes keys; a thread that meets an equal tag assumes "same key").
-// After a barrier every key is visible.  Pass B walks the records again and, for every k-mer, probes
-// until it finds the slot whose full key matches, then counts.  If pass A merged two different keys
-// that share slot sequence and fingerprint, pass B does not find the second key: it flags overflow
-// and the class is split (different class hash bits separate the pair), so counts stay exact.
-// ---------------------------------------------------------------------------------------------
-template <int CAP> struct InsertWide {
-    uint32_t* tags;
-    u128* keys;
-    uint32_t* n_distinct;
-    volatile uint32_t* overflow;
-    uint32_t cls_mask, cls_val;
-    RFX_HD void operator()(u128 key) const {
-#if defined(__CUDA_ARCH__)
-        const uint64_t h = key_hash(key);
-        if (((uint32_t)(h >> 43) & cls_mask) != cls_val) return;  // class = hash bits 43..63
-        const uint32_t tag = 1u | ((uint32_t)(h >> 12) << 1);  // fingerprint = hash bits 12..42
-        uint32_t slot = (uint32_t)h & (CAP - 1);
-        for (int probe = 0; probe < CAP; probe++) {
-            uint32_t cur = tags[slot];
-            if (cur == 0u) cur = atomicCAS(&tags[slot], 0u, tag);
-            if (cur == 0u) {
-                keys[slot] = key;
-                if (atomicAdd(n_distinct, 1u) >= (uint32_t)(CAP * 3 / 4)) *overflow = 1u;
-                return;
-            }
-            if (cur == tag) return;  // presumed equal; verified in pass B
-            slot = (slot + 1) & (CAP - 1);
-        }
-        *overflow = 1u;
-#else
-        (void)key;
-#endif
-    }
-};
-
-template <int CAP> struct CountWide {
-    const uint32_t* tags;
-    const u128* keys;
-    uint32_t* cnts;
-    volatile uint32_t* overflow;
-    uint32_t cls_mask, cls_val;
-    RFX_HD void operator()(u128 key) const {
-#if defined(__CUDA_ARCH__)
-        const uint64_t h = key_hash(key);
-        if (((uint32_t)(h >> 43) & cls_mask) != cls_val) return;  // class = hash bits 43..63
-        uint32_t slot = (uint32_t)h & (CAP - 1);
-        for (int probe = 0; probe < CAP; probe++) {
-            if (tags[slot] == 0u) break;
-            if (keys[slot] == key) { atomicAdd(&cnts[slot], 1u); return; }
-            slot = (slot + 1) & (CAP - 1);
-        }
-        *overflow = 1u;  // key was swallowed by a fingerprint collision in pass A
-#else
-        (void)key;
-#endif
-    }
-};
-
-template <int RECW, int CAP>
-__global__ void __launch_bounds__(CNT_THREADS) count_bins_wide_kernel(CountArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u128* keys = reinterpret_cast<u128*>(smem_raw);
-    uint32_t* tags = reinterpret_cast<uint32_t*>(keys + CAP);
-    uint32_t* cnts = tags + CAP;
-    __shared__ uint32_t s_distinct, s_overflow, s_sp;
-    __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
-    __shared__ uint32_t s_warp_tot[CNT_THREADS / 32];
-    __shared__ unsigned long long s_out_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (uint32_t bin = blockIdx.x; bin < A.n_bins; bin += gridDim.x) {
-        __syncthreads();  // every thread has left the previous bin's class loop before the stack is re-armed
-        if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
-        __syncthreads();
-        while (true) {
-            __syncthreads();
-            if (s_sp == 0) break;
-            const uint32_t depth = s_stack_depth[s_sp - 1], cval = s_stack_val[s_sp - 1];
-            __syncthreads();
-            if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; }
-            for (int i = tid; i < CAP; i += CNT_THREADS) { tags[i] = 0u; cnts[i] = 0u; }
-            __syncthreads();
-            const uint32_t cmask = (1u << depth) - 1u;
-            InsertWide<CAP> ins{tags, keys, &s_distinct, &s_overflow, cmask, cval};
-            for (int seg = 0; seg < A.n_seg; seg++) {
-            const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
-            const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
-            for (uint64_t r = beg + tid; r < end; r += CNT_THREADS) {
-                if (*(volatile uint32_t*)&s_overflow) break;
-                uint64_t rec[RECW];
-#pragma unroll
-                for (int i = 0; i < RECW; i += 2) {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW + i);
-                    rec[i] = v.x; rec[i + 1] = v.y;
-                }
-                rec_foreach_kmer<u128, RECW>(rec, A.k, ins);
-            }
-            }
-            __syncthreads();
-            if (!s_overflow) {
-                CountWide<CAP> cnt{tags, keys, cnts, &s_overflow, cmask, cval};
-                for (int seg = 0; seg < A.n_seg; seg++) {
-                const uint64_t* so = A.seg_off + (size_t)seg * (A.n_bins + 1);
-                const uint64_t beg = A.seg_base[seg] + so[bin] - so[0], end = A.seg_base[seg] + so[bin + 1] - so[0];
-                for (uint64_t r = beg + tid; r < end; r += CNT_THREADS) {
-                    if (*(volatile uint32_t*)&s_overflow) break;
-                    uint64_t rec[RECW];
-#pragma unroll
-                    for (int i = 0; i < RECW; i += 2) {
-                        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(A.records + r * RECW + i);
-                        rec[i] = v.x; rec[i + 1] = v.y;
-                    }
-                    rec_foreach_kmer<u128, RECW>(rec, A.k, cnt);
-                }
-                }
-                __syncthreads();
-            }
-            if (s_overflow) {
-                if (tid == 0) {
-                    if (depth >= 20 || s_sp + 2 > CNT_STACK) {
-                        atomicExch(&A.dstat[DS_OVERFLOW], 2ull);
-                    } else {
-                        s_stack_val[s_sp] = cval; s_stack_depth[s_sp] = depth + 1; s_sp++;
-                        s_stack_val[s_sp] = cval | (1u << depth); s_stack_depth[s_sp] = depth + 1; s_sp++;
-                        atomicAdd(&A.dstat[DS_SPLITS], 1ull);
-                    }
-                }
-                continue;
-            }
-            uint32_t mine = 0, inst = 0;
-            for (int i = tid; i < CAP; i += CNT_THREADS) {
-                const uint32_t cn = cnts[i];
-                inst += cn;
-                mine += (cn >= A.min_count && cn <= A.max_count && tags[i] != 0u) ? 1u : 0u;
-            }
-            uint32_t incl = mine;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) inst += __shfl_xor_sync(0xffffffffu, inst, d);
-            if (lane == 31) s_warp_tot[warp] = incl;
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t tot = 0;
-                for (int w = 0; w < CNT_THREADS / 32; w++) { uint32_t t = s_warp_tot[w]; s_warp_tot[w] = tot; tot += t; }
-                s_out_base = tot ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
-                atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)s_distinct);
-                if (s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
-            }
-            if (lane == 0 && inst) atomicAdd(&A.dstat[DS_INSTANCES], (unsigned long long)inst);
-            __syncthreads();
-            unsigned long long o = s_out_base + s_warp_tot[warp] + (incl - mine);
-            if (o + mine <= A.out_cap) {
-                u128* ok = reinterpret_cast<u128*>(A.out_keys);
-                for (int i = tid; i < CAP; i += CNT_THREADS) {
-                    const uint32_t cn = cnts[i];
-                    if (cn >= A.min_count && cn <= A.max_count && tags[i] != 0u) { ok[o] = keys[i]; A.out_counts[o] = cn; o++; }
-                }
-            }
-        }
-    }
+// geometry (shared memory per CTA -> CTAs per SM):
+//   k <= 31: 2 x 768 x 16 B record stages + 4096 x 12 B k-mer table + lists + 1024-entry record-tag table = 89.5 KB -> 2
+//   k  > 31: 2 x 192 x 32 B record stages + 2048 x 24 B k-mer table + lists + 256-entry record-tag table  =  66 KB -> 3
+template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t launch_count(const CountArgs& A, cudaStream_t st) {
+    const size_t smem = (size_t)CNT_STAGES * (RCAP * 3 / 4) * (WIDE ? 32 : 16) + (size_t)CAP * (WIDE ? 24 : 12) + (size_t)RCAP * 10 +
+                        (size_t)(RCAP * 3 / 4) * 2 + (size_t)(CAP * 3 / 4) * 2;
+    cudaError_t e = cudaFuncSetAttribute(count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = 148u * PER_SM;
+    if (grid > A.n_bins) grid = A.n_bins;
+    count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM><<<grid, NT + 32, smem, st>>>(A);
+    return cudaGetLastError();
 }
-
-constexpr int CAP_NARROW = 2048;   // k-mer table: 2048 * (8 + 4) B = 24 KB
-constexpr int RCAP_NARROW = 1024;  // record table: 1024 * (16 + 8 + 4 + 2) B = 30 KB   -> 54 KB / CTA, 4 CTAs / SM
-constexpr int CAP_WIDE = 4096;    // 4096 * (16 + 4 + 4) B = 96 KB -> 2 CTAs / SM
 
 int stage_count(Ctx* c) {
     cudaStream_t st = c->stream;
@@ -501,26 +641,23 @@ int stage_count(Ctx* c) {
     A.out_keys = c->keys.p; A.out_counts = c->counts.as<uint32_t>();
     A.dstat = c->dstat.as<unsigned long long>();
     A.out_cap = cap;
+    if (A.n_seg > MAX_SEG) return ctx_fail(c, RFX_E_INVALID, "more than %d record segments", MAX_SEG);
     if (c->n_records) {
         cudaEventRecord(c->evk[4], st);
+        cudaError_t le;
+        const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob
+        const std::string vs = variant ? variant : "";
         if (!c->wide) {
-            const size_t smem = (size_t)CAP_NARROW * 12 + (size_t)RCAP_NARROW * 30;
-            unsigned grid = c->n_bins < 148u * 4u * 8u ? c->n_bins : 148u * 4u * 8u;
-            const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob: "big" = 512 threads, 2048-entry record table
-            if (variant && !strcmp(variant, "big")) {
-                const size_t smem2 = (size_t)CAP_NARROW * 12 + (size_t)2048 * 30;
-                RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, 2048, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                count_bins_narrow_kernel<2, CAP_NARROW, 2048, 512><<<grid, 512, smem2, st>>>(A);
-            } else {
-                RFX_CUDA(c, cudaFuncSetAttribute(count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW, CNT_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                count_bins_narrow_kernel<2, CAP_NARROW, RCAP_NARROW, CNT_THREADS><<<grid, CNT_THREADS, smem, st>>>(A);
-            }
+            if (vs == "a") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
+            else if (vs == "b") le = launch_count<false, 2048, 1024, 256, 3>(A, st);
+            else if (vs == "c") le = launch_count<false, 2048, 512, 128, 5>(A, st);
+            else if (vs == "d") le = launch_count<false, 4096, 512, 128, 3>(A, st);
+            else le = launch_count<false, 4096, 1024, 256, 2>(A, st);
         } else {
-            const size_t smem = (size_t)CAP_WIDE * 24;
-            RFX_CUDA(c, cudaFuncSetAttribute(count_bins_wide_kernel<4, CAP_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            unsigned grid = c->n_bins < 148u * 2u * 8u ? c->n_bins : 148u * 2u * 8u;
-            count_bins_wide_kernel<4, CAP_WIDE><<<grid, CNT_THREADS, smem, st>>>(A);
+            if (vs == "a") le = launch_count<true, 4096, 512, 384, 1>(A, st);
+            else le = launch_count<true, 2048, 256, 192, 3>(A, st);
         }
+        if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count kernel launch failed: %s", cudaGetErrorString(le));
         cudaEventRecord(c->evk[5], st);
         c->launches++;
     }
@@ -531,7 +668,10 @@ int stage_count(Ctx* c) {
     c->ms[2] += stage_end(c);
     c->ms_kernel[2] = 0;
     if (c->n_records) cudaEventElapsedTime(&c->ms_kernel[2], c->evk[4], c->evk[5]);
-    if (h[DS_OVERFLOW] == 2) return ctx_fail(c, RFX_E_CAPACITY, "a counting bin could not be split further");
+    if (h[DS_OVERFLOW] == 2)
+        return ctx_fail(c, RFX_E_CAPACITY, "a counting bin could not be split further (splits %llu: table full %llu, probe exhausted %llu, tag collision %llu, %llu)",
+                        (unsigned long long)h[DS_SPLITS], (unsigned long long)h[DS_OVF_WHY], (unsigned long long)h[DS_OVF_WHY + 1],
+                        (unsigned long long)h[DS_OVF_WHY + 2], (unsigned long long)h[DS_OVF_WHY + 3]);
     if (h[DS_OVERFLOW] == 1 || h[DS_OUT_CURSOR] > cap)
         return ctx_fail(c, RFX_E_CAPACITY, "filtered table needs %llu rows, capacity %llu: raise table_capacity",
                         (unsigned long long)h[DS_OUT_CURSOR], (unsigned long long)cap);

@@ -140,7 +140,9 @@ enum {
     DS_SPILL = 12,
     DS_NSPL = 13,
     DS_FQ_STATE = 14,  // lineMark carried between the chunks of one rfx_push_fastq call
-    DS_NSLOTS = 16
+    DS_TICKET = 15,    // next bin handed to a counting CTA
+    DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
+    DS_NSLOTS = 24
 };
 
 static const uint32_t NONE32 = 0xffffffffu;
@@ -153,6 +155,7 @@ int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);
 int stage_graph(Ctx* c);
+uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards);
 
 inline void stage_begin(Ctx* c) { cudaEventRecord(c->ev0, c->stream); }
 inline float stage_end(Ctx* c) {

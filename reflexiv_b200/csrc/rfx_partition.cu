@@ -281,15 +281,21 @@ struct BinOffsetOut {
 
 __global__ void set_last_offset_kernel(uint64_t* off, uint64_t n_bins, const uint64_t* total) { off[n_bins] = *total; }
 
-static uint32_t choose_bins(Ctx* c, int n_shards) {
-    if (c->forced_bins) return c->forced_bins;
-    uint64_t target = c->prm.bin_target_kmers > 0 ? (uint64_t)c->prm.bin_target_kmers : 16384;
-    uint64_t nb = (c->n_instances + target - 1) / target;
+// Bins are sized so that one bin is one chunk of the counting kernel (rfx_count.cu) and its distinct k-mers fit the
+// shared-memory table even when every fourth (k = 31) or second (k = 61) instance is a sequencing-error singleton.
+uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards) {
+    uint64_t target = c->prm.bin_target_kmers > 0 ? (uint64_t)c->prm.bin_target_kmers : (c->wide ? 2048 : 6144);
+    uint64_t nb = (instances + target - 1) / target;
     if (nb < 64) nb = 64;
     if (nb > (1u << 24)) nb = 1u << 24;
     // multiple of the shard count so every shard owns the same number of bins
     nb = (nb + n_shards - 1) / n_shards * n_shards;
     return (uint32_t)nb;
+}
+
+static uint32_t choose_bins(Ctx* c, int n_shards) {
+    if (c->forced_bins) return c->forced_bins;
+    return choose_bin_count(c, c->n_instances, n_shards);
 }
 
 int stage_partition(Ctx* c, int n_shards) {

@@ -187,6 +187,10 @@ class ReflexivContext:
         self._check(self.L.rfx_record_bytes(self._ctx, C.byref(n)), self._ctx)
         return n.value
 
+    def choose_bins(self, global_instances: int, n_shards: int = 1) -> int:
+        """The library's bin count for `global_instances` k-mer instances over `n_shards` shards."""
+        return int(self.L.rfx_choose_bins(self._ctx, global_instances, n_shards))
+
     def partition(self, n_shards: int, n_bins_total: int = 0):
         self._check(self.L.rfx_partition(self._ctx, n_shards, n_bins_total), self._ctx)
 

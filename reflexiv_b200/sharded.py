@@ -29,9 +29,11 @@ def shard_of_bin(bin_id: int, n_bins_total: int, n_shards: int) -> int:
     return bin_id // (n_bins_total // n_shards)
 
 
-def choose_total_bins(global_instances: int, n_shards: int, target_per_bin: int = 16384, lo: int = 64, hi: int = 1 << 24) -> int:
-    """Same rule as the library's single-process choice (rfx_partition.cu: choose_bins), on the GLOBAL instance count,
-    rounded up to a multiple of the shard count so that every rank computes the same number."""
+def choose_total_bins(global_instances: int, n_shards: int, target_per_bin: int = 6144, lo: int = 64, hi: int = 1 << 24) -> int:
+    """Same rule as the library's single-process choice (rfx_partition.cu: choose_bin_count; 6144 instances per bin for
+    k <= 31, 4096 for k > 31), on the GLOBAL instance count, rounded up to a multiple of the shard count so that every
+    rank computes the same number.  With a context at hand prefer ``ctx.choose_bins`` (rfx_choose_bins), which asks
+    the library itself."""
     nb = max(lo, min(hi, -(-global_instances // target_per_bin)))
     return -(-nb // n_shards) * n_shards
 
