@@ -8,7 +8,7 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-so
 rows = list(csv.reader(out.splitlines()))
 fname = None; hdr = None; agg = []
 for r in rows:
-    if len(r) >= 2 and r[0] == "File Name": fname = r[1].split("/")[-1]; continue
+    if len(r) >= 2 and r[0] in ("File Name", "File Path"): fname = r[1].split("/")[-1]; continue
     if len(r) > 5 and r[0] == "Line No": hdr = r; continue
     if hdr is None or len(r) < len(hdr) - 2: continue
     if r[0].isdigit():
@@ -18,6 +18,18 @@ for r in rows:
             except: return 0
         agg.append((fname, int(r[0]), r[1], num(r[ii]), num(r[wi]), num(r[bi]), num(r[hdr.index("stall_long_sb")]), num(r[hdr.index("stall_short_sb")])))
 ti = sum(a[3] for a in agg) or 1; ts = sum(a[4] for a in agg) or 1
+# optional line-range buckets: name=file:lo-hi,... in env BUCKETS
+import os
+if os.environ.get("BUCKETS"):
+    for spec in os.environ["BUCKETS"].split(","):
+        name, rng = spec.split("=")
+        f, lr = rng.split(":")
+        lo, hi = map(int, lr.split("-"))
+        bi = sum(a[3] for a in agg if a[0] == f and lo <= a[1] <= hi)
+        bs = sum(a[4] for a in agg if a[0] == f and lo <= a[1] <= hi)
+        print("bucket %-12s inst %5.1f%%  samples %5.1f%%" % (name, 100 * bi / ti, 100 * bs / ts))
+    for f in sorted(set(a[0] for a in agg)):
+        print("file %-28s inst %5.1f%%  samples %5.1f%%" % (f, 100 * sum(a[3] for a in agg if a[0] == f) / ti, 100 * sum(a[4] for a in agg if a[0] == f) / ts))
 print("total warp instr %d, samples %d" % (ti, ts))
 print(" inst%  samp%  (bar  lsb  ssb)  file:line  source")
 for f, ln, src, i, s, b, l, sh in agg:

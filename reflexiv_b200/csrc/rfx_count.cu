@@ -51,6 +51,9 @@ struct CountArgs {
     uint32_t* out_counts;
     unsigned long long* dstat;
     unsigned long long out_cap;
+    // tickets t = 0 .. n_tickets-1 map to bins t * bin_stride (the full run: n_tickets = n_bins, stride 1)
+    uint32_t n_tickets, bin_stride;
+    int dry;  // pilot run: count and report statistics, write no rows
 };
 
 constexpr int MAX_SEG = 64;
@@ -203,6 +206,9 @@ __device__ __forceinline__ void expand_warp(const uint64_t* w, uint32_t nk, uint
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
     const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
+#ifdef RFX_DEBUG_COUNT
+    if (lane == 0) { atomicAdd(&sink.T.why[6], (unsigned long long)total); atomicAdd(&sink.T.why[7], (unsigned long long)((total + 31) / 32)); }
+#endif
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
         const uint32_t t = t0 + lane;
         uint32_t s = 0;  // number of records whose inclusive prefix is <= t  ==  source record of k-mer t
@@ -346,8 +352,8 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             unsigned long long t = 0;
             if (lane == 0) t = atomicAdd(&A.dstat[DS_TICKET], 1ull);
             t = __shfl_sync(0xffffffffu, t, 0);
-            const bool end = t >= (unsigned long long)A.n_bins;
-            const uint32_t bin = end ? 0u : (uint32_t)t;
+            const bool end = t >= (unsigned long long)A.n_tickets;
+            const uint32_t bin = end ? 0u : (uint32_t)t * A.bin_stride;
             // per-segment extent of the bin: lanes over segments
             uint32_t tot = 0;
             unsigned long long my_beg[(MAX_SEG + 31) / 32];
@@ -478,6 +484,9 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 compute_barrier<NT>();
                 // ---- B: expand the distinct records, spread evenly over the warps ----
                 const int n_uniq = (int)s_nuniq;
+#ifdef RFX_DEBUG_COUNT
+                if (tid == 0) { atomicAdd(&A.dstat[20], (unsigned long long)n_uniq); atomicAdd(&A.dstat[21], (unsigned long long)cn); }
+#endif
                 int per = (n_uniq + NW - 1) / NW;
                 per = per < 4 ? 4 : per > 32 ? 32 : per;
 #pragma unroll 1
@@ -549,12 +558,12 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             compute_barrier<NT>();
             if (tid == 0) {
                 const uint32_t tot = s_npass;
-                s_out_base = tot ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
+                s_out_base = (tot && !A.dry) ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
                 atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)nd);
-                if (s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
+                if (!A.dry && s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
             }
             compute_barrier<NT>();
-            const bool room = s_out_base + s_npass <= A.out_cap;
+            const bool room = !A.dry && s_out_base + s_npass <= A.out_cap;
             for (uint32_t i0 = (uint32_t)warp * 32u; i0 < nd; i0 += NT) {
                 const uint32_t i = i0 + lane;
                 bool keep = false;
@@ -594,7 +603,7 @@ template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t l
     cudaError_t e = cudaFuncSetAttribute(count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     unsigned grid = 148u * PER_SM;
-    if (grid > A.n_bins) grid = A.n_bins;
+    if (grid > A.n_tickets) grid = A.n_tickets;
     count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM><<<grid, NT + 32, smem, st>>>(A);
     return cudaGetLastError();
 }
@@ -642,16 +651,35 @@ int stage_count(Ctx* c) {
     A.dstat = c->dstat.as<unsigned long long>();
     A.out_cap = cap;
     if (A.n_seg > MAX_SEG) return ctx_fail(c, RFX_E_INVALID, "more than %d record segments", MAX_SEG);
+    A.n_tickets = c->n_bins; A.bin_stride = 1; A.dry = 0;
     if (c->n_records) {
         cudaEventRecord(c->evk[4], st);
         cudaError_t le;
-        const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob
-        const std::string vs = variant ? variant : "";
+        const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob: force a geometry
+        std::string vs = variant ? variant : "";
         if (!c->wide) {
-            if (vs == "a") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
+            if (vs.empty()) {
+                // Pilot: count ~300 evenly spaced bins with the large table, write nothing, and look at how many distinct
+                // k-mers a bin holds.  Clean high-coverage reads (tens per bin) run fastest on the small table at 3 CTAs / SM;
+                // noisy reads (every fourth instance a singleton) need the large one or most bins would be split.
+                CountArgs P = A;
+                P.n_tickets = c->n_bins < 296u ? c->n_bins : 296u;
+                P.bin_stride = c->n_bins / P.n_tickets;
+                P.dry = 1;
+                le = launch_count<false, 4096, 1024, 384, 2>(P, st);
+                if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count pilot launch failed: %s", cudaGetErrorString(le));
+                uint64_t ph[DS_NSLOTS];
+                RFX_CUDA(c, cudaMemcpyAsync(ph, c->dstat.p, sizeof(ph), cudaMemcpyDeviceToHost, st));
+                RFX_CUDA(c, cudaStreamSynchronize(st));
+                RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+                c->launches++;
+                const uint64_t per_bin = ph[DS_DISTINCT] / P.n_tickets;
+                vs = (per_bin <= 600 && ph[DS_SPLITS] == 0) ? "small" : "large";
+            }
+            if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
+            else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
             else if (vs == "b") le = launch_count<false, 2048, 1024, 256, 3>(A, st);
-            else if (vs == "c") le = launch_count<false, 2048, 512, 128, 5>(A, st);
-            else if (vs == "d") le = launch_count<false, 4096, 512, 128, 3>(A, st);
+            else if (vs == "e") le = launch_count<false, 2048, 512, 192, 5>(A, st);
             else le = launch_count<false, 4096, 1024, 256, 2>(A, st);
         } else {
             if (vs == "a") le = launch_count<true, 4096, 512, 384, 1>(A, st);
@@ -675,6 +703,10 @@ int stage_count(Ctx* c) {
     if (h[DS_OVERFLOW] == 1 || h[DS_OUT_CURSOR] > cap)
         return ctx_fail(c, RFX_E_CAPACITY, "filtered table needs %llu rows, capacity %llu: raise table_capacity",
                         (unsigned long long)h[DS_OUT_CURSOR], (unsigned long long)cap);
+#ifdef RFX_DEBUG_COUNT
+    fprintf(stderr, "DEBUG count: records %llu unique %llu expanded k-mers %llu warp steps %llu\n", (unsigned long long)h[21], (unsigned long long)h[20],
+            (unsigned long long)h[22], (unsigned long long)h[23]);
+#endif
     c->n_rows = h[DS_OUT_CURSOR];
     c->n_distinct = h[DS_DISTINCT];
     c->n_bin_splits = h[DS_SPLITS];
