@@ -56,6 +56,7 @@ struct EmitDesc {
 // up): bin lookup, run cutting and descriptor emission then run with most lanes busy instead of ~3 of 32.
 // Semantics are exactly those of bin_scan_read() (rfx_core.h), which the host harness and the spill pass still use.
 constexpr int SCAN_Q = 20;  // queued minimiser changes per read between two drains
+constexpr uint32_t SCAN_TODO = 0xffffffffu;  // rd_runs marker: left to the general kernel by the fast path
 
 struct RunState {
     uint32_t run_bin, run_start;
@@ -73,7 +74,7 @@ template <bool FIXED>
 __global__ void __launch_bounds__(PART_THREADS)
     bin_scan_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
                     BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
-                    uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
+                    uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat, int only_todo) {
     extern __shared__ uint32_t scan_smem[];
     const int k = FIXED ? 31 : P.k, m = FIXED ? 11 : P.m, w = FIXED ? 21 : P.w;
     uint32_t* ring = scan_smem + threadIdx.x;                                   // [2*w][PART_THREADS]
@@ -86,6 +87,10 @@ __global__ void __launch_bounds__(PART_THREADS)
         const uint64_t r = base + threadIdx.x;
         uint32_t len = r < n_reads ? rd_len[r] : 0u;
         if (len < (uint32_t)k) len = 0;
+        // second pass behind bin_scan_fast_kernel: only the reads it left behind
+        const bool mine = r < n_reads && (!only_todo || rd_runs[r] == SCAN_TODO);
+        if (only_todo && !__any_sync(0xffffffffu, mine)) continue;
+        if (!mine) len = 0;
         const uint64_t* rd = packed + (r < n_reads ? rd_woff[r] : 0ull);
         uint32_t maxlen = len;
 #pragma unroll
@@ -157,11 +162,131 @@ __global__ void __launch_bounds__(PART_THREADS)
         }
         drain();
         if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len - (uint32_t)k + 1u - rst.run_start, P.max_nk);
-        if (r < n_reads) {
+        if (mine) {
             const bool spill = em.n > em.stored;
             rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
             if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path of pass 1 for compile-time (K, M): the whole sliding-minimum state lives in registers.
+// The m-mers of a read are taken in blocks of W = K - M + 1 (van Herk / Gil-Werman): 32 bases starting at the block
+// are funnelled into one 64-bit window, so every base, shift and mask inside the fully unrolled block is an
+// immediate; the block's W hashes stay in registers until its suffix minima are formed at the block end, and the
+// minimum of a k-mer's window is min(prefix minimum of this block, suffix minimum of the previous block).  A warp takes
+// this path when its 32 reads have the same length (one position schedule for all lanes, no per-base predicates);
+// any other warp marks its reads SCAN_TODO and the general kernel above picks them up.  Results are bit-identical
+// to bin_scan_read() (rfx_core.h).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FAST_Q = 40;  // queued minimiser changes per read between two drains (a block adds at most W)
+
+template <int M, int W> struct FastScan {
+    uint32_t mfl, mr;        // rolling m-mer: forward left-aligned in the top 2M bits, reverse complement right-aligned
+    uint32_t sfx[W + 1];     // suffix minima of the previous block, sfx[W] = +inf
+    uint32_t prev_h, qn;
+    uint32_t* qh;            // [FAST_Q][PART_THREADS] lane-interleaved
+    uint16_t* qp;
+
+    __device__ __forceinline__ void roll(uint32_t v) {
+        mfl = (mfl << 2) | (v << (32 - 2 * M));
+        mr = (mr >> 2) | ((v ^ 3u) << (2 * (M - 1)));
+    }
+    // MODE 0: first block (its last m-mer completes k-mer 0), 1: full block, 2: last, partial block of `lim` m-mers
+    template <int MODE> __device__ __forceinline__ void block(uint64_t win, uint32_t i0, int lim) {
+        uint32_t hb[W];
+        uint32_t pre = 0xffffffffu;
+#pragma unroll
+        for (int p = 0; p < W; p++) {
+            if (MODE == 2 && p >= lim) break;
+            roll((uint32_t)(win >> (62 - 2 * p)) & 3u);
+            const uint32_t f = mfl >> (32 - 2 * M);
+            const uint32_t h = mmer_hash(f < mr ? f : mr);
+            hb[p] = h;
+            pre = h < pre ? h : pre;
+            if (MODE != 0 || p == W - 1) {
+                uint32_t hmin = pre;
+                if (p != W - 1) hmin = sfx[p + 1] < hmin ? sfx[p + 1] : hmin;
+                if (MODE == 0 || hmin != prev_h) {  // minimiser changed (or first k-mer): remember where, decide later
+                    prev_h = hmin;
+                    qh[qn * PART_THREADS] = hmin;
+                    qp[qn * PART_THREADS] = (uint16_t)(i0 + (uint32_t)p);
+                    qn++;
+                }
+            }
+        }
+        if (MODE != 2) {
+            sfx[W - 1] = hb[W - 1];
+#pragma unroll
+            for (int t = W - 2; t >= 0; t--) sfx[t] = hb[t] < sfx[t + 1] ? hb[t] : sfx[t + 1];
+        }
+    }
+};
+
+template <int K, int M>
+__global__ void __launch_bounds__(PART_THREADS)
+    bin_scan_fast_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
+                         BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
+                         uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
+    constexpr int W = K - M + 1;
+    static_assert(W <= 32 && M <= 16 && M >= 2, "one 64-bit window per block");
+    __shared__ uint32_t s_qh[FAST_Q * PART_THREADS];
+    __shared__ uint16_t s_qp[FAST_Q * PART_THREADS];
+    for (uint64_t base = (uint64_t)blockIdx.x * PART_THREADS; base < n_reads; base += (uint64_t)gridDim.x * PART_THREADS) {
+        const uint64_t r = base + threadIdx.x;
+        const uint32_t len = r < n_reads ? rd_len[r] : 0u;
+        const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
+        if (!__all_sync(0xffffffffu, len == len0) || len0 < (uint32_t)K || len0 > 60000u) {
+            if (r < n_reads) rd_runs[r] = SCAN_TODO;
+            continue;
+        }
+        const uint64_t* rd = packed + rd_woff[r];
+        EmitDesc em{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u};
+        RunState rst{0u, 0u, false};
+        FastScan<M, W> S;
+        S.mfl = 0; S.mr = 0; S.prev_h = 0; S.qn = 0;
+        S.qh = s_qh + threadIdx.x; S.qp = s_qp + threadIdx.x;
+#pragma unroll
+        for (int t = 0; t <= W; t++) S.sfx[t] = 0xffffffffu;
+        auto drain = [&]() {
+            uint32_t maxq = S.qn;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, d));
+            for (uint32_t t = 0; t < maxq; t++) {
+                if (t < S.qn) {
+                    const uint32_t i = S.qp[t * PART_THREADS];
+                    const uint32_t bin = bin_of_minimizer(S.qh[t * PART_THREADS], P.n_bins);
+                    if (!rst.have) { rst.have = true; rst.run_bin = bin; rst.run_start = i; }
+                    else if (bin != rst.run_bin) {
+                        emit_run(em, rst.run_bin, rst.run_start, i - rst.run_start, P.max_nk);
+                        rst.run_bin = bin; rst.run_start = i;
+                    }
+                }
+            }
+            S.qn = 0;
+        };
+        {   // the first M - 1 bases complete no m-mer
+            const uint64_t w0 = rd[0];
+#pragma unroll
+            for (int t = 0; t < M - 1; t++) S.roll((uint32_t)(w0 >> (62 - 2 * t)) & 3u);
+        }
+        const uint32_t n_mmers = len0 - (uint32_t)M + 1u;
+        const uint32_t n_full = n_mmers / (uint32_t)W, rem = n_mmers % (uint32_t)W;
+        S.template block<0>(packed_window(rd, (uint64_t)(M - 1)), 0u - (uint32_t)(W - 1), W);
+        for (uint32_t b = 1; b < n_full; b++) {
+            S.template block<1>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)b * W), b * W - (uint32_t)(W - 1), W);
+            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain();
+        }
+        if (rem) {
+            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain();
+            S.template block<2>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)n_full * W), n_full * W - (uint32_t)(W - 1), (int)rem);
+        }
+        drain();
+        if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len0 - (uint32_t)K + 1u - rst.run_start, P.max_nk);
+        const bool spill = em.n > em.stored;
+        rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);
+        if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
     }
 }
 
@@ -336,14 +461,20 @@ int stage_partition(Ctx* c, int n_shards) {
         RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         cudaEventRecord(c->evk[0], st);
-        if (fixed)
+        if (fixed) {
+            // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
+            bin_scan_fast_kernel<31, 11><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
+                                                                        bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
+                                                                        c->dstat.as<unsigned long long>());
             bin_scan_kernel<true><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
                                                                          bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                                         c->dstat.as<unsigned long long>());
-        else
+                                                                         c->dstat.as<unsigned long long>(), 1);
+            c->launches++;
+        } else {
             bin_scan_kernel<false><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
                                                                           bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                                          c->dstat.as<unsigned long long>());
+                                                                          c->dstat.as<unsigned long long>(), 0);
+        }
         cudaEventRecord(c->evk[1], st);
         c->launches++;
     }
