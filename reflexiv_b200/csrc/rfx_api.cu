@@ -56,7 +56,7 @@ static void free_all(Ctx* c) {
     DevBuf* all[] = {&c->text, &c->line_start, &c->line_at, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
                      &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->ad[0],
                      &c->ad[1], &c->open_next, &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
-                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base};
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin};
     for (DevBuf* b : all) devbuf_free(*b);
 }
 
@@ -199,7 +199,7 @@ const char* rfx_last_error(const rfx_ctx* c) { return c ? c->err.c_str() : g_cre
 int rfx_reset(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
-    c->n_records = 0; c->n_bins = 0; c->have_records = false;
+    c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
     c->have_contigs = false;
     c->rx_bytes = 0; c->shard_id = -1; c->n_seg = 0;
@@ -284,7 +284,13 @@ int rfx_count(rfx_ctx* c) {
     cudaSetDevice(c->prm.device);
     if (c->shard_id >= 0 && c->n_seg > 0) RFX_TRY(stage_adopt_segments(c));
     else if (c->shard_id >= 0) RFX_TRY(stage_rebin(c));
-    else if (!c->have_records) RFX_TRY(stage_partition(c, 1));
+    else if (!c->have_records) {
+        // one GPU, records stay local: single-pass slab partition; inputs with very heavy bins fall back to two passes
+        const char* e = getenv("RFX_PARTITION");
+        const bool two_pass = e && !strcmp(e, "twopass");
+        if (!two_pass) RFX_TRY(stage_partition_slab(c));
+        if (two_pass || !c->have_records) RFX_TRY(stage_partition(c, 1));
+    }
     return stage_count(c);
 }
 

@@ -54,6 +54,11 @@ struct CountArgs {
     // tickets t = 0 .. n_tickets-1 map to bins t * bin_stride (the full run: n_tickets = n_bins, stride 1)
     uint32_t n_tickets, bin_stride;
     int dry;  // pilot run: count and report statistics, write no rows
+    // single-pass partition: segment 0 is the slab layout (bin b = records[b * slab_cap ..], min(slab_cnt[b], slab_cap)
+    // records); the offset-described segments follow as segments 1 ..
+    const uint32_t* slab_cnt;
+    uint32_t slab_cap;
+    const uint64_t* seg_records;  // record array of the offset-described segments (== records unless slab)
 };
 
 constexpr int MAX_SEG = 64;
@@ -363,10 +368,18 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 const int sg = r * 32 + lane;
                 my_beg[r] = 0; my_cnt[r] = 0;
                 if (!end && sg < n_seg) {
-                    const uint64_t* so = A.seg_off + (size_t)sg * (A.n_bins + 1);
-                    const uint64_t o0 = so[0], ob = so[bin], oe = so[bin + 1];
-                    my_beg[r] = A.seg_base[sg] + ob - o0;
-                    my_cnt[r] = (uint32_t)(oe - ob);
+                    if (A.slab_cap && sg == 0) {
+                        const uint32_t cn = A.slab_cnt[bin];
+                        my_beg[r] = (unsigned long long)bin * A.slab_cap;
+                        my_cnt[r] = cn < A.slab_cap ? cn : A.slab_cap;
+                    } else {
+                        const int so_i = A.slab_cap ? sg - 1 : sg;
+                        const uint64_t* so = A.seg_off + (size_t)so_i * (A.n_bins + 1);
+                        const uint64_t o0 = so[0], ob = so[bin], oe = so[bin + 1];
+                        // offset segments of a slab run live in their own array: address them relative to `records`
+                        my_beg[r] = A.seg_base[so_i] + ob - o0 + (unsigned long long)((A.seg_records - A.records) / RECW);
+                        my_cnt[r] = (uint32_t)(oe - ob);
+                    }
                 }
                 uint32_t incl = my_cnt[r];
 #pragma unroll
@@ -644,6 +657,13 @@ int stage_count(Ctx* c) {
     A.seg_off = segmented ? c->seg_off.as<uint64_t>() : c->bin_off.as<uint64_t>();
     A.seg_base = c->seg_base.as<uint64_t>();
     A.n_seg = segmented ? c->n_seg : 1;
+    A.slab_cnt = nullptr; A.slab_cap = 0; A.seg_records = A.records;
+    if (!segmented && c->slab_cap) {  // single-pass partition: slab segment + (maybe) the overflow segment
+        A.slab_cnt = c->bin_cursor.as<uint32_t>();
+        A.slab_cap = c->slab_cap;
+        A.n_seg = c->n_ovf ? 2 : 1;
+        A.seg_records = c->n_ovf ? c->rx_records.as<uint64_t>() : A.records;
+    }
     A.n_bins = c->n_bins;
     A.k = c->k;
     A.min_count = minc; A.max_count = maxc;

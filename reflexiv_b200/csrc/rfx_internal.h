@@ -77,6 +77,11 @@ struct Ctx {
     int32_t n_shards = 1;
     uint64_t n_records = 0;
     bool have_records = false;
+    // single-pass (slab) layout: bin b = records[b * slab_cap ..] (first min(count, slab_cap) records) + an exactly
+    // partitioned overflow segment in rx_records; slab_cap == 0: compact two-pass layout described by bin_off
+    uint32_t slab_cap = 0;
+    uint64_t n_ovf = 0;
+    DevBuf ovf_rec, ovf_bin;
     uint32_t forced_bins = 0;  // total bin count imposed by the caller (sharded runs), 0 = choose
     // records received from other shards (rfx_begin_shard / rfx_load_records_device)
     DevBuf rx_records;
@@ -141,6 +146,7 @@ enum {
     DS_NSPL = 13,
     DS_FQ_STATE = 14,  // lineMark carried between the chunks of one rfx_push_fastq call
     DS_TICKET = 15,    // next bin handed to a counting CTA
+    DS_OVF_RECORDS = 20,  // records that did not fit their slab (single-pass partition)
     DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
     DS_NSLOTS = 24
 };
@@ -151,6 +157,7 @@ static const uint32_t NONE32 = 0xffffffffu;
 int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chunk = true, bool more_follows = false);
 int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);
 int stage_partition(Ctx* c, int n_shards);
+int stage_partition_slab(Ctx* c);
 int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);

@@ -32,6 +32,8 @@ struct EmitDesc {
     uint32_t* spill_cnt;
     uint32_t n;        // runs seen
     uint32_t stored;   // runs that got a descriptor (always a prefix of the read's runs)
+    RFX_HD uint32_t reserve(uint32_t) { return 0u; }
+    RFX_HD void put(uint32_t bin, uint32_t, uint32_t first_kmer, uint32_t n_k) { (*this)(bin, first_kmer, n_k); }
     RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
 #if defined(__CUDA_ARCH__)
         if (n < max_slots && first_kmer < 65536u) {
@@ -63,18 +65,81 @@ struct RunState {
     bool have;
 };
 
-__device__ __forceinline__ void emit_run(EmitDesc& em, uint32_t bin, uint32_t first, uint32_t n_k, uint32_t max_nk) {
+// what pass 1 does with a run is a template parameter of the scan kernels: a *Factory travels as kernel argument and
+// makes the per-read emitter
+struct DescFactory {
+    uint32_t* desc;
+    uint16_t* pos;
+    uint64_t stride;
+    uint32_t max_slots;
+    uint32_t* bin_cnt;
+    uint32_t* spill_cnt;
+    typedef EmitDesc Emit;
+    static constexpr bool kNeedsRuns = true;  // rd_runs[] feeds pass 2
+    __device__ __forceinline__ EmitDesc make(uint64_t r, const uint64_t*) const { return EmitDesc{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u}; }
+};
+
+// Single-pass partition ("slab" layout): bin b owns the fixed range [b * cap, (b + 1) * cap) of the record array, so a
+// run's record can be cut and stored the moment pass 1 sees it -- one atomic on the bin's cursor, no descriptors,
+// no second pass over the reads, no prefix scan.  Records that do not fit their slab go to a small overflow list
+// (with their bin), which is partitioned exactly afterwards and reaches the counting kernel as a second segment.
+template <int RECW> struct EmitSlab {
+    const uint64_t* rd;
+    uint64_t* records;
+    uint32_t* bin_cnt;
+    uint32_t cap;
+    uint64_t* ovf_rec;
+    uint32_t* ovf_bin;
+    unsigned long long* ovf_cursor;  // dstat[DS_OVF_RECORDS]
+    unsigned long long ovf_cap;
+    int k;
+    uint32_t n, stored;
+    // reserve() and put() are separate so that a caller can have several atomics in flight before it needs a rank
+    __device__ __forceinline__ uint32_t reserve(uint32_t bin) { return atomicAdd(&bin_cnt[bin], 1u); }
+    __device__ __forceinline__ void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) { put(bin, reserve(bin), first_kmer, n_k); }
+    __device__ __forceinline__ void put(uint32_t bin, uint32_t rank, uint32_t first_kmer, uint32_t n_k) {
+        uint64_t rec[RECW];
+        rec_build<RECW>(rd, first_kmer, n_k, k, rec);
+        uint64_t* dst;
+        if (rank < cap) {
+            dst = records + ((uint64_t)bin * cap + rank) * RECW;
+        } else {
+            const unsigned long long o = atomicAdd(ovf_cursor, 1ull);
+            if (o >= ovf_cap) return;  // the host sees cursor > capacity and falls back to the two-pass partition
+            ovf_bin[o] = bin;
+            dst = ovf_rec + o * RECW;
+        }
+#pragma unroll
+        for (int i = 0; i < RECW; i += 2) *reinterpret_cast<ulonglong2*>(dst + i) = make_ulonglong2(rec[i], rec[i + 1]);
+    }
+};
+template <int RECW> struct SlabFactory {
+    uint64_t* records;
+    uint32_t* bin_cnt;
+    uint32_t cap;
+    uint64_t* ovf_rec;
+    uint32_t* ovf_bin;
+    unsigned long long* ovf_cursor;
+    unsigned long long ovf_cap;
+    int k;
+    typedef EmitSlab<RECW> Emit;
+    static constexpr bool kNeedsRuns = false;
+    __device__ __forceinline__ EmitSlab<RECW> make(uint64_t, const uint64_t* rd) const {
+        return EmitSlab<RECW>{rd, records, bin_cnt, cap, ovf_rec, ovf_bin, ovf_cursor, ovf_cap, k, 0u, 0u};
+    }
+};
+
+template <class Emit> __device__ __forceinline__ void emit_run(Emit& em, uint32_t bin, uint32_t first, uint32_t n_k, uint32_t max_nk) {
     while (n_k > max_nk) { em(bin, first, max_nk); first += max_nk; n_k -= max_nk; }  // same cuts as the streaming rule
     em(bin, first, n_k);
 }
 
 // FIXED: the default geometry (k = 31, m = 11, w = 21) as compile-time constants, so masks, shifts and the block
 // length fold into immediates; any other (k, m) takes the run-time version of the same code.
-template <bool FIXED>
+template <bool FIXED, class Factory>
 __global__ void __launch_bounds__(PART_THREADS)
     bin_scan_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
-                    BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
-                    uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat, int only_todo) {
+                    BinParams P, Factory F, uint32_t* __restrict__ rd_runs, unsigned long long* dstat, int only_todo) {
     extern __shared__ uint32_t scan_smem[];
     const int k = FIXED ? 31 : P.k, m = FIXED ? 11 : P.m, w = FIXED ? 21 : P.w;
     uint32_t* ring = scan_smem + threadIdx.x;                                   // [2*w][PART_THREADS]
@@ -95,7 +160,7 @@ __global__ void __launch_bounds__(PART_THREADS)
         uint32_t maxlen = len;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, d));
-        EmitDesc em{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u};
+        typename Factory::Emit em = F.make(r, rd);
         RunState rst{0u, 0u, false};
         uint32_t mf = 0, mr = 0, qn = 0, prev_h = 0;
         uint64_t cur = 0;
@@ -162,7 +227,7 @@ __global__ void __launch_bounds__(PART_THREADS)
         }
         drain();
         if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len - (uint32_t)k + 1u - rst.run_start, P.max_nk);
-        if (mine) {
+        if (mine && Factory::kNeedsRuns) {
             const bool spill = em.n > em.stored;
             rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
             if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
@@ -224,11 +289,10 @@ template <int M, int W> struct FastScan {
     }
 };
 
-template <int K, int M>
+template <int K, int M, class Factory>
 __global__ void __launch_bounds__(PART_THREADS)
     bin_scan_fast_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
-                         BinParams P, uint32_t* __restrict__ bin_cnt, uint32_t* __restrict__ spill_cnt, uint32_t* __restrict__ desc, uint16_t* __restrict__ pos,
-                         uint64_t stride, uint32_t max_slots, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
+                         BinParams P, Factory F, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
     constexpr int W = K - M + 1;
     static_assert(W <= 32 && M <= 16 && M >= 2, "one 64-bit window per block");
     __shared__ uint32_t s_qh[FAST_Q * PART_THREADS];
@@ -242,29 +306,48 @@ __global__ void __launch_bounds__(PART_THREADS)
             continue;
         }
         const uint64_t* rd = packed + rd_woff[r];
-        EmitDesc em{desc + r, pos + r, stride, max_slots, bin_cnt, spill_cnt, 0u, 0u};
+        typename Factory::Emit em = F.make(r, rd);
         RunState rst{0u, 0u, false};
         FastScan<M, W> S;
         S.mfl = 0; S.mr = 0; S.prev_h = 0; S.qn = 0;
         S.qh = s_qh + threadIdx.x; S.qp = s_qp + threadIdx.x;
 #pragma unroll
         for (int t = 0; t <= W; t++) S.sfx[t] = 0xffffffffu;
-        auto drain = [&]() {
+        // Phase A turns the queued minimiser changes into closed runs, written back over the queue (a run per change at
+        // most); phase B takes the runs two at a time, so both bin atomics are in flight before either rank is needed.
+        auto drain = [&](bool final, uint32_t n_kmers) {
+            uint32_t nr = 0;
             uint32_t maxq = S.qn;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, d));
+            auto close = [&](uint32_t end) {
+                const uint32_t n_k = end - rst.run_start;
+                if (n_k > P.max_nk) { emit_run(em, rst.run_bin, rst.run_start, n_k, P.max_nk); return; }  // rare: cut and store right away
+                S.qh[nr * PART_THREADS] = (rst.run_bin << 8) | n_k;
+                S.qp[nr * PART_THREADS] = (uint16_t)rst.run_start;
+                nr++;
+            };
             for (uint32_t t = 0; t < maxq; t++) {
                 if (t < S.qn) {
                     const uint32_t i = S.qp[t * PART_THREADS];
                     const uint32_t bin = bin_of_minimizer(S.qh[t * PART_THREADS], P.n_bins);
                     if (!rst.have) { rst.have = true; rst.run_bin = bin; rst.run_start = i; }
-                    else if (bin != rst.run_bin) {
-                        emit_run(em, rst.run_bin, rst.run_start, i - rst.run_start, P.max_nk);
-                        rst.run_bin = bin; rst.run_start = i;
-                    }
+                    else if (bin != rst.run_bin) { close(i); rst.run_bin = bin; rst.run_start = i; }
                 }
             }
+            if (final && rst.have) close(n_kmers);
             S.qn = 0;
+            uint32_t maxr = nr;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, d));
+            for (uint32_t t = 0; t < maxr; t += 2) {
+                const bool a = t < nr, b = t + 1 < nr;
+                uint32_t d1 = 0, d2 = 0, f1 = 0, f2 = 0, r1 = 0, r2 = 0;
+                if (a) { d1 = S.qh[t * PART_THREADS]; f1 = S.qp[t * PART_THREADS]; r1 = em.reserve(d1 >> 8); }
+                if (b) { d2 = S.qh[(t + 1) * PART_THREADS]; f2 = S.qp[(t + 1) * PART_THREADS]; r2 = em.reserve(d2 >> 8); }
+                if (a) em.put(d1 >> 8, r1, f1, d1 & 255u);
+                if (b) em.put(d2 >> 8, r2, f2, d2 & 255u);
+            }
         };
         {   // the first M - 1 bases complete no m-mer
             const uint64_t w0 = rd[0];
@@ -276,17 +359,20 @@ __global__ void __launch_bounds__(PART_THREADS)
         S.template block<0>(packed_window(rd, (uint64_t)(M - 1)), 0u - (uint32_t)(W - 1), W);
         for (uint32_t b = 1; b < n_full; b++) {
             S.template block<1>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)b * W), b * W - (uint32_t)(W - 1), W);
-            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain();
+            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
         }
         if (rem) {
-            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain();
+            if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
             S.template block<2>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)n_full * W), n_full * W - (uint32_t)(W - 1), (int)rem);
         }
-        drain();
-        if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len0 - (uint32_t)K + 1u - rst.run_start, P.max_nk);
-        const bool spill = em.n > em.stored;
-        rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);
-        if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
+        drain(true, len0 - (uint32_t)K + 1u);
+        if (Factory::kNeedsRuns) {
+            const bool spill = em.n > em.stored;
+            rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);
+            if (spill) atomicExch(&dstat[DS_SPILL], 1ull);
+        } else {
+            rd_runs[r] = 0u;  // done (anything but SCAN_TODO)
+        }
     }
 }
 
@@ -423,6 +509,130 @@ static uint32_t choose_bins(Ctx* c, int n_shards) {
     return choose_bin_count(c, c->n_instances, n_shards);
 }
 
+// pass 1 with either emitter: the register-resident scan for the default geometry, then (or instead) the general kernel
+template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, const Factory& F, unsigned grid) {
+    cudaStream_t st = c->stream;
+    const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring
+    const size_t smem_scan = smem + (size_t)2 * SCAN_Q * PART_THREADS * sizeof(uint32_t);  // + the change queues
+    const bool fixed = P.k == 31 && P.m == 11;
+    RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+    RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+    if (fixed) {
+        // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
+        bin_scan_fast_kernel<31, 11, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
+                                                                             c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
+        bin_scan_kernel<true, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
+                                                                              c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
+        c->launches += 2;
+    } else {
+        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
+                                                                               c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 0);
+        c->launches++;
+    }
+    RFX_CUDA(c, cudaGetLastError());
+    return RFX_OK;
+}
+
+// ---- single-pass partition into slabs (one GPU, records stay local) -------------------------------------------
+struct SlabCountIn {
+    const uint32_t* cnt;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return cnt[i]; }
+};
+struct OvfCountIn {
+    const uint32_t* cnt;
+    uint32_t cap;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return cnt[i] > cap ? cnt[i] - cap : 0u; }
+};
+template <int RECW>
+__global__ void ovf_scatter_kernel(const uint64_t* __restrict__ ovf_rec, const uint32_t* __restrict__ ovf_bin, uint64_t n, const uint64_t* __restrict__ off,
+                                   uint32_t* __restrict__ cursor, uint64_t* __restrict__ out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = ovf_bin[i];
+        const uint64_t slot = off[b] + atomicAdd(&cursor[b], 1u);
+#pragma unroll
+        for (int q = 0; q < RECW; q += 2) *reinterpret_cast<ulonglong2*>(out + slot * RECW + q) = *reinterpret_cast<const ulonglong2*>(ovf_rec + i * RECW + q);
+    }
+}
+
+// returns RFX_OK with c->slab_cap == 0 when the overflow list did not suffice (caller falls back to the two-pass path)
+int stage_partition_slab(Ctx* c) {
+    cudaStream_t st = c->stream;
+    stage_begin(c);
+    c->n_shards = 1;
+    c->n_bins = choose_bin_count(c, c->n_instances, 1);
+    BinParams P;
+    P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
+    const size_t nb = c->n_bins;
+    // expected records: one run per (w + 1) / 2 k-mers plus one cut per read; slabs hold twice the average bin
+    const uint64_t est = c->n_instances * 2 / (uint64_t)(P.w + 1) + c->n_reads + 1;
+    uint64_t cap = ((c->wide ? 3 : 2) * est / nb + 8 + 3) & ~(uint64_t)3;  // k > 31: few minimiser loci per bin, uneven bins
+    if (cap > 0x7fffffffull) cap = 0x7fffffffull;
+    uint64_t ovf_cap = est / (c->wide ? 3 : 8) + 4096;
+    RFX_TRY(devbuf_reserve(c, c->bin_cursor, nb * 4 * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->records, (nb * cap * c->recw + 2) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->ovf_rec, (ovf_cap * c->recw + 2) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->ovf_bin, ovf_cap * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->rd_runs, (size_t)(c->n_reads + 1) * sizeof(uint32_t)));
+    RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, nb * 4 * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_OVF_RECORDS, 0, sizeof(uint64_t), st));
+    uint32_t* bin_cnt = c->bin_cursor.as<uint32_t>();
+    uint32_t* ovf_cursor_bin = bin_cnt + nb;
+    unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
+    if (grid < 1) grid = 1;
+    if (grid > 148u * 64u) grid = 148u * 64u;
+    uint64_t n_records = 0, n_ovf = 0;
+    c->ms_kernel[0] = c->ms_kernel[1] = 0;
+    if (c->n_reads) {
+        cudaEventRecord(c->evk[0], st);
+        if (c->recw == 2) {
+            SlabFactory<2> F{c->records.as<uint64_t>(), bin_cnt, (uint32_t)cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
+                             c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, ovf_cap, c->k};
+            RFX_TRY(launch_scan(c, P, F, grid));
+        } else {
+            SlabFactory<4> F{c->records.as<uint64_t>(), bin_cnt, (uint32_t)cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
+                             c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, ovf_cap, c->k};
+            RFX_TRY(launch_scan(c, P, F, grid));
+        }
+        cudaEventRecord(c->evk[1], st);
+        // total records (statistics) and the overflow count
+        ScanPlan<uint64_t> plan;
+        RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(c->n_bins) * sizeof(uint64_t)));
+        plan.bind(c->n_bins, c->scan_ws.as<uint64_t>());
+        scan_prepare(plan, SlabCountIn{bin_cnt}, OpAddU64{}, (uint64_t)0, st);
+        c->launches += plan.levels;
+        RFX_CUDA(c, cudaMemcpyAsync(&n_records, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        RFX_CUDA(c, cudaMemcpyAsync(&n_ovf, c->dstat.as<uint64_t>() + DS_OVF_RECORDS, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        RFX_CUDA(c, cudaStreamSynchronize(st));
+        if (n_ovf > ovf_cap) {  // a few very heavy bins: this input needs the exact layout
+            c->slab_cap = 0;
+            c->ms[1] += stage_end(c);
+            return RFX_OK;
+        }
+        c->n_ovf = n_ovf;
+        if (n_ovf) {
+            // exact partition of the overflow list -> segment 1 of the counting kernel
+            RFX_TRY(devbuf_reserve(c, c->bin_off, (nb + 1) * sizeof(uint64_t)));
+            RFX_TRY(devbuf_reserve(c, c->rx_records, (n_ovf * c->recw + 2) * sizeof(uint64_t)));
+            scan_prepare(plan, OvfCountIn{bin_cnt, (uint32_t)cap}, OpAddU64{}, (uint64_t)0, st);
+            scan_apply(plan, OvfCountIn{bin_cnt, (uint32_t)cap}, BinOffset2Out{c->bin_off.as<uint64_t>()}, OpAddU64{}, (uint64_t)0, st);
+            set_last_offset_kernel<<<1, 1, 0, st>>>(c->bin_off.as<uint64_t>(), c->n_bins, plan.total);
+            unsigned g2 = (unsigned)((n_ovf + 255) / 256);
+            if (g2 > 148u * 16u) g2 = 148u * 16u;
+            if (c->recw == 2) ovf_scatter_kernel<2><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
+            else ovf_scatter_kernel<4><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
+            c->launches += 2 * plan.levels + 2;
+        }
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "slab partition failed: %s", cudaGetErrorString(e));
+        cudaEventElapsedTime(&c->ms_kernel[0], c->evk[0], c->evk[1]);
+    }
+    c->slab_cap = (uint32_t)cap;
+    c->n_records = n_records;
+    c->have_records = true;
+    c->ms[1] += stage_end(c);
+    return RFX_OK;
+}
+
 int stage_partition(Ctx* c, int n_shards) {
     cudaStream_t st = c->stream;
     if (n_shards < 1) return ctx_fail(c, RFX_E_INVALID, "n_shards must be >= 1");
@@ -452,31 +662,14 @@ int stage_partition(Ctx* c, int n_shards) {
     uint32_t* desc = c->run_desc.as<uint32_t>();
     uint16_t* pos = reinterpret_cast<uint16_t*>(desc + slots * stride + 32);
     const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring (spill pass)
-    const size_t smem_scan = smem + (size_t)2 * SCAN_Q * PART_THREADS * sizeof(uint32_t);  // + the change queues
     unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
     if (grid < 1) grid = 1;
     if (grid > 148u * 64u) grid = 148u * 64u;
+    c->slab_cap = 0;
     if (c->n_reads) {
-        const bool fixed = P.k == 31 && P.m == 11;
-        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
-        RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
         cudaEventRecord(c->evk[0], st);
-        if (fixed) {
-            // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
-            bin_scan_fast_kernel<31, 11><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
-                                                                        bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                                        c->dstat.as<unsigned long long>());
-            bin_scan_kernel<true><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
-                                                                         bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                                         c->dstat.as<unsigned long long>(), 1);
-            c->launches++;
-        } else {
-            bin_scan_kernel<false><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, P,
-                                                                          bin_cnt, spill_cnt, desc, pos, stride, (uint32_t)slots, c->rd_runs.as<uint32_t>(),
-                                                                          c->dstat.as<unsigned long long>(), 0);
-        }
+        RFX_TRY(launch_scan(c, P, DescFactory{desc, pos, stride, (uint32_t)slots, bin_cnt, spill_cnt}, grid));
         cudaEventRecord(c->evk[1], st);
-        c->launches++;
     }
     // exclusive scan of the per-bin record counts -> bin offsets
     ScanPlan<uint64_t> plan;
