@@ -272,9 +272,10 @@ def main():
 
     # Roofline of the counting stage.  Algorithmic bytes (stated in DESIGN.md):
     #   B_count = sum(read_len) + 16 * N * W + (8 * W + 4) * D'     (W = 1 word per key for k = 31; 17.25 B per k-mer)
-    # That figure is for the whole counting stage, which here is three launches (minimiser scan, record emission,
-    # per-bin count), so `achieved` divides it by the SUM of their CUDA-event durations; the dominant kernel is named
-    # and every kernel's duration is listed.
+    # That figure is for the whole counting stage: the minimiser scan that cuts and stores the super-k-mer records
+    # (one launch on one GPU; scan + record scatter when records are exchanged between GPUs) and the per-bin count
+    # (a ~300-bin pilot launch plus the main launch), so `achieved` divides it by the SUM of their CUDA-event
+    # durations; the dominant kernel is named and every kernel's duration is listed.
     peak, peak_src = hbm_peak()
     inst_local = st["n_instances"] if world == 1 else n_inst_rank
     rows_local = st["n_rows"] if world == 1 else st["n_rows"] // world
@@ -283,11 +284,11 @@ def main():
     dom = max(kern_ms, key=kern_ms.get)
     count_path_ms = sum(kern_ms.values())
     ach = b_count / (count_path_ms * 1e-3) / 1e9 if count_path_ms else None
-    roofline = {"bound": "hbm", "kernel": "counting stage: bin_scan_kernel + emit_records_kernel + count_bins_narrow_kernel", "dominant_kernel": dom,
+    roofline = {"bound": "hbm", "kernel": "counting stage: bin_scan_fast_kernel (minimiser scan + record store" + (")" if world == 1 else "; emit_records_kernel scatter)") + " + count_bins_kernel (pilot + main)", "dominant_kernel": dom,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_count, "algorithmic_bytes_per_kmer": b_count / inst_local if inst_local else None,
                 "kernel_ms": kern_ms, "stage_kmers_per_s": inst_local / (count_path_ms * 1e-3) if count_path_ms else None,
-                "bound_observed": "instruction issue (ncu: issue-active 70-86 %, DRAM 1-11 %), see profiles/"}
+                "bound_observed": "instruction issue / shared-memory latency (ncu: issue-active 49-59 %, DRAM 7-9 %), see profiles/"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
