@@ -214,19 +214,20 @@ __device__ __forceinline__ void expand_warp(const uint64_t* w, uint32_t nk, uint
 #ifdef RFX_DEBUG_COUNT
     if (lane == 0) { atomicAdd(&sink.T.why[6], (unsigned long long)total); atomicAdd(&sink.T.why[7], (unsigned long long)((total + 31) / 32)); }
 #endif
+    // Source record of k-mer t: the non-empty records are lanes 0 .. r-1 (idle lanes only trail), so it is
+    // (number of records that start at or before t) - 1.  Per step every record that starts inside the step's window
+    // of 32 k-mers sets one bit; one warp-wide OR and a popcount replace a binary search over the prefix sums.
+    const uint32_t pe = pi - nk;  // exclusive prefix: first k-mer of this lane's record
+    uint32_t base = 0;            // records that start before the window
     for (uint32_t t0 = 0; t0 < total; t0 += 32) {
         const uint32_t t = t0 + lane;
-        uint32_t s = 0;  // number of records whose inclusive prefix is <= t  ==  source record of k-mer t
-#pragma unroll
-        for (int step = 16; step; step >>= 1) {
-            const uint32_t pv = __shfl_sync(0xffffffffu, pi, (s + step - 1) & 31);
-            if (pv <= t) s += step;
-        }
-        s &= 31;
-        const uint32_t pis = __shfl_sync(0xffffffffu, pi, s);
-        const uint32_t nks = __shfl_sync(0xffffffffu, nk, s);
+        const uint32_t rel = pe - t0;
+        const uint32_t heads = __reduce_or_sync(0xffffffffu, (nk != 0u && rel < 32u) ? (1u << rel) : 0u);
+        const uint32_t s = (base + (uint32_t)__popc(heads & (0xffffffffu >> (31 - lane))) - 1u) & 31u;
+        base += (uint32_t)__popc(heads);
+        const uint32_t pes = __shfl_sync(0xffffffffu, pe, s);
         const uint32_t ms = __shfl_sync(0xffffffffu, mult, s);
-        const uint32_t off = t - (pis - nks);  // k-mer index inside the record
+        const uint32_t off = t - pes;  // k-mer index inside the record
         const uint32_t b = 16u + 2u * off;     // first bit of the k-mer in the record's bit stream
         if (!WIDE) {
             const uint64_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);

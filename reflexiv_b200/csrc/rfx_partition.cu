@@ -313,41 +313,24 @@ __global__ void __launch_bounds__(PART_THREADS)
         S.qh = s_qh + threadIdx.x; S.qp = s_qp + threadIdx.x;
 #pragma unroll
         for (int t = 0; t <= W; t++) S.sfx[t] = 0xffffffffu;
-        // Phase A turns the queued minimiser changes into closed runs, written back over the queue (a run per change at
-        // most); phase B takes the runs two at a time, so both bin atomics are in flight before either rank is needed.
+        // the whole warp drains its queues together: bin lookup, run cutting and record emission run with most lanes busy
         auto drain = [&](bool final, uint32_t n_kmers) {
-            uint32_t nr = 0;
             uint32_t maxq = S.qn;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, d));
-            auto close = [&](uint32_t end) {
-                const uint32_t n_k = end - rst.run_start;
-                if (n_k > P.max_nk) { emit_run(em, rst.run_bin, rst.run_start, n_k, P.max_nk); return; }  // rare: cut and store right away
-                S.qh[nr * PART_THREADS] = (rst.run_bin << 8) | n_k;
-                S.qp[nr * PART_THREADS] = (uint16_t)rst.run_start;
-                nr++;
-            };
             for (uint32_t t = 0; t < maxq; t++) {
                 if (t < S.qn) {
                     const uint32_t i = S.qp[t * PART_THREADS];
                     const uint32_t bin = bin_of_minimizer(S.qh[t * PART_THREADS], P.n_bins);
                     if (!rst.have) { rst.have = true; rst.run_bin = bin; rst.run_start = i; }
-                    else if (bin != rst.run_bin) { close(i); rst.run_bin = bin; rst.run_start = i; }
+                    else if (bin != rst.run_bin) {
+                        emit_run(em, rst.run_bin, rst.run_start, i - rst.run_start, P.max_nk);
+                        rst.run_bin = bin; rst.run_start = i;
+                    }
                 }
             }
-            if (final && rst.have) close(n_kmers);
             S.qn = 0;
-            uint32_t maxr = nr;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, d));
-            for (uint32_t t = 0; t < maxr; t += 2) {
-                const bool a = t < nr, b = t + 1 < nr;
-                uint32_t d1 = 0, d2 = 0, f1 = 0, f2 = 0, r1 = 0, r2 = 0;
-                if (a) { d1 = S.qh[t * PART_THREADS]; f1 = S.qp[t * PART_THREADS]; r1 = em.reserve(d1 >> 8); }
-                if (b) { d2 = S.qh[(t + 1) * PART_THREADS]; f2 = S.qp[(t + 1) * PART_THREADS]; r2 = em.reserve(d2 >> 8); }
-                if (a) em.put(d1 >> 8, r1, f1, d1 & 255u);
-                if (b) em.put(d2 >> 8, r2, f2, d2 & 255u);
-            }
+            if (final && rst.have) emit_run(em, rst.run_bin, rst.run_start, n_kmers - rst.run_start, P.max_nk);
         };
         {   // the first M - 1 bases complete no m-mer
             const uint64_t w0 = rd[0];
