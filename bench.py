@@ -109,7 +109,7 @@ def cpu_reference_run(sample_reads: int = 1_000_000, threads: int = 0):
             "count_stage_kmers_per_s": n_inst / (t1 - t0), "reads_per_s": 2 * pairs / (t2 - t0), "seconds": t2 - t0}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -126,7 +126,7 @@ def run_reference(args):
             "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -142,8 +142,17 @@ def main():
     ap.add_argument("--error-rate", type=float, default=0.0, help="informational: per-base substitution rate of the synthetic reads")
     ap.add_argument("--genome", type=int, default=GENOME_LEN, help="informational: genome length per GPU")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything else any library prints (NCCL's version banner, warnings)
+    # goes to stderr, and the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
         return
 
     import numpy as np
@@ -316,7 +325,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_run().items() if k in ("value", "unit", "cores", "kind", "sample", "count_stage_kmers_per_s", "reads_per_s")}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
