@@ -208,9 +208,9 @@ def main():
             ctx.count()
         else:
             sharded.sharded_count(ctx, torch, dist, device, n_bins_total)
-            sharded.gather_tables(ctx, torch, dist, device)
+            gst = sharded.gather_tables(ctx, torch, dist, device)
         t2 = time.perf_counter()
-        st = ctx.assemble()
+        st = ctx.assemble() if world == 1 else sharded.sharded_assemble(ctx, torch, dist, device, gst["row_ranges"])
         t3 = time.perf_counter()
         if from_host:
             bases, offs, left, right = ctx.contigs_raw((out_bases, out_offs, out_left, out_right))
@@ -311,7 +311,7 @@ def main():
                                    f"k={kk}, cover 2, full run path (FASTQ text -> counts -> fork filters -> contigs)"
                                    + ("" if (kk, args.error_rate, args.genome) == (K, 0.0, GENOME_LEN) else f" [informational variant: error rate {args.error_rate}]"),
                        "l2_policy": f"inputs larger than L2: {n_bytes / 1e6:.0f} MB of FASTQ text per GPU per step, nothing reused across steps",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: minimiser-bin shards, NCCL all-to-all of super-k-mer records, replicated graph stage",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: minimiser-bin shards, NCCL all-to-all of super-k-mer records, graph stages sharded by row owner (alive bytes, splitter list and chain tuples exchanged)",
                        "timing": "host clock around blocking C-ABI calls bracketed by barrier + cuda synchronize, max over ranks; per-stage and per-kernel times from CUDA events on the library's stream"},
             "reads_per_s": n_reads * world / (t_dev / args.steps),
             "stage_ms": stage_ms, "result": {k: st[k] for k in ("n_reads", "n_instances", "n_distinct", "n_rows", "n_records", "n_bins", "n_bin_splits",

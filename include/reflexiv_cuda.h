@@ -182,6 +182,34 @@ int rfx_counts_device(rfx_ctx* ctx, const void** d_keys, const uint32_t** d_coun
 /* Replace (append == 0) or extend (append != 0) the table from device memory in that same layout. */
 int rfx_load_counts_device(rfx_ctx* ctx, const void* d_keys, const uint32_t* d_counts, uint64_t n_rows, int32_t append);
 
+/* ---- sharded assembly (one context per GPU; the caller issues the collectives between the steps) ----------------
+ * replaces, across GPUs, the same reference stages as rfx_assemble (ReflexivDSMain.java:221-338); the exchanges take
+ * the place of the reference's global sort("k-1") shuffles.  Every rank holds the WHOLE filtered table (shard tables
+ * concatenated in rank order, rfx_load_counts_device) and owns rows [row_lo, row_hi) of it.  Sequence:
+ *   rfx_gs_begin      index + right fork filter of the own rows
+ *   [every rank broadcasts its slice [2*row_lo, 2*row_hi) of the alive bytes (rfx_gs_alive)]
+ *   rfx_gs_left       left fork filter of the own rows
+ *   [broadcast the slices again]
+ *   rfx_gs_link       links, splitter selection and segment walk of the own nodes; returns the own splitter triples
+ *                     (node, next splitter node or 0xffffffff, segment length), n_splitters entries each
+ *   [all-gather the three arrays in rank order; my_offset = number of splitters of the lower ranks]
+ *   rfx_gs_rank       ranks the gathered list, finishes the own nodes, returns the own chain tuples: tails are
+ *                     {u32 head, u32 length, i32 right flag}, heads {u32 head, i32 left flag}.  has_cycle != 0: the
+ *                     graph has a closed path; fall back to rfx_assemble (the table is already whole on every rank)
+ *   [all-gather tails and heads]
+ *   rfx_gs_contigs    contig table (identical on every rank) + the bases of the own nodes; *d_bases is zero elsewhere
+ *   [all-reduce MAX over the n_bases bytes; sum the four statistics over the ranks (rfx_stats of each rank holds its
+ *    own n_oriented / n_budget_junctions / n_budget_admissible / n_cycles)]
+ *   rfx_gs_finish     stores the global statistics; rfx_contigs_size / rfx_contigs_copy work as after rfx_assemble */
+int rfx_gs_begin(rfx_ctx* ctx, uint64_t row_lo, uint64_t row_hi);
+int rfx_gs_alive(rfx_ctx* ctx, uint8_t** d_alive, uint64_t* n_nodes);
+int rfx_gs_left(rfx_ctx* ctx);
+int rfx_gs_link(rfx_ctx* ctx, uint64_t* n_splitters, const uint32_t** d_node, const uint32_t** d_next, const uint32_t** d_len);
+int rfx_gs_rank(rfx_ctx* ctx, const uint32_t* d_node, const uint32_t* d_next, const uint32_t* d_len, uint64_t n_total, uint64_t my_offset,
+                uint64_t* n_tails, const void** d_tails, uint64_t* n_heads, const void** d_heads, int32_t* has_cycle);
+int rfx_gs_contigs(rfx_ctx* ctx, const void* d_tails, uint64_t n_tails, const void* d_heads, uint64_t n_heads, char** d_bases, uint64_t* n_bases);
+int rfx_gs_finish(rfx_ctx* ctx, uint64_t n_oriented, uint64_t n_budget_junctions, uint64_t n_budget_admissible, uint64_t n_cycles);
+
 /* ---- synthetic data (host, deterministic) ----------------------------------------- */
 int64_t rfx_synth_genome(uint8_t* out, int64_t n_bases, uint64_t seed);
 /* FASTQ text of pairs [first_pair, first_pair+n_pairs): mate 1 records then mate 2 records.

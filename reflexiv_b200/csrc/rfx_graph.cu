@@ -61,11 +61,15 @@ template <class KT> __global__ void ht_build_kernel(Graph<KT> G) {
     }
 }
 
-// A7.  alive bit0 = survives the right fork filter.
+// The alive byte of an oriented k-mer: bit0 survives the right fork filter, bit1 survives both, bit2 right flag < 0,
+// bit3 left flag < 0.  The sign bits are all a neighbour needs to know about a node's flags (junction_joins), so in
+// a sharded run one byte per node is the only per-node state that crosses GPUs.
+// All per-node kernels take an oid range [lo, hi): the whole table on one GPU, the rank's own rows in a sharded run.
+//
+// A7.
 template <class KT>
-__global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ alive, int32_t* __restrict__ rflag) {
-    const uint64_t n = 2 * G.n_rows;
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+__global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ alive, int32_t* __restrict__ rflag, uint64_t lo, uint64_t hi) {
+    for (uint64_t oid = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < hi; oid += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t row = (uint32_t)(oid >> 1);
         const KT key = G.keys[row];
         const KT rc = revcomp(key, G.k);
@@ -87,18 +91,17 @@ __global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ al
             }
         }
         const ForkResult res = right_fork(cnt, dup, E, G.k - 1);
-        alive[oid] = (res.winner == (int)myb) ? 1 : 0;
+        alive[oid] = (uint8_t)(((res.winner == (int)myb) ? 1 : 0) | (res.flag < 0 ? 4 : 0));
         rflag[oid] = res.flag;
     }
 }
 
-// A8.  alive bit1 = survives both filters.
+// A8.
 template <class KT>
-__global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* __restrict__ lflag) {
-    const uint64_t n = 2 * G.n_rows;
+__global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* __restrict__ lflag, uint64_t lo, uint64_t hi) {
     const int top = 2 * (G.k - 1);
     const KT sufmask = mask_bases<KT>(G.k - 1);
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t oid = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < hi; oid += (uint64_t)gridDim.x * blockDim.x) {
         lflag[oid] = 0;
         if (!(alive[oid] & 1)) continue;
         const KT X = G.oriented((uint32_t)oid);
@@ -115,17 +118,19 @@ __global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* 
             }
         }
         const ForkResult res = left_fork(cnt, E, G.k - 1);
-        if (res.winner == (int)mya) { alive[oid] = 3; lflag[oid] = res.flag; }
+        if (res.winner == (int)mya) { alive[oid] = (uint8_t)((alive[oid] & 4) | 3 | (res.flag < 0 ? 8 : 0)); lflag[oid] = res.flag; }
     }
 }
 
-// Neighbour links.  succ/pred are preset to NONE32.
-template <class KT>
+// Neighbour links.  succ/pred are preset to NONE32.  On one GPU a node writes its successor's pred[]; in a sharded
+// run (SHARDED) a node may only write its own entries, so it finds its predecessor itself (4 more probes) and reads
+// the neighbour's flag signs from the alive byte.
+template <class KT, bool SHARDED>
 __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag,
-                            uint32_t* __restrict__ succ, uint32_t* pred, uint32_t* __restrict__ open_next, unsigned long long* dstat) {
-    const uint64_t n = 2 * G.n_rows;
+                            uint32_t* __restrict__ succ, uint32_t* pred, uint32_t* __restrict__ open_next, unsigned long long* dstat, uint64_t lo, uint64_t hi) {
     const KT sufmask = mask_bases<KT>(G.k - 1);
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+    const int top = 2 * (G.k - 1);
+    for (uint64_t oid = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < hi; oid += (uint64_t)gridDim.x * blockDim.x) {
         if (!(alive[oid] & 2)) continue;
         const KT X = G.oriented((uint32_t)oid);
         const KT suffix = X & sufmask;
@@ -138,14 +143,31 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
             if (oy != NONE32 && (alive[oy] & 2)) { next = oy; n_cand++; }
         }
         if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
-        if (next == NONE32) continue;
-        if (junction_joins(rflag[oid], lflag[next])) {
-            if (next == (uint32_t)oid) { atomicAdd(&dstat[DS_CYCLES], 1ull); continue; }  // 1-cycle: a record never merges with itself
-            succ[oid] = next;
-            if (atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
-        } else {
-            open_next[oid] = next;
-            atomicAdd(&dstat[DS_BUDGET], 1ull);
+        if (next != NONE32) {
+            const bool joins = SHARDED ? (((alive[oid] >> 2) & 1) == ((alive[next] >> 3) & 1)) : junction_joins(rflag[oid], lflag[next]);
+            if (joins) {
+                if (next == (uint32_t)oid) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
+                else {
+                    succ[oid] = next;
+                    if (!SHARDED && atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+                }
+            } else {
+                open_next[oid] = next;
+                atomicAdd(&dstat[DS_BUDGET], 1ull);
+            }
+        }
+        if (SHARDED) {
+            const KT prefix = X >> 2;
+            uint32_t prev = NONE32;
+            int n_prev = 0;
+#pragma unroll
+            for (uint32_t a = 0; a < 4; a++) {
+                uint32_t cz;
+                const uint32_t oz = G.find(((KT)a << top) | prefix, &cz);
+                if (oz != NONE32 && (alive[oz] & 2)) { prev = oz; n_prev++; }
+            }
+            if (n_prev > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 2ull); continue; }
+            if (prev != NONE32 && prev != (uint32_t)oid && (((alive[prev] >> 2) & 1) == ((alive[oid] >> 3) & 1))) pred[oid] = prev;
         }
     }
 }
@@ -396,9 +418,9 @@ template <class KT> static int graph_impl(Ctx* c) {
         uint32_t* succ = c->succ.as<uint32_t>();
         uint32_t* pred = c->pred.as<uint32_t>();
         ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G);
-        right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, rflag);
-        left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, lflag);
-        link_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, open_next.as<uint32_t>(), dstat);
+        right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, rflag, 0, n);
+        left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, lflag, 0, n);
+        link_kernel<KT, false><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, open_next.as<uint32_t>(), dstat, 0, n);
         c->launches += 4;
         cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
@@ -521,6 +543,400 @@ template <class KT> static int graph_impl(Ctx* c) {
         c->have_contigs = true;
     } while (0);
     return rc;
+}
+
+// =================================================================================================================
+// Sharded graph stages: one process per GPU, rows sharded by minimiser bin exactly as the counting left
+// them.  Every rank holds the whole (k-mer, count) table and its index (cheap: 12 B per row, built once), but does the
+// per-node work -- fork filters, links, chain walking, base gather -- for its OWN rows only.  What crosses GPUs:
+//   * one byte per node after each fork filter (alive + flag signs), broadcast by its owner;
+//   * the splitter list: chain heads, a 1-in-16 sample and every node whose predecessor lives on another GPU.  An owner
+//     walks each of its splitters to the next one; (node, next splitter node, segment length) triples are all-gathered
+//     and every rank ranks that reduced list (a few % of the nodes) -- the "cross-shard chain joins" of the extension;
+//   * one (head, length, right flag) tuple per chain and one (head, left flag) per head, from which every rank builds
+//     the same contig table; each rank then writes the bases of its own nodes and a byte-wise max merges the buffers.
+// The collectives themselves are issued by the caller (reflexiv_b200/sharded.py, NCCL) between these steps.
+// Cycles (no head anywhere) are not handled here: rfx_gs_rank reports them and the caller uses the replicated path.
+// =================================================================================================================
+struct GsTail { uint32_t head, len; int32_t rflag; };
+struct GsHead { uint32_t head; int32_t lflag; };
+
+__device__ __forceinline__ bool gs_own(uint32_t x, uint64_t lo, uint64_t hi) { return x >= lo && x < hi; }
+
+__global__ void gs_splitter_select_kernel(uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred,
+                                          uint32_t* __restrict__ spl_id, uint32_t* __restrict__ spl_node, unsigned long long* dstat) {
+    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t id = NONE32;
+        if (alive[x] & 2) {
+            const uint32_t p = pred[x];
+            if (p == NONE32 || is_random_splitter((uint32_t)x) || !gs_own(p, lo, hi)) {
+                id = (uint32_t)atomicAdd(&dstat[DS_NSPL], 1ull);
+                spl_node[id] = (uint32_t)x;
+            }
+        }
+        spl_id[x] = id;
+    }
+}
+// every own splitter walks its successors up to the next splitter: a sampled node, or a node on another GPU
+__global__ void gs_splitter_walk_kernel(uint64_t m, uint64_t lo, uint64_t hi, const uint32_t* __restrict__ spl_node, const uint32_t* __restrict__ succ,
+                                        uint64_t* __restrict__ loc, uint32_t* __restrict__ nxt, uint32_t* __restrict__ seg_len) {
+    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m; id += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t x = spl_node[id];
+        uint32_t off = 0;
+        loc[x] = ad_pack((uint32_t)id, 0u);
+        uint32_t y = succ[x];
+        while (y != NONE32 && gs_own(y, lo, hi) && !is_random_splitter(y)) {
+            off++;
+            loc[y] = ad_pack((uint32_t)id, off);
+            y = succ[y];
+        }
+        nxt[id] = y;
+        seg_len[id] = off + 1u;
+    }
+}
+// reduced list over ALL splitters (gathered): index by node, then predecessor-splitter links
+__global__ void gs_index_kernel(uint64_t M, const uint32_t* __restrict__ g_node, uint32_t* __restrict__ gidx, uint64_t* __restrict__ sp_ad) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        gidx[g_node[i]] = (uint32_t)i;
+        sp_ad[i] = ad_pack((uint32_t)i, 0u);
+    }
+}
+__global__ void gs_reduced_link_kernel(uint64_t M, const uint32_t* __restrict__ g_next, const uint32_t* __restrict__ g_len, const uint32_t* __restrict__ gidx,
+                                       uint64_t* __restrict__ sp_ad, unsigned long long* dstat) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = g_next[i];
+        if (y == NONE32) continue;
+        const uint32_t j = gidx[y];
+        if (j == NONE32) { atomicExch(&dstat[DS_GRAPH_ERR], 5ull); continue; }  // successor splitter missing from the gathered list
+        sp_ad[j] = ad_pack((uint32_t)i, g_len[i]);
+    }
+}
+// after the jumps every splitter must hang off a true head (an entry that still is its own ancestor at distance 0)
+__global__ void gs_cycle_check_kernel(uint64_t M, const uint64_t* __restrict__ sp_ad, unsigned long long* dstat) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = (uint32_t)sp_ad[i];
+        if (sp_ad[a] != ad_pack(a, 0u)) atomicExch(&dstat[DS_CYCLE_NODES], 1ull);
+    }
+}
+__global__ void gs_finalize_kernel(uint64_t lo, uint64_t hi, uint64_t my_off, const uint8_t* __restrict__ alive, const uint64_t* __restrict__ loc,
+                                   const uint64_t* __restrict__ sp_ad, const uint32_t* __restrict__ g_node, uint64_t* __restrict__ ad,
+                                   unsigned long long* dstat) {
+    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2)) { ad[x] = ad_pack((uint32_t)x, 0u); continue; }
+        const uint64_t l = loc[x];
+        if (l == ~0ull) { ad[x] = ad_pack((uint32_t)x, 0u); atomicExch(&dstat[DS_CYCLE_NODES], 1ull); continue; }  // cycle without a splitter
+        const uint64_t v = sp_ad[my_off + (uint32_t)l];
+        ad[x] = ad_pack(g_node[(uint32_t)v], (uint32_t)(v >> 32) + (uint32_t)(l >> 32));
+    }
+}
+__global__ void gs_chains_kernel(uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
+                                 const uint64_t* __restrict__ ad, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag, GsTail* __restrict__ tails,
+                                 GsHead* __restrict__ heads, unsigned long long* dstat) {
+    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2)) continue;
+        atomicAdd(&dstat[DS_ORIENTED], 1ull);
+        if (succ[x] == NONE32) {
+            const uint64_t v = ad[x];
+            tails[atomicAdd(&dstat[DS_NSPL], 1ull)] = GsTail{(uint32_t)v, (uint32_t)(v >> 32) + 1u, rflag[x]};
+        }
+        if (pred[x] == NONE32) heads[atomicAdd(&dstat[DS_CHANGED], 1ull)] = GsHead{(uint32_t)x, lflag[x]};
+    }
+}
+__global__ void gs_scatter_heads_kernel(uint64_t n, const GsHead* __restrict__ heads, int32_t* __restrict__ lflag) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) lflag[heads[i].head] = heads[i].lflag;
+}
+struct GsContigIn {
+    const GsTail* tails;
+    const int32_t* lflag;
+    int k, min_contig;
+    __device__ __forceinline__ U64x3 operator()(uint64_t i) const {
+        const GsTail t = tails[i];
+        const uint64_t len = (uint64_t)t.len + (uint64_t)k - 1;
+        const bool keep = !(lflag[t.head] <= -10000000 && t.rflag <= -10000000) && len >= (uint64_t)min_contig;  // DSKmerToContig, ReflexivDSMain.java:749-754
+        return keep ? U64x3{1, len, 1} : U64x3{0, 0, 1};
+    }
+};
+struct GsContigOut {
+    const GsTail* tails;
+    const int32_t* lflag;
+    uint32_t* ctg_idx;
+    uint32_t* chain_len;
+    uint64_t* ctg_off;
+    int32_t* ctg_left;
+    int32_t* ctg_right;
+    __device__ __forceinline__ void operator()(uint64_t i, U64x3 excl, U64x3 v) const {
+        const GsTail t = tails[i];
+        chain_len[t.head] = t.len;
+        if (v.a) {
+            ctg_idx[t.head] = (uint32_t)excl.a;
+            ctg_off[excl.a] = excl.b;
+            ctg_left[excl.a] = lflag[t.head];
+            ctg_right[excl.a] = t.rflag;
+        }
+    }
+};
+template <class KT>
+__global__ void gs_gather_kernel(Graph<KT> G, uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint64_t* __restrict__ ad,
+                                 const uint32_t* __restrict__ ctg_idx, const uint64_t* __restrict__ ctg_off, char* __restrict__ out) {
+    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2)) continue;
+        const uint64_t v = ad[x];
+        const uint32_t h = (uint32_t)v;
+        const uint32_t ci = ctg_idx[h];
+        if (ci == NONE32) continue;
+        const KT X = G.oriented((uint32_t)x);
+        char* dst = out + ctg_off[ci];
+        dst[(uint64_t)(G.k - 1) + (uint32_t)(v >> 32)] = "ACGT"[(uint32_t)X & 3u];
+        if (h == (uint32_t)x)
+            for (int j = 0; j < G.k - 1; j++) dst[j] = "ACGT"[(uint32_t)(X >> (2 * (G.k - 1 - j))) & 3u];
+    }
+}
+__global__ void gs_budget_kernel(uint64_t lo, uint64_t hi, const uint32_t* __restrict__ open_next, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag,
+                                 const int32_t* __restrict__ rflag, const uint64_t* __restrict__ ad, const uint32_t* __restrict__ chain_len, unsigned long long* dstat) {
+    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = open_next[x];
+        if (y == NONE32) continue;
+        // y is a head (the junction in front of it stayed open), so its left flag arrived with the head tuples
+        const int64_t r_ext = (int64_t)(ad[x] >> 32) + 1, f_ext = (int64_t)chain_len[y];
+        if ((lflag[y] >= 0 && lflag[y] - r_ext >= 0) || (rflag[x] >= 0 && rflag[x] - f_ext >= 0)) atomicAdd(&dstat[DS_BUDGET_ADM], 1ull);
+    }
+}
+
+template <class KT> static Graph<KT> gs_graph(Ctx* c) {
+    return Graph<KT>{c->keys.as<KT>(), c->counts.as<uint32_t>(), c->n_rows, c->ht.as<uint32_t>(), c->ht_cap - 1, c->k};
+}
+static int gs_sync(Ctx* c, const char* what) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    return RFX_OK;
+}
+
+// step 1: index over the whole table, right fork filter for the own rows
+template <class KT> static int gs_begin_impl(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const uint64_t n_rows = c->n_rows, n = 2 * n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi;
+    if (n >= 0xffffffffull) return ctx_fail(c, RFX_E_CAPACITY, "more than 2^31 rows: oriented ids do not fit 32 bits");
+    stage_begin(c);
+    uint64_t ht_cap = 1024;
+    while (ht_cap < 2 * n_rows) ht_cap <<= 1;
+    c->ht_cap = ht_cap;
+    RFX_TRY(devbuf_reserve(c, c->ht, ht_cap * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->rflag, (n + 1) * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->lflag, (n + 1) * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->alive, n + 16));
+    RFX_TRY(devbuf_reserve(c, c->succ, (n + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->pred, (n + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->open_next, (n + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->spl_id, (n + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->loc, (n + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->ad[0], (n + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->chain_len, (n + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->ctg_idx, (n + 1) * sizeof(uint32_t)));
+    const uint64_t own = hi - lo;
+    RFX_TRY(devbuf_reserve(c, c->spl_node, (own + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->gs_next, (own + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->gs_len, (own + 1) * sizeof(uint32_t)));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, ht_cap * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->alive.p, 0, n + 16, st));
+    Graph<KT> G = gs_graph<KT>(c);
+    if (n_rows) ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G);
+    if (own) right_filter_kernel<KT><<<grid_n(own), 256, 0, st>>>(G, c->prm.min_error_coverage, c->alive.as<uint8_t>(), c->rflag.as<int32_t>(), lo, hi);
+    c->launches += 2;
+    RFX_TRY(gs_sync(c, "sharded right filter"));
+    c->ms[3] += stage_end(c);
+    c->have_contigs = false;
+    return RFX_OK;
+}
+
+// step 2 (alive bytes of every rank are in place): left fork filter for the own rows
+template <class KT> static int gs_left_impl(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const uint64_t lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi;
+    stage_begin(c);
+    if (hi > lo) left_filter_kernel<KT><<<grid_n(hi - lo), 256, 0, st>>>(gs_graph<KT>(c), c->prm.min_error_coverage, c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), lo, hi);
+    c->launches++;
+    RFX_TRY(gs_sync(c, "sharded left filter"));
+    c->ms[3] += stage_end(c);
+    return RFX_OK;
+}
+
+// step 3 (alive bytes final everywhere): links of the own nodes, splitters, segment walk
+template <class KT> static int gs_link_impl(Ctx* c, uint64_t* n_splitters) {
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
+    unsigned long long* dstat = c->dstat.as<unsigned long long>();
+    stage_begin(c);
+    RFX_CUDA(c, cudaMemsetAsync(c->succ.p, 0xff, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->pred.p, 0xff, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->open_next.p, 0xff, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->loc.p, 0xff, (n + 1) * sizeof(uint64_t), st));
+    if (own)
+        link_kernel<KT, true><<<grid_n(own), 256, 0, st>>>(gs_graph<KT>(c), c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), c->succ.as<uint32_t>(),
+                                                           c->pred.as<uint32_t>(), c->open_next.as<uint32_t>(), dstat, lo, hi);
+    uint64_t h[DS_NSLOTS];
+    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RFX_TRY(gs_sync(c, "sharded link"));
+    c->ms[3] += stage_end(c);
+    if (h[DS_GRAPH_ERR]) return ctx_fail(c, RFX_E_GRAPH, "fork filters left a (k-1)-mer with degree > 1 (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]);
+    c->n_budget = h[DS_BUDGET];
+    c->n_cycles = h[DS_CYCLES];
+    stage_begin(c);
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st));
+    uint64_t m = 0;
+    if (own) gs_splitter_select_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->alive.as<uint8_t>(), c->pred.as<uint32_t>(), c->spl_id.as<uint32_t>(), c->spl_node.as<uint32_t>(), dstat);
+    RFX_CUDA(c, cudaMemcpyAsync(&m, dstat + DS_NSPL, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_TRY(gs_sync(c, "splitter selection"));
+    if (m) gs_splitter_walk_kernel<<<grid_n(m), 256, 0, st>>>(m, lo, hi, c->spl_node.as<uint32_t>(), c->succ.as<uint32_t>(), c->loc.as<uint64_t>(), c->gs_next.as<uint32_t>(), c->gs_len.as<uint32_t>());
+    c->launches += 3;
+    RFX_TRY(gs_sync(c, "splitter walk"));
+    c->ms[4] += stage_end(c);
+    c->gs_m = m;
+    *n_splitters = m;
+    return RFX_OK;
+}
+
+// step 4 (splitter triples of every rank gathered, rank order): rank the reduced list, finish the own nodes, list chains
+static int gs_rank_impl(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads) {
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
+    unsigned long long* dstat = c->dstat.as<unsigned long long>();
+    stage_begin(c);
+    for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, c->sp_ad[i], (M + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->gs_tails, (own + 1) * sizeof(GsTail)));
+    RFX_TRY(devbuf_reserve(c, c->gs_heads, (own + 1) * sizeof(GsHead)));
+    uint32_t* gidx = c->spl_id.as<uint32_t>();  // the per-node splitter ids are no longer needed: reuse as node -> global splitter index
+    RFX_CUDA(c, cudaMemsetAsync(gidx, 0xff, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_GRAPH_ERR, 0, sizeof(uint64_t), st));
+    int scur = 0;
+    if (M) {
+        gs_index_kernel<<<grid_n(M), 256, 0, st>>>(M, g_node, gidx, c->sp_ad[0].as<uint64_t>());
+        gs_reduced_link_kernel<<<grid_n(M), 256, 0, st>>>(M, g_next, g_len, gidx, c->sp_ad[0].as<uint64_t>(), dstat);
+        c->launches += 2;
+        int slimit = 2;
+        while ((1ull << slimit) < M + 1) slimit++;
+        slimit += 2;
+        for (int round = 0; round < slimit;) {
+            RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st));
+            for (int q = 0; q < 4 && round < slimit; q++, round++) {
+                rank_step_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), c->sp_ad[scur ^ 1].as<uint64_t>(), dstat);
+                c->launches++;
+                scur ^= 1;
+            }
+            uint64_t changed = 0;
+            RFX_CUDA(c, cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            RFX_TRY(gs_sync(c, "reduced list ranking"));
+            if (!changed) break;
+        }
+        gs_cycle_check_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), dstat);
+    }
+    if (own) gs_finalize_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, my_off, c->alive.as<uint8_t>(), c->loc.as<uint64_t>(), c->sp_ad[scur].as<uint64_t>(), g_node, c->ad[0].as<uint64_t>(), dstat);
+    uint64_t h[DS_NSLOTS];
+    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RFX_TRY(gs_sync(c, "sharded rank finalize"));
+    if (h[DS_GRAPH_ERR]) return ctx_fail(c, RFX_E_GRAPH, "sharded ranking: inconsistent splitter list (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]);
+    c->gs_cycle = h[DS_CYCLE_NODES] != 0;
+    // chains: (head, length, right flag) per own tail, (head, left flag) per own head
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_ORIENTED, 0, sizeof(uint64_t), st));
+    if (own && !c->gs_cycle)
+        gs_chains_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->alive.as<uint8_t>(), c->succ.as<uint32_t>(), c->pred.as<uint32_t>(), c->ad[0].as<uint64_t>(), c->lflag.as<int32_t>(),
+                                                      c->rflag.as<int32_t>(), c->gs_tails.as<GsTail>(), c->gs_heads.as<GsHead>(), dstat);
+    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RFX_TRY(gs_sync(c, "chain listing"));
+    c->launches += 3;
+    c->ms[4] += stage_end(c);
+    c->gs_n_tails = h[DS_NSPL]; c->gs_n_heads = h[DS_CHANGED]; c->n_oriented = h[DS_ORIENTED];
+    *n_tails = c->gs_n_tails; *n_heads = c->gs_n_heads;
+    return RFX_OK;
+}
+
+// step 5 (chain tuples of every rank gathered): the contig table (identical on every rank) and the bases of the own nodes
+template <class KT> static int gs_contigs_impl(Ctx* c, const GsTail* tails, uint64_t n_tails, const GsHead* heads, uint64_t n_heads) {
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
+    unsigned long long* dstat = c->dstat.as<unsigned long long>();
+    stage_begin(c);
+    RFX_CUDA(c, cudaMemsetAsync(c->ctg_idx.p, 0xff, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->chain_len.p, 0, (n + 1) * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_BUDGET_ADM, 0, sizeof(uint64_t), st));
+    if (n_heads) gs_scatter_heads_kernel<<<grid_n(n_heads), 256, 0, st>>>(n_heads, heads, c->lflag.as<int32_t>());
+    U64x3 tot{0, 0, 0};
+    ScanPlan<U64x3> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<U64x3>::workspace_elems(n_tails + 1) * sizeof(U64x3)));
+    GsContigIn in{tails, c->lflag.as<int32_t>(), c->k, c->prm.min_contig};
+    if (n_tails) {
+        plan.bind(n_tails, c->scan_ws.as<U64x3>());
+        scan_prepare(plan, in, OpAddU64x3{}, U64x3{0, 0, 0}, st);
+        c->launches += 2 * plan.levels;
+        RFX_CUDA(c, cudaMemcpyAsync(&tot, plan.total, sizeof(tot), cudaMemcpyDeviceToHost, st));
+        RFX_TRY(gs_sync(c, "sharded contig scan"));
+    }
+    RFX_TRY(devbuf_reserve(c, c->ctg_off, (tot.a + 1) * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->ctg_left, (tot.a + 1) * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->ctg_right, (tot.a + 1) * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->ctg_bases, tot.b + 16));
+    RFX_CUDA(c, cudaMemsetAsync(c->ctg_bases.p, 0, tot.b + 16, st));
+    if (n_tails) {
+        GsContigOut out{tails, c->lflag.as<int32_t>(), c->ctg_idx.as<uint32_t>(), c->chain_len.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_left.as<int32_t>(),
+                        c->ctg_right.as<int32_t>()};
+        scan_apply(plan, in, out, OpAddU64x3{}, U64x3{0, 0, 0}, st);
+        set_u64_kernel<<<1, 1, 0, st>>>(c->ctg_off.as<uint64_t>() + tot.a, plan.total);
+    } else {
+        RFX_CUDA(c, cudaMemsetAsync(c->ctg_off.p, 0, sizeof(uint64_t), st));
+    }
+    if (own) {
+        gs_gather_kernel<KT><<<grid_n(own), 256, 0, st>>>(gs_graph<KT>(c), lo, hi, c->alive.as<uint8_t>(), c->ad[0].as<uint64_t>(), c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(),
+                                                          c->ctg_bases.as<char>());
+        gs_budget_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->open_next.as<uint32_t>(), c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), c->ad[0].as<uint64_t>(),
+                                                      c->chain_len.as<uint32_t>(), dstat);
+    }
+    c->launches += 5;
+    uint64_t adm = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&adm, dstat + DS_BUDGET_ADM, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_TRY(gs_sync(c, "sharded contig gather"));
+    c->ms[5] += stage_end(c);
+    c->n_contigs = tot.a;
+    c->n_contig_bases = tot.b;
+    c->n_budget_adm = adm;
+    return RFX_OK;
+}
+
+int stage_gs_begin(Ctx* c, uint64_t row_lo, uint64_t row_hi) {
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "rfx_gs_begin: no count table");
+    if (!c->prm.bubble) return ctx_fail(c, RFX_E_UNSUPPORTED, "-bubble: see rfx_assemble");
+    if (c->k < 2) return ctx_fail(c, RFX_E_INVALID, "assembly needs k >= 2");
+    if (row_lo > row_hi || row_hi > c->n_rows) return ctx_fail(c, RFX_E_INVALID, "rfx_gs_begin: rows [%llu, %llu) outside the table of %llu rows",
+                                                                 (unsigned long long)row_lo, (unsigned long long)row_hi, (unsigned long long)c->n_rows);
+    c->gs_row_lo = row_lo; c->gs_row_hi = row_hi; c->gs_step = 1; c->gs_cycle = false;
+    return c->wide ? gs_begin_impl<u128>(c) : gs_begin_impl<uint64_t>(c);
+}
+int stage_gs_left(Ctx* c) {
+    if (c->gs_step != 1) return ctx_fail(c, RFX_E_STATE, "rfx_gs_left: call rfx_gs_begin first");
+    c->gs_step = 2;
+    return c->wide ? gs_left_impl<u128>(c) : gs_left_impl<uint64_t>(c);
+}
+int stage_gs_link(Ctx* c, uint64_t* n_splitters) {
+    if (c->gs_step != 2) return ctx_fail(c, RFX_E_STATE, "rfx_gs_link: call rfx_gs_left first");
+    c->gs_step = 3;
+    return c->wide ? gs_link_impl<u128>(c, n_splitters) : gs_link_impl<uint64_t>(c, n_splitters);
+}
+int stage_gs_rank(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads, int32_t* has_cycle) {
+    if (c->gs_step != 3) return ctx_fail(c, RFX_E_STATE, "rfx_gs_rank: call rfx_gs_link first");
+    if (my_off + c->gs_m > M) return ctx_fail(c, RFX_E_INVALID, "rfx_gs_rank: own splitters [%llu, +%llu) outside the gathered list of %llu", (unsigned long long)my_off,
+                                              (unsigned long long)c->gs_m, (unsigned long long)M);
+    c->gs_step = 4;
+    RFX_TRY(gs_rank_impl(c, g_node, g_next, g_len, M, my_off, n_tails, n_heads));
+    *has_cycle = c->gs_cycle ? 1 : 0;
+    return RFX_OK;
+}
+int stage_gs_contigs(Ctx* c, const void* tails, uint64_t n_tails, const void* heads, uint64_t n_heads) {
+    if (c->gs_step != 4 || c->gs_cycle) return ctx_fail(c, RFX_E_STATE, "rfx_gs_contigs: call rfx_gs_rank first (and use rfx_assemble when it reports a cycle)");
+    c->gs_step = 5;
+    return c->wide ? gs_contigs_impl<u128>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads)
+                   : gs_contigs_impl<uint64_t>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads);
 }
 
 int stage_graph(Ctx* c) {

@@ -122,6 +122,12 @@ struct Ctx {
     uint64_t n_oriented = 0, n_budget = 0, n_budget_adm = 0, n_cycles = 0, n_contigs = 0, n_contig_bases = 0;
     bool have_contigs = false;
 
+    // ---- sharded graph stages (rfx_gs_*) ----
+    uint64_t gs_row_lo = 0, gs_row_hi = 0, gs_m = 0, gs_n_tails = 0, gs_n_heads = 0;
+    int gs_step = 0;
+    bool gs_cycle = false;
+    DevBuf gs_next, gs_len, gs_tails, gs_heads;
+
     float ms[6] = {0, 0, 0, 0, 0, 0};
     float ms_kernel[3] = {0, 0, 0};  // histogram, scatter, count: last launch only
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -162,6 +168,12 @@ int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);
 int stage_graph(Ctx* c);
+int stage_gs_begin(Ctx* c, uint64_t row_lo, uint64_t row_hi);
+int stage_gs_left(Ctx* c);
+int stage_gs_link(Ctx* c, uint64_t* n_splitters);
+int stage_gs_rank(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads,
+                  int32_t* has_cycle);
+int stage_gs_contigs(Ctx* c, const void* tails, uint64_t n_tails, const void* heads, uint64_t n_heads);
 uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards);
 
 inline void stage_begin(Ctx* c) { cudaEventRecord(c->ev0, c->stream); }

@@ -106,8 +106,8 @@ def sharded_count(ctx, torch, dist, device, n_bins_total: int, group=None, rebin
 
 
 def gather_tables(ctx, torch, dist, device, group=None) -> dict:
-    """Replicates the global (k-mer, count) table on every rank (all_gather of the disjoint shard tables) so the
-    graph stages can run; returns the context stats."""
+    """Replicates the global (k-mer, count) table on every rank (all_gather of the disjoint shard tables, concatenated
+    in rank order) so the graph stages can run; returns the context stats plus `row_ranges`, the rows every rank owns."""
     pk, pc, n, kb = ctx.counts_device()
     keys = device_view(torch, pk, n * kb, device)
     cnts = device_view(torch, pc, n * 4, device)
@@ -116,4 +116,67 @@ def gather_tables(ctx, torch, dist, device, group=None) -> dict:
     n_all = sum(sizes) // kb
     _sync(torch, device)
     ctx.load_counts_device(all_keys.data_ptr() if n_all else 0, all_cnts.data_ptr() if n_all else 0, n_all, append=False)
+    st = ctx.stats()
+    lo, ranges = 0, []
+    for sz in sizes:
+        ranges.append((lo, lo + sz // kb))
+        lo += sz // kb
+    st["row_ranges"] = ranges
+    return st
+
+
+def _bcast_slices(torch, dist, buf, ranges, group=None):
+    """Every rank r owns buf[ranges[r][0]:ranges[r][1]]; after the call every rank holds every slice (in place)."""
+    world = dist.get_world_size(group)
+    for r in range(world):
+        lo, hi = ranges[r]
+        if hi > lo:
+            dist.broadcast(buf[lo:hi], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
+def sharded_assemble(ctx, torch, dist, device, row_ranges, group=None) -> dict:
+    """Graph stages across the ranks of `group` (include/reflexiv_cuda.h: rfx_gs_*): every rank holds the whole table
+    (gather_tables) and does the per-node work for its own rows; one byte per node after each fork filter, the
+    splitter list of the chain walk and one tuple per chain are what travels.  On return every rank holds the same
+    contig set, as after ctx.assemble().  A graph with a closed path falls back to the replicated ctx.assemble()."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    row_lo, row_hi = row_ranges[rank]
+    oid_ranges = [(2 * a, 2 * b) for a, b in row_ranges]
+    ctx.gs_begin(row_lo, row_hi)
+    p_alive, n_nodes = ctx.gs_alive()
+    alive = device_view(torch, p_alive, n_nodes, device)
+    _bcast_slices(torch, dist, alive, oid_ranges, group)
+    _sync(torch, device)
+    ctx.gs_left()
+    _bcast_slices(torch, dist, alive, oid_ranges, group)
+    _sync(torch, device)
+    m, p_node, p_next, p_len = ctx.gs_link()
+    u32 = torch.int32
+    trip = [device_view(torch, p, m * 4, device).view(u32).clone() if m else torch.empty(0, dtype=u32, device=device) for p in (p_node, p_next, p_len)]
+    g_node, sizes = gather_varlen(torch, dist, trip[0], group)
+    g_next, _ = gather_varlen(torch, dist, trip[1], group)
+    g_len, _ = gather_varlen(torch, dist, trip[2], group)
+    m_total, my_off = sum(sizes), sum(sizes[:rank])
+    _sync(torch, device)
+    nt, p_t, nh, p_h, has_cycle = ctx.gs_rank(g_node.data_ptr() if m_total else 0, g_next.data_ptr() if m_total else 0, g_len.data_ptr() if m_total else 0,
+                                              m_total, my_off)
+    flag = torch.tensor([1 if has_cycle else 0], dtype=torch.int64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        return ctx.assemble()  # closed paths are opened by the replicated path (rare; none in the BASELINE configs)
+    tails = device_view(torch, p_t, nt * 12, device).view(u32).clone() if nt else torch.empty(0, dtype=u32, device=device)
+    heads = device_view(torch, p_h, nh * 8, device).view(u32).clone() if nh else torch.empty(0, dtype=u32, device=device)
+    all_tails, _ = gather_varlen(torch, dist, tails, group)
+    all_heads, _ = gather_varlen(torch, dist, heads, group)
+    nt_all, nh_all = all_tails.numel() // 3, all_heads.numel() // 2
+    _sync(torch, device)
+    p_bases, n_bases = ctx.gs_contigs(all_tails.data_ptr() if nt_all else 0, nt_all, all_heads.data_ptr() if nh_all else 0, nh_all)
+    st = ctx.stats()
+    if n_bases:
+        bases = device_view(torch, p_bases, n_bases, device)
+        dist.all_reduce(bases, op=dist.ReduceOp.MAX, group=group)
+    tot = torch.tensor([st["n_oriented"], st["n_budget_junctions"], st["n_budget_admissible"], st["n_cycles"]], dtype=torch.int64, device=device)
+    dist.all_reduce(tot, group=group)
+    _sync(torch, device)
+    ctx.gs_finish(*[int(x) for x in tot.tolist()])
     return ctx.stats()

@@ -1,6 +1,7 @@
 """NCCL path on real GPUs (needs >= 2): reads split across ranks, super-k-mer records exchanged with one all-to-all,
-shards counted locally, tables all-gathered, graph stages replicated.  The union of the shard tables and the contigs
-must equal the single-process oracle bit for bit."""
+shards counted locally, tables all-gathered, graph stages sharded by row owner (fork filters, links, chain walk and
+base gather on the own rows; alive bytes, splitter list and chain tuples exchanged) or, for comparison, replicated.
+The union of the shard tables and the contigs must equal the single-process oracle bit for bit."""
 import os
 import sys
 
@@ -11,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, k, rebin, out_dir):
+def _worker(rank, world, port, k, rebin, graph, out_dir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -40,8 +41,13 @@ def _worker(rank, world, port, k, rebin, out_dir):
     keys, cnt = ctx.counts()
     np.save(os.path.join(out_dir, f"keys_{rank}.npy"), keys)
     np.save(os.path.join(out_dir, f"cnt_{rank}.npy"), cnt)
-    sharded.gather_tables(ctx, torch, dist, device)
-    ctx.assemble()
+    gst = sharded.gather_tables(ctx, torch, dist, device)
+    if graph == "sharded":
+        st2 = sharded.sharded_assemble(ctx, torch, dist, device, gst["row_ranges"])
+    else:
+        st2 = ctx.assemble()
+    np.save(os.path.join(out_dir, f"asm_stats_{rank}.npy"), np.array([st2["n_oriented"], st2["n_contigs"], st2["n_contig_bases"], st2["n_budget_junctions"],
+                                                                      st2["n_budget_admissible"], st2["n_cycles"]], dtype=np.int64))
     contigs = sorted(c for c, _, _ in ctx.contigs())
     with open(os.path.join(out_dir, f"contigs_{rank}.txt"), "w") as f:
         f.write("\n".join(contigs))
@@ -50,8 +56,8 @@ def _worker(rank, world, port, k, rebin, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,rebin", [(31, False), (61, False), (31, True)])
-def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin):
+@pytest.mark.parametrize("k,rebin,graph", [(31, False, "sharded"), (61, False, "sharded"), (31, True, "replicated"), (21, False, "sharded")])
+def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin, graph):
     import torch
     import torch.multiprocessing as mp
     from conftest import make_reads
@@ -61,7 +67,7 @@ def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin):
         pytest.skip("needs >= 2 GPUs")
     world = min(world, 4)
     port = 29700 + os.getpid() % 1000 + k + (7 if rebin else 0)
-    mp.spawn(_worker, args=(world, port, k, rebin, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, k, rebin, graph, str(tmp_path)), nprocs=world, join=True)
     txt = bytes(make_reads(31, 60_000, 12_000, read_len=150, err=0.005, frag=400))
     ref = orc.run_pipeline(txt, k=k, cover=2, min_contig=200)
     c = ref["counts"]
@@ -79,3 +85,7 @@ def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin):
     expect = "\n".join(sorted(ref["asm"]["contigs"]))
     for r in range(world):
         assert (tmp_path / f"contigs_{r}.txt").read_text() == expect
+    stats = [np.load(tmp_path / f"asm_stats_{r}.npy").tolist() for r in range(world)]
+    assert all(s == stats[0] for s in stats)                                  # every rank reports the global numbers
+    a = ref["asm"]
+    assert stats[0][1] == len(a["contigs"]) and stats[0][2] == sum(len(x) for x in a["contigs"])
