@@ -195,6 +195,7 @@ def main():
     out_left = torch.empty(1 << 16, dtype=torch.int32, pin_memory=True).numpy()
     out_right = torch.empty(1 << 16, dtype=torch.int32, pin_memory=True).numpy()
     e2e_parts = {"push_fastq": 0.0, "count": 0.0, "assemble": 0.0, "fetch_contigs": 0.0}
+    lap_prof = {} if os.environ.get("RFX_BENCH_PROF") else None  # host-side stopwatch of the sharded steps (adds device syncs)
 
     def step(from_host: bool):
         ctx.reset()
@@ -207,10 +208,10 @@ def main():
         if world == 1:
             ctx.count()
         else:
-            sharded.sharded_count(ctx, torch, dist, device, n_bins_total)
-            gst = sharded.gather_tables(ctx, torch, dist, device)
+            sharded.sharded_count(ctx, torch, dist, device, n_bins_total, prof=lap_prof)
+            gst = sharded.gather_tables(ctx, torch, dist, device, prof=lap_prof)
         t2 = time.perf_counter()
-        st = ctx.assemble() if world == 1 else sharded.sharded_assemble(ctx, torch, dist, device, gst["row_ranges"])
+        st = ctx.assemble() if world == 1 else sharded.sharded_assemble(ctx, torch, dist, device, gst["row_ranges"], prof=lap_prof)
         t3 = time.perf_counter()
         if from_host:
             bases, offs, left, right = ctx.contigs_raw((out_bases, out_offs, out_left, out_right))
@@ -258,6 +259,8 @@ def main():
 
     for _ in range(args.warmup):
         step(False)
+    if lap_prof is not None:
+        lap_prof.clear()
     sampler = ClockSampler(local)
     sampler.start()
     t_dev, stats, launches, _ = timed(args.steps, False)
@@ -324,6 +327,9 @@ def main():
             "gpu_launches": launches, "clocks": clocks}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = {k: v for k, v in cpu_reference_run().items() if k in ("value", "unit", "cores", "kind", "sample", "count_stage_kmers_per_s", "reads_per_s")}
+    if lap_prof:
+        print(f"rank {rank} host stopwatch (ms per step, after warm-up):", {k2: round(v / (2 * args.steps + 1) * 1e3, 3) for k2, v in lap_prof.items()},
+              file=sys.stderr)
     if rank == 0:
         emit(line)
     ctx.close()

@@ -174,6 +174,9 @@ int rfx_load_records_device(rfx_ctx* ctx, const void* d_records, uint64_t n_byte
  * Do not mix with rfx_load_records_device inside one rfx_begin_shard. */
 int rfx_shard_bin_offsets(rfx_ctx* ctx, int32_t shard, const uint64_t** d_offsets, uint32_t* n_offsets);
 int rfx_load_segment_device(rfx_ctx* ctx, const void* d_records, uint64_t n_bytes, const uint64_t* d_bin_offsets);
+/* Optional zero-copy receive: after rfx_begin_shard, a device buffer of n_bytes owned by the context; slices received
+ * into it back to back (sender 0 first) and then announced with rfx_load_segment_device in that order are used in place. */
+int rfx_rx_buffer(rfx_ctx* ctx, uint64_t n_bytes, void** d_ptr);
 int rfx_record_bytes(rfx_ctx* ctx, int32_t* bytes_per_record);
 /* The filtered table as device pointers (valid until the next rfx_count / rfx_load_* / rfx_reset): keys are
  * key_bytes (8 for k <= 31, 16 for k > 31) little-endian right-aligned 2k-bit integers, i.e. the library's internal

@@ -62,6 +62,7 @@ SYMBOLS = {
     "rfx_stats": (C.c_int, [_P, C.POINTER(RfxStats)]),
     "rfx_partition": (C.c_int, [_P, C.c_int32, C.c_uint32]),
     "rfx_choose_bins": (C.c_uint32, [_P, C.c_uint64, C.c_int32]),
+    "rfx_rx_buffer": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_void_p)]),
     "rfx_gs_begin": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "rfx_gs_alive": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "rfx_gs_left": (C.c_int, [_P]),

@@ -514,6 +514,16 @@ int rfx_load_records_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes)
     return RFX_OK;
 }
 
+int rfx_rx_buffer(rfx_ctx* c, uint64_t n_bytes, void** d_ptr) {
+    if (!c || !d_ptr) return RFX_E_INVALID;
+    if (c->shard_id < 0) return ctx_fail(c, RFX_E_STATE, "rfx_rx_buffer: call rfx_begin_shard first");
+    if (c->rx_bytes) return ctx_fail(c, RFX_E_STATE, "rfx_rx_buffer: segments were already loaded");
+    cudaSetDevice(c->prm.device);
+    RFX_TRY(devbuf_reserve(c, c->rx_records, n_bytes + 16));
+    *d_ptr = c->rx_records.p;
+    return RFX_OK;
+}
+
 int rfx_counts_device(rfx_ctx* c, const void** d_keys, const uint32_t** d_counts, uint64_t* n_rows, int32_t* key_bytes) {
     if (!c) return RFX_E_INVALID;
     if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "no count table");
@@ -563,7 +573,9 @@ int rfx_load_segment_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes,
     const uint32_t bps = c->forced_bins / (uint32_t)c->n_shards;
     RFX_TRY(devbuf_reserve(c, c->rx_records, c->rx_bytes + n_bytes + 16, true));
     RFX_TRY(devbuf_reserve(c, c->seg_off, (size_t)(c->n_seg + 1) * (bps + 1) * sizeof(uint64_t), true));
-    if (n_bytes) RFX_CUDA(c, cudaMemcpyAsync(c->rx_records.as<uint8_t>() + c->rx_bytes, d_records, n_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    // a slice received straight into rfx_rx_buffer() memory is already where it belongs
+    if (n_bytes && d_records != (const void*)(c->rx_records.as<uint8_t>() + c->rx_bytes))
+        RFX_CUDA(c, cudaMemcpyAsync(c->rx_records.as<uint8_t>() + c->rx_bytes, d_records, n_bytes, cudaMemcpyDeviceToDevice, c->stream));
     RFX_CUDA(c, cudaMemcpyAsync(c->seg_off.as<uint64_t>() + (size_t)c->n_seg * (bps + 1), d_bin_offsets, (size_t)(bps + 1) * sizeof(uint64_t),
                                 cudaMemcpyDeviceToDevice, c->stream));
     RFX_CUDA(c, cudaStreamSynchronize(c->stream));

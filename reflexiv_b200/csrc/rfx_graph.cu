@@ -562,6 +562,9 @@ struct GsTail { uint32_t head, len; int32_t rflag; };
 struct GsHead { uint32_t head; int32_t lflag; };
 
 __device__ __forceinline__ bool gs_own(uint32_t x, uint64_t lo, uint64_t hi) { return x >= lo && x < hi; }
+// own segments already end at every GPU boundary (every ~10 nodes with minimiser sharding), so the random sample only
+// has to bound the walk through unusually long own stretches
+__device__ __forceinline__ bool gs_random_splitter(uint32_t x) { return (fmix32(x ^ 0xa5a5a5a5u) & 127u) == 0u; }
 
 __global__ void gs_splitter_select_kernel(uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred,
                                           uint32_t* __restrict__ spl_id, uint32_t* __restrict__ spl_node, unsigned long long* dstat) {
@@ -569,7 +572,7 @@ __global__ void gs_splitter_select_kernel(uint64_t lo, uint64_t hi, const uint8_
         uint32_t id = NONE32;
         if (alive[x] & 2) {
             const uint32_t p = pred[x];
-            if (p == NONE32 || is_random_splitter((uint32_t)x) || !gs_own(p, lo, hi)) {
+            if (p == NONE32 || gs_random_splitter((uint32_t)x) || !gs_own(p, lo, hi)) {
                 id = (uint32_t)atomicAdd(&dstat[DS_NSPL], 1ull);
                 spl_node[id] = (uint32_t)x;
             }
@@ -585,7 +588,7 @@ __global__ void gs_splitter_walk_kernel(uint64_t m, uint64_t lo, uint64_t hi, co
         uint32_t off = 0;
         loc[x] = ad_pack((uint32_t)id, 0u);
         uint32_t y = succ[x];
-        while (y != NONE32 && gs_own(y, lo, hi) && !is_random_splitter(y)) {
+        while (y != NONE32 && gs_own(y, lo, hi) && !gs_random_splitter(y)) {
             off++;
             loc[y] = ad_pack((uint32_t)id, off);
             y = succ[y];
@@ -764,13 +767,14 @@ template <class KT> static int gs_left_impl(Ctx* c) {
 // step 3 (alive bytes final everywhere): links of the own nodes, splitters, segment walk
 template <class KT> static int gs_link_impl(Ctx* c, uint64_t* n_splitters) {
     cudaStream_t st = c->stream;
-    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
+    const uint64_t lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
     unsigned long long* dstat = c->dstat.as<unsigned long long>();
     stage_begin(c);
-    RFX_CUDA(c, cudaMemsetAsync(c->succ.p, 0xff, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->pred.p, 0xff, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->open_next.p, 0xff, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->loc.p, 0xff, (n + 1) * sizeof(uint64_t), st));
+    // per-node arrays are only ever read at own nodes: clear the own range
+    RFX_CUDA(c, cudaMemsetAsync(c->succ.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->pred.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->open_next.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->loc.as<uint64_t>() + lo, 0xff, own * sizeof(uint64_t), st));
     if (own)
         link_kernel<KT, true><<<grid_n(own), 256, 0, st>>>(gs_graph<KT>(c), c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), c->succ.as<uint32_t>(),
                                                            c->pred.as<uint32_t>(), c->open_next.as<uint32_t>(), dstat, lo, hi);

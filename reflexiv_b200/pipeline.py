@@ -213,6 +213,11 @@ class ReflexivContext:
     def load_segment_device(self, rec_ptr: int, n_bytes: int, offsets_ptr: int):
         self._check(self.L.rfx_load_segment_device(self._ctx, rec_ptr, n_bytes, offsets_ptr), self._ctx)
 
+    def rx_buffer(self, n_bytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.L.rfx_rx_buffer(self._ctx, n_bytes, C.byref(p)), self._ctx)
+        return p.value or 0
+
     def counts_device(self):
         """(keys device pointer, counts device pointer, n_rows, key_bytes) of the filtered table in HBM."""
         pk, pc, n, kb = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_int32()
