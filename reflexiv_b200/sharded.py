@@ -165,9 +165,23 @@ def gather_tables(ctx, torch, dist, device, group=None, prof=None) -> dict:
     return st
 
 
+_UNEVEN_ALL_GATHER = {}
+
+
 def _bcast_slices(torch, dist, buf, ranges, group=None):
-    """Every rank r owns buf[ranges[r][0]:ranges[r][1]]; after the call every rank holds every slice (in place)."""
-    world = dist.get_world_size(group)
+    """Every rank r owns buf[ranges[r][0]:ranges[r][1]]; after the call every rank holds every slice (in place).
+    One all_gather over views of `buf` where the backend takes uneven sizes (NCCL: one grouped launch), else one
+    broadcast per rank."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    key = dist.get_backend(group)
+    if _UNEVEN_ALL_GATHER.get(key, True):
+        try:
+            views = [buf[lo:hi] for lo, hi in ranges]
+            dist.all_gather(views, views[rank].clone(), group=group)
+            _UNEVEN_ALL_GATHER[key] = True
+            return
+        except (RuntimeError, ValueError, NotImplementedError):
+            _UNEVEN_ALL_GATHER[key] = False
     for r in range(world):
         lo, hi = ranges[r]
         if hi > lo:
