@@ -487,6 +487,16 @@ uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards) {
     return (uint32_t)nb;
 }
 
+// Minimiser length.  Bins are whole minimiser values, so there must be many more values than bins or the bins come
+// out uneven: 4^11 / 2 = 2.1 M canonical 11-mers serve up to 2^16 bins, beyond that 15-mers (5.4 * 10^8 values).  The
+// rule depends on the TOTAL bin count only, so every rank of a sharded run derives the same m.
+static void set_minimizer(Ctx* c, uint32_t n_bins_total) {
+    int m = c->prm.minimizer_len > 0 ? c->prm.minimizer_len : (n_bins_total > 65536u ? 15 : 11);
+    if (m > 16) m = 16;
+    if (m > c->k) m = c->k;
+    c->m = m;
+}
+
 static uint32_t choose_bins(Ctx* c, int n_shards) {
     if (c->forced_bins) return c->forced_bins;
     return choose_bin_count(c, c->n_instances, n_shards);
@@ -497,7 +507,7 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     cudaStream_t st = c->stream;
     const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring
     const size_t smem_scan = smem + (size_t)2 * SCAN_Q * PART_THREADS * sizeof(uint32_t);  // + the change queues
-    const bool fixed = P.k == 31 && P.m == 11;
+    const bool fixed = P.k == 31 && P.m == 11, fast15 = P.k == 31 && P.m == 15;
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     if (fixed) {
@@ -506,6 +516,13 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
                                                                              c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
         bin_scan_kernel<true, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
                                                                               c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
+        c->launches += 2;
+    } else if (fast15) {
+        // large inputs (more than 2^16 bins): same register-resident scan with 15-mers
+        bin_scan_fast_kernel<31, 15, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
+                                                                             c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
+        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
+                                                                               c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
         c->launches += 2;
     } else {
         bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
@@ -543,6 +560,7 @@ int stage_partition_slab(Ctx* c) {
     stage_begin(c);
     c->n_shards = 1;
     c->n_bins = choose_bin_count(c, c->n_instances, 1);
+    set_minimizer(c, c->n_bins);
     BinParams P;
     P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
     const size_t nb = c->n_bins;
@@ -623,6 +641,7 @@ int stage_partition(Ctx* c, int n_shards) {
     c->n_shards = n_shards;
     c->n_bins = choose_bins(c, n_shards);
     if (c->n_bins % (uint32_t)n_shards) return ctx_fail(c, RFX_E_INVALID, "n_bins_total %u is not a multiple of n_shards %d", c->n_bins, n_shards);
+    set_minimizer(c, c->n_bins);
     BinParams P;
     P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
     // descriptor slots per read: twice the expected number of runs (a run is about (w+1)/2 k-mers), 8..64
@@ -731,6 +750,7 @@ int stage_rebin(Ctx* c) {
     stage_begin(c);
     const uint32_t bps = c->forced_bins / (uint32_t)c->n_shards;
     const uint64_t n_rec = c->rx_bytes / (uint64_t)(c->recw * 8);
+    set_minimizer(c, c->forced_bins);
     BinParams P;
     P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->forced_bins; P.max_nk = c->max_nk;
     c->n_bins = bps;

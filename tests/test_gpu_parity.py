@@ -165,6 +165,18 @@ def test_counts_match_oracle_all_k(R, orc, example_text, k):
     assert np.array_equal(g_counts, counts)
 
 
+@pytest.mark.parametrize("k,m", [(31, 15), (31, 9), (27, 15), (61, 16)])
+def test_counts_do_not_depend_on_the_minimiser_length(R, orc, example_text, k, m):
+    """m = 15 is what inputs with more than 2^16 bins use (register-resident scan, single-pass slab partition)."""
+    ints, counts, c, _ = _oracle_table(orc, example_text, k, orc.FASTQ_RUN)
+    with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1), minimizer_len=m) as ctx:
+        ctx.push_fastq(example_text)
+        st = ctx.count()
+        g_ints, g_counts = _sorted_table(R, ctx, k)
+    assert st["n_instances"] == c["n_instances"] and st["n_distinct"] == c["n_distinct"]
+    assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
 @pytest.mark.parametrize("counter_mode,cover,maxcov", [(False, 2, 10_000_000), (False, 3, 20), (True, 1, 10_000_000), (True, 2, 30), (True, 0, 5)])
 def test_coverage_filter_rules(R, orc, example_text, counter_mode, cover, maxcov):
     """A4: `run` always applies both bounds; `counter` only applies cover if > 1 and maxcov if < 10^7."""
