@@ -288,6 +288,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int N> __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 constexpr int CNT_STAGES = 2;
+#ifndef K4_SOLO_MAX
+#define K4_SOLO_MAX 0u  // bins with at most this many distinct k-mers are compacted by warp 0 alone (0: always all warps)
+#endif
 constexpr uint32_t BIN_END = 0xffffffffu;
 
 // what the producer warp hands over per bin
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     uint16_t* ridx = reinterpret_cast<uint16_t*>(rmult + RCAP);
     uint16_t* ulist = ridx + RCAP;   // [CHUNK] entries of the chunk: slot (< RCAP) or RCAP + record index (a record that lost a tag collision)
     uint16_t* klist = ulist + CHUNK; // [KMAX]
-    __shared__ uint32_t s_distinct, s_overflow, s_sp, s_nuniq, s_npass, s_cursor, s_early;
+    __shared__ uint32_t s_distinct[2], s_nuniq[2], s_overflow, s_sp, s_npass, s_cursor, s_early;
     __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
     __shared__ unsigned long long s_out_base;
     __shared__ BinDesc s_desc[CNT_STAGES];
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     if (warp < NW) {
         for (int i = tid; i < CAP; i += NT) { if (WIDE) tags[i] = 0u; else keys[i] = ~0ull; cnts[i] = 0u; }
         for (int i = tid; i < RCAP; i += NT) { rtag[i] = 0u; rmult[i] = 0u; }
+        if (tid == 0) { s_distinct[0] = s_distinct[1] = 0; s_nuniq[0] = s_nuniq[1] = 0; s_overflow = 0; }
     }
     __syncthreads();
 
@@ -410,31 +414,244 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     }
 
     // ---------------- compute warps ----------------
-    const KmerTable<WIDE, CAP> T{keys, keys_lo, tags, cnts, klist, &s_distinct, &s_overflow, A.dstat + DS_OVF_WHY};
+    // Counters are double buffered by bin parity, so the common case -- one class, one staged chunk -- needs no barrier
+    // beyond the three that separate A1 | A2 | B | K4: thread 0 clears the other parity's counters right behind the
+    // first barrier of a bin, when nobody can still be reading them.
     auto clear_all = [&]() {
         for (int i = tid; i < CAP; i += NT) { if (WIDE) tags[i] = 0u; else keys[i] = ~0ull; cnts[i] = 0u; }
         for (int i = tid; i < RCAP; i += NT) { rtag[i] = 0u; rmult[i] = 0u; }
     };
     uint32_t aux_phase = 0;
+    unsigned long long acc_inst = 0, acc_distinct = 0;  // warp 0 / lane 0: flushed once at the end
     for (uint32_t it = 0;; it++) {
         const int st = (int)(it % CNT_STAGES);
+        const int par = (int)(it & 1u);
         mbar_wait(&s_full[st], (it / CNT_STAGES) & 1);
         const BinDesc& D = s_desc[st];
         if (D.bin == BIN_END) break;
         const uint64_t* buf = rbuf + (size_t)st * CHUNK * RECW;
         const uint32_t n_rec = D.seg_pre[n_seg];
-        bool staged = true;  // the buffer holds chunk 0 of the bin
-        compute_barrier<NT>();  // every thread has left the previous bin's class loop before the stack is re-armed
-        if (tid == 0) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
+        uint32_t* const nuniq = &s_nuniq[par];
+        const KmerTable<WIDE, CAP> T{keys, keys_lo, tags, cnts, klist, &s_distinct[par], &s_overflow, A.dstat + DS_OVF_WHY};
+
+        // A1 | A2 | B of one chunk of `cn` records sitting in `buf`; `after_first` runs on thread 0 behind the first barrier
+        auto run_chunk = [&](uint32_t cn, uint32_t depth, uint32_t cval, bool fast) {
+            // ---- A1: collapse identical records ----
+            uint64_t v[PER_THREAD][RECW];
+            uint32_t myslot[PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; j++) {
+                const uint32_t li = (uint32_t)j * NT + tid;  // chunk-local record index
+                myslot[j] = 0xffffffffu;
+                if (li < cn) {
+#pragma unroll
+                    for (int q = 0; q < RECW; q += 2) {
+                        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
+                        v[j][q] = x.x; v[j][q + 1] = x.y;
+                    }
+                    uint32_t h, tag;
+                    record_hash<RECW>(v[j], h, tag);
+                    uint32_t slot = h & (RCAP - 1);
+                    while (true) {  // at most CHUNK < RCAP entries: an empty slot always exists
+                        uint32_t cur = rtag[slot];
+                        if (cur == 0u) {
+                            cur = atomicCAS(&rtag[slot], 0u, tag);
+                            if (cur == 0u) { ridx[slot] = (uint16_t)li; ulist[atomicAdd(nuniq, 1u)] = (uint16_t)slot; break; }
+                        }
+                        if (cur == tag) break;
+                        slot = (slot + 1) & (RCAP - 1);
+                    }
+                    atomicAdd(&rmult[slot], 1u);
+                    myslot[j] = slot;
+                }
+            }
+            compute_barrier<NT>();
+            if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_overflow = 0; }
+            // ---- A2: confirm against the claimant's record ----
+#pragma unroll
+            for (int j = 0; j < PER_THREAD; j++) {
+                if (myslot[j] != 0xffffffffu) {
+                    const uint32_t li = (uint32_t)j * NT + tid;
+                    const uint32_t ci = ridx[myslot[j]];
+                    if (ci != li) {
+                        bool same = true;
+#pragma unroll
+                        for (int q = 0; q < RECW; q += 2) {
+                            const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)ci * RECW + q);
+                            same = same && x.x == v[j][q] && x.y == v[j][q + 1];
+                        }
+                        if (!same) {
+                            atomicSub(&rmult[myslot[j]], 1u);
+                            ulist[atomicAdd(nuniq, 1u)] = (uint16_t)(RCAP + li);
+                        }
+                    }
+                }
+            }
+            compute_barrier<NT>();
+            // ---- B: expand the distinct records, spread evenly over the warps ----
+            const int n_uniq = (int)*nuniq;
+#ifdef RFX_DEBUG_COUNT
+            if (tid == 0) { atomicAdd(&A.dstat[20], (unsigned long long)n_uniq); atomicAdd(&A.dstat[21], (unsigned long long)cn); }
+#endif
+            int per = (n_uniq + NW - 1) / NW;
+            per = per < 4 ? 4 : per > 32 ? 32 : per;
+#pragma unroll 1
+            for (int pass = 0; pass < (WIDE ? 2 : 1); pass++) {
+                const bool last = pass == (WIDE ? 1 : 0);
+                for (int ubase = warp * per; ubase < n_uniq; ubase += NW * per) {
+                    if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
+                    const int u = ubase + lane;
+                    uint32_t mult = 0, nk = 0;
+                    uint64_t w[RECW];
+#pragma unroll
+                    for (int q = 0; q < RECW; q++) w[q] = 0ull;
+                    if (lane < per && u < n_uniq) {
+                        const uint32_t e = ulist[u];
+                        uint32_t li;
+                        if (e < (uint32_t)RCAP) {
+                            mult = rmult[e]; li = ridx[e];
+                            if (last) { rtag[e] = 0u; rmult[e] = 0u; }  // the slot is this lane's alone: leave it clean
+                        } else { mult = 1u; li = e - RCAP; }
+                        if (mult) {
+#pragma unroll
+                            for (int q = 0; q < RECW; q += 2) {
+                                const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
+                                w[q] = x.x; w[q + 1] = x.y;
+                            }
+                            nk = (uint32_t)(w[0] >> 48);
+                        }
+                    }
+                    if (!WIDE) expand_warp<false>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 0>{T, depth, cval}, &s_overflow);
+                    else if (pass == 0) expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 1>{T, depth, cval}, &s_overflow);
+                    else expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 2>{T, depth, cval}, &s_overflow);
+                }
+                compute_barrier<NT>();
+            }
+        };
+
+        bool slow = n_rec > (uint32_t)CHUNK, resume_split = false;
+        if (!slow) {
+            // ---- fast path: the whole bin is the staged chunk, depth 0 ----
+            run_chunk(n_rec, 0u, 0u, true);
+            // (run_chunk ended on a barrier: the stage and the record-tag table are free, the k-mer table is complete)
+            const bool ovf = s_overflow != 0;
+            const uint32_t nd = s_distinct[par];
+            if (!ovf) {
+                if (tid == 0) mbar_arrive(&s_empty[st]);
+                if (nd <= K4_SOLO_MAX) {
+                    // K4 by warp 0 alone while the other warps move on to the next bin's A1
+                    if (warp == 0) {
+                        uint32_t mine = 0, inst = 0;
+                        for (uint32_t i = lane; i < nd; i += 32) {
+                            const uint32_t c = cnts[klist[i]];
+                            inst += c;
+                            mine += (c >= A.min_count && c <= A.max_count) ? 1u : 0u;
+                        }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) { mine += __shfl_xor_sync(0xffffffffu, mine, d); inst += __shfl_xor_sync(0xffffffffu, inst, d); }
+                        unsigned long long base = 0;
+                        if (lane == 0) {
+                            acc_inst += inst; acc_distinct += nd;
+                            if (mine && !A.dry) {
+                                base = atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)mine);
+                                if (base + mine > A.out_cap) { atomicExch(&A.dstat[DS_OVERFLOW], 1ull); base = ~0ull; }
+                            } else base = ~0ull;
+                        }
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        uint32_t done = 0;
+                        for (uint32_t i0 = 0; i0 < nd; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            bool keep = false;
+                            uint32_t c = 0, slot = 0;
+                            if (i < nd) { slot = klist[i]; c = cnts[slot]; keep = c >= A.min_count && c <= A.max_count; }
+                            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                            if (i < nd) {
+                                if (keep && base != ~0ull) {
+                                    const unsigned long long o = base + done + (uint32_t)__popc(ball & ((1u << lane) - 1u));
+                                    if (!WIDE) reinterpret_cast<uint64_t*>(A.out_keys)[o] = keys[slot];
+                                    else reinterpret_cast<KT*>(A.out_keys)[o] = ((u128)keys[slot] << 64) | keys_lo[slot];
+                                    A.out_counts[o] = c;
+                                }
+                                if (WIDE) tags[slot] = 0u; else keys[slot] = ~0ull;
+                                cnts[slot] = 0u;
+                            }
+                            done += (uint32_t)__popc(ball);
+                        }
+                    }
+                    continue;
+                }
+                // many distinct k-mers (noisy reads): everybody helps, at the price of two more barriers
+                if (tid == 0) { s_npass = 0; s_cursor = 0; }
+                compute_barrier<NT>();
+                uint32_t mine = 0, inst = 0;
+                for (uint32_t i = tid; i < nd; i += NT) {
+                    const uint32_t c = cnts[klist[i]];
+                    inst += c;
+                    mine += (c >= A.min_count && c <= A.max_count) ? 1u : 0u;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { mine += __shfl_xor_sync(0xffffffffu, mine, d); inst += __shfl_xor_sync(0xffffffffu, inst, d); }
+                if (lane == 0) {
+                    if (mine) atomicAdd(&s_npass, mine);
+                    if (inst) atomicAdd(&A.dstat[DS_INSTANCES], (unsigned long long)inst);
+                }
+                compute_barrier<NT>();
+                if (tid == 0) {
+                    const uint32_t tot = s_npass;
+                    s_out_base = (tot && !A.dry) ? atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)tot) : 0ull;
+                    atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)nd);
+                    if (!A.dry && s_out_base + tot > A.out_cap) atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
+                }
+                compute_barrier<NT>();
+                const bool room = !A.dry && s_out_base + s_npass <= A.out_cap;
+                for (uint32_t i0 = (uint32_t)warp * 32u; i0 < nd; i0 += NT) {
+                    const uint32_t i = i0 + lane;
+                    bool keep = false;
+                    uint32_t c = 0, slot = 0;
+                    if (i < nd) { slot = klist[i]; c = cnts[slot]; keep = c >= A.min_count && c <= A.max_count; }
+                    const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                    uint32_t base = 0;
+                    if (lane == 0 && ball) base = atomicAdd(&s_cursor, (uint32_t)__popc(ball));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (i < nd) {
+                        if (keep && room) {
+                            const unsigned long long o = s_out_base + base + (uint32_t)__popc(ball & ((1u << lane) - 1u));
+                            if (!WIDE) reinterpret_cast<uint64_t*>(A.out_keys)[o] = keys[slot];
+                            else reinterpret_cast<KT*>(A.out_keys)[o] = ((u128)keys[slot] << 64) | keys_lo[slot];
+                            A.out_counts[o] = c;
+                        }
+                        if (WIDE) tags[slot] = 0u; else keys[slot] = ~0ull;
+                        cnts[slot] = 0u;
+                    }
+                }
+                continue;
+            }
+            // the table overflowed: split depth 0 in two and let the general loop run the halves
+            compute_barrier<NT>();
+            if (tid == 0) {
+                s_sp = 0;
+                for (uint32_t c = 0; c < 2u; c++) { s_stack_val[s_sp] = c; s_stack_depth[s_sp] = 1u; s_sp++; }
+                atomicAdd(&A.dstat[DS_SPLITS], 1ull);
+            }
+            clear_all();
+            slow = true; resume_split = true;
+        }
+        // ---- general path: several chunks and / or sub-classes ----
+        bool staged = !resume_split;  // the buffer holds chunk 0 of the bin
+        compute_barrier<NT>();  // every thread has left the previous bin before the stack is re-armed
+        if (tid == 0) {
+            if (!resume_split) { s_sp = 1; s_stack_val[0] = 0; s_stack_depth[0] = 0; }
+            s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0;
+        }
         while (true) {
             compute_barrier<NT>();
             if (s_sp == 0) break;
             const uint32_t depth = s_stack_depth[s_sp - 1], cval = s_stack_val[s_sp - 1];
             compute_barrier<NT>();
-            if (tid == 0) { s_sp--; s_distinct = 0; s_overflow = 0; s_npass = 0; s_cursor = 0; s_early = 0; }
+            if (tid == 0) { s_sp--; s_distinct[par] = 0; s_overflow = 0; s_npass = 0; s_cursor = 0; s_early = 0; }
             for (uint32_t cbeg = 0; cbeg < n_rec; cbeg += CHUNK) {
                 const uint32_t cn = n_rec - cbeg < (uint32_t)CHUNK ? n_rec - cbeg : (uint32_t)CHUNK;
-                if (tid == 0) s_nuniq = 0;
+                if (tid == 0) s_nuniq[par] = 0;
                 if (!(staged && cbeg == 0)) {
                     // later chunks and sub-class re-runs: fetched on demand (every thread is past its reads of the buffer)
                     compute_barrier<NT>();
@@ -445,96 +662,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 }
                 compute_barrier<NT>();
                 if (s_overflow) break;
-                // ---- A1: collapse identical records ----
-                uint64_t v[PER_THREAD][RECW];
-                uint32_t myslot[PER_THREAD];
-#pragma unroll
-                for (int j = 0; j < PER_THREAD; j++) {
-                    const uint32_t li = (uint32_t)j * NT + tid;  // chunk-local record index
-                    myslot[j] = 0xffffffffu;
-                    if (li < cn) {
-#pragma unroll
-                        for (int q = 0; q < RECW; q += 2) {
-                            const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
-                            v[j][q] = x.x; v[j][q + 1] = x.y;
-                        }
-                        uint32_t h, tag;
-                        record_hash<RECW>(v[j], h, tag);
-                        uint32_t slot = h & (RCAP - 1);
-                        while (true) {  // at most CHUNK < RCAP entries: an empty slot always exists
-                            uint32_t cur = rtag[slot];
-                            if (cur == 0u) {
-                                cur = atomicCAS(&rtag[slot], 0u, tag);
-                                if (cur == 0u) { ridx[slot] = (uint16_t)li; ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)slot; break; }
-                            }
-                            if (cur == tag) break;
-                            slot = (slot + 1) & (RCAP - 1);
-                        }
-                        atomicAdd(&rmult[slot], 1u);
-                        myslot[j] = slot;
-                    }
-                }
-                compute_barrier<NT>();
-                // ---- A2: confirm against the claimant's record ----
-#pragma unroll
-                for (int j = 0; j < PER_THREAD; j++) {
-                    if (myslot[j] != 0xffffffffu) {
-                        const uint32_t li = (uint32_t)j * NT + tid;
-                        const uint32_t ci = ridx[myslot[j]];
-                        if (ci != li) {
-                            bool same = true;
-#pragma unroll
-                            for (int q = 0; q < RECW; q += 2) {
-                                const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)ci * RECW + q);
-                                same = same && x.x == v[j][q] && x.y == v[j][q + 1];
-                            }
-                            if (!same) {
-                                atomicSub(&rmult[myslot[j]], 1u);
-                                ulist[atomicAdd(&s_nuniq, 1u)] = (uint16_t)(RCAP + li);
-                            }
-                        }
-                    }
-                }
-                compute_barrier<NT>();
-                // ---- B: expand the distinct records, spread evenly over the warps ----
-                const int n_uniq = (int)s_nuniq;
-#ifdef RFX_DEBUG_COUNT
-                if (tid == 0) { atomicAdd(&A.dstat[20], (unsigned long long)n_uniq); atomicAdd(&A.dstat[21], (unsigned long long)cn); }
-#endif
-                int per = (n_uniq + NW - 1) / NW;
-                per = per < 4 ? 4 : per > 32 ? 32 : per;
-#pragma unroll 1
-                for (int pass = 0; pass < (WIDE ? 2 : 1); pass++) {
-                    const bool last = pass == (WIDE ? 1 : 0);
-                    for (int ubase = warp * per; ubase < n_uniq; ubase += NW * per) {
-                        if (__any_sync(0xffffffffu, *(volatile uint32_t*)&s_overflow)) break;  // warp-uniform: shuffles follow
-                        const int u = ubase + lane;
-                        uint32_t mult = 0, nk = 0;
-                        uint64_t w[RECW];
-#pragma unroll
-                        for (int q = 0; q < RECW; q++) w[q] = 0ull;
-                        if (lane < per && u < n_uniq) {
-                            const uint32_t e = ulist[u];
-                            uint32_t li;
-                            if (e < (uint32_t)RCAP) {
-                                mult = rmult[e]; li = ridx[e];
-                                if (last) { rtag[e] = 0u; rmult[e] = 0u; }  // the slot is this lane's alone: leave it clean
-                            } else { mult = 1u; li = e - RCAP; }
-                            if (mult) {
-#pragma unroll
-                                for (int q = 0; q < RECW; q += 2) {
-                                    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
-                                    w[q] = x.x; w[q + 1] = x.y;
-                                }
-                                nk = (uint32_t)(w[0] >> 48);
-                            }
-                        }
-                        if (!WIDE) expand_warp<false>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 0>{T, depth, cval}, &s_overflow);
-                        else if (pass == 0) expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 1>{T, depth, cval}, &s_overflow);
-                        else expand_warp<true>(w, nk, mult, k, lane, KmerSink<WIDE, CAP, 2>{T, depth, cval}, &s_overflow);
-                    }
-                    compute_barrier<NT>();
-                }
+                run_chunk(cn, depth, cval, false);
                 if (s_overflow && tid == 0 && 2 * (cbeg + cn) <= n_rec) s_early = 1;  // overflowed within the first half
             }
             compute_barrier<NT>();
@@ -556,7 +684,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             }
             if (n_rec > (uint32_t)CHUNK) staged = false;
             // ---- K4: coverage filter + compaction over the occupied slots ----
-            const uint32_t nd = s_distinct;
+            const uint32_t nd = s_distinct[par];
             uint32_t mine = 0, inst = 0;
             for (uint32_t i = tid; i < nd; i += NT) {
                 const uint32_t c = cnts[klist[i]];
@@ -604,7 +732,11 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             }
         }
         // the class loop left through a compute barrier: every thread is done with the stage
-        if (tid == 0) mbar_arrive(&s_empty[st]);
+        if (tid == 0) { mbar_arrive(&s_empty[st]); s_nuniq[par] = 0; s_distinct[par] = 0; }
+    }
+    if (tid == 0) {
+        if (acc_inst) atomicAdd(&A.dstat[DS_INSTANCES], acc_inst);
+        if (acc_distinct) atomicAdd(&A.dstat[DS_DISTINCT], acc_distinct);
     }
 }
 

@@ -339,14 +339,20 @@ __global__ void __launch_bounds__(PART_THREADS)
         }
         const uint32_t n_mmers = len0 - (uint32_t)M + 1u;
         const uint32_t n_full = n_mmers / (uint32_t)W, rem = n_mmers % (uint32_t)W;
-        S.template block<0>(packed_window(rd, (uint64_t)(M - 1)), 0u - (uint32_t)(W - 1), W);
+        // the 64-bit base window of block b + 1 is requested before block b is worked on: its latency (the first touch of
+        // a read's words misses L1) hides behind ~500 instructions instead of stalling the warp at every block start
+        uint64_t win = packed_window(rd, (uint64_t)(M - 1));
+        uint64_t win_next = (n_full > 1 || rem) ? packed_window(rd, (uint64_t)(M - 1) + (uint64_t)W) : 0ull;
+        S.template block<0>(win, 0u - (uint32_t)(W - 1), W);
         for (uint32_t b = 1; b < n_full; b++) {
-            S.template block<1>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)b * W), b * W - (uint32_t)(W - 1), W);
+            win = win_next;
+            if (b + 1 < n_full || rem) win_next = packed_window(rd, (uint64_t)(M - 1) + (uint64_t)(b + 1) * W);
+            S.template block<1>(win, b * W - (uint32_t)(W - 1), W);
             if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
         }
         if (rem) {
             if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
-            S.template block<2>(packed_window(rd, (uint64_t)(M - 1) + (uint64_t)n_full * W), n_full * W - (uint32_t)(W - 1), (int)rem);
+            S.template block<2>(win_next, n_full * W - (uint32_t)(W - 1), (int)rem);
         }
         drain(true, len0 - (uint32_t)K + 1u);
         if (Factory::kNeedsRuns) {
