@@ -17,47 +17,131 @@
 // After the two fork filters every (k-1)-mer has at most one surviving out-edge and one in-edge, so
 // the reference's sort-and-merge iteration converges to the maximal paths of that graph; pointer
 // jumping computes (head, rank) for every node in O(log n) rounds instead.
+#include <stdlib.h>
+#include <string.h>
+
 #include "rfx_internal.h"
 #include "rfx_scan.cuh"
 
 namespace rfx {
 
+// The index is local to minimiser bins: a row lives in the hash region of the bin its canonical minimiser hashes to
+// (regions are back to back in ht[], 4 * rows + 2 slots each).  A neighbour shares k-1 bases with the node that asks
+// for it, so its minimiser -- hence its region -- is almost always the node's own: the probes of the fork filters and
+// of the link pass stay inside a few hundred bytes that the neighbouring threads (rows come out of the counting
+// kernel grouped by bin) have just touched, instead of landing anywhere in a table of hundreds of megabytes.  The
+// asking node computes the m-mer hashes of its own k-mer once; a candidate's minimiser is then the minimum over the
+// shared (k-1)-mer plus one new m-mer.  (The same bin -> owner map is what lets a sharded run route a probe.)
 template <class KT> struct Graph {
     const KT* keys;
     const uint32_t* counts;
     uint64_t n_rows;
     uint32_t* ht;
-    uint64_t ht_mask;
-    int k;
+    const uint64_t* hoff;  // [g_bins + 1] first slot of every bin's region
+    uint32_t g_bins;       // 1: the whole table is one region of cap0 slots (tables that fit L2)
+    uint32_t cap0;
+    int k, m;
 
-    __device__ __forceinline__ uint32_t lookup(KT canon) const {
-        uint64_t slot = key_hash(canon) & ht_mask;
+    __device__ __forceinline__ uint32_t bin_of(uint32_t hmin) const { return (uint32_t)(((uint64_t)fmix32(hmin ^ 0x7f4a7c15u) * g_bins) >> 32); }
+    // hash of the canonical form of an m-mer given right aligned
+    __device__ __forceinline__ uint32_t mm_hash(uint32_t mm) const {
+        uint32_t r = brev32(mm);
+        r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+        r = (~r) >> (32 - 2 * m);
+        return mmer_hash(mm < r ? mm : r);
+    }
+    // minima of the m-mer hashes inside the first / the last k-1 bases of X
+    __device__ __forceinline__ void minima(KT X, uint32_t& pre_min, uint32_t& suf_min) const {
+        const uint32_t mmask = (m >= 16) ? 0xffffffffu : ((1u << (2 * m)) - 1u);
+        const int mtop = 2 * (m - 1), w = k - m + 1;
+        KT Y = X << (8 * (int)sizeof(KT) - 2 * k);  // first base in the top two bits
+        uint32_t mf = 0, mr = 0;
+        pre_min = 0xffffffffu; suf_min = 0xffffffffu;
+        for (int t = 0; t < k; t++) {
+            const uint32_t v = (uint32_t)(Y >> (8 * (int)sizeof(KT) - 2)) & 3u;
+            Y <<= 2;
+            mf = ((mf << 2) | v) & mmask;
+            mr = (mr >> 2) | ((v ^ 3u) << mtop);
+            if (t >= m - 1) {
+                const int j = t - m + 1;
+                const uint32_t h = mmer_hash(mf < mr ? mf : mr);
+                if (j <= w - 2) pre_min = h < pre_min ? h : pre_min;
+                if (j >= 1) suf_min = h < suf_min ? h : suf_min;
+            }
+        }
+    }
+    // hash of the last m-mer of (S + b) / the first m-mer of (a + S), S a right-aligned (k-1)-mer
+    __device__ __forceinline__ uint32_t last_mm(KT S, uint32_t b) const {
+        const uint32_t low = (m >= 17) ? 0u : ((uint32_t)S & ((m >= 16) ? 0x3fffffffu : ((1u << (2 * (m - 1))) - 1u)));
+        return mm_hash((low << 2) | b);
+    }
+    __device__ __forceinline__ uint32_t first_mm(KT S, uint32_t a) const {
+        const uint32_t top = (uint32_t)(S >> (2 * (k - 1 - (m - 1)))) & ((1u << (2 * (m - 1))) - 1u);
+        return mm_hash((a << (2 * (m - 1))) | top);
+    }
+    __device__ __forceinline__ uint32_t lookup(KT canon, uint32_t hmin) const {
+        uint64_t lo = 0;
+        uint32_t cap = cap0;
+        if (g_bins > 1) {
+            const uint32_t b = bin_of(hmin);
+            lo = hoff[b];
+            cap = (uint32_t)(hoff[b + 1] - lo);
+        }
+        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(key_hash(canon) >> 20) * cap) >> 32);
         while (true) {
-            const uint32_t v = ht[slot];
+            const uint32_t v = ht[lo + slot];
             if (v == NONE32) return NONE32;
             if (keys[v] == canon) return v;
-            slot = (slot + 1) & ht_mask;
+            slot = slot + 1 == cap ? 0u : slot + 1;
         }
     }
     __device__ __forceinline__ KT oriented(uint32_t oid) const {
         const KT key = keys[oid >> 1];
         return (oid & 1u) ? revcomp(key, k) : key;
     }
-    // oriented id of the oriented k-mer Z, NONE32 if its canonical form is not in the table
-    __device__ __forceinline__ uint32_t find(KT Z, uint32_t* cnt) const {
+    // oriented id of the oriented k-mer Z (whose minimiser hash is hmin), NONE32 if its canonical form is not in the table
+    __device__ __forceinline__ uint32_t find(KT Z, uint32_t hmin, uint32_t* cnt) const {
         const KT zc = revcomp(Z, k);
         const bool fwd = !(zc < Z);
-        const uint32_t r = lookup(fwd ? Z : zc);
+        const uint32_t r = lookup(fwd ? Z : zc, hmin);
         if (r == NONE32) return NONE32;
         *cnt = counts[r];
         return 2u * r + (fwd ? 0u : 1u);
     }
 };
 
-template <class KT> __global__ void ht_build_kernel(Graph<KT> G) {
+// index build: bin of every row + rows per bin, region offsets by scan, insertion
+template <class KT> __global__ void row_bin_kernel(Graph<KT> G, uint32_t* __restrict__ row_bin, uint32_t* __restrict__ bin_rows) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G.n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t slot = key_hash(G.keys[r]) & G.ht_mask;
-        while (atomicCAS(&G.ht[slot], NONE32, (uint32_t)r) != NONE32) slot = (slot + 1) & G.ht_mask;
+        uint32_t a, b;
+        G.minima(G.keys[r], a, b);
+        // minimiser of the whole k-mer: the first m-mer is in the prefix part, the last one in the suffix part
+        const uint32_t bin = G.bin_of(a < b ? a : b);
+        row_bin[r] = bin;
+        atomicAdd(&bin_rows[bin], 1u);
+    }
+}
+struct RegionIn {
+    const uint32_t* bin_rows;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return 4ull * bin_rows[i] + 2ull; }
+};
+struct RegionOut {
+    uint64_t* hoff;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t excl, uint64_t) const { hoff[i] = excl; }
+};
+__global__ void set_last_region_kernel(uint64_t* hoff, uint64_t g_bins, const uint64_t* total) { hoff[g_bins] = *total; }
+
+template <class KT> __global__ void ht_build_kernel(Graph<KT> G, const uint32_t* __restrict__ row_bin) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < G.n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = 0;
+        uint32_t cap = G.cap0;
+        if (G.g_bins > 1) {
+            const uint32_t b = row_bin[r];
+            lo = G.hoff[b];
+            cap = (uint32_t)(G.hoff[b + 1] - lo);
+        }
+        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(key_hash(G.keys[r]) >> 20) * cap) >> 32);
+        while (atomicCAS(&G.ht[lo + slot], NONE32, (uint32_t)r) != NONE32) slot = slot + 1 == cap ? 0u : slot + 1;
     }
 }
 
@@ -77,6 +161,8 @@ __global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ al
         const KT X = (oid & 1u) ? rc : key;
         const KT prefix = X >> 2;
         const uint32_t myb = (uint32_t)X & 3u;
+        uint32_t pre_min = 0, suf_min = 0;
+        if (G.g_bins > 1) G.minima(X, pre_min, suf_min);
         uint32_t cnt[4];
         bool dup[4];
 #pragma unroll
@@ -85,7 +171,8 @@ __global__ void right_filter_kernel(Graph<KT> G, int E, uint8_t* __restrict__ al
             else {
                 const KT Z = (prefix << 2) | (KT)b;
                 const KT zc = revcomp(Z, G.k);
-                const uint32_t r = G.lookup(zc < Z ? zc : Z);
+                const uint32_t hl = G.g_bins > 1 ? G.last_mm(prefix, b) : 0u;
+                const uint32_t r = G.lookup(zc < Z ? zc : Z, hl < pre_min ? hl : pre_min);
                 cnt[b] = r == NONE32 ? 0u : G.counts[r];
                 dup[b] = (Z == zc);
             }
@@ -107,13 +194,16 @@ __global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* 
         const KT X = G.oriented((uint32_t)oid);
         const KT suffix = X & sufmask;
         const uint32_t mya = (uint32_t)(X >> top) & 3u;
+        uint32_t pre_min = 0, suf_min = 0;
+        if (G.g_bins > 1) G.minima(X, pre_min, suf_min);
         uint32_t cnt[4];
 #pragma unroll
         for (uint32_t a = 0; a < 4; a++) {
             if (a == mya) cnt[a] = G.counts[oid >> 1];
             else {
                 uint32_t cz = 0;
-                const uint32_t oz = G.find(((KT)a << top) | suffix, &cz);
+                const uint32_t hf = G.g_bins > 1 ? G.first_mm(suffix, a) : 0u;
+                const uint32_t oz = G.find(((KT)a << top) | suffix, hf < suf_min ? hf : suf_min, &cz);
                 cnt[a] = (oz != NONE32 && (alive[oz] & 1)) ? cz : 0u;
             }
         }
@@ -134,12 +224,15 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
         if (!(alive[oid] & 2)) continue;
         const KT X = G.oriented((uint32_t)oid);
         const KT suffix = X & sufmask;
+        uint32_t pre_min = 0, suf_min = 0;
+        if (G.g_bins > 1) G.minima(X, pre_min, suf_min);
         uint32_t next = NONE32;
         int n_cand = 0;
 #pragma unroll
         for (uint32_t b = 0; b < 4; b++) {
             uint32_t cz;
-            const uint32_t oy = G.find((suffix << 2) | (KT)b, &cz);
+            const uint32_t hl = G.g_bins > 1 ? G.last_mm(suffix, b) : 0u;
+            const uint32_t oy = G.find((suffix << 2) | (KT)b, hl < suf_min ? hl : suf_min, &cz);
             if (oy != NONE32 && (alive[oy] & 2)) { next = oy; n_cand++; }
         }
         if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
@@ -163,7 +256,8 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
 #pragma unroll
             for (uint32_t a = 0; a < 4; a++) {
                 uint32_t cz;
-                const uint32_t oz = G.find(((KT)a << top) | prefix, &cz);
+                const uint32_t hf = G.g_bins > 1 ? G.first_mm(prefix, a) : 0u;
+                const uint32_t oz = G.find(((KT)a << top) | prefix, hf < pre_min ? hf : pre_min, &cz);
                 if (oz != NONE32 && (alive[oz] & 2)) { prev = oz; n_prev++; }
             }
             if (n_prev > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 2ull); continue; }
@@ -366,6 +460,51 @@ static unsigned grid_n(uint64_t n) {
     return (unsigned)(g > 148u * 16u ? 148u * 16u : g);
 }
 
+template <class KT> static Graph<KT> make_graph(Ctx* c) {
+    return Graph<KT>{c->keys.as<KT>(), c->counts.as<uint32_t>(), c->n_rows, c->ht.as<uint32_t>(), c->g_hoff.as<uint64_t>(), c->g_bins, c->g_bins > 1 ? 0u : (uint32_t)c->ht_cap, c->k, c->g_m};
+}
+
+// builds the bin-local index over the whole table (asynchronous on the context's stream)
+template <class KT> static int build_index(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const uint64_t n_rows = c->n_rows;
+    // a table that fits L2 (keys + counts + index, about 20 B per row of the 126 MB) is served fastest by ONE region:
+    // the minimiser arithmetic only pays once probes would otherwise go to HBM
+    uint64_t gb = n_rows / 32;
+    if (gb < 64) gb = 64;
+    if (gb > (1ull << 26)) gb = 1ull << 26;
+    const char* force = getenv("RFX_GRAPH_INDEX");  // "local" / "global": tests exercise both on small inputs
+    const bool local = force ? !strcmp(force, "local") : n_rows > 6000000ull;
+    if (!local) gb = 1;
+    c->g_bins = (uint32_t)gb;
+    int m = gb > 65536 ? 15 : 11;  // many more minimiser values than bins (as in rfx_partition.cu: set_minimizer)
+    if (m > c->k - 1) m = c->k - 1;
+    c->g_m = m;
+    RFX_TRY(devbuf_reserve(c, c->g_rowbin, (n_rows + 1) * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->g_binrows, gb * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, c->g_hoff, (gb + 1) * sizeof(uint64_t)));
+    const uint64_t slots = 4 * n_rows + 2 * gb;  // load factor <= 1/4 in every region: most probes are for absent neighbours
+    RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
+    c->ht_cap = slots;
+    RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
+    Graph<KT> G = make_graph<KT>(c);
+    if (local) {
+        RFX_CUDA(c, cudaMemsetAsync(c->g_binrows.p, 0, gb * sizeof(uint32_t), st));
+        if (n_rows) row_bin_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G, c->g_rowbin.as<uint32_t>(), c->g_binrows.as<uint32_t>());
+        ScanPlan<uint64_t> plan;
+        RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(gb) * sizeof(uint64_t)));
+        plan.bind(gb, c->scan_ws.as<uint64_t>());
+        RegionIn in{c->g_binrows.as<uint32_t>()};
+        scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
+        scan_apply(plan, in, RegionOut{c->g_hoff.as<uint64_t>()}, OpAddU64{}, (uint64_t)0, st);
+        set_last_region_kernel<<<1, 1, 0, st>>>(c->g_hoff.as<uint64_t>(), gb, plan.total);
+        c->launches += 2 + 2 * plan.levels;
+    }
+    if (n_rows) ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G, c->g_rowbin.as<uint32_t>());
+    c->launches++;
+    return RFX_OK;
+}
+
 template <class KT> static int graph_impl(Ctx* c) {
     cudaStream_t st = c->stream;
     const uint64_t n_rows = c->n_rows, n = 2 * n_rows;
@@ -383,10 +522,6 @@ template <class KT> static int graph_impl(Ctx* c) {
 
     // ---- K5 ----
     stage_begin(c);
-    uint64_t ht_cap = 1024;
-    while (ht_cap < 2 * n_rows) ht_cap <<= 1;
-    c->ht_cap = ht_cap;
-    RFX_TRY(devbuf_reserve(c, c->ht, ht_cap * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->rflag, n * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->lflag, n * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->alive, n));
@@ -404,8 +539,8 @@ template <class KT> static int graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, open_next, n * sizeof(uint32_t)));
     int rc = RFX_OK;
     do {
-        Graph<KT> G{c->keys.as<KT>(), c->counts.as<uint32_t>(), n_rows, c->ht.as<uint32_t>(), ht_cap - 1, c->k};
-        cudaMemsetAsync(c->ht.p, 0xff, ht_cap * sizeof(uint32_t), st);
+        if ((rc = build_index<KT>(c)) != RFX_OK) break;
+        Graph<KT> G = make_graph<KT>(c);
         cudaMemsetAsync(c->succ.p, 0xff, n * sizeof(uint32_t), st);
         cudaMemsetAsync(c->pred.p, 0xff, n * sizeof(uint32_t), st);
         cudaMemsetAsync(open_next.p, 0xff, n * sizeof(uint32_t), st);
@@ -417,11 +552,10 @@ template <class KT> static int graph_impl(Ctx* c) {
         int32_t* rflag = c->rflag.as<int32_t>();
         uint32_t* succ = c->succ.as<uint32_t>();
         uint32_t* pred = c->pred.as<uint32_t>();
-        ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G);
         right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, rflag, 0, n);
         left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, lflag, 0, n);
         link_kernel<KT, false><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, open_next.as<uint32_t>(), dstat, 0, n);
-        c->launches += 4;
+        c->launches += 3;
         cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "graph kernels failed: %s", cudaGetErrorString(e)); break; }
@@ -705,9 +839,7 @@ __global__ void gs_budget_kernel(uint64_t lo, uint64_t hi, const uint32_t* __res
     }
 }
 
-template <class KT> static Graph<KT> gs_graph(Ctx* c) {
-    return Graph<KT>{c->keys.as<KT>(), c->counts.as<uint32_t>(), c->n_rows, c->ht.as<uint32_t>(), c->ht_cap - 1, c->k};
-}
+template <class KT> static Graph<KT> gs_graph(Ctx* c) { return make_graph<KT>(c); }
 static int gs_sync(Ctx* c, const char* what) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
@@ -720,10 +852,6 @@ template <class KT> static int gs_begin_impl(Ctx* c) {
     const uint64_t n_rows = c->n_rows, n = 2 * n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi;
     if (n >= 0xffffffffull) return ctx_fail(c, RFX_E_CAPACITY, "more than 2^31 rows: oriented ids do not fit 32 bits");
     stage_begin(c);
-    uint64_t ht_cap = 1024;
-    while (ht_cap < 2 * n_rows) ht_cap <<= 1;
-    c->ht_cap = ht_cap;
-    RFX_TRY(devbuf_reserve(c, c->ht, ht_cap * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->rflag, (n + 1) * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->lflag, (n + 1) * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->alive, n + 16));
@@ -740,10 +868,9 @@ template <class KT> static int gs_begin_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->gs_next, (own + 1) * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->gs_len, (own + 1) * sizeof(uint32_t)));
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, ht_cap * sizeof(uint32_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->alive.p, 0, n + 16, st));
+    RFX_TRY(build_index<KT>(c));
     Graph<KT> G = gs_graph<KT>(c);
-    if (n_rows) ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G);
     if (own) right_filter_kernel<KT><<<grid_n(own), 256, 0, st>>>(G, c->prm.min_error_coverage, c->alive.as<uint8_t>(), c->rflag.as<int32_t>(), lo, hi);
     c->launches += 2;
     RFX_TRY(gs_sync(c, "sharded right filter"));

@@ -103,6 +103,9 @@ struct Ctx {
     // ---- de Bruijn graph over oriented k-mers (id = 2*row + strand) ----
     DevBuf ht;          // u32[ht_cap] row index or 0xffffffff
     uint64_t ht_cap = 0;
+    DevBuf g_rowbin, g_binrows, g_hoff;  // bin-local index: bin of every row, rows per bin, region offsets
+    uint32_t g_bins = 0;
+    int g_m = 11;
     DevBuf rflag, lflag;  // i32[2*n_rows]
     DevBuf alive;         // u8[2*n_rows]  bit0: survives right filter, bit1: survives both
     DevBuf succ, pred;    // u32[2*n_rows]

@@ -306,7 +306,19 @@ def test_assembly_matches_oracle(R, orc, k, cover, E, err):
     assert st["n_contigs"] >= 2
 
 
-def test_cycles_and_tiny_graphs(R, orc):
+@pytest.mark.parametrize("k,cover,E,err", [(31, 2, 8, 0.01), (61, 2, 8, 0.005), (24, 1, 8, 0.01), (5, 1, 8, 0.0), (12, 2, 0, 0.01), (33, 2, 8, 0.0)])
+def test_assembly_with_the_bin_local_index(R, orc, monkeypatch, k, cover, E, err):
+    """Tables beyond the L2 use minimiser-bin-local index regions; forced here on small inputs (RFX_GRAPH_INDEX=local)."""
+    from reflexiv_b200 import synth
+    monkeypatch.setenv("RFX_GRAPH_INDEX", "local")
+    g = synth.genome(30_000, 200 + k)
+    g[12000:12800] = g[3000:3800]
+    g[20000:20040] = np.frombuffer(b"AT" * 20, np.uint8)
+    txt = synth.fastq(g, 6000, read_len=150, frag_len=400, error_rate=err, seed_reads=7, seed_errors=8)
+    _check_assembly(R, orc, txt, k, cover, E, min_contig=100)
+
+
+def test_cycles_and_tiny_graphs(R, orc, monkeypatch):
     def fq(seqs):
         return "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
     rng = np.random.default_rng(3)
@@ -316,6 +328,10 @@ def test_cycles_and_tiny_graphs(R, orc):
     _check_assembly(R, orc, fq(["A" * 100] * 3), 31, 2, min_contig=10)       # homopolymer: 1-cycle
     _check_assembly(R, orc, fq(["ACGT" * 30] * 3), 16, 2, min_contig=10)     # period-4 cycle, even k, palindromes
     _check_assembly(R, orc, fq([circ[:33]] * 2), 31, 2, min_contig=10)       # three k-mers
+    monkeypatch.setenv("RFX_GRAPH_INDEX", "local")
+    _check_assembly(R, orc, fq(reads), 31, 2, min_contig=50)
+    _check_assembly(R, orc, fq(["A" * 100] * 3), 31, 2, min_contig=10)
+    _check_assembly(R, orc, fq(["ACGT" * 30] * 3), 16, 2, min_contig=10)
 
 
 def test_load_counts_seam(R, orc, example_text):
