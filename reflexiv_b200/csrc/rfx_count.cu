@@ -811,7 +811,11 @@ int stage_count(Ctx* c) {
         const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob: force a geometry
         std::string vs = variant ? variant : "";
         if (!c->wide) {
-            if (vs.empty()) {
+            if (vs.empty() && c->count_geometry && c->count_geometry_bins == c->n_bins) {
+                // same context, same bin count as the run the pilot looked at (a driver pushing batch after batch of one
+                // data set): keep its choice; a run that splits more than 1 % of its bins drops it again (below)
+                vs = c->count_geometry == 1 ? "small" : "large";
+            } else if (vs.empty()) {
                 // Pilot: count ~300 evenly spaced bins with the large table, write nothing, and look at how many distinct
                 // k-mers a bin holds.  Clean high-coverage reads (tens per bin) run fastest on the small table at 3 CTAs / SM;
                 // noisy reads (every fourth instance a singleton) need the large one or most bins would be split.
@@ -828,6 +832,8 @@ int stage_count(Ctx* c) {
                 c->launches++;
                 const uint64_t per_bin = ph[DS_DISTINCT] / P.n_tickets;
                 vs = (per_bin <= 600 && ph[DS_SPLITS] == 0) ? "small" : "large";
+                c->count_geometry = vs == "small" ? 1 : 2;
+                c->count_geometry_bins = c->n_bins;
             }
             if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
             else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
@@ -863,6 +869,7 @@ int stage_count(Ctx* c) {
     c->n_rows = h[DS_OUT_CURSOR];
     c->n_distinct = h[DS_DISTINCT];
     c->n_bin_splits = h[DS_SPLITS];
+    if (c->n_bin_splits * 100 > c->n_bins) c->count_geometry = 0;  // the remembered geometry no longer fits the data: pilot again next time
     if (c->n_instances == 0) c->n_instances = h[DS_INSTANCES];
     else if (h[DS_INSTANCES] != c->n_instances)
         return ctx_fail(c, RFX_E_STATE, "internal: counted %llu k-mer instances, extracted %llu", (unsigned long long)h[DS_INSTANCES],

@@ -98,6 +98,8 @@ struct Ctx {
     DevBuf counts;      // u32[table_cap]
     DevBuf dstat;       // u64[16] device-side counters
     uint64_t table_cap = 0, n_rows = 0, n_distinct = 0, n_bin_splits = 0;
+    int count_geometry = 0;           // 0: unknown (run the pilot), 1: small table, 2: large table -- survives rfx_reset
+    uint32_t count_geometry_bins = 0; // bin count of the run the pilot looked at
     bool have_counts = false;
 
     // ---- de Bruijn graph over oriented k-mers (id = 2*row + strand) ----
