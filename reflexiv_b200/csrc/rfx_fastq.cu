@@ -122,15 +122,23 @@ struct LineFnIn {
     const uint8_t* line_at;  // written next to line_start by the newline pass: no random text access here
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return line_at[i] ? FN_AT : FN_OTHER; }
 };
+// Per line: NOT_A_READ, or the effective length of the read (after clipping and the minimum-length rule).  Written once
+// by the filter pass, so the two passes of the read-table scan load 4 coalesced bytes per line instead of chasing
+// line_start[] into the text (the '\r' check) twice.
+constexpr uint32_t NOT_A_READ = 0xffffffffu;
+
 struct LineFnOut {
     uint64_t n_lines;  // lines known to exist from the start of this chunk on (the chunk's own, +2 if more text follows)
-    uint8_t* seq_flag;
+    uint32_t* seq_eff;
     const unsigned long long* state_in;  // lineMark at the start of the chunk
+    Lines L;
+    int k, fc, ec;
     __device__ __forceinline__ void operator()(uint64_t i, uint32_t excl, uint32_t fn) const {
         const uint32_t state_before = (excl >> (3u * (uint32_t)*state_in)) & 7u;  // prefix function applied to the carried lineMark
         // the sequence line is the one that moves lineMark 1 -> 2; the unit is emitted only when the
         // two following lines exist (lineMark 3 -> 4)
-        seq_flag[i] = (state_before == 1u && fn == FN_OTHER && i + 2 < n_lines) ? 1 : 0;
+        const bool is_read = state_before == 1u && fn == FN_OTHER && i + 2 < n_lines;
+        seq_eff[i] = is_read ? effective_read_len((int64_t)L.len(i), k, fc, ec) : NOT_A_READ;
     }
 };
 
@@ -140,17 +148,15 @@ __global__ void fq_state_update_kernel(const uint32_t* total_fn, unsigned long l
 
 __device__ __forceinline__ bool is_atcgn(uint8_t a) { return a == 'A' || a == 'T' || a == 'C' || a == 'G' || a == 'N'; }
 
-__global__ void flag_lines_kernel(Lines L, int mode, uint8_t* seq_flag) {
+__global__ void flag_lines_kernel(Lines L, int mode, uint32_t* seq_eff, int k, int fc, int ec) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint8_t f = 1;
+        bool f = true;
+        const uint64_t l = L.len(i);
         if (mode == RFX_FASTQ_COUNTER) {  // ReflexivDataFrameCounter.java:247-266
-            const uint64_t l = L.len(i);
             const uint8_t* s = L.text + L.start[i];
-            f = (l > 20 && s[0] != '@' && s[0] != '+' && is_atcgn(s[0]) && is_atcgn(s[4]) && is_atcgn(s[9]) &&
-                 is_atcgn(s[14]) && is_atcgn(s[19]))
-                    ? 1 : 0;
+            f = l > 20 && s[0] != '@' && s[0] != '+' && is_atcgn(s[0]) && is_atcgn(s[4]) && is_atcgn(s[9]) && is_atcgn(s[14]) && is_atcgn(s[19]);
         }
-        seq_flag[i] = f;
+        seq_eff[i] = f ? effective_read_len((int64_t)l, k, fc, ec) : NOT_A_READ;
     }
 }
 
@@ -178,11 +184,16 @@ struct OpAddU64x4 {
 
 struct ReadIn {
     Lines L;
-    const uint8_t* seq_flag;  // nullptr: every line is a read
+    const uint32_t* seq_eff;  // nullptr: every line is a read, lengths from line_start[]
     int k, fc, ec;
     __device__ __forceinline__ U64x4 operator()(uint64_t i) const {
-        if (seq_flag && !seq_flag[i]) return U64x4{0, 0, 0, 0};
-        const uint32_t e = effective_read_len((int64_t)L.len(i), k, fc, ec);
+        uint32_t e;
+        if (seq_eff) {
+            e = seq_eff[i];
+            if (e == NOT_A_READ) return U64x4{0, 0, 0, 0};
+        } else {
+            e = effective_read_len((int64_t)L.len(i), k, fc, ec);
+        }
         return U64x4{1, (uint64_t)((e + 31u) >> 5), e, e ? (uint64_t)(e - (uint32_t)k + 1u) : 0u};
     }
 };
@@ -263,7 +274,7 @@ static unsigned grid_for(uint64_t n, int block, unsigned cap = 148 * 16) {
 }
 
 // Builds the read table for `n_lines` lines and appends the packed reads to the context.
-static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint8_t* seq_flag) {
+static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* seq_flag) {
     cudaStream_t st = c->stream;
     ScanPlan<U64x4> plan;
     RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<U64x4>::workspace_elems(L.n_lines) * sizeof(U64x4)));
@@ -338,18 +349,19 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
 
     // 2. which lines are reads
     Lines L{d_text, ls, n_lines, 1u};
-    RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines));
-    const uint8_t* flags = c->seq_flag.as<uint8_t>();
+    RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
+    const uint32_t* flags = c->seq_flag.as<uint32_t>();
     if (c->prm.fastq_mode == RFX_FASTQ_RUN) {
         ScanPlan<uint32_t> fs;
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
         fs.bind(n_lines, c->scan_ws.as<uint32_t>());
         scan_prepare(fs, LineFnIn{lat}, OpCompose{}, FN_IDENT, st);
-        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines + (more_follows ? 2u : 0u), c->seq_flag.as<uint8_t>(), fq_state}, OpCompose{}, FN_IDENT, st);
+        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines + (more_follows ? 2u : 0u), c->seq_flag.as<uint32_t>(), fq_state, L, c->k, c->prm.front_clip, c->prm.end_clip},
+                   OpCompose{}, FN_IDENT, st);
         fq_state_update_kernel<<<1, 1, 0, st>>>(fs.total, fq_state);
         c->launches += 2 * fs.levels + 1;
     } else if (c->prm.fastq_mode == RFX_FASTQ_COUNTER) {
-        flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint8_t>());
+        flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint32_t>(), c->k, c->prm.front_clip, c->prm.end_clip);
         c->launches += 1;
     } else {
         flags = nullptr;
