@@ -5,11 +5,10 @@
 //
 // One CTA owns one minimiser bin at a time (bins are handed out by an atomic ticket, so a heavy bin never
 // holds up a static schedule).  Per bin:
-//   A1  every thread hashes its super-k-mer records whole into a shared-memory tag table: identical records
-//       -- the same genome window seen by many reads -- collapse into one entry with a multiplicity;
-//   A2  every thread checks that the entry it counted into really is its record (compared against the
-//       claimant's record, re-read from L1/L2); a record that lost a tag collision becomes an entry of its
-//       own, so the collapse is exact;
+//   A   every thread hashes its super-k-mer records whole into a shared-memory table whose slot word carries a
+//       21-bit tag and the index of the record that claimed the slot: a record that meets its own tag compares
+//       itself with the claimant's record (staged in shared memory) on the spot, so identical records -- the
+//       same genome window seen by many reads -- collapse exactly into one entry with a multiplicity;
 //   B   the distinct records are expanded: a warp takes 32 entries, prefix-sums their k-mer counts and walks
 //       the flattened (record, k-mer) space 32 k-mers per step -- shuffle binary search for the source record,
 //       record words fetched by shuffle, the k-mer cut straight out of the 2-bit stream, brev-based reverse
@@ -331,8 +330,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     uint32_t* cnts = tags + (WIDE ? CAP : 0);
     uint32_t* rtag = cnts + CAP;
     uint32_t* rmult = rtag + RCAP;
-    uint16_t* ridx = reinterpret_cast<uint16_t*>(rmult + RCAP);
-    uint16_t* ulist = ridx + RCAP;   // [CHUNK] entries of the chunk: slot (< RCAP) or RCAP + record index (a record that lost a tag collision)
+    uint16_t* ulist = reinterpret_cast<uint16_t*>(rmult + RCAP);  // [CHUNK] claimed slots of the chunk, in claim order
     uint16_t* klist = ulist + CHUNK; // [KMAX]
     __shared__ uint32_t s_distinct[2], s_nuniq[2], s_overflow, s_sp, s_npass, s_cursor, s_early;
     __shared__ uint32_t s_stack_val[CNT_STACK], s_stack_depth[CNT_STACK];
@@ -415,7 +413,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
 
     // ---------------- compute warps ----------------
     // Counters are double buffered by bin parity, so the common case -- one class, one staged chunk -- needs no barrier
-    // beyond the three that separate A1 | A2 | B | K4: thread 0 clears the other parity's counters right behind the
+    // beyond the ones that separate A | B | K4: thread 0 clears the other parity's counters right behind the
     // first barrier of a bin, when nobody can still be reading them.
     auto clear_all = [&]() {
         for (int i = tid; i < CAP; i += NT) { if (WIDE) tags[i] = 0u; else keys[i] = ~0ull; cnts[i] = 0u; }
@@ -434,60 +432,51 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
         uint32_t* const nuniq = &s_nuniq[par];
         const KmerTable<WIDE, CAP> T{keys, keys_lo, tags, cnts, klist, &s_distinct[par], &s_overflow, A.dstat + DS_OVF_WHY};
 
-        // A1 | A2 | B of one chunk of `cn` records sitting in `buf`; `after_first` runs on thread 0 behind the first barrier
+        // A | B of one chunk of `cn` records sitting in `buf` (`fast`: thread 0 also clears the other parity behind the first barrier)
         auto run_chunk = [&](uint32_t cn, uint32_t depth, uint32_t cval, bool fast) {
-            // ---- A1: collapse identical records ----
-            uint64_t v[PER_THREAD][RECW];
-            uint32_t myslot[PER_THREAD];
+            // ---- A: collapse identical records ----
+            // One 32-bit word per slot carries a 21-bit tag AND the chunk-local index of the record that claimed the
+            // slot, so a later record with the same tag compares itself with the claimant's record (in the staged
+            // buffer) on the spot: a proper hash insert with full-key compare, no confirmation pass.
+            constexpr uint32_t IDX_BITS = 11, IDX_MASK = (1u << IDX_BITS) - 1u;
+            static_assert(CHUNK <= (1 << IDX_BITS), "record index must fit the slot word");
 #pragma unroll
             for (int j = 0; j < PER_THREAD; j++) {
                 const uint32_t li = (uint32_t)j * NT + tid;  // chunk-local record index
-                myslot[j] = 0xffffffffu;
                 if (li < cn) {
+                    uint64_t v[RECW];
 #pragma unroll
                     for (int q = 0; q < RECW; q += 2) {
                         const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)li * RECW + q);
-                        v[j][q] = x.x; v[j][q + 1] = x.y;
+                        v[q] = x.x; v[q + 1] = x.y;
                     }
                     uint32_t h, tag;
-                    record_hash<RECW>(v[j], h, tag);
+                    record_hash<RECW>(v, h, tag);
+                    const uint32_t word = ((tag | (1u << IDX_BITS)) & ~IDX_MASK) | li;  // never 0
                     uint32_t slot = h & (RCAP - 1);
                     while (true) {  // at most CHUNK < RCAP entries: an empty slot always exists
                         uint32_t cur = rtag[slot];
                         if (cur == 0u) {
-                            cur = atomicCAS(&rtag[slot], 0u, tag);
-                            if (cur == 0u) { ridx[slot] = (uint16_t)li; ulist[atomicAdd(nuniq, 1u)] = (uint16_t)slot; break; }
+                            cur = atomicCAS(&rtag[slot], 0u, word);
+                            if (cur == 0u) { ulist[atomicAdd(nuniq, 1u)] = (uint16_t)slot; break; }
                         }
-                        if (cur == tag) break;
+                        if (((cur ^ word) & ~IDX_MASK) == 0u) {
+                            const uint64_t* o = buf + (size_t)(cur & IDX_MASK) * RECW;
+                            bool same = true;
+#pragma unroll
+                            for (int q = 0; q < RECW; q += 2) {
+                                const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(o + q);
+                                same = same && x.x == v[q] && x.y == v[q + 1];
+                            }
+                            if (same) break;
+                        }
                         slot = (slot + 1) & (RCAP - 1);
                     }
                     atomicAdd(&rmult[slot], 1u);
-                    myslot[j] = slot;
                 }
             }
             compute_barrier<NT>();
             if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_overflow = 0; }
-            // ---- A2: confirm against the claimant's record ----
-#pragma unroll
-            for (int j = 0; j < PER_THREAD; j++) {
-                if (myslot[j] != 0xffffffffu) {
-                    const uint32_t li = (uint32_t)j * NT + tid;
-                    const uint32_t ci = ridx[myslot[j]];
-                    if (ci != li) {
-                        bool same = true;
-#pragma unroll
-                        for (int q = 0; q < RECW; q += 2) {
-                            const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(buf + (size_t)ci * RECW + q);
-                            same = same && x.x == v[j][q] && x.y == v[j][q + 1];
-                        }
-                        if (!same) {
-                            atomicSub(&rmult[myslot[j]], 1u);
-                            ulist[atomicAdd(nuniq, 1u)] = (uint16_t)(RCAP + li);
-                        }
-                    }
-                }
-            }
-            compute_barrier<NT>();
             // ---- B: expand the distinct records, spread evenly over the warps ----
             const int n_uniq = (int)*nuniq;
 #ifdef RFX_DEBUG_COUNT
@@ -507,11 +496,9 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                     for (int q = 0; q < RECW; q++) w[q] = 0ull;
                     if (lane < per && u < n_uniq) {
                         const uint32_t e = ulist[u];
-                        uint32_t li;
-                        if (e < (uint32_t)RCAP) {
-                            mult = rmult[e]; li = ridx[e];
-                            if (last) { rtag[e] = 0u; rmult[e] = 0u; }  // the slot is this lane's alone: leave it clean
-                        } else { mult = 1u; li = e - RCAP; }
+                        mult = rmult[e];
+                        const uint32_t li = rtag[e] & ((1u << 11) - 1u);
+                        if (last) { rtag[e] = 0u; rmult[e] = 0u; }  // the slot is this lane's alone: leave it clean
                         if (mult) {
 #pragma unroll
                             for (int q = 0; q < RECW; q += 2) {
@@ -744,7 +731,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
 //   k <= 31: 2 x 768 x 16 B record stages + 4096 x 12 B k-mer table + lists + 1024-entry record-tag table = 89.5 KB -> 2
 //   k  > 31: 2 x 192 x 32 B record stages + 2048 x 24 B k-mer table + lists + 256-entry record-tag table  =  66 KB -> 3
 template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t launch_count(const CountArgs& A, cudaStream_t st) {
-    const size_t smem = (size_t)CNT_STAGES * (RCAP * 3 / 4) * (WIDE ? 32 : 16) + (size_t)CAP * (WIDE ? 24 : 12) + (size_t)RCAP * 10 +
+    const size_t smem = (size_t)CNT_STAGES * (RCAP * 3 / 4) * (WIDE ? 32 : 16) + (size_t)CAP * (WIDE ? 24 : 12) + (size_t)RCAP * 8 +
                         (size_t)(RCAP * 3 / 4) * 2 + (size_t)(CAP * 3 / 4) * 2;
     cudaError_t e = cudaFuncSetAttribute(count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
