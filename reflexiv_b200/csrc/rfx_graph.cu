@@ -41,6 +41,10 @@ template <class KT> struct Graph {
     uint32_t g_bins;       // 1: the whole table is one region of cap0 slots (tables that fit L2)
     uint32_t cap0;
     int k, m;
+    // presence bits (one hash, >= 16 bits per row): three of four probes ask for a k-mer that does not exist, and
+    // most of those are answered from this small array (16 MB at config 2) without touching the index or the keys
+    uint32_t* bloom;
+    uint64_t bloom_mask;  // number of bits - 1 (power of two), 0: no filter
 
     __device__ __forceinline__ uint32_t bin_of(uint32_t hmin) const { return (uint32_t)(((uint64_t)fmix32(hmin ^ 0x7f4a7c15u) * g_bins) >> 32); }
     // hash of the canonical form of an m-mer given right aligned
@@ -80,6 +84,11 @@ template <class KT> struct Graph {
         return mm_hash((a << (2 * (m - 1))) | top);
     }
     __device__ __forceinline__ uint32_t lookup(KT canon, uint32_t hmin) const {
+        const uint64_t kh = key_hash(canon);
+        if (bloom_mask) {
+            const uint64_t bit = (kh >> 13) & bloom_mask;
+            if (!((bloom[bit >> 5] >> (bit & 31u)) & 1u)) return NONE32;
+        }
         uint64_t lo = 0;
         uint32_t cap = cap0;
         if (g_bins > 1) {
@@ -87,7 +96,7 @@ template <class KT> struct Graph {
             lo = hoff[b];
             cap = (uint32_t)(hoff[b + 1] - lo);
         }
-        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(key_hash(canon) >> 20) * cap) >> 32);
+        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(kh >> 20) * cap) >> 32);
         while (true) {
             const uint32_t v = ht[lo + slot];
             if (v == NONE32) return NONE32;
@@ -140,7 +149,12 @@ template <class KT> __global__ void ht_build_kernel(Graph<KT> G, const uint32_t*
             lo = G.hoff[b];
             cap = (uint32_t)(G.hoff[b + 1] - lo);
         }
-        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(key_hash(G.keys[r]) >> 20) * cap) >> 32);
+        const uint64_t kh = key_hash(G.keys[r]);
+        if (G.bloom_mask) {
+            const uint64_t bit = (kh >> 13) & G.bloom_mask;
+            atomicOr(&G.bloom[bit >> 5], 1u << (bit & 31u));
+        }
+        uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(kh >> 20) * cap) >> 32);
         while (atomicCAS(&G.ht[lo + slot], NONE32, (uint32_t)r) != NONE32) slot = slot + 1 == cap ? 0u : slot + 1;
     }
 }
@@ -461,7 +475,8 @@ static unsigned grid_n(uint64_t n) {
 }
 
 template <class KT> static Graph<KT> make_graph(Ctx* c) {
-    return Graph<KT>{c->keys.as<KT>(), c->counts.as<uint32_t>(), c->n_rows, c->ht.as<uint32_t>(), c->g_hoff.as<uint64_t>(), c->g_bins, c->g_bins > 1 ? 0u : (uint32_t)c->ht_cap, c->k, c->g_m};
+    return Graph<KT>{c->keys.as<KT>(), c->counts.as<uint32_t>(), c->n_rows, c->ht.as<uint32_t>(), c->g_hoff.as<uint64_t>(), c->g_bins, c->g_bins > 1 ? 0u : (uint32_t)c->ht_cap, c->k, c->g_m,
+                     c->g_bloom.as<uint32_t>(), c->g_bloom_mask};
 }
 
 // builds the bin-local index over the whole table (asynchronous on the context's stream)
@@ -487,6 +502,14 @@ template <class KT> static int build_index(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
     c->ht_cap = slots;
     RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
+    // presence bits only where they stay (mostly) cache resident (<= 128 MB); beyond that the bin-local regions do the job
+    uint64_t bits = 1024;
+    while (bits < 16 * n_rows) bits <<= 1;
+    c->g_bloom_mask = bits <= (1024ull << 20) ? bits - 1 : 0;
+    if (c->g_bloom_mask) {
+        RFX_TRY(devbuf_reserve(c, c->g_bloom, bits / 8));
+        RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.p, 0, bits / 8, st));
+    }
     Graph<KT> G = make_graph<KT>(c);
     if (local) {
         RFX_CUDA(c, cudaMemsetAsync(c->g_binrows.p, 0, gb * sizeof(uint32_t), st));

@@ -105,7 +105,8 @@ struct Ctx {
     // ---- de Bruijn graph over oriented k-mers (id = 2*row + strand) ----
     DevBuf ht;          // u32[ht_cap] row index or 0xffffffff
     uint64_t ht_cap = 0;
-    DevBuf g_rowbin, g_binrows, g_hoff;  // bin-local index: bin of every row, rows per bin, region offsets
+    DevBuf g_rowbin, g_binrows, g_hoff, g_bloom;
+    uint64_t g_bloom_mask = 0;  // bin-local index: bin of every row, rows per bin, region offsets
     uint32_t g_bins = 0;
     int g_m = 11;
     DevBuf rflag, lflag;  // i32[2*n_rows]
