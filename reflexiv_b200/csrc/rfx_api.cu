@@ -199,7 +199,7 @@ const char* rfx_last_error(const rfx_ctx* c) { return c ? c->err.c_str() : g_cre
 int rfx_reset(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
-    c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0;
+    c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0; c->sp_active = false;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
     c->have_contigs = false;
     c->rx_bytes = 0; c->shard_id = -1; c->n_seg = 0;
@@ -210,7 +210,7 @@ int rfx_reset(rfx_ctx* c) {
 int rfx_push_fastq_device(rfx_ctx* c, const uint8_t* d_buf, size_t len) {
     if (!c || (!d_buf && len)) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->sp_active = false;
     return stage_parse_fastq(c, d_buf, len, true, false);
 }
 
@@ -246,6 +246,12 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     }
     cuts.push_back(len);
     const size_t n_chunks = cuts.size() - 1;
+    // With several chunks and nothing pushed before, the single-GPU partition follows the upload: bin geometry from the
+    // first chunk scaled to the whole text, every chunk's reads scanned while the next chunk is still on the bus.
+    // (A later rfx_partition -- sharded runs -- or another push simply discards that work.)
+    const char* sp_env = getenv("RFX_STREAM_PARTITION");
+    bool stream_part = n_chunks >= 2 && c->n_reads == 0 && !(sp_env && !strcmp(sp_env, "0"));
+    c->sp_active = false;
     RFX_CUDA(c, cudaMemsetAsync(d_text + len, 0, 128, c->copy_stream));
     RFX_CUDA(c, cudaMemcpyAsync(d_text, buf, cuts[1], cudaMemcpyHostToDevice, c->copy_stream));
     RFX_CUDA(c, cudaEventRecord(c->copy_done[0], c->copy_stream));
@@ -256,6 +262,14 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
         }
         RFX_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[i & 1], 0));
         RFX_TRY(stage_parse_fastq(c, d_text + cuts[i], cuts[i + 1] - cuts[i], i == 0, i + 1 < n_chunks));
+        if (stream_part) {
+            if (i == 0) {
+                if (c->n_reads == 0) { stream_part = false; continue; }
+                const double scale = 1.02 * (double)len / (double)cuts[1];
+                RFX_TRY(stage_stream_partition_begin(c, (uint64_t)((double)c->n_instances * scale) + 1, (uint64_t)((double)c->n_reads * scale) + 1));
+            }
+            RFX_TRY(stage_stream_partition_scan(c));
+        }
     }
     return RFX_OK;
 }
@@ -263,7 +277,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
 int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {
     if (!c || !offsets || (!bases && n_reads && offsets[n_reads])) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->sp_active = false;
     return stage_push_reads(c, bases, offsets, n_reads);
 }
 

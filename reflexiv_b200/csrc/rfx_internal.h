@@ -81,6 +81,11 @@ struct Ctx {
     // partitioned overflow segment in rx_records; slab_cap == 0: compact two-pass layout described by bin_off
     uint32_t slab_cap = 0;
     uint64_t n_ovf = 0;
+    // streamed slab partition (rfx_push_fastq): geometry fixed from the first chunk, reads scanned as they arrive
+    bool sp_active = false;
+    uint32_t sp_cap = 0;
+    uint64_t sp_ovf_cap = 0, sp_done = 0;
+    float sp_kernel_ms = 0;
     DevBuf ovf_rec, ovf_bin;
     uint32_t forced_bins = 0;  // total bin count imposed by the caller (sharded runs), 0 = choose
     // records received from other shards (rfx_begin_shard / rfx_load_records_device)
@@ -170,6 +175,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
 int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);
 int stage_partition(Ctx* c, int n_shards);
 int stage_partition_slab(Ctx* c);
+int stage_stream_partition_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads);
+int stage_stream_partition_scan(Ctx* c);
 int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);

@@ -509,8 +509,13 @@ static uint32_t choose_bins(Ctx* c, int n_shards) {
 }
 
 // pass 1 with either emitter: the register-resident scan for the default geometry, then (or instead) the general kernel
-template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, const Factory& F, unsigned grid) {
+template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, const Factory& F, uint64_t read_off, uint64_t n_reads) {
     cudaStream_t st = c->stream;
+    unsigned grid = (unsigned)((n_reads + PART_THREADS - 1) / PART_THREADS);
+    if (grid < 1) grid = 1;
+    if (grid > 148u * 64u) grid = 148u * 64u;
+    const uint32_t* rd_len = c->rd_len.as<uint32_t>() + read_off;
+    const uint64_t* rd_woff = c->rd_woff.as<uint64_t>() + read_off;
     const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring
     const size_t smem_scan = smem + (size_t)2 * SCAN_Q * PART_THREADS * sizeof(uint32_t);  // + the change queues
     const bool fixed = P.k == 31 && P.m == 11, fast15 = P.k == 31 && P.m == 15;
@@ -518,21 +523,21 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     if (fixed) {
         // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
-        bin_scan_fast_kernel<31, 11, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
-                                                                             c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
-        bin_scan_kernel<true, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
-                                                                              c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
+        bin_scan_fast_kernel<31, 11, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+                                                                             n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
+        bin_scan_kernel<true, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+                                                                              n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
         c->launches += 2;
     } else if (fast15) {
         // large inputs (more than 2^16 bins): same register-resident scan with 15-mers
-        bin_scan_fast_kernel<31, 15, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
-                                                                             c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
-        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
-                                                                               c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
+        bin_scan_fast_kernel<31, 15, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+                                                                             n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
+        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+                                                                               n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
         c->launches += 2;
     } else {
-        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>(),
-                                                                               c->n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 0);
+        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+                                                                               n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 0);
         c->launches++;
     }
     RFX_CUDA(c, cudaGetLastError());
@@ -560,47 +565,71 @@ __global__ void ovf_scatter_kernel(const uint64_t* __restrict__ ovf_rec, const u
     }
 }
 
-// returns RFX_OK with c->slab_cap == 0 when the overflow list did not suffice (caller falls back to the two-pass path)
-int stage_partition_slab(Ctx* c) {
+// The slab partition in three steps, so that the scan can follow the reads as they arrive (rfx_push_fastq uploads the
+// text in chunks: the reads of chunk i are scanned while chunk i + 1 is still crossing PCIe):
+//   slab_begin   bin geometry and slabs from an (estimated) instance / read count
+//   slab_scan    the minimiser scan over reads [off, off + n), records stored as they are cut
+//   slab_finish  totals, overflow segment; leaves c->have_records false when the overflow list did not suffice
+//                (caller falls back to the two-pass path)
+static int slab_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads) {
     cudaStream_t st = c->stream;
-    stage_begin(c);
     c->n_shards = 1;
-    c->n_bins = choose_bin_count(c, c->n_instances, 1);
+    c->n_bins = choose_bin_count(c, est_instances, 1);
     set_minimizer(c, c->n_bins);
-    BinParams P;
-    P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
+    const int w = c->k - c->m + 1;
     const size_t nb = c->n_bins;
     // expected records: one run per (w + 1) / 2 k-mers plus one cut per read; slabs hold twice the average bin
-    const uint64_t est = c->n_instances * 2 / (uint64_t)(P.w + 1) + c->n_reads + 1;
+    const uint64_t est = est_instances * 2 / (uint64_t)(w + 1) + est_reads + 1;
     uint64_t cap = ((c->wide ? 3 : 2) * est / nb + 8 + 3) & ~(uint64_t)3;  // k > 31: few minimiser loci per bin, uneven bins
     if (cap > 0x7fffffffull) cap = 0x7fffffffull;
-    uint64_t ovf_cap = est / (c->wide ? 3 : 8) + 4096;
+    const uint64_t ovf_cap = est / (c->wide ? 3 : 8) + 4096;
     RFX_TRY(devbuf_reserve(c, c->bin_cursor, nb * 4 * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->records, (nb * cap * c->recw + 2) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ovf_rec, (ovf_cap * c->recw + 2) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ovf_bin, ovf_cap * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->rd_runs, (size_t)(c->n_reads + 1) * sizeof(uint32_t)));
     RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, nb * 4 * sizeof(uint32_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_OVF_RECORDS, 0, sizeof(uint64_t), st));
+    c->sp_cap = (uint32_t)cap; c->sp_ovf_cap = ovf_cap; c->sp_done = 0; c->sp_kernel_ms = 0;
+    return RFX_OK;
+}
+
+static int slab_scan(Ctx* c, uint64_t read_off, uint64_t n) {
+    if (n == 0) return RFX_OK;
+    cudaStream_t st = c->stream;
+    BinParams P;
+    P.k = c->k; P.m = c->m; P.w = c->k - c->m + 1; P.n_bins = c->n_bins; P.max_nk = c->max_nk;
+    RFX_TRY(devbuf_reserve(c, c->rd_runs, (size_t)(n + 1) * sizeof(uint32_t)));
+    uint32_t* bin_cnt = c->bin_cursor.as<uint32_t>();
+    cudaEventRecord(c->evk[0], st);
+    if (c->recw == 2) {
+        SlabFactory<2> F{c->records.as<uint64_t>(), bin_cnt, c->sp_cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
+                         c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, c->sp_ovf_cap, c->k};
+        RFX_TRY(launch_scan(c, P, F, read_off, n));
+    } else {
+        SlabFactory<4> F{c->records.as<uint64_t>(), bin_cnt, c->sp_cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
+                         c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, c->sp_ovf_cap, c->k};
+        RFX_TRY(launch_scan(c, P, F, read_off, n));
+    }
+    cudaEventRecord(c->evk[1], st);
+    cudaError_t e = cudaEventSynchronize(c->evk[1]);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "slab scan failed: %s", cudaGetErrorString(e));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
+    c->sp_kernel_ms += ms;
+    c->sp_done = read_off + n;
+    return RFX_OK;
+}
+
+static int slab_finish(Ctx* c) {
+    cudaStream_t st = c->stream;
+    const size_t nb = c->n_bins;
+    const uint64_t cap = c->sp_cap;
     uint32_t* bin_cnt = c->bin_cursor.as<uint32_t>();
     uint32_t* ovf_cursor_bin = bin_cnt + nb;
-    unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
-    if (grid < 1) grid = 1;
-    if (grid > 148u * 64u) grid = 148u * 64u;
     uint64_t n_records = 0, n_ovf = 0;
-    c->ms_kernel[0] = c->ms_kernel[1] = 0;
+    c->ms_kernel[0] = c->sp_kernel_ms; c->ms_kernel[1] = 0;
+    c->slab_cap = 0;
     if (c->n_reads) {
-        cudaEventRecord(c->evk[0], st);
-        if (c->recw == 2) {
-            SlabFactory<2> F{c->records.as<uint64_t>(), bin_cnt, (uint32_t)cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
-                             c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, ovf_cap, c->k};
-            RFX_TRY(launch_scan(c, P, F, grid));
-        } else {
-            SlabFactory<4> F{c->records.as<uint64_t>(), bin_cnt, (uint32_t)cap, c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(),
-                             c->dstat.as<unsigned long long>() + DS_OVF_RECORDS, ovf_cap, c->k};
-            RFX_TRY(launch_scan(c, P, F, grid));
-        }
-        cudaEventRecord(c->evk[1], st);
         // total records (statistics) and the overflow count
         ScanPlan<uint64_t> plan;
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(c->n_bins) * sizeof(uint64_t)));
@@ -610,11 +639,7 @@ int stage_partition_slab(Ctx* c) {
         RFX_CUDA(c, cudaMemcpyAsync(&n_records, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         RFX_CUDA(c, cudaMemcpyAsync(&n_ovf, c->dstat.as<uint64_t>() + DS_OVF_RECORDS, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         RFX_CUDA(c, cudaStreamSynchronize(st));
-        if (n_ovf > ovf_cap) {  // a few very heavy bins: this input needs the exact layout
-            c->slab_cap = 0;
-            c->ms[1] += stage_end(c);
-            return RFX_OK;
-        }
+        if (n_ovf > c->sp_ovf_cap) return RFX_OK;  // a few very heavy bins (or a bad size estimate): this input needs the exact layout
         c->n_ovf = n_ovf;
         if (n_ovf) {
             // exact partition of the overflow list -> segment 1 of the counting kernel
@@ -628,22 +653,51 @@ int stage_partition_slab(Ctx* c) {
             if (c->recw == 2) ovf_scatter_kernel<2><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
             else ovf_scatter_kernel<4><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
             c->launches += 2 * plan.levels + 2;
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "slab partition failed: %s", cudaGetErrorString(e));
         }
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "slab partition failed: %s", cudaGetErrorString(e));
-        cudaEventElapsedTime(&c->ms_kernel[0], c->evk[0], c->evk[1]);
     }
     c->slab_cap = (uint32_t)cap;
     c->n_records = n_records;
     c->have_records = true;
-    c->ms[1] += stage_end(c);
     return RFX_OK;
+}
+
+// streamed use (rfx_push_fastq): sizes come from the first chunk, scaled to the whole text
+int stage_stream_partition_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads) {
+    stage_begin(c);
+    int rc = slab_begin(c, est_instances, est_reads);
+    c->sp_active = rc == RFX_OK;
+    c->ms[1] += stage_end(c);
+    return rc;
+}
+int stage_stream_partition_scan(Ctx* c) {
+    if (!c->sp_active) return RFX_OK;
+    stage_begin(c);
+    int rc = slab_scan(c, c->sp_done, c->n_reads - c->sp_done);
+    c->ms[1] += stage_end(c);
+    return rc;
+}
+
+// One GPU, records stay local.  Uses what the streamed scans already did when they cover every read.
+int stage_partition_slab(Ctx* c) {
+    stage_begin(c);
+    int rc = RFX_OK;
+    if (!(c->sp_active && c->sp_done == c->n_reads && c->n_reads)) {
+        rc = slab_begin(c, c->n_instances, c->n_reads);
+        if (rc == RFX_OK) rc = slab_scan(c, 0, c->n_reads);
+    }
+    c->sp_active = false;
+    if (rc == RFX_OK) rc = slab_finish(c);
+    c->ms[1] += stage_end(c);
+    return rc;
 }
 
 int stage_partition(Ctx* c, int n_shards) {
     cudaStream_t st = c->stream;
     if (n_shards < 1) return ctx_fail(c, RFX_E_INVALID, "n_shards must be >= 1");
     stage_begin(c);
+    c->sp_active = false;  // whatever a streamed slab scan did is not used by the compact layout
     c->n_shards = n_shards;
     c->n_bins = choose_bins(c, n_shards);
     if (c->n_bins % (uint32_t)n_shards) return ctx_fail(c, RFX_E_INVALID, "n_bins_total %u is not a multiple of n_shards %d", c->n_bins, n_shards);
@@ -676,7 +730,7 @@ int stage_partition(Ctx* c, int n_shards) {
     c->slab_cap = 0;
     if (c->n_reads) {
         cudaEventRecord(c->evk[0], st);
-        RFX_TRY(launch_scan(c, P, DescFactory{desc, pos, stride, (uint32_t)slots, bin_cnt, spill_cnt}, grid));
+        RFX_TRY(launch_scan(c, P, DescFactory{desc, pos, stride, (uint32_t)slots, bin_cnt, spill_cnt}, 0, c->n_reads));
         cudaEventRecord(c->evk[1], st);
     }
     // exclusive scan of the per-bin record counts -> bin offsets
