@@ -169,15 +169,6 @@ template <bool WIDE, int CAP> struct KmerTable {
             if (cur == tag && keys[slot] == hi && keys_lo[slot] == lo) { atomicAdd(&cnts[slot], mult); return; }
             slot = (slot + 1) & (CAP - 1);
         }
-#ifdef RFX_DEBUG_COUNT
-        if (!*overflow) {
-            int found = -1;
-            for (int i = 0; i < CAP; i++) if (tags[i] && keys[i] == hi && keys_lo[i] == lo) found = i;
-            int chain = 0; uint32_t s2 = h & (CAP - 1);
-            while (tags[s2] && chain < CAP) { s2 = (s2 + 1) & (CAP - 1); chain++; }
-            printf("MISS key %016llx:%016llx tag %08x start %u chain %d found_at %d tag_there %08x nd %u\n", hi, lo, tag, h & (CAP - 1), chain, found, found >= 0 ? tags[found] : 0u, *n_distinct);
-        }
-#endif
         flag(2);  // swallowed by a tag collision in B1
     }
 };
@@ -210,9 +201,6 @@ __device__ __forceinline__ void expand_warp(const uint64_t* w, uint32_t nk, uint
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, pi, d); if (lane >= d) pi += o; }
     const uint32_t total = __shfl_sync(0xffffffffu, pi, 31);
-#ifdef RFX_DEBUG_COUNT
-    if (lane == 0) { atomicAdd(&sink.T.why[6], (unsigned long long)total); atomicAdd(&sink.T.why[7], (unsigned long long)((total + 31) / 32)); }
-#endif
     // Source record of k-mer t: the non-empty records are lanes 0 .. r-1 (idle lanes only trail), so it is
     // (number of records that start at or before t) - 1.  Per step every record that starts inside the step's window
     // of 32 k-mers sets one bit; one warp-wide OR and a popcount replace a binary search over the prefix sums.
@@ -287,9 +275,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int N> __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 constexpr int CNT_STAGES = 2;
-#ifndef K4_SOLO_MAX
-#define K4_SOLO_MAX 0u  // bins with at most this many distinct k-mers are compacted by warp 0 alone (0: always all warps)
-#endif
 constexpr uint32_t BIN_END = 0xffffffffu;
 
 // what the producer warp hands over per bin
@@ -420,7 +405,6 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
         for (int i = tid; i < RCAP; i += NT) { rtag[i] = 0u; rmult[i] = 0u; }
     };
     uint32_t aux_phase = 0;
-    unsigned long long acc_inst = 0, acc_distinct = 0;  // warp 0 / lane 0: flushed once at the end
     for (uint32_t it = 0;; it++) {
         const int st = (int)(it % CNT_STAGES);
         const int par = (int)(it & 1u);
@@ -476,12 +460,9 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 }
             }
             compute_barrier<NT>();
-            if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_overflow = 0; }
+            if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_overflow = 0; s_npass = 0; s_cursor = 0; }
             // ---- B: expand the distinct records, spread evenly over the warps ----
             const int n_uniq = (int)*nuniq;
-#ifdef RFX_DEBUG_COUNT
-            if (tid == 0) { atomicAdd(&A.dstat[20], (unsigned long long)n_uniq); atomicAdd(&A.dstat[21], (unsigned long long)cn); }
-#endif
             int per = (n_uniq + NW - 1) / NW;
             per = per < 4 ? 4 : per > 32 ? 32 : per;
 #pragma unroll 1
@@ -525,51 +506,8 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             const uint32_t nd = s_distinct[par];
             if (!ovf) {
                 if (tid == 0) mbar_arrive(&s_empty[st]);
-                if (nd <= K4_SOLO_MAX) {
-                    // K4 by warp 0 alone while the other warps move on to the next bin's A1
-                    if (warp == 0) {
-                        uint32_t mine = 0, inst = 0;
-                        for (uint32_t i = lane; i < nd; i += 32) {
-                            const uint32_t c = cnts[klist[i]];
-                            inst += c;
-                            mine += (c >= A.min_count && c <= A.max_count) ? 1u : 0u;
-                        }
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) { mine += __shfl_xor_sync(0xffffffffu, mine, d); inst += __shfl_xor_sync(0xffffffffu, inst, d); }
-                        unsigned long long base = 0;
-                        if (lane == 0) {
-                            acc_inst += inst; acc_distinct += nd;
-                            if (mine && !A.dry) {
-                                base = atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)mine);
-                                if (base + mine > A.out_cap) { atomicExch(&A.dstat[DS_OVERFLOW], 1ull); base = ~0ull; }
-                            } else base = ~0ull;
-                        }
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        uint32_t done = 0;
-                        for (uint32_t i0 = 0; i0 < nd; i0 += 32) {
-                            const uint32_t i = i0 + lane;
-                            bool keep = false;
-                            uint32_t c = 0, slot = 0;
-                            if (i < nd) { slot = klist[i]; c = cnts[slot]; keep = c >= A.min_count && c <= A.max_count; }
-                            const uint32_t ball = __ballot_sync(0xffffffffu, keep);
-                            if (i < nd) {
-                                if (keep && base != ~0ull) {
-                                    const unsigned long long o = base + done + (uint32_t)__popc(ball & ((1u << lane) - 1u));
-                                    if (!WIDE) reinterpret_cast<uint64_t*>(A.out_keys)[o] = keys[slot];
-                                    else reinterpret_cast<KT*>(A.out_keys)[o] = ((u128)keys[slot] << 64) | keys_lo[slot];
-                                    A.out_counts[o] = c;
-                                }
-                                if (WIDE) tags[slot] = 0u; else keys[slot] = ~0ull;
-                                cnts[slot] = 0u;
-                            }
-                            done += (uint32_t)__popc(ball);
-                        }
-                    }
-                    continue;
-                }
-                // many distinct k-mers (noisy reads): everybody helps, at the price of two more barriers
-                if (tid == 0) { s_npass = 0; s_cursor = 0; }
-                compute_barrier<NT>();
+                // K4: coverage filter + compaction over the occupied slots, all warps (its two counters were cleared
+                // behind the bin's first barrier)
                 uint32_t mine = 0, inst = 0;
                 for (uint32_t i = tid; i < nd; i += NT) {
                     const uint32_t c = cnts[klist[i]];
@@ -721,15 +659,12 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
         // the class loop left through a compute barrier: every thread is done with the stage
         if (tid == 0) { mbar_arrive(&s_empty[st]); s_nuniq[par] = 0; s_distinct[par] = 0; }
     }
-    if (tid == 0) {
-        if (acc_inst) atomicAdd(&A.dstat[DS_INSTANCES], acc_inst);
-        if (acc_distinct) atomicAdd(&A.dstat[DS_DISTINCT], acc_distinct);
-    }
 }
 
 // geometry (shared memory per CTA -> CTAs per SM):
-//   k <= 31: 2 x 768 x 16 B record stages + 4096 x 12 B k-mer table + lists + 1024-entry record-tag table = 89.5 KB -> 2
-//   k  > 31: 2 x 192 x 32 B record stages + 2048 x 24 B k-mer table + lists + 256-entry record-tag table  =  66 KB -> 3
+//   k <= 31, small: 2 x 768 x 16 B record stages + 2048 x 12 B k-mer table + lists + 1024-entry record table = 61 KB -> 3
+//   k <= 31, large: the same with a 4096-slot k-mer table                                                    = 87 KB -> 2
+//   k  > 31:        2 x 192 x 32 B record stages + 2048 x 24 B k-mer table + lists + 256-entry record table  = 66 KB -> 3
 template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t launch_count(const CountArgs& A, cudaStream_t st) {
     const size_t smem = (size_t)CNT_STAGES * (RCAP * 3 / 4) * (WIDE ? 32 : 16) + (size_t)CAP * (WIDE ? 24 : 12) + (size_t)RCAP * 8 +
                         (size_t)(RCAP * 3 / 4) * 2 + (size_t)(CAP * 3 / 4) * 2;
@@ -795,7 +730,7 @@ int stage_count(Ctx* c) {
     if (c->n_records) {
         cudaEventRecord(c->evk[4], st);
         cudaError_t le;
-        const char* variant = getenv("RFX_COUNT_VARIANT");  // tuning knob: force a geometry
+        const char* variant = getenv("RFX_COUNT_VARIANT");  // "small" / "large": skip the pilot and force a geometry (tests, tuning)
         std::string vs = variant ? variant : "";
         if (!c->wide) {
             if (vs.empty() && c->count_geometry && c->count_geometry_bins == c->n_bins) {
@@ -824,12 +759,9 @@ int stage_count(Ctx* c) {
             }
             if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
             else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
-            else if (vs == "b") le = launch_count<false, 2048, 1024, 256, 3>(A, st);
-            else if (vs == "e") le = launch_count<false, 2048, 512, 192, 5>(A, st);
-            else le = launch_count<false, 4096, 1024, 256, 2>(A, st);
+            else return ctx_fail(c, RFX_E_INVALID, "RFX_COUNT_VARIANT must be small or large");
         } else {
-            if (vs == "a") le = launch_count<true, 4096, 512, 384, 1>(A, st);
-            else le = launch_count<true, 2048, 256, 192, 3>(A, st);
+            le = launch_count<true, 2048, 256, 192, 3>(A, st);
         }
         if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count kernel launch failed: %s", cudaGetErrorString(le));
         cudaEventRecord(c->evk[5], st);
@@ -849,10 +781,6 @@ int stage_count(Ctx* c) {
     if (h[DS_OVERFLOW] == 1 || h[DS_OUT_CURSOR] > cap)
         return ctx_fail(c, RFX_E_CAPACITY, "filtered table needs %llu rows, capacity %llu: raise table_capacity",
                         (unsigned long long)h[DS_OUT_CURSOR], (unsigned long long)cap);
-#ifdef RFX_DEBUG_COUNT
-    fprintf(stderr, "DEBUG count: records %llu unique %llu expanded k-mers %llu warp steps %llu\n", (unsigned long long)h[21], (unsigned long long)h[20],
-            (unsigned long long)h[22], (unsigned long long)h[23]);
-#endif
     c->n_rows = h[DS_OUT_CURSOR];
     c->n_distinct = h[DS_DISTINCT];
     c->n_bin_splits = h[DS_SPLITS];
