@@ -163,7 +163,8 @@ enum {
     DS_NSPL = 13,
     DS_FQ_STATE = 14,  // lineMark carried between the chunks of one rfx_push_fastq call
     DS_TICKET = 15,    // next bin handed to a counting CTA
-    DS_OVF_RECORDS = 20,  // records that did not fit their slab (single-pass partition)
+    DS_OVF_RECORDS = 20,
+    DS_SCAN_TODO = 21,    // the register-resident scan left reads to the general kernel  // records that did not fit their slab (single-pass partition)
     DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
     DS_NSLOTS = 24
 };

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(PART_THREADS)
     bin_scan_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
                     BinParams P, Factory F, uint32_t* __restrict__ rd_runs, unsigned long long* dstat, int only_todo) {
     extern __shared__ uint32_t scan_smem[];
+    if (only_todo && dstat[DS_SCAN_TODO] == 0ull) return;  // the fast path took every warp
     const int k = FIXED ? 31 : P.k, m = FIXED ? 11 : P.m, w = FIXED ? 21 : P.w;
     uint32_t* ring = scan_smem + threadIdx.x;                                   // [2*w][PART_THREADS]
     uint32_t* qh = scan_smem + 2 * w * PART_THREADS + threadIdx.x;              // [SCAN_Q][PART_THREADS] minimiser hash
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(PART_THREADS)
         const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
         if (!__all_sync(0xffffffffu, len == len0) || len0 < (uint32_t)K || len0 > 60000u) {
             if (r < n_reads) rd_runs[r] = SCAN_TODO;
+            if ((threadIdx.x & 31) == 0) atomicExch(&dstat[DS_SCAN_TODO], 1ull);
             continue;
         }
         const uint64_t* rd = packed + rd_woff[r];
@@ -521,18 +523,19 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     const bool fixed = P.k == 31 && P.m == 11, fast15 = P.k == 31 && P.m == 15;
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+    const unsigned grid2 = grid < 148u * 4u ? grid : 148u * 4u;  // follow-up pass: usually nothing to do
     if (fixed) {
         // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
         bin_scan_fast_kernel<31, 11, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
                                                                              n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
-        bin_scan_kernel<true, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+        bin_scan_kernel<true, Factory><<<grid2, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
                                                                               n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
         c->launches += 2;
     } else if (fast15) {
         // large inputs (more than 2^16 bins): same register-resident scan with 15-mers
         bin_scan_fast_kernel<31, 15, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
                                                                              n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>());
-        bin_scan_kernel<false, Factory><<<grid, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
+        bin_scan_kernel<false, Factory><<<grid2, PART_THREADS, smem_scan, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
                                                                                n_reads, P, F, c->rd_runs.as<uint32_t>(), c->dstat.as<unsigned long long>(), 1);
         c->launches += 2;
     } else {
@@ -588,7 +591,7 @@ static int slab_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads) {
     RFX_TRY(devbuf_reserve(c, c->ovf_rec, (ovf_cap * c->recw + 2) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ovf_bin, ovf_cap * sizeof(uint32_t)));
     RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, nb * 4 * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_OVF_RECORDS, 0, sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_OVF_RECORDS, 0, 2 * sizeof(uint64_t), st));  // + DS_SCAN_TODO
     c->sp_cap = (uint32_t)cap; c->sp_ovf_cap = ovf_cap; c->sp_done = 0; c->sp_kernel_ms = 0;
     return RFX_OK;
 }
@@ -717,6 +720,7 @@ int stage_partition(Ctx* c, int n_shards) {
     RFX_TRY(devbuf_reserve(c, c->rd_runs, (size_t)(c->n_reads + 1) * sizeof(uint32_t)));
     RFX_CUDA(c, cudaMemsetAsync(c->bin_cursor.p, 0, nb * 4 * sizeof(uint32_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_SPILL, 0, sizeof(uint64_t), st));
+    RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_SCAN_TODO, 0, sizeof(uint64_t), st));
     uint32_t* bin_cnt = c->bin_cursor.as<uint32_t>();
     uint32_t* spill_cnt = bin_cnt + nb;
     uint32_t* cursor = spill_cnt + nb;
