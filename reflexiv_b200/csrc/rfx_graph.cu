@@ -17,6 +17,7 @@
 // After the two fork filters every (k-1)-mer has at most one surviving out-edge and one in-edge, so
 // the reference's sort-and-merge iteration converges to the maximal paths of that graph; pointer
 // jumping computes (head, rank) for every node in O(log n) rounds instead.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -304,6 +305,41 @@ __global__ void rank_step_kernel(uint64_t n, const uint64_t* __restrict__ ad_in,
     }
     if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_CHANGED], 1ull);
 }
+// All pointer-jumping rounds over the splitter list in ONE cooperative launch: the list is small (a few MB), so a round
+// is a few microseconds of work and what used to cost was 20-odd launches and the host reading a "changed" flag every
+// fourth one.  Grid-wide barrier between rounds; three rotating flags tell every block whether the round changed
+// anything (a flag is cleared one round before it is used and read one round after).
+__global__ void __launch_bounds__(256) rank_all_kernel(const unsigned long long* m_ptr, uint64_t* ad0, uint64_t* ad1, unsigned long long* dstat) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const uint64_t m = *m_ptr;
+    int max_rounds = 2;
+    while ((1ull << max_rounds) < m + 1) max_rounds++;
+    max_rounds += 2;
+    unsigned long long* flags = dstat + DS_RANK_FLAGS;
+    uint64_t* in = ad0;
+    uint64_t* out = ad1;
+    int cur = 0;
+    for (int round = 0; round < max_rounds; round++) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[(round + 1) % 3] = 0ull;
+        bool changed = false;
+        for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < m; x += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t mine = in[x];
+            const uint32_t a = (uint32_t)mine;
+            if (a == (uint32_t)x) { out[x] = mine; continue; }
+            const uint64_t up = in[a];
+            const uint32_t aa = (uint32_t)up;
+            out[x] = ad_pack(aa, (uint32_t)(mine >> 32) + (uint32_t)(up >> 32));
+            changed |= (aa != a);
+        }
+        if (__any_sync(0xffffffffu, changed) && (threadIdx.x & 31) == 0) atomicExch(&flags[round % 3], 1ull);
+        grid.sync();
+        uint64_t* t = in; in = out; out = t;
+        cur ^= 1;
+        if (*(volatile unsigned long long*)&flags[round % 3] == 0ull) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) dstat[DS_RANK_CUR] = (unsigned long long)cur;
+}
+
 // ---- K6 (work-efficient variant): rank through a sample of splitters ------------------------------------------
 // Heads and one node in 16 (hash of the id) are splitters.  Each splitter walks its successors up to the next
 // splitter, stamping (owner, offset) on the way: every node is touched once.  Only the splitter list (n/16 entries,
@@ -323,8 +359,9 @@ __global__ void splitter_select_kernel(uint64_t n, const uint8_t* __restrict__ a
         spl_id[x] = id;
     }
 }
-__global__ void splitter_walk_kernel(uint64_t m, const uint32_t* __restrict__ spl_node, const uint32_t* __restrict__ succ,
+__global__ void splitter_walk_kernel(const unsigned long long* m_ptr, const uint32_t* __restrict__ spl_node, const uint32_t* __restrict__ succ,
                                      const uint32_t* __restrict__ spl_id, uint64_t* __restrict__ loc, uint64_t* sp_ad) {
+    const uint64_t m = *m_ptr;  // number of splitters, still on the device: no host round trip between select and walk
     for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m; id += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t x = spl_node[id];
         uint32_t off = 0;
@@ -340,8 +377,9 @@ __global__ void splitter_walk_kernel(uint64_t m, const uint32_t* __restrict__ sp
     }
 }
 __global__ void rank_finalize_kernel(uint64_t n, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred, const uint64_t* __restrict__ loc,
-                                     const uint64_t* __restrict__ sp_ad, const uint32_t* __restrict__ spl_node, uint64_t* __restrict__ ad,
+                                     const uint64_t* sp_ad0, const uint64_t* sp_ad1, const uint32_t* __restrict__ spl_node, uint64_t* __restrict__ ad,
                                      unsigned long long* dstat) {
+    const uint64_t* sp_ad = dstat[DS_RANK_CUR] ? sp_ad1 : sp_ad0;
     bool on_cycle = false;
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t l = loc[x];
@@ -601,34 +639,22 @@ template <class KT> static int graph_impl(Ctx* c) {
                 cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st);
                 cudaMemsetAsync(loc, 0xff, n * sizeof(uint64_t), st);
                 splitter_select_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, spl_id, spl_node, c->sp_ad[0].as<uint64_t>(), dstat);
-                uint64_t m = 0;
-                cudaMemcpyAsync(&m, dstat + DS_NSPL, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-                e = cudaStreamSynchronize(st);
-                if (e != cudaSuccess) break;
-                int scur = 0;
-                if (m) {
-                    splitter_walk_kernel<<<grid_n(m), 256, 0, st>>>(m, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
-                    int slimit = 2;
-                    while ((1ull << slimit) < m + 1) slimit++;
-                    slimit += 2;
-                    // the host looks at the "changed" flag only every 4 rounds (extra rounds are idempotent)
-                    for (int round = 0; round < slimit;) {
-                        cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st);
-                        for (int q = 0; q < 4 && round < slimit; q++, round++) {
-                            rank_step_kernel<<<grid_n(m), 256, 0, st>>>(m, c->sp_ad[scur].as<uint64_t>(), c->sp_ad[scur ^ 1].as<uint64_t>(), dstat);
-                            c->launches++;
-                            scur ^= 1;
-                        }
-                        uint64_t changed = 0;
-                        cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
-                        e = cudaStreamSynchronize(st);
-                        if (e != cudaSuccess) break;
-                        if (!changed) break;
-                    }
+                // select -> walk -> all jumping rounds -> finalize without a host round trip in between
+                splitter_walk_kernel<<<148 * 16, 256, 0, st>>>(dstat + DS_NSPL, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
+                cudaMemsetAsync(dstat + DS_RANK_FLAGS, 0, 3 * sizeof(uint64_t), st);
+                cudaMemsetAsync(dstat + DS_RANK_CUR, 0, sizeof(uint64_t), st);
+                {
+                    const unsigned long long* m_ptr = dstat + DS_NSPL;
+                    uint64_t* a0 = c->sp_ad[0].as<uint64_t>();
+                    uint64_t* a1 = c->sp_ad[1].as<uint64_t>();
+                    unsigned long long* ds = dstat;
+                    void* args[] = {(void*)&m_ptr, (void*)&a0, (void*)&a1, (void*)&ds};
+                    e = cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(148 * 4), dim3(256), args, 0, st);
                     if (e != cudaSuccess) break;
                 }
                 cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st);
-                rank_finalize_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, loc, c->sp_ad[scur].as<uint64_t>(), spl_node, c->ad[0].as<uint64_t>(), dstat);
+                rank_finalize_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, loc, c->sp_ad[0].as<uint64_t>(), c->sp_ad[1].as<uint64_t>(), spl_node, c->ad[0].as<uint64_t>(), dstat);
+                c->launches++;
                 c->launches += 3;
                 uint64_t any_cycle = 0;
                 cudaMemcpyAsync(&any_cycle, dstat + DS_CYCLE_NODES, sizeof(uint64_t), cudaMemcpyDeviceToHost, st);

@@ -166,7 +166,9 @@ enum {
     DS_OVF_RECORDS = 20,
     DS_SCAN_TODO = 21,    // the register-resident scan left reads to the general kernel  // records that did not fit their slab (single-pass partition)
     DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
-    DS_NSLOTS = 24
+    DS_RANK_CUR = 22,     // which of the two (ancestor, distance) buffers holds the result of rank_all_kernel
+    DS_RANK_FLAGS = 24,   // 3 rotating 'something changed' flags of rank_all_kernel
+    DS_NSLOTS = 32
 };
 
 static const uint32_t NONE32 = 0xffffffffu;
