@@ -505,6 +505,7 @@ __global__ void gather_contigs_kernel(Graph<KT> G, const uint8_t* __restrict__ a
 }
 
 __global__ void set_u64_kernel(uint64_t* p, const U64x3* tot) { *p = tot->b; }
+__global__ void set_value_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
 static unsigned grid_n(uint64_t n) {
     uint64_t g = (n + 255) / 256;
@@ -994,21 +995,23 @@ static int gs_rank_impl(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, 
         gs_index_kernel<<<grid_n(M), 256, 0, st>>>(M, g_node, gidx, c->sp_ad[0].as<uint64_t>());
         gs_reduced_link_kernel<<<grid_n(M), 256, 0, st>>>(M, g_next, g_len, gidx, c->sp_ad[0].as<uint64_t>(), dstat);
         c->launches += 2;
-        int slimit = 2;
-        while ((1ull << slimit) < M + 1) slimit++;
-        slimit += 2;
-        for (int round = 0; round < slimit;) {
-            RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st));
-            for (int q = 0; q < 4 && round < slimit; q++, round++) {
-                rank_step_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), c->sp_ad[scur ^ 1].as<uint64_t>(), dstat);
-                c->launches++;
-                scur ^= 1;
-            }
-            uint64_t changed = 0;
-            RFX_CUDA(c, cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-            RFX_TRY(gs_sync(c, "reduced list ranking"));
-            if (!changed) break;
+        // all jumping rounds in one cooperative launch (rank_all_kernel); it reads the list length from the device
+        set_value_kernel<<<1, 1, 0, st>>>(dstat + DS_NSPL, (unsigned long long)M);
+        RFX_CUDA(c, cudaMemsetAsync(dstat + DS_RANK_FLAGS, 0, 3 * sizeof(uint64_t), st));
+        RFX_CUDA(c, cudaMemsetAsync(dstat + DS_RANK_CUR, 0, sizeof(uint64_t), st));
+        {
+            const unsigned long long* m_ptr = dstat + DS_NSPL;
+            uint64_t* a0 = c->sp_ad[0].as<uint64_t>();
+            uint64_t* a1 = c->sp_ad[1].as<uint64_t>();
+            unsigned long long* ds = dstat;
+            void* args[] = {(void*)&m_ptr, (void*)&a0, (void*)&a1, (void*)&ds};
+            RFX_CUDA(c, cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(148 * 4), dim3(256), args, 0, st));
         }
+        uint64_t which = 0;
+        RFX_CUDA(c, cudaMemcpyAsync(&which, dstat + DS_RANK_CUR, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        RFX_TRY(gs_sync(c, "reduced list ranking"));
+        scur = (int)which;
+        c->launches += 2;
         gs_cycle_check_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), dstat);
     }
     if (own) gs_finalize_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, my_off, c->alive.as<uint8_t>(), c->loc.as<uint64_t>(), c->sp_ad[scur].as<uint64_t>(), g_node, c->ad[0].as<uint64_t>(), dstat);
