@@ -300,14 +300,18 @@ __global__ void __launch_bounds__(PART_THREADS)
     __shared__ uint16_t s_qp[FAST_Q * PART_THREADS];
     for (uint64_t base = (uint64_t)blockIdx.x * PART_THREADS; base < n_reads; base += (uint64_t)gridDim.x * PART_THREADS) {
         const uint64_t r = base + threadIdx.x;
-        const uint32_t len = r < n_reads ? rd_len[r] : 0u;
+        const bool valid = r < n_reads;
+        if (!__any_sync(0xffffffffu, valid)) continue;  // (valid lanes are a prefix of the warp: lane 0 is one of them)
+        const uint32_t len = valid ? rd_len[r] : 0u;
         const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
-        if (!__all_sync(0xffffffffu, len == len0) || len0 < (uint32_t)K || len0 > 60000u) {
-            if (r < n_reads) rd_runs[r] = SCAN_TODO;
+        if (!__all_sync(0xffffffffu, !valid || len == len0) || len0 < (uint32_t)K || len0 > 60000u) {
+            if (valid) rd_runs[r] = SCAN_TODO;
             if ((threadIdx.x & 31) == 0) atomicExch(&dstat[DS_SCAN_TODO], 1ull);
             continue;
         }
-        const uint64_t* rd = packed + rd_woff[r];
+        // the lanes behind the last read walk lane 0's read along (same schedule, nothing emitted)
+        const uint64_t woff = __shfl_sync(0xffffffffu, valid ? rd_woff[r] : 0ull, valid ? (int)(threadIdx.x & 31) : 0);
+        const uint64_t* rd = packed + woff;
         typename Factory::Emit em = F.make(r, rd);
         RunState rst{0u, 0u, false};
         FastScan<M, W> S;
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(PART_THREADS)
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) maxq = max(maxq, __shfl_xor_sync(0xffffffffu, maxq, d));
             for (uint32_t t = 0; t < maxq; t++) {
-                if (t < S.qn) {
+                if (valid && t < S.qn) {
                     const uint32_t i = S.qp[t * PART_THREADS];
                     const uint32_t bin = bin_of_minimizer(S.qh[t * PART_THREADS], P.n_bins);
                     if (!rst.have) { rst.have = true; rst.run_bin = bin; rst.run_start = i; }
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(PART_THREADS)
                 }
             }
             S.qn = 0;
-            if (final && rst.have) emit_run(em, rst.run_bin, rst.run_start, n_kmers - rst.run_start, P.max_nk);
+            if (valid && final && rst.have) emit_run(em, rst.run_bin, rst.run_start, n_kmers - rst.run_start, P.max_nk);
         };
         {   // the first M - 1 bases complete no m-mer
             const uint64_t w0 = rd[0];
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(PART_THREADS)
             S.template block<2>(win_next, n_full * W - (uint32_t)(W - 1), (int)rem);
         }
         drain(true, len0 - (uint32_t)K + 1u);
+        if (!valid) continue;
         if (Factory::kNeedsRuns) {
             const bool spill = em.n > em.stored;
             rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);
