@@ -182,36 +182,55 @@ struct OpAddU64x4 {
     __device__ __forceinline__ U64x4 operator()(U64x4 x, U64x4 y) const { return U64x4{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
 };
 
+// The scan element is one 64-bit word, reads in the high half and packed words in the low half (both < 2^32 per call:
+// up to 137 G bases of text at once); bases and k-mer instances are only needed as totals and are summed on the side.
 struct ReadIn {
     Lines L;
     const uint32_t* seq_eff;  // nullptr: every line is a read, lengths from line_start[]
     int k, fc, ec;
-    __device__ __forceinline__ U64x4 operator()(uint64_t i) const {
-        uint32_t e;
-        if (seq_eff) {
-            e = seq_eff[i];
-            if (e == NOT_A_READ) return U64x4{0, 0, 0, 0};
-        } else {
-            e = effective_read_len((int64_t)L.len(i), k, fc, ec);
-        }
-        return U64x4{1, (uint64_t)((e + 31u) >> 5), e, e ? (uint64_t)(e - (uint32_t)k + 1u) : 0u};
+    __device__ __forceinline__ uint32_t eff(uint64_t i) const {
+        return seq_eff ? seq_eff[i] : effective_read_len((int64_t)L.len(i), k, fc, ec);
+    }
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        const uint32_t e = eff(i);
+        if (e == NOT_A_READ) return 0ull;
+        return (1ull << 32) | (uint64_t)((e + 31u) >> 5);
     }
 };
 struct ReadOut {
-    Lines L;
+    ReadIn in;
     uint64_t read_base, word_base;
-    int fc;
     uint64_t* rd_src;
     uint32_t* rd_len;
     uint64_t* rd_woff;
-    __device__ __forceinline__ void operator()(uint64_t i, U64x4 excl, U64x4 v) const {
-        if (!v.a) return;
-        const uint64_t r = excl.a;
-        rd_src[r] = L.start[i] + (uint64_t)fc;
-        rd_len[read_base + r] = (uint32_t)v.c;
-        rd_woff[read_base + r] = word_base + excl.b;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t excl, uint64_t v) const {
+        if (!v) return;
+        const uint32_t e = in.eff(i);
+        const uint64_t r = excl >> 32;
+        rd_src[r] = in.L.start[i] + (uint64_t)in.fc;
+        rd_len[read_base + r] = e;
+        rd_woff[read_base + r] = word_base + (excl & 0xffffffffull);
     }
 };
+// bases kept and k-mer instances of the appended reads: one pass over their lengths, one atomic pair per block
+__global__ void __launch_bounds__(256) read_totals_kernel(const uint32_t* __restrict__ rd_len, uint64_t n, int k, unsigned long long* totals) {
+    unsigned long long b = 0, inst = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t e = rd_len[i];
+        b += e;
+        inst += e ? (unsigned long long)(e - (uint32_t)k + 1u) : 0ull;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { b += __shfl_xor_sync(0xffffffffu, b, d); inst += __shfl_xor_sync(0xffffffffu, inst, d); }
+    __shared__ unsigned long long sb[8], si[8];
+    if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = b; si[threadIdx.x >> 5] = inst; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) { b += sb[w]; inst += si[w]; }
+        if (b) atomicAdd(&totals[0], b);
+        if (inst) atomicAdd(&totals[1], inst);
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // warp-cooperative 2-bit encoder: a lane turns 4 ASCII bases into one byte with SIMD-in-register
@@ -276,16 +295,17 @@ static unsigned grid_for(uint64_t n, int block, unsigned cap = 148 * 16) {
 // Builds the read table for `n_lines` lines and appends the packed reads to the context.
 static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* seq_flag) {
     cudaStream_t st = c->stream;
-    ScanPlan<U64x4> plan;
-    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<U64x4>::workspace_elems(L.n_lines) * sizeof(U64x4)));
-    plan.bind(L.n_lines, c->scan_ws.as<U64x4>());
+    if (L.n_lines && (L.start == nullptr)) return ctx_fail(c, RFX_E_INVALID, "append_reads: no line table");
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(L.n_lines) * sizeof(uint64_t)));
+    plan.bind(L.n_lines, c->scan_ws.as<uint64_t>());
     ReadIn in{L, seq_flag, c->k, c->prm.front_clip, c->prm.end_clip};
-    scan_prepare(plan, in, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
+    scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
     c->launches += 2 * plan.levels;
-    U64x4 tot;
+    uint64_t tot = 0;
     RFX_CUDA(c, cudaMemcpyAsync(&tot, plan.total, sizeof(tot), cudaMemcpyDeviceToHost, st));
     RFX_CUDA(c, cudaStreamSynchronize(st));
-    const uint64_t n_new = tot.a, w_new = tot.b;
+    const uint64_t n_new = tot >> 32, w_new = tot & 0xffffffffull;
     if (n_new == 0) return RFX_OK;
     DevBuf& rd_src = c->rd_src;
     RFX_TRY(devbuf_reserve(c, rd_src, n_new * sizeof(uint64_t)));
@@ -294,20 +314,25 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* 
         if ((rc = devbuf_reserve(c, c->rd_len, (c->n_reads + n_new) * sizeof(uint32_t), true)) != RFX_OK) break;
         if ((rc = devbuf_reserve(c, c->rd_woff, (c->n_reads + n_new) * sizeof(uint64_t), true)) != RFX_OK) break;
         if ((rc = devbuf_reserve(c, c->packed, (c->n_words + w_new + 8) * sizeof(uint64_t), true)) != RFX_OK) break;
-        ReadOut out{L, c->n_reads, c->n_words, c->prm.front_clip, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
-        scan_apply(plan, in, out, OpAddU64x4{}, U64x4{0, 0, 0, 0}, st);
+        unsigned long long* totals = c->dstat.as<unsigned long long>() + DS_READ_TOTALS;
+        cudaMemsetAsync(totals, 0, 2 * sizeof(uint64_t), st);
+        ReadOut out{in, c->n_reads, c->n_words, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
+        scan_apply(plan, in, out, OpAddU64{}, (uint64_t)0, st);
+        read_totals_kernel<<<grid_for(n_new, 256, 148 * 2), 256, 0, st>>>(c->rd_len.as<uint32_t>() + c->n_reads, n_new, c->k, totals);
         encode_reads_kernel<<<grid_for(n_new * 8, 256, 148 * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
                                                                                 c->rd_woff.as<uint64_t>(), n_new, c->n_reads,
                                                                                 c->packed.as<uint64_t>());
         // padding words after the last read: packed_window() may look one word ahead
         cudaMemsetAsync(c->packed.as<uint64_t>() + c->n_words + w_new, 0, 8 * sizeof(uint64_t), st);
         c->launches += 2;
+        uint64_t ht[2] = {0, 0};
+        cudaMemcpyAsync(ht, totals, sizeof(ht), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "encode failed: %s", cudaGetErrorString(e)); break; }
         c->n_reads += n_new;
         c->n_words += w_new;
-        c->n_bases += tot.c;
-        c->n_instances += tot.d;
+        c->n_bases += ht[0];
+        c->n_instances += ht[1];
     } while (0);
     return rc;
 }

@@ -167,7 +167,8 @@ enum {
     DS_SCAN_TODO = 21,    // the register-resident scan left reads to the general kernel  // records that did not fit their slab (single-pass partition)
     DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
     DS_RANK_CUR = 22,     // which of the two (ancestor, distance) buffers holds the result of rank_all_kernel
-    DS_RANK_FLAGS = 24,   // 3 rotating 'something changed' flags of rank_all_kernel
+    DS_RANK_FLAGS = 24,
+    DS_READ_TOTALS = 28,  // 2 slots: bases kept and k-mer instances of the reads being appended   // 3 rotating 'something changed' flags of rank_all_kernel
     DS_NSLOTS = 32
 };
 
