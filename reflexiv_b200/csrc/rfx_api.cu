@@ -30,6 +30,13 @@ int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep) {
     size_t want = bytes;
     if (keep && b.cap) want = bytes > b.cap * 2 ? bytes : b.cap * 2;  // appended buffers grow geometrically
     want = (want + 255) & ~(size_t)255;
+    if (b.p && !(keep && b.cap)) {
+        // contents are not needed: give the old block back first, so that growing a 45 GB buffer by 2 % does not need 90 GB
+        if (c && c->stream) cudaStreamSynchronize(c->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
@@ -38,7 +45,7 @@ int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep) {
     }
     if (b.p) {
         if (c && c->stream) cudaStreamSynchronize(c->stream);
-        if (keep && b.cap) cudaMemcpy(p, b.p, b.cap, cudaMemcpyDeviceToDevice);
+        cudaMemcpy(p, b.p, b.cap, cudaMemcpyDeviceToDevice);
         cudaFree(b.p);
     }
     b.p = p;

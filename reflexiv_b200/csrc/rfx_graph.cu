@@ -522,13 +522,17 @@ template <class KT> static Graph<KT> make_graph(Ctx* c) {
 template <class KT> static int build_index(Ctx* c) {
     cudaStream_t st = c->stream;
     const uint64_t n_rows = c->n_rows;
-    // a table that fits L2 (keys + counts + index, about 20 B per row of the 126 MB) is served fastest by ONE region:
-    // the minimiser arithmetic only pays once probes would otherwise go to HBM
+    // Presence bits (>= 16 per row) answer most probes as long as they stay (mostly) cache resident: up to 2^30 bits
+    // (128 MB, 64 M rows) the table is ONE region behind that filter.  Beyond that a filter access is just one more
+    // trip to HBM (measured at 1.5 * 10^8 rows: 102 ms with it, 76 ms without), and what helps instead is locality:
+    // regions per minimiser bin, no filter.
+    uint64_t bits = 1024;
+    while (bits < 16 * n_rows) bits <<= 1;
+    const char* force = getenv("RFX_GRAPH_INDEX");  // "local" / "global": tests exercise both on small inputs
+    const bool local = force ? !strcmp(force, "local") : bits > (1024ull << 20);
     uint64_t gb = n_rows / 32;
     if (gb < 64) gb = 64;
     if (gb > (1ull << 26)) gb = 1ull << 26;
-    const char* force = getenv("RFX_GRAPH_INDEX");  // "local" / "global": tests exercise both on small inputs
-    const bool local = force ? !strcmp(force, "local") : n_rows > 6000000ull;
     if (!local) gb = 1;
     c->g_bins = (uint32_t)gb;
     int m = gb > 65536 ? 15 : 11;  // many more minimiser values than bins (as in rfx_partition.cu: set_minimizer)
@@ -541,10 +545,7 @@ template <class KT> static int build_index(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
     c->ht_cap = slots;
     RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
-    // presence bits only where they stay (mostly) cache resident (<= 128 MB); beyond that the bin-local regions do the job
-    uint64_t bits = 1024;
-    while (bits < 16 * n_rows) bits <<= 1;
-    c->g_bloom_mask = bits <= (1024ull << 20) ? bits - 1 : 0;
+    c->g_bloom_mask = (!local || force) && bits <= (1024ull << 20) ? bits - 1 : 0;
     if (c->g_bloom_mask) {
         RFX_TRY(devbuf_reserve(c, c->g_bloom, bits / 8));
         RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.p, 0, bits / 8, st));
