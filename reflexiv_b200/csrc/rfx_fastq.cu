@@ -6,7 +6,7 @@
 //   nucleotideValue + the clip / minimum-length rule  ReflexivDataFrameCounter.java:471, 513-525
 //
 // Device data flow (all in HBM):
-//   text bytes --newline scan--> line_start[] --filter scan--> seq_flag[] --sum scan--> read table
+//   text bytes --newline scan--> line_start[] --filter scan--> seq_eff[] (read? effective length) --sum scan--> read table
 //   (source offset, effective length, word offset) --warp-cooperative encoder--> packed 2-bit reads.
 #include "rfx_internal.h"
 #include "rfx_scan.cuh"
@@ -161,27 +161,8 @@ __global__ void flag_lines_kernel(Lines L, int mode, uint32_t* seq_eff, int k, i
 }
 
 // ------------------------------------------------------------------------------------------
-// read table: a = reads, b = packed words, c = bases kept, d = k-mer instances
+// read table
 // ------------------------------------------------------------------------------------------
-struct U64x4 {
-    uint64_t a, b, c, d;
-};
-__device__ __forceinline__ U64x4 shfl_up_any(U64x4 v, int s) {
-    U64x4 r;
-    r.a = __shfl_up_sync(0xffffffffu, v.a, s); r.b = __shfl_up_sync(0xffffffffu, v.b, s);
-    r.c = __shfl_up_sync(0xffffffffu, v.c, s); r.d = __shfl_up_sync(0xffffffffu, v.d, s);
-    return r;
-}
-__device__ __forceinline__ U64x4 shfl_idx_any(U64x4 v, int l) {
-    U64x4 r;
-    r.a = __shfl_sync(0xffffffffu, v.a, l); r.b = __shfl_sync(0xffffffffu, v.b, l);
-    r.c = __shfl_sync(0xffffffffu, v.c, l); r.d = __shfl_sync(0xffffffffu, v.d, l);
-    return r;
-}
-struct OpAddU64x4 {
-    __device__ __forceinline__ U64x4 operator()(U64x4 x, U64x4 y) const { return U64x4{x.a + y.a, x.b + y.b, x.c + y.c, x.d + y.d}; }
-};
-
 // The scan element is one 64-bit word, reads in the high half and packed words in the low half (both < 2^32 per call:
 // up to 137 G bases of text at once); bases and k-mer instances are only needed as totals and are summed on the side.
 struct ReadIn {

@@ -59,7 +59,7 @@ struct Ctx {
     DevBuf text;        // staging for host FASTQ text
     DevBuf line_start;  // u64[n_lines + 1]
     DevBuf line_at;     // u8[n_lines + 1] line starts with '@'
-    DevBuf seq_flag;    // u8[n_lines]
+    DevBuf seq_flag;    // u32[n_lines]  NOT_A_READ, or the effective length of the read on that line
     DevBuf scan_ws;     // scan workspace
     DevBuf rd_src;      // u64[new reads] text offset of each read of the current push (scratch)
     DevBuf rd_len;      // u32[n_reads]   effective length (0 = contributes nothing)

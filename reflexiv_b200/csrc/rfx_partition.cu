@@ -32,8 +32,6 @@ struct EmitDesc {
     uint32_t* spill_cnt;
     uint32_t n;        // runs seen
     uint32_t stored;   // runs that got a descriptor (always a prefix of the read's runs)
-    RFX_HD uint32_t reserve(uint32_t) { return 0u; }
-    RFX_HD void put(uint32_t bin, uint32_t, uint32_t first_kmer, uint32_t n_k) { (*this)(bin, first_kmer, n_k); }
     RFX_HD void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
 #if defined(__CUDA_ARCH__)
         if (n < max_slots && first_kmer < 65536u) {
@@ -94,10 +92,8 @@ template <int RECW> struct EmitSlab {
     unsigned long long ovf_cap;
     int k;
     uint32_t n, stored;
-    // reserve() and put() are separate so that a caller can have several atomics in flight before it needs a rank
-    __device__ __forceinline__ uint32_t reserve(uint32_t bin) { return atomicAdd(&bin_cnt[bin], 1u); }
-    __device__ __forceinline__ void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) { put(bin, reserve(bin), first_kmer, n_k); }
-    __device__ __forceinline__ void put(uint32_t bin, uint32_t rank, uint32_t first_kmer, uint32_t n_k) {
+    __device__ __forceinline__ void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
+        const uint32_t rank = atomicAdd(&bin_cnt[bin], 1u);
         uint64_t rec[RECW];
         rec_build<RECW>(rd, first_kmer, n_k, k, rec);
         uint64_t* dst;

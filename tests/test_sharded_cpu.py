@@ -100,3 +100,36 @@ def test_bin_geometry_helpers():
         per = nb // world
         assert [sharded.shard_of_bin(b, nb, world) for b in (0, per - 1, per if world > 1 else 0, nb - 1)][-1] == world - 1
     assert sharded.choose_total_bins(10, 8) == 64
+
+
+def _plumbing_worker(rank, world, port):
+    from reflexiv_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # gather_varlen: ragged 1-D and 2-D inputs come back concatenated in rank order
+    rows = 3 + 2 * rank
+    one = torch.arange(rows, dtype=torch.int64) + 100 * rank
+    g, sizes = sharded.gather_varlen(torch, dist, one)
+    assert sizes == [3 + 2 * r for r in range(world)]
+    assert g.tolist() == [100 * r + i for r in range(world) for i in range(3 + 2 * r)]
+    two = (torch.arange(rows * 3, dtype=torch.int32) + 1000 * rank).reshape(rows, 3)
+    g2, sizes2 = sharded.gather_varlen(torch, dist, two)
+    assert sizes2 == sizes and g2.shape == (sum(sizes), 3)
+    assert g2[sizes[0]:sizes[0] + 2].tolist() == [[1000, 1001, 1002], [1003, 1004, 1005]]
+    empty, esz = sharded.gather_varlen(torch, dist, torch.empty(0, dtype=torch.int32))
+    assert empty.numel() == 0 and esz == [0] * world
+    # _bcast_slices: every rank ends up with every owner's slice, whatever path the backend allows
+    ranges = [(0, 5), (5, 12)]
+    buf = torch.zeros(12, dtype=torch.uint8)
+    lo, hi = ranges[rank]
+    buf[lo:hi] = rank + 1
+    sharded._bcast_slices(torch, dist, buf, ranges)
+    assert buf.tolist() == [1] * 5 + [2] * 7
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_collective_helpers_on_gloo():
+    port = 29800 + os.getpid() % 1000
+    mp.spawn(_plumbing_worker, args=(2, port), nprocs=2, join=True)
