@@ -303,7 +303,9 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_count, "algorithmic_bytes_per_kmer": b_count / inst_local if inst_local else None,
                 "kernel_ms": kern_ms, "stage_kmers_per_s": inst_local / (count_path_ms * 1e-3) if count_path_ms else None,
-                "bound_observed": "instruction issue / shared-memory latency (ncu: issue-active 49-59 %, DRAM 7-9 %), see profiles/"}
+                "bound_observed": "instruction issue / shared-memory latency (ncu: issue-active 51-58 %, DRAM 7-9 %), see profiles/",
+                "count_geometry": "picked by a pilot launch over ~300 sampled bins (0.03 ms + one readback) the first time a context counts; the context "
+                                  "keeps the choice while the bin count stays the same, so the pilot runs in the warm-up steps, not in the timed ones"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:

@@ -95,9 +95,10 @@ typedef struct {
     float ms_extend;   /* K6: list ranking */
     float ms_contigs;  /* K7: contig gather */
     /* single-kernel durations of the last rfx_count (CUDA events around the launch only) */
-    float ms_kernel_bin_histogram; /* bin_scan_kernel: minimiser scan, run descriptors, bin histogram */
-    float ms_kernel_bin_scatter;   /* emit_records_kernel: super-k-mer records into bins */
-    float ms_kernel_count;         /* count_bins_*_kernel         */
+    float ms_kernel_bin_histogram; /* minimiser scan (bin_scan_fast_kernel / bin_scan_kernel): one GPU: scan + record store into the
+                                      bin slabs; sharded: scan + run descriptors + bin histogram */
+    float ms_kernel_bin_scatter;   /* emit_records_kernel (sharded runs only): super-k-mer records into the compact layout */
+    float ms_kernel_count;         /* count_bins_kernel (pilot, when it runs, + main launch) */
     float reserved1;
 } rfx_stats_t;
 
