@@ -256,6 +256,58 @@ template <class Emit> RFX_HD void bin_scan_read(const uint64_t* rd, uint32_t len
     emit(run_bin, run_start, len - (uint32_t)k + 1u - run_start);
 }
 
+// The k-mer with index `off` of a record (forward orientation, right aligned), cut straight out of the record's bit
+// stream: what the counting kernel's warp-wide expansion does per lane (rfx_count.cu: expand_warp).  Static indices
+// only, so the words stay in registers.
+template <class KT, int RECW> RFX_HD KT rec_kmer_at(const uint64_t (&w)[RECW], uint32_t off, int k) {
+    const uint32_t b = 16u + 2u * off;  // first bit of the k-mer in the bit stream (bit 0 = top bit of word 0)
+    if (RECW == 2 && sizeof(KT) == 8) {
+        uint64_t hi;
+        if (b < 64u) hi = (w[0] << b) | ((w[1] >> 1) >> (63u - b));
+        else hi = w[1] << (b - 64u);
+        return (KT)(hi >> (64 - 2 * k));
+    }
+    // 128 bits starting at bit b of the stream w[0] w[1] .. w[RECW-1] 0 0
+    const uint32_t wi = b >> 6, sh = b & 63u;
+    const uint64_t w2 = RECW > 2 ? w[RECW > 2 ? 2 : 0] : 0ull, w3 = RECW > 3 ? w[RECW > 3 ? 3 : 0] : 0ull;
+    const uint64_t a0 = wi == 0 ? w[0] : wi == 1 ? w[1] : wi == 2 ? w2 : w3;
+    const uint64_t a1 = wi == 0 ? w[1] : wi == 1 ? w2 : wi == 2 ? w3 : 0ull;
+    const uint64_t a2 = wi == 0 ? w2 : wi == 1 ? w3 : 0ull;
+    const uint64_t hi = (a0 << sh) | ((a1 >> 1) >> (63u - sh));
+    const uint64_t lo = (a1 << sh) | ((a2 >> 1) >> (63u - sh));
+    const u128 v = (((u128)hi << 64) | lo) >> (128 - 2 * k);
+    return (KT)v;
+}
+
+// Hashing for the counting tables.  Every 32-bit word goes through a 32 x 32 -> 64-bit multiply whose halves are folded
+// together ("mum"): the high half carries the word's top bits down, so -- unlike a plain (word * odd) ^ ... chain,
+// where a difference in the top bits of one word can cancel a difference in the top bits of another -- related k-mers
+// (a substitution here, another 16 bases further on) do not collide systematically.  Only speed depends on the
+// quality of these hashes: equal hashes are always confirmed against the full record / key before anything is counted.
+RFX_HD uint32_t mum32(uint32_t x, uint32_t c) {
+    const uint64_t p = (uint64_t)x * c;
+    return (uint32_t)p ^ (uint32_t)(p >> 32);
+}
+RFX_HD uint32_t hash_lane_a(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t x = mum32(a ^ 0x9E3779B9u, 0x9E3779B1u) ^ b;
+    x = mum32(x, 0x85EBCA77u) ^ c;
+    x = mum32(x, 0xC2B2AE3Du) ^ d;
+    return mum32(x, 0x27D4EB2Fu);
+}
+RFX_HD uint32_t hash_lane_b(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t x = mum32(a ^ 0x7F4A7C15u, 0x2C1B3C6Du) ^ b;
+    x = mum32(x, 0x7FEB352Du) ^ c;
+    x = mum32(x, 0x846CA68Bu) ^ d;
+    return mum32(x, 0x165667B1u);
+}
+// k <= 31: table slot from the result; sub-class bits (24) from a second product of the same mixed word
+RFX_HD uint32_t narrow_hash(uint64_t key, uint32_t& cls) {
+    const uint32_t x = mum32((uint32_t)key ^ 0x9E3779B9u, 0x9E3779B1u) ^ (uint32_t)(key >> 32);
+    const uint64_t p = (uint64_t)x * 0x85EBCA77u;
+    cls = ((uint32_t)(p >> 32) * 0x27D4EB2Fu) >> 8;
+    return (uint32_t)p ^ (uint32_t)(p >> 32);
+}
+
 // Bin of a record = bin of its first k-mer (every k-mer of a record shares it).  Used by the receiving
 // side of a sharded run to re-group records that arrive as per-sender slices.
 template <int RECW> RFX_HD uint32_t rec_first_bin(const uint64_t* rec, const BinParams& P) {

@@ -62,43 +62,13 @@ struct CountArgs {
 
 constexpr int MAX_SEG = 64;
 
-// Hashing.  Every 32-bit word goes through a 32 x 32 -> 64-bit multiply whose halves are folded together ("mum"):
-// the high half carries the word's top bits down, so -- unlike a plain (word * odd) ^ ... chain, where a difference
-// in the top bits of one word can cancel a difference in the top bits of another -- related k-mers (a substitution
-// here, another 16 bases further on) do not collide systematically.  Only speed depends on the quality of these
-// hashes: equal hashes are always confirmed against the full record / key before anything is counted.
-__device__ __forceinline__ uint32_t mum32(uint32_t x, uint32_t c) {
-    const uint64_t p = (uint64_t)x * c;
-    return (uint32_t)p ^ (uint32_t)(p >> 32);
-}
-__device__ __forceinline__ uint32_t lane_a(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t x = mum32(a ^ 0x9E3779B9u, 0x9E3779B1u) ^ b;
-    x = mum32(x, 0x85EBCA77u) ^ c;
-    x = mum32(x, 0xC2B2AE3Du) ^ d;
-    return mum32(x, 0x27D4EB2Fu);
-}
-__device__ __forceinline__ uint32_t lane_b(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t x = mum32(a ^ 0x7F4A7C15u, 0x2C1B3C6Du) ^ b;
-    x = mum32(x, 0x7FEB352Du) ^ c;
-    x = mum32(x, 0x846CA68Bu) ^ d;
-    return mum32(x, 0x165667B1u);
-}
-
 // slot hash + tag of a whole record (tag 0 = empty slot)
 template <int RECW> __device__ __forceinline__ void record_hash(const uint64_t (&w)[RECW], uint32_t& slot_h, uint32_t& tag) {
-    uint32_t x = lane_a((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
-    if (RECW == 4) x = lane_b((uint32_t)w[2] ^ x, (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
+    uint32_t x = hash_lane_a((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
+    if (RECW == 4) x = hash_lane_b((uint32_t)w[2] ^ x, (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
     const uint64_t p = (uint64_t)x * 0xD3A2646Cu;
     slot_h = (uint32_t)p ^ (uint32_t)(p >> 32);
     tag = (uint32_t)(p >> 32) * 0xFD7046C5u | 1u;
-}
-
-// k <= 31: table slot from h; sub-class bits (24) from a second product of the same mixed word
-__device__ __forceinline__ uint32_t narrow_hash(uint64_t key, uint32_t& cls) {
-    const uint32_t x = mum32((uint32_t)key ^ 0x9E3779B9u, 0x9E3779B1u) ^ (uint32_t)(key >> 32);
-    const uint64_t p = (uint64_t)x * 0x85EBCA77u;
-    cls = ((uint32_t)(p >> 32) * 0x27D4EB2Fu) >> 8;
-    return (uint32_t)p ^ (uint32_t)(p >> 32);
 }
 
 // The shared-memory k-mer table of one CTA.
@@ -185,8 +155,8 @@ template <bool WIDE, int CAP, int PHASE> struct KmerSink {
     __device__ __forceinline__ void operator()(u128 key, uint32_t mult) const {
         const uint64_t hi = (uint64_t)(key >> 64), lo = (uint64_t)key;
         // two independent 32-bit lanes: slot = low bits of h1, class = its top bits, tag = h2
-        const uint32_t h1 = lane_a((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
-        const uint32_t h2 = lane_b((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+        const uint32_t h1 = hash_lane_a((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+        const uint32_t h2 = hash_lane_b((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
         if (depth != 0 && (h1 >> (32u - depth)) != cval) return;
         if (PHASE == 1) T.claim(key, h1, h2 | 1u);
         else T.count(key, h1, h2 | 1u, mult);
@@ -215,29 +185,18 @@ __device__ __forceinline__ void expand_warp(const uint64_t* w, uint32_t nk, uint
         const uint32_t pes = __shfl_sync(0xffffffffu, pe, s);
         const uint32_t ms = __shfl_sync(0xffffffffu, mult, s);
         const uint32_t off = t - pes;  // k-mer index inside the record
-        const uint32_t b = 16u + 2u * off;     // first bit of the k-mer in the record's bit stream
         if (!WIDE) {
-            const uint64_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
+            const uint64_t ws[2] = {__shfl_sync(0xffffffffu, w[0], s), __shfl_sync(0xffffffffu, w[1], s)};
             if (t < total) {
-                uint64_t hi;
-                if (b < 64u) hi = (w0 << b) | ((w1 >> 1) >> (63u - b));
-                else hi = w1 << (b - 64u);
-                const uint64_t fwd = hi >> (64 - 2 * k);
+                const uint64_t fwd = rec_kmer_at<uint64_t, 2>(ws, off, k);
                 const uint64_t rc = revcomp(fwd, k);
                 sink(fwd < rc ? fwd : rc, ms);
             }
         } else {
-            const uint64_t w0 = __shfl_sync(0xffffffffu, w[0], s), w1 = __shfl_sync(0xffffffffu, w[1], s);
-            const uint64_t w2 = __shfl_sync(0xffffffffu, w[2], s), w3 = __shfl_sync(0xffffffffu, w[3], s);
+            const uint64_t ws[4] = {__shfl_sync(0xffffffffu, w[0], s), __shfl_sync(0xffffffffu, w[1], s), __shfl_sync(0xffffffffu, w[2], s),
+                                    __shfl_sync(0xffffffffu, w[3], s)};
             if (t < total) {
-                // 128 bits starting at bit b of the 256-bit stream w0 w1 w2 w3
-                const uint32_t wi = b >> 6, sh = b & 63u;
-                const uint64_t a0 = wi == 0 ? w0 : wi == 1 ? w1 : wi == 2 ? w2 : w3;
-                const uint64_t a1 = wi == 0 ? w1 : wi == 1 ? w2 : wi == 2 ? w3 : 0ull;
-                const uint64_t a2 = wi == 0 ? w2 : wi == 1 ? w3 : 0ull;
-                const uint64_t hi = (a0 << sh) | ((a1 >> 1) >> (63u - sh));
-                const uint64_t lo = (a1 << sh) | ((a2 >> 1) >> (63u - sh));
-                const u128 fwd = (((u128)hi << 64) | lo) >> (128 - 2 * k);
+                const u128 fwd = rec_kmer_at<u128, 4>(ws, off, k);
                 const u128 rc = revcomp(fwd, k);
                 sink(fwd < rc ? fwd : rc, ms);  // forward on a tie (Counter64.java:686)
             }

@@ -190,6 +190,48 @@ void emu_fork_fetch(uint64_t* hi, uint64_t* lo, int32_t* left, int32_t* right) {
     }
 }
 
+// rec_kmer_at (the counting kernel's per-lane cut) against the rolling extraction, k-mer by k-mer; returns mismatches
+struct VecSink {
+    std::vector<u128>* v;
+    void operator()(uint64_t key) const { v->push_back((u128)key); }
+    void operator()(u128 key) const { v->push_back(key); }
+};
+int64_t emu_check_kmer_at(const uint64_t* recs, int64_t n_rec, int k) {
+    const int recw = rec_words_for_k(k);
+    int64_t bad = 0;
+    std::vector<u128> ref;
+    for (int64_t r = 0; r < n_rec; r++) {
+        const uint64_t* rec = recs + r * recw;
+        ref.clear();
+        const uint32_t nk = (uint32_t)(rec[0] >> 48);
+        if (recw == 2) {
+            rec_foreach_kmer<uint64_t, 2>(rec, k, VecSink{&ref});
+            const uint64_t w[2] = {rec[0], rec[1]};
+            for (uint32_t off = 0; off < nk; off++) {
+                const uint64_t f = rec_kmer_at<uint64_t, 2>(w, off, k), rc = revcomp(f, k);
+                if (off >= ref.size() || ref[off] != (u128)(f < rc ? f : rc)) bad++;
+            }
+        } else {
+            rec_foreach_kmer<u128, 4>(rec, k, VecSink{&ref});
+            const uint64_t w[4] = {rec[0], rec[1], rec[2], rec[3]};
+            for (uint32_t off = 0; off < nk; off++) {
+                const u128 f = rec_kmer_at<u128, 4>(w, off, k), rc = revcomp(f, k);
+                if (off >= ref.size() || ref[off] != (f < rc ? f : rc)) bad++;
+            }
+        }
+        if (ref.size() != nk) bad++;
+    }
+    return bad;
+}
+// the table hashes: out[0] = lane a, out[1] = lane b of the 128-bit key, out[2] = narrow_hash(lo), out[3] = its class bits
+void emu_table_hashes(uint64_t hi, uint64_t lo, uint32_t* out) {
+    out[0] = hash_lane_a((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+    out[1] = hash_lane_b((uint32_t)hi, (uint32_t)(hi >> 32), (uint32_t)lo, (uint32_t)(lo >> 32));
+    uint32_t cls = 0;
+    out[2] = narrow_hash(lo, cls);
+    out[3] = cls;
+}
+
 uint64_t emu_revcomp64(uint64_t x, int nb) { return revcomp(x, nb); }
 void emu_revcomp128(uint64_t hi, uint64_t lo, int nb, uint64_t* ohi, uint64_t* olo) {
     u128 r = revcomp(((u128)hi << 64) | lo, nb);

@@ -153,3 +153,46 @@ def test_canonical_assembly_vs_pass_simulation_on_clean_data(orc):
         assert any(c in f for f in fix)
     # same k-mer content: (#bases - (k-1)) summed over contigs = number of oriented k-mers
     assert sum(len(c) - 30 for c in fix) == sum(len(c) - 30 for c in b["asm"]["contigs"]) == len(a["forks"]["left"])
+
+
+@pytest.mark.parametrize("k,m", [(31, 11), (21, 9), (5, 5), (32, 11), (33, 16), (47, 11), (61, 11), (63, 13)])
+def test_flat_kmer_cut_equals_rolling_extraction(orc, hostemu, k, m):
+    """rec_kmer_at -- what a lane of the counting kernel's warp-wide expansion does -- against rec_foreach_kmer, on records
+    cut from long reads so that k = 32 reaches the last word of a 32-byte record (89 k-mers: bit offset 192)."""
+    txt = bytes(make_reads(5 + k, 3_000, 60, read_len=400, err=0.0, frag=600))
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    elen, woff, words = _pack(hostemu, txt, starts, lens, k)
+    recs, _ = _records(hostemu, elen, woff, words, k, m, 1)     # one bin: a read is one run, cut into full records
+    nk = (recs[:, 0] >> np.uint64(48)).astype(np.int64)
+    recw = recs.shape[1]
+    assert nk.max() == (recw * 64 - 16) // 2 - k + 1            # records of maximal length are among them
+    assert hostemu.emu_check_kmer_at(recs.ctypes.data, C.c_int64(len(recs)), k) == 0
+
+
+def test_table_hashes_do_not_cancel_top_bits(hostemu):
+    """Two 61-mers from the reference's example that differ in the top bits of two 32-bit words collided in BOTH hashes
+    of a plain (word * odd) ^ ... combination; the folded multiplies separate them, and close relatives in general."""
+    out = (C.c_uint32 * 4)()
+    def h(hi, lo):
+        hostemu.emu_table_hashes(C.c_uint64(hi), C.c_uint64(lo), out)
+        return tuple(out)
+    a = h(0x003bfa4dbcc08ba3, 0xdb2e38efd1733f32)
+    b = h(0x003bfa4dfcc08ba3, 0xdb2e38ef11733f32)
+    assert a[0] != b[0] and a[1] != b[1]
+    rng = np.random.default_rng(11)
+    seen_pair, seen_narrow = set(), set()
+    n = 0
+    for _ in range(300):
+        hi, lo = int(rng.integers(0, 1 << 58)), int(rng.integers(0, 1 << 63))
+        for w in range(4):                       # flip the top two bits of every 32-bit word, alone and in pairs
+            for w2 in range(w, 4):
+                dhi = ((3 << 30) << (32 * (w - 2))) if w >= 2 else 0
+                dlo = ((3 << 30) << (32 * w)) if w < 2 else 0
+                dhi ^= ((1 << 30) << (32 * (w2 - 2))) if w2 >= 2 else 0
+                dlo ^= ((1 << 30) << (32 * w2)) if w2 < 2 else 0
+                r = h(hi ^ dhi, lo ^ dlo)
+                seen_pair.add((r[0], r[1])); seen_narrow.add((r[2], r[3]))
+                n += 1
+    assert len(seen_pair) == n                   # no pair of relatives shares both table hashes
+    # the narrow hash only sees lo: of the ten variants per key, (0,2)/(0,3), (1,2)/(1,3) and (2,2)/(2,3)/(3,3) share lo
+    assert len(seen_narrow) == 300 * 6
