@@ -151,6 +151,24 @@ int rfx_contigs_copy(rfx_ctx* ctx, char* bases, uint64_t* offsets, int32_t* left
 int rfx_oriented_size(rfx_ctx* ctx, uint64_t* n);
 int rfx_oriented_copy(rfx_ctx* ctx, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right);
 
+/* ---- Count_<k>_sorted (the "left and right sorting" stage of the reference's multi-k workflows) ----
+ * Replaces ReflexivDSKmerLeftAndRightSorting.assemblyFromKmer() (pipeline/ReflexivDSKmerLeftAndRightSorting.java:105-243,
+ * called from pipeline/Pipelines.java:1309-1313): both orientations of every row of the context's count table go
+ * through that class's two fork filters (:432-537, :700-818) and every survivor becomes a row `KMER,1|left|right`
+ * (:249-274) with left / right in {-1, max_kmer_size + 3}.  The table is used as it stands: the caller applies the
+ * stage's `count <= maxcov` rule (:186-193) when it loads or counts (rfx_params.max_kmer_coverage).
+ *   min_error_coverage  param.minErrorCoverage (util/DefaultParam.java:106; Pipelines.java:1412-1416 sets 3 * cover for k >= 61)
+ *   min_repeat_fold     param.minRepeatFold    (util/DefaultParam.java:107: 1.5)
+ *   max_kmer_size       param.kmerListInt[last] (util/DefaultParam.java:87: 95 for the default list)
+ * RFX_E_UNSUPPORTED where the reference itself cannot run: min_error_coverage == 0, (k-1) % 31 == 0.
+ * Invalidates the results of rfx_assemble (the graph index and flag arrays are shared). */
+int rfx_sort_kmers(rfx_ctx* ctx, int32_t min_error_coverage, double min_repeat_fold, int32_t max_kmer_size);
+int rfx_sorted_size(rfx_ctx* ctx, uint64_t* n_rows);
+/* oriented k-mers (right-aligned, hi/lo halves) with their flags; caller buffers of n_rows elements each */
+int rfx_sorted_copy(rfx_ctx* ctx, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right);
+/* the CSV text of Count_<k>_sorted/part-*.csv, formatted on the device; out == NULL: size query */
+int rfx_sorted_csv(rfx_ctx* ctx, char* out, uint64_t cap, uint64_t* n_bytes);
+
 int rfx_stats(rfx_ctx* ctx, rfx_stats_t* out);
 
 /* ---- sharded counting (one context per GPU; the caller moves records between GPUs) ------------

@@ -54,6 +54,10 @@ def lib():
         L.orc_fork_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_void_p), C.c_void_p]
+        L.orc_sorted_rows.restype = C.c_int64
+        L.orc_sorted_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
+                                      C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p)]
         L.orc_assemble.restype = C.c_int
         L.orc_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.POINTER(_Contigs)]
@@ -127,6 +131,26 @@ def fork_filter(keys_hi, keys_lo, counts, k: int, min_error_cov: int = 8):
         raise ValueError(f"orc_fork_filter failed: {n}")
     return dict(keys_hi=_take(ph, n, np.uint64), keys_lo=_take(pl, n, np.uint64), left=_take(pL, n, np.int32),
                 right=_take(pR, n, np.int32), stats=dict(zip(FORK_STATS, stats.tolist())))
+
+
+def sorted_rows(keys_hi, keys_lo, counts, k: int, min_error_cov: int = 8, min_repeat_fold: float = 1.5,
+                max_kmer_size: int = 95, max_cov: int = 10_000_000):
+    """the rows of Count_<k>_sorted as dict(keys_hi, keys_lo, left, right), sorted by key."""
+    kh = np.ascontiguousarray(keys_hi, dtype=np.uint64)
+    kl = np.ascontiguousarray(keys_lo, dtype=np.uint64)
+    ct = np.ascontiguousarray(counts, dtype=np.uint32)
+    ph, pl, pL, pR = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n = lib().orc_sorted_rows(kh.ctypes.data, kl.ctypes.data, ct.ctypes.data, len(kh), k, min_error_cov, min_repeat_fold,
+                              max_kmer_size, max_cov, C.byref(ph), C.byref(pl), C.byref(pL), C.byref(pR))
+    if n < 0:
+        raise ValueError(f"orc_sorted_rows: outside the reference's working domain ({n})")
+    return dict(keys_hi=_take(ph, n, np.uint64), keys_lo=_take(pl, n, np.uint64), left=_take(pL, n, np.int32),
+                right=_take(pR, n, np.int32))
+
+
+def sorted_rows_text(res, k: int) -> str:
+    """`KMER,1|left|right\n` rows (DSBinaryFullKmerArrayToString, LeftAndRightSorting.java:249-274), sorted by key."""
+    return "".join(f"{decode_kmer(h, l, k)},1|{a}|{b}\n" for h, l, a, b in zip(res["keys_hi"], res["keys_lo"], res["left"], res["right"]))
 
 
 def assemble(keys_hi, keys_lo, left, right, k: int, min_contig: int = 500, mode: int = ASM_CANONICAL,

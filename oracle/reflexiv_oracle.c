@@ -466,6 +466,167 @@ int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
 }
 
 /* ------------------------------------------------------------------------ */
+/* Count_<k>_sorted, the "left and right sorting" stage          */
+/* pipeline/ReflexivDSKmerLeftAndRightSorting.java:105-243 (LRS below)         */
+/* ------------------------------------------------------------------------ */
+
+/* buildingAlongFromThreeInt, LRS:596-622: marker in the top two bits, the two
+ * covers as non-negative 32-bit halves (a negative value v is stored as
+ * 30000 - v, magnitudes saturate at 30000). */
+static int64_t lrs_build(int marker, int left, int right) {
+    int64_t info = (int64_t)((uint64_t)marker << 62);
+    if (left >= 30000) left = 30000; else if (left <= -30000) left = 30000 - (-30000); else if (left < 0) left = 30000 - left;
+    if (right >= 30000) right = 30000; else if (right <= -30000) right = 30000 - (-30000); else if (right < 0) right = 30000 - right;
+    info |= (int64_t)left << 32;
+    info |= (int64_t)right;
+    return info;
+}
+static int lrs_marker(int64_t a) { return (int)((uint64_t)a >> 62); }            /* getReflexivMarker, LRS:569-572 */
+static int lrs_left(int64_t a) {                                                   /* getLeftMarker, LRS:574-584 */
+    int v = (int)((uint64_t)a >> 32);
+    v &= ~(3 << 30);
+    if (v > 30000) v = 30000 - v;
+    return v;
+}
+static int lrs_right(int64_t a) {                                                  /* getRightMarker, LRS:586-594 */
+    int v = (int)a;
+    if (v > 30000) v = 30000 - v;
+    return v;
+}
+
+typedef struct { u128 key; int64_t attr; } lrs_t;
+static int lrs_cmp_key(const void *a, const void *b) {
+    u128 x = ((const lrs_t *)a)->key, y = ((const lrs_t *)b)->key;
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+static int lrs_cmp_rot(const void *a, const void *b) {
+    u128 x = rot_key(((const lrs_t *)a)->key, g_rot_k), y = rot_key(((const lrs_t *)b)->key, g_rot_k);
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+
+/* Input: the (k-mer, count) rows of a Count_<k> table.  Output: the rows of Count_<k>_sorted as (oriented k-mer,
+ * left, right), sorted by key; the reference prints them as `KMER,1|left|right` (LRS:249-274).  Rows above
+ * max_cov are dropped (LRS:186-193: the lower bound is commented out there).  X = max_kmer_size + 3 with
+ * max_kmer_size = param.kmerListInt[last] (LRS:445).  E == 0 selects DSFilterForkSubKmer, which reads a five-column
+ * row out of a three-column dataset and cannot run in the reference: rejected.  k-mers with (k-1) % 31 == 0 lose
+ * their last base in DSForwardSubKmerExtraction (LRS:930-936 takes the wrong block): rejected. */
+int64_t orc_sorted_rows(const uint64_t *keys_hi, const uint64_t *keys_lo, const uint32_t *counts, int64_t n, int k,
+                        int min_error_cov, double min_repeat_fold, int max_kmer_size, int64_t max_cov,
+                        uint64_t **o_hi, uint64_t **o_lo, int32_t **o_left, int32_t **o_right) {
+    if (k < 2 || k > 63 || min_error_cov == 0 || (k - 1) % 31 == 0) return -1;
+    const int E = min_error_cov, X = max_kmer_size + 3;
+    const double F = min_repeat_fold;
+    lrs_t *a = (lrs_t *)malloc((size_t)(n > 0 ? 2 * n : 1) * sizeof(lrs_t));
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if ((int64_t)counts[i] > max_cov) continue;
+        /* DSKmerReverseComplement, LRS:1583-1632: the k-mer, then its reverse complement, same cover;
+         * DSForwardSubKmerExtraction, LRS:915-978: attribute (1, cover, cover) */
+        u128 key = mk128(keys_hi[i], keys_lo[i]);
+        a[m].key = key; a[m].attr = lrs_build(1, (int)counts[i], (int)counts[i]); m++;
+        a[m].key = revcomp(key, k); a[m].attr = a[m - 1].attr; m++;
+    }
+    /* sort("k-1"), LRS:202; canonical order inside a group: ascending last base */
+    qsort(a, (size_t)m, sizeof(lrs_t), lrs_cmp_key);
+    /* DSFilterForkSubKmerWithErrorCorrection, LRS:432-537 */
+    int64_t w = 0;
+    for (int64_t i = 0; i < m;) {
+        int64_t j = i + 1;
+        u128 prefix = a[i].key >> 2;
+        while (j < m && (a[j].key >> 2) == prefix) j++;
+        lrs_t cur = a[i];
+        cur.attr = lrs_build(lrs_marker(a[i].attr), lrs_left(a[i].attr), -1);
+        for (int64_t x = i + 1; x < j; x++) {
+            int marker = lrs_marker(a[x].attr), leftMarker = lrs_left(a[x].attr);
+            int highest = lrs_left(cur.attr);
+            if (leftMarker > highest) {
+                int64_t attr;
+                if (highest <= E && leftMarker >= F * highest) attr = lrs_build(marker, leftMarker, -1);
+                else if (highest == 1) attr = lrs_build(marker, leftMarker, -1);
+                else attr = lrs_build(marker, leftMarker, max_kmer_size + 3);
+                cur = a[x]; cur.attr = attr;
+            } else if (leftMarker == highest) {
+                /* extension = last base left-aligned + end marker: the larger base wins (LRS:473) */
+                if ((a[x].key & 3) > (cur.key & 3)) {
+                    cur = a[x];
+                    cur.attr = lrs_build(marker, leftMarker, highest == 1 ? -1 : X);
+                } else {
+                    cur.attr = lrs_build(lrs_marker(cur.attr), lrs_left(cur.attr), highest == 1 ? -1 : X);
+                }
+            } else {
+                if (leftMarker <= E && highest >= F * leftMarker) {
+                    cur.attr = lrs_build(lrs_marker(cur.attr), lrs_left(cur.attr), -1);
+                } else {
+                    /* LRS:504-518: the attribute is built from the ARRIVING row's markers before the stored row is
+                     * read back, so the stored k-mer continues with the weaker row's coverage */
+                    cur.attr = lrs_build(marker, leftMarker, leftMarker == 1 ? -1 : X);
+                }
+            }
+        }
+        a[w++] = cur;
+        i = j;
+    }
+    m = w;
+    /* DSReflectedSubKmerExtractionFromForward, LRS:1109-1178: key on the suffix, marker 2; sort("k-1"), LRS:217 */
+    for (int64_t i = 0; i < m; i++) a[i].attr = lrs_build(2, lrs_left(a[i].attr), lrs_right(a[i].attr));
+    g_rot_k = k;
+    qsort(a, (size_t)m, sizeof(lrs_t), lrs_cmp_rot);
+    /* DSFilterForkReflectedSubKmerWithErrorCorrection, LRS:700-818 */
+    const u128 sufmask = mask_bases(k - 1);
+    w = 0;
+    for (int64_t i = 0; i < m;) {
+        int64_t j = i + 1;
+        u128 suffix = a[i].key & sufmask;
+        while (j < m && (a[j].key & sufmask) == suffix) j++;
+        lrs_t cur = a[i];
+        int HC = lrs_left(a[i].attr); /* HighCoverLastCoverage */
+        cur.attr = lrs_build(lrs_marker(a[i].attr), -1, lrs_right(a[i].attr));
+        for (int64_t x = i + 1; x < j; x++) {
+            int marker = lrs_marker(a[x].attr), leftMarker = lrs_left(a[x].attr), rightMarker = lrs_right(a[x].attr);
+            if (leftMarker > HC) {
+                int64_t attr;
+                if (HC <= E && leftMarker >= F * HC) attr = lrs_build(marker, -1, rightMarker);
+                else attr = lrs_build(marker, X, rightMarker);
+                HC = leftMarker;
+                cur = a[x]; cur.attr = attr;
+            } else if (leftMarker == HC) {
+                unsigned fx = (unsigned)(a[x].key >> (2 * (k - 1))) & 3u, fc = (unsigned)(cur.key >> (2 * (k - 1))) & 3u;
+                if (((fx << 2) | 1u) > ((fc << 2) | 1u)) { /* first base + end marker, LRS:746-751 */
+                    cur = a[x];
+                    cur.attr = lrs_build(marker, X, HC == 1 ? -1 : rightMarker);
+                } else {
+                    cur.attr = lrs_build(lrs_marker(cur.attr), X, lrs_right(cur.attr));
+                }
+            } else {
+                if (leftMarker <= E && HC >= F * leftMarker) {
+                    cur.attr = lrs_build(lrs_marker(cur.attr), -1, lrs_right(cur.attr));
+                } else {
+                    /* LRS:790-806: built from the arriving row's right marker, then stored on the kept k-mer */
+                    cur.attr = lrs_build(marker, X, leftMarker == 1 ? -1 : rightMarker);
+                }
+            }
+        }
+        a[w++] = cur;
+        i = j;
+    }
+    m = w;
+    /* DSSubKmerToFullKmer, LRS:1321-1346: full k-mer, marker 1 */
+    qsort(a, (size_t)m, sizeof(lrs_t), lrs_cmp_key);
+    *o_hi = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
+    *o_lo = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
+    *o_left = (int32_t *)malloc((size_t)(m ? m : 1) * sizeof(int32_t));
+    *o_right = (int32_t *)malloc((size_t)(m ? m : 1) * sizeof(int32_t));
+    for (int64_t i = 0; i < m; i++) {
+        (*o_hi)[i] = (uint64_t)(a[i].key >> 64);
+        (*o_lo)[i] = (uint64_t)a[i].key;
+        (*o_left)[i] = lrs_left(a[i].attr);
+        (*o_right)[i] = lrs_right(a[i].attr);
+    }
+    free(a);
+    return m;
+}
+
+/* ------------------------------------------------------------------------ */
 /* A9 + A10: extension                                                       */
 /* ------------------------------------------------------------------------ */
 

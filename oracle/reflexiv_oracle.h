@@ -55,6 +55,15 @@ int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
                         int64_t n, int k, int min_error_cov, uint64_t **o_hi, uint64_t **o_lo,
                         int32_t **o_left, int32_t **o_right, int64_t *stats /* [8] */);
 
+/* Count_<k>_sorted ------------------------------------------- */
+/* pipeline/ReflexivDSKmerLeftAndRightSorting.java:105-243: both orientations of every row with count <= max_cov
+ * through that class's two fork filters (flags -1 / max_kmer_size + 3, coverages saturating at 30000).  Output
+ * sorted by key; the reference writes the rows as `KMER,1|left|right`.  Returns -1 outside the reference's working
+ * domain (min_error_cov == 0, (k-1) % 31 == 0, k > 63). */
+int64_t orc_sorted_rows(const uint64_t *keys_hi, const uint64_t *keys_lo, const uint32_t *counts, int64_t n, int k,
+                        int min_error_cov, double min_repeat_fold, int max_kmer_size, int64_t max_cov,
+                        uint64_t **o_hi, uint64_t **o_lo, int32_t **o_left, int32_t **o_right);
+
 /* Extension (A9 + A10) ---------------------------------------------------- */
 enum {
     ORC_ASM_CANONICAL = 0, /* fixed point: maximal chains over mergeable junctions */

@@ -59,6 +59,10 @@ SYMBOLS = {
     "rfx_contigs_copy": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfx_oriented_size": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rfx_oriented_copy": (C.c_int, [_P, _P, _P, _P, _P]),
+    "rfx_sort_kmers": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32]),
+    "rfx_sorted_size": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "rfx_sorted_copy": (C.c_int, [_P, _P, _P, _P, _P]),
+    "rfx_sorted_csv": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rfx_stats": (C.c_int, [_P, C.POINTER(RfxStats)]),
     "rfx_partition": (C.c_int, [_P, C.c_int32, C.c_uint32]),
     "rfx_choose_bins": (C.c_uint32, [_P, C.c_uint64, C.c_int32]),

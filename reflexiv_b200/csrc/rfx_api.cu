@@ -63,7 +63,7 @@ static void free_all(Ctx* c) {
     DevBuf* all[] = {&c->text, &c->line_start, &c->line_at, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
                      &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->ad[0],
                      &c->ad[1], &c->open_next, &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
-                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->gs_next, &c->gs_len, &c->gs_tails, &c->gs_heads, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom};
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->gs_next, &c->gs_len, &c->gs_tails, &c->gs_heads, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom, &c->srt_left, &c->srt_right};
     for (DevBuf* b : all) devbuf_free(*b);
 }
 
@@ -117,6 +117,46 @@ template <class KT> struct OrientedOut {
         lo[excl] = (uint64_t)wide;
         left[excl] = lflag[x];
         right[excl] = rflag[x];
+    }
+};
+
+// ---- Count_<k>_sorted rows: "KMER,1|left|right\n" (DSBinaryFullKmerArrayToString, ReflexivDSKmerLeftAndRightSorting.java:249-274;
+// DSSubKmerToFullKmer sets every marker to 1, :1323) ----
+__device__ __forceinline__ uint32_t dec_width(int32_t v) { return v < 0 ? 1u + dec_digits((uint32_t)(-(int64_t)v)) : dec_digits((uint32_t)v); }
+__device__ __forceinline__ char* put_dec(char* p, int32_t v) {
+    if (v < 0) *p++ = '-';
+    uint32_t u = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+    const uint32_t d = dec_digits(u);
+    for (int j = (int)d - 1; j >= 0; j--) { p[j] = (char)('0' + u % 10); u /= 10; }
+    return p + d;
+}
+struct SortedCsvIn {
+    const uint8_t* alive;
+    const int32_t* left;
+    const int32_t* right;
+    int k;
+    __device__ __forceinline__ uint64_t operator()(uint64_t x) const {
+        return (alive[x] & 2) ? (uint64_t)k + 3 + dec_width(left[x]) + 1 + dec_width(right[x]) + 1 : 0;
+    }
+};
+template <class KT> struct SortedCsvOut {
+    const KT* keys;
+    const int32_t* left;
+    const int32_t* right;
+    int k;
+    char* out;
+    __device__ __forceinline__ void operator()(uint64_t x, uint64_t excl, uint64_t len) const {
+        if (!len) return;
+        char* p = out + excl;
+        KT key = keys[x >> 1];
+        if (x & 1) key = revcomp(key, k);
+        for (int j = 0; j < k; j++) p[j] = "ACGT"[(uint32_t)(key >> (2 * (k - 1 - j))) & 3u];
+        p += k;
+        *p++ = ','; *p++ = '1'; *p++ = '|';
+        p = put_dec(p, left[x]);
+        *p++ = '|';
+        p = put_dec(p, right[x]);
+        *p = '\n';
     }
 };
 
@@ -208,7 +248,7 @@ int rfx_reset(rfx_ctx* c) {
     c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
     c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0; c->sp_active = false;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
-    c->have_contigs = false;
+    c->have_contigs = false; c->have_sorted = false;
     c->rx_bytes = 0; c->shard_id = -1; c->n_seg = 0;
     for (float& m : c->ms) m = 0;
     return RFX_OK;
@@ -217,7 +257,7 @@ int rfx_reset(rfx_ctx* c) {
 int rfx_push_fastq_device(rfx_ctx* c, const uint8_t* d_buf, size_t len) {
     if (!c || (!d_buf && len)) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->sp_active = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; c->sp_active = false;
     return stage_parse_fastq(c, d_buf, len, true, false);
 }
 
@@ -228,7 +268,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     if (!c || (!buf && len)) return RFX_E_INVALID;
     if (len == 0) return RFX_OK;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false;
     RFX_TRY(devbuf_reserve(c, c->text, len + 128));
     uint8_t* d_text = c->text.as<uint8_t>();
     // chunk boundaries: just behind a newline; the last chunk keeps at least two lines
@@ -284,7 +324,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
 int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {
     if (!c || !offsets || (!bases && n_reads && offsets[n_reads])) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->sp_active = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; c->sp_active = false;
     return stage_push_reads(c, bases, offsets, n_reads);
 }
 
@@ -373,7 +413,7 @@ int rfx_load_counts(rfx_ctx* c, const uint64_t* keys, const uint32_t* counts, ui
     c->n_rows = n_rows;
     c->table_cap = n_rows + 1;
     c->have_counts = true;
-    c->have_contigs = false;
+    c->have_contigs = false; c->have_sorted = false;
     return RFX_OK;
 }
 
@@ -445,12 +485,12 @@ int rfx_oriented_size(rfx_ctx* c, uint64_t* n) {
     return RFX_OK;
 }
 
-int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right) {
-    if (!c || !keys_hi || !keys_lo || !left || !right) return RFX_E_INVALID;
-    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no graph (call rfx_assemble)");
+// survivors (alive & 2) with their two flags, in oid order
+static int copy_survivors(Ctx* c, const char* who, uint64_t m, const int32_t* d_lflag, const int32_t* d_rflag, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left,
+                          int32_t* right) {
     cudaSetDevice(c->prm.device);
     cudaStream_t st = c->stream;
-    const uint64_t n = 2 * c->n_rows, m = c->n_oriented;
+    const uint64_t n = 2 * c->n_rows;
     if (m == 0) return RFX_OK;
     ScanPlan<uint64_t> plan;
     RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n) * sizeof(uint64_t)));
@@ -463,10 +503,8 @@ int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t*
     uint64_t* d_lo = d_hi + m;
     int32_t* d_l = reinterpret_cast<int32_t*>(d_lo + m);
     int32_t* d_r = d_l + m;
-    if (!c->wide)
-        scan_apply(plan, in, OrientedOut<uint64_t>{c->keys.as<uint64_t>(), c->k, c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
-    else
-        scan_apply(plan, in, OrientedOut<u128>{c->keys.as<u128>(), c->k, c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
+    if (!c->wide) scan_apply(plan, in, OrientedOut<uint64_t>{c->keys.as<uint64_t>(), c->k, d_lflag, d_rflag, d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
+    else scan_apply(plan, in, OrientedOut<u128>{c->keys.as<u128>(), c->k, d_lflag, d_rflag, d_hi, d_lo, d_l, d_r}, OpAddU64{}, (uint64_t)0, st);
     c->launches += 2 * plan.levels + 1;
     cudaMemcpyAsync(keys_hi, d_hi, m * 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(keys_lo, d_lo, m * 8, cudaMemcpyDeviceToHost, st);
@@ -474,7 +512,64 @@ int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t*
     cudaMemcpyAsync(right, d_r, m * 4, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     devbuf_free(tmp);
-    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rfx_oriented_copy: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "%s: %s", who, cudaGetErrorString(e));
+    return RFX_OK;
+}
+
+int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right) {
+    if (!c || !keys_hi || !keys_lo || !left || !right) return RFX_E_INVALID;
+    if (!c->have_contigs) return ctx_fail(c, RFX_E_STATE, "no graph (call rfx_assemble)");
+    return copy_survivors(c, "rfx_oriented_copy", c->n_oriented, c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), keys_hi, keys_lo, left, right);
+}
+
+// ---- Count_<k>_sorted (ReflexivDSKmerLeftAndRightSorting.java:105-243) ----
+int rfx_sort_kmers(rfx_ctx* c, int32_t min_error_coverage, double min_repeat_fold, int32_t max_kmer_size) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    return stage_sorted(c, min_error_coverage, min_repeat_fold, max_kmer_size);
+}
+
+int rfx_sorted_size(rfx_ctx* c, uint64_t* n_rows) {
+    if (!c || !n_rows) return RFX_E_INVALID;
+    if (!c->have_sorted) return ctx_fail(c, RFX_E_STATE, "no sorted rows (call rfx_sort_kmers)");
+    *n_rows = c->n_sorted;
+    return RFX_OK;
+}
+
+int rfx_sorted_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t* left, int32_t* right) {
+    if (!c || !keys_hi || !keys_lo || !left || !right) return RFX_E_INVALID;
+    if (!c->have_sorted) return ctx_fail(c, RFX_E_STATE, "no sorted rows (call rfx_sort_kmers)");
+    return copy_survivors(c, "rfx_sorted_copy", c->n_sorted, c->srt_left.as<int32_t>(), c->srt_right.as<int32_t>(), keys_hi, keys_lo, left, right);
+}
+
+int rfx_sorted_csv(rfx_ctx* c, char* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!c || !n_bytes) return RFX_E_INVALID;
+    if (!c->have_sorted) return ctx_fail(c, RFX_E_STATE, "no sorted rows (call rfx_sort_kmers)");
+    cudaSetDevice(c->prm.device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows;
+    if (c->n_sorted == 0) { *n_bytes = 0; return RFX_OK; }
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n) * sizeof(uint64_t)));
+    plan.bind(n, c->scan_ws.as<uint64_t>());
+    SortedCsvIn in{c->alive.as<uint8_t>(), c->srt_left.as<int32_t>(), c->srt_right.as<int32_t>(), c->k};
+    scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 2 * plan.levels;
+    uint64_t total = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&total, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    RFX_CUDA(c, cudaStreamSynchronize(st));
+    *n_bytes = total;
+    if (!out) return RFX_OK;
+    if (cap < total) return ctx_fail(c, RFX_E_INVALID, "rfx_sorted_csv: buffer of %llu bytes, need %llu", (unsigned long long)cap, (unsigned long long)total);
+    DevBuf txt;
+    RFX_TRY(devbuf_reserve(c, txt, total + 16));
+    if (!c->wide) scan_apply(plan, in, SortedCsvOut<uint64_t>{c->keys.as<uint64_t>(), c->srt_left.as<int32_t>(), c->srt_right.as<int32_t>(), c->k, txt.as<char>()}, OpAddU64{}, (uint64_t)0, st);
+    else scan_apply(plan, in, SortedCsvOut<u128>{c->keys.as<u128>(), c->srt_left.as<int32_t>(), c->srt_right.as<int32_t>(), c->k, txt.as<char>()}, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 1;
+    cudaError_t e = cudaMemcpyAsync(out, txt.p, total, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    devbuf_free(txt);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rfx_sorted_csv: %s", cudaGetErrorString(e));
     return RFX_OK;
 }
 
@@ -519,7 +614,7 @@ int rfx_begin_shard(rfx_ctx* c, int32_t shard_id, int32_t n_shards, uint32_t n_b
         return c ? ctx_fail(c, RFX_E_INVALID, "rfx_begin_shard: bad shard geometry") : RFX_E_INVALID;
     c->shard_id = shard_id; c->n_shards = n_shards; c->forced_bins = n_bins_total;
     c->rx_bytes = 0; c->n_seg = 0;
-    c->have_records = false; c->have_counts = false; c->have_contigs = false;
+    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false;
     return RFX_OK;
 }
 
@@ -570,7 +665,7 @@ int rfx_load_counts_device(rfx_ctx* c, const void* d_keys, const uint32_t* d_cou
     c->n_rows = base + n_rows;
     c->table_cap = c->n_rows + 1;
     c->have_counts = true;
-    c->have_contigs = false;
+    c->have_contigs = false; c->have_sorted = false;
     return RFX_OK;
 }
 

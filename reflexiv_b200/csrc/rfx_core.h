@@ -401,6 +401,75 @@ RFX_HD ForkResult left_fork(const uint32_t cnt[4], int E, int sub) {
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fork filters of the "left and right sorting" stage that writes Count_<k>_sorted
+// (ReflexivDSKmerLeftAndRightSorting.java:105-243).  Same scan as A7 / A8, other flags:
+// a clean end is -1, a fork winner is X = (largest k of the k-mer list) + 3, coverages saturate at
+// 30000 (buildingAlongFromThreeInt, :596-622), an error needs `fold` times the coverage
+// (param.minRepeatFold) and coverage 1 is always an error.  Two quirks of the reference are kept:
+// when a weaker, non-error row arrives the stored row takes over the ARRIVING row's coverage in the
+// right filter (:504-518: the attribute is built before the stored row is re-read) and the arriving
+// row's right flag in the left filter (:790-806).  Candidates are visited in ascending base order,
+// the same canonical resolution of Spark's arrival order as above.
+// ---------------------------------------------------------------------------------------------
+struct SortedFork {
+    int winner;           // base (0..3) of the surviving candidate, -1 if the group is empty
+    int32_t left, right;  // right filter: coverage carried on, right flag; left filter: left flag, right flag
+};
+RFX_HD int32_t sorted_cov(uint32_t count) { return count >= 30000u ? 30000 : (int32_t)count; }
+
+// DSFilterForkSubKmerWithErrorCorrection, ReflexivDSKmerLeftAndRightSorting.java:432-537
+RFX_HD SortedFork sorted_right_fork(const uint32_t cnt[4], const bool dup[4], int E, double fold, int X) {
+    SortedFork r; r.winner = -1; r.left = 0; r.right = 0;
+    for (int b = 0; b < 4; b++) {
+        if (!cnt[b]) continue;
+        const int reps = dup[b] ? 2 : 1;
+        for (int rep = 0; rep < reps; rep++) {
+            const int32_t c = sorted_cov(cnt[b]);
+            if (r.winner < 0) { r.winner = b; r.left = c; r.right = -1; continue; }
+            const int32_t h = r.left;
+            if (c > h) {
+                r.right = (h <= E && (double)c >= fold * (double)h) ? -1 : (h == 1 ? -1 : X);
+                r.winner = b; r.left = c;
+            } else if (c == h) {
+                if (b > r.winner) r.winner = b;
+                r.right = h == 1 ? -1 : X;
+            } else if (c <= E && (double)h >= fold * (double)c) {
+                r.right = -1;
+            } else {
+                r.left = c;
+                r.right = c == 1 ? -1 : X;
+            }
+        }
+    }
+    return r;
+}
+
+// DSFilterForkReflectedSubKmerWithErrorCorrection, ReflexivDSKmerLeftAndRightSorting.java:700-818.
+// cov[a] = coverage the right filter left on the candidate with first base a (0 = absent), rfl[a] = its right flag.
+RFX_HD SortedFork sorted_left_fork(const int32_t cov[4], const int32_t rfl[4], int E, double fold, int X) {
+    SortedFork r; r.winner = -1; r.left = 0; r.right = 0;
+    int32_t H = 0;  // HighCoverLastCoverage
+    for (int a = 0; a < 4; a++) {
+        if (!cov[a]) continue;
+        const int32_t c = cov[a];
+        if (r.winner < 0) { r.winner = a; H = c; r.left = -1; r.right = rfl[a]; continue; }
+        if (c > H) {
+            r.left = (H <= E && (double)c >= fold * (double)H) ? -1 : X;
+            r.right = rfl[a]; r.winner = a; H = c;
+        } else if (c == H) {
+            r.winner = a; r.left = X;  // the larger first base wins (:746-756), which is the arriving one
+            r.right = H == 1 ? -1 : rfl[a];
+        } else if (c <= E && (double)H >= fold * (double)c) {
+            r.left = -1;
+        } else {
+            r.left = X;
+            r.right = c == 1 ? -1 : rfl[a];
+        }
+    }
+    return r;
+}
+
 // A junction X -> Y is merged when the reflected record's right flag and the forward record's left
 // flag are both negative or both non-negative (ReflexivDSMain.java:3069-3075, 1809-1815).  Mixed-sign
 // ("budget") junctions stay open: canonical resolution, DESIGN.md.

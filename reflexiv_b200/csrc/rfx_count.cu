@@ -749,7 +749,7 @@ int stage_count(Ctx* c) {
         return ctx_fail(c, RFX_E_STATE, "internal: counted %llu k-mer instances, extracted %llu", (unsigned long long)h[DS_INSTANCES],
                         (unsigned long long)c->n_instances);
     c->have_counts = true;
-    c->have_contigs = false;
+    c->have_contigs = false; c->have_sorted = false;
     return RFX_OK;
 }
 

@@ -227,6 +227,73 @@ __global__ void left_filter_kernel(Graph<KT> G, int E, uint8_t* alive, int32_t* 
     }
 }
 
+// ---- Count_<k>_sorted: the fork filters of ReflexivDSKmerLeftAndRightSorting.java ----------------
+// Same probing as A7 / A8; what differs is the rule (sorted_right_fork / sorted_left_fork, rfx_core.h) and that the
+// left filter needs, from every candidate, the coverage and the right flag the right filter left on it.
+template <class KT>
+__global__ void sorted_right_kernel(Graph<KT> G, int E, double fold, int X, uint8_t* __restrict__ alive, int32_t* __restrict__ cov, int32_t* __restrict__ rflag,
+                                    uint64_t n) {
+    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(oid >> 1);
+        const KT key = G.keys[row];
+        const KT rc = revcomp(key, G.k);
+        if ((oid & 1u) && rc == key) { alive[oid] = 0; continue; }  // palindrome: one node, not two
+        const KT Xk = (oid & 1u) ? rc : key;
+        const KT prefix = Xk >> 2;
+        const uint32_t myb = (uint32_t)Xk & 3u;
+        uint32_t pre_min = 0, suf_min = 0;
+        if (G.g_bins > 1) G.minima(Xk, pre_min, suf_min);
+        uint32_t cnt[4];
+        bool dup[4];
+#pragma unroll
+        for (uint32_t b = 0; b < 4; b++) {
+            if (b == myb) { cnt[b] = G.counts[row]; dup[b] = (rc == key); }
+            else {
+                const KT Z = (prefix << 2) | (KT)b;
+                const KT zc = revcomp(Z, G.k);
+                const uint32_t hl = G.g_bins > 1 ? G.last_mm(prefix, b) : 0u;
+                const uint32_t r = G.lookup(zc < Z ? zc : Z, hl < pre_min ? hl : pre_min);
+                cnt[b] = r == NONE32 ? 0u : G.counts[r];
+                dup[b] = (Z == zc);
+            }
+        }
+        const SortedFork res = sorted_right_fork(cnt, dup, E, fold, X);
+        const bool won = res.winner == (int)myb;
+        alive[oid] = won ? 1 : 0;
+        if (won) { cov[oid] = res.left; rflag[oid] = res.right; }
+    }
+}
+
+template <class KT>
+__global__ void sorted_left_kernel(Graph<KT> G, int E, double fold, int X, uint8_t* alive, const int32_t* __restrict__ cov, const int32_t* __restrict__ rflag,
+                                   int32_t* __restrict__ out_left, int32_t* __restrict__ out_right, uint64_t n) {
+    const int top = 2 * (G.k - 1);
+    const KT sufmask = mask_bases<KT>(G.k - 1);
+    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[oid] & 1)) continue;
+        const KT Xk = G.oriented((uint32_t)oid);
+        const KT suffix = Xk & sufmask;
+        const uint32_t mya = (uint32_t)(Xk >> top) & 3u;
+        uint32_t pre_min = 0, suf_min = 0;
+        if (G.g_bins > 1) G.minima(Xk, pre_min, suf_min);
+        int32_t cv[4], rf[4];
+#pragma unroll
+        for (uint32_t a = 0; a < 4; a++) {
+            if (a == mya) { cv[a] = cov[oid]; rf[a] = rflag[oid]; }
+            else {
+                uint32_t cz = 0;
+                const uint32_t hf = G.g_bins > 1 ? G.first_mm(suffix, a) : 0u;
+                const uint32_t oz = G.find(((KT)a << top) | suffix, hf < suf_min ? hf : suf_min, &cz);
+                const bool there = oz != NONE32 && (alive[oz] & 1);
+                cv[a] = there ? cov[oz] : 0;
+                rf[a] = there ? rflag[oz] : 0;
+            }
+        }
+        const SortedFork res = sorted_left_fork(cv, rf, E, fold, X);
+        if (res.winner == (int)mya) { alive[oid] = 3; out_left[oid] = res.left; out_right[oid] = res.right; }  // bit 0 stays: others still read it
+    }
+}
+
 // Neighbour links.  succ/pred are preset to NONE32.  On one GPU a node writes its successor's pred[]; in a sharded
 // run (SHARDED) a node may only write its own entries, so it finds its predecessor itself (4 more probes) and reads
 // the neighbour's flag signs from the alive byte.
@@ -507,6 +574,11 @@ __global__ void gather_contigs_kernel(Graph<KT> G, const uint8_t* __restrict__ a
 __global__ void set_u64_kernel(uint64_t* p, const U64x3* tot) { *p = tot->b; }
 __global__ void set_value_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
+struct AliveBoth {
+    const uint8_t* alive;
+    __device__ __forceinline__ uint64_t operator()(uint64_t x) const { return (alive[x] & 2) ? 1 : 0; }
+};
+
 static unsigned grid_n(uint64_t n) {
     uint64_t g = (n + 255) / 256;
     if (g < 1) g = 1;
@@ -575,6 +647,7 @@ template <class KT> static int graph_impl(Ctx* c) {
     uint64_t h[DS_NSLOTS];
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
     c->n_oriented = c->n_budget = c->n_budget_adm = c->n_cycles = c->n_contigs = c->n_contig_bases = 0;
+    c->have_sorted = false;  // index, alive bytes and flag arrays are rebuilt below
     if (n_rows == 0) {
         RFX_TRY(devbuf_reserve(c, c->ctg_off, sizeof(uint64_t)));
         RFX_CUDA(c, cudaMemsetAsync(c->ctg_off.p, 0, sizeof(uint64_t), st));
@@ -955,7 +1028,7 @@ template <class KT> static int gs_begin_impl(Ctx* c) {
     c->launches += 2;
     RFX_TRY(gs_sync(c, "sharded right filter"));
     c->ms[3] += stage_end(c);
-    c->have_contigs = false;
+    c->have_contigs = false; c->have_sorted = false;
     return RFX_OK;
 }
 
@@ -1170,6 +1243,56 @@ int stage_gs_contigs(Ctx* c, const void* tails, uint64_t n_tails, const void* he
     c->gs_step = 5;
     return c->wide ? gs_contigs_impl<u128>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads)
                    : gs_contigs_impl<uint64_t>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads);
+}
+
+template <class KT> static int sorted_impl(Ctx* c, int E, double fold, int X) {
+    cudaStream_t st = c->stream;
+    const uint64_t n = 2 * c->n_rows;
+    c->n_sorted = 0;
+    c->have_contigs = false;  // the index, the alive bytes and the flag arrays are taken over
+    if (n == 0) { c->have_sorted = true; return RFX_OK; }
+    if (n >= 0xffffffffull) return ctx_fail(c, RFX_E_CAPACITY, "more than 2^31 rows: oriented ids do not fit 32 bits");
+    stage_begin(c);
+    RFX_TRY(devbuf_reserve(c, c->rflag, n * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->lflag, n * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->alive, n));
+    RFX_TRY(devbuf_reserve(c, c->srt_left, n * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, c->srt_right, n * sizeof(int32_t)));
+    RFX_TRY(build_index<KT>(c));
+    Graph<KT> G = make_graph<KT>(c);
+    uint8_t* alive = c->alive.as<uint8_t>();
+    int32_t* cov = c->lflag.as<int32_t>();
+    int32_t* rflag = c->rflag.as<int32_t>();
+    sorted_right_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, fold, X, alive, cov, rflag, n);
+    sorted_left_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, fold, X, alive, cov, rflag, c->srt_left.as<int32_t>(), c->srt_right.as<int32_t>(), n);
+    c->launches += 2;
+    // survivors
+    ScanPlan<uint64_t> plan;
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n) * sizeof(uint64_t)));
+    plan.bind(n, c->scan_ws.as<uint64_t>());
+    scan_prepare(plan, AliveBoth{alive}, OpAddU64{}, (uint64_t)0, st);
+    c->launches += 2 * plan.levels;
+    uint64_t total = 0;
+    RFX_CUDA(c, cudaMemcpyAsync(&total, plan.total, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "sorted-stage kernels failed: %s", cudaGetErrorString(e));
+    c->ms[3] += stage_end(c);
+    c->n_sorted = total;
+    c->have_sorted = true;
+    return RFX_OK;
+}
+
+int stage_sorted(Ctx* c, int E, double fold, int max_kmer_size) {
+    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "rfx_sort_kmers: no count table (call rfx_count or rfx_load_counts first)");
+    if (E == 0)
+        return ctx_fail(c, RFX_E_UNSUPPORTED,
+                        "min_error_coverage 0 selects DSFilterForkSubKmer, which reads five columns from a three-column row "
+                        "(ReflexivDSKmerLeftAndRightSorting.java:366-407) and cannot run in the reference");
+    if (c->k < 2 || (c->k - 1) % 31 == 0)
+        return ctx_fail(c, RFX_E_UNSUPPORTED, "k = %d: DSForwardSubKmerExtraction takes the last base from the wrong block when (k-1) %% 31 == 0 "
+                        "(ReflexivDSKmerLeftAndRightSorting.java:930-936)", c->k);
+    if (!(fold > 0) || max_kmer_size < 1 || max_kmer_size + 3 >= 30000) return ctx_fail(c, RFX_E_INVALID, "rfx_sort_kmers: bad fold / max_kmer_size");
+    return c->wide ? sorted_impl<u128>(c, E, fold, max_kmer_size + 3) : sorted_impl<uint64_t>(c, E, fold, max_kmer_size + 3);
 }
 
 int stage_graph(Ctx* c) {

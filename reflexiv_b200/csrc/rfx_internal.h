@@ -133,6 +133,11 @@ struct Ctx {
     uint64_t n_oriented = 0, n_budget = 0, n_budget_adm = 0, n_cycles = 0, n_contigs = 0, n_contig_bases = 0;
     bool have_contigs = false;
 
+    // ---- Count_<k>_sorted (rfx_sort_kmers): flags of the oriented k-mers that survive that stage's filters (alive & 2) ----
+    DevBuf srt_left, srt_right;  // i32[2*n_rows]
+    uint64_t n_sorted = 0;
+    bool have_sorted = false;
+
     // ---- sharded graph stages (rfx_gs_*) ----
     uint64_t gs_row_lo = 0, gs_row_hi = 0, gs_m = 0, gs_n_tails = 0, gs_n_heads = 0;
     int gs_step = 0;
@@ -185,6 +190,7 @@ int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);
 int stage_graph(Ctx* c);
+int stage_sorted(Ctx* c, int min_error_coverage, double min_repeat_fold, int max_kmer_size);
 int stage_gs_begin(Ctx* c, uint64_t row_lo, uint64_t row_hi);
 int stage_gs_left(Ctx* c);
 int stage_gs_link(Ctx* c, uint64_t* n_splitters);

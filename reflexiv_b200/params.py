@@ -24,6 +24,8 @@ class DefaultParam:
     minKmerCoverage: int = 2          # :104
     maxKmerCoverage: int = 10_000_000  # :105
     minErrorCoverage: int = 8         # :106  (4 * minKmerCoverage at construction; -cover does not update it)
+    minRepeatFold: float = 1.5        # :107  (Count_<k>_sorted stage)
+    kmerList: str = "23,31,41,53,67,81,95"  # :87   (its largest entry + 3 is the fork flag of that stage)
     minContig: int = 500              # :108
     bubble: bool = True               # :109
     cache: bool = False
@@ -41,6 +43,11 @@ class DefaultParam:
     @property
     def subKmerSize(self) -> int:
         return self.kmerSize - 1
+
+    @property
+    def kmerListInt(self) -> List[int]:
+        """setKmerListArray, DefaultParam.java:155-161"""
+        return [int(x) for x in self.kmerList.split(",")]
 
 
 class ParseExit(Exception):

@@ -4,6 +4,8 @@
 * ``Pipelines.reflexivDSCounterPipe``    <- pipeline/Pipelines.java:148-152 -> ReflexivDataFrameCounter.assembly() (:139-236)
 * ``Pipelines.reflexivDSMainPipe``       <- pipeline/Pipelines.java:90-98   -> ReflexivDSMain.assembly() (:123-357)
                                             and assemblyFromKmer() (:362-713) when -kmerc is given
+* ``Pipelines.reflexivLeftAndRightSortingPipe`` <- pipeline/Pipelines.java:1309-1313 -> ReflexivDSKmerLeftAndRightSorting
+                                            .assemblyFromKmer() (:105-243): Count_<k> CSV -> ``<out>/Count_<k>_sorted``
 
 Same output trees as the reference: ``<out>/Count_<k>/part-*.csv[.gz]`` + ``_SUCCESS`` (rows ``KMER,count``) and
 ``<out>/part-NNNNN`` contig files (``>Contig-<len>-(<left>,<right>)-<idx>`` + sequence wrapped at 100).
@@ -175,6 +177,34 @@ class ReflexivContext:
         if n.value:
             self._check(self.L.rfx_oriented_copy(self._ctx, hi.ctypes.data, lo.ctypes.data, le.ctypes.data, ri.ctypes.data), self._ctx)
         return hi, lo, le, ri
+
+    # ---- Count_<k>_sorted (ReflexivDSKmerLeftAndRightSorting.java:105-243) ----
+    def sort_kmers(self, min_error_coverage: int = 8, min_repeat_fold: float = 1.5, max_kmer_size: int = 95) -> int:
+        """Runs that stage's two fork filters over both orientations of the count table; returns the number of rows."""
+        self._check(self.L.rfx_sort_kmers(self._ctx, min_error_coverage, min_repeat_fold, max_kmer_size), self._ctx)
+        n = C.c_uint64()
+        self._check(self.L.rfx_sorted_size(self._ctx, C.byref(n)), self._ctx)
+        return n.value
+
+    def sorted_rows(self):
+        """(keys_hi, keys_lo, left, right) of the rows of Count_<k>_sorted, order unspecified."""
+        n = C.c_uint64()
+        self._check(self.L.rfx_sorted_size(self._ctx, C.byref(n)), self._ctx)
+        hi = np.empty(n.value, dtype=np.uint64)
+        lo = np.empty(n.value, dtype=np.uint64)
+        le = np.empty(n.value, dtype=np.int32)
+        ri = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(self.L.rfx_sorted_copy(self._ctx, hi.ctypes.data, lo.ctypes.data, le.ctypes.data, ri.ctypes.data), self._ctx)
+        return hi, lo, le, ri
+
+    def sorted_csv(self) -> bytes:
+        n = C.c_uint64()
+        self._check(self.L.rfx_sorted_csv(self._ctx, None, 0, C.byref(n)), self._ctx)
+        buf = np.empty(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self.L.rfx_sorted_csv(self._ctx, buf.ctypes.data, buf.size, C.byref(n)), self._ctx)
+        return buf.tobytes()
 
     def stats(self) -> dict:
         s = RfxStats()
@@ -428,4 +458,33 @@ class Pipelines:
             with open(os.path.join(out_dir, "part-00000"), "wb") as f:
                 f.write(data)
         open(os.path.join(out_dir, "_SUCCESS"), "w").close()
+        return st
+
+    def reflexivLeftAndRightSortingPipe(self) -> dict:
+        """Count_<k> CSV (param.inputKmerPath) -> <out>/Count_<k>_sorted/part-*.csv[.gz] + _SUCCESS, rows `KMER,1|left|right`
+        (ReflexivDSKmerLeftAndRightSorting.java:168-240).  K-mers whose length is not in the k-mer list are dropped by the
+        reference's binarizer (:1695), so a k outside the list writes an empty table."""
+        p = self.param
+        keys, counts = parse_count_csv(read_input_text(p.inputKmerPath), p.kmerSize)
+        keep = counts <= p.maxKmerCoverage  # :186-193, the lower bound is commented out in the reference
+        if p.kmerSize not in p.kmerListInt:
+            keep &= False
+        with ReflexivContext(p, counter_mode=False, device=self.device) as ctx:
+            ctx.load_counts(keys[keep], counts[keep])
+            n = ctx.sort_kmers(p.minErrorCoverage, p.minRepeatFold, p.kmerListInt[-1])
+            csv = ctx.sorted_csv()
+            st = ctx.stats()
+        out_dir = os.path.join(p.outputPath, f"Count_{p.kmerSize}_sorted")
+        os.makedirs(out_dir, exist_ok=True)  # SaveMode.Overwrite, :226-238
+        for f in os.listdir(out_dir):
+            os.remove(os.path.join(out_dir, f))
+        name = f"part-00000-{uuid.uuid4()}-c000.csv"
+        if p.gzip:
+            with gzip.open(os.path.join(out_dir, name + ".gz"), "wb") as f:
+                f.write(csv)
+        else:
+            with open(os.path.join(out_dir, name), "wb") as f:
+                f.write(csv)
+        open(os.path.join(out_dir, "_SUCCESS"), "w").close()
+        st["n_sorted_rows"] = n
         return st

@@ -51,6 +51,7 @@ def hostemu():
         "emu_bins_bruteforce": (I64, [P, U32, I, I, U32, P]),
         "emu_fork_filter": (I64, [P, P, P, I64, I, I]),
         "emu_fork_fetch": (None, [P, P, P, P]),
+        "emu_sorted_filter": (I64, [P, P, P, I64, I, I, C.c_double, I]),
         "emu_check_kmer_at": (I64, [P, I64, I]),
         "emu_table_hashes": (None, [C.c_uint64, C.c_uint64, P]),
         "emu_revcomp64": (C.c_uint64, [C.c_uint64, I]),

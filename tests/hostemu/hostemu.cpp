@@ -177,12 +177,62 @@ template <class KT> static int64_t fork_impl(const std::map<u128, uint32_t>& tab
     return (int64_t)g_okeys.size();
 }
 
+// Count_<k>_sorted: the per-group formulation of sorted_right_kernel / sorted_left_kernel (rfx_graph.cu)
+template <class KT> static int64_t sorted_impl(const std::map<u128, uint32_t>& tab, int k, int E, double fold, int X) {
+    g_okeys.clear(); g_oleft.clear(); g_oright.clear();
+    auto cnt_of = [&](KT Z) -> uint32_t {
+        KT zc = revcomp(Z, k);
+        auto it = tab.find((u128)(zc < Z ? zc : Z));
+        return it == tab.end() ? 0u : it->second;
+    };
+    std::map<u128, std::pair<int32_t, int32_t>> rsurv;  // survivors of the right filter: (coverage carried on, right flag)
+    for (auto& kv : tab) {
+        KT key = (KT)kv.first, rc = revcomp(key, k);
+        for (int strand = 0; strand < 2; strand++) {
+            if (strand && rc == key) continue;
+            KT Xk = strand ? rc : key;
+            KT prefix = Xk >> 2;
+            uint32_t myb = (uint32_t)Xk & 3u, cnt[4];
+            bool dup[4];
+            for (uint32_t b = 0; b < 4; b++) {
+                KT Z = (prefix << 2) | (KT)b;
+                cnt[b] = b == myb ? kv.second : cnt_of(Z);
+                dup[b] = (Z == revcomp(Z, k));
+            }
+            SortedFork res = sorted_right_fork(cnt, dup, E, fold, X);
+            if (res.winner == (int)myb) rsurv[(u128)Xk] = std::make_pair(res.left, res.right);
+        }
+    }
+    const int top = 2 * (k - 1);
+    const KT sufmask = mask_bases<KT>(k - 1);
+    for (auto& kv : rsurv) {
+        KT Xk = (KT)kv.first;
+        KT suffix = Xk & sufmask;
+        uint32_t mya = (uint32_t)(Xk >> top) & 3u;
+        int32_t cov[4], rfl[4];
+        for (uint32_t a = 0; a < 4; a++) {
+            KT Z = ((KT)a << top) | suffix;
+            auto it = rsurv.find((u128)Z);
+            cov[a] = it == rsurv.end() ? 0 : it->second.first;
+            rfl[a] = it == rsurv.end() ? 0 : it->second.second;
+        }
+        SortedFork res = sorted_left_fork(cov, rfl, E, fold, X);
+        if (res.winner == (int)mya) { g_okeys.push_back((u128)Xk); g_oleft.push_back(res.left); g_oright.push_back(res.right); }
+    }
+    return (int64_t)g_okeys.size();
+}
+
 extern "C" {
 
 int64_t emu_fork_filter(const uint64_t* hi, const uint64_t* lo, const uint32_t* cnt, int64_t n, int k, int E) {
     std::map<u128, uint32_t> tab;
     for (int64_t i = 0; i < n; i++) tab[((u128)hi[i] << 64) | lo[i]] = cnt[i];
     return k <= 31 ? fork_impl<uint64_t>(tab, k, E) : fork_impl<u128>(tab, k, E);
+}
+int64_t emu_sorted_filter(const uint64_t* hi, const uint64_t* lo, const uint32_t* cnt, int64_t n, int k, int E, double fold, int X) {
+    std::map<u128, uint32_t> tab;
+    for (int64_t i = 0; i < n; i++) tab[((u128)hi[i] << 64) | lo[i]] = cnt[i];
+    return k <= 31 ? sorted_impl<uint64_t>(tab, k, E, fold, X) : sorted_impl<u128>(tab, k, E, fold, X);
 }
 void emu_fork_fetch(uint64_t* hi, uint64_t* lo, int32_t* left, int32_t* right) {
     for (size_t i = 0; i < g_okeys.size(); i++) {

@@ -138,6 +138,66 @@ def test_fork_filters_per_group_formulation(orc, hostemu, k, E, cover, err):
         assert ref["stats"]["right_forks"] > 0
 
 
+def _emu_sorted(hostemu, cnt, k, E, fold, X):
+    n = hostemu.emu_sorted_filter(cnt["keys_hi"].ctypes.data, cnt["keys_lo"].ctypes.data, cnt["counts"].ctypes.data, C.c_int64(len(cnt["counts"])), k, E,
+                                  C.c_double(fold), X)
+    hi = np.zeros(n, np.uint64); lo = np.zeros(n, np.uint64); le = np.zeros(n, np.int32); ri = np.zeros(n, np.int32)
+    hostemu.emu_fork_fetch(hi.ctypes.data, lo.ctypes.data, le.ctypes.data, ri.ctypes.data)
+    order = np.lexsort((lo, hi))
+    return hi[order], lo[order], le[order], ri[order]
+
+
+@pytest.mark.parametrize("k,E,fold,kmax,cover,err", [(31, 8, 1.5, 95, 1, 0.01), (31, 6, 2.0, 31, 2, 0.01), (23, 8, 1.5, 95, 1, 0.02), (15, 3, 1.5, 53, 1, 0.03),
+                                                      (41, 8, 1.5, 95, 1, 0.01), (12, 8, 1.5, 95, 1, 0.02), (53, 24, 2.0, 95, 1, 0.01)])
+def test_sorted_stage_per_group_formulation(orc, hostemu, k, E, fold, kmax, cover, err):
+    """Count_<k>_sorted: sorted_right_fork / sorted_left_fork evaluated per (k-1)-mer group, as the GPU does,
+    against the oracle's sort + sequential scan with the reference's packed attribute word -- including the two places
+    where the reference lets a weaker row's coverage / right flag leak into the stored row."""
+    from reflexiv_b200 import synth
+    g = synth.genome(3000, 17 + k)
+    g[1500:1900] = g[200:600]
+    g[2500:2520] = np.frombuffer(b"ACGT" * 5, np.uint8)
+    txt = synth.fastq(g, 900, read_len=100, frag_len=250, error_rate=err, seed_reads=5, seed_errors=6)
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    cnt = orc.count_kmers(txt, starts, lens, k, min_count=cover)
+    cnt["counts"][::97] = 40000 + np.arange(len(cnt["counts"][::97]), dtype=np.uint32)   # above the 30000 saturation
+    ref = orc.sorted_rows(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], k, E, fold, kmax)
+    hi, lo, le, ri = _emu_sorted(hostemu, cnt, k, E, fold, kmax + 3)
+    assert np.array_equal(hi, ref["keys_hi"]) and np.array_equal(lo, ref["keys_lo"])
+    assert np.array_equal(le, ref["left"]) and np.array_equal(ri, ref["right"])
+    assert set(np.unique(le)) <= {-1, kmax + 3} and set(np.unique(ri)) <= {-1, kmax + 3}
+    if k == 31:
+        assert (le == kmax + 3).any() and (ri == kmax + 3).any()     # real forks are present
+
+
+def test_sorted_stage_reference_quirks_by_hand(orc):
+    """Three hand-made groups (k = 5, E = 2, fold 1.5, list maximum 5 -> X = 8):
+       * prefix AAAA with last bases A:5, C:3 -- neither is an error: A survives but carries C's coverage 3 on
+         (LeftAndRightSorting.java:504-518), which then decides the left filter of its suffix group;
+       * coverage 1 never wins a fork flag (highestLeftMarker == 1 -> -1)."""
+    def enc(s):
+        v = 0
+        for ch in s:
+            v = (v << 2) | "ACGT".index(ch)
+        return v
+    def canon(s):
+        rc = s.translate(str.maketrans("ACGT", "TGCA"))[::-1]
+        return min(s, rc)
+    rows = {"AAAAA": 5, "AAAAC": 3, "CAAAA": 4, "GGGCA": 1, "GGGCC": 1}
+    table = {}
+    for s, c in rows.items():
+        table[canon(s)] = c
+    keys = np.array([enc(s) for s in table], np.uint64)
+    res = orc.sorted_rows(np.zeros(len(keys), np.uint64), keys, np.array(list(table.values()), np.uint32), 5, 2, 1.5, 5)
+    got = {orc.decode_kmer(0, l, 5): (int(a), int(b)) for l, a, b in zip(res["keys_lo"], res["left"], res["right"])}
+    # right filter, prefix AAAA: A(5) then C(3): C is no error (3 > E) -> A stays with coverage 3, right = 8.
+    # left filter, suffix AAAA: first bases A (AAAAA, carried coverage 3) then C (CAAAA, coverage 4): 4 > 3, 3 > E -> CAAAA wins
+    # with left = 8 although AAAAA was counted 5 times.
+    assert "AAAAA" not in got and got["CAAAA"][0] == 8
+    # GGGC + A / C, both coverage 1: the larger base wins, flag -1 because the coverage is 1
+    assert "GGGCA" not in got and got["GGGCC"][1] == -1
+
+
 def test_canonical_assembly_vs_pass_simulation_on_clean_data(orc):
     """Error-free reads, no repeats: no budget flag survives, so the fixed point is order independent.  The
     reference's pass simulation may stop before it (its stopping rule only compares record counts three passes

@@ -346,6 +346,78 @@ def test_load_counts_seam(R, orc, example_text):
     assert got == sorted(ref["asm"]["contigs"])
 
 
+@pytest.mark.parametrize("k,E,fold,kmax,cover,err,index", [(31, 8, 1.5, 95, 1, 0.01, None), (31, 6, 2.0, 31, 2, 0.01, "local"), (23, 8, 1.5, 95, 1, 0.02, None),
+                                                            (41, 8, 1.5, 95, 1, 0.01, None), (53, 24, 2.0, 95, 1, 0.005, "local"), (12, 3, 1.5, 53, 1, 0.02, None)])
+def test_sorted_stage_matches_oracle(R, orc, monkeypatch, k, E, fold, kmax, cover, err, index):
+    """SURVEY 8f-2, Count_<k>_sorted: rfx_sort_kmers against the oracle's restatement of ReflexivDSKmerLeftAndRightSorting
+    (rows as arrays and as the CSV text the reference writes), with both index layouts and coverages past the 30000
+    saturation; the assembly results of the same context stay retrievable only until the stage takes the index over."""
+    from reflexiv_b200 import synth
+    if index:
+        monkeypatch.setenv("RFX_GRAPH_INDEX", index)
+    g = synth.genome(30_000, 300 + k)
+    g[12000:12800] = g[3000:3800]
+    g[20000:20040] = np.frombuffer(b"AT" * 20, np.uint8)
+    txt = synth.fastq(g, 6000, read_len=150, frag_len=400, error_rate=err, seed_reads=9, seed_errors=10)
+    s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    c = orc.count_kmers(txt, s, l, k, min_count=cover)
+    c["counts"][::131] = 40000 + np.arange(len(c["counts"][::131]), dtype=np.uint32)
+    ref = orc.sorted_rows(c["keys_hi"], c["keys_lo"], c["counts"], k, E, fold, kmax)
+    ints = [(int(h) << 64) | int(lo) for h, lo in zip(c["keys_hi"], c["keys_lo"])]
+    keys = R.pipeline.encode_kmer_rows([orc.decode_kmer(h, lo, k) for h, lo in zip(c["keys_hi"], c["keys_lo"])], k)
+    assert R.pipeline.keys_to_int(keys, k) == ints
+    with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1)) as ctx:
+        ctx.load_counts(keys, c["counts"])
+        n = ctx.sort_kmers(E, fold, kmax)
+        hi, lo, le, ri = ctx.sorted_rows()
+        csv = ctx.sorted_csv()
+        with pytest.raises(R.RfxError) as e:
+            ctx.contigs()
+        assert e.value.code == R._lib.RFX_E_STATE
+    assert n == len(ref["left"]) and n > 0
+    order = np.lexsort((lo, hi))
+    assert np.array_equal(hi[order], ref["keys_hi"]) and np.array_equal(lo[order], ref["keys_lo"])
+    assert np.array_equal(le[order], ref["left"]) and np.array_equal(ri[order], ref["right"])
+    assert sorted(csv.decode().splitlines()) == sorted(orc.sorted_rows_text(ref, k).splitlines())
+    if k == 31 and index is None:
+        assert (le == kmax + 3).any() and (ri == kmax + 3).any()
+
+
+def test_sorted_stage_pipeline_and_domain(R, orc, example_text, tmp_path):
+    """Count_<k> CSV -> Count_<k>_sorted through the host mirror of Pipelines.reflexivLeftAndRightSortingPipe, and the
+    inputs the reference itself cannot process."""
+    import gzip
+    cout = tmp_path / "work"
+    from conftest import GOLDEN
+    pc = R.ParameterOfCounter(["-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(cout), "-kmer", "31", "-cover", "1", "-gzip"]).importCommandLine()
+    R.Pipelines(pc).reflexivDSCounterPipe()
+    p = R.DefaultParam(kmerSize=31, outputPath=str(cout), inputKmerPath=str(cout / "Count_31" / "part*.csv.gz"), gzip=True, maxKmerCoverage=1_000_000)
+    st = R.Pipelines(p).reflexivLeftAndRightSortingPipe()
+    d = cout / "Count_31_sorted"
+    parts = [f for f in os.listdir(d) if f.startswith("part-")]
+    assert len(parts) == 1 and (d / "_SUCCESS").exists()
+    rows = sorted(gzip.open(d / parts[0]).read().decode().splitlines())
+    s, l = orc.fastq_reads(example_text, orc.FASTQ_COUNTER)
+    c = orc.count_kmers(example_text, s, l, 31)
+    ref = orc.sorted_rows(c["keys_hi"], c["keys_lo"], c["counts"], 31, 8, 1.5, 95, 1_000_000)
+    assert rows == sorted(orc.sorted_rows_text(ref, 31).splitlines()) and st["n_sorted_rows"] == len(rows)
+    assert all(r[31:34] == ",1|" for r in rows)
+    # a k outside the k-mer list: the reference's binarizer drops every row
+    p2 = R.DefaultParam(kmerSize=31, outputPath=str(tmp_path / "w2"), inputKmerPath=str(cout / "Count_31" / "part*.csv.gz"), kmerList="23,41")
+    assert R.Pipelines(p2).reflexivLeftAndRightSortingPipe()["n_sorted_rows"] == 0
+    for k, E in [(31, 0), (32, 8), (63, 8)]:
+        with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1)) as ctx:
+            ctx.push_fastq(example_text)
+            ctx.count()
+            with pytest.raises(R.RfxError) as e:
+                ctx.sort_kmers(E, 1.5, 95)
+            assert e.value.code == R._lib.RFX_E_UNSUPPORTED
+    with R.ReflexivContext(_param(R, kmerSize=31)) as ctx:
+        with pytest.raises(R.RfxError) as e:
+            ctx.sort_kmers()
+        assert e.value.code == R._lib.RFX_E_STATE
+
+
 def test_error_paths(R, example_text):
     with R.ReflexivContext(_param(R, kmerSize=31)) as ctx:
         with pytest.raises(R.RfxError) as e:
