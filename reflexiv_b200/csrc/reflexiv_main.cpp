@@ -9,17 +9,25 @@
 // The reference's driver is Java; a JDK is not available in this image, so the host side above the C ABI is C++
 // (INTEGRATION.md shows the JNI / Panama binding a Java driver would use instead).
 #include <dirent.h>
+#include <fcntl.h>
 #include <glob.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/reflexiv_cuda.h"
@@ -62,24 +70,70 @@ static int bad_params(const std::string& why) {  // Parameter.java:601-611: mess
     return 0;
 }
 
-static bool read_file(const std::string& path, std::string& out) {
-    const bool gz = path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0;
-    if (path.size() > 4 && path.compare(path.size() - 4, 4, ".4mc") == 0) {
-        fprintf(stderr, "%s: 4mc input needs hadoop-4mc; decompress first or use gzip / plain text\n", path.c_str());
-        return false;
-    }
-    gzFile f = gzopen(path.c_str(), "rb");  // zlib reads plain files transparently
-    if (!f) return false;
-    (void)gz;
-    char buf[1 << 16];
-    int n;
-    while ((n = gzread(f, buf, sizeof(buf))) > 0) out.append(buf, (size_t)n);
-    gzclose(f);
-    if (!out.empty() && out.back() != '\n') out.push_back('\n');
-    return true;
+// ---- input files -----------------------------------------------------------------------------------
+// spark.read().text(glob) reads every matching file as its own set of partitions, in parallel
+// (ReflexivDataFrameCounter.java:161-188, ReflexivDSMain.java:188).  Here: a few host threads inflate .gz files ahead
+// of the consumer (zlib), plain files are mapped, and the consumer takes the files in path order -- one rfx_push_fastq
+// per file, so the host never holds more than the look-ahead window and the GPU parses file i while i+1.. inflate.
+static bool ends_with(const std::string& s, const char* suf) {
+    const size_t n = strlen(suf);
+    return s.size() > n && s.compare(s.size() - n, n, suf) == 0;
 }
 
-static bool read_glob(const std::string& pattern, std::string& out) {
+struct InputFile {
+    std::string path;
+    std::string data;            // inflated text, or a plain file that had to be copied
+    const char* map = nullptr;   // plain file mapped read-only
+    size_t map_len = 0;
+    bool ok = false, done = false;
+    const char* bytes() const { return map ? map : data.data(); }
+    size_t size() const { return map ? map_len : data.size(); }
+    void release() {
+        if (map) munmap(const_cast<char*>(map), map_len);
+        map = nullptr; map_len = 0;
+        std::string().swap(data);
+    }
+};
+
+static bool load_file(InputFile& f) {
+    if (ends_with(f.path, ".4mc")) {
+        fprintf(stderr, "%s: 4mc input needs hadoop-4mc; decompress first or use gzip / plain text\n", f.path.c_str());
+        return false;
+    }
+    if (!ends_with(f.path, ".gz")) {
+        const int fd = open(f.path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); return false; }
+        if (st.st_size == 0) { close(fd); return true; }
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        close(fd);
+        if (m != MAP_FAILED) {
+            if (static_cast<const char*>(m)[st.st_size - 1] == '\n') {
+                madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                f.map = static_cast<const char*>(m); f.map_len = (size_t)st.st_size;
+                return true;
+            }
+            f.data.assign(static_cast<const char*>(m), (size_t)st.st_size);  // no final newline: a copy that gets one
+            munmap(m, (size_t)st.st_size);
+            f.data.push_back('\n');
+            return true;
+        }
+    }
+    gzFile g = gzopen(f.path.c_str(), "rb");  // zlib reads plain files transparently (mmap failed: pipes, odd file systems)
+    if (!g) return false;
+    gzbuffer(g, 1u << 20);
+    std::vector<char> buf(4u << 20);
+    int n;
+    while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) f.data.append(buf.data(), (size_t)n);
+    int zerr = Z_OK;
+    gzerror(g, &zerr);
+    const bool ok = gzclose(g) == Z_OK && n == 0 && (zerr == Z_OK || zerr == Z_STREAM_END);  // Z_BUF_ERROR: the stream ends early
+    if (!f.data.empty() && f.data.back() != '\n') f.data.push_back('\n');
+    return ok;
+}
+
+static bool expand_inputs(const std::string& pattern, std::vector<std::string>& files) {
     glob_t g;
     std::vector<std::string> paths;
     if (glob(pattern.c_str(), 0, nullptr, &g) == 0)
@@ -97,11 +151,69 @@ static bool read_glob(const std::string& pattern, std::string& out) {
                 closedir(d);
             }
             std::sort(inner.begin(), inner.end());
-            for (const std::string& q : inner)
-                if (!read_file(q, out)) return false;
-        } else if (!read_file(p, out)) return false;
+            files.insert(files.end(), inner.begin(), inner.end());
+        } else files.push_back(p);
     }
     return true;
+}
+
+// Hands the files matching `pattern` to `consume(bytes, len)` in path order; up to `ahead` files are being read or
+// wait decoded at any time.  Returns false on the first file that cannot be read or that `consume` rejects.
+static bool stream_inputs(const std::string& pattern, const std::function<bool(const char*, size_t)>& consume) {
+    std::vector<std::string> paths;
+    if (!expand_inputs(pattern, paths)) return false;
+    std::vector<InputFile> files(paths.size());
+    for (size_t i = 0; i < paths.size(); i++) files[i].path = paths[i];
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t ahead = hw ? hw : 4;
+    if (const char* e = getenv("REFLEXIV_READERS")) ahead = (size_t)std::max(1, atoi(e));
+    ahead = std::min<size_t>(std::min<size_t>(ahead, 16), files.size());
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t next = 0, consumed = 0;
+    bool stop = false;
+    auto worker = [&]() {
+        for (;;) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || next >= files.size() || next < consumed + ahead; });
+                if (stop || next >= files.size()) return;
+                i = next++;
+            }
+            const bool ok = load_file(files[i]);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                files[i].ok = ok; files[i].done = true;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < ahead; t++) pool.emplace_back(worker);
+    bool ok = true;
+    for (size_t i = 0; i < files.size() && ok; i++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return files[i].done; });
+        }
+        if (!files[i].ok) { fprintf(stderr, "reflexiv: cannot read %s\n", files[i].path.c_str()); ok = false; }
+        else if (files[i].size() && !consume(files[i].bytes(), files[i].size())) ok = false;
+        files[i].release();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            consumed = i + 1;
+        }
+        cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cv.notify_all();
+    for (std::thread& t : pool) t.join();
+    for (InputFile& f : files) f.release();
+    return ok;
 }
 
 static bool write_out(const std::string& path, const char* data, size_t n, bool gz) {
@@ -224,17 +336,27 @@ int main(int argc, char** argv) {
     info("Initiating CUDA context ...");
     rfx_ctx* c = nullptr;
     if (rfx_create(&c, &p) != RFX_OK) return fail(nullptr, "rfx_create");
-    std::string text;
     if (from_kmer) {
-        if (!read_glob(v["kmerc"], text)) { rfx_destroy(c); return 1; }
         std::vector<uint64_t> keys;
         std::vector<uint32_t> counts;
-        if (!parse_counts(text, p.kmer_size, p.min_kmer_coverage, p.max_kmer_coverage, keys, counts)) { fprintf(stderr, "reflexiv: malformed k-mer count row\n"); rfx_destroy(c); return 1; }
+        bool well_formed = true;
+        const bool read_ok = stream_inputs(v["kmerc"], [&](const char* data, size_t n) {
+            well_formed = parse_counts(std::string(data, n), p.kmer_size, p.min_kmer_coverage, p.max_kmer_coverage, keys, counts);
+            return well_formed;
+        });
+        if (!well_formed) fprintf(stderr, "reflexiv: malformed k-mer count row\n");
+        if (!read_ok) { rfx_destroy(c); return 1; }
         if (rfx_load_counts(c, keys.data(), counts.data(), counts.size()) != RFX_OK) return fail(c, "rfx_load_counts");
     } else {
-        if (!read_glob(v["fastq"], text)) { rfx_destroy(c); return 1; }
-        if (rfx_push_fastq(c, reinterpret_cast<const uint8_t*>(text.data()), text.size()) != RFX_OK) return fail(c, "rfx_push_fastq");
-        std::string().swap(text);
+        bool push_ok = true, pushed = false;
+        const bool read_ok = stream_inputs(v["fastq"], [&](const char* data, size_t n) {
+            push_ok = rfx_push_fastq(c, reinterpret_cast<const uint8_t*>(data), n) == RFX_OK;
+            pushed = true;
+            return push_ok;
+        });
+        if (!push_ok) return fail(c, "rfx_push_fastq");
+        if (!read_ok) { rfx_destroy(c); return 1; }
+        if (!pushed && rfx_push_fastq(c, reinterpret_cast<const uint8_t*>(""), 0) != RFX_OK) return fail(c, "rfx_push_fastq");  // only empty files
         if (rfx_count(c) != RFX_OK) return fail(c, "rfx_count");
     }
     mkdir(outdir.c_str(), 0755);

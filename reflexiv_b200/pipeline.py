@@ -362,21 +362,41 @@ def format_contig(seq: str, left: int, right: int, idx: int) -> str:
     return f">Contig-{len(seq)}-({left},{right})-{idx}\n{body}"
 
 
-def read_input_text(pattern: str) -> bytes:
-    """spark.read().text(glob): every matching file, .gz inflated on the host (zlib), concatenated in path order."""
+def _input_paths(pattern: str) -> List[str]:
     paths = sorted(glob.glob(pattern)) or ([pattern] if os.path.exists(pattern) else [])
     if not paths:
         raise FileNotFoundError(f"Input path does not exist: {pattern}")
-    chunks = []
+    out = []
     for p in paths:
         if os.path.isdir(p):
-            for q in sorted(os.listdir(p)):
-                if q.startswith(("_", ".")):
-                    continue
-                chunks.append(_read_one(os.path.join(p, q)))
+            out += [os.path.join(p, q) for q in sorted(os.listdir(p)) if not q.startswith(("_", "."))]
         else:
-            chunks.append(_read_one(p))
-    return b"".join(c if c.endswith(b"\n") or not c else c + b"\n" for c in chunks)
+            out.append(p)
+    return out
+
+
+def iter_input_files(pattern: str, readers: Optional[int] = None):
+    """spark.read().text(glob): the text of every matching file in path order, .gz inflated on a few host threads ahead of
+    the consumer (zlib releases the GIL), every chunk ending on a newline.  Same scheme as the `reflexiv` binary
+    (csrc/reflexiv_main.cpp: stream_inputs): the host holds a look-ahead window, not the whole input."""
+    from concurrent.futures import ThreadPoolExecutor
+    paths = _input_paths(pattern)
+    readers = max(1, min(readers or (os.cpu_count() or 4), 16, len(paths)))
+    with ThreadPoolExecutor(max_workers=readers) as pool:
+        pending = [pool.submit(_read_one, p) for p in paths[:readers]]
+        nxt = len(pending)
+        while pending:
+            c = pending.pop(0).result()
+            if nxt < len(paths):
+                pending.append(pool.submit(_read_one, paths[nxt]))
+                nxt += 1
+            if c:
+                yield c if c.endswith(b"\n") else c + b"\n"
+
+
+def read_input_text(pattern: str) -> bytes:
+    """All matching files concatenated (small inputs: count tables, tests)."""
+    return b"".join(iter_input_files(pattern))
 
 
 def _read_one(path: str) -> bytes:
@@ -414,9 +434,13 @@ class Pipelines:
 
     def reflexivDSCounterPipe(self) -> dict:
         p = self.param
-        text = read_input_text(p.inputFqPath)
         with ReflexivContext(p, counter_mode=True, device=self.device) as ctx:
-            ctx.push_fastq(text)
+            n_files = 0
+            for chunk in iter_input_files(p.inputFqPath):  # one push per file, the next files inflate meanwhile
+                ctx.push_fastq(chunk)
+                n_files += 1
+            if not n_files:
+                ctx.push_fastq(b"")
             st = ctx.count()
             csv = ctx.counts_csv()
         out_dir = os.path.join(p.outputPath, f"Count_{p.kmerSize}")
@@ -445,7 +469,12 @@ class Pipelines:
                 keep = (counts >= p.minKmerCoverage) & (counts <= p.maxKmerCoverage)  # DSMain.java:405-412
                 ctx.load_counts(keys[keep], counts[keep])
             else:
-                ctx.push_fastq(read_input_text(p.inputFqPath))
+                n_files = 0
+                for chunk in iter_input_files(p.inputFqPath):
+                    ctx.push_fastq(chunk)
+                    n_files += 1
+                if not n_files:
+                    ctx.push_fastq(b"")
                 ctx.count()
             st = ctx.assemble()
             contigs = ctx.contigs()

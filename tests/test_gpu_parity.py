@@ -522,3 +522,43 @@ def test_reflexiv_binary_matches_documented_run(R, tmp_path, golden):
     # reference behaviour on bad options: message, exit code 0, nothing written
     r = subprocess.run([exe, "run", "-fastq", "x", "-outfile", str(tmp_path / "z"), "-nosuch"], capture_output=True, text=True)
     assert r.returncode == 0 and "Parameter settings incorrect" in r.stdout and not (tmp_path / "z").exists()
+
+
+def test_reflexiv_binary_streams_many_input_files(R, example_text, tmp_path, golden):
+    """the driver inflates / maps the files matching -fastq on a few host threads and pushes them one by one
+    (one rfx_push_fastq per file).  Plain, gzip'ed, empty and newline-less files, one reader or many: same table."""
+    import gzip
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "reflexiv_b200", "reflexiv")
+    lines = example_text.split(b"\n")
+    recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines) - 1, 4)]
+    assert b"".join(recs) == example_text
+    ind = tmp_path / "in"
+    ind.mkdir()
+    cuts = [0, 300, 301, 900, 1500, 1500, 2000, len(recs)]
+    for j in range(len(cuts) - 1):
+        blob = b"".join(recs[cuts[j]:cuts[j + 1]])
+        if j % 3 == 0:
+            (ind / f"part{j}.fq").write_bytes(blob)
+        elif j % 3 == 1:
+            (ind / f"part{j}.fq").write_bytes(blob[:-1])          # no final newline
+        else:
+            with gzip.open(ind / f"part{j}.fq.gz", "wb") as f:
+                f.write(blob)
+    tables = []
+    for readers in ("1", "8"):
+        out = tmp_path / f"c{readers}"
+        r = subprocess.run([exe, "counter", "-fastq", str(ind / "part*"), "-outfile", str(out), "-kmer", "31", "-cover", "2"], capture_output=True, text=True,
+                           env=dict(os.environ, REFLEXIV_READERS=readers))
+        assert r.returncode == 0, r.stderr
+        parts = [f for f in os.listdir(out / "Count_31") if f.startswith("part-")]
+        tables.append(sorted((out / "Count_31" / parts[0]).read_text().splitlines()))
+    assert tables[0] == tables[1]
+    assert hashlib.sha256(("\n".join(tables[0]) + "\n").encode()).hexdigest() == golden["oracle"]["count_ge2"]["sha256_sorted_csv"]
+    # the directory itself as input (Spark reads every file in it), run command
+    r = subprocess.run([exe, "run", "-fastq", str(ind), "-outfile", str(tmp_path / "asm"), "-kmer", "31", "-cover", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "asm" / "part-00000").read_text().startswith(">Contig-4558-(-4,-4)-0\n")
+    r = subprocess.run([exe, "counter", "-fastq", str(tmp_path / "nothing*"), "-outfile", str(tmp_path / "n"), "-kmer", "31"], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not exist" in r.stderr
