@@ -54,6 +54,12 @@ def main(ref="/root/reference"):
         out["oracle"][f"contigs_cover{cov}"] = {"lengths": [len(x) for x in r["asm"]["contigs"]],
                                                 "canonical_sha256": [hashlib.sha256(x.encode()).hexdigest() for x in cs],
                                                 "fork_stats": r["forks"]["stats"]}
+    # Count_31_sorted of the example (defaults minErrorCoverage 8, minRepeatFold 1.5, k-mer list up to 95).
+    # The reference documents no output of this stage: these digests pin the oracle against regressions only.
+    srt = orc.sorted_rows(allc["keys_hi"], allc["keys_lo"], allc["counts"], 31, 8, 1.5, 95, 1_000_000)
+    out["oracle"]["sorted_k31"] = {"rows": int(len(srt["left"])), "left_forks": int((srt["left"] == 98).sum()),
+                                   "right_forks": int((srt["right"] == 98).sum()),
+                                   "sha256_sorted_csv": hashlib.sha256(orc.sorted_rows_text(srt, 31).encode()).hexdigest()}
     json.dump(out, open(os.path.join(HERE, "example_k31.json"), "w"), indent=1)
     print(json.dumps(out["oracle"], indent=1))
 
