@@ -562,7 +562,10 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     cudaStream_t st = c->stream;
     unsigned grid = (unsigned)((n_reads + PART_THREADS - 1) / PART_THREADS);
     if (grid < 1) grid = 1;
-    static const unsigned grid_cap = [] { const char* e = getenv("RFX_SCAN_GRID"); const int v = e ? atoi(e) : 0; return 148u * (unsigned)(v > 0 ? v : 64); }();
+    // one tile of PART_THREADS reads per block as long as that stays below 148 * 256 blocks: with 7 blocks resident per
+    // SM a block-strided loop of 2-3 tiles per block ends in a ragged last wave (measured at config 2: capped at
+    // 148 * 64 blocks 1.028 ms, one tile per block 1.006 ms)
+    const unsigned grid_cap = 148u * 256u;
     if (grid > grid_cap) grid = grid_cap;
     const uint32_t* rd_len = c->rd_len.as<uint32_t>() + read_off;
     const uint64_t* rd_woff = c->rd_woff.as<uint64_t>() + read_off;
