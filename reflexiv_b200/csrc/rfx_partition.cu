@@ -18,15 +18,6 @@
 namespace rfx {
 
 constexpr int PART_THREADS = 128;
-#ifndef RFX_EMIT_DEFER
-#define RFX_EMIT_DEFER 0
-#endif
-#ifndef RFX_FAST_Q
-#define RFX_FAST_Q 40
-#endif
-#ifndef RFX_SCAN_MINB
-#define RFX_SCAN_MINB 7
-#endif
 
 // Pass 1 (the only pass that walks the bases): every run of k-mers that share a bin becomes one 32-bit descriptor
 // (bin << 8 | n_kmers) plus a 16-bit start position, both in read-interleaved arrays (slot i of read r at
@@ -56,7 +47,6 @@ struct EmitDesc {
         (void)bin; (void)first_kmer; (void)n_k;
 #endif
     }
-    RFX_HD void finish() {}
 };
 
 // The 32 reads of a warp advance in lock step, one base per iteration.  The per-base work (roll the m-mer, hash it,
@@ -102,43 +92,14 @@ template <int RECW> struct EmitSlab {
     unsigned long long ovf_cap;
     int k;
     uint32_t n, stored;
-    // A record's slot is requested (atomic on the bin cursor) and its read words are fetched when the run is cut; the
-    // record is built and stored when the NEXT run is cut (after that run's own requests went out) or the read ends.
-    // The round trips of run i+1 thus overlap with the arithmetic and the store of run i instead of following them.
-    uint32_t p_bin, p_rank, p_first, p_nk;  // p_nk == 0: nothing pending
-#if RFX_EMIT_DEFER == 3
-    uint64_t p_w[RECW + 1];                 // read words [first / 32, first / 32 + RECW] of the pending run
-#endif
+    // The record is cut and stored the moment its run ends.  Deferring the store behind the next run's atomic (so
+    // that the two round trips overlap) was measured and is slower: 1.06 ms instead of 1.00 ms with the pending run in
+    // four registers, 1.48 ms with its read words prefetched as well (the scan is register bound: 72 registers at 7
+    // blocks per SM; 64 registers / 8 blocks: 1.02 ms).
     __device__ __forceinline__ void operator()(uint32_t bin, uint32_t first_kmer, uint32_t n_k) {
-#if RFX_EMIT_DEFER
         const uint32_t rank = atomicAdd(&bin_cnt[bin], 1u);
-#if RFX_EMIT_DEFER == 3
-        uint64_t w[RECW + 1];
-#pragma unroll
-        for (int i = 0; i <= RECW; i++) w[i] = rd[(first_kmer >> 5) + i];
-#endif
-        finish();
-        p_rank = rank; p_bin = bin; p_first = first_kmer; p_nk = n_k;
-#if RFX_EMIT_DEFER == 3
-#pragma unroll
-        for (int i = 0; i <= RECW; i++) p_w[i] = w[i];
-#endif
-#else
-        put(bin, atomicAdd(&bin_cnt[bin], 1u), first_kmer, n_k);
-#endif
-    }
-    __device__ __forceinline__ void finish() {
-#if RFX_EMIT_DEFER
-        if (p_nk) { put(p_bin, p_rank, p_first, p_nk); p_nk = 0; }
-#endif
-    }
-    __device__ __forceinline__ void put(uint32_t bin, uint32_t rank, uint32_t first_kmer, uint32_t n_k) {
         uint64_t rec[RECW];
-#if RFX_EMIT_DEFER == 3
-        rec_build<RECW>(p_w, first_kmer & 31u, n_k, k, rec);
-#else
         rec_build<RECW>(rd, first_kmer, n_k, k, rec);
-#endif
         uint64_t* dst;
         if (rank < cap) {
             dst = records + ((uint64_t)bin * cap + rank) * RECW;
@@ -267,7 +228,6 @@ __global__ void __launch_bounds__(PART_THREADS)
         }
         drain();
         if (rst.have) emit_run(em, rst.run_bin, rst.run_start, len - (uint32_t)k + 1u - rst.run_start, P.max_nk);
-        em.finish();
         if (mine && Factory::kNeedsRuns) {
             const bool spill = em.n > em.stored;
             rd_runs[r] = em.stored | (spill ? 0x80000000u : 0u);  // top bit: this read needs the spill pass
@@ -286,7 +246,7 @@ __global__ void __launch_bounds__(PART_THREADS)
 // any other warp marks its reads SCAN_TODO and the general kernel above picks them up.  Results are bit-identical
 // to bin_scan_read() (rfx_core.h).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int FAST_Q = RFX_FAST_Q;  // queued minimiser changes per read between two drains (a block adds at most W)
+constexpr int FAST_Q = 40;  // queued minimiser changes per read between two drains (a block adds at most W)
 
 template <int M, int W> struct FastScan {
     uint32_t mfl, mr;        // rolling m-mer: forward left-aligned in the top 2M bits, reverse complement right-aligned
@@ -331,7 +291,7 @@ template <int M, int W> struct FastScan {
 };
 
 template <int K, int M, class Factory>
-__global__ void __launch_bounds__(PART_THREADS, RFX_SCAN_MINB)
+__global__ void __launch_bounds__(PART_THREADS, 7)  // 72 registers: seven blocks per SM, which is also what the 30 KB of queues allow
     bin_scan_fast_kernel(const uint64_t* __restrict__ packed, const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff, uint64_t n_reads,
                          BinParams P, Factory F, uint32_t* __restrict__ rd_runs, unsigned long long* dstat) {
     constexpr int W = K - M + 1;
@@ -377,7 +337,6 @@ __global__ void __launch_bounds__(PART_THREADS, RFX_SCAN_MINB)
             }
             S.qn = 0;
             if (valid && final && rst.have) emit_run(em, rst.run_bin, rst.run_start, n_kmers - rst.run_start, P.max_nk);
-            if (final) em.finish();
         };
         {   // the first M - 1 bases complete no m-mer
             const uint64_t w0 = rd[0];
@@ -438,7 +397,6 @@ template <int RECW> struct EmitSpill {
         (void)bin; (void)first_kmer; (void)n_k;
 #endif
     }
-    RFX_HD void finish() {}
 };
 
 // Pass 2: per-record work only.  A block owns 32 consecutive reads at a time; its 8 warps take the descriptor slots
