@@ -41,9 +41,11 @@ static void info(const char* msg) {  // util/InfoDumper.java: "Reflexiv HH:mm:ss
 }
 
 static const char* HELP =
-    "usage: reflexiv <run|counter> [--spark-options ignored] -fastq <glob> -outfile <dir> [-kmer 31] [-cover 2]\n"
+    "usage: reflexiv <run|counter|sort> [--spark-options ignored] -fastq <glob> -outfile <dir> [-kmer 31] [-cover 2]\n"
     "       [-maxcov 10000000] [-error 8] [-clipf N] [-clipe N] [-mincontig 500] [-miniter 15] [-maxiter 150]\n"
-    "       [-partition N] [-partitionredu 200] [-kmerc <Count_k csv glob>] [-infmt fmt] [-bubble] [-gzip] [-cache]\n";
+    "       [-partition N] [-partitionredu 200] [-kmerc <Count_k csv glob>] [-infmt fmt] [-bubble] [-gzip] [-cache]\n"
+    "       sort: -kmerc <Count_k csv glob> -outfile <dir> -kmer k [-maxcov N] [-error 8] [-klist 23,31,...] [-accurate]\n"
+    "             writes <dir>/Count_<k>_sorted (rows KMER,1|left|right)\n";
 
 struct Opt { bool has_arg; };
 static std::map<std::string, Opt> run_options() {
@@ -265,12 +267,14 @@ static bool parse_counts(const std::string& text, int k, int minc, int maxc, std
 int main(int argc, char** argv) {
     if (argc < 2) { fputs(HELP, stdout); return 1; }
     const std::string cmd = argv[1];
-    if (cmd != "run" && cmd != "counter") {
-        fprintf(stderr, "reflexiv: command '%s' is outside the GPU path (supported: run, counter)\n", cmd.c_str());
+    // `sort` is not a command of bin/reflexiv: it runs the one stage of the multi-k workflows that is on the GPU path
+    // (Pipelines.reflexivLeftAndRightSortingPipe, Count_<k> -> Count_<k>_sorted) on its own, with the `run` option names
+    if (cmd != "run" && cmd != "counter" && cmd != "sort") {
+        fprintf(stderr, "reflexiv: command '%s' is outside the GPU path (supported: run, counter, sort)\n", cmd.c_str());
         fputs(HELP, stdout);
         return 1;
     }
-    const bool counter = cmd == "counter";
+    const bool counter = cmd == "counter", sorter = cmd == "sort";
     // bin/reflexiv:209-238: `--x [value]` belongs to spark-submit, `-x [value]` to Reflexiv
     std::vector<std::string> own;
     for (int i = 2; i < argc; i++) {
@@ -279,7 +283,7 @@ int main(int argc, char** argv) {
         if (a.rfind("--", 0) == 0) { if (next_is_value) i++; continue; }
         if (a[0] == '-') { own.push_back(a); if (next_is_value) own.push_back(argv[++i]); }
     }
-    info(counter ? "Reflexiv counter initiating ... " : "Reflexiv main initiating ... ");
+    info(counter ? "Reflexiv counter initiating ... " : sorter ? "Reflexiv k-mer sorting initiating ... " : "Reflexiv main initiating ... ");
     info("interpreting parameters.");
     const auto table = counter ? counter_options() : run_options();
     std::map<std::string, std::string> v;
@@ -317,8 +321,26 @@ int main(int argc, char** argv) {
     if (v.count("bubble")) p.bubble = 0;
     const bool gz = v.count("gzip") > 0;
     const std::string infmt = v.count("infmt") ? v["infmt"] : "4mc";
-    const bool from_kmer = !counter && v.count("kmerc") && !v.count("fastq");
+    const bool from_kmer = !counter && v.count("kmerc") && (sorter || !v.count("fastq"));
+    if (sorter && !from_kmer) { fputs(HELP, stdout); return 0; }
     if (!v.count("fastq") && !from_kmer) { fputs(HELP, stdout); return 0; }  // Parameter.java:565-568
+    // -klist / -accurate: Parameter.java:362-387, 417-420 (read by the sorted stage only)
+    std::vector<int> klist;
+    {
+        const std::string ks = v.count("klist") ? v["klist"] : "23,31,41,53,67,81,95";  // DefaultParam.java:87
+        size_t pos = 0;
+        while (pos <= ks.size()) {
+            size_t end = ks.find(',', pos);
+            if (end == std::string::npos) end = ks.size();
+            char* e = nullptr;
+            const std::string tok = ks.substr(pos, end - pos);
+            const long x = strtol(tok.c_str(), &e, 0);
+            if (tok.empty() || !e || *e) return bad_params("For input string: \"" + tok + "\"");
+            klist.push_back((int)x);
+            pos = end + 1;
+        }
+    }
+    const double min_repeat_fold = v.count("accurate") ? 2.0 : 1.5;  // DefaultParam.java:107
     if (!v.count("outfile")) { info("Output file not set of -outfile options"); return 0; }
     const std::string outdir = v["outfile"];
     p.counter_mode = counter ? 1 : 0;
@@ -326,9 +348,10 @@ int main(int argc, char** argv) {
     if (const char* d = getenv("REFLEXIV_DEVICE")) p.device = atoi(d);
 
     const std::string target = counter ? outdir + "/Count_" + std::to_string(p.kmer_size)
-                                       : (from_kmer ? outdir + "/Assemble_" + std::to_string(p.kmer_size) : outdir);
+                               : sorter ? outdir + "/Count_" + std::to_string(p.kmer_size) + "_sorted"
+                                        : (from_kmer ? outdir + "/Assemble_" + std::to_string(p.kmer_size) : outdir);
     struct stat stt;
-    if (!counter && stat(target.c_str(), &stt) == 0) {  // Hadoop FileAlreadyExistsException in saveAsTextFile
+    if (!counter && !sorter && stat(target.c_str(), &stt) == 0) {  // Hadoop FileAlreadyExistsException in saveAsTextFile
         fprintf(stderr, "reflexiv: output directory %s already exists\n", target.c_str());
         return 1;
     }
@@ -341,9 +364,12 @@ int main(int argc, char** argv) {
         std::vector<uint32_t> counts;
         bool well_formed = true;
         const bool read_ok = stream_inputs(v["kmerc"], [&](const char* data, size_t n) {
-            well_formed = parse_counts(std::string(data, n), p.kmer_size, p.min_kmer_coverage, p.max_kmer_coverage, keys, counts);
+            // run: cover <= count <= maxcov (ReflexivDSMain.java:405-412); sort: count <= maxcov only
+            // (ReflexivDSKmerLeftAndRightSorting.java:186-193) and only k-mers whose length is in the list (:1695)
+            well_formed = parse_counts(std::string(data, n), p.kmer_size, sorter ? INT32_MIN : p.min_kmer_coverage, p.max_kmer_coverage, keys, counts);
             return well_formed;
         });
+        if (sorter && std::find(klist.begin(), klist.end(), p.kmer_size) == klist.end()) { keys.clear(); counts.clear(); }
         if (!well_formed) fprintf(stderr, "reflexiv: malformed k-mer count row\n");
         if (!read_ok) { rfx_destroy(c); return 1; }
         if (rfx_load_counts(c, keys.data(), counts.data(), counts.size()) != RFX_OK) return fail(c, "rfx_load_counts");
@@ -360,11 +386,14 @@ int main(int argc, char** argv) {
         if (rfx_count(c) != RFX_OK) return fail(c, "rfx_count");
     }
     mkdir(outdir.c_str(), 0755);
-    if (counter) {
+    if (counter || sorter) {
         uint64_t nbytes = 0;
-        if (rfx_counts_csv(c, nullptr, 0, &nbytes) != RFX_OK) return fail(c, "rfx_counts_csv");
+        if (sorter && rfx_sort_kmers(c, p.min_error_coverage, min_repeat_fold, klist.back() /* param.kmerListInt[last], :445 */) != RFX_OK)
+            return fail(c, "rfx_sort_kmers");
+        auto csv_fn = sorter ? rfx_sorted_csv : rfx_counts_csv;
+        if (csv_fn(c, nullptr, 0, &nbytes) != RFX_OK) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
         std::vector<char> csv(nbytes ? nbytes : 1);
-        if (rfx_counts_csv(c, csv.data(), nbytes, &nbytes) != RFX_OK) return fail(c, "rfx_counts_csv");
+        if (nbytes && csv_fn(c, csv.data(), nbytes, &nbytes) != RFX_OK) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
         mkdir(target.c_str(), 0755);
         if (DIR* d = opendir(target.c_str())) {  // SaveMode.Overwrite
             while (dirent* e = readdir(d))

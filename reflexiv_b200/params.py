@@ -139,6 +139,14 @@ class Parameter(_Parser):
             p.partitions = self._need(self._int(v["partition"]) >= 0, "partition", self._int(v["partition"]))
         if "partitionredu" in v:
             p.shufflePartition = self._need(self._int(v["partitionredu"]) >= 0, "partitionredu", self._int(v["partitionredu"]))
+        if "klist" in v:
+            p.kmerList = v["klist"]  # Parameter.java:362-382 (the per-entry range check there is vacuous); read by the sorted stage
+            try:
+                p.kmerListInt
+            except ValueError:
+                raise ParseExit(f"Parameter settings incorrect.\nFor input string: \"{v['klist']}\"")
+        if "accurate" in v:
+            p.minRepeatFold = 2.0  # Parameter.java:417-420
         if "bubble" in v:
             p.bubble = False  # Parameter.java:420-422
         p.stitch = "stitch" in v

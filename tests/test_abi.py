@@ -95,6 +95,13 @@ def test_launcher_and_option_parsing():
     for bad in (["-fastq", "x", "-outfile", "o", "-clipf", "0"], ["-outfile", "o"], ["-fastq", "x", "-nosuch"], ["-help"]):
         with pytest.raises(ParseExit):
             Parameter(bad).importCommandLine()
+    # -klist / -accurate feed the Count_<k>_sorted stage (Parameter.java:362-387, 417-420; DefaultParam.java:87, 107)
+    d = Parameter(["-kmerc", "x", "-outfile", "o"]).importCommandLine()
+    assert (d.kmerListInt[-1], d.minRepeatFold) == (95, 1.5)
+    q = Parameter(["-kmerc", "x", "-outfile", "o", "-klist", "21,33", "-accurate"]).importCommandLine()
+    assert (q.kmerListInt, q.minRepeatFold) == ([21, 33], 2.0)
+    with pytest.raises(ParseExit):
+        Parameter(["-kmerc", "x", "-outfile", "o", "-klist", "21,zz"]).importCommandLine()
     with pytest.raises(ParseExit):
         ParameterOfCounter(["-fastq", "x", "-outfile", "o", "-mincontig", "5"]).importCommandLine()  # not a counter option
     c = ParameterOfCounter(["-fastq", "x", "-outfile", "o", "-kmer", "61", "-infmt", "line"]).importCommandLine()

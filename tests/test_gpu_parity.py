@@ -402,6 +402,28 @@ def test_sorted_stage_pipeline_and_domain(R, orc, example_text, tmp_path):
     ref = orc.sorted_rows(c["keys_hi"], c["keys_lo"], c["counts"], 31, 8, 1.5, 95, 1_000_000)
     assert rows == sorted(orc.sorted_rows_text(ref, 31).splitlines()) and st["n_sorted_rows"] == len(rows)
     assert all(r[31:34] == ",1|" for r in rows)
+    # the same stage through the C++ driver (`reflexiv sort`, option names of `run`)
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "reflexiv_b200", "reflexiv")
+    r = subprocess.run([exe, "sort", "-kmerc", str(cout / "Count_31" / "part*.csv.gz"), "-outfile", str(tmp_path / "cli"), "-kmer", "31", "-maxcov", "1000000"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    dd = tmp_path / "cli" / "Count_31_sorted"
+    pp = [f for f in os.listdir(dd) if f.startswith("part-")]
+    assert len(pp) == 1 and (dd / "_SUCCESS").exists()
+    assert sorted((dd / pp[0]).read_text().splitlines()) == rows
+    r = subprocess.run([exe, "sort", "-kmerc", str(cout / "Count_31" / "part*.csv.gz"), "-outfile", str(tmp_path / "cli2"), "-kmer", "31", "-klist", "23,41", "-gzip"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pp = [f for f in os.listdir(tmp_path / "cli2" / "Count_31_sorted") if f.startswith("part-")]
+    assert len(pp) == 1 and gzip.open(tmp_path / "cli2" / "Count_31_sorted" / pp[0]).read() == b""
+    r = subprocess.run([exe, "sort", "-kmerc", str(cout / "Count_31" / "part*.csv.gz"), "-outfile", str(tmp_path / "cli3"), "-kmer", "31", "-accurate", "-error", "6"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pp = [f for f in os.listdir(tmp_path / "cli3" / "Count_31_sorted") if f.startswith("part-")]
+    ref2 = orc.sorted_rows(c["keys_hi"], c["keys_lo"], c["counts"], 31, 6, 2.0, 95)
+    assert sorted((tmp_path / "cli3" / "Count_31_sorted" / pp[0]).read_text().splitlines()) == sorted(orc.sorted_rows_text(ref2, 31).splitlines())
     # a k outside the k-mer list: the reference's binarizer drops every row
     p2 = R.DefaultParam(kmerSize=31, outputPath=str(tmp_path / "w2"), inputKmerPath=str(cout / "Count_31" / "part*.csv.gz"), kmerList="23,41")
     assert R.Pipelines(p2).reflexivLeftAndRightSortingPipe()["n_sorted_rows"] == 0
