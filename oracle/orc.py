@@ -63,6 +63,7 @@ def lib():
                                    C.c_int, C.c_int, C.c_int, C.POINTER(_Contigs)]
         L.orc_contigs_free.argtypes = [C.POINTER(_Contigs)]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -87,6 +88,11 @@ def _as_bytes_array(txt) -> np.ndarray:
 
 FASTQ_RUN, FASTQ_COUNTER, FASTQ_LINE = 0, 1, 2
 ASM_CANONICAL, ASM_REFSIM = 0, 1
+
+
+def set_threads(n: int):
+    """Threads for the sort-based stages (fork filters, REFSIM passes); 1 = the deterministic single-partition order."""
+    lib().orc_set_threads(int(n))
 
 
 def fastq_reads(txt, mode: int = FASTQ_RUN):

@@ -47,6 +47,49 @@ static u128 revcomp(u128 x, int k) {
 
 void orc_free(void *p) { free(p); }
 
+/* ---- host threads for the sort-based stages ------------------------------ */
+/* The reference runs every sort("k-1") as a range shuffle over all executor
+ * cores and every mapPartitions over one partition per core.  With
+ * orc_set_threads(T > 1) the fork filters sort with T threads and the
+ * extension passes (ORC_ASM_REFSIM) sort with T threads and scan T range
+ * partitions concurrently -- a partition never splits a run of equal keys,
+ * exactly like Spark's RangePartitioner.  T = 1 (default) is the
+ * deterministic single-partition order the tests use. */
+static int g_threads = 1;
+void orc_set_threads(int n) { g_threads = n > 1 ? n : 1; }
+
+/* qsort on T chunks in parallel, then pairwise merges (parallel across pairs) */
+static void par_qsort(void *base, size_t n, size_t size, int (*cmp)(const void *, const void *)) {
+    int T = g_threads;
+    if (T <= 1 || n < 65536) { qsort(base, n, size, cmp); return; }
+    while ((size_t)T * 4096 > n) T /= 2;
+    size_t *cut = (size_t *)malloc((size_t)(T + 1) * sizeof(size_t));
+    for (int t = 0; t <= T; t++) cut[t] = n * (size_t)t / (size_t)T;
+    char *a = (char *)base;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+    for (int t = 0; t < T; t++) qsort(a + cut[t] * size, cut[t + 1] - cut[t], size, cmp);
+    char *tmp = (char *)malloc(n * size);
+    char *src = a, *dst = tmp;
+    for (int width = 1; width < T; width *= 2) {
+        int n_pairs = (T + 2 * width - 1) / (2 * width);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+        for (int pi = 0; pi < n_pairs; pi++) {
+            int lo = pi * 2 * width, mid = lo + width < T ? lo + width : T, hi = lo + 2 * width < T ? lo + 2 * width : T;
+            size_t i = cut[lo], ie = cut[mid], j = cut[mid], je = cut[hi], o = cut[lo];
+            while (i < ie && j < je) {
+                if (cmp(src + j * size, src + i * size) < 0) { memcpy(dst + o * size, src + j * size, size); j++; }
+                else { memcpy(dst + o * size, src + i * size, size); i++; }
+                o++;
+            }
+            if (i < ie) memcpy(dst + o * size, src + i * size, (ie - i) * size);
+            if (j < je) memcpy(dst + o * size, src + j * size, (je - j) * size);
+        }
+        char *sw = src; src = dst; dst = sw;
+    }
+    if (src != a) memcpy(a, src, n * size);
+    free(tmp); free(cut);
+}
+
 /* ------------------------------------------------------------------------ */
 /* A1 / A1': FASTQ line filters                                              */
 /* ------------------------------------------------------------------------ */
@@ -370,7 +413,7 @@ int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
     int64_t m = 2 * n;
     /* sort("k-1") on the (k-1)-prefix, DSMain:232.  CANONICAL ORDER: rows that
      * share a prefix are visited in ascending last-base order (full key order). */
-    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
+    par_qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
 
     /* A7 right fork filter: DSFilterForkSubKmerWithErrorCorrection
      * (DSMain:3431-3483) when minErrorCoverage != 0, DSFilterForkSubKmer
@@ -408,7 +451,7 @@ int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
      * DSFilterForkReflectedSubKmerWithErrorCorrection (DSMain:3550-3616) /
      * DSFilterForkReflectedSubKmer (DSMain:3489-3541). */
     g_rot_k = k;
-    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_rot);
+    par_qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_rot);
     const u128 sufmask = mask_bases(k - 1);
     w = 0;
     for (int64_t i = 0; i < m;) {
@@ -447,7 +490,7 @@ int64_t orc_fork_filter(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
         i = j;
     }
     m = w;
-    qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
+    par_qsort(a, (size_t)m, sizeof(okmer_t), ok_cmp_key);
     *o_hi = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
     *o_lo = (uint64_t *)malloc((size_t)(m ? m : 1) * sizeof(uint64_t));
     *o_left = (int32_t *)malloc((size_t)(m ? m : 1) * sizeof(int32_t));
@@ -861,6 +904,39 @@ static void extension_pass(rvec_t *in, rvec_t *out, int k) {
     in->n = 0;
 }
 
+/* sort("k-1") + mapPartitions(DSExtendReflexivKmer*): the sorted records are cut into range partitions at key
+ * boundaries and every partition is scanned by its own task (own toggle, own output), DSMain:261-326. */
+static void sort_and_pass(rvec_t *in, rvec_t *out, int k) {
+    par_qsort(in->v, in->n, sizeof(rrec_t), rrec_cmp);
+    int T = g_threads;
+    if (T <= 1 || in->n < 65536) { extension_pass(in, out, k); return; }
+    size_t *cut = (size_t *)malloc((size_t)(T + 1) * sizeof(size_t));
+    cut[0] = 0;
+    for (int t = 1; t < T; t++) {
+        size_t c = in->n * (size_t)t / (size_t)T;
+        if (c < cut[t - 1]) c = cut[t - 1];
+        while (c > 0 && c < in->n && in->v[c].sub == in->v[c - 1].sub) c++; /* equal keys stay in one partition */
+        cut[t] = c;
+    }
+    cut[T] = in->n;
+    rvec_t *parts = (rvec_t *)calloc((size_t)T, sizeof(rvec_t));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        rvec_t view = {in->v + cut[t], cut[t + 1] - cut[t], 0};
+        extension_pass(&view, &parts[t], k);
+    }
+    size_t total = out->n;
+    for (int t = 0; t < T; t++) total += parts[t].n;
+    if (total > out->cap) { out->cap = total; out->v = (rrec_t *)realloc(out->v, out->cap * sizeof(rrec_t)); }
+    for (int t = 0; t < T; t++) {
+        if (parts[t].n) memcpy(out->v + out->n, parts[t].v, parts[t].n * sizeof(rrec_t));
+        out->n += parts[t].n;
+        free(parts[t].v);
+    }
+    free(parts); free(cut);
+    in->n = 0;
+}
+
 static int assemble_refsim(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
                            int k, int min_contig, int min_iter, int max_iter, orc_contigs *out) {
     rvec_t a = {0}, b = {0};
@@ -869,33 +945,41 @@ static int assemble_refsim(const u128 *keys, const int32_t *left, const int32_t 
     okmer_t *o = (okmer_t *)malloc((size_t)(n ? n : 1) * sizeof(okmer_t));
     for (int64_t i = 0; i < n; i++) { o[i].key = keys[i]; o[i].left = left[i]; o[i].right = right[i]; }
     g_rot_k = k;
-    qsort(o, (size_t)n, sizeof(okmer_t), ok_cmp_rot);
+    par_qsort(o, (size_t)n, sizeof(okmer_t), ok_cmp_rot);
     /* DSkmerRandomReflection, DSMain:3688-3792 */
-    int toggle = 2;
-    for (int64_t i = 0; i < n; i++) {
-        rrec_t r;
-        r.len = (uint32_t)k;
-        r.seq = (uint8_t *)malloc((size_t)k);
-        for (int j = 0; j < k; j++) r.seq[j] = (uint8_t)((o[i].key >> (2 * (k - 1 - j))) & 3);
-        r.marker = 2; r.left = o[i].left; r.right = o[i].right;
-        r.sub = seq_sub(&r, k);
-        randomize(&a, r, &toggle, k);
+    {
+        const int T = (g_threads > 1 && n >= 65536) ? g_threads : 1; /* one task per partition, each with its own toggle */
+        a.cap = (size_t)(n ? n : 1);
+        a.v = (rrec_t *)malloc(a.cap * sizeof(rrec_t));
+        a.n = (size_t)n;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; t++) {
+            int toggle = 2;
+            for (int64_t i = n * t / T; i < n * (t + 1) / T; i++) {
+                rrec_t r;
+                r.len = (uint32_t)k;
+                r.seq = (uint8_t *)malloc((size_t)k);
+                for (int j = 0; j < k; j++) r.seq[j] = (uint8_t)((o[i].key >> (2 * (k - 1 - j))) & 3);
+                r.marker = 2; r.left = o[i].left; r.right = o[i].right;
+                r.sub = seq_sub(&r, k);
+                if (r.marker != toggle) { r.marker = toggle; r.sub = seq_sub(&r, k); } /* randomize(), in place */
+                a.v[i] = r;
+                toggle = (toggle == 1) ? 2 : 1;
+            }
+        }
     }
     free(o);
     /* DSMain:261-326 */
     int iterations = 0;
     int64_t passes = 0;
-    qsort(a.v, a.n, sizeof(rrec_t), rrec_cmp);
-    extension_pass(&a, &b, k); passes++;
+    sort_and_pass(&a, &b, k); passes++;
     for (int i = 1; i < 4; i++) {
         iterations++;
-        qsort(b.v, b.n, sizeof(rrec_t), rrec_cmp);
-        extension_pass(&b, &a, k); passes++;
+        sort_and_pass(&b, &a, k); passes++;
         rvec_t t = a; a = b; b = t;
     }
-    qsort(b.v, b.n, sizeof(rrec_t), rrec_cmp);
     iterations++;
-    extension_pass(&b, &a, k); passes++; /* DSExtendReflexivKmerToArrayFirstTime */
+    sort_and_pass(&b, &a, k); passes++; /* DSExtendReflexivKmerToArrayFirstTime */
     int64_t contig_number = 0;
     while (iterations <= max_iter) {
         iterations++;
@@ -904,8 +988,7 @@ static int assemble_refsim(const u128 *keys, const int32_t *left, const int32_t 
             if (contig_number == cur) break;
             contig_number = cur;
         }
-        qsort(a.v, a.n, sizeof(rrec_t), rrec_cmp);
-        extension_pass(&a, &b, k); passes++;
+        sort_and_pass(&a, &b, k); passes++;
         rvec_t t = a; a = b; b = t;
     }
     /* DSBinaryReflexivKmerArrayToString + DSKmerToContig, DSMain:855-900, 743-771 */

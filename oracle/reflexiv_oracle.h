@@ -88,6 +88,10 @@ void orc_contigs_free(orc_contigs *c);
 
 void orc_free(void *p);
 
+/* Host threads for the sort-based stages (fork filters, ORC_ASM_REFSIM passes): T-thread sorts and one scan task per
+ * range partition, as Spark local[T] runs them.  Default 1: one partition, the deterministic order the tests pin. */
+void orc_set_threads(int n);
+
 #ifdef __cplusplus
 }
 #endif
