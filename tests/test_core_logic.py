@@ -256,3 +256,43 @@ def test_table_hashes_do_not_cancel_top_bits(hostemu):
     assert len(seen_pair) == n                   # no pair of relatives shares both table hashes
     # the narrow hash only sees lo: of the ten variants per key, (0,2)/(0,3), (1,2)/(1,3) and (2,2)/(2,3)/(3,3) share lo
     assert len(seen_narrow) == 300 * 6
+
+
+def _random_table(rng, k, density, max_count, heavy=0.0):
+    """A random canonical count table over ALL 4^k k-mers (small k): dense enough that 3- and 4-way forks, coverage ties
+    and (even k) palindromes are everywhere."""
+    n_all = 1 << (2 * k)
+    v = np.arange(n_all, dtype=np.uint64)
+    rc = np.zeros(n_all, dtype=np.uint64)
+    x = v.copy()
+    for _ in range(k):
+        rc = (rc << np.uint64(2)) | (np.uint64(3) - (x & np.uint64(3)))
+        x >>= np.uint64(2)
+    canon = v[v <= rc]
+    keep = canon[rng.random(len(canon)) < density]
+    counts = rng.integers(1, max_count + 1, len(keep)).astype(np.uint32)
+    if heavy:
+        big = rng.random(len(keep)) < heavy
+        counts[big] = rng.integers(29_990, 30_020, int(big.sum())).astype(np.uint32)   # around the 30000 saturation of the sorted stage
+    return dict(keys_hi=np.zeros(len(keep), np.uint64), keys_lo=keep, counts=counts)
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 7])
+def test_fork_filters_fuzz_on_dense_random_tables(orc, hostemu, k):
+    """Both fork-filter pairs (the `run` command's and the sorted stage's), per-group GPU formulation vs the oracle's
+    sort + scan, on tables where most (k-1)-mer groups hold 2-4 candidates."""
+    rng = np.random.default_rng(100 + k)
+    for trial in range(12):
+        cnt = _random_table(rng, k, density=float(rng.choice([0.15, 0.5, 0.9])), max_count=int(rng.choice([2, 5, 20])), heavy=0.05 if trial % 3 == 0 else 0.0)
+        if len(cnt["counts"]) == 0:
+            continue
+        for E in (0, 3, 8):
+            ref = orc.fork_filter(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], k, E)
+            hi, lo, le, ri = _emu_fork(hostemu, cnt, k, E)
+            assert np.array_equal(lo, ref["keys_lo"]) and np.array_equal(le, ref["left"]) and np.array_equal(ri, ref["right"]), (k, trial, E)
+        for E, fold, kmax in ((2, 1.5, 7), (8, 2.0, 95), (1, 1.0, 31)):
+            if (k - 1) % 31 == 0:
+                continue
+            ref = orc.sorted_rows(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], k, E, fold, kmax)
+            hi, lo, le, ri = _emu_sorted(hostemu, cnt, k, E, fold, kmax + 3)
+            assert np.array_equal(lo, ref["keys_lo"]) and np.array_equal(le, ref["left"]) and np.array_equal(ri, ref["right"]), (k, trial, E, fold)
