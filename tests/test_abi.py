@@ -122,3 +122,25 @@ def test_contig_and_key_formatting_helpers():
         assert keys_to_int(rows, k) == [int("".join(format("ACGT".index(c), "02b") for c in s), 2) for s in kmers]
     keys, counts = parse_count_csv(b"ACGTA,12\n(TTTTT,3)\nGGGGG,12345678901\n", 5)
     assert counts.tolist() == [12, 3, 1_000_000_000] and decode_keys(keys, 5) == ["ACGTA", "TTTTT", "GGGGG"]
+
+
+def test_python_launcher_mirrors_the_reference_exit_codes(tmp_path):
+    """`python -m reflexiv_b200 <command>` (bin/reflexiv + main/Main.java): option errors print and exit 0 like the
+    reference (Parameter.java:601-611), commands outside the GPU path and a missing GPU exit 1 -- never a CPU fallback."""
+    import subprocess
+    import sys
+    from conftest import ROOT, GOLDEN
+    def run(*a):
+        return subprocess.run([sys.executable, "-m", "reflexiv_b200", *a], capture_output=True, text=True, cwd=ROOT)
+    r = run("run", "--driver-memory", "3G", "-fastq", "x", "-nosuch")
+    assert r.returncode == 0 and "Parameter settings incorrect" in r.stderr and "Reflexiv" in r.stdout
+    r = run("run", "-outfile", str(tmp_path / "o"))
+    assert r.returncode == 0 and "usage: reflexiv run" in r.stdout and not (tmp_path / "o").exists()
+    r = run("sort", "-fastq", "x", "-outfile", str(tmp_path / "o"))        # the sorted stage reads a count table
+    assert r.returncode == 0 and "usage" in r.stdout
+    r = run("meta", "-fastq", "x")
+    assert r.returncode == 1 and "outside the GPU path" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = run("counter", "-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(tmp_path / "c"), "-kmer", "31")
+        assert r.returncode == 1 and "CUDA" in r.stderr and not (tmp_path / "c" / "Count_31").exists()
