@@ -238,28 +238,61 @@ static int fail(rfx_ctx* c, const char* what) {
     return 1;
 }
 
-// KmerBinarizer input: `KMER,count` or legacy `(KMER,count)`, ReflexivDSMain.java:3872-3948
-static bool parse_counts(const std::string& text, int k, int minc, int maxc, std::vector<uint64_t>& keys, std::vector<uint32_t>& counts) {
-    const int words = k <= 31 ? 1 : k / 32 + 1;
-    size_t pos = 0;
-    while (pos < text.size()) {
-        size_t end = text.find('\n', pos);
-        if (end == std::string::npos) end = text.size();
-        std::string line = text.substr(pos, end - pos);
+// One worker's share of the rows: [data + from, data + to), both on line starts.  No allocation per row.
+static bool parse_count_rows(const char* data, size_t from, size_t to, int k, int minc, int maxc, std::vector<uint64_t>& keys, std::vector<uint32_t>& counts) {
+    const int words = k <= 31 ? 1 : k / 32 + 1, res = k % 32;
+    size_t pos = from;
+    while (pos < to) {
+        const char* nl = static_cast<const char*>(memchr(data + pos, '\n', to - pos));
+        size_t end = nl ? (size_t)(nl - data) : to;
+        size_t b = pos, e = end;
         pos = end + 1;
-        if (line.empty()) continue;
-        if (line[0] == '(') line = line.substr(1);
-        if (!line.empty() && line.back() == ')') line.pop_back();
-        size_t comma = line.find(',');
-        if (comma == std::string::npos || (int)comma < k) return false;
-        const std::string num = line.substr(comma + 1);
-        long cover = num.size() >= 10 ? 1000000000L : atol(num.c_str());
+        if (e > b && data[e - 1] == '\r') e--;
+        if (b == e) continue;
+        if (data[b] == '(') b++;
+        if (e > b && data[e - 1] == ')') e--;
+        const char* cm = static_cast<const char*>(memchr(data + b, ',', e - b));
+        if (!cm || (cm - (data + b)) < k) return false;
+        const char* num = cm + 1;
+        const size_t nd = (size_t)(data + e - num);
+        long cover = 0;
+        if (nd >= 10) cover = 1000000000L;  // ReflexivDSMain.java:3895-3910
+        else for (size_t i = 0; i < nd; i++) { if (num[i] < '0' || num[i] > '9') break; cover = cover * 10 + (num[i] - '0'); }
         if (cover < minc || cover > maxc) continue;  // ReflexivDSMain.java:405-412
         unsigned __int128 v = 0;
-        for (int i = 0; i < k; i++) { char ch = line[i]; v = (v << 2) | (ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3); }
+        for (int i = 0; i < k; i++) { const char ch = data[b + i]; v = (v << 2) | (ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3); }
         if (words == 1) keys.push_back((uint64_t)v);
-        else { const int res = k % 32; keys.push_back((uint64_t)(v >> (2 * res))); keys.push_back((uint64_t)v & ((res ? ((uint64_t)1 << (2 * res)) : 1) - 1)); }
+        else { keys.push_back((uint64_t)(v >> (2 * res))); keys.push_back((uint64_t)v & ((res ? ((uint64_t)1 << (2 * res)) : 1) - 1)); }
         counts.push_back((uint32_t)cover);
+    }
+    return true;
+}
+
+// KmerBinarizer input: `KMER,count` or legacy `(KMER,count)`, ReflexivDSMain.java:3872-3948.  Large tables are cut at line
+// starts into one piece per host thread (Spark parses every partition of the CSV on its own core); row order is kept.
+static bool parse_counts(const char* data, size_t n, int k, int minc, int maxc, std::vector<uint64_t>& keys, std::vector<uint32_t>& counts) {
+    unsigned T = std::thread::hardware_concurrency();
+    if (const char* e = getenv("REFLEXIV_READERS")) T = (unsigned)std::max(1, atoi(e));
+    if (T > 32) T = 32;
+    if (T <= 1 || n < (4u << 20)) return parse_count_rows(data, 0, n, k, minc, maxc, keys, counts);
+    std::vector<size_t> cut(T + 1, n);
+    cut[0] = 0;
+    for (unsigned t = 1; t < T; t++) {
+        size_t c = std::max(cut[t - 1], n / T * t);
+        const char* nl = c < n ? static_cast<const char*>(memchr(data + c, '\n', n - c)) : nullptr;
+        cut[t] = nl ? (size_t)(nl - data) + 1 : n;
+    }
+    std::vector<std::vector<uint64_t>> pk(T);
+    std::vector<std::vector<uint32_t>> pc(T);
+    std::vector<char> ok(T, 1);
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < T; t++)
+        pool.emplace_back([&, t] { ok[t] = parse_count_rows(data, cut[t], cut[t + 1], k, minc, maxc, pk[t], pc[t]) ? 1 : 0; });
+    for (std::thread& th : pool) th.join();
+    for (unsigned t = 0; t < T; t++) {
+        if (!ok[t]) return false;
+        keys.insert(keys.end(), pk[t].begin(), pk[t].end());
+        counts.insert(counts.end(), pc[t].begin(), pc[t].end());
     }
     return true;
 }
@@ -366,7 +399,7 @@ int main(int argc, char** argv) {
         const bool read_ok = stream_inputs(v["kmerc"], [&](const char* data, size_t n) {
             // run: cover <= count <= maxcov (ReflexivDSMain.java:405-412); sort: count <= maxcov only
             // (ReflexivDSKmerLeftAndRightSorting.java:186-193) and only k-mers whose length is in the list (:1695)
-            well_formed = parse_counts(std::string(data, n), p.kmer_size, sorter ? INT32_MIN : p.min_kmer_coverage, p.max_kmer_coverage, keys, counts);
+            well_formed = parse_counts(data, n, p.kmer_size, sorter ? INT32_MIN : p.min_kmer_coverage, p.max_kmer_coverage, keys, counts);
             return well_formed;
         });
         if (sorter && std::find(klist.begin(), klist.end(), p.kmer_size) == klist.end()) { keys.clear(); counts.clear(); }

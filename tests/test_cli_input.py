@@ -13,6 +13,22 @@ HARNESS = r'''
 #include "%s"
 #undef main
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "counts")) {   // counts <file> <k> <minc> <maxc>: parse_counts, rows as "w0 [w1] count"
+        std::string text;
+        FILE* f = fopen(argv[2], "rb");
+        char buf[1 << 16]; size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+        fclose(f);
+        std::vector<uint64_t> keys; std::vector<uint32_t> counts;
+        const int k = atoi(argv[3]);
+        if (!parse_counts(text.data(), text.size(), k, atoi(argv[4]), atoi(argv[5]), keys, counts)) { fprintf(stderr, "malformed\n"); return 2; }
+        const size_t w = k <= 31 ? 1 : k / 32 + 1;
+        for (size_t i = 0; i < counts.size(); i++) {
+            for (size_t j = 0; j < w; j++) printf("%%llu ", (unsigned long long)keys[i * w + j]);
+            printf("%%u\n", counts[i]);
+        }
+        return 0;
+    }
     std::string all; size_t calls = 0;
     const size_t fail_at = argc > 2 ? (size_t)atoi(argv[2]) : (size_t)-1;
     bool ok = stream_inputs(argv[1], [&](const char* d, size_t n) { all.append(d, n); return calls++ != fail_at; });
@@ -93,3 +109,45 @@ def test_python_mirror_reads_the_same_way(example_text, tmp_path):
     assert read_input_text(str(ind / "part*")) == example_text
     with pytest.raises(FileNotFoundError):
         read_input_text(str(tmp_path / "none*"))
+
+
+def test_count_table_parser(harness, tmp_path):
+    """-kmerc rows (KmerBinarizer, ReflexivDSMain.java:3872-3948): both row forms, the >= 10-digit clamp, coverage bounds,
+    one- and two-word keys in the reference layout, and the threaded path (pieces cut at line starts) against the Python mirror."""
+    import numpy as np
+    from reflexiv_b200.pipeline import parse_count_csv
+    rng = np.random.default_rng(5)
+    def kmers(n, k):
+        return ["".join("ACGT"[c] for c in rng.integers(0, 4, k)) for _ in range(n)]
+    def run(path, k, minc, maxc, readers="1"):
+        r = subprocess.run([harness, "counts", str(path), str(k), str(minc), str(maxc)], capture_output=True, text=True, env=dict(os.environ, REFLEXIV_READERS=readers))
+        return r.returncode, [tuple(int(x) for x in line.split()) for line in r.stdout.splitlines()]
+    # small table, every row form
+    rows31 = kmers(6, 31)
+    text = f"{rows31[0]},5\n({rows31[1]},17)\n{rows31[2]},12345678901\n\n{rows31[3]},1\r\n{rows31[4]},3000\n{rows31[5]},7"
+    (tmp_path / "a.csv").write_text(text)
+    rc, got = run(tmp_path / "a.csv", 31, 2, 10_000_000)
+    keys, cnt = parse_count_csv(text.replace("\r", "").encode(), 31)
+    keep = (cnt >= 2) & (cnt <= 10_000_000)
+    assert rc == 0 and got == [(int(k[0]), int(c)) for k, c in zip(keys[keep], cnt[keep])]
+    assert [c for _, c in got] == [5, 17, 3000, 7]                 # the 11-digit count clamps to 10^9 and falls above maxcov
+    rc, got = run(tmp_path / "a.csv", 31, -2**31, 2**31 - 1)
+    assert [c for _, c in got] == [5, 17, 1_000_000_000, 1, 3000, 7]
+    # two-word keys (k = 61: 32 bases, then 29 right aligned)
+    rows61 = kmers(50, 61)
+    text61 = "".join(f"{s},{i + 1}\n" for i, s in enumerate(rows61))
+    (tmp_path / "b.csv").write_text(text61)
+    rc, got = run(tmp_path / "b.csv", 61, 1, 100)
+    keys, cnt = parse_count_csv(text61.encode(), 61)
+    assert rc == 0 and got == [(int(k[0]), int(k[1]), int(c)) for k, c in zip(keys, cnt)]
+    # malformed rows are reported, not skipped
+    (tmp_path / "c.csv").write_text(f"{rows31[0]},5\nACGT,3\n")
+    assert run(tmp_path / "c.csv", 31, 1, 100)[0] == 2
+    # a table large enough for the threaded path: same rows in the same order with 1 and 8 parser threads
+    big = kmers(4000, 31)
+    text_big = "".join(f"{big[i % 4000]},{i % 90 + 1}\n" for i in range(140_000))
+    (tmp_path / "d.csv").write_text(text_big)
+    assert len(text_big) > (4 << 20)
+    rc1, one = run(tmp_path / "d.csv", 31, 3, 80, "1")
+    rc8, eight = run(tmp_path / "d.csv", 31, 3, 80, "8")
+    assert rc1 == 0 and rc8 == 0 and one == eight and len(one) == sum(1 for i in range(140_000) if 3 <= i % 90 + 1 <= 80)
