@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]): synthetic E. coli-size genome (4.6 Mbp), 15
 k = 31, full `reflexiv run` path: FASTQ text -> 2-bit reads -> canonical k-mer count table -> coverage filter ->
 fork filters -> contig extension -> contig bases.  A step is one pass over the whole read set.  At N > 1 every rank
 holds the same amount of reads (weak scaling: genome and read set grow with N), records are exchanged with one NCCL
-all-to-all, shards count locally, the shard tables are all-gathered and the graph stages run replicated.
+all-to-all, shards count locally, the shard tables are all-gathered and every rank runs the graph stages for the rows
+it owns (alive bytes, the splitter list of the chain walk and one tuple per chain are what is exchanged).
 
 `value`   k-mer instances per second over the whole step, inputs (FASTQ text) resident in HBM.
 `e2e`     same metric through the public API with host buffers: H2D of the FASTQ text from pinned memory and D2H of
