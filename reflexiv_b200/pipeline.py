@@ -411,18 +411,47 @@ def _read_one(path: str) -> bytes:
 
 def parse_count_csv(text: bytes, k: int) -> Tuple[np.ndarray, np.ndarray]:
     """KmerBinarizer input forms: `KMER,count` and the legacy `(KMER,count)`; counts of >= 10 digits clamp to 10^9
-    (DSMain.java:3895-3910)."""
-    kmers, counts = [], []
-    for line in text.decode().splitlines():
-        line = line.strip()
-        if not line:
-            continue
-        if line.startswith("("):
-            line = line[1:-1]
-        a, b = line.split(",")
-        kmers.append(a)
-        counts.append(1_000_000_000 if len(b) >= 10 else int(b))
-    return encode_kmer_rows(kmers, k), np.array(counts, dtype=np.uint32)
+    (DSMain.java:3895-3910).  Vectorised over the rows (numpy): a table of millions of rows parses in seconds.
+    Returns (keys uint64[n, words] in the reference layout, counts uint32[n])."""
+    a = np.frombuffer(bytes(text), dtype=np.uint8)
+    w = 1 if k <= 31 else k // 32 + 1
+    if a.size == 0:
+        return np.empty((0, w), np.uint64), np.empty(0, np.uint32)
+    nl = np.flatnonzero(a == 10)
+    starts = np.concatenate(([0], nl + 1)).astype(np.int64)
+    ends = np.concatenate((nl, [a.size])).astype(np.int64)
+    pad = np.concatenate((a, np.zeros(16, np.uint8)))          # so that fixed-width gathers may look past the end
+    ends = ends - ((ends > starts) & (pad[np.maximum(ends - 1, 0)] == 13))                  # "\r\n"
+    keep = ends > starts
+    starts, ends = starts[keep], ends[keep]
+    starts = starts + (pad[starts] == ord("("))
+    ends = ends - (pad[np.maximum(ends - 1, 0)] == ord(")"))
+    if np.any(ends - starts < k + 2) or np.any(pad[starts + k] != ord(",")):
+        raise ValueError("malformed k-mer count row")
+    # k-mer: A=0 C=1 G=2, anything else 3 (nucleotideValue, DSMain.java:3935-3947)
+    chars = pad[starts[:, None] + np.arange(k)[None, :]]
+    codes = np.full(chars.shape, 3, np.uint64)
+    codes[chars == ord("A")] = 0
+    codes[chars == ord("C")] = 1
+    codes[chars == ord("G")] = 2
+    keys = np.zeros((len(starts), w), np.uint64)
+    if k <= 31:
+        for i in range(k):
+            keys[:, 0] = (keys[:, 0] << np.uint64(2)) | codes[:, i]
+    else:                                                        # 32 bases per word, the last word holds k % 32 right aligned
+        for i in range(k):
+            j = i // 32
+            keys[:, j] = (keys[:, j] << np.uint64(2)) | codes[:, i]
+    nd = ends - (starts + k + 1)
+    counts = np.zeros(len(starts), np.int64)
+    for d in range(int(min(nd.max(), 9)) if len(nd) else 0):
+        ch = pad[starts + k + 1 + d].astype(np.int64)
+        use = (d < nd) & (nd < 10)
+        if np.any(use & ((ch < 48) | (ch > 57))):
+            raise ValueError("malformed k-mer count row")
+        counts = np.where(use, counts * 10 + (ch - 48), counts)
+    counts[nd >= 10] = 1_000_000_000
+    return keys, counts.astype(np.uint32)
 
 
 class Pipelines:

@@ -151,3 +151,24 @@ def test_count_table_parser(harness, tmp_path):
     rc1, one = run(tmp_path / "d.csv", 31, 3, 80, "1")
     rc8, eight = run(tmp_path / "d.csv", 31, 3, 80, "8")
     assert rc1 == 0 and rc8 == 0 and one == eight and len(one) == sum(1 for i in range(140_000) if 3 <= i % 90 + 1 <= 80)
+
+
+def test_python_count_table_parser_row_forms():
+    """pipeline.parse_count_csv (vectorised): every row form against a plain per-line restatement of KmerBinarizer."""
+    import numpy as np
+    from reflexiv_b200.pipeline import encode_kmer_rows, parse_count_csv
+    rng = np.random.default_rng(9)
+    for k in (5, 31, 33, 61):
+        rows = ["".join("ACGTN"[c] for c in rng.integers(0, 5, k)) for _ in range(400)]
+        parts, want_k, want_c = [], [], []
+        for i, r in enumerate(rows):
+            c = int(rng.choice([1, 7, 42, 999, 123456789, 1234567890, 98765432109]))
+            parts.append([f"({r},{c})\n", f"{r},{c}\r\n", f"{r},{c}\n\n", f"{r},{c}\n"][i % 4])
+            want_k.append(r)
+            want_c.append(1_000_000_000 if c >= 10 ** 9 else c)     # >= 10 digits clamp (DSMain.java:3895-3910)
+        keys, counts = parse_count_csv("".join(parts).encode()[:-1], k)      # the last row without its newline
+        assert np.array_equal(keys, encode_kmer_rows(want_k, k)) and counts.tolist() == want_c
+    for bad in (b"ACGT,3\n", b"ACGTACGTACGTACGTACGTACGTACGTACG;3\n", b"ACGTACGTACGTACGTACGTACGTACGTACG,3x\n"):
+        with pytest.raises(ValueError):
+            parse_count_csv(bad, 31)
+    assert parse_count_csv(b"\n\n", 31)[1].size == 0
