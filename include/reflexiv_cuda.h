@@ -82,8 +82,8 @@ typedef struct {
     uint64_t n_bins;
     uint64_t n_bin_splits;   /* counting bins that had to be re-run in sub-classes */
     uint64_t n_oriented;     /* oriented k-mers surviving both fork filters (A7, A8) */
-    uint64_t n_budget_junctions;   /* junctions left open because exactly one flag is >= 0 */
-    uint64_t n_budget_admissible;  /* ... of which a clause-3/4 merge would still be admissible */
+    uint64_t n_budget_junctions;   /* junctions whose two flags have different signs as the fork filters left them */
+    uint64_t n_budget_admissible;  /* k-mers absorbed by budget walks (clause 3 / 4 merges, ReflexivDSMain.java:3077-3084) */
     uint64_t n_cycles;
     uint64_t n_contigs;
     uint64_t n_contig_bases;

@@ -87,7 +87,7 @@ def _as_bytes_array(txt) -> np.ndarray:
 
 
 FASTQ_RUN, FASTQ_COUNTER, FASTQ_LINE = 0, 1, 2
-ASM_CANONICAL, ASM_REFSIM = 0, 1
+ASM_CANONICAL, ASM_REFSIM, ASM_SCHEDULED = 0, 1, 2
 
 
 def set_threads(n: int):

@@ -726,24 +726,88 @@ static int64_t lb_key(const u128 *keys, int64_t n, u128 x) {
     return lo;
 }
 
-/* A junction X -> Y (suffix(X) == prefix(Y)) is joined by the scan of
+/* ---- junctions and budget flags ------------------------------------------
+ * A junction X -> Y (suffix(X) == prefix(Y)) is joined by the scan of
  * DSExtendReflexivKmer*.call (DSMain:3069-3075 / 1809-1815) when the forward
  * record's left flag and the reflected record's right flag are both negative
- * or both non-negative.  Clauses 3/4 (budget >= 0 against a clean end,
- * DSMain:3077-3084) depend on how long the partner already is when Spark
- * happens to co-present the pair.  CANONICAL ORDER: unconditional joins run
- * to the fixed point first; the mixed-sign junctions are left open and
- * counted (n_budget_junctions / n_budget_admissible). */
+ * or both non-negative (clauses 1 and 2).  A fork winner's flag k-1 facing a
+ * clean end is a BUDGET (clauses 3 / 4, DSMain:3077-3084, reflexivExtend
+ * :3237-3325): the flagged fragment absorbs the clean neighbour while the
+ * neighbour's extension is no longer than the budget; the budget shrinks by
+ * the bases absorbed and OVERWRITES the flag of the new outer end.  How much a
+ * fork winner absorbs therefore depends on how long its neighbour already is
+ * when Spark happens to co-present the pair -- anything from 0 to k-1 k-mers.
+ *
+ * CANONICAL ORDER: flagged ends grow one k-mer at a time before
+ * any clean-clean join is made, the walker further upstream in its own
+ * direction first.  Along a path this is the recurrence
+ *     E(v) = (face(v) < 0 && E(prev(v)) >= 1) ? E(prev(v)) - 1 : budget(v)
+ * evaluated once along succ (budget = right flag, face = left flag) and once
+ * along pred (budget = left flag, face = right flag): a walk absorbs at most
+ * k-1 k-mers, ends in front of a non-negative facing flag (clause 2 joins
+ * there), and an absorbed fork winner loses its own budget exactly like the
+ * overwritten flag in reflexivExtend.  A junction is joined when a walk went
+ * through it or when the two effective flags have the same sign.
+ * assemble_scheduled() below applies the reference's four clauses literally
+ * under that schedule; tests check that both give the same contigs. */
 static inline int junction_joins(int32_t x_right, int32_t y_left) {
     return (y_left < 0 && x_right < 0) || (y_left >= 0 && x_right >= 0);
 }
 
-static int assemble_canonical(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
-                              int k, int min_contig, orc_contigs *out) {
+/* start of the recurrence on a closed raw path L[0..m-1] (direction order): a node that cannot be absorbed
+ * (facing flag >= 0), else the node behind >= bmax consecutive budget-less nodes (no walk survives them), else --
+ * every walk may wrap around -- CANONICAL ORDER: the fork winner with the smallest oriented k-mer starts fresh.
+ * Returns -1 when no node of the loop carries a budget. */
+static int64_t loop_start(const int64_t *L, int64_t m, const int32_t *bud, const int32_t *face, const u128 *keys, int bmax) {
+    int64_t n_cand = 0;
+    for (int64_t i = 0; i < m; i++) if (bud[L[i]] >= 0) n_cand++;
+    if (!n_cand) return -1;
+    for (int64_t i = 0; i < m; i++) if (face[L[i]] >= 0) return i;
+    int64_t run = 0;
+    for (int64_t i = 0; i < 2 * m; i++) {
+        if (bud[L[i % m]] < 0) { if (++run >= bmax) return (i + 1) % m; }
+        else run = 0;
+    }
+    int64_t best = -1;
+    for (int64_t i = 0; i < m; i++)
+        if (bud[L[i]] >= 0 && (best < 0 || keys[L[i]] < keys[L[best]])) best = i;
+    return best;
+}
+
+/* one direction of the recurrence.  nxt / prv: raw links along the walking direction (self loops removed);
+ * eff[] comes in as a copy of bud[]; bit: 1 = walks along succ, 2 = along pred (jmark is indexed by the LEFT node
+ * of the junction in sequence order). */
+static void budget_scan(int bit, int64_t n, const int64_t *nxt, const int64_t *prv, const int32_t *bud, const int32_t *face,
+                        const u128 *keys, int bmax, int32_t *eff, uint8_t *jmark, int64_t *absorbed) {
+    char *seen = (char *)calloc((size_t)(n ? n : 1), 1);
+    int64_t *L = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
+    for (int64_t h = 0; h < n; h++) {
+        if (prv[h] >= 0) continue;
+        seen[h] = 1;
+        for (int64_t p = h, v = nxt[h]; v >= 0; p = v, v = nxt[v]) {
+            seen[v] = 1;
+            if (face[v] < 0 && eff[p] >= 1) { eff[v] = eff[p] - 1; jmark[bit == 1 ? p : v] |= (uint8_t)bit; (*absorbed)++; }
+        }
+    }
+    for (int64_t v0 = 0; v0 < n; v0++) {
+        if (seen[v0]) continue;
+        int64_t m = 0;
+        for (int64_t v = v0; !seen[v]; v = nxt[v]) { seen[v] = 1; L[m++] = v; }
+        const int64_t st = loop_start(L, m, bud, face, keys, bmax);
+        if (st < 0) continue;
+        for (int64_t i = 1; i < m; i++) {
+            const int64_t p = L[(st + i - 1) % m], v = L[(st + i) % m];
+            if (face[v] < 0 && eff[p] >= 1) { eff[v] = eff[p] - 1; jmark[bit == 1 ? p : v] |= (uint8_t)bit; (*absorbed)++; }
+        }
+    }
+    free(seen); free(L);
+}
+
+/* raw neighbour links of the filter output (every (k-1)-mer has in- and out-degree <= 1); a k-mer whose suffix is
+ * its own prefix never meets itself (one record): no link, reported through self_loop[]. */
+static int raw_links(const u128 *keys, int64_t n, int k, int64_t *succ, int64_t *pred, char *self_loop) {
     const u128 sufmask = mask_bases(k - 1);
-    int64_t *succ = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
-    int64_t *pred = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
-    for (int64_t i = 0; i < n; i++) pred[i] = -1;
+    for (int64_t i = 0; i < n; i++) { pred[i] = -1; self_loop[i] = 0; }
     int bad = 0;
     for (int64_t i = 0; i < n; i++) {
         u128 lo = (keys[i] & sufmask) << 2;
@@ -751,7 +815,7 @@ static int assemble_canonical(const u128 *keys, const int32_t *left, const int32
         succ[i] = -1;
         if (p < n && (keys[p] >> 2) == (lo >> 2)) {
             if (p + 1 < n && (keys[p + 1] >> 2) == (lo >> 2)) bad = 1; /* out-degree > 1: not a filter output */
-            succ[i] = p;
+            if (p == i) self_loop[i] = 1; else succ[i] = p;
         }
     }
     for (int64_t i = 0; i < n && !bad; i++) {
@@ -760,32 +824,47 @@ static int assemble_canonical(const u128 *keys, const int32_t *left, const int32
             pred[succ[i]] = i;
         }
     }
-    if (bad) { free(succ); free(pred); return -2; }
+    return bad;
+}
+
+static int assemble_canonical(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
+                              int k, int min_contig, orc_contigs *out) {
+    const size_t nn = (size_t)(n ? n : 1);
+    int64_t *succ = (int64_t *)malloc(nn * sizeof(int64_t));
+    int64_t *pred = (int64_t *)malloc(nn * sizeof(int64_t));
+    char *self_loop = (char *)malloc(nn);
+    if (raw_links(keys, n, k, succ, pred, self_loop)) { free(succ); free(pred); free(self_loop); return -2; }
+    /* budget walks */
+    int32_t *effL = (int32_t *)malloc(nn * sizeof(int32_t)), *effR = (int32_t *)malloc(nn * sizeof(int32_t));
+    uint8_t *jmark = (uint8_t *)calloc(nn, 1);
+    memcpy(effL, left, (size_t)n * sizeof(int32_t));
+    memcpy(effR, right, (size_t)n * sizeof(int32_t));
+    int64_t absorbed = 0, budget = 0, self_cycles = 0;
+    budget_scan(1, n, succ, pred, right, left, keys, k - 1, effR, jmark, &absorbed);
+    budget_scan(2, n, pred, succ, left, right, keys, k - 1, effL, jmark, &absorbed);
     /* keep only joining junctions */
-    int64_t budget = 0;
     for (int64_t i = 0; i < n; i++) {
-        if (succ[i] >= 0 && !junction_joins(right[i], left[succ[i]])) {
-            budget++;
-            pred[succ[i]] = -1;
-            succ[i] = -(2 + succ[i]); /* remember the open junction for the admissibility count */
-        }
+        if (self_loop[i]) { if (junction_joins(right[i], left[i])) self_cycles++; else budget++; }
+        if (succ[i] < 0) continue;
+        if (!junction_joins(right[i], left[succ[i]])) budget++; /* mixed signs as the filters left them */
+        if (!(jmark[i] || junction_joins(effR[i], effL[succ[i]]))) { pred[succ[i]] = -1; succ[i] = -1; }
     }
     cbuild_t cb; cb_init(&cb, out);
     out->n_budget_junctions = budget;
-    char *seen = (char *)calloc((size_t)(n ? n : 1), 1);
-    int64_t *chain_len = (int64_t *)calloc((size_t)(n ? n : 1), sizeof(int64_t)); /* indexed by head and by tail */
+    out->n_budget_admissible = absorbed; /* k-mers absorbed by budget walks (clause 3 / 4 merges) */
+    out->n_cycles = self_cycles;
+    char *seen = (char *)calloc(nn, 1);
     /* chains, in ascending order of head key */
     for (int64_t h = 0; h < n; h++) {
         if (pred[h] >= 0) continue;
         int64_t cnt = 0, t = h;
-        for (int64_t x = h; x >= 0; x = succ[x] >= 0 ? succ[x] : -1) { seen[x] = 1; cnt++; t = x; }
-        chain_len[h] = cnt; chain_len[t] = cnt;
+        for (int64_t x = h; x >= 0; x = succ[x]) { seen[x] = 1; cnt++; t = x; }
         int64_t len = cnt + k - 1;
-        if (!contig_kept(len, left[h], right[t], min_contig)) continue;
-        char *dst = cb_begin(&cb, (size_t)len, left[h], right[t]);
+        if (!contig_kept(len, effL[h], effR[t], min_contig)) continue;
+        char *dst = cb_begin(&cb, (size_t)len, effL[h], effR[t]);
         for (int b = 0; b < k; b++) dst[b] = ACGT[(unsigned)(keys[h] >> (2 * (k - 1 - b))) & 3];
         int64_t pos = k;
-        for (int64_t x = succ[h]; x >= 0; x = succ[x] >= 0 ? succ[x] : -1) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
+        for (int64_t x = succ[h]; x >= 0; x = succ[x]) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
     }
     /* cycles: every junction joins.  The reference ends with one record whose
      * two ends are the same (k-1)-mer; where it is cut is arrival-order
@@ -798,22 +877,129 @@ static int assemble_canonical(const u128 *keys, const int32_t *left, const int32
         out->n_cycles++;
         int64_t len = cnt + k - 1;
         int64_t t = pred[s];
-        if (!contig_kept(len, left[s], right[t], min_contig)) continue;
-        char *dst = cb_begin(&cb, (size_t)len, left[s], right[t]);
+        if (!contig_kept(len, effL[s], effR[t], min_contig)) continue;
+        char *dst = cb_begin(&cb, (size_t)len, effL[s], effR[t]);
         for (int b = 0; b < k; b++) dst[b] = ACGT[(unsigned)(keys[s] >> (2 * (k - 1 - b))) & 3];
         int64_t pos = k;
         for (int64_t x = succ[s]; x != s; x = succ[x]) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
     }
-    /* open junctions where clause 3/4 would still fire on the finished fragments */
-    for (int64_t i = 0; i < n; i++) {
-        if (succ[i] <= -2) {
-            int64_t y = -(succ[i] + 2);
-            int64_t r_ext = chain_len[i], f_ext = chain_len[y]; /* |ext| = k-mers in the fragment */
-            if (left[y] >= 0 && left[y] - r_ext >= 0) out->n_budget_admissible++;
-            else if (right[i] >= 0 && right[i] - f_ext >= 0) out->n_budget_admissible++;
+    free(seen); free(succ); free(pred); free(self_loop); free(effL); free(effR); free(jmark);
+    return 0;
+}
+
+/* ---- the same schedule, clause by clause ------------------------------------
+ * Fragments are runs of the raw path; merge_frag() is the decision of
+ * DSExtendReflexivKmer.call (DSMain:3070-3089) and the flag rule of
+ * reflexivExtend (DSMain:3265-3279) on a (reflected R, forward F) pair.
+ * Phase 1: every flagged right end absorbs single clean k-mers, paths walked
+ * downstream; phase 2: the same for flagged left ends, walked upstream;
+ * phase 3: every junction the clauses admit, to the fixed point. */
+typedef struct { int64_t tail; int32_t left, right; int64_t n; } frag_t;
+
+static int merge_frag(frag_t *fr, int64_t *head_of_tail, char *is_tail, int64_t a, int64_t b, int allow_same_sign) {
+    frag_t *R = &fr[a], *F = &fr[b];
+    int32_t bubble;
+    if (F->left < 0 && R->right < 0) { if (!allow_same_sign) return 0; bubble = -1; }
+    else if (F->left >= 0 && R->right >= 0) { if (!allow_same_sign) return 0; bubble = -1; }
+    else if (F->left >= 0 && F->left - R->n >= 0) bubble = (int32_t)(F->left - R->n);
+    else if (R->right >= 0 && R->right - F->n >= 0) bubble = (int32_t)(R->right - F->n);
+    else return 0;
+    int32_t nl, nr;
+    if (bubble < 0) { nl = R->left; nr = F->right; }
+    else if (F->left > 0) { nl = bubble; nr = F->right; }
+    else { nl = R->left; nr = bubble; }
+    is_tail[R->tail] = 0;
+    R->left = nl; R->right = nr; R->n += F->n; R->tail = F->tail;
+    head_of_tail[R->tail] = a;
+    return 1;
+}
+
+static int assemble_scheduled(const u128 *keys, const int32_t *left, const int32_t *right, int64_t n,
+                              int k, int min_contig, orc_contigs *out) {
+    const size_t nn = (size_t)(n ? n : 1);
+    int64_t *succ = (int64_t *)malloc(nn * sizeof(int64_t));
+    int64_t *pred = (int64_t *)malloc(nn * sizeof(int64_t));
+    char *self_loop = (char *)malloc(nn);
+    if (raw_links(keys, n, k, succ, pred, self_loop)) { free(succ); free(pred); free(self_loop); return -2; }
+    frag_t *fr = (frag_t *)malloc(nn * sizeof(frag_t));          /* indexed by head node */
+    int64_t *head_of_tail = (int64_t *)malloc(nn * sizeof(int64_t));
+    char *is_head = (char *)malloc(nn), *is_tail = (char *)malloc(nn);
+    for (int64_t i = 0; i < n; i++) { is_tail[i] = 1; fr[i].tail = i; fr[i].left = left[i]; fr[i].right = right[i]; fr[i].n = 1; head_of_tail[i] = i; is_head[i] = 1; }
+    /* closed raw paths are walked from the canonical start of each direction (loop_start): cut_R / cut_L mark the
+     * junction IN FRONT of that start as not to be crossed by a walk of that direction */
+    char *seen = (char *)calloc(nn, 1), *stop_R = (char *)calloc(nn, 1), *stop_L = (char *)calloc(nn, 1);
+    int64_t *L = (int64_t *)malloc(nn * sizeof(int64_t));
+    int64_t *startR = (int64_t *)malloc(nn * sizeof(int64_t)), *startL = (int64_t *)malloc(nn * sizeof(int64_t));
+    int64_t n_sR = 0, n_sL = 0;
+    for (int64_t h = 0; h < n; h++) if (pred[h] < 0) { startR[n_sR++] = h; for (int64_t v = h; v >= 0; v = succ[v]) seen[v] = 1; }
+    for (int64_t t = 0; t < n; t++) if (succ[t] < 0) startL[n_sL++] = t;
+    for (int64_t v0 = 0; v0 < n; v0++) {
+        if (seen[v0]) continue;
+        int64_t m = 0;
+        for (int64_t v = v0; !seen[v]; v = succ[v]) { seen[v] = 1; L[m++] = v; }
+        int64_t st = loop_start(L, m, right, left, keys, k - 1);
+        if (st >= 0) { startR[n_sR++] = L[st]; stop_R[L[st]] = 1; }
+        /* the same loop in upstream order */
+        for (int64_t i = 0; i < m / 2; i++) { int64_t t = L[i]; L[i] = L[m - 1 - i]; L[m - 1 - i] = t; }
+        st = loop_start(L, m, left, right, keys, k - 1);
+        if (st >= 0) { startL[n_sL++] = L[st]; stop_L[L[st]] = 1; }
+    }
+    /* phase 1: right budgets, downstream */
+    for (int64_t s = 0; s < n_sR; s++) {
+        int64_t a = startR[s];
+        for (;;) {
+            const int64_t z = succ[fr[a].tail];
+            if (z < 0 || stop_R[z]) break;
+            if (fr[a].right >= 0 && fr[z].left < 0 && fr[z].n == 1 && merge_frag(fr, head_of_tail, is_tail, a, z, 0)) { is_head[z] = 0; continue; }
+            a = z;
         }
     }
-    free(seen); free(chain_len); free(succ); free(pred);
+    /* phase 2: left budgets, upstream.  b is always a fragment head */
+    for (int64_t s = 0; s < n_sL; s++) {
+        int64_t x0 = startL[s];
+        while (!is_tail[x0]) x0 = succ[x0];  /* the fragment that holds the start node */
+        int64_t b = head_of_tail[x0];
+        const int closed = stop_L[startL[s]];
+        for (;;) {
+            const int64_t zt = pred[b];
+            if (zt < 0 || (closed && zt == x0)) break;
+            const int64_t a = head_of_tail[zt];
+            if (a == b) break;
+            if (fr[b].left >= 0 && fr[a].right < 0 && fr[a].n == 1 && merge_frag(fr, head_of_tail, is_tail, a, b, 0)) { is_head[b] = 0; b = a; continue; }
+            b = a;
+        }
+    }
+    /* phase 3: whatever the clauses admit, to the fixed point */
+    for (int changed = 1; changed;) {
+        changed = 0;
+        for (int64_t a = 0; a < n; a++) {
+            if (!is_head[a]) continue;
+            for (;;) {
+                const int64_t z = succ[fr[a].tail];
+                if (z < 0 || z == a || !is_head[z]) break;
+                if (!merge_frag(fr, head_of_tail, is_tail, a, z, 1)) break;
+                is_head[z] = 0; changed = 1;
+            }
+        }
+    }
+    cbuild_t cb; cb_init(&cb, out);
+    for (int64_t h = 0; h < n; h++) {
+        if (!is_head[h]) continue;
+        int64_t s = h;
+        if (succ[fr[h].tail] == h && junction_joins(fr[h].right, fr[h].left)) { /* closed: rotate to the smallest k-mer like the canonical form (flags are those of the cut the schedule made) */
+            out->n_cycles++;
+            for (int64_t x = succ[h]; x != h; x = succ[x]) if (keys[x] < keys[s]) s = x;
+        }
+        const int64_t len = fr[h].n + k - 1;
+        if (!contig_kept(len, fr[h].left, fr[h].right, min_contig)) continue;
+        char *dst = cb_begin(&cb, (size_t)len, fr[h].left, fr[h].right);
+        for (int b = 0; b < k; b++) dst[b] = ACGT[(unsigned)(keys[s] >> (2 * (k - 1 - b))) & 3];
+        int64_t pos = k, x = succ[s];
+        for (int64_t i = 1; i < fr[h].n; i++, x = succ[x]) dst[pos++] = ACGT[(unsigned)keys[x] & 3];
+    }
+    for (int64_t i = 0; i < n; i++) if (self_loop[i] && junction_joins(right[i], left[i])) out->n_cycles++;
+    free(succ); free(pred); free(self_loop); free(fr); free(head_of_tail); free(is_head); free(is_tail); free(seen); free(stop_R); free(stop_L);
+    free(L); free(startR); free(startL);
     return 0;
 }
 
@@ -1012,9 +1198,9 @@ int orc_assemble(const uint64_t *o_hi, const uint64_t *o_lo, const int32_t *o_le
     u128 *keys = (u128 *)malloc((size_t)(n ? n : 1) * sizeof(u128));
     for (int64_t i = 0; i < n; i++) keys[i] = mk128(o_hi[i], o_lo[i]);
     for (int64_t i = 1; i < n; i++) if (!(keys[i - 1] < keys[i])) { free(keys); return -3; } /* sorted, unique */
-    int rc = mode == ORC_ASM_REFSIM
-                 ? assemble_refsim(keys, o_left, o_right, n, k, min_contig, min_iter, max_iter, out)
-                 : assemble_canonical(keys, o_left, o_right, n, k, min_contig, out);
+    int rc = mode == ORC_ASM_REFSIM      ? assemble_refsim(keys, o_left, o_right, n, k, min_contig, min_iter, max_iter, out)
+             : mode == ORC_ASM_SCHEDULED ? assemble_scheduled(keys, o_left, o_right, n, k, min_contig, out)
+                                         : assemble_canonical(keys, o_left, o_right, n, k, min_contig, out);
     free(keys);
     return rc;
 }

@@ -66,8 +66,9 @@ int64_t orc_sorted_rows(const uint64_t *keys_hi, const uint64_t *keys_lo, const 
 
 /* Extension (A9 + A10) ---------------------------------------------------- */
 enum {
-    ORC_ASM_CANONICAL = 0, /* fixed point: maximal chains over mergeable junctions */
-    ORC_ASM_REFSIM = 1     /* pass-by-pass simulation of sort + DSExtendReflexivKmer* */
+    ORC_ASM_CANONICAL = 0, /* fixed point under the canonical schedule: budget walks (closed form), then maximal chains */
+    ORC_ASM_REFSIM = 1,    /* pass-by-pass simulation of sort + DSExtendReflexivKmer* with the reference's own toggle order */
+    ORC_ASM_SCHEDULED = 2  /* the reference's four merge clauses applied literally under the canonical schedule */
 };
 
 typedef struct {
@@ -77,8 +78,8 @@ typedef struct {
     int32_t *left;
     int32_t *right;
     int64_t n_passes;          /* refsim only */
-    int64_t n_budget_junctions;/* junctions with exactly one flag >= 0 (left unmerged by the canonical rule) */
-    int64_t n_budget_admissible;/* ... of which a clause-3/4 merge would be admissible at the fixed point */
+    int64_t n_budget_junctions;/* junctions whose two flags have different signs as the fork filters left them */
+    int64_t n_budget_admissible;/* k-mers absorbed by budget walks (clause 3 / 4 merges, DSMain:3077-3084) */
     int64_t n_cycles;
 } orc_contigs;
 

@@ -294,9 +294,11 @@ __global__ void sorted_left_kernel(Graph<KT> G, int E, double fold, int X, uint8
     }
 }
 
-// Neighbour links.  succ/pred are preset to NONE32.  On one GPU a node writes its successor's pred[]; in a sharded
-// run (SHARDED) a node may only write its own entries, so it finds its predecessor itself (4 more probes) and reads
-// the neighbour's flag signs from the alive byte.
+// Neighbour links.  succ/pred are preset to NONE32.  On one GPU a node writes its successor's pred[] and EVERY junction
+// is linked (raw links): which of them hold is decided afterwards (budget walks + junction_finalize_kernel) and only
+// matters when some flag is non-negative, i.e. a real fork survived (DS_FLAGGED).  In a sharded run (SHARDED) a node
+// may only write its own entries, so it finds its predecessor itself (4 more probes) and reads the neighbour's flag
+// signs from the alive byte.
 template <class KT, bool SHARDED>
 __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag,
                             uint32_t* __restrict__ succ, uint32_t* pred, uint32_t* __restrict__ open_next, unsigned long long* dstat, uint64_t lo, uint64_t hi) {
@@ -318,17 +320,19 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
             if (oy != NONE32 && (alive[oy] & 2)) { next = oy; n_cand++; }
         }
         if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
+        if (!SHARDED && (lflag[oid] >= 0 || rflag[oid] >= 0)) atomicAdd(&dstat[DS_FLAGGED], 1ull);
         if (next != NONE32) {
             const bool joins = SHARDED ? (((alive[oid] >> 2) & 1) == ((alive[next] >> 3) & 1)) : junction_joins(rflag[oid], lflag[next]);
-            if (joins) {
-                if (next == (uint32_t)oid) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
-                else {
-                    succ[oid] = next;
-                    if (!SHARDED && atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
-                }
+            if (!joins) atomicAdd(&dstat[DS_BUDGET], 1ull);
+            if (next == (uint32_t)oid) {
+                if (joins) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
+            } else if (!SHARDED) {
+                succ[oid] = next;
+                if (atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+            } else if (joins) {
+                succ[oid] = next;
             } else {
                 open_next[oid] = next;
-                atomicAdd(&dstat[DS_BUDGET], 1ull);
             }
         }
         if (SHARDED) {
@@ -345,6 +349,81 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
             if (n_prev > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 2ull); continue; }
             if (prev != NONE32 && prev != (uint32_t)oid && (((alive[prev] >> 2) & 1) == ((alive[oid] >> 3) & 1))) pred[oid] = prev;
         }
+    }
+}
+
+// ---- budget walks (A9, clauses 3 / 4: ReflexivDSMain.java:3077-3084, flag rule of reflexivExtend :3265-3279) ----------
+// A fork winner's flag k-1 facing a clean end is a budget: the flagged fragment absorbs clean k-mers one at a time, the
+// budget shrinks by one per k-mer and overwrites the flag of the new outer end; it stops in front of a non-negative
+// facing flag (clause 2 joins there) or when it is used up.  Canonical schedule (oracle: budget_scan): along
+// a path   E(v) = (face(v) < 0 && E(prev(v)) >= 1) ? E(prev(v)) - 1 : budget(v),   once along succ (budget = right flag,
+// face = left flag) and once along pred.  Fork winners are rare, so the recurrence is evaluated from them: a thread per
+// node with a budget first decides whether an upstream walk absorbs it (it looks upstream until a node that cannot be
+// absorbed, a path end, or k-1 budget-less nodes in a row -- no walk survives those), then, if not, walks downstream
+// writing the effective flags of what it absorbs and marking the junctions it went through (alive bit 4 / 5 on the
+// junction's left node).  On a closed path where every walk may wrap around, the fork winner with the smallest oriented
+// k-mer starts fresh (oracle: loop_start).
+__device__ __forceinline__ void alive_or(uint8_t* alive, uint64_t i, uint32_t bit) {
+    atomicOr(reinterpret_cast<unsigned int*>(alive + (i & ~(uint64_t)3)), bit << (8u * (uint32_t)(i & 3u)));
+}
+template <class KT, int DIR>
+__global__ void budget_walk_kernel(Graph<KT> G, uint64_t n, uint8_t* alive, const int32_t* __restrict__ bud, const int32_t* __restrict__ face,
+                                   const uint32_t* __restrict__ nxt, const uint32_t* __restrict__ prv, int32_t* eff, int bmax, unsigned long long* dstat) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2) || bud[x] < 0) continue;
+        const uint32_t s = (uint32_t)x;
+        if (nxt[s] == NONE32) continue;  // nothing downstream to absorb
+        uint32_t stop = s;
+        bool fresh = true;
+        if (face[s] < 0 && prv[s] != NONE32) {
+            uint32_t u = prv[s], start = NONE32;
+            int gap = 0;
+            while (true) {
+                if (u == s) break;  // closed path without a fixed point: smallest fork winner starts
+                gap = bud[u] < 0 ? gap + 1 : 0;
+                if (face[u] >= 0 || prv[u] == NONE32 || gap >= bmax) { start = u; break; }
+                u = prv[u];
+            }
+            if (start == NONE32) {
+                uint32_t m = s;
+                KT mk = G.oriented(s);
+                for (u = prv[s]; u != s; u = prv[u])
+                    if (bud[u] >= 0) { const KT ku = G.oriented(u); if (ku < mk) { mk = ku; m = u; } }
+                start = m;
+                stop = m;
+            }
+            if (start != s) {
+                int32_t E = bud[start];
+                for (uint32_t v = nxt[start]; v != s; v = nxt[v]) E = (face[v] < 0 && E >= 1) ? E - 1 : bud[v];
+                fresh = !(E >= 1);  // face[s] < 0 here
+            }
+        }
+        if (!fresh) continue;  // absorbed: the walk that takes it writes its flag
+        int32_t rem = bud[s];
+        uint32_t cur = s;
+        unsigned long long taken = 0;
+        while (rem >= 1) {
+            const uint32_t z = nxt[cur];
+            if (z == NONE32 || z == stop || z == s || face[z] >= 0) break;
+            rem--;
+            eff[z] = rem;
+            alive_or(alive, DIR == 0 ? cur : z, DIR == 0 ? 16u : 32u);
+            taken++;
+            cur = z;
+        }
+        if (taken) atomicAdd(&dstat[DS_ABSORBED], taken);
+    }
+}
+// which junctions hold: a walk went through, or the effective flags have the same sign
+__global__ void junction_finalize_kernel(uint64_t n, const uint8_t* __restrict__ alive, const int32_t* __restrict__ eff_l, const int32_t* __restrict__ eff_r,
+                                         uint32_t* succ, uint32_t* pred) {
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(alive[x] & 2)) continue;
+        const uint32_t y = succ[x];
+        if (y == NONE32) continue;
+        if ((alive[x] & 48) || junction_joins(eff_r[x], eff_l[y])) continue;
+        succ[x] = NONE32;
+        pred[y] = NONE32;
     }
 }
 
@@ -503,17 +582,6 @@ __global__ void tails_kernel(uint64_t n, const uint8_t* __restrict__ alive, cons
             chain_len[h] = (uint32_t)(v >> 32) + 1u;
             tail_of[h] = (uint32_t)x;
         }
-    }
-}
-
-__global__ void budget_admissible_kernel(uint64_t n, const uint32_t* __restrict__ open_next, const int32_t* __restrict__ lflag,
-                                         const int32_t* __restrict__ rflag, const uint64_t* __restrict__ ad, const uint32_t* __restrict__ chain_len,
-                                         unsigned long long* dstat) {
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t y = open_next[x];
-        if (y == NONE32) continue;
-        const int64_t r_ext = (int64_t)(ad[x] >> 32) + 1, f_ext = (int64_t)chain_len[y];
-        if ((lflag[y] >= 0 && lflag[y] - r_ext >= 0) || (rflag[x] >= 0 && rflag[x] - f_ext >= 0)) atomicAdd(&dstat[DS_BUDGET_ADM], 1ull);
     }
 }
 
@@ -698,6 +766,23 @@ template <class KT> static int graph_impl(Ctx* c) {
         c->ms[3] += stage_end(c);
         if (h[DS_GRAPH_ERR]) { rc = ctx_fail(c, RFX_E_GRAPH, "fork filters left a (k-1)-mer with degree > 1 (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]); break; }
         c->n_budget = h[DS_BUDGET];
+        if (h[DS_FLAGGED]) {
+            // real forks survived the filters: budget walks, then cut the junctions that do not hold (still part of K5's time)
+            stage_begin(c);
+            if ((rc = devbuf_reserve(c, c->eff_l, n * sizeof(int32_t))) != RFX_OK) break;
+            if ((rc = devbuf_reserve(c, c->eff_r, n * sizeof(int32_t))) != RFX_OK) break;
+            cudaMemcpyAsync(c->eff_l.p, lflag, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(c->eff_r.p, rflag, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+            budget_walk_kernel<KT, 0><<<grid_n(n), 256, 0, st>>>(G, n, alive, rflag, lflag, succ, pred, c->eff_r.as<int32_t>(), c->k - 1, dstat);
+            budget_walk_kernel<KT, 1><<<grid_n(n), 256, 0, st>>>(G, n, alive, lflag, rflag, pred, succ, c->eff_l.as<int32_t>(), c->k - 1, dstat);
+            junction_finalize_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, c->eff_l.as<int32_t>(), c->eff_r.as<int32_t>(), succ, pred);
+            c->launches += 3;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "budget walks failed: %s", cudaGetErrorString(e)); break; }
+            c->ms[3] += stage_end(c);
+            lflag = c->eff_l.as<int32_t>();  // the contig stage reads the effective flags of heads and tails
+            rflag = c->eff_r.as<int32_t>();
+        }
 
         // ---- K6 ----
         stage_begin(c);
@@ -790,8 +875,7 @@ template <class KT> static int graph_impl(Ctx* c) {
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "list ranking failed: %s", cudaGetErrorString(e)); break; }
         const uint64_t* ad = c->ad[cur].as<uint64_t>();
         tails_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, succ, ad, c->chain_len.as<uint32_t>(), c->tail_of.as<uint32_t>());
-        budget_admissible_kernel<<<grid_n(n), 256, 0, st>>>(n, open_next.as<uint32_t>(), lflag, rflag, ad, c->chain_len.as<uint32_t>(), dstat);
-        c->launches += 2;
+        c->launches += 1;
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = ctx_fail(c, RFX_E_CUDA, "chain kernels failed: %s", cudaGetErrorString(e)); break; }
         c->ms[4] += stage_end(c);
@@ -825,7 +909,7 @@ template <class KT> static int graph_impl(Ctx* c) {
         c->n_contigs = tot.a;
         c->n_contig_bases = tot.b;
         c->n_oriented = tot.c;
-        c->n_budget_adm = h[DS_BUDGET_ADM];
+        c->n_budget_adm = h[DS_ABSORBED];
         c->n_cycles = h[DS_CYCLES];
         c->have_contigs = true;
     } while (0);

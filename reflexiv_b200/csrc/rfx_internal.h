@@ -115,6 +115,7 @@ struct Ctx {
     uint32_t g_bins = 0;
     int g_m = 11;
     DevBuf rflag, lflag;  // i32[2*n_rows]
+    DevBuf eff_l, eff_r;  // i32[2*n_rows] flags after the budget walks (only when a fork winner survived)
     DevBuf alive;         // u8[2*n_rows]  bit0: survives right filter, bit1: survives both
     DevBuf succ, pred;    // u32[2*n_rows]
     DevBuf ad[2];         // u64[2*n_rows] packed (ancestor, distance) for pointer jumping, double buffered
@@ -171,6 +172,8 @@ enum {
     DS_OVF_RECORDS = 20,
     DS_SCAN_TODO = 21,    // the register-resident scan left reads to the general kernel  // records that did not fit their slab (single-pass partition)
     DS_OVF_WHY = 16,   // 4 slots: why counting bins were split (table full, probe exhausted, tag collision, narrow probe exhausted)
+    DS_FLAGGED = 23,      // surviving oriented k-mers with a non-negative flag (fork winners): budget walks needed
+    DS_ABSORBED = 27,     // k-mers absorbed by budget walks
     DS_RANK_CUR = 22,     // which of the two (ancestor, distance) buffers holds the result of rank_all_kernel
     DS_RANK_FLAGS = 24,
     DS_READ_TOTALS = 28,  // 2 slots: bases kept and k-mer instances of the reads being appended   // 3 rotating 'something changed' flags of rank_all_kernel

@@ -318,6 +318,61 @@ def test_assembly_with_the_bin_local_index(R, orc, monkeypatch, k, cover, E, err
     _check_assembly(R, orc, txt, k, cover, E, min_contig=100)
 
 
+def _uniform_table(g: np.ndarray, k: int, seed: int):
+    """Canonical k-mer table of a genome with near-equal counts (10..12): every fork is a real one (flag k-1)."""
+    code = np.zeros(256, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        code[ch] = i
+    c = code[g].astype(object)
+    mask = (1 << (2 * k)) - 1
+    fwd = rc = 0
+    seen = {}
+    for i, v in enumerate(c.tolist()):
+        fwd = ((fwd << 2) | v) & mask
+        rc = (rc >> 2) | ((3 - v) << (2 * (k - 1)))
+        if i >= k - 1:
+            key = min(fwd, rc)
+            seen.setdefault(key, 10 + (hash((key, seed)) % 3))
+    keys = np.array(sorted(seen), dtype=np.uint64)
+    counts = np.array([seen[int(x)] for x in keys], dtype=np.uint32)
+    return keys, counts
+
+
+@pytest.mark.parametrize("k,glen,seed", [(9, 3000, 1), (10, 2000, 4), (11, 20000, 2), (13, 60000, 3), (12, 40000, 6), (31, 8000, 5)])
+def test_budget_walks_on_dense_forks(R, orc, monkeypatch, k, glen, seed):
+    """A9 clauses 3 / 4 (ReflexivDSMain.java:3077-3084): fork winners absorb up to k-1 clean k-mers.  Random genomes at small k
+    are full of repeated (k-1)-mers, so winners sit within reach of each other, face each other and lie on closed paths;
+    the GPU must give the oracle's canonical contigs WITH their header flags, and the canonical closed form must equal
+    the reference's four merge clauses applied literally under the same schedule (ORC_ASM_SCHEDULED)."""
+    from reflexiv_b200 import synth
+    g = synth.genome(glen, 300 + seed)
+    if k == 31:
+        g[5000:5400] = g[1000:1400]
+        g[7000:7060] = g[2000:2060]
+        g[3000] = ord("A") if g[3000] != ord("A") else ord("C")
+    keys, counts = _uniform_table(g, k, seed)
+    zero = np.zeros(len(keys), np.uint64)
+    ff = orc.fork_filter(zero, keys, counts, k, 8)
+    a = orc.assemble(ff["keys_hi"], ff["keys_lo"], ff["left"], ff["right"], k, k, orc.ASM_CANONICAL)
+    s = orc.assemble(ff["keys_hi"], ff["keys_lo"], ff["left"], ff["right"], k, k, orc.ASM_SCHEDULED)
+    assert a["n_budget_admissible"] > 0 and a["n_budget_junctions"] > 0
+    if a["n_cycles"] == 0 and s["n_cycles"] == 0:
+        assert sorted(zip(a["contigs"], a["left"].tolist(), a["right"].tolist())) == sorted(zip(s["contigs"], s["left"].tolist(), s["right"].tolist()))
+    else:
+        assert sorted(a["contigs"]) == sorted(s["contigs"])  # where a closed contig is cut decides its two flags
+    for index in ("global", "local"):
+        monkeypatch.setenv("RFX_GRAPH_INDEX", index)
+        with R.ReflexivContext(_param(R, kmerSize=k, minContig=k)) as ctx:
+            ctx.load_counts(keys.reshape(-1, 1), counts)
+            st = ctx.assemble()
+            hi, lo, le, ri = ctx.oriented()
+            contigs = ctx.contigs()
+        order = np.lexsort((lo, hi))
+        assert np.array_equal(lo[order], ff["keys_lo"]) and np.array_equal(le[order], ff["left"]) and np.array_equal(ri[order], ff["right"])
+        assert (st["n_budget_junctions"], st["n_budget_admissible"], st["n_cycles"]) == (a["n_budget_junctions"], a["n_budget_admissible"], a["n_cycles"])
+        assert sorted(contigs) == sorted(zip(a["contigs"], a["left"].tolist(), a["right"].tolist()))
+
+
 def test_cycles_and_tiny_graphs(R, orc, monkeypatch):
     def fq(seqs):
         return "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(seqs)).encode()
