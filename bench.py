@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
 def make_inputs(rank: int, world: int, genome_len: int = GENOME_LEN, error_rate: float = 0.0):
     """This rank's FASTQ text: pairs [rank*P, (rank+1)*P) of a genome of world * 4.6 Mbp."""
     import numpy as np
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(genome_len * world)
     pairs = synth.n_pairs_for(genome_len, COVERAGE, READ_LEN)
     txt = synth.fastq(g, pairs, read_len=READ_LEN, frag_len=400, first_pair=rank * pairs, error_rate=error_rate)
@@ -88,7 +88,7 @@ def cpu_reference_run(sample_reads: int = 1_000_000, threads: int = 0):
     filter -> fork filters -> sort + merge passes), on a bounded sample of the same workload."""
     import numpy as np
     from oracle import orc
-    from reflexiv_b200 import synth
+    from workload import synth
     threads = threads or os.cpu_count() or 1
     # sample = the reads of a 1/x genome at the same coverage, so the k-mer spectrum is that of the workload
     frac_genome = max(20_000, int(GENOME_LEN * sample_reads / (2 * synth.n_pairs_for(GENOME_LEN, COVERAGE, READ_LEN))))

@@ -232,20 +232,6 @@ int rfx_gs_rank(rfx_ctx* ctx, const uint32_t* d_node, const uint32_t* d_next, co
 int rfx_gs_contigs(rfx_ctx* ctx, const void* d_tails, uint64_t n_tails, const void* d_heads, uint64_t n_heads, char** d_bases, uint64_t* n_bases);
 int rfx_gs_finish(rfx_ctx* ctx, uint64_t n_oriented, uint64_t n_budget_junctions, uint64_t n_budget_admissible, uint64_t n_cycles);
 
-/* ---- synthetic data (host, deterministic) ----------------------------------------- */
-int64_t rfx_synth_genome(uint8_t* out, int64_t n_bases, uint64_t seed);
-/* FASTQ text of pairs [first_pair, first_pair+n_pairs): mate 1 records then mate 2 records.
- * Returns bytes written, or the required capacity when out == NULL. */
-int64_t rfx_synth_fastq(const uint8_t* genome, int64_t genome_len, int64_t first_pair, int64_t n_pairs,
-                        int32_t read_len, int32_t frag_len, double error_rate, uint64_t seed_reads,
-                        uint64_t seed_errors, uint8_t* out, int64_t cap);
-
-/* ---- debug / test access to intermediate device state (copies to host) ----------------------- */
-int rfx_debug_reads(rfx_ctx* ctx, uint64_t* n_reads, uint64_t* total_words, uint32_t* lens /*n_reads or NULL*/,
-                    uint64_t* word_offsets /*n_reads or NULL*/, uint64_t* words /*total_words or NULL*/);
-int rfx_debug_records(rfx_ctx* ctx, uint64_t* n_records, uint32_t* n_bins, uint64_t* bin_offsets /*n_bins+1 or NULL*/,
-                      uint64_t* records /* n_records * words or NULL */);
-
 const char* rfx_version(void);
 
 #ifdef __cplusplus

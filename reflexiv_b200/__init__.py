@@ -8,7 +8,6 @@ There is no CPU implementation here: every entry point fails if the CUDA library
 from ._lib import RfxError, load_library, lib_path  # noqa: F401
 from .params import DefaultParam, Parameter, ParameterOfCounter  # noqa: F401
 from .pipeline import ReflexivContext, Pipelines  # noqa: F401
-from . import synth  # noqa: F401
 
 __all__ = ["RfxError", "load_library", "lib_path", "DefaultParam", "Parameter", "ParameterOfCounter",
-           "ReflexivContext", "Pipelines", "synth"]
+           "ReflexivContext", "Pipelines"]

@@ -83,11 +83,6 @@ SYMBOLS = {
     "rfx_load_segment_device": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "rfx_counts_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "rfx_load_counts_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32]),
-    "rfx_synth_genome": (C.c_int64, [_P, C.c_int64, C.c_uint64]),
-    "rfx_synth_fastq": (C.c_int64, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_uint64,
-                                    C.c_uint64, _P, C.c_int64]),
-    "rfx_debug_reads": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P, _P, _P]),
-    "rfx_debug_records": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), _P, _P]),
 }
 
 

@@ -299,26 +299,33 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     const char* sp_env = getenv("RFX_STREAM_PARTITION");
     bool stream_part = n_chunks >= 2 && c->n_reads == 0 && !(sp_env && !strcmp(sp_env, "0"));
     c->sp_active = false;
-    RFX_CUDA(c, cudaMemsetAsync(d_text + len, 0, 128, c->copy_stream));
-    RFX_CUDA(c, cudaMemcpyAsync(d_text, buf, cuts[1], cudaMemcpyHostToDevice, c->copy_stream));
-    RFX_CUDA(c, cudaEventRecord(c->copy_done[0], c->copy_stream));
-    for (size_t i = 0; i < n_chunks; i++) {
-        if (i + 1 < n_chunks) {
-            RFX_CUDA(c, cudaMemcpyAsync(d_text + cuts[i + 1], buf + cuts[i + 1], cuts[i + 2] - cuts[i + 1], cudaMemcpyHostToDevice, c->copy_stream));
-            RFX_CUDA(c, cudaEventRecord(c->copy_done[(i + 1) & 1], c->copy_stream));
-        }
-        RFX_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[i & 1], 0));
-        RFX_TRY(stage_parse_fastq(c, d_text + cuts[i], cuts[i + 1] - cuts[i], i == 0, i + 1 < n_chunks));
-        if (stream_part) {
-            if (i == 0) {
-                if (c->n_reads == 0) { stream_part = false; continue; }
-                const double scale = 1.02 * (double)len / (double)cuts[1];
-                RFX_TRY(stage_stream_partition_begin(c, (uint64_t)((double)c->n_instances * scale) + 1, (uint64_t)((double)c->n_reads * scale) + 1));
+    // every error path waits for the copy stream: the next chunk's upload may still be reading the caller's buffer,
+    // and the header promises that host buffers are not touched after the call returns
+    auto body = [&]() -> int {
+        RFX_CUDA(c, cudaMemsetAsync(d_text + len, 0, 128, c->copy_stream));
+        RFX_CUDA(c, cudaMemcpyAsync(d_text, buf, cuts[1], cudaMemcpyHostToDevice, c->copy_stream));
+        RFX_CUDA(c, cudaEventRecord(c->copy_done[0], c->copy_stream));
+        for (size_t i = 0; i < n_chunks; i++) {
+            if (i + 1 < n_chunks) {
+                RFX_CUDA(c, cudaMemcpyAsync(d_text + cuts[i + 1], buf + cuts[i + 1], cuts[i + 2] - cuts[i + 1], cudaMemcpyHostToDevice, c->copy_stream));
+                RFX_CUDA(c, cudaEventRecord(c->copy_done[(i + 1) & 1], c->copy_stream));
             }
-            RFX_TRY(stage_stream_partition_scan(c));
+            RFX_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_done[i & 1], 0));
+            RFX_TRY(stage_parse_fastq(c, d_text + cuts[i], cuts[i + 1] - cuts[i], i == 0, i + 1 < n_chunks));
+            if (stream_part) {
+                if (i == 0) {
+                    if (c->n_reads == 0) { stream_part = false; continue; }
+                    const double scale = 1.02 * (double)len / (double)cuts[1];
+                    RFX_TRY(stage_stream_partition_begin(c, (uint64_t)((double)c->n_instances * scale) + 1, (uint64_t)((double)c->n_reads * scale) + 1));
+                }
+                RFX_TRY(stage_stream_partition_scan(c));
+            }
         }
-    }
-    return RFX_OK;
+        return RFX_OK;
+    };
+    const int rc = body();
+    if (rc != RFX_OK) cudaStreamSynchronize(c->copy_stream);
+    return rc;
 }
 
 int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {
@@ -747,29 +754,6 @@ int rfx_gs_finish(rfx_ctx* c, uint64_t n_oriented, uint64_t n_budget, uint64_t n
     c->n_oriented = n_oriented; c->n_budget = n_budget; c->n_budget_adm = n_budget_admissible; c->n_cycles = n_cycles;
     c->gs_step = 0;
     c->have_contigs = true;
-    return RFX_OK;
-}
-
-// ---- debug ---------------------------------------------------------------------------------------
-int rfx_debug_reads(rfx_ctx* c, uint64_t* n_reads, uint64_t* total_words, uint32_t* lens, uint64_t* word_offsets, uint64_t* words) {
-    if (!c) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    if (n_reads) *n_reads = c->n_reads;
-    if (total_words) *total_words = c->n_words;
-    if (lens && c->n_reads) RFX_CUDA(c, cudaMemcpy(lens, c->rd_len.p, c->n_reads * 4, cudaMemcpyDeviceToHost));
-    if (word_offsets && c->n_reads) RFX_CUDA(c, cudaMemcpy(word_offsets, c->rd_woff.p, c->n_reads * 8, cudaMemcpyDeviceToHost));
-    if (words && c->n_words) RFX_CUDA(c, cudaMemcpy(words, c->packed.p, c->n_words * 8, cudaMemcpyDeviceToHost));
-    return RFX_OK;
-}
-
-int rfx_debug_records(rfx_ctx* c, uint64_t* n_records, uint32_t* n_bins, uint64_t* bin_offsets, uint64_t* records) {
-    if (!c) return RFX_E_INVALID;
-    if (!c->have_records) return ctx_fail(c, RFX_E_STATE, "no records");
-    cudaSetDevice(c->prm.device);
-    if (n_records) *n_records = c->n_records;
-    if (n_bins) *n_bins = c->n_bins;
-    if (bin_offsets) RFX_CUDA(c, cudaMemcpy(bin_offsets, c->bin_off.p, ((size_t)c->n_bins + 1) * 8, cudaMemcpyDeviceToHost));
-    if (records && c->n_records) RFX_CUDA(c, cudaMemcpy(records, c->records.p, c->n_records * c->recw * 8, cudaMemcpyDeviceToHost));
     return RFX_OK;
 }
 

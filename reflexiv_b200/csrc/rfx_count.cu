@@ -419,7 +419,9 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 }
             }
             compute_barrier<NT>();
-            if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_overflow = 0; s_npass = 0; s_cursor = 0; }
+            // (s_overflow is NOT reset here: warps past this barrier may already be flagging it in phase B.  It is zero on
+            // entry to every bin: cleared at kernel start, and by whoever consumed it -- the split path below)
+            if (fast && tid == 0) { s_nuniq[par ^ 1] = 0; s_distinct[par ^ 1] = 0; s_npass = 0; s_cursor = 0; }
             // ---- B: expand the distinct records, spread evenly over the warps ----
             const int n_uniq = (int)*nuniq;
             int per = (n_uniq + NW - 1) / NW;
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             run_chunk(n_rec, 0u, 0u, true);
             // (run_chunk ended on a barrier: the stage and the record-tag table are free, the k-mer table is complete)
             const bool ovf = s_overflow != 0;
-            const uint32_t nd = s_distinct[par];
+            const uint32_t nd = s_distinct[par] < (uint32_t)KmerTable<WIDE, CAP>::KMAX ? s_distinct[par] : (uint32_t)KmerTable<WIDE, CAP>::KMAX;
             if (!ovf) {
                 if (tid == 0) mbar_arrive(&s_empty[st]);
                 // K4: coverage filter + compaction over the occupied slots, all warps (its two counters were cleared
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
             }
             if (n_rec > (uint32_t)CHUNK) staged = false;
             // ---- K4: coverage filter + compaction over the occupied slots ----
-            const uint32_t nd = s_distinct[par];
+            const uint32_t nd = s_distinct[par] < (uint32_t)KmerTable<WIDE, CAP>::KMAX ? s_distinct[par] : (uint32_t)KmerTable<WIDE, CAP>::KMAX;
             uint32_t mine = 0, inst = 0;
             for (uint32_t i = tid; i < nd; i += NT) {
                 const uint32_t c = cnts[klist[i]];
@@ -629,7 +631,7 @@ template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t l
                         (size_t)(RCAP * 3 / 4) * 2 + (size_t)(CAP * 3 / 4) * 2;
     cudaError_t e = cudaFuncSetAttribute(count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    unsigned grid = 148u * PER_SM;
+    unsigned grid = sm_count() * PER_SM;
     if (grid > A.n_tickets) grid = A.n_tickets;
     count_bins_kernel<WIDE, CAP, RCAP, NT, PER_SM><<<grid, NT + 32, smem, st>>>(A);
     return cudaGetLastError();

@@ -267,7 +267,8 @@ __global__ void offsets_to_u64_kernel(const uint64_t* in, uint64_t n, uint64_t* 
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
-static unsigned grid_for(uint64_t n, int block, unsigned cap = 148 * 16) {
+static unsigned grid_for(uint64_t n, int block, unsigned cap = 0) {
+    if (!cap) cap = sm_count() * 16;
     uint64_t g = (n + block - 1) / block;
     if (g < 1) g = 1;
     return (unsigned)(g > cap ? cap : g);
@@ -299,8 +300,8 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* 
         cudaMemsetAsync(totals, 0, 2 * sizeof(uint64_t), st);
         ReadOut out{in, c->n_reads, c->n_words, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(), c->rd_woff.as<uint64_t>()};
         scan_apply(plan, in, out, OpAddU64{}, (uint64_t)0, st);
-        read_totals_kernel<<<grid_for(n_new, 256, 148 * 2), 256, 0, st>>>(c->rd_len.as<uint32_t>() + c->n_reads, n_new, c->k, totals);
-        encode_reads_kernel<<<grid_for(n_new * 8, 256, 148 * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
+        read_totals_kernel<<<grid_for(n_new, 256, sm_count() * 2), 256, 0, st>>>(c->rd_len.as<uint32_t>() + c->n_reads, n_new, c->k, totals);
+        encode_reads_kernel<<<grid_for(n_new * 8, 256, sm_count() * 32), 256, 0, st>>>(d_text, rd_src.as<uint64_t>(), c->rd_len.as<uint32_t>(),
                                                                                 c->rd_woff.as<uint64_t>(), n_new, c->n_reads,
                                                                                 c->packed.as<uint64_t>());
         // padding words after the last read: packed_window() may look one word ahead

@@ -650,7 +650,8 @@ struct AliveBoth {
 static unsigned grid_n(uint64_t n) {
     uint64_t g = (n + 255) / 256;
     if (g < 1) g = 1;
-    return (unsigned)(g > 148u * 16u ? 148u * 16u : g);
+    const uint64_t cap = (uint64_t)sm_count() * 16u;
+    return (unsigned)(g > cap ? cap : g);
 }
 
 template <class KT> static Graph<KT> make_graph(Ctx* c) {
@@ -800,7 +801,7 @@ template <class KT> static int graph_impl(Ctx* c) {
                 cudaMemsetAsync(loc, 0xff, n * sizeof(uint64_t), st);
                 splitter_select_kernel<<<grid_n(n), 256, 0, st>>>(n, alive, pred, spl_id, spl_node, c->sp_ad[0].as<uint64_t>(), dstat);
                 // select -> walk -> jumping rounds -> finalize; the splitter count stays on the device
-                splitter_walk_kernel<<<148 * 16, 256, 0, st>>>(dstat + DS_NSPL, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
+                splitter_walk_kernel<<<sm_count() * 16, 256, 0, st>>>(dstat + DS_NSPL, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
                 cudaMemsetAsync(dstat + DS_RANK_FLAGS, 0, 3 * sizeof(uint64_t), st);
                 cudaMemsetAsync(dstat + DS_RANK_CUR, 0, sizeof(uint64_t), st);
                 if (n <= (16ull << 20)) {
@@ -810,7 +811,7 @@ template <class KT> static int graph_impl(Ctx* c) {
                     uint64_t* a1 = c->sp_ad[1].as<uint64_t>();
                     unsigned long long* ds = dstat;
                     void* args[] = {(void*)&m_ptr, (void*)&a0, (void*)&a1, (void*)&ds};
-                    e = cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(148 * 4), dim3(256), args, 0, st);
+                    e = cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(sm_count() * 4), dim3(256), args, 0, st);
                     if (e != cudaSuccess) break;
                 } else {
                     // long lists: one launch per round over as many threads as entries (the co-resident grid of the
@@ -1193,7 +1194,7 @@ static int gs_rank_impl(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, 
                 uint64_t* a1 = c->sp_ad[1].as<uint64_t>();
                 unsigned long long* ds = dstat;
                 void* args[] = {(void*)&m_ptr, (void*)&a0, (void*)&a1, (void*)&ds};
-                RFX_CUDA(c, cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(148 * 4), dim3(256), args, 0, st));
+                RFX_CUDA(c, cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(sm_count() * 4), dim3(256), args, 0, st));
             }
             uint64_t which = 0;
             RFX_CUDA(c, cudaMemcpyAsync(&which, dstat + DS_RANK_CUR, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));

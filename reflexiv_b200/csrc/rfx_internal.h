@@ -182,6 +182,20 @@ enum {
 
 static const uint32_t NONE32 = 0xffffffffu;
 
+// SMs of the current device (148 on a B200), queried once per device: launch grids are sized in multiples of it
+inline unsigned sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev] = n;
+    }
+    return (unsigned)cached[dev];
+}
+
 // stage entry points (each in its own .cu)
 int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chunk = true, bool more_follows = false);
 int stage_push_reads(Ctx* c, const uint8_t* h_bases, const uint64_t* h_offsets, uint64_t n_reads);

@@ -9,9 +9,11 @@
 // instance), and all instances of one canonical k-mer are guaranteed to land in one bin because the
 // bin is a function of the strand-symmetric minimiser of the k-mer.
 //
-// Two launches of one kernel: (1) histogram of records per bin, (2) scatter.  One thread walks one
-// read (rfx_core.h: bin_scan_read); the sliding-minimum ring lives in shared memory, interleaved by
-// lane so the 32 reads of a warp never bank-conflict.
+// One GPU: ONE pass over the reads -- the scan kernel cuts every run's record out of the read and stores it at
+// bin * cap + atomicAdd(cursor[bin]) ("slab" layout, SlabFactory).  Runs that are exchanged between GPUs through NCCL
+// (rfx_partition) take two passes: descriptors + bin histogram, prefix scan, then emit_records_kernel scatters the
+// records into the compact shard-major layout.  One thread walks one read; the register-resident fast path keeps the
+// whole sliding-minimum state in registers, the general kernel keeps a lane-interleaved ring in shared memory.
 #include "rfx_internal.h"
 #include "rfx_scan.cuh"
 
@@ -523,7 +525,7 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     // one tile of PART_THREADS reads per block as long as that stays below 148 * 256 blocks: with 7 blocks resident per
     // SM a block-strided loop of 2-3 tiles per block ends in a ragged last wave (measured at config 2: capped at
     // 148 * 64 blocks 1.028 ms, one tile per block 1.006 ms)
-    const unsigned grid_cap = 148u * 256u;
+    const unsigned grid_cap = sm_count() * 256u;
     if (grid > grid_cap) grid = grid_cap;
     const uint32_t* rd_len = c->rd_len.as<uint32_t>() + read_off;
     const uint64_t* rd_woff = c->rd_woff.as<uint64_t>() + read_off;
@@ -532,7 +534,7 @@ template <class Factory> static int launch_scan(Ctx* c, const BinParams& P, cons
     const bool fixed = P.k == 31 && P.m == 11, fast15 = P.k == 31 && P.m == 15;
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<true, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     RFX_CUDA(c, cudaFuncSetAttribute(bin_scan_kernel<false, Factory>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
-    const unsigned grid2 = grid < 148u * 4u ? grid : 148u * 4u;  // follow-up pass: usually nothing to do
+    const unsigned grid2 = grid < sm_count() * 4u ? grid : sm_count() * 4u;  // follow-up pass: usually nothing to do
     if (fixed) {
         // register-resident scan for every warp of equal-length reads, then the general kernel for what it left behind
         bin_scan_fast_kernel<31, 11, Factory><<<grid, PART_THREADS, 0, st>>>(c->packed.as<uint64_t>(), rd_len, rd_woff,
@@ -661,7 +663,7 @@ static int slab_finish(Ctx* c) {
             scan_apply(plan, OvfCountIn{bin_cnt, (uint32_t)cap}, BinOffset2Out{c->bin_off.as<uint64_t>()}, OpAddU64{}, (uint64_t)0, st);
             set_last_offset_kernel<<<1, 1, 0, st>>>(c->bin_off.as<uint64_t>(), c->n_bins, plan.total);
             unsigned g2 = (unsigned)((n_ovf + 255) / 256);
-            if (g2 > 148u * 16u) g2 = 148u * 16u;
+            if (g2 > sm_count() * 16u) g2 = sm_count() * 16u;
             if (c->recw == 2) ovf_scatter_kernel<2><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
             else ovf_scatter_kernel<4><<<g2, 256, 0, st>>>(c->ovf_rec.as<uint64_t>(), c->ovf_bin.as<uint32_t>(), n_ovf, c->bin_off.as<uint64_t>(), ovf_cursor_bin, c->rx_records.as<uint64_t>());
             c->launches += 2 * plan.levels + 2;
@@ -739,7 +741,7 @@ int stage_partition(Ctx* c, int n_shards) {
     const size_t smem = (size_t)2 * P.w * PART_THREADS * sizeof(uint32_t);           // sliding-minimum ring (spill pass)
     unsigned grid = (unsigned)((c->n_reads + PART_THREADS - 1) / PART_THREADS);
     if (grid < 1) grid = 1;
-    if (grid > 148u * 64u) grid = 148u * 64u;
+    if (grid > sm_count() * 64u) grid = sm_count() * 64u;
     c->slab_cap = 0;
     if (c->n_reads) {
         cudaEventRecord(c->evk[0], st);
@@ -761,7 +763,7 @@ int stage_partition(Ctx* c, int n_shards) {
     RFX_TRY(devbuf_reserve(c, c->records, (n_records * c->recw + 2) * sizeof(uint64_t)));
     if (c->n_reads && n_records) {
         const uint64_t n_tiles = (c->n_reads + 31) / 32;
-        unsigned g2 = (unsigned)(n_tiles > 148u * 64u ? 148u * 64u : n_tiles);
+        unsigned g2 = (unsigned)(n_tiles > sm_count() * 64u ? sm_count() * 64u : n_tiles);
         cudaEventRecord(c->evk[2], st);
         if (c->recw == 2)
             emit_records_kernel<2><<<g2, 256, 0, st>>>(c->packed.as<uint64_t>(), c->rd_woff.as<uint64_t>(), c->n_reads, c->bin_off.as<uint64_t>(), cursor, desc, pos,
@@ -837,7 +839,7 @@ int stage_rebin(Ctx* c) {
     const uint32_t base = (uint32_t)c->shard_id * bps;
     unsigned grid = (unsigned)((n_rec + 255) / 256);
     if (grid < 1) grid = 1;
-    if (grid > 148u * 16u) grid = 148u * 16u;
+    if (grid > sm_count() * 16u) grid = sm_count() * 16u;
     if (n_rec) {
         if (c->recw == 2) rebin_kernel<2, false><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, nullptr, dstat);
         else rebin_kernel<4, false><<<grid, 256, 0, st>>>(c->rx_records.as<uint64_t>(), n_rec, P, base, bps, cursor, nullptr, dstat);

@@ -290,24 +290,6 @@ class ReflexivContext:
     def gs_finish(self, n_oriented: int, n_budget: int, n_budget_adm: int, n_cycles: int):
         self._check(self.L.rfx_gs_finish(self._ctx, n_oriented, n_budget, n_budget_adm, n_cycles), self._ctx)
 
-    # ---- debug ----
-    def debug_reads(self):
-        n, w = C.c_uint64(), C.c_uint64()
-        self._check(self.L.rfx_debug_reads(self._ctx, C.byref(n), C.byref(w), None, None, None), self._ctx)
-        lens = np.empty(n.value, dtype=np.uint32)
-        woff = np.empty(n.value, dtype=np.uint64)
-        words = np.empty(w.value, dtype=np.uint64)
-        self._check(self.L.rfx_debug_reads(self._ctx, C.byref(n), C.byref(w), lens.ctypes.data, woff.ctypes.data, words.ctypes.data), self._ctx)
-        return lens, woff, words
-
-    def debug_records(self):
-        n, nb = C.c_uint64(), C.c_uint32()
-        self._check(self.L.rfx_debug_records(self._ctx, C.byref(n), C.byref(nb), None, None), self._ctx)
-        offs = np.empty(nb.value + 1, dtype=np.uint64)
-        recs = np.empty((n.value, self.record_bytes() // 8), dtype=np.uint64)
-        self._check(self.L.rfx_debug_records(self._ctx, C.byref(n), C.byref(nb), offs.ctypes.data, recs.ctypes.data), self._ctx)
-        return offs, recs
-
 
 # ------------------------------------------------------------------------------------------------------
 # helpers shared by the pipelines

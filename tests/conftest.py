@@ -72,8 +72,46 @@ def rfxlib():
     return _lib.load_library()
 
 
+class _Hooks:
+    """tests/hooks/librfx_testhooks.so: copies of a context's packed reads / super-k-mer records (test-only)."""
+
+    def __init__(self):
+        import ctypes as C
+        d = os.path.join(ROOT, "tests", "hooks")
+        subprocess.run(["make", "-s", "-C", d], check=True)
+        self.C = C
+        self.L = C.CDLL(os.path.join(d, "librfx_testhooks.so"))
+        P = C.c_void_p
+        self.L.rfx_debug_reads.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), P, P, P]
+        self.L.rfx_debug_records.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), P, P]
+
+    def reads(self, ctx):
+        C = self.C
+        n, w = C.c_uint64(), C.c_uint64()
+        assert self.L.rfx_debug_reads(ctx._ctx, C.byref(n), C.byref(w), None, None, None) == 0
+        lens = np.empty(n.value, dtype=np.uint32)
+        woff = np.empty(n.value, dtype=np.uint64)
+        words = np.empty(w.value, dtype=np.uint64)
+        assert self.L.rfx_debug_reads(ctx._ctx, C.byref(n), C.byref(w), lens.ctypes.data, woff.ctypes.data, words.ctypes.data) == 0
+        return lens, woff, words
+
+    def records(self, ctx):
+        C = self.C
+        n, nb = C.c_uint64(), C.c_uint32()
+        assert self.L.rfx_debug_records(ctx._ctx, C.byref(n), C.byref(nb), None, None) == 0
+        offs = np.empty(nb.value + 1, dtype=np.uint64)
+        recs = np.empty((n.value, ctx.record_bytes() // 8), dtype=np.uint64)
+        assert self.L.rfx_debug_records(ctx._ctx, C.byref(n), C.byref(nb), offs.ctypes.data, recs.ctypes.data) == 0
+        return offs, recs
+
+
+@pytest.fixture(scope="session")
+def hooks():
+    return _Hooks()
+
+
 def make_reads(seed: int, genome_len: int, n_pairs: int, read_len: int = 100, err: float = 0.0, frag: int = 250) -> np.ndarray:
     """Small synthetic FASTQ through the library's host generator."""
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(genome_len, seed)
     return synth.fastq(g, n_pairs, read_len=read_len, frag_len=frag, error_rate=err, seed_reads=seed + 1, seed_errors=seed + 2)

@@ -57,7 +57,7 @@ def test_bad_params_rejected(rfxlib):
 
 
 def test_synth_generator_is_deterministic_and_well_formed(rfxlib, orc):
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(5000)
     assert set(np.unique(g).tolist()) <= set(b"ACGT") and np.array_equal(g, synth.genome(5000))
     a = synth.fastq(g, 300, read_len=150, frag_len=400)

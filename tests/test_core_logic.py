@@ -123,7 +123,7 @@ def test_fork_filters_per_group_formulation(orc, hostemu, k, E, cover, err):
     """The GPU evaluates each (k-1)-mer group from its four candidate neighbours (right_fork / left_fork in rfx_core.h);
     the oracle sorts and scans like the reference.  Both must keep the same oriented k-mers with the same flags,
     including real forks (repeats), ties and, for even k, palindromes."""
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(3000, 7 + k)
     g[1500:1900] = g[200:600]          # a repeat -> real forks
     g[2500:2520] = np.frombuffer(b"ACGT" * 5, np.uint8)  # low-complexity / palindromic stretch
@@ -153,7 +153,7 @@ def test_sorted_stage_per_group_formulation(orc, hostemu, k, E, fold, kmax, cove
     """Count_<k>_sorted: sorted_right_fork / sorted_left_fork evaluated per (k-1)-mer group, as the GPU does,
     against the oracle's sort + sequential scan with the reference's packed attribute word -- including the two places
     where the reference lets a weaker row's coverage / right flag leak into the stored row."""
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(3000, 17 + k)
     g[1500:1900] = g[200:600]
     g[2500:2520] = np.frombuffer(b"ACGT" * 5, np.uint8)

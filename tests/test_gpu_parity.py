@@ -44,7 +44,7 @@ def _param(R, **kw):
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("k,fc,ec", [(31, 0, 0), (21, 3, 5), (61, 0, 0)])
-def test_k1_reads_and_packing(R, orc, hostemu, example_text, mode, k, fc, ec):
+def test_k1_reads_and_packing(R, orc, hostemu, hooks, example_text, mode, k, fc, ec):
     txt = example_text[:300_000]
     txt = txt[:txt.rfind(b"\n@NODE")] + b"\n"
     if mode == 2:
@@ -57,7 +57,7 @@ def test_k1_reads_and_packing(R, orc, hostemu, example_text, mode, k, fc, ec):
     hostemu.emu_pack_reads(a.ctypes.data, s.ctypes.data, l.ctypes.data, len(s), k, fc, ec, elen.ctypes.data, woff.ctypes.data, words.ctypes.data)
     with R.ReflexivContext(_param(R, kmerSize=k, frontClip=fc, endClip=ec), fastq_mode=mode) as ctx:
         ctx.push_fastq(txt)
-        g_len, g_woff, g_words = ctx.debug_reads()
+        g_len, g_woff, g_words = hooks.reads(ctx)
         st = ctx.stats()
     assert st["n_reads"] == len(s)
     assert np.array_equal(g_len, elen)
@@ -66,7 +66,7 @@ def test_k1_reads_and_packing(R, orc, hostemu, example_text, mode, k, fc, ec):
     assert st["n_bases"] == int(elen.sum())
 
 
-def test_k1_state_machine_edge_cases(R, orc):
+def test_k1_state_machine_edge_cases(R, orc, hooks):
     txt = (b"garbage before the first record\n"
            b"@r1\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n@IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
            b"@r2\nTTTTACGTACGTACGTACGTACGAACGTACGTACGT\n+r2\n+IIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n"
@@ -77,7 +77,7 @@ def test_k1_state_machine_edge_cases(R, orc):
         s, l = orc.fastq_reads(t, orc.FASTQ_RUN)
         with R.ReflexivContext(_param(R, kmerSize=15)) as ctx:
             ctx.push_fastq(t)
-            g_len, _, _ = ctx.debug_reads()
+            g_len, _, _ = hooks.reads(ctx)
         assert g_len.tolist() == l.tolist()
     with R.ReflexivContext(_param(R, kmerSize=15)) as ctx:
         ctx.push_fastq(b"")
@@ -88,7 +88,7 @@ def test_k1_state_machine_edge_cases(R, orc):
         assert ctx.assemble()["n_contigs"] == 0 and ctx.contigs() == []
 
 
-def test_chunked_upload_carries_the_fastq_state(R, orc, example_text, monkeypatch):
+def test_chunked_upload_carries_the_fastq_state(R, orc, hooks, example_text, monkeypatch):
     """rfx_push_fastq uploads big inputs in chunks cut at arbitrary newlines (here: every ~3 KB, so chunks start in
     the middle of records, on '+' lines and on quality lines that begin with '@'); the carried lineMark must make
     that invisible."""
@@ -97,7 +97,7 @@ def test_chunked_upload_carries_the_fastq_state(R, orc, example_text, monkeypatc
         s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
         with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
             ctx.push_fastq(txt)
-            g_len, _, _ = ctx.debug_reads()
+            g_len, _, _ = hooks.reads(ctx)
             assert ctx.stats()["n_reads"] == len(s)
             assert np.array_equal(g_len, np.where(l.astype(np.int64) - 31 > 1, l, 0).astype(np.uint32))
     ints, counts, c, _ = _oracle_table(orc, example_text, 31, orc.FASTQ_RUN)
@@ -112,13 +112,13 @@ def test_chunked_upload_carries_the_fastq_state(R, orc, example_text, monkeypatc
 # K2: super-k-mer records
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k,m", [(31, 0), (31, 15), (21, 9), (61, 0), (33, 16)])
-def test_k2_records_hold_exactly_the_kmer_instances(R, orc, hostemu, example_text, k, m):
+def test_k2_records_hold_exactly_the_kmer_instances(R, orc, hostemu, hooks, example_text, k, m):
     txt = example_text
     ints, counts, c, _ = _oracle_table(orc, txt, k, orc.FASTQ_RUN)
     with R.ReflexivContext(_param(R, kmerSize=k), minimizer_len=m) as ctx:
         ctx.push_fastq(txt)
         ctx.partition(1)
-        offs, recs = ctx.debug_records()
+        offs, recs = hooks.records(ctx)
         st = ctx.stats()
         mm = m if m else 11
         n_bins = st["n_bins"]
@@ -297,7 +297,7 @@ def test_docs_golden_contig_on_gpu(R, orc, example_text, golden):
 
 @pytest.mark.parametrize("k,cover,E,err", [(31, 2, 8, 0.0), (31, 2, 8, 0.01), (31, 2, 0, 0.01), (21, 1, 8, 0.02), (41, 2, 8, 0.01), (61, 2, 8, 0.005), (24, 1, 8, 0.01)])
 def test_assembly_matches_oracle(R, orc, k, cover, E, err):
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(30_000, 100 + k)
     g[12000:12800] = g[3000:3800]    # repeat: real forks, budget junctions
     g[20000:20040] = np.frombuffer(b"AT" * 20, np.uint8)  # palindromic low-complexity stretch (cycles for even k)
@@ -309,7 +309,7 @@ def test_assembly_matches_oracle(R, orc, k, cover, E, err):
 @pytest.mark.parametrize("k,cover,E,err", [(31, 2, 8, 0.01), (61, 2, 8, 0.005), (24, 1, 8, 0.01), (5, 1, 8, 0.0), (12, 2, 0, 0.01), (33, 2, 8, 0.0)])
 def test_assembly_with_the_bin_local_index(R, orc, monkeypatch, k, cover, E, err):
     """Tables beyond the L2 use minimiser-bin-local index regions; forced here on small inputs (RFX_GRAPH_INDEX=local)."""
-    from reflexiv_b200 import synth
+    from workload import synth
     monkeypatch.setenv("RFX_GRAPH_INDEX", "local")
     g = synth.genome(30_000, 200 + k)
     g[12000:12800] = g[3000:3800]
@@ -344,7 +344,7 @@ def test_budget_walks_on_dense_forks(R, orc, monkeypatch, k, glen, seed):
     are full of repeated (k-1)-mers, so winners sit within reach of each other, face each other and lie on closed paths;
     the GPU must give the oracle's canonical contigs WITH their header flags, and the canonical closed form must equal
     the reference's four merge clauses applied literally under the same schedule (ORC_ASM_SCHEDULED)."""
-    from reflexiv_b200 import synth
+    from workload import synth
     g = synth.genome(glen, 300 + seed)
     if k == 31:
         g[5000:5400] = g[1000:1400]
@@ -407,7 +407,7 @@ def test_sorted_stage_matches_oracle(R, orc, monkeypatch, k, E, fold, kmax, cove
     """SURVEY 8f-2, Count_<k>_sorted: rfx_sort_kmers against the oracle's restatement of ReflexivDSKmerLeftAndRightSorting
     (rows as arrays and as the CSV text the reference writes), with both index layouts and coverages past the 30000
     saturation; the assembly results of the same context stay retrievable only until the stage takes the index over."""
-    from reflexiv_b200 import synth
+    from workload import synth
     if index:
         monkeypatch.setenv("RFX_GRAPH_INDEX", index)
     g = synth.genome(30_000, 300 + k)
@@ -547,7 +547,7 @@ def test_full_size_properties_config2_slice(R, orc):
     """Size-independent properties at a larger scale (a 1/8 slice of BASELINE config 2): the sum of counts equals the
     number of k-mer instances, the table has no duplicates, error-free 100x reads reproduce every genome k-mer with
     the right multiplicity bound, and the contigs are substrings of the genome."""
-    from reflexiv_b200 import synth
+    from workload import synth
     G = 575_000
     g = synth.genome(G)
     n_pairs = synth.n_pairs_for(G, 100.0)

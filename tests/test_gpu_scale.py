@@ -13,7 +13,7 @@ MREADS = float(os.environ.get("RFX_SCALE_TEST", "4"))
 @pytest.mark.skipif(MREADS <= 0, reason="RFX_SCALE_TEST=0")
 def test_large_input_properties(orc):
     import reflexiv_b200 as R
-    from reflexiv_b200 import synth
+    from workload import synth
     n_pairs = int(MREADS * 1e6 / 2)
     G = int(n_pairs * 2 * 150 / 100)          # 100x coverage
     g = synth.genome(G)

@@ -82,7 +82,7 @@ def _left_fork(cnt, E, sub):  # rfx_core.h: left_fork
 
 @pytest.mark.parametrize("n_ranks", [2, 8])
 def test_sharded_fork_filters_with_replicated_presence_bits(orc, n_ranks):
-    from reflexiv_b200 import synth
+    from workload import synth
     E, n_bins = 8, 64 * n_ranks
     g = synth.genome(3000, 900)
     g[1500:1800] = g[300:600]                       # a repeat: real forks

@@ -11,7 +11,11 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "../../include/reflexiv_cuda.h"
+
+/* Not part of libreflexiv_cuda: the workload generator of bench.py and the tests (librfx_synth.so, plain C). */
+int64_t rfx_synth_genome(uint8_t* out, int64_t n_bases, uint64_t seed);
+int64_t rfx_synth_fastq(const uint8_t* genome, int64_t genome_len, int64_t first_pair, int64_t n_pairs, int32_t read_len, int32_t frag_len,
+                        double error_rate, uint64_t seed_reads, uint64_t seed_errors, uint8_t* out, int64_t cap);
 
 static inline uint64_t splitmix64(uint64_t x) {
     x += 0x9e3779b97f4a7c15ULL;
