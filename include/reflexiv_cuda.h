@@ -204,33 +204,41 @@ int rfx_counts_device(rfx_ctx* ctx, const void** d_keys, const uint32_t** d_coun
 /* Replace (append == 0) or extend (append != 0) the table from device memory in that same layout. */
 int rfx_load_counts_device(rfx_ctx* ctx, const void* d_keys, const uint32_t* d_counts, uint64_t n_rows, int32_t append);
 
-/* ---- sharded assembly (one context per GPU; the caller issues the collectives between the steps) ----------------
- * replaces, across GPUs, the same reference stages as rfx_assemble (ReflexivDSMain.java:221-338); the exchanges take
- * the place of the reference's global sort("k-1") shuffles.  Every rank holds the WHOLE filtered table (shard tables
- * concatenated in rank order, rfx_load_counts_device) and owns rows [row_lo, row_hi) of it.  Sequence:
- *   rfx_gs_begin      index + right fork filter of the own rows
- *   [every rank broadcasts its slice [2*row_lo, 2*row_hi) of the alive bytes (rfx_gs_alive)]
- *   rfx_gs_left       left fork filter of the own rows
- *   [broadcast the slices again]
- *   rfx_gs_link       links, splitter selection and segment walk of the own nodes; returns the own splitter triples
- *                     (node, next splitter node or 0xffffffff, segment length), n_splitters entries each
- *   [all-gather the three arrays in rank order; my_offset = number of splitters of the lower ranks]
- *   rfx_gs_rank       ranks the gathered list, finishes the own nodes, returns the own chain tuples: tails are
- *                     {u32 head, u32 length, i32 right flag}, heads {u32 head, i32 left flag}.  has_cycle != 0: the
- *                     graph has a closed path; fall back to rfx_assemble (the table is already whole on every rank)
- *   [all-gather tails and heads]
- *   rfx_gs_contigs    contig table (identical on every rank) + the bases of the own nodes; *d_bases is zero elsewhere
- *   [all-reduce MAX over the n_bases bytes; sum the four statistics over the ranks (rfx_stats of each rank holds its
- *    own n_oriented / n_budget_junctions / n_budget_admissible / n_cycles)]
- *   rfx_gs_finish     stores the global statistics; rfx_contigs_size / rfx_contigs_copy work as after rfx_assemble */
-int rfx_gs_begin(rfx_ctx* ctx, uint64_t row_lo, uint64_t row_hi);
-int rfx_gs_alive(rfx_ctx* ctx, uint8_t** d_alive, uint64_t* n_nodes);
-int rfx_gs_left(rfx_ctx* ctx);
-int rfx_gs_link(rfx_ctx* ctx, uint64_t* n_splitters, const uint32_t** d_node, const uint32_t** d_next, const uint32_t** d_len);
-int rfx_gs_rank(rfx_ctx* ctx, const uint32_t* d_node, const uint32_t* d_next, const uint32_t* d_len, uint64_t n_total, uint64_t my_offset,
-                uint64_t* n_tails, const void** d_tails, uint64_t* n_heads, const void** d_heads, int32_t* has_cycle);
-int rfx_gs_contigs(rfx_ctx* ctx, const void* d_tails, uint64_t n_tails, const void* d_heads, uint64_t n_heads, char** d_bases, uint64_t* n_bases);
-int rfx_gs_finish(rfx_ctx* ctx, uint64_t n_oriented, uint64_t n_budget_junctions, uint64_t n_budget_admissible, uint64_t n_cycles);
+/* ---- multi-GPU over peer memory (one context per GPU = one rank; NVLink / NVSwitch) ---------------------------------
+ * Replaces, across GPUs, the reference's shuffles: groupBy("value") (ReflexivDataFrameCounter.java:198-200,
+ * ReflexivDSMain.java:207-209) and every sort("k-1") of the fork filters and of the extension loop
+ * (ReflexivDSMain.java:232, 244, 261-326).  After rfx_shard_init all device buffers of the context live in one arena;
+ * rfx_shard_export / rfx_shard_connect let every rank map every other rank's arena (CUDA IPC between processes, plain
+ * pointers inside one process -- ranks may even share a device, which is how a one-GPU box tests the path).  The kernels
+ * then read and write peer HBM directly: no collective library on the data path.
+ *   every rank:  rfx_shard_init -> rfx_shard_export -> [caller gathers the world * RFX_SHARD_HANDLE_BYTES bytes] ->
+ *                rfx_shard_connect -> { rfx_reset, rfx_push_fastq*, rfx_count_sharded, rfx_assemble_sharded, results }*
+ * rfx_count_sharded / rfx_assemble_sharded are collective: every rank must call them (from its own host thread or
+ * process); they meet in cross-GPU barriers and fail with RFX_E_STATE if a peer never arrives.
+ * On return from rfx_count_sharded the context holds its shard of the global table (the rows whose minimiser bin it
+ * owns; rfx_counts_* work on it); after rfx_assemble_sharded it holds the contigs whose first k-mer it owns
+ * (rfx_contigs_* work on them): the union over the ranks is the result of the single-GPU calls. */
+#define RFX_SHARD_HANDLE_BYTES 128
+typedef struct {
+    int32_t rank, world;
+    uint64_t arena_bytes, arena_used;
+    uint64_t n_instances_global;  /* k-mer instances extracted by all ranks */
+    uint64_t n_shard_instances;   /* ... that fell into this rank's bins */
+    uint64_t n_rows_global, n_oriented_global, n_contigs_global, n_contig_bases_global;
+    uint64_t n_remote_probes;     /* neighbour probes answered from a peer's index */
+    uint64_t n_l1_splitters, n_l2_splitters;
+    float ms_comm;                /* barriers + value exchanges of the last sharded calls */
+    int32_t fell_back;            /* last rfx_assemble_sharded met a closed path: rank 0 assembled the whole table */
+} rfx_shard_stats_t;
+int rfx_shard_init(rfx_ctx* ctx, int32_t rank, int32_t world, uint64_t arena_bytes /* 0: half of the free device memory */);
+int rfx_shard_export(rfx_ctx* ctx, void* handle /* RFX_SHARD_HANDLE_BYTES */);
+int rfx_shard_connect(rfx_ctx* ctx, const void* handles /* world * RFX_SHARD_HANDLE_BYTES, rank order */, int32_t world);
+/* optional: the total number of minimiser bins (a multiple of world, same on every rank; rfx_choose_bins).  Known up
+ * front it lets rfx_push_fastq scan each uploaded chunk straight into the slabs; otherwise the ranks agree on it. */
+int rfx_shard_set_bins(rfx_ctx* ctx, uint32_t n_bins_total);
+int rfx_count_sharded(rfx_ctx* ctx);
+int rfx_assemble_sharded(rfx_ctx* ctx);
+int rfx_shard_stats(rfx_ctx* ctx, rfx_shard_stats_t* out);
 
 const char* rfx_version(void);
 

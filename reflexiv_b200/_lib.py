@@ -37,6 +37,18 @@ class RfxStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+RFX_SHARD_HANDLE_BYTES = 128
+
+
+class RfxShardStats(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32)] + [(n, C.c_uint64) for n in (
+        "arena_bytes", "arena_used", "n_instances_global", "n_shard_instances", "n_rows_global", "n_oriented_global", "n_contigs_global",
+        "n_contig_bases_global", "n_remote_probes", "n_l1_splitters", "n_l2_splitters")] + [("ms_comm", C.c_float), ("fell_back", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 # every symbol include/reflexiv_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -67,14 +79,6 @@ SYMBOLS = {
     "rfx_partition": (C.c_int, [_P, C.c_int32, C.c_uint32]),
     "rfx_choose_bins": (C.c_uint32, [_P, C.c_uint64, C.c_int32]),
     "rfx_rx_buffer": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_void_p)]),
-    "rfx_gs_begin": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
-    "rfx_gs_alive": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
-    "rfx_gs_left": (C.c_int, [_P]),
-    "rfx_gs_link": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
-    "rfx_gs_rank": (C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
-                              C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
-    "rfx_gs_contigs": (C.c_int, [_P, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
-    "rfx_gs_finish": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "rfx_shard_records": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "rfx_begin_shard": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint32]),
     "rfx_load_records_device": (C.c_int, [_P, _P, C.c_uint64]),
@@ -83,6 +87,13 @@ SYMBOLS = {
     "rfx_load_segment_device": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "rfx_counts_device": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "rfx_load_counts_device": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_int32]),
+    "rfx_shard_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_uint64]),
+    "rfx_shard_export": (C.c_int, [_P, _P]),
+    "rfx_shard_connect": (C.c_int, [_P, _P, C.c_int32]),
+    "rfx_shard_set_bins": (C.c_int, [_P, C.c_uint32]),
+    "rfx_count_sharded": (C.c_int, [_P]),
+    "rfx_assemble_sharded": (C.c_int, [_P]),
+    "rfx_shard_stats": (C.c_int, [_P, C.POINTER(RfxShardStats)]),
 }
 
 

@@ -9,6 +9,7 @@
 
 #include "rfx_internal.h"
 #include "rfx_scan.cuh"
+#include "rfx_shard.h"
 
 namespace rfx {
 
@@ -30,6 +31,24 @@ int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep) {
     size_t want = bytes;
     if (keep && b.cap) want = bytes > b.cap * 2 ? bytes : b.cap * 2;  // appended buffers grow geometrically
     want = (want + 255) & ~(size_t)255;
+    if (c && c->arena) {
+        // sharded run: bump allocation inside the peer-visible arena.  No cudaMalloc / cudaFree while other ranks may sit in
+        // a cross-GPU barrier (both can synchronise the whole device); an outgrown block is only given up, the arena
+        // is sized for the run (rfx_shard_init).
+        if (!keep || !b.cap) want += want / 8;  // head room, so that slightly different sizes from step to step do not move the block
+        want = (want + 255) & ~(size_t)255;
+        if (c->arena_used + want > c->arena_bytes)
+            return ctx_fail(c, RFX_E_NOMEM, "peer-visible arena exhausted (%llu of %llu bytes used, %zu more needed): raise arena_bytes in rfx_shard_init",
+                            (unsigned long long)c->arena_used, (unsigned long long)c->arena_bytes, want);
+        void* p = c->arena + c->arena_used;
+        c->arena_used += want;
+        if (b.p && keep && b.cap) cudaMemcpyAsync(p, b.p, b.cap, cudaMemcpyDeviceToDevice, c->stream);
+        if (b.p && !b.in_arena) { if (c->stream) cudaStreamSynchronize(c->stream); cudaFree(b.p); }
+        b.p = p;
+        b.cap = want;
+        b.in_arena = true;
+        return RFX_OK;
+    }
     if (b.p && !(keep && b.cap)) {
         // contents are not needed: give the old block back first, so that growing a 45 GB buffer by 2 % does not need 90 GB
         if (c && c->stream) cudaStreamSynchronize(c->stream);
@@ -54,16 +73,17 @@ int devbuf_reserve(Ctx* c, DevBuf& b, size_t bytes, bool keep) {
 }
 
 void devbuf_free(DevBuf& b) {
-    if (b.p) cudaFree(b.p);
+    if (b.p && !b.in_arena) cudaFree(b.p);
+    b.in_arena = false;
     b.p = nullptr;
     b.cap = 0;
 }
 
-static void free_all(Ctx* c) {
+void free_all_buffers(Ctx* c) {
     DevBuf* all[] = {&c->text, &c->line_start, &c->line_at, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
                      &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->ad[0],
-                     &c->ad[1], &c->open_next, &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
-                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->gs_next, &c->gs_len, &c->gs_tails, &c->gs_heads, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom, &c->srt_left, &c->srt_right, &c->eff_l, &c->eff_r};
+                     &c->ad[1], &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom, &c->srt_left, &c->srt_right, &c->eff_l, &c->eff_r, &c->seg_ext};
     for (DevBuf* b : all) devbuf_free(*b);
 }
 
@@ -231,7 +251,8 @@ void rfx_destroy(rfx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    free_all(c);
+    free_all_buffers(c);
+    shard_release(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (int i = 0; i < 6; i++) if (c->evk[i]) cudaEventDestroy(c->evk[i]);
@@ -689,7 +710,7 @@ int rfx_shard_bin_offsets(rfx_ctx* c, int32_t shard, const uint64_t** d_offsets,
 int rfx_load_segment_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes, const uint64_t* d_bin_offsets) {
     if (!c || (!d_records && n_bytes) || !d_bin_offsets) return RFX_E_INVALID;
     if (c->shard_id < 0) return ctx_fail(c, RFX_E_STATE, "rfx_load_segment_device: call rfx_begin_shard first");
-    if (c->n_seg >= 64) return ctx_fail(c, RFX_E_INVALID, "more than 64 segments");
+    if (c->n_seg >= RFX_MAX_SEG) return ctx_fail(c, RFX_E_INVALID, "more than %d segments", RFX_MAX_SEG);
     if (c->n_seg == 0 && c->rx_bytes) return ctx_fail(c, RFX_E_STATE, "do not mix rfx_load_records_device and rfx_load_segment_device");
     if (n_bytes % (uint64_t)(c->recw * 8)) return ctx_fail(c, RFX_E_INVALID, "record bytes not a multiple of %d", c->recw * 8);
     cudaSetDevice(c->prm.device);
@@ -705,55 +726,6 @@ int rfx_load_segment_device(rfx_ctx* c, const void* d_records, uint64_t n_bytes,
     c->seg_base_host[c->n_seg] = c->rx_bytes / (uint64_t)(c->recw * 8);
     c->n_seg++;
     c->rx_bytes += n_bytes;
-    return RFX_OK;
-}
-
-// ---- sharded graph stages ------------------------------------------------------------------------
-int rfx_gs_begin(rfx_ctx* c, uint64_t row_lo, uint64_t row_hi) {
-    if (!c) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    return stage_gs_begin(c, row_lo, row_hi);
-}
-int rfx_gs_alive(rfx_ctx* c, uint8_t** d_alive, uint64_t* n_nodes) {
-    if (!c || !d_alive || !n_nodes) return RFX_E_INVALID;
-    if (c->gs_step < 1) return ctx_fail(c, RFX_E_STATE, "rfx_gs_alive: call rfx_gs_begin first");
-    *d_alive = c->alive.as<uint8_t>();
-    *n_nodes = 2 * c->n_rows;
-    return RFX_OK;
-}
-int rfx_gs_left(rfx_ctx* c) {
-    if (!c) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    return stage_gs_left(c);
-}
-int rfx_gs_link(rfx_ctx* c, uint64_t* n_splitters, const uint32_t** d_node, const uint32_t** d_next, const uint32_t** d_len) {
-    if (!c || !n_splitters || !d_node || !d_next || !d_len) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    RFX_TRY(stage_gs_link(c, n_splitters));
-    *d_node = c->spl_node.as<uint32_t>(); *d_next = c->gs_next.as<uint32_t>(); *d_len = c->gs_len.as<uint32_t>();
-    return RFX_OK;
-}
-int rfx_gs_rank(rfx_ctx* c, const uint32_t* d_node, const uint32_t* d_next, const uint32_t* d_len, uint64_t n_total, uint64_t my_offset, uint64_t* n_tails,
-                const void** d_tails, uint64_t* n_heads, const void** d_heads, int32_t* has_cycle) {
-    if (!c || !n_tails || !d_tails || !n_heads || !d_heads || !has_cycle || (n_total && (!d_node || !d_next || !d_len))) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    RFX_TRY(stage_gs_rank(c, d_node, d_next, d_len, n_total, my_offset, n_tails, n_heads, has_cycle));
-    *d_tails = c->gs_tails.p; *d_heads = c->gs_heads.p;
-    return RFX_OK;
-}
-int rfx_gs_contigs(rfx_ctx* c, const void* d_tails, uint64_t n_tails, const void* d_heads, uint64_t n_heads, char** d_bases, uint64_t* n_bases) {
-    if (!c || !d_bases || !n_bases || (n_tails && !d_tails) || (n_heads && !d_heads)) return RFX_E_INVALID;
-    cudaSetDevice(c->prm.device);
-    RFX_TRY(stage_gs_contigs(c, d_tails, n_tails, d_heads, n_heads));
-    *d_bases = c->ctg_bases.as<char>(); *n_bases = c->n_contig_bases;
-    return RFX_OK;
-}
-int rfx_gs_finish(rfx_ctx* c, uint64_t n_oriented, uint64_t n_budget, uint64_t n_budget_admissible, uint64_t n_cycles) {
-    if (!c) return RFX_E_INVALID;
-    if (c->gs_step != 5) return ctx_fail(c, RFX_E_STATE, "rfx_gs_finish: call rfx_gs_contigs first");
-    c->n_oriented = n_oriented; c->n_budget = n_budget; c->n_budget_adm = n_budget_admissible; c->n_cycles = n_cycles;
-    c->gs_step = 0;
-    c->have_contigs = true;
     return RFX_OK;
 }
 

@@ -37,11 +37,11 @@ namespace rfx {
 constexpr int CNT_STACK = 64;
 
 struct CountArgs {
-    const uint64_t* records;
-    // bin b = concatenation over segments s of records[seg_base[s] + off_s[b] - off_s[0] .. seg_base[s] + off_s[b+1] - off_s[0])
-    // with off_s = seg_off + s * (n_bins + 1).  A local partition is one segment with base 0.
-    const uint64_t* seg_off;
-    const uint64_t* seg_base;
+    // bin b = concatenation over segments s of ext[s * n_bins + b].cnt records starting at the absolute address
+    // ext[s * n_bins + b].addr -- a local slab, an exactly partitioned overflow list, a slice received through NCCL or
+    // a PEER GPU's slab read in place over NVLink (rfx_shard.cu): the kernel does not care, its producer warp issues
+    // one bulk copy per non-empty segment (build_ext_kernel fills the table)
+    const SegExt* ext;
     int n_seg;
     uint32_t n_bins;
     int k;
@@ -53,14 +53,9 @@ struct CountArgs {
     // tickets t = 0 .. n_tickets-1 map to bins t * bin_stride (the full run: n_tickets = n_bins, stride 1)
     uint32_t n_tickets, bin_stride;
     int dry;  // pilot run: count and report statistics, write no rows
-    // single-pass partition: segment 0 is the slab layout (bin b = records[b * slab_cap ..], min(slab_cnt[b], slab_cap)
-    // records); the offset-described segments follow as segments 1 ..
-    const uint32_t* slab_cnt;
-    uint32_t slab_cap;
-    const uint64_t* seg_records;  // record array of the offset-described segments (== records unless slab)
 };
 
-constexpr int MAX_SEG = 64;
+constexpr int MAX_SEG = RFX_MAX_SEG;
 
 // slot hash + tag of a whole record (tag 0 = empty slot)
 template <int RECW> __device__ __forceinline__ void record_hash(const uint64_t (&w)[RECW], uint32_t& slot_h, uint32_t& tag) {
@@ -238,7 +233,7 @@ constexpr uint32_t BIN_END = 0xffffffffu;
 
 // what the producer warp hands over per bin
 struct BinDesc {
-    unsigned long long seg_beg[MAX_SEG];  // first record of the bin inside each segment
+    unsigned long long seg_beg[MAX_SEG];  // address of the bin's first record inside each segment
     uint32_t seg_pre[MAX_SEG + 1];        // bin-local index of the first record of each segment
     uint32_t bin;
 };
@@ -251,7 +246,8 @@ __device__ __forceinline__ void issue_chunk(const CountArgs& A, const BinDesc& D
     for (int s = 0; s < n_seg; s++) {
         const uint32_t lo = D.seg_pre[s] > cbeg ? D.seg_pre[s] : cbeg;
         const uint32_t hi = D.seg_pre[s + 1] < cend ? D.seg_pre[s + 1] : cend;
-        if (lo < hi) bulk_g2s(dst + (size_t)(lo - cbeg) * RECW, A.records + (D.seg_beg[s] + (lo - D.seg_pre[s])) * RECW, (hi - lo) * (uint32_t)(RECW * 8), bar);
+        if (lo < hi)
+            bulk_g2s(dst + (size_t)(lo - cbeg) * RECW, reinterpret_cast<const uint64_t*>(D.seg_beg[s]) + (size_t)(lo - D.seg_pre[s]) * RECW, (hi - lo) * (uint32_t)(RECW * 8), bar);
     }
 }
 
@@ -315,18 +311,9 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
                 const int sg = r * 32 + lane;
                 my_beg[r] = 0; my_cnt[r] = 0;
                 if (!end && sg < n_seg) {
-                    if (A.slab_cap && sg == 0) {
-                        const uint32_t cn = A.slab_cnt[bin];
-                        my_beg[r] = (unsigned long long)bin * A.slab_cap;
-                        my_cnt[r] = cn < A.slab_cap ? cn : A.slab_cap;
-                    } else {
-                        const int so_i = A.slab_cap ? sg - 1 : sg;
-                        const uint64_t* so = A.seg_off + (size_t)so_i * (A.n_bins + 1);
-                        const uint64_t o0 = so[0], ob = so[bin], oe = so[bin + 1];
-                        // offset segments of a slab run live in their own array: address them relative to `records`
-                        my_beg[r] = A.seg_base[so_i] + ob - o0 + (unsigned long long)((A.seg_records - A.records) / RECW);
-                        my_cnt[r] = (uint32_t)(oe - ob);
-                    }
+                    const SegExt e = A.ext[(size_t)sg * A.n_bins + bin];
+                    my_beg[r] = e.addr;
+                    my_cnt[r] = e.cnt;
                 }
                 uint32_t incl = my_cnt[r];
 #pragma unroll
@@ -622,6 +609,29 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     }
 }
 
+// (segment, bin) -> extent, for every layout the records may be in (rfx_internal.h: ExtSrc)
+__global__ void build_ext_kernel(ExtSrcs S, int n_seg, uint32_t n_bins, int recw, SegExt* __restrict__ ext) {
+    const uint64_t total = (uint64_t)n_seg * n_bins;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int sg = (int)(i / n_bins);
+        const uint32_t b = (uint32_t)(i % n_bins);
+        const ExtSrc& x = S.s[sg];
+        const uint64_t gb = (uint64_t)x.bin_base + b;
+        SegExt e;
+        e.pad = 0;
+        if (x.slab_cap) {
+            const uint32_t cn = x.slab_cnt[gb];
+            e.cnt = cn < x.slab_cap ? cn : x.slab_cap;
+            e.addr = (unsigned long long)(x.rec + gb * x.slab_cap * (uint64_t)recw);
+        } else {
+            const uint64_t o = x.off[gb], oe = x.off[gb + 1];
+            e.cnt = (uint32_t)(oe - o);
+            e.addr = (unsigned long long)(x.rec + (o - x.off_sub) * (uint64_t)recw);
+        }
+        ext[i] = e;
+    }
+}
+
 // geometry (shared memory per CTA -> CTAs per SM):
 //   k <= 31, small: 2 x 768 x 16 B record stages + 2048 x 12 B k-mer table + lists + 1024-entry record table = 61 KB -> 3
 //   k <= 31, large: the same with a 4096-slot k-mer table                                                    = 87 KB -> 2
@@ -637,9 +647,52 @@ template <bool WIDE, int CAP, int RCAP, int NT, int PER_SM> static cudaError_t l
     return cudaGetLastError();
 }
 
+// offsets of the first bin of every received slice (its sender's absolute offset of that bin)
+__global__ void seg_first_offsets_kernel(const uint64_t* seg_off, int n_seg, uint32_t bps, uint64_t* out) {
+    if ((int)threadIdx.x < n_seg) out[threadIdx.x] = seg_off[(size_t)threadIdx.x * (bps + 1)];
+}
+
+// the locally held records in whatever layout the partition left them
 int stage_count(Ctx* c) {
-    cudaStream_t st = c->stream;
     if (!c->have_records) return ctx_fail(c, RFX_E_STATE, "rfx_count: no records (push reads first)");
+    ExtSrcs S;
+    memset(&S, 0, sizeof(S));
+    int n_seg = 1;
+    const bool segmented = c->shard_id >= 0 && c->n_seg > 0;
+    if (segmented) {
+        // slices received through NCCL, each grouped by bin with its sender's offsets (rfx_load_segment_device)
+        if (c->n_seg > RFX_MAX_SEG) return ctx_fail(c, RFX_E_INVALID, "more than %d record segments", RFX_MAX_SEG);
+        uint64_t first[RFX_MAX_SEG];
+        const uint32_t bps = c->n_bins;
+        RFX_TRY(devbuf_reserve(c, c->seg_base, 64 * sizeof(uint64_t)));
+        seg_first_offsets_kernel<<<1, 32, 0, c->stream>>>(c->seg_off.as<uint64_t>(), c->n_seg, bps, c->seg_base.as<uint64_t>());
+        RFX_CUDA(c, cudaMemcpyAsync(first, c->seg_base.p, (size_t)c->n_seg * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+        RFX_CUDA(c, cudaStreamSynchronize(c->stream));
+        n_seg = c->n_seg;
+        for (int i = 0; i < n_seg; i++) {
+            S.s[i].rec = c->rx_records.as<uint64_t>() + c->seg_base_host[i] * (uint64_t)c->recw;
+            S.s[i].off = c->seg_off.as<uint64_t>() + (size_t)i * (bps + 1);
+            S.s[i].off_sub = first[i];
+        }
+    } else if (c->slab_cap) {
+        // single-pass partition: slab segment + (maybe) the exactly partitioned overflow list
+        S.s[0].rec = c->records.as<uint64_t>();
+        S.s[0].slab_cnt = c->bin_cursor.as<uint32_t>();
+        S.s[0].slab_cap = c->slab_cap;
+        if (c->n_ovf) {
+            S.s[1].rec = c->rx_records.as<uint64_t>();
+            S.s[1].off = c->bin_off.as<uint64_t>();
+            n_seg = 2;
+        }
+    } else {
+        S.s[0].rec = c->records.as<uint64_t>();
+        S.s[0].off = c->bin_off.as<uint64_t>();
+    }
+    return stage_count_segments(c, S, n_seg, c->n_bins, true);
+}
+
+int stage_count_segments(Ctx* c, const ExtSrcs& S, int n_seg, uint32_t n_bins, bool check_instances) {
+    cudaStream_t st = c->stream;
     stage_begin(c);
     // effective coverage bounds (A4)
     uint32_t minc = (uint32_t)(c->prm.min_kmer_coverage < 0 ? 0 : c->prm.min_kmer_coverage);
@@ -654,6 +707,7 @@ int stage_count(Ctx* c) {
     if (!cap) {
         // every surviving row needs >= minc instances; keep a floor for tiny inputs
         uint64_t inst = c->n_instances ? c->n_instances : c->n_records * c->max_nk;
+        if (!check_instances) inst += inst / 4 + 4096;  // a shard's share of the global instances: about the local count
         cap = inst / minc + 1024;
         const uint64_t soft = 1ull << 31;  // 2 G rows (24-40 GB): beyond this the caller must say so
         if (cap > soft) cap = soft;
@@ -663,38 +717,31 @@ int stage_count(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->counts, cap * sizeof(uint32_t)));
     c->table_cap = cap;
     RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+    RFX_TRY(devbuf_reserve(c, c->seg_ext, ((size_t)n_seg * n_bins + 1) * sizeof(SegExt)));
+    if (n_bins) {
+        uint64_t g = ((uint64_t)n_seg * n_bins + 255) / 256;
+        if (g > sm_count() * 16u) g = sm_count() * 16u;
+        build_ext_kernel<<<(unsigned)g, 256, 0, st>>>(S, n_seg, n_bins, c->recw, c->seg_ext.as<SegExt>());
+        c->launches++;
+    }
     CountArgs A;
-    const bool segmented = c->shard_id >= 0 && c->n_seg > 0;
-    if (!segmented) {  // one segment: the locally partitioned (or re-binned) records
-        RFX_TRY(devbuf_reserve(c, c->seg_base, 64 * sizeof(uint64_t)));
-        RFX_CUDA(c, cudaMemsetAsync(c->seg_base.p, 0, sizeof(uint64_t), st));
-    }
-    A.records = segmented ? c->rx_records.as<uint64_t>() : c->records.as<uint64_t>();
-    A.seg_off = segmented ? c->seg_off.as<uint64_t>() : c->bin_off.as<uint64_t>();
-    A.seg_base = c->seg_base.as<uint64_t>();
-    A.n_seg = segmented ? c->n_seg : 1;
-    A.slab_cnt = nullptr; A.slab_cap = 0; A.seg_records = A.records;
-    if (!segmented && c->slab_cap) {  // single-pass partition: slab segment + (maybe) the overflow segment
-        A.slab_cnt = c->bin_cursor.as<uint32_t>();
-        A.slab_cap = c->slab_cap;
-        A.n_seg = c->n_ovf ? 2 : 1;
-        A.seg_records = c->n_ovf ? c->rx_records.as<uint64_t>() : A.records;
-    }
-    A.n_bins = c->n_bins;
+    A.ext = c->seg_ext.as<SegExt>();
+    A.n_seg = n_seg;
+    A.n_bins = n_bins;
     A.k = c->k;
     A.min_count = minc; A.max_count = maxc;
     A.out_keys = c->keys.p; A.out_counts = c->counts.as<uint32_t>();
     A.dstat = c->dstat.as<unsigned long long>();
     A.out_cap = cap;
-    if (A.n_seg > MAX_SEG) return ctx_fail(c, RFX_E_INVALID, "more than %d record segments", MAX_SEG);
-    A.n_tickets = c->n_bins; A.bin_stride = 1; A.dry = 0;
-    if (c->n_records) {
+    A.n_tickets = n_bins; A.bin_stride = 1; A.dry = 0;
+    const bool any = check_instances ? c->n_records != 0 : n_bins != 0;
+    if (any) {
         cudaEventRecord(c->evk[4], st);
         cudaError_t le;
         const char* variant = getenv("RFX_COUNT_VARIANT");  // "small" / "large": skip the pilot and force a geometry (tests, tuning)
         std::string vs = variant ? variant : "";
         if (!c->wide) {
-            if (vs.empty() && c->count_geometry && c->count_geometry_bins == c->n_bins) {
+            if (vs.empty() && c->count_geometry && c->count_geometry_bins == n_bins) {
                 // same context, same bin count as the run the pilot looked at (a driver pushing batch after batch of one
                 // data set): keep its choice; a run that splits more than 1 % of its bins drops it again (below)
                 vs = c->count_geometry == 1 ? "small" : "large";
@@ -703,8 +750,8 @@ int stage_count(Ctx* c) {
                 // k-mers a bin holds.  Clean high-coverage reads (tens per bin) run fastest on the small table at 3 CTAs / SM;
                 // noisy reads (every fourth instance a singleton) need the large one or most bins would be split.
                 CountArgs P = A;
-                P.n_tickets = c->n_bins < 296u ? c->n_bins : 296u;
-                P.bin_stride = c->n_bins / P.n_tickets;
+                P.n_tickets = n_bins < 296u ? n_bins : 296u;
+                P.bin_stride = n_bins / P.n_tickets;
                 P.dry = 1;
                 le = launch_count<false, 4096, 1024, 384, 2>(P, st);
                 if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count pilot launch failed: %s", cudaGetErrorString(le));
@@ -716,7 +763,7 @@ int stage_count(Ctx* c) {
                 const uint64_t per_bin = ph[DS_DISTINCT] / P.n_tickets;
                 vs = (per_bin <= 600 && ph[DS_SPLITS] == 0) ? "small" : "large";
                 c->count_geometry = vs == "small" ? 1 : 2;
-                c->count_geometry_bins = c->n_bins;
+                c->count_geometry_bins = n_bins;
             }
             if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
             else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
@@ -734,7 +781,7 @@ int stage_count(Ctx* c) {
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count kernel failed: %s", cudaGetErrorString(e));
     c->ms[2] += stage_end(c);
     c->ms_kernel[2] = 0;
-    if (c->n_records) cudaEventElapsedTime(&c->ms_kernel[2], c->evk[4], c->evk[5]);
+    if (any) cudaEventElapsedTime(&c->ms_kernel[2], c->evk[4], c->evk[5]);
     if (h[DS_OVERFLOW] == 2)
         return ctx_fail(c, RFX_E_CAPACITY, "a counting bin could not be split further (splits %llu: table full %llu, probe exhausted %llu, tag collision %llu, %llu)",
                         (unsigned long long)h[DS_SPLITS], (unsigned long long)h[DS_OVF_WHY], (unsigned long long)h[DS_OVF_WHY + 1],
@@ -745,8 +792,10 @@ int stage_count(Ctx* c) {
     c->n_rows = h[DS_OUT_CURSOR];
     c->n_distinct = h[DS_DISTINCT];
     c->n_bin_splits = h[DS_SPLITS];
-    if (c->n_bin_splits * 100 > c->n_bins) c->count_geometry = 0;  // the remembered geometry no longer fits the data: pilot again next time
-    if (c->n_instances == 0) c->n_instances = h[DS_INSTANCES];
+    if (c->n_bin_splits * 100 > n_bins) c->count_geometry = 0;  // the remembered geometry no longer fits the data: pilot again next time
+    c->n_shard_instances = h[DS_INSTANCES];
+    if (!check_instances) {}  // a shard counts the instances of ITS bins, not those of the reads this rank scanned
+    else if (c->n_instances == 0) c->n_instances = h[DS_INSTANCES];
     else if (h[DS_INSTANCES] != c->n_instances)
         return ctx_fail(c, RFX_E_STATE, "internal: counted %llu k-mer instances, extracted %llu", (unsigned long long)h[DS_INSTANCES],
                         (unsigned long long)c->n_instances);

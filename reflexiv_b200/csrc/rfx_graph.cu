@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include "rfx_internal.h"
+#include "rfx_graph.cuh"
 #include "rfx_scan.cuh"
 
 namespace rfx {
@@ -48,42 +49,10 @@ template <class KT> struct Graph {
     uint64_t bloom_mask;  // number of bits - 1 (power of two), 0: no filter
 
     __device__ __forceinline__ uint32_t bin_of(uint32_t hmin) const { return (uint32_t)(((uint64_t)fmix32(hmin ^ 0x7f4a7c15u) * g_bins) >> 32); }
-    // hash of the canonical form of an m-mer given right aligned
-    __device__ __forceinline__ uint32_t mm_hash(uint32_t mm) const {
-        uint32_t r = brev32(mm);
-        r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-        r = (~r) >> (32 - 2 * m);
-        return mmer_hash(mm < r ? mm : r);
-    }
-    // minima of the m-mer hashes inside the first / the last k-1 bases of X
-    __device__ __forceinline__ void minima(KT X, uint32_t& pre_min, uint32_t& suf_min) const {
-        const uint32_t mmask = (m >= 16) ? 0xffffffffu : ((1u << (2 * m)) - 1u);
-        const int mtop = 2 * (m - 1), w = k - m + 1;
-        KT Y = X << (8 * (int)sizeof(KT) - 2 * k);  // first base in the top two bits
-        uint32_t mf = 0, mr = 0;
-        pre_min = 0xffffffffu; suf_min = 0xffffffffu;
-        for (int t = 0; t < k; t++) {
-            const uint32_t v = (uint32_t)(Y >> (8 * (int)sizeof(KT) - 2)) & 3u;
-            Y <<= 2;
-            mf = ((mf << 2) | v) & mmask;
-            mr = (mr >> 2) | ((v ^ 3u) << mtop);
-            if (t >= m - 1) {
-                const int j = t - m + 1;
-                const uint32_t h = mmer_hash(mf < mr ? mf : mr);
-                if (j <= w - 2) pre_min = h < pre_min ? h : pre_min;
-                if (j >= 1) suf_min = h < suf_min ? h : suf_min;
-            }
-        }
-    }
-    // hash of the last m-mer of (S + b) / the first m-mer of (a + S), S a right-aligned (k-1)-mer
-    __device__ __forceinline__ uint32_t last_mm(KT S, uint32_t b) const {
-        const uint32_t low = (m >= 17) ? 0u : ((uint32_t)S & ((m >= 16) ? 0x3fffffffu : ((1u << (2 * (m - 1))) - 1u)));
-        return mm_hash((low << 2) | b);
-    }
-    __device__ __forceinline__ uint32_t first_mm(KT S, uint32_t a) const {
-        const uint32_t top = (uint32_t)(S >> (2 * (k - 1 - (m - 1)))) & ((1u << (2 * (m - 1))) - 1u);
-        return mm_hash((a << (2 * (m - 1))) | top);
-    }
+    __device__ __forceinline__ uint32_t mm_hash(uint32_t mm) const { return mm_hash_m(mm, m); }
+    __device__ __forceinline__ void minima(KT X, uint32_t& pre_min, uint32_t& suf_min) const { kmer_minima<KT>(X, k, m, pre_min, suf_min); }
+    __device__ __forceinline__ uint32_t last_mm(KT S, uint32_t b) const { return last_mm_of<KT>(S, b, m); }
+    __device__ __forceinline__ uint32_t first_mm(KT S, uint32_t a) const { return first_mm_of<KT>(S, a, k, m); }
     __device__ __forceinline__ uint32_t lookup(KT canon, uint32_t hmin) const {
         const uint64_t kh = key_hash(canon);
         if (bloom_mask) {
@@ -294,16 +263,13 @@ __global__ void sorted_left_kernel(Graph<KT> G, int E, double fold, int X, uint8
     }
 }
 
-// Neighbour links.  succ/pred are preset to NONE32.  On one GPU a node writes its successor's pred[] and EVERY junction
-// is linked (raw links): which of them hold is decided afterwards (budget walks + junction_finalize_kernel) and only
-// matters when some flag is non-negative, i.e. a real fork survived (DS_FLAGGED).  In a sharded run (SHARDED) a node
-// may only write its own entries, so it finds its predecessor itself (4 more probes) and reads the neighbour's flag
-// signs from the alive byte.
-template <class KT, bool SHARDED>
+// Neighbour links.  succ/pred are preset to NONE32.  A node writes its successor's pred[] and EVERY junction is linked
+// (raw links): which of them hold is decided afterwards (budget walks + junction_finalize_kernel) and only matters when
+// some flag is non-negative, i.e. a real fork survived (DS_FLAGGED).
+template <class KT>
 __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag,
-                            uint32_t* __restrict__ succ, uint32_t* pred, uint32_t* __restrict__ open_next, unsigned long long* dstat, uint64_t lo, uint64_t hi) {
+                            uint32_t* __restrict__ succ, uint32_t* pred, unsigned long long* dstat, uint64_t lo, uint64_t hi) {
     const KT sufmask = mask_bases<KT>(G.k - 1);
-    const int top = 2 * (G.k - 1);
     for (uint64_t oid = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < hi; oid += (uint64_t)gridDim.x * blockDim.x) {
         if (!(alive[oid] & 2)) continue;
         const KT X = G.oriented((uint32_t)oid);
@@ -320,34 +286,16 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
             if (oy != NONE32 && (alive[oy] & 2)) { next = oy; n_cand++; }
         }
         if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
-        if (!SHARDED && (lflag[oid] >= 0 || rflag[oid] >= 0)) atomicAdd(&dstat[DS_FLAGGED], 1ull);
+        if (lflag[oid] >= 0 || rflag[oid] >= 0) atomicAdd(&dstat[DS_FLAGGED], 1ull);
         if (next != NONE32) {
-            const bool joins = SHARDED ? (((alive[oid] >> 2) & 1) == ((alive[next] >> 3) & 1)) : junction_joins(rflag[oid], lflag[next]);
+            const bool joins = junction_joins(rflag[oid], lflag[next]);
             if (!joins) atomicAdd(&dstat[DS_BUDGET], 1ull);
             if (next == (uint32_t)oid) {
                 if (joins) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
-            } else if (!SHARDED) {
+            } else {
                 succ[oid] = next;
                 if (atomicExch(&pred[next], (uint32_t)oid) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
-            } else if (joins) {
-                succ[oid] = next;
-            } else {
-                open_next[oid] = next;
             }
-        }
-        if (SHARDED) {
-            const KT prefix = X >> 2;
-            uint32_t prev = NONE32;
-            int n_prev = 0;
-#pragma unroll
-            for (uint32_t a = 0; a < 4; a++) {
-                uint32_t cz;
-                const uint32_t hf = G.g_bins > 1 ? G.first_mm(prefix, a) : 0u;
-                const uint32_t oz = G.find(((KT)a << top) | prefix, hf < pre_min ? hf : pre_min, &cz);
-                if (oz != NONE32 && (alive[oz] & 2)) { prev = oz; n_prev++; }
-            }
-            if (n_prev > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 2ull); continue; }
-            if (prev != NONE32 && prev != (uint32_t)oid && (((alive[prev] >> 2) & 1) == ((alive[oid] >> 3) & 1))) pred[oid] = prev;
         }
     }
 }
@@ -363,9 +311,6 @@ __global__ void link_kernel(Graph<KT> G, const uint8_t* __restrict__ alive, cons
 // writing the effective flags of what it absorbs and marking the junctions it went through (alive bit 4 / 5 on the
 // junction's left node).  On a closed path where every walk may wrap around, the fork winner with the smallest oriented
 // k-mer starts fresh (oracle: loop_start).
-__device__ __forceinline__ void alive_or(uint8_t* alive, uint64_t i, uint32_t bit) {
-    atomicOr(reinterpret_cast<unsigned int*>(alive + (i & ~(uint64_t)3)), bit << (8u * (uint32_t)(i & 3u)));
-}
 template <class KT, int DIR>
 __global__ void budget_walk_kernel(Graph<KT> G, uint64_t n, uint8_t* alive, const int32_t* __restrict__ bud, const int32_t* __restrict__ face,
                                    const uint32_t* __restrict__ nxt, const uint32_t* __restrict__ prv, int32_t* eff, int bmax, unsigned long long* dstat) {
@@ -430,7 +375,6 @@ __global__ void junction_finalize_kernel(uint64_t n, const uint8_t* __restrict__
 // ---- K6: pointer jumping towards the head ------------------------------------------------------
 // One 64-bit word per node: low half = current ancestor, high half = distance to it, so a jump costs one random
 // 8-byte read.  Double buffered (Jacobi), so every round is deterministic.
-__device__ __forceinline__ uint64_t ad_pack(uint32_t anc, uint32_t dist) { return (uint64_t)anc | ((uint64_t)dist << 32); }
 
 __global__ void rank_init_kernel(uint64_t n, const uint32_t* __restrict__ pred, uint64_t* __restrict__ ad) {
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
@@ -740,15 +684,12 @@ template <class KT> static int graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->loc, n * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->chain_len, n * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_idx, n * sizeof(uint32_t)));
-    DevBuf& open_next = c->open_next;  // separate from tail_of: both are live in the admissibility pass
-    RFX_TRY(devbuf_reserve(c, open_next, n * sizeof(uint32_t)));
     int rc = RFX_OK;
     do {
         if ((rc = build_index<KT>(c)) != RFX_OK) break;
         Graph<KT> G = make_graph<KT>(c);
         cudaMemsetAsync(c->succ.p, 0xff, n * sizeof(uint32_t), st);
         cudaMemsetAsync(c->pred.p, 0xff, n * sizeof(uint32_t), st);
-        cudaMemsetAsync(open_next.p, 0xff, n * sizeof(uint32_t), st);
         cudaMemsetAsync(c->chain_len.p, 0, n * sizeof(uint32_t), st);
         cudaMemsetAsync(c->tail_of.p, 0xff, n * sizeof(uint32_t), st);
         const int E = c->prm.min_error_coverage;
@@ -759,7 +700,7 @@ template <class KT> static int graph_impl(Ctx* c) {
         uint32_t* pred = c->pred.as<uint32_t>();
         right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, rflag, 0, n);
         left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, E, alive, lflag, 0, n);
-        link_kernel<KT, false><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, open_next.as<uint32_t>(), dstat, 0, n);
+        link_kernel<KT><<<grid_n(n), 256, 0, st>>>(G, alive, lflag, rflag, succ, pred, dstat, 0, n);
         c->launches += 3;
         cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
@@ -804,7 +745,7 @@ template <class KT> static int graph_impl(Ctx* c) {
                 splitter_walk_kernel<<<sm_count() * 16, 256, 0, st>>>(dstat + DS_NSPL, spl_node, succ, spl_id, loc, c->sp_ad[0].as<uint64_t>());
                 cudaMemsetAsync(dstat + DS_RANK_FLAGS, 0, 3 * sizeof(uint64_t), st);
                 cudaMemsetAsync(dstat + DS_RANK_CUR, 0, sizeof(uint64_t), st);
-                if (n <= (16ull << 20)) {
+                if (n <= (16ull << 20) && !c->arena) {  // (a rank of a sharded run may share its device with a peer that waits in a barrier: no co-resident grid)
                     // up to ~10^6 splitters: every round in one cooperative launch, no host round trip at all
                     const unsigned long long* m_ptr = dstat + DS_NSPL;
                     uint64_t* a0 = c->sp_ad[0].as<uint64_t>();
@@ -917,419 +858,6 @@ template <class KT> static int graph_impl(Ctx* c) {
     return rc;
 }
 
-// =================================================================================================================
-// Sharded graph stages: one process per GPU, rows sharded by minimiser bin exactly as the counting left
-// them.  Every rank holds the whole (k-mer, count) table and its index (cheap: 12 B per row, built once), but does the
-// per-node work -- fork filters, links, chain walking, base gather -- for its OWN rows only.  What crosses GPUs:
-//   * one byte per node after each fork filter (alive + flag signs), broadcast by its owner;
-//   * the splitter list: chain heads, a 1-in-16 sample and every node whose predecessor lives on another GPU.  An owner
-//     walks each of its splitters to the next one; (node, next splitter node, segment length) triples are all-gathered
-//     and every rank ranks that reduced list (a few % of the nodes) -- the "cross-shard chain joins" of the extension;
-//   * one (head, length, right flag) tuple per chain and one (head, left flag) per head, from which every rank builds
-//     the same contig table; each rank then writes the bases of its own nodes and a byte-wise max merges the buffers.
-// The collectives themselves are issued by the caller (reflexiv_b200/sharded.py, NCCL) between these steps.
-// Cycles (no head anywhere) are not handled here: rfx_gs_rank reports them and the caller uses the replicated path.
-// =================================================================================================================
-struct GsTail { uint32_t head, len; int32_t rflag; };
-struct GsHead { uint32_t head; int32_t lflag; };
-
-__device__ __forceinline__ bool gs_own(uint32_t x, uint64_t lo, uint64_t hi) { return x >= lo && x < hi; }
-// own segments already end at every GPU boundary (every ~10 nodes with minimiser sharding), so the random sample only
-// has to bound the walk through unusually long own stretches
-__device__ __forceinline__ bool gs_random_splitter(uint32_t x) { return (fmix32(x ^ 0xa5a5a5a5u) & 127u) == 0u; }
-
-__global__ void gs_splitter_select_kernel(uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ pred,
-                                          uint32_t* __restrict__ spl_id, uint32_t* __restrict__ spl_node, unsigned long long* dstat) {
-    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t id = NONE32;
-        if (alive[x] & 2) {
-            const uint32_t p = pred[x];
-            if (p == NONE32 || gs_random_splitter((uint32_t)x) || !gs_own(p, lo, hi)) {
-                id = (uint32_t)atomicAdd(&dstat[DS_NSPL], 1ull);
-                spl_node[id] = (uint32_t)x;
-            }
-        }
-        spl_id[x] = id;
-    }
-}
-// every own splitter walks its successors up to the next splitter: a sampled node, or a node on another GPU
-__global__ void gs_splitter_walk_kernel(uint64_t m, uint64_t lo, uint64_t hi, const uint32_t* __restrict__ spl_node, const uint32_t* __restrict__ succ,
-                                        uint64_t* __restrict__ loc, uint32_t* __restrict__ nxt, uint32_t* __restrict__ seg_len) {
-    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m; id += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t x = spl_node[id];
-        uint32_t off = 0;
-        loc[x] = ad_pack((uint32_t)id, 0u);
-        uint32_t y = succ[x];
-        while (y != NONE32 && gs_own(y, lo, hi) && !gs_random_splitter(y)) {
-            off++;
-            loc[y] = ad_pack((uint32_t)id, off);
-            y = succ[y];
-        }
-        nxt[id] = y;
-        seg_len[id] = off + 1u;
-    }
-}
-// reduced list over ALL splitters (gathered): index by node, then predecessor-splitter links
-__global__ void gs_index_kernel(uint64_t M, const uint32_t* __restrict__ g_node, uint32_t* __restrict__ gidx, uint64_t* __restrict__ sp_ad) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        gidx[g_node[i]] = (uint32_t)i;
-        sp_ad[i] = ad_pack((uint32_t)i, 0u);
-    }
-}
-__global__ void gs_reduced_link_kernel(uint64_t M, const uint32_t* __restrict__ g_next, const uint32_t* __restrict__ g_len, const uint32_t* __restrict__ gidx,
-                                       uint64_t* __restrict__ sp_ad, unsigned long long* dstat) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t y = g_next[i];
-        if (y == NONE32) continue;
-        const uint32_t j = gidx[y];
-        if (j == NONE32) { atomicExch(&dstat[DS_GRAPH_ERR], 5ull); continue; }  // successor splitter missing from the gathered list
-        sp_ad[j] = ad_pack((uint32_t)i, g_len[i]);
-    }
-}
-// after the jumps every splitter must hang off a true head (an entry that still is its own ancestor at distance 0)
-__global__ void gs_cycle_check_kernel(uint64_t M, const uint64_t* __restrict__ sp_ad, unsigned long long* dstat) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = (uint32_t)sp_ad[i];
-        if (sp_ad[a] != ad_pack(a, 0u)) atomicExch(&dstat[DS_CYCLE_NODES], 1ull);
-    }
-}
-__global__ void gs_finalize_kernel(uint64_t lo, uint64_t hi, uint64_t my_off, const uint8_t* __restrict__ alive, const uint64_t* __restrict__ loc,
-                                   const uint64_t* __restrict__ sp_ad, const uint32_t* __restrict__ g_node, uint64_t* __restrict__ ad,
-                                   unsigned long long* dstat) {
-    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
-        if (!(alive[x] & 2)) { ad[x] = ad_pack((uint32_t)x, 0u); continue; }
-        const uint64_t l = loc[x];
-        if (l == ~0ull) { ad[x] = ad_pack((uint32_t)x, 0u); atomicExch(&dstat[DS_CYCLE_NODES], 1ull); continue; }  // cycle without a splitter
-        const uint64_t v = sp_ad[my_off + (uint32_t)l];
-        ad[x] = ad_pack(g_node[(uint32_t)v], (uint32_t)(v >> 32) + (uint32_t)(l >> 32));
-    }
-}
-__global__ void gs_chains_kernel(uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint32_t* __restrict__ succ, const uint32_t* __restrict__ pred,
-                                 const uint64_t* __restrict__ ad, const int32_t* __restrict__ lflag, const int32_t* __restrict__ rflag, GsTail* __restrict__ tails,
-                                 GsHead* __restrict__ heads, unsigned long long* dstat) {
-    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
-        if (!(alive[x] & 2)) continue;
-        atomicAdd(&dstat[DS_ORIENTED], 1ull);
-        if (succ[x] == NONE32) {
-            const uint64_t v = ad[x];
-            tails[atomicAdd(&dstat[DS_NSPL], 1ull)] = GsTail{(uint32_t)v, (uint32_t)(v >> 32) + 1u, rflag[x]};
-        }
-        if (pred[x] == NONE32) heads[atomicAdd(&dstat[DS_CHANGED], 1ull)] = GsHead{(uint32_t)x, lflag[x]};
-    }
-}
-__global__ void gs_scatter_heads_kernel(uint64_t n, const GsHead* __restrict__ heads, int32_t* __restrict__ lflag) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) lflag[heads[i].head] = heads[i].lflag;
-}
-struct GsContigIn {
-    const GsTail* tails;
-    const int32_t* lflag;
-    int k, min_contig;
-    __device__ __forceinline__ U64x3 operator()(uint64_t i) const {
-        const GsTail t = tails[i];
-        const uint64_t len = (uint64_t)t.len + (uint64_t)k - 1;
-        const bool keep = !(lflag[t.head] <= -10000000 && t.rflag <= -10000000) && len >= (uint64_t)min_contig;  // DSKmerToContig, ReflexivDSMain.java:749-754
-        return keep ? U64x3{1, len, 1} : U64x3{0, 0, 1};
-    }
-};
-struct GsContigOut {
-    const GsTail* tails;
-    const int32_t* lflag;
-    uint32_t* ctg_idx;
-    uint32_t* chain_len;
-    uint64_t* ctg_off;
-    int32_t* ctg_left;
-    int32_t* ctg_right;
-    __device__ __forceinline__ void operator()(uint64_t i, U64x3 excl, U64x3 v) const {
-        const GsTail t = tails[i];
-        chain_len[t.head] = t.len;
-        if (v.a) {
-            ctg_idx[t.head] = (uint32_t)excl.a;
-            ctg_off[excl.a] = excl.b;
-            ctg_left[excl.a] = lflag[t.head];
-            ctg_right[excl.a] = t.rflag;
-        }
-    }
-};
-template <class KT>
-__global__ void gs_gather_kernel(Graph<KT> G, uint64_t lo, uint64_t hi, const uint8_t* __restrict__ alive, const uint64_t* __restrict__ ad,
-                                 const uint32_t* __restrict__ ctg_idx, const uint64_t* __restrict__ ctg_off, char* __restrict__ out) {
-    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
-        if (!(alive[x] & 2)) continue;
-        const uint64_t v = ad[x];
-        const uint32_t h = (uint32_t)v;
-        const uint32_t ci = ctg_idx[h];
-        if (ci == NONE32) continue;
-        const KT X = G.oriented((uint32_t)x);
-        char* dst = out + ctg_off[ci];
-        dst[(uint64_t)(G.k - 1) + (uint32_t)(v >> 32)] = "ACGT"[(uint32_t)X & 3u];
-        if (h == (uint32_t)x)
-            for (int j = 0; j < G.k - 1; j++) dst[j] = "ACGT"[(uint32_t)(X >> (2 * (G.k - 1 - j))) & 3u];
-    }
-}
-__global__ void gs_budget_kernel(uint64_t lo, uint64_t hi, const uint32_t* __restrict__ open_next, const uint8_t* __restrict__ alive, const int32_t* __restrict__ lflag,
-                                 const int32_t* __restrict__ rflag, const uint64_t* __restrict__ ad, const uint32_t* __restrict__ chain_len, unsigned long long* dstat) {
-    for (uint64_t x = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < hi; x += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t y = open_next[x];
-        if (y == NONE32) continue;
-        // y is a head (the junction in front of it stayed open), so its left flag arrived with the head tuples
-        const int64_t r_ext = (int64_t)(ad[x] >> 32) + 1, f_ext = (int64_t)chain_len[y];
-        if ((lflag[y] >= 0 && lflag[y] - r_ext >= 0) || (rflag[x] >= 0 && rflag[x] - f_ext >= 0)) atomicAdd(&dstat[DS_BUDGET_ADM], 1ull);
-    }
-}
-
-template <class KT> static Graph<KT> gs_graph(Ctx* c) { return make_graph<KT>(c); }
-static int gs_sync(Ctx* c, const char* what) {
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
-    return RFX_OK;
-}
-
-// step 1: index over the whole table, right fork filter for the own rows
-template <class KT> static int gs_begin_impl(Ctx* c) {
-    cudaStream_t st = c->stream;
-    const uint64_t n_rows = c->n_rows, n = 2 * n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi;
-    if (n >= 0xffffffffull) return ctx_fail(c, RFX_E_CAPACITY, "more than 2^31 rows: oriented ids do not fit 32 bits");
-    stage_begin(c);
-    RFX_TRY(devbuf_reserve(c, c->rflag, (n + 1) * sizeof(int32_t)));
-    RFX_TRY(devbuf_reserve(c, c->lflag, (n + 1) * sizeof(int32_t)));
-    RFX_TRY(devbuf_reserve(c, c->alive, n + 16));
-    RFX_TRY(devbuf_reserve(c, c->succ, (n + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->pred, (n + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->open_next, (n + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->spl_id, (n + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->loc, (n + 1) * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, c->ad[0], (n + 1) * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, c->chain_len, (n + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->ctg_idx, (n + 1) * sizeof(uint32_t)));
-    const uint64_t own = hi - lo;
-    RFX_TRY(devbuf_reserve(c, c->spl_node, (own + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->gs_next, (own + 1) * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->gs_len, (own + 1) * sizeof(uint32_t)));
-    RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->alive.p, 0, n + 16, st));
-    RFX_TRY(build_index<KT>(c));
-    Graph<KT> G = gs_graph<KT>(c);
-    if (own) right_filter_kernel<KT><<<grid_n(own), 256, 0, st>>>(G, c->prm.min_error_coverage, c->alive.as<uint8_t>(), c->rflag.as<int32_t>(), lo, hi);
-    c->launches += 2;
-    RFX_TRY(gs_sync(c, "sharded right filter"));
-    c->ms[3] += stage_end(c);
-    c->have_contigs = false; c->have_sorted = false;
-    return RFX_OK;
-}
-
-// step 2 (alive bytes of every rank are in place): left fork filter for the own rows
-template <class KT> static int gs_left_impl(Ctx* c) {
-    cudaStream_t st = c->stream;
-    const uint64_t lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi;
-    stage_begin(c);
-    if (hi > lo) left_filter_kernel<KT><<<grid_n(hi - lo), 256, 0, st>>>(gs_graph<KT>(c), c->prm.min_error_coverage, c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), lo, hi);
-    c->launches++;
-    RFX_TRY(gs_sync(c, "sharded left filter"));
-    c->ms[3] += stage_end(c);
-    return RFX_OK;
-}
-
-// step 3 (alive bytes final everywhere): links of the own nodes, splitters, segment walk
-template <class KT> static int gs_link_impl(Ctx* c, uint64_t* n_splitters) {
-    cudaStream_t st = c->stream;
-    const uint64_t lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
-    unsigned long long* dstat = c->dstat.as<unsigned long long>();
-    stage_begin(c);
-    // per-node arrays are only ever read at own nodes: clear the own range
-    RFX_CUDA(c, cudaMemsetAsync(c->succ.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->pred.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->open_next.as<uint32_t>() + lo, 0xff, own * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->loc.as<uint64_t>() + lo, 0xff, own * sizeof(uint64_t), st));
-    if (own)
-        link_kernel<KT, true><<<grid_n(own), 256, 0, st>>>(gs_graph<KT>(c), c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), c->succ.as<uint32_t>(),
-                                                           c->pred.as<uint32_t>(), c->open_next.as<uint32_t>(), dstat, lo, hi);
-    uint64_t h[DS_NSLOTS];
-    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-    RFX_TRY(gs_sync(c, "sharded link"));
-    c->ms[3] += stage_end(c);
-    if (h[DS_GRAPH_ERR]) return ctx_fail(c, RFX_E_GRAPH, "fork filters left a (k-1)-mer with degree > 1 (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]);
-    c->n_budget = h[DS_BUDGET];
-    c->n_cycles = h[DS_CYCLES];
-    stage_begin(c);
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st));
-    uint64_t m = 0;
-    if (own) gs_splitter_select_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->alive.as<uint8_t>(), c->pred.as<uint32_t>(), c->spl_id.as<uint32_t>(), c->spl_node.as<uint32_t>(), dstat);
-    RFX_CUDA(c, cudaMemcpyAsync(&m, dstat + DS_NSPL, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    RFX_TRY(gs_sync(c, "splitter selection"));
-    if (m) gs_splitter_walk_kernel<<<grid_n(m), 256, 0, st>>>(m, lo, hi, c->spl_node.as<uint32_t>(), c->succ.as<uint32_t>(), c->loc.as<uint64_t>(), c->gs_next.as<uint32_t>(), c->gs_len.as<uint32_t>());
-    c->launches += 3;
-    RFX_TRY(gs_sync(c, "splitter walk"));
-    c->ms[4] += stage_end(c);
-    c->gs_m = m;
-    *n_splitters = m;
-    return RFX_OK;
-}
-
-// step 4 (splitter triples of every rank gathered, rank order): rank the reduced list, finish the own nodes, list chains
-static int gs_rank_impl(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads) {
-    cudaStream_t st = c->stream;
-    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
-    unsigned long long* dstat = c->dstat.as<unsigned long long>();
-    stage_begin(c);
-    for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, c->sp_ad[i], (M + 1) * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, c->gs_tails, (own + 1) * sizeof(GsTail)));
-    RFX_TRY(devbuf_reserve(c, c->gs_heads, (own + 1) * sizeof(GsHead)));
-    uint32_t* gidx = c->spl_id.as<uint32_t>();  // the per-node splitter ids are no longer needed: reuse as node -> global splitter index
-    RFX_CUDA(c, cudaMemsetAsync(gidx, 0xff, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CYCLE_NODES, 0, sizeof(uint64_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_GRAPH_ERR, 0, sizeof(uint64_t), st));
-    int scur = 0;
-    if (M) {
-        gs_index_kernel<<<grid_n(M), 256, 0, st>>>(M, g_node, gidx, c->sp_ad[0].as<uint64_t>());
-        gs_reduced_link_kernel<<<grid_n(M), 256, 0, st>>>(M, g_next, g_len, gidx, c->sp_ad[0].as<uint64_t>(), dstat);
-        c->launches += 2;
-        if (M <= 1000000ull) {
-            // short list: all jumping rounds in one cooperative launch (rank_all_kernel); it reads the length from the device
-            set_value_kernel<<<1, 1, 0, st>>>(dstat + DS_NSPL, (unsigned long long)M);
-            RFX_CUDA(c, cudaMemsetAsync(dstat + DS_RANK_FLAGS, 0, 3 * sizeof(uint64_t), st));
-            RFX_CUDA(c, cudaMemsetAsync(dstat + DS_RANK_CUR, 0, sizeof(uint64_t), st));
-            {
-                const unsigned long long* m_ptr = dstat + DS_NSPL;
-                uint64_t* a0 = c->sp_ad[0].as<uint64_t>();
-                uint64_t* a1 = c->sp_ad[1].as<uint64_t>();
-                unsigned long long* ds = dstat;
-                void* args[] = {(void*)&m_ptr, (void*)&a0, (void*)&a1, (void*)&ds};
-                RFX_CUDA(c, cudaLaunchCooperativeKernel((void*)rank_all_kernel, dim3(sm_count() * 4), dim3(256), args, 0, st));
-            }
-            uint64_t which = 0;
-            RFX_CUDA(c, cudaMemcpyAsync(&which, dstat + DS_RANK_CUR, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-            RFX_TRY(gs_sync(c, "reduced list ranking"));
-            scur = (int)which;
-            c->launches += 2;
-        } else {
-            // long list (several GPUs' worth of splitters): one launch per round over as many threads as there are
-            // entries beats the co-resident grid (measured at 4 GPUs: 1.2 ms against 3.8 ms)
-            int slimit = 2;
-            while ((1ull << slimit) < M + 1) slimit++;
-            slimit += 2;
-            for (int round = 0; round < slimit;) {
-                RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st));
-                for (int q = 0; q < 4 && round < slimit; q++, round++) {
-                    rank_step_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), c->sp_ad[scur ^ 1].as<uint64_t>(), dstat);
-                    c->launches++;
-                    scur ^= 1;
-                }
-                uint64_t changed = 0;
-                RFX_CUDA(c, cudaMemcpyAsync(&changed, dstat + DS_CHANGED, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-                RFX_TRY(gs_sync(c, "reduced list ranking"));
-                if (!changed) break;
-            }
-        }
-        gs_cycle_check_kernel<<<grid_n(M), 256, 0, st>>>(M, c->sp_ad[scur].as<uint64_t>(), dstat);
-    }
-    if (own) gs_finalize_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, my_off, c->alive.as<uint8_t>(), c->loc.as<uint64_t>(), c->sp_ad[scur].as<uint64_t>(), g_node, c->ad[0].as<uint64_t>(), dstat);
-    uint64_t h[DS_NSLOTS];
-    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-    RFX_TRY(gs_sync(c, "sharded rank finalize"));
-    if (h[DS_GRAPH_ERR]) return ctx_fail(c, RFX_E_GRAPH, "sharded ranking: inconsistent splitter list (code %llu)", (unsigned long long)h[DS_GRAPH_ERR]);
-    c->gs_cycle = h[DS_CYCLE_NODES] != 0;
-    // chains: (head, length, right flag) per own tail, (head, left flag) per own head
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_NSPL, 0, sizeof(uint64_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_CHANGED, 0, sizeof(uint64_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_ORIENTED, 0, sizeof(uint64_t), st));
-    if (own && !c->gs_cycle)
-        gs_chains_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->alive.as<uint8_t>(), c->succ.as<uint32_t>(), c->pred.as<uint32_t>(), c->ad[0].as<uint64_t>(), c->lflag.as<int32_t>(),
-                                                      c->rflag.as<int32_t>(), c->gs_tails.as<GsTail>(), c->gs_heads.as<GsHead>(), dstat);
-    RFX_CUDA(c, cudaMemcpyAsync(h, c->dstat.p, sizeof(h), cudaMemcpyDeviceToHost, st));
-    RFX_TRY(gs_sync(c, "chain listing"));
-    c->launches += 3;
-    c->ms[4] += stage_end(c);
-    c->gs_n_tails = h[DS_NSPL]; c->gs_n_heads = h[DS_CHANGED]; c->n_oriented = h[DS_ORIENTED];
-    *n_tails = c->gs_n_tails; *n_heads = c->gs_n_heads;
-    return RFX_OK;
-}
-
-// step 5 (chain tuples of every rank gathered): the contig table (identical on every rank) and the bases of the own nodes
-template <class KT> static int gs_contigs_impl(Ctx* c, const GsTail* tails, uint64_t n_tails, const GsHead* heads, uint64_t n_heads) {
-    cudaStream_t st = c->stream;
-    const uint64_t n = 2 * c->n_rows, lo = 2 * c->gs_row_lo, hi = 2 * c->gs_row_hi, own = hi - lo;
-    unsigned long long* dstat = c->dstat.as<unsigned long long>();
-    stage_begin(c);
-    RFX_CUDA(c, cudaMemsetAsync(c->ctg_idx.p, 0xff, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->chain_len.p, 0, (n + 1) * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(dstat + DS_BUDGET_ADM, 0, sizeof(uint64_t), st));
-    if (n_heads) gs_scatter_heads_kernel<<<grid_n(n_heads), 256, 0, st>>>(n_heads, heads, c->lflag.as<int32_t>());
-    U64x3 tot{0, 0, 0};
-    ScanPlan<U64x3> plan;
-    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<U64x3>::workspace_elems(n_tails + 1) * sizeof(U64x3)));
-    GsContigIn in{tails, c->lflag.as<int32_t>(), c->k, c->prm.min_contig};
-    if (n_tails) {
-        plan.bind(n_tails, c->scan_ws.as<U64x3>());
-        scan_prepare(plan, in, OpAddU64x3{}, U64x3{0, 0, 0}, st);
-        c->launches += 2 * plan.levels;
-        RFX_CUDA(c, cudaMemcpyAsync(&tot, plan.total, sizeof(tot), cudaMemcpyDeviceToHost, st));
-        RFX_TRY(gs_sync(c, "sharded contig scan"));
-    }
-    RFX_TRY(devbuf_reserve(c, c->ctg_off, (tot.a + 1) * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, c->ctg_left, (tot.a + 1) * sizeof(int32_t)));
-    RFX_TRY(devbuf_reserve(c, c->ctg_right, (tot.a + 1) * sizeof(int32_t)));
-    RFX_TRY(devbuf_reserve(c, c->ctg_bases, tot.b + 16));
-    RFX_CUDA(c, cudaMemsetAsync(c->ctg_bases.p, 0, tot.b + 16, st));
-    if (n_tails) {
-        GsContigOut out{tails, c->lflag.as<int32_t>(), c->ctg_idx.as<uint32_t>(), c->chain_len.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_left.as<int32_t>(),
-                        c->ctg_right.as<int32_t>()};
-        scan_apply(plan, in, out, OpAddU64x3{}, U64x3{0, 0, 0}, st);
-        set_u64_kernel<<<1, 1, 0, st>>>(c->ctg_off.as<uint64_t>() + tot.a, plan.total);
-    } else {
-        RFX_CUDA(c, cudaMemsetAsync(c->ctg_off.p, 0, sizeof(uint64_t), st));
-    }
-    if (own) {
-        gs_gather_kernel<KT><<<grid_n(own), 256, 0, st>>>(gs_graph<KT>(c), lo, hi, c->alive.as<uint8_t>(), c->ad[0].as<uint64_t>(), c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(),
-                                                          c->ctg_bases.as<char>());
-        gs_budget_kernel<<<grid_n(own), 256, 0, st>>>(lo, hi, c->open_next.as<uint32_t>(), c->alive.as<uint8_t>(), c->lflag.as<int32_t>(), c->rflag.as<int32_t>(), c->ad[0].as<uint64_t>(),
-                                                      c->chain_len.as<uint32_t>(), dstat);
-    }
-    c->launches += 5;
-    uint64_t adm = 0;
-    RFX_CUDA(c, cudaMemcpyAsync(&adm, dstat + DS_BUDGET_ADM, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    RFX_TRY(gs_sync(c, "sharded contig gather"));
-    c->ms[5] += stage_end(c);
-    c->n_contigs = tot.a;
-    c->n_contig_bases = tot.b;
-    c->n_budget_adm = adm;
-    return RFX_OK;
-}
-
-int stage_gs_begin(Ctx* c, uint64_t row_lo, uint64_t row_hi) {
-    if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "rfx_gs_begin: no count table");
-    if (!c->prm.bubble) return ctx_fail(c, RFX_E_UNSUPPORTED, "-bubble: see rfx_assemble");
-    if (c->k < 2) return ctx_fail(c, RFX_E_INVALID, "assembly needs k >= 2");
-    if (row_lo > row_hi || row_hi > c->n_rows) return ctx_fail(c, RFX_E_INVALID, "rfx_gs_begin: rows [%llu, %llu) outside the table of %llu rows",
-                                                                 (unsigned long long)row_lo, (unsigned long long)row_hi, (unsigned long long)c->n_rows);
-    c->gs_row_lo = row_lo; c->gs_row_hi = row_hi; c->gs_step = 1; c->gs_cycle = false;
-    return c->wide ? gs_begin_impl<u128>(c) : gs_begin_impl<uint64_t>(c);
-}
-int stage_gs_left(Ctx* c) {
-    if (c->gs_step != 1) return ctx_fail(c, RFX_E_STATE, "rfx_gs_left: call rfx_gs_begin first");
-    c->gs_step = 2;
-    return c->wide ? gs_left_impl<u128>(c) : gs_left_impl<uint64_t>(c);
-}
-int stage_gs_link(Ctx* c, uint64_t* n_splitters) {
-    if (c->gs_step != 2) return ctx_fail(c, RFX_E_STATE, "rfx_gs_link: call rfx_gs_left first");
-    c->gs_step = 3;
-    return c->wide ? gs_link_impl<u128>(c, n_splitters) : gs_link_impl<uint64_t>(c, n_splitters);
-}
-int stage_gs_rank(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads, int32_t* has_cycle) {
-    if (c->gs_step != 3) return ctx_fail(c, RFX_E_STATE, "rfx_gs_rank: call rfx_gs_link first");
-    if (my_off + c->gs_m > M) return ctx_fail(c, RFX_E_INVALID, "rfx_gs_rank: own splitters [%llu, +%llu) outside the gathered list of %llu", (unsigned long long)my_off,
-                                              (unsigned long long)c->gs_m, (unsigned long long)M);
-    c->gs_step = 4;
-    RFX_TRY(gs_rank_impl(c, g_node, g_next, g_len, M, my_off, n_tails, n_heads));
-    *has_cycle = c->gs_cycle ? 1 : 0;
-    return RFX_OK;
-}
-int stage_gs_contigs(Ctx* c, const void* tails, uint64_t n_tails, const void* heads, uint64_t n_heads) {
-    if (c->gs_step != 4 || c->gs_cycle) return ctx_fail(c, RFX_E_STATE, "rfx_gs_contigs: call rfx_gs_rank first (and use rfx_assemble when it reports a cycle)");
-    c->gs_step = 5;
-    return c->wide ? gs_contigs_impl<u128>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads)
-                   : gs_contigs_impl<uint64_t>(c, (const GsTail*)tails, n_tails, (const GsHead*)heads, n_heads);
-}
-
 template <class KT> static int sorted_impl(Ctx* c, int E, double fold, int X) {
     cudaStream_t st = c->stream;
     const uint64_t n = 2 * c->n_rows;
@@ -1391,3 +919,5 @@ int stage_graph(Ctx* c) {
 }
 
 }  // namespace rfx
+
+#include "rfx_shard_graph.cuh"

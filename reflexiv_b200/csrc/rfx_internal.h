@@ -15,6 +15,7 @@ namespace rfx {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool in_arena = false;  // carved out of the context's peer-visible arena (sharded runs): never cudaFree'd on its own
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -35,6 +36,28 @@ void devbuf_free(DevBuf& b);
         int rc_ = (expr);             \
         if (rc_ != RFX_OK) return rc_; \
     } while (0)
+
+// ---- record segments of the counting kernel ----
+// One entry per (segment, bin): where the bin's records inside that segment start (absolute address, possibly in a peer
+// GPU's memory) and how many there are.  Built by build_ext_kernel from at most RFX_MAX_SEG segment descriptions.
+#define RFX_MAX_SEG 16
+#define RFX_MAX_RANKS 8
+#define RFX_PUB_SLOTS 56
+struct SegExt {
+    unsigned long long addr;
+    uint32_t cnt, pad;
+};
+struct ExtSrc {
+    const uint64_t* rec;       // record array of the segment
+    const uint32_t* slab_cnt;  // slab layout: records of bin b at rec[b * slab_cap ..], min(slab_cnt[b], slab_cap) of them
+    const uint64_t* off;       // offset layout: records of bin b at rec[off[b] - off_sub .. off[b + 1] - off_sub)
+    uint64_t off_sub;          // subtracted from the offsets (a received slice carries its sender's absolute offsets)
+    uint32_t slab_cap;         // != 0: slab layout
+    uint32_t bin_base;         // the segment's arrays are indexed by bin_base + (bin of the table)
+};
+struct ExtSrcs {
+    ExtSrc s[RFX_MAX_SEG];
+};
 
 struct StageTimer {
     cudaEvent_t a = nullptr, b = nullptr;
@@ -93,6 +116,7 @@ struct Ctx {
     uint64_t rx_bytes = 0;
     int32_t shard_id = -1;
     // per-sender segments (rfx_load_segment_device): record base in rx_records + the sender's bin offsets
+    DevBuf seg_ext;       // SegExt[n_seg][n_bins]: what the counting kernel walks
     DevBuf seg_off;       // u64[n_seg][bps + 1]
     DevBuf seg_base;      // u64[n_seg]
     uint64_t seg_base_host[64];
@@ -102,7 +126,7 @@ struct Ctx {
     DevBuf keys;        // KT[table_cap]  right-aligned canonical k-mers
     DevBuf counts;      // u32[table_cap]
     DevBuf dstat;       // u64[16] device-side counters
-    uint64_t table_cap = 0, n_rows = 0, n_distinct = 0, n_bin_splits = 0;
+    uint64_t table_cap = 0, n_rows = 0, n_distinct = 0, n_bin_splits = 0, n_shard_instances = 0;
     int count_geometry = 0;           // 0: unknown (run the pilot), 1: small table, 2: large table -- survives rfx_reset
     uint32_t count_geometry_bins = 0; // bin count of the run the pilot looked at
     bool have_counts = false;
@@ -119,7 +143,6 @@ struct Ctx {
     DevBuf alive;         // u8[2*n_rows]  bit0: survives right filter, bit1: survives both
     DevBuf succ, pred;    // u32[2*n_rows]
     DevBuf ad[2];         // u64[2*n_rows] packed (ancestor, distance) for pointer jumping, double buffered
-    DevBuf open_next;     // u32[2*n_rows] successor across a junction that stays open
     DevBuf spl_id;        // u32[2*n_rows] splitter index of a node, NONE if it is not a splitter
     DevBuf spl_node;      // u32[2*n_rows] node of a splitter
     DevBuf loc;           // u64[2*n_rows] (owning splitter, offset from it)
@@ -139,11 +162,24 @@ struct Ctx {
     uint64_t n_sorted = 0;
     bool have_sorted = false;
 
-    // ---- sharded graph stages (rfx_gs_*) ----
-    uint64_t gs_row_lo = 0, gs_row_hi = 0, gs_m = 0, gs_n_tails = 0, gs_n_heads = 0;
-    int gs_step = 0;
-    bool gs_cycle = false;
-    DevBuf gs_next, gs_len, gs_tails, gs_heads;
+    // ---- sharded runs over peer memory (rfx_shard.cu): one context per GPU, every device buffer of the context lives in
+    // ONE cudaMalloc'ed arena that the other ranks map (CUDA IPC between processes, plain pointers inside a process) ----
+    int sh_rank = -1, sh_world = 0;
+    uint8_t* arena = nullptr;
+    uint64_t arena_bytes = 0, arena_used = 0;
+    uint8_t* peer_base[RFX_MAX_RANKS] = {nullptr};  // arena of every rank as seen from this device (own: arena)
+    bool peer_ipc[RFX_MAX_RANKS] = {false};         // opened through cudaIpcOpenMemHandle
+    unsigned long long sh_epoch = 0;                // barriers passed
+    unsigned long long sh_exchanges = 0;            // value exchanges made (parity picks the published block)
+    unsigned long long* h_pub = nullptr;            // pinned: own published values + everybody's after an exchange
+    uint32_t sh_bins = 0;                           // total bin count of sharded counting (0: agreed on per run)
+    uint32_t sh_bins_run = 0;                       // ... the one in force for the slab scan (rfx_partition.cu: slab_begin)
+    uint64_t sh_inst_global = 0;                    // k-mer instances extracted by all ranks
+    cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+    float ms_comm = 0;                              // cross-GPU barriers + value exchanges of the last sharded calls
+    void* hbar = nullptr;                           // host-side barrier of ranks that share a device inside one process
+    unsigned long long hbar_key = 0;
+    struct GShard* gshard = nullptr;                // state of the sharded graph stages
 
     float ms[6] = {0, 0, 0, 0, 0, 0};
     float ms_kernel[3] = {0, 0, 0};  // histogram, scatter, count: last launch only
@@ -177,7 +213,11 @@ enum {
     DS_RANK_CUR = 22,     // which of the two (ancestor, distance) buffers holds the result of rank_all_kernel
     DS_RANK_FLAGS = 24,
     DS_READ_TOTALS = 28,  // 2 slots: bases kept and k-mer instances of the reads being appended   // 3 rotating 'something changed' flags of rank_all_kernel
-    DS_NSLOTS = 32
+    DS_XBAR_ERR = 30,     // a cross-GPU barrier timed out (rfx_shard.cu)
+    DS_NL2 = 32,          // level-2 splitters of the sharded chain ranking (rfx_shard_graph.cuh)
+    DS_REMOTE = 33,       // neighbour probes answered from a peer's index
+    DS_SG_CYCLE = 34,     // a closed path was seen
+    DS_NSLOTS = 40
 };
 
 static const uint32_t NONE32 = 0xffffffffu;
@@ -206,15 +246,13 @@ int stage_stream_partition_scan(Ctx* c);
 int stage_rebin(Ctx* c);
 int stage_adopt_segments(Ctx* c);
 int stage_count(Ctx* c);
+int stage_count_segments(Ctx* c, const ExtSrcs& S, int n_seg, uint32_t n_bins, bool check_instances);
 int stage_graph(Ctx* c);
 int stage_sorted(Ctx* c, int min_error_coverage, double min_repeat_fold, int max_kmer_size);
-int stage_gs_begin(Ctx* c, uint64_t row_lo, uint64_t row_hi);
-int stage_gs_left(Ctx* c);
-int stage_gs_link(Ctx* c, uint64_t* n_splitters);
-int stage_gs_rank(Ctx* c, const uint32_t* g_node, const uint32_t* g_next, const uint32_t* g_len, uint64_t M, uint64_t my_off, uint64_t* n_tails, uint64_t* n_heads,
-                  int32_t* has_cycle);
-int stage_gs_contigs(Ctx* c, const void* tails, uint64_t n_tails, const void* heads, uint64_t n_heads);
 uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards);
+int stage_count_sharded(Ctx* c);
+int stage_assemble_sharded(Ctx* c);
+void shard_release(Ctx* c);
 
 inline void stage_begin(Ctx* c) { cudaEventRecord(c->ev0, c->stream); }
 inline float stage_end(Ctx* c) {

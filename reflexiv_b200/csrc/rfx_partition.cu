@@ -588,7 +588,8 @@ __global__ void ovf_scatter_kernel(const uint64_t* __restrict__ ovf_rec, const u
 static int slab_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads) {
     cudaStream_t st = c->stream;
     c->n_shards = 1;
-    c->n_bins = choose_bin_count(c, est_instances, 1);
+    // sharded runs over peer memory: every rank scans into slabs over ALL bins of the run (rfx_shard.cu)
+    c->n_bins = (c->sh_world > 0 && c->sh_bins_run) ? c->sh_bins_run : choose_bin_count(c, est_instances, 1);
     set_minimizer(c, c->n_bins);
     const int w = c->k - c->m + 1;
     const size_t nb = c->n_bins;
@@ -596,7 +597,7 @@ static int slab_begin(Ctx* c, uint64_t est_instances, uint64_t est_reads) {
     const uint64_t est = est_instances * 2 / (uint64_t)(w + 1) + est_reads + 1;
     uint64_t cap = ((c->wide ? 3 : 2) * est / nb + 8 + 3) & ~(uint64_t)3;  // k > 31: few minimiser loci per bin, uneven bins
     if (cap > 0x7fffffffull) cap = 0x7fffffffull;
-    const uint64_t ovf_cap = est / (c->wide ? 3 : 8) + 4096;
+    const uint64_t ovf_cap = est / ((c->wide || c->sh_world > 0) ? 3 : 8) + 4096;
     RFX_TRY(devbuf_reserve(c, c->bin_cursor, nb * 4 * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->records, (nb * cap * c->recw + 2) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ovf_rec, (ovf_cap * c->recw + 2) * sizeof(uint64_t)));
@@ -697,7 +698,8 @@ int stage_stream_partition_scan(Ctx* c) {
 int stage_partition_slab(Ctx* c) {
     stage_begin(c);
     int rc = RFX_OK;
-    if (!(c->sp_active && c->sp_done == c->n_reads && c->n_reads)) {
+    const bool bins_fit = !(c->sh_world > 0 && c->sh_bins_run) || c->n_bins == c->sh_bins_run;
+    if (!(c->sp_active && c->sp_done == c->n_reads && c->n_reads && bins_fit)) {
         rc = slab_begin(c, c->n_instances, c->n_reads);
         if (rc == RFX_OK) rc = slab_scan(c, 0, c->n_reads);
     }

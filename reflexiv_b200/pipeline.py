@@ -257,38 +257,36 @@ class ReflexivContext:
     def load_counts_device(self, keys_ptr: int, counts_ptr: int, n_rows: int, append: bool = False):
         self._check(self.L.rfx_load_counts_device(self._ctx, keys_ptr, counts_ptr, n_rows, 1 if append else 0), self._ctx)
 
-    # ---- sharded assembly (see include/reflexiv_cuda.h: rfx_gs_*) ----
-    def gs_begin(self, row_lo: int, row_hi: int):
-        self._check(self.L.rfx_gs_begin(self._ctx, row_lo, row_hi), self._ctx)
+    # ---- multi-GPU over peer memory (include/reflexiv_cuda.h: rfx_shard_*) ----
+    def shard_init(self, rank: int, world: int, arena_bytes: int = 0):
+        self._check(self.L.rfx_shard_init(self._ctx, rank, world, arena_bytes), self._ctx)
 
-    def gs_alive(self) -> Tuple[int, int]:
-        p, n = C.c_void_p(), C.c_uint64()
-        self._check(self.L.rfx_gs_alive(self._ctx, C.byref(p), C.byref(n)), self._ctx)
-        return (p.value or 0), n.value
+    def shard_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.RFX_SHARD_HANDLE_BYTES)
+        self._check(self.L.rfx_shard_export(self._ctx, buf), self._ctx)
+        return buf.raw
 
-    def gs_left(self):
-        self._check(self.L.rfx_gs_left(self._ctx), self._ctx)
+    def shard_connect(self, handles: bytes, world: int):
+        assert len(handles) == world * _lib.RFX_SHARD_HANDLE_BYTES
+        self._check(self.L.rfx_shard_connect(self._ctx, handles, world), self._ctx)
 
-    def gs_link(self) -> Tuple[int, int, int, int]:
-        """(n_splitters, node ptr, next ptr, len ptr): uint32 device arrays of the own splitter triples."""
-        m, a, b, c = C.c_uint64(), C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._check(self.L.rfx_gs_link(self._ctx, C.byref(m), C.byref(a), C.byref(b), C.byref(c)), self._ctx)
-        return m.value, (a.value or 0), (b.value or 0), (c.value or 0)
+    def shard_set_bins(self, n_bins_total: int):
+        self._check(self.L.rfx_shard_set_bins(self._ctx, n_bins_total), self._ctx)
 
-    def gs_rank(self, node_ptr: int, next_ptr: int, len_ptr: int, n_total: int, my_offset: int):
-        """-> (n_tails, tails ptr [12 B each], n_heads, heads ptr [8 B each], has_cycle)"""
-        nt, pt, nh, ph, cyc = C.c_uint64(), C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_int32()
-        self._check(self.L.rfx_gs_rank(self._ctx, node_ptr, next_ptr, len_ptr, n_total, my_offset, C.byref(nt), C.byref(pt), C.byref(nh), C.byref(ph), C.byref(cyc)),
-                    self._ctx)
-        return nt.value, (pt.value or 0), nh.value, (ph.value or 0), bool(cyc.value)
+    def count_sharded(self):
+        """Collective: every rank calls it.  On return this context holds the rows whose minimiser bin it owns."""
+        self._check(self.L.rfx_count_sharded(self._ctx), self._ctx)
+        return self.stats()
 
-    def gs_contigs(self, tails_ptr: int, n_tails: int, heads_ptr: int, n_heads: int) -> Tuple[int, int]:
-        p, n = C.c_void_p(), C.c_uint64()
-        self._check(self.L.rfx_gs_contigs(self._ctx, tails_ptr, n_tails, heads_ptr, n_heads, C.byref(p), C.byref(n)), self._ctx)
-        return (p.value or 0), n.value
+    def assemble_sharded(self):
+        """Collective.  On return this context holds the contigs whose first k-mer it owns."""
+        self._check(self.L.rfx_assemble_sharded(self._ctx), self._ctx)
+        return self.stats()
 
-    def gs_finish(self, n_oriented: int, n_budget: int, n_budget_adm: int, n_cycles: int):
-        self._check(self.L.rfx_gs_finish(self._ctx, n_oriented, n_budget, n_budget_adm, n_cycles), self._ctx)
+    def shard_stats(self) -> dict:
+        s = _lib.RfxShardStats()
+        self._check(self.L.rfx_shard_stats(self._ctx, C.byref(s)), self._ctx)
+        return s.as_dict()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -1,11 +1,15 @@
-"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for the exchanges.
+"""Multi-GPU plumbing around the library's sharded calls.
 
-The counting path shards by minimiser bin: every rank bins its own reads into super-k-mer records
-laid out shard-major, one all-to-all moves each shard's slice to its owner (this is the step that replaces Spark's
-groupBy hash shuffle, ReflexivDataFrameCounter.java:198-200), the owner re-bins and counts locally.  Shard tables are
-disjoint, so their concatenation is the global table; no reduction collective is involved.
+The data path lives in the library (include/reflexiv_cuda.h: rfx_shard_*, csrc/rfx_shard.cu, rfx_shard_graph.cuh): one
+context per GPU, every rank's buffers in an arena the other ranks map, kernels reading and writing peer HBM over
+NVLink.  What this module adds is the set-up a launcher has to do once: hand every rank the handles of all ranks --
+through torch.distributed when there is one process per GPU (`connect`), directly when the ranks are threads of one
+process (`LocalRanks`, which is also how a one-GPU box runs the multi-rank path: several ranks share the device).
 
-`exchange_bytes` is backend agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+`sharded_count` is the measured alternative for the counting exchange: records laid out shard-major and moved by one
+NCCL all-to-all (the shape of Spark's groupBy shuffle, ReflexivDataFrameCounter.java:198-200) instead of being pulled
+out of the peers' slabs by the counting kernel itself.  `exchange_bytes` is backend agnostic (NCCL on GPUs, gloo in
+the CPU tests)."""
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
@@ -143,28 +147,6 @@ def sharded_count(ctx, torch, dist, device, n_bins_total: int, group=None, rebin
     return st
 
 
-def gather_tables(ctx, torch, dist, device, group=None, prof=None) -> dict:
-    """Replicates the global (k-mer, count) table on every rank (all_gather of the disjoint shard tables, concatenated
-    in rank order) so the graph stages can run; returns the context stats plus `row_ranges`, the rows every rank owns."""
-    lap = _Lap(torch, device, prof)
-    pk, pc, n, kb = ctx.counts_device()
-    keys = device_view(torch, pk, n * kb, device)
-    cnts = device_view(torch, pc, n * 4, device)
-    all_keys, sizes = gather_varlen(torch, dist, keys, group)
-    all_cnts, _ = gather_varlen(torch, dist, cnts, group)
-    n_all = sum(sizes) // kb
-    _sync(torch, device)
-    ctx.load_counts_device(all_keys.data_ptr() if n_all else 0, all_cnts.data_ptr() if n_all else 0, n_all, append=False)
-    lap("gather_tables")
-    st = ctx.stats()
-    lo, ranges = 0, []
-    for sz in sizes:
-        ranges.append((lo, lo + sz // kb))
-        lo += sz // kb
-    st["row_ranges"] = ranges
-    return st
-
-
 _UNEVEN_ALL_GATHER = {}
 
 
@@ -188,74 +170,48 @@ def _bcast_slices(torch, dist, buf, ranges, group=None):
             dist.broadcast(buf[lo:hi], src=dist.get_global_rank(group, r) if group is not None else r, group=group)
 
 
-def sharded_assemble(ctx, torch, dist, device, row_ranges, group=None, prof=None) -> dict:
-    """Graph stages across the ranks of `group` (include/reflexiv_cuda.h: rfx_gs_*): every rank holds the whole table
-    (gather_tables) and does the per-node work for its own rows; one byte per node after each fork filter, the
-    splitter list of the chain walk and one tuple per chain are what travels.  On return every rank holds the same
-    contig set, as after ctx.assemble().  A graph with a closed path falls back to the replicated ctx.assemble()."""
+# ---- peer-memory runs: set-up ------------------------------------------------------------------------------------------
+def connect(ctx, dist, group=None, arena_bytes: int = 0):
+    """One process per GPU: rfx_shard_init on this rank, handles exchanged through `dist` (any backend), peers mapped.
+    Afterwards ctx.count_sharded() / ctx.assemble_sharded() are collective calls over the ranks of `group`."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    row_lo, row_hi = row_ranges[rank]
-    oid_ranges = [(2 * a, 2 * b) for a, b in row_ranges]
-    lap = _Lap(torch, device, prof)
-    ctx.gs_begin(row_lo, row_hi)
-    lap("asm.begin")
-    p_alive, n_nodes = ctx.gs_alive()
-    alive = device_view(torch, p_alive, n_nodes, device)
-    _bcast_slices(torch, dist, alive, oid_ranges, group)
-    _sync(torch, device)
-    lap("asm.comm")
-    ctx.gs_left()
-    lap("asm.left")
-    _bcast_slices(torch, dist, alive, oid_ranges, group)
-    _sync(torch, device)
-    lap("asm.comm")
-    m, p_node, p_next, p_len = ctx.gs_link()
-    lap("asm.link")
-    u32 = torch.int32
-    trip = torch.empty((m, 3), dtype=u32, device=device)  # one gather for the three arrays
-    for j, p in enumerate((p_node, p_next, p_len)):
-        if m:
-            trip[:, j] = device_view(torch, p, m * 4, device).view(u32)
-    g_trip, sizes = gather_varlen(torch, dist, trip, group)
-    g_trip = g_trip.t().contiguous()
-    g_node, g_next, g_len = g_trip[0], g_trip[1], g_trip[2]
-    m_total, my_off = sum(sizes), sum(sizes[:rank])
-    _sync(torch, device)
-    lap("asm.comm")
-    nt, p_t, nh, p_h, has_cycle = ctx.gs_rank(g_node.data_ptr() if m_total else 0, g_next.data_ptr() if m_total else 0, g_len.data_ptr() if m_total else 0,
-                                              m_total, my_off)
-    lap("asm.rank")
-    tails = device_view(torch, p_t, nt * 12, device).view(u32) if nt else torch.empty(0, dtype=u32, device=device)
-    heads = device_view(torch, p_h, nh * 8, device).view(u32) if nh else torch.empty(0, dtype=u32, device=device)
-    # one gather for both lists and the per-rank scalars: a 6-word header [n_tails, n_heads, has_cycle, n_oriented,
-    # n_budget_junctions, n_cycles] (counts < 2^31 per rank), then the tuples
-    st0 = ctx.stats()
-    H = 6
-    hdr_local = torch.tensor([nt, nh, 1 if has_cycle else 0, st0["n_oriented"], st0["n_budget_junctions"], st0["n_cycles"]], dtype=u32, device=device)
-    g_blob, bsizes = gather_varlen(torch, dist, torch.cat([hdr_local, tails, heads]), group)
-    starts = [sum(bsizes[:r]) for r in range(world)]
-    hdr = g_blob[torch.tensor([starts[r] + j for r in range(world) for j in range(H)], device=device)].tolist()
-    if any(hdr[H * r + 2] for r in range(world)):
-        return ctx.assemble()  # closed paths are opened by the replicated path (rare; none in the BASELINE configs)
-    parts_t, parts_h = [], []
-    for r in range(world):
-        a, b, pos = hdr[H * r], hdr[H * r + 1], starts[r] + H
-        parts_t.append(g_blob[pos:pos + 3 * a])
-        parts_h.append(g_blob[pos + 3 * a:pos + 3 * a + 2 * b])
-    all_tails, all_heads = torch.cat(parts_t), torch.cat(parts_h)
-    sums = [sum(hdr[H * r + j] for r in range(world)) for j in (3, 4, 5)]
-    nt_all, nh_all = all_tails.numel() // 3, all_heads.numel() // 2
-    _sync(torch, device)
-    lap("asm.comm")
-    p_bases, n_bases = ctx.gs_contigs(all_tails.data_ptr() if nt_all else 0, nt_all, all_heads.data_ptr() if nh_all else 0, nh_all)
-    lap("asm.contigs")
-    st = ctx.stats()
-    if n_bases:
-        bases = device_view(torch, p_bases, n_bases, device)
-        dist.all_reduce(bases, op=dist.ReduceOp.MAX, group=group)
-    adm = torch.tensor([st["n_budget_admissible"]], dtype=torch.int64, device=device)
-    dist.all_reduce(adm, group=group)
-    _sync(torch, device)
-    ctx.gs_finish(sums[0], sums[1], int(adm.item()), sums[2])
-    lap("asm.comm")
-    return ctx.stats()
+    ctx.shard_init(rank, world, arena_bytes)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, ctx.shard_export(), group=group)
+    ctx.shard_connect(b"".join(blobs), world)
+
+
+class LocalRanks:
+    """Ranks as host threads of one process, one context each (contexts on different GPUs, or sharing one)."""
+
+    def __init__(self, ctxs, arena_bytes: int = 0):
+        self.ctxs = list(ctxs)
+        world = len(self.ctxs)
+        for r, c in enumerate(self.ctxs):
+            c.shard_init(r, world, arena_bytes)
+        blobs = b"".join(c.shard_export() for c in self.ctxs)
+        for c in self.ctxs:
+            c.shard_connect(blobs, world)
+
+    def run(self, fn):
+        """fn(rank, ctx) on every rank at once (the library calls release the GIL); returns the results in rank order."""
+        import threading
+        out, err = [None] * len(self.ctxs), [None] * len(self.ctxs)
+
+        def body(r):
+            try:
+                out[r] = fn(r, self.ctxs[r])
+            except BaseException as e:  # noqa: BLE001 -- re-raised below
+                err[r] = e
+
+        ts = [threading.Thread(target=body, args=(r,)) for r in range(len(self.ctxs))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        failed = [(r, e) for r, e in enumerate(err) if e is not None]
+        if len(failed) == 1:
+            raise failed[0][1]
+        if failed:  # a rank that fails leaves its peers waiting in a barrier until they time out: show every rank's story
+            raise RuntimeError("; ".join(f"rank {r}: {e}" for r, e in failed)) from failed[0][1]
+        return out

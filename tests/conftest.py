@@ -7,6 +7,13 @@ import sys
 import numpy as np
 import pytest
 
+# Ranks that share a device (tests/test_multi_gpu.py) must not share a hardware work queue: a rank waiting in a cross-GPU
+# barrier would hold up the kernels of the rank it is waiting for.  Read by the driver when CUDA starts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and no kernel may be loaded lazily while a peer rank on the SAME device spins in a barrier (loading a module can wait
+# for the device to drain): load every kernel when the library is loaded.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

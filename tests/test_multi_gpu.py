@@ -1,7 +1,11 @@
-"""NCCL path on real GPUs (needs >= 2): reads split across ranks, super-k-mer records exchanged with one all-to-all,
-shards counted locally, tables all-gathered, graph stages sharded by row owner (fork filters, links, chain walk and
-base gather on the own rows; alive bytes, splitter list and chain tuples exchanged) or, for comparison, replicated.
-The union of the shard tables and the contigs must equal the single-process oracle bit for bit."""
+"""Multi-rank runs over peer memory (include/reflexiv_cuda.h: rfx_shard_*): reads split across ranks, every rank scans
+its reads into slabs over all minimiser bins, the owner of a bin counts it straight out of the peers' slabs, the graph
+stages run on the own rows with neighbour probes, chain links and contig bases crossing ranks through peer pointers.
+The union of the shard tables, of the fork-filter survivors and of the contigs must equal the single-process oracle
+bit for bit.
+
+Two set-ups: ranks as host threads of one process SHARING device 0 (runs on a one-GPU box, which is what the round-end
+test box is), and one process per GPU with the arenas mapped through CUDA IPC (needs >= 2 GPUs)."""
 import os
 import sys
 
@@ -12,80 +16,193 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, k, rebin, graph, out_dir):
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    import torch.distributed as dist
-    import reflexiv_b200 as R
-    from reflexiv_b200 import sharded
-    from conftest import make_reads
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    device = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
-    txt = bytes(make_reads(31, 60_000, 12_000, read_len=150, err=0.005, frag=400))
-    # rank r takes the r-th slice of the records (cut on record boundaries)
+def _split(txt: bytes, world: int):
     cuts = [0]
     for r in range(1, world):
         cuts.append(txt.find(b"\n@r", len(txt) * r // world) + 1)
     cuts.append(len(txt))
-    mine = txt[cuts[rank]:cuts[rank + 1]]
+    return [txt[cuts[r]:cuts[r + 1]] for r in range(world)]
+
+
+def _rank_body(parts, bins, results):
+    def body(rank, ctx):
+        ctx.reset()
+        if parts[rank]:
+            ctx.push_fastq(parts[rank])
+        if bins:
+            ctx.shard_set_bins(bins)
+        st = ctx.count_sharded()
+        keys, cnt = ctx.counts()
+        st2 = ctx.assemble_sharded()
+        sh = ctx.shard_stats()
+        ori = ctx.oriented() if not sh["fell_back"] else None
+        results[rank] = dict(keys=keys, cnt=cnt, st=st, st2=st2, sh=sh, ori=ori, contigs=ctx.contigs())
+    return body
+
+
+def _check_against_oracle(orc, txt, k, cover, E, min_contig, results):
+    from reflexiv_b200.pipeline import keys_to_int
+    starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    c = orc.count_kmers(txt, starts, lens, k, 0, 0, cover, 10_000_000, 1)
+    f = orc.fork_filter(c["keys_hi"], c["keys_lo"], c["counts"], k, E)
+    a = orc.assemble(f["keys_hi"], f["keys_lo"], f["left"], f["right"], k, min_contig, orc.ASM_CANONICAL)
+    ref_ints = [(int(h) << 64) | int(l) for h, l in zip(c["keys_hi"], c["keys_lo"])]
+    got = {}
+    for res in results:
+        for key, n in zip(keys_to_int(res["keys"], k), res["cnt"].tolist()):
+            assert key not in got  # shard tables are disjoint
+            got[key] = n
+    assert sorted(got) == ref_ints
+    assert [got[x] for x in ref_ints] == c["counts"].tolist()
+    assert sum(r["st"]["n_rows"] for r in results) == len(ref_ints)
+    fell_back = any(r["sh"]["fell_back"] for r in results)
+    if not fell_back:
+        hi = np.concatenate([r["ori"][0] for r in results]); lo = np.concatenate([r["ori"][1] for r in results])
+        le = np.concatenate([r["ori"][2] for r in results]); ri = np.concatenate([r["ori"][3] for r in results])
+        order = np.lexsort((lo, hi))
+        assert np.array_equal(hi[order], f["keys_hi"]) and np.array_equal(lo[order], f["keys_lo"])
+        assert np.array_equal(le[order], f["left"]) and np.array_equal(ri[order], f["right"])
+    got_c = sorted((s, l, r) for res in results for s, l, r in res["contigs"])
+    exp_c = sorted(zip(a["contigs"], a["left"].tolist(), a["right"].tolist()))
+    assert got_c == exp_c
+    tot = lambda name: sum(r["st2"][name] for r in results)  # noqa: E731
+    assert tot("n_oriented") == len(f["left"])
+    assert (tot("n_budget_junctions"), tot("n_budget_admissible"), tot("n_cycles")) == (a["n_budget_junctions"], a["n_budget_admissible"], a["n_cycles"])
+    assert results[0]["sh"]["n_contigs_global"] == len(a["contigs"])
+    return a, fell_back
+
+
+def _run_threads(R, txt, world, k, cover, E, min_contig, bins=0, arena=1 << 30, device=0):
+    from reflexiv_b200 import sharded
+    ctxs = [R.ReflexivContext(R.DefaultParam(kmerSize=k, minKmerCoverage=cover, minErrorCoverage=E, minContig=min_contig), device=device) for _ in range(world)]
+    try:
+        grp = sharded.LocalRanks(ctxs, arena_bytes=arena)
+        results = [None] * world
+        grp.run(_rank_body(_split(txt, world), bins, results))
+        # a second run on the same contexts: arenas, barrier epochs and published blocks are reused
+        again = [None] * world
+        grp.run(_rank_body(_split(txt, world), bins, again))
+        from reflexiv_b200.pipeline import keys_to_int
+        for a, b in zip(results, again):  # row order inside a shard table is not fixed (rows leave the counting kernel through an atomic cursor)
+            assert dict(zip(keys_to_int(a["keys"], k), a["cnt"].tolist())) == dict(zip(keys_to_int(b["keys"], k), b["cnt"].tolist()))
+        assert sorted(x for r in results for x in r["contigs"]) == sorted(x for r in again for x in r["contigs"])
+    finally:
+        for c in ctxs:
+            c.close()
+    return results
+
+
+@pytest.fixture(scope="module")
+def R():
+    import reflexiv_b200 as R
+    return R
+
+
+def _genome_reads(k, err, seed=0, glen=30_000, pairs=6000, at=False):
+    from workload import synth
+    g = synth.genome(glen, 400 + k + seed)
+    if glen >= 13000:
+        g[12000:12800] = g[3000:3800]    # repeat: real forks, budget junctions
+    if at:
+        g[20000:20040] = np.frombuffer(b"AT" * 20, np.uint8)  # palindromic low-complexity stretch: closed paths
+    return bytes(synth.fastq(g, pairs, read_len=150, frag_len=400, error_rate=err, seed_reads=5 + seed, seed_errors=6 + seed))
+
+
+@pytest.mark.parametrize("world,k,cover,E,err,at", [(2, 31, 2, 8, 0.0, False), (3, 31, 2, 8, 0.01, False), (2, 61, 2, 8, 0.005, False), (4, 21, 1, 8, 0.02, False),
+                                                    (2, 31, 2, 0, 0.01, False), (1, 31, 2, 8, 0.01, False), (3, 41, 2, 8, 0.01, True), (2, 24, 1, 8, 0.01, True)])
+def test_ranks_sharing_one_device(R, orc, world, k, cover, E, err, at):
+    txt = _genome_reads(k, err, at=at)
+    results = _run_threads(R, txt, world, k, cover, E, 100)
+    a, fell_back = _check_against_oracle(orc, txt, k, cover, E, 100, results)
+    assert len(a["contigs"]) >= 2
+    assert fell_back == (a["n_cycles"] > 0 and world >= 1) or not at
+    if world > 1:
+        assert all(r["st"]["n_rows"] > 0 for r in results)
+        assert sum(r["sh"]["n_remote_probes"] for r in results) > 0  # some neighbours do live on another rank
+
+
+def test_docs_golden_contig_over_three_ranks(R, orc, example_text, golden):
+    """The reference's documented answer (`reflexiv run -kmer 31 -cover 3` on example/) from a sharded run."""
+    import hashlib
+    results = _run_threads(R, example_text, 3, 31, 3, 8, 500)
+    contigs = [s for r in results for s, _, _ in r["contigs"]]
+    assert sorted(len(c) for c in contigs) == [4558, 4558]
+    assert sum(c.startswith(golden["documented"]["prefix_1200"]) for c in contigs) == 1
+    cs = orc.canonical_contig_set(contigs)
+    assert [hashlib.sha256(x.encode()).hexdigest() for x in cs] == golden["oracle"]["contigs_cover3"]["canonical_sha256"]
+
+
+def test_closed_paths_and_empty_ranks(R, orc):
+    """A circular genome has no head: the ranks notice and rank 0 assembles the whole table.  Ranks without reads or rows take part."""
+    from workload import synth
+    g = synth.genome(2000, 9)
+    circ = bytes(g) + bytes(g[:200])
+    reads = [circ[i:i + 120] for i in range(0, 2000, 7)] * 2
+    txt = "".join(f"@r{i}\n{r.decode()}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)).encode()
+    results = _run_threads(R, txt, 2, 31, 2, 8, 50)
+    a, fell_back = _check_against_oracle(orc, txt, 31, 2, 8, 50, results)
+    assert fell_back and a["n_cycles"] >= 1
+    # one rank gets no reads at all
+    txt2 = _genome_reads(31, 0.0, glen=6000, pairs=600)
+    ctxs = [R.ReflexivContext(R.DefaultParam(kmerSize=31, minKmerCoverage=2, minContig=100), device=0) for _ in range(2)]
+    from reflexiv_b200 import sharded
+    try:
+        grp = sharded.LocalRanks(ctxs, arena_bytes=1 << 29)
+        results = [None] * 2
+        grp.run(_rank_body([txt2, b""], 0, results))
+    finally:
+        for c in ctxs:
+            c.close()
+    _check_against_oracle(orc, txt2, 31, 2, 8, 100, results)
+
+
+def test_dense_forks_across_ranks(R, orc):
+    """Budget walks (A9 clauses 3 / 4) that cross ranks: small k on a random genome puts fork winners within reach of each other."""
+    from workload import synth
+    g = synth.genome(20_000, 311)
+    txt = bytes(synth.fastq(g, 4000, read_len=100, frag_len=300, error_rate=0.0, seed_reads=3, seed_errors=4))
+    for k in (11, 13):
+        results = _run_threads(R, txt, 3, k, 1, 8, k)
+        a, _ = _check_against_oracle(orc, txt, k, 1, 8, k, results)
+        assert a["n_budget_admissible"] > 0
+
+
+# ---- one process per GPU, arenas mapped through CUDA IPC ------------------------------------------------------------------
+def _worker(rank, world, port, k, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pickle
+    import torch
+    import torch.distributed as dist
+    import reflexiv_b200 as R
+    from reflexiv_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    txt = _genome_reads(k, 0.005, glen=60_000, pairs=12_000)
     ctx = R.ReflexivContext(R.DefaultParam(kmerSize=k, minContig=200), device=rank)
-    ctx.push_fastq(mine)
-    inst = torch.tensor([ctx.stats()["n_instances"]], dtype=torch.int64, device=device)
-    dist.all_reduce(inst)
-    n_bins_total = sharded.choose_total_bins(int(inst.item()), world, 4096)
-    st = sharded.sharded_count(ctx, torch, dist, device, n_bins_total, rebin=rebin)
-    keys, cnt = ctx.counts()
-    np.save(os.path.join(out_dir, f"keys_{rank}.npy"), keys)
-    np.save(os.path.join(out_dir, f"cnt_{rank}.npy"), cnt)
-    gst = sharded.gather_tables(ctx, torch, dist, device)
-    if graph == "sharded":
-        st2 = sharded.sharded_assemble(ctx, torch, dist, device, gst["row_ranges"])
-    else:
-        st2 = ctx.assemble()
-    np.save(os.path.join(out_dir, f"asm_stats_{rank}.npy"), np.array([st2["n_oriented"], st2["n_contigs"], st2["n_contig_bases"], st2["n_budget_junctions"],
-                                                                      st2["n_budget_admissible"], st2["n_cycles"]], dtype=np.int64))
-    contigs = sorted(c for c, _, _ in ctx.contigs())
-    with open(os.path.join(out_dir, f"contigs_{rank}.txt"), "w") as f:
-        f.write("\n".join(contigs))
-    ctx.close()
+    sharded.connect(ctx, dist, arena_bytes=2 << 30)
+    results = [None] * world
+    _rank_body(_split(txt, world), 0, results)(rank, ctx)
+    with open(os.path.join(out_dir, f"res_{rank}.pkl"), "wb") as f:
+        pickle.dump(results[rank], f)
     dist.barrier()
+    ctx.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("k,rebin,graph", [(31, False, "sharded"), (61, False, "sharded"), (31, True, "replicated"), (21, False, "sharded")])
-def test_sharded_count_and_assembly_over_nccl(tmp_path, orc, k, rebin, graph):
+@pytest.mark.parametrize("k", [31, 61, 21])
+def test_one_process_per_gpu_over_ipc(tmp_path, orc, k):
+    import pickle
     import torch
     import torch.multiprocessing as mp
-    from conftest import make_reads
-    from reflexiv_b200.pipeline import keys_to_int
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(world, 4)
-    port = 29700 + os.getpid() % 1000 + k + (7 if rebin else 0)
-    mp.spawn(_worker, args=(world, port, k, rebin, graph, str(tmp_path)), nprocs=world, join=True)
-    txt = bytes(make_reads(31, 60_000, 12_000, read_len=150, err=0.005, frag=400))
-    ref = orc.run_pipeline(txt, k=k, cover=2, min_contig=200)
-    c = ref["counts"]
-    ref_ints = [(int(h) << 64) | int(l) for h, l in zip(c["keys_hi"], c["keys_lo"])]
-    got = {}
-    for r in range(world):
-        keys = np.load(tmp_path / f"keys_{r}.npy")
-        cnt = np.load(tmp_path / f"cnt_{r}.npy")
-        assert len(keys) > 0
-        for key, n in zip(keys_to_int(keys, k), cnt.tolist()):
-            assert key not in got          # shard tables are disjoint
-            got[key] = n
-    assert sorted(got) == ref_ints
-    assert [got[x] for x in ref_ints] == c["counts"].tolist()
-    expect = "\n".join(sorted(ref["asm"]["contigs"]))
-    for r in range(world):
-        assert (tmp_path / f"contigs_{r}.txt").read_text() == expect
-    stats = [np.load(tmp_path / f"asm_stats_{r}.npy").tolist() for r in range(world)]
-    assert all(s == stats[0] for s in stats)                                  # every rank reports the global numbers
-    a = ref["asm"]
-    assert stats[0][1] == len(a["contigs"]) and stats[0][2] == sum(len(x) for x in a["contigs"])
+    port = 29700 + os.getpid() % 1000 + k
+    mp.spawn(_worker, args=(world, port, k, str(tmp_path)), nprocs=world, join=True)
+    txt = _genome_reads(k, 0.005, glen=60_000, pairs=12_000)
+    results = [pickle.load(open(tmp_path / f"res_{r}.pkl", "rb")) for r in range(world)]
+    _check_against_oracle(orc, txt, k, 2, 8, 200, results)
