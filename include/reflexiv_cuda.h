@@ -219,6 +219,7 @@ int rfx_load_counts_device(rfx_ctx* ctx, const void* d_keys, const uint32_t* d_c
  * owns; rfx_counts_* work on it); after rfx_assemble_sharded it holds the contigs whose first k-mer it owns
  * (rfx_contigs_* work on them): the union over the ranks is the result of the single-GPU calls. */
 #define RFX_SHARD_HANDLE_BYTES 128
+#define RFX_SHARD_MAX_RANKS 8
 typedef struct {
     int32_t rank, world;
     uint64_t arena_bytes, arena_used;
@@ -239,6 +240,9 @@ int rfx_shard_set_bins(rfx_ctx* ctx, uint32_t n_bins_total);
 int rfx_count_sharded(rfx_ctx* ctx);
 int rfx_assemble_sharded(rfx_ctx* ctx);
 int rfx_shard_stats(rfx_ctx* ctx, rfx_shard_stats_t* out);
+
+/* number of CUDA devices the library can use (a launcher maps ranks to devices with it) */
+int rfx_device_count(int32_t* n_devices);
 
 const char* rfx_version(void);
 

@@ -94,6 +94,7 @@ SYMBOLS = {
     "rfx_count_sharded": (C.c_int, [_P]),
     "rfx_assemble_sharded": (C.c_int, [_P]),
     "rfx_shard_stats": (C.c_int, [_P, C.POINTER(RfxShardStats)]),
+    "rfx_device_count": (C.c_int, [C.POINTER(C.c_int32)]),
 }
 
 

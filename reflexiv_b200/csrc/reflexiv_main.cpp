@@ -297,6 +297,167 @@ static bool parse_counts(const char* data, size_t n, int k, int minc, int maxc, 
     return true;
 }
 
+// ---- outputs (one part file per rank, as Spark writes one per partition) -----------------------------------------------
+static bool write_csv_part(rfx_ctx* c, bool sorter, const std::string& target, int rank, bool gz) {
+    uint64_t nbytes = 0;
+    auto csv_fn = sorter ? rfx_sorted_csv : rfx_counts_csv;
+    if (csv_fn(c, nullptr, 0, &nbytes) != RFX_OK) return false;
+    std::vector<char> csv(nbytes ? nbytes : 1);
+    if (nbytes && csv_fn(c, csv.data(), nbytes, &nbytes) != RFX_OK) return false;
+    char name[128];
+    snprintf(name, sizeof(name), "/part-%05d-%08lx-%04x-%04x-%04x-%012lx-c000.csv", rank, (unsigned long)time(nullptr) & 0xffffffffUL, rand() & 0xffff,
+             rand() & 0xffff, rand() & 0xffff, ((unsigned long)rand() << 16 ^ (unsigned long)rand()) & 0xffffffffffffUL);
+    if (!write_out(target + name, csv.data(), nbytes, gz)) { fprintf(stderr, "reflexiv: cannot write %s\n", target.c_str()); return false; }
+    return true;
+}
+// DSKmerToContig + changeLine + TagRowContigID, ReflexivDSMain.java:743-794, 717-725; ids continue from id_base
+static bool write_contig_part(rfx_ctx* c, const std::string& target, int rank, uint64_t id_base, bool gz, uint64_t* n_out) {
+    uint64_t n = 0, total = 0;
+    if (rfx_contigs_size(c, &n, &total) != RFX_OK) return false;
+    std::vector<char> bases(total ? total : 1);
+    std::vector<uint64_t> offs(n + 1);
+    std::vector<int32_t> left(n ? n : 1), right(n ? n : 1);
+    if (rfx_contigs_copy(c, bases.data(), offs.data(), left.data(), right.data()) != RFX_OK) return false;
+    std::string out;
+    out.reserve(total + total / 100 + 64 * n + 16);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t len = offs[i + 1] - offs[i];
+        char head[96];
+        snprintf(head, sizeof(head), ">Contig-%llu-(%d,%d)-%llu\n", (unsigned long long)len, left[i], right[i], (unsigned long long)(id_base + i));
+        out += head;
+        for (uint64_t j = 0; j < len; j += 100) {
+            out.append(bases.data() + offs[i] + j, (size_t)std::min<uint64_t>(100, len - j));
+            out.push_back('\n');
+        }
+    }
+    char name[32];
+    snprintf(name, sizeof(name), "/part-%05d", rank);
+    if (!write_out(target + name, out.data(), out.size(), gz)) { fprintf(stderr, "reflexiv: cannot write %s\n", target.c_str()); return false; }
+    if (n_out) *n_out = n;
+    return true;
+}
+static void clear_dir(const std::string& target) {  // SaveMode.Overwrite
+    if (DIR* d = opendir(target.c_str())) {
+        while (dirent* e = readdir(d))
+            if (e->d_name[0] != '.' || strlen(e->d_name) > 2) remove((target + "/" + e->d_name).c_str());
+        closedir(d);
+    }
+}
+
+// ---- --gpus N: one context per rank, ranks are host threads; the library's sharded calls do the exchange over peer memory ----
+// Where a 4-line FASTQ text may be cut: in front of a line that starts with '@' whose second-next line starts with '+'
+// (a quality line may start with '@' too, but then the second-next line is a sequence).
+static size_t record_start_near(const char* d, size_t n, size_t pos) {
+    if (pos >= n) return n;
+    const size_t limit = std::min(n, pos + ((size_t)4 << 20));
+    const char* nl = static_cast<const char*>(memchr(d + pos, '\n', n - pos));
+    while (nl && (size_t)(nl - d) + 1 < limit) {
+        const size_t l0 = (size_t)(nl - d) + 1;
+        const char* n1 = static_cast<const char*>(memchr(d + l0, '\n', n - l0));
+        const char* n2 = n1 ? static_cast<const char*>(memchr(n1 + 1, '\n', n - (size_t)(n1 + 1 - d))) : nullptr;
+        if (d[l0] == '@' && n2 && (size_t)(n1 + 1 - d) < n && n1[1] != '+' && n2[1] == '+') return l0;
+        nl = n1;
+    }
+    return n;  // no safe cut nearby: the rest stays with the previous rank
+}
+struct Rank {
+    rfx_ctx* c = nullptr;
+    std::vector<std::pair<const char*, size_t>> parts;
+    int rc = RFX_OK;
+    const char* what = "";
+};
+static int run_sharded(int n_gpus, rfx_params p, bool counter, const std::string& pattern, const std::string& outdir, const std::string& target, bool gz) {
+    int32_t n_dev = 0;
+    if (rfx_device_count(&n_dev) != RFX_OK || n_dev < 1) { fprintf(stderr, "reflexiv: no CUDA device\n"); return 1; }
+    std::vector<Rank> R(n_gpus);
+    const int dev0 = p.device;
+    for (int r = 0; r < n_gpus; r++) {
+        p.device = (dev0 + r) % n_dev;  // fewer devices than ranks: ranks share devices (how a one-GPU box runs this path)
+        if (rfx_create(&R[r].c, &p) != RFX_OK) { fprintf(stderr, "reflexiv: rfx_create (rank %d): %s\n", r, rfx_last_error(nullptr)); return 1; }
+    }
+    auto destroy_all = [&] { for (auto& k : R) if (k.c) rfx_destroy(k.c); };
+    uint64_t arena = getenv("REFLEXIV_ARENA_MB") ? (uint64_t)atoll(getenv("REFLEXIV_ARENA_MB")) << 20 : 0;
+    if (!arena && n_dev < n_gpus) { fprintf(stderr, "reflexiv: %d ranks on %d device(s): set REFLEXIV_ARENA_MB (device memory per rank)\n", n_gpus, n_dev); destroy_all(); return 1; }
+    std::vector<unsigned char> blobs((size_t)n_gpus * RFX_SHARD_HANDLE_BYTES);
+    for (int r = 0; r < n_gpus; r++) {
+        if (rfx_shard_init(R[r].c, r, n_gpus, arena) != RFX_OK || rfx_shard_export(R[r].c, blobs.data() + (size_t)r * RFX_SHARD_HANDLE_BYTES) != RFX_OK) {
+            fprintf(stderr, "reflexiv: rfx_shard_init (rank %d): %s\n", r, rfx_last_error(R[r].c)); destroy_all(); return 1;
+        }
+    }
+    for (int r = 0; r < n_gpus; r++)
+        if (rfx_shard_connect(R[r].c, blobs.data(), n_gpus) != RFX_OK) { fprintf(stderr, "reflexiv: rfx_shard_connect (rank %d): %s\n", r, rfx_last_error(R[r].c)); destroy_all(); return 1; }
+    // input: every file is cut into n_gpus runs of whole records (`run`) or whole lines (`counter`); rank r takes the r-th run of every file
+    bool push_ok = true;
+    const bool read_ok = stream_inputs(pattern, [&](const char* data, size_t n) {
+        std::vector<size_t> cut(n_gpus + 1, n);
+        cut[0] = 0;
+        for (int r = 1; r < n_gpus; r++) {
+            size_t want = n / n_gpus * r;
+            if (want < cut[r - 1]) want = cut[r - 1];
+            if (counter) {
+                const char* nl = want < n ? static_cast<const char*>(memchr(data + want, '\n', n - want)) : nullptr;
+                cut[r] = nl ? (size_t)(nl - data) + 1 : n;
+            } else cut[r] = record_start_near(data, n, want);
+        }
+        // the pushes of one file run concurrently, one thread per rank, before the reader hands out the next file
+        std::vector<std::thread> th;
+        for (int r = 0; r < n_gpus; r++)
+            th.emplace_back([&, r] {
+                if (cut[r + 1] > cut[r] && R[r].rc == RFX_OK) {
+                    R[r].rc = rfx_push_fastq(R[r].c, reinterpret_cast<const uint8_t*>(data + cut[r]), cut[r + 1] - cut[r]);
+                    R[r].what = "rfx_push_fastq";
+                }
+            });
+        for (auto& t : th) t.join();
+        for (auto& k : R) push_ok = push_ok && k.rc == RFX_OK;
+        return push_ok;
+    });
+    if (!read_ok || !push_ok) {
+        for (int r = 0; r < n_gpus; r++) if (R[r].rc != RFX_OK) fprintf(stderr, "reflexiv: %s (rank %d): %s\n", R[r].what, r, rfx_last_error(R[r].c));
+        destroy_all();
+        return 1;
+    }
+    // collective stages, one thread per rank
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_gpus; r++)
+        th.emplace_back([&, r] {
+            Rank& k = R[r];
+            k.what = "rfx_count_sharded";
+            if ((k.rc = rfx_count_sharded(k.c)) != RFX_OK) return;
+            if (!counter) { k.what = "rfx_assemble_sharded"; k.rc = rfx_assemble_sharded(k.c); }
+        });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < n_gpus; r++)
+        if (R[r].rc != RFX_OK) { fprintf(stderr, "reflexiv: %s (rank %d): %s\n", R[r].what, r, rfx_last_error(R[r].c)); push_ok = false; }
+    if (!push_ok) { destroy_all(); return 1; }
+    mkdir(outdir.c_str(), 0755);
+    mkdir(target.c_str(), 0755);
+    if (counter) clear_dir(target);
+    uint64_t id_base = 0;
+    rfx_stats_t tot;
+    memset(&tot, 0, sizeof(tot));
+    for (int r = 0; r < n_gpus; r++) {
+        uint64_t n = 0;
+        const bool ok = counter ? write_csv_part(R[r].c, false, target, r, gz) : write_contig_part(R[r].c, target, r, id_base, false, &n);
+        if (!ok) { fprintf(stderr, "reflexiv: writing the output of rank %d failed: %s\n", r, rfx_last_error(R[r].c)); destroy_all(); return 1; }
+        id_base += n;
+        rfx_stats_t s;
+        rfx_stats(R[r].c, &s);
+        tot.n_reads += s.n_reads; tot.n_instances += s.n_instances; tot.n_distinct += s.n_distinct; tot.n_rows += s.n_rows; tot.n_contigs += s.n_contigs;
+    }
+    FILE* okf = fopen((target + "/_SUCCESS").c_str(), "wb");
+    if (okf) fclose(okf);
+    rfx_shard_stats_t sh;
+    rfx_shard_stats(R[0].c, &sh);
+    char msg[512];
+    snprintf(msg, sizeof(msg), "done on %d ranks: %llu reads, %llu k-mers, %llu distinct, %llu rows, %llu contigs; rank 0: %llu neighbour probes answered by a peer, %.2f ms in barriers",
+             n_gpus, (unsigned long long)tot.n_reads, (unsigned long long)tot.n_instances, (unsigned long long)tot.n_distinct, (unsigned long long)tot.n_rows,
+             (unsigned long long)tot.n_contigs, (unsigned long long)sh.n_remote_probes, sh.ms_comm);
+    info(msg);
+    destroy_all();
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 2) { fputs(HELP, stdout); return 1; }
     const std::string cmd = argv[1];
@@ -309,11 +470,17 @@ int main(int argc, char** argv) {
     }
     const bool counter = cmd == "counter", sorter = cmd == "sort";
     // bin/reflexiv:209-238: `--x [value]` belongs to spark-submit, `-x [value]` to Reflexiv
+    // ... of which this driver reads one: `--gpus N` (what `--master local[N]` is to the reference; also REFLEXIV_GPUS)
     std::vector<std::string> own;
+    int n_gpus = getenv("REFLEXIV_GPUS") ? atoi(getenv("REFLEXIV_GPUS")) : 1;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         const bool next_is_value = i + 1 < argc && argv[i + 1][0] != '-';
-        if (a.rfind("--", 0) == 0) { if (next_is_value) i++; continue; }
+        if (a.rfind("--", 0) == 0) {
+            if (a == "--gpus" && next_is_value) n_gpus = atoi(argv[i + 1]);
+            if (next_is_value) i++;
+            continue;
+        }
         if (a[0] == '-') { own.push_back(a); if (next_is_value) own.push_back(argv[++i]); }
     }
     info(counter ? "Reflexiv counter initiating ... " : sorter ? "Reflexiv k-mer sorting initiating ... " : "Reflexiv main initiating ... ");
@@ -389,6 +556,12 @@ int main(int argc, char** argv) {
         return 1;
     }
 
+    if (n_gpus > 1 && (from_kmer || sorter)) { fprintf(stderr, "reflexiv: --gpus applies to runs from reads (-fastq); this one starts from a count table\n"); n_gpus = 1; }
+    if (n_gpus > RFX_SHARD_MAX_RANKS) { fprintf(stderr, "reflexiv: --gpus %d: at most %d\n", n_gpus, RFX_SHARD_MAX_RANKS); return 1; }
+    if (n_gpus > 1) {
+        info("Initiating CUDA contexts ...");
+        return run_sharded(n_gpus, p, counter, v["fastq"], outdir, target, gz);
+    }
     info("Initiating CUDA context ...");
     rfx_ctx* c = nullptr;
     if (rfx_create(&c, &p) != RFX_OK) return fail(nullptr, "rfx_create");
@@ -420,45 +593,15 @@ int main(int argc, char** argv) {
     }
     mkdir(outdir.c_str(), 0755);
     if (counter || sorter) {
-        uint64_t nbytes = 0;
         if (sorter && rfx_sort_kmers(c, p.min_error_coverage, min_repeat_fold, klist.back() /* param.kmerListInt[last], :445 */) != RFX_OK)
             return fail(c, "rfx_sort_kmers");
-        auto csv_fn = sorter ? rfx_sorted_csv : rfx_counts_csv;
-        if (csv_fn(c, nullptr, 0, &nbytes) != RFX_OK) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
-        std::vector<char> csv(nbytes ? nbytes : 1);
-        if (nbytes && csv_fn(c, csv.data(), nbytes, &nbytes) != RFX_OK) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
         mkdir(target.c_str(), 0755);
-        if (DIR* d = opendir(target.c_str())) {  // SaveMode.Overwrite
-            while (dirent* e = readdir(d))
-                if (e->d_name[0] != '.' || strlen(e->d_name) > 2) remove((target + "/" + e->d_name).c_str());
-            closedir(d);
-        }
-        char name[128];
-        snprintf(name, sizeof(name), "/part-00000-%08lx-%04x-%04x-%04x-%012lx-c000.csv", (unsigned long)time(nullptr) & 0xffffffffUL, rand() & 0xffff,
-                 rand() & 0xffff, rand() & 0xffff, ((unsigned long)rand() << 16 ^ (unsigned long)rand()) & 0xffffffffffffUL);
-        if (!write_out(target + name, csv.data(), nbytes, gz)) { fprintf(stderr, "reflexiv: cannot write %s\n", target.c_str()); rfx_destroy(c); return 1; }
+        clear_dir(target);
+        if (!write_csv_part(c, sorter, target, 0, gz)) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
     } else {
         if (rfx_assemble(c) != RFX_OK) return fail(c, "rfx_assemble");
-        uint64_t n = 0, total = 0;
-        if (rfx_contigs_size(c, &n, &total) != RFX_OK) return fail(c, "rfx_contigs_size");
-        std::vector<char> bases(total ? total : 1);
-        std::vector<uint64_t> offs(n + 1);
-        std::vector<int32_t> left(n ? n : 1), right(n ? n : 1);
-        if (rfx_contigs_copy(c, bases.data(), offs.data(), left.data(), right.data()) != RFX_OK) return fail(c, "rfx_contigs_copy");
-        std::string out;
-        out.reserve(total + total / 100 + 64 * n + 16);
-        for (uint64_t i = 0; i < n; i++) {  // DSKmerToContig + changeLine + TagRowContigID, ReflexivDSMain.java:743-794, 717-725
-            const uint64_t len = offs[i + 1] - offs[i];
-            char head[96];
-            snprintf(head, sizeof(head), ">Contig-%llu-(%d,%d)-%llu\n", (unsigned long long)len, left[i], right[i], (unsigned long long)i);
-            out += head;
-            for (uint64_t j = 0; j < len; j += 100) {
-                out.append(bases.data() + offs[i] + j, (size_t)std::min<uint64_t>(100, len - j));
-                out.push_back('\n');
-            }
-        }
         mkdir(target.c_str(), 0755);
-        if (!write_out(target + "/part-00000", out.data(), out.size(), gz && from_kmer)) { fprintf(stderr, "reflexiv: cannot write %s\n", target.c_str()); rfx_destroy(c); return 1; }
+        if (!write_contig_part(c, target, 0, 0, gz && from_kmer, nullptr)) return fail(c, "rfx_contigs_copy");
     }
     FILE* ok = fopen((target + "/_SUCCESS").c_str(), "wb");
     if (ok) fclose(ok);

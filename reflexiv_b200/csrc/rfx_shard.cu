@@ -360,6 +360,14 @@ int rfx_assemble_sharded(rfx_ctx* c) {
     return stage_assemble_sharded(c);
 }
 
+int rfx_device_count(int32_t* n_devices) {
+    if (!n_devices) return RFX_E_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); *n_devices = 0; return RFX_E_CUDA; }
+    *n_devices = n;
+    return RFX_OK;
+}
+
 int rfx_shard_stats(rfx_ctx* c, rfx_shard_stats_t* out) {
     if (!c || !out) return RFX_E_INVALID;
     memset(out, 0, sizeof(*out));

@@ -206,3 +206,33 @@ def test_one_process_per_gpu_over_ipc(tmp_path, orc, k):
     txt = _genome_reads(k, 0.005, glen=60_000, pairs=12_000)
     results = [pickle.load(open(tmp_path / f"res_{r}.pkl", "rb")) for r in range(world)]
     _check_against_oracle(orc, txt, k, 2, 8, 200, results)
+
+
+def test_reflexiv_binary_with_gpus_option(tmp_path, golden):
+    """`reflexiv run --gpus 3` / `reflexiv counter --gpus 2` (csrc/reflexiv_main.cpp: run_sharded): ranks are host threads of the
+    driver, every input file is cut into runs of whole records, one part file per rank.  On a box with fewer devices than
+    ranks the ranks share devices (REFLEXIV_ARENA_MB = device memory per rank)."""
+    import gzip
+    import hashlib
+    import subprocess
+    from conftest import GOLDEN
+    exe = os.path.join(ROOT, "reflexiv_b200", "reflexiv")
+    env = dict(os.environ, REFLEXIV_ARENA_MB="768", CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    out = tmp_path / "result"
+    r = subprocess.run([exe, "run", "--gpus", "3", "--driver-memory", "3G", "-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(out), "-kmer", "31",
+                        "-cover", "3"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr + r.stdout
+    assert (out / "_SUCCESS").exists()
+    recs = "".join((out / f).read_text() for f in sorted(os.listdir(out)) if f.startswith("part-")).strip().split(">")[1:]
+    heads = [x.split("\n")[0] for x in recs]
+    assert sorted(heads) == ["Contig-4558-(-4,-4)-0", "Contig-4558-(-4,-4)-1"]
+    seqs = ["".join(x.strip().split("\n")[1:]) for x in recs]
+    assert sum(s.startswith(golden["documented"]["prefix_1200"]) for s in seqs) == 1
+    cout = tmp_path / "c"
+    r = subprocess.run([exe, "counter", "--gpus", "2", "-fastq", os.path.join(GOLDEN, "paired_dat*.fq.gz"), "-outfile", str(cout), "-kmer", "31", "-cover", "2", "-gzip"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr + r.stdout
+    parts = sorted(f for f in os.listdir(cout / "Count_31") if f.startswith("part-"))
+    assert len(parts) == 2
+    rows = sorted(x for f in parts for x in gzip.open(cout / "Count_31" / f).read().decode().splitlines())
+    assert hashlib.sha256(("\n".join(rows) + "\n").encode()).hexdigest() == golden["oracle"]["count_ge2"]["sha256_sorted_csv"]
