@@ -171,10 +171,12 @@ struct Ctx {
     bool peer_ipc[RFX_MAX_RANKS] = {false};         // opened through cudaIpcOpenMemHandle
     unsigned long long sh_epoch = 0;                // barriers passed
     unsigned long long sh_exchanges = 0;            // value exchanges made (parity picks the published block)
+    unsigned long long* d_pub = nullptr;            // device staging: everybody's published block, gathered by one kernel
     unsigned long long* h_pub = nullptr;            // pinned: own published values + everybody's after an exchange
     uint32_t sh_bins = 0;                           // total bin count of sharded counting (0: agreed on per run)
     uint32_t sh_bins_run = 0;                       // ... the one in force for the slab scan (rfx_partition.cu: slab_begin)
     uint64_t sh_inst_global = 0;                    // k-mer instances extracted by all ranks
+    uint64_t sh_rows_global = 0;                    // rows of all shard tables (known to every rank after rfx_count_sharded)
     cudaEvent_t ev_comm[2] = {nullptr, nullptr};
     float ms_comm = 0;                              // cross-GPU barriers + value exchanges of the last sharded calls
     void* hbar = nullptr;                           // host-side barrier of ranks that share a device inside one process
@@ -216,7 +218,8 @@ enum {
     DS_XBAR_ERR = 30,     // a cross-GPU barrier timed out (rfx_shard.cu)
     DS_NL2 = 32,          // level-2 splitters of the sharded chain ranking (rfx_shard_graph.cuh)
     DS_REMOTE = 33,       // neighbour probes answered from a peer's index
-    DS_SG_CYCLE = 34,     // a closed path was seen
+    DS_SG_CYCLE = 34,
+    DS_WORK = 35,         // 3 slots: nodes the first pass of a sharded K5 kernel put off (their probe goes to a peer)     // a closed path was seen
     DS_NSLOTS = 40
 };
 

@@ -99,6 +99,14 @@ static bool host_barrier_wait(HostBarrier* hb) {
     return true;
 }
 
+// everybody's published slots [first, first + n) -> one local block, so that the host needs ONE device-to-host copy
+__global__ void gather_pub_kernel(PeerBases P, int par, int first, int n, unsigned long long* __restrict__ out) {
+    for (int i = threadIdx.x; i < P.n * n; i += blockDim.x) {
+        const int r = i / n, s = i % n;
+        out[(size_t)r * RFX_PUB_SLOTS + first + s] = *reinterpret_cast<const volatile unsigned long long*>(&reinterpret_cast<const ShardCtl*>(P.base[r])->pub[par][first + s]);
+    }
+}
+
 PeerBases peer_bases(const Ctx* c) {
     PeerBases P;
     P.n = c->sh_world; P.me = c->sh_rank;
@@ -142,10 +150,9 @@ int shard_exchange(Ctx* c, int first, int n, const unsigned long long* mine, uns
     for (int i = 0; i < n_dev; i++)
         RFX_CUDA(c, cudaMemcpyAsync(&own->pub[par][dev_first + i], c->dstat.as<unsigned long long>() + dev_slots[i], sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
     RFX_TRY(shard_barrier(c));
-    for (int r = 0; r < c->sh_world; r++) {
-        const ShardCtl* ctl = reinterpret_cast<const ShardCtl*>(c->peer_base[r]);
-        RFX_CUDA(c, cudaMemcpyAsync(h + (size_t)(r + 1) * RFX_PUB_SLOTS + first, &ctl->pub[par][first], (size_t)n * sizeof(unsigned long long), cudaMemcpyDefault, c->stream));
-    }
+    gather_pub_kernel<<<1, 256, 0, c->stream>>>(peer_bases(c), par, first, n, c->d_pub);
+    c->launches++;
+    RFX_CUDA(c, cudaMemcpyAsync(h + RFX_PUB_SLOTS, c->d_pub, (size_t)c->sh_world * RFX_PUB_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     cudaEventRecord(c->ev_comm[1], c->stream);
     RFX_TRY(shard_check(c, "shard exchange"));
     float ms = 0;
@@ -228,14 +235,11 @@ int stage_count_sharded(Ctx* c) {
     }
     c->sh_inst_global = inst_global;
     RFX_TRY(stage_count_segments(c, S, n_seg, bps, false));
-    // 5. nobody may touch its slabs again before every rank has counted
-    cudaEventRecord(c->ev_comm[0], c->stream);
-    RFX_TRY(shard_barrier(c));
-    cudaEventRecord(c->ev_comm[1], c->stream);
-    RFX_TRY(shard_check(c, "sharded counting"));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev_comm[0], c->ev_comm[1]);
-    c->ms_comm += ms;
+    // 5. nobody may touch its slabs again before every rank has counted; the same exchange tells everybody the global row count
+    mine[0] = c->n_rows;
+    RFX_TRY(shard_exchange(c, PUB_INSTANCES, 1, mine, all));
+    c->sh_rows_global = 0;
+    for (int r = 0; r < world; r++) c->sh_rows_global += all[(size_t)r * RFX_PUB_SLOTS + PUB_INSTANCES];
     c->n_bins = B;
     return RFX_OK;
 }
@@ -275,6 +279,8 @@ int rfx_shard_init(rfx_ctx* c, int32_t rank, int32_t world, uint64_t arena_bytes
     c->arena = (uint8_t*)p;
     c->arena_bytes = arena_bytes;
     c->arena_used = (sizeof(ShardCtl) + 255) & ~(size_t)255;
+    c->d_pub = reinterpret_cast<unsigned long long*>(c->arena + c->arena_used);  // staging of everybody's published block
+    c->arena_used += ((size_t)RFX_MAX_RANKS * RFX_PUB_SLOTS * sizeof(unsigned long long) + 255) & ~(size_t)255;
     c->sh_rank = rank; c->sh_world = world; c->sh_epoch = 0; c->sh_exchanges = 0;
     for (int r = 0; r < RFX_MAX_RANKS; r++) { c->peer_base[r] = nullptr; c->peer_ipc[r] = false; }
     return RFX_OK;

@@ -26,6 +26,10 @@
 //              and rank 0 pulls the shard tables and runs the single-GPU stages on the whole table (rare).
 #pragma once
 
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "rfx_shard.h"
 
 namespace rfx {
@@ -40,7 +44,7 @@ struct SGPeer {
     const void* keys;
     const uint32_t* counts;
     const uint32_t* ht;
-    const uint32_t* bloom;  // the LOCAL copy of that rank's presence bits
+    const uint32_t* filter; // that rank's presence bits in ITS memory (only used to pull its slice)
     uint8_t* alive;
     int32_t *lflag, *rflag, *eff_l, *eff_r;
     uint32_t *succ, *pred, *spl_id;
@@ -55,13 +59,21 @@ struct SGPeer {
     uint32_t* ctg_idx;
     uint64_t* ctg_off;
     char* ctg_bases;
-    uint64_t bloom_mask;
     uint32_t ht_cap, pad;
 };
 struct SGView {
     SGPeer p[RFX_MAX_RANKS];
     int me, world, k, m;
     uint32_t B, bps;
+    // Presence bits of ALL ranks' rows, one region of 2^rb_shift bits per minimiser bin (>= 16 bits per row on average), the
+    // whole array replicated on every rank (a rank fills the regions of its own bins, the others pull them: 2 B per row).
+    // A node's neighbours mostly share its minimiser -- its bin -- and rows sit in the table grouped by bin, so the probes of
+    // neighbouring threads fall into the same few hundred bytes; the array is streamed through once instead of being hit at
+    // random (at 8 GPUs it is 8 x the size of one rank's rows and no longer fits the L2).
+    const uint32_t* filter;
+    int rb_shift;
+    uint64_t inv_bps;  // ceil(2^64 / bps): bin -> owner without a division
+    __device__ __forceinline__ int owner_of_bin(uint32_t bin) const { return bps == 1u ? (int)bin : (int)__umul64hi((uint64_t)bin, inv_bps); }
 };
 
 // slots of the published block (ShardCtl::pub, from PUB_GRAPH on): arena offsets first, then values
@@ -74,24 +86,32 @@ enum {
 static_assert(PUB_GRAPH + GP_END <= RFX_PUB_SLOTS, "published block too small");
 
 struct GShard {
-    DevBuf bloom_all, l1_nl, l1_loc, l1_fin, l1_dst, l2_of, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
-    const uint32_t* bloom_local[RFX_MAX_RANKS] = {nullptr};  // local copies of the peers' presence bits (this run)
+    DevBuf rmin, work, l1_nl, l1_loc, l1_fin, l1_dst, l2_of, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
     uint64_t n_remote = 0, n_l1 = 0, n_l2 = 0, n_rows_global = 0, n_oriented_global = 0, n_contigs_global = 0, n_bases_global = 0;
-    int fell_back = 0;
+    int fell_back = 0, rb_shift = 6;
 };
 
 // ---- neighbour lookup ------------------------------------------------------------------------------------------------
-// gid of the oriented k-mer Z (minimiser hash hmin), NONE32 if its canonical form is in no rank's table
-template <class KT> __device__ __forceinline__ uint32_t sg_find(const SGView& V, KT Z, uint32_t hmin, uint32_t* cnt, unsigned long long* dstat) {
+// gid of the oriented k-mer Z (minimiser hash hmin), NONE32 if its canonical form is in no rank's table.
+// DEFER: the first pass of a K5 kernel does not walk a peer's index -- a warp with one such lane would stall all its lanes
+// for three trips over NVLink -- but sets `deferred`; the node goes onto a work list and a second, small launch in which EVERY
+// lane is a remote probe takes care of the list (measured at 2 GPUs: link pass 1.32 -> see profiles/).
+template <class KT, bool DEFER>
+__device__ __forceinline__ uint32_t sg_find(const SGView& V, KT Z, uint32_t h_new, uint32_t h_side, uint32_t bin_side, uint32_t* cnt, uint32_t& n_remote, bool& deferred) {
     const KT zc = revcomp(Z, V.k);
     const bool fwd = !(zc < Z);
     const KT canon = fwd ? Z : zc;
-    const int r = (int)(bin_of_minimizer(hmin, V.B) / V.bps);
-    const SGPeer& P = V.p[r];
+    // Z = the shared (k-1)-mer (minimum h_side over its m-mers, bin bin_side) plus one new m-mer (hash h_new)
+    const uint32_t bin = h_new < h_side ? bin_of_minimizer(h_new, V.B) : bin_side;
     const uint64_t kh = key_hash(canon);
-    const uint64_t bit = (kh >> 13) & P.bloom_mask;
-    if (!((P.bloom[bit >> 5] >> (bit & 31u)) & 1u)) return NONE32;
-    if (r != V.me) atomicAdd(&dstat[DS_REMOTE], 1ull);
+    const uint64_t bit = ((uint64_t)bin << V.rb_shift) + ((kh >> 13) & ((1ull << V.rb_shift) - 1ull));
+    if (!((V.filter[bit >> 5] >> (bit & 31u)) & 1u)) return NONE32;
+    const int r = V.owner_of_bin(bin);
+    if (r != V.me) {
+        if (DEFER) { deferred = true; return NONE32; }
+        n_remote++;
+    }
+    const SGPeer& P = V.p[r];
     const KT* keys = reinterpret_cast<const KT*>(P.keys);
     const uint32_t cap = P.ht_cap;
     uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(kh >> 20) * cap) >> 32);
@@ -105,122 +125,218 @@ template <class KT> __device__ __forceinline__ uint32_t sg_find(const SGView& V,
     *cnt = P.counts[v];
     return gid_make(r, 2u * v + (fwd ? 0u : 1u));
 }
+// neighbour probes answered from a peer's index: one atomic per warp, at the end of the kernel
+__device__ __forceinline__ void sg_flush_remote(uint32_t n_remote, unsigned long long* dstat) {
+    __syncwarp();
+    const uint32_t t = __reduce_add_sync(0xffffffffu, n_remote);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&dstat[DS_REMOTE], (unsigned long long)t);
+}
+// the two passes of a K5 kernel: pass 1 (DEFER) runs over the own nodes and lists the ones it puts off, pass 2 runs over that list
+struct SGWork {
+    uint32_t* list;               // pass 1 appends, pass 2 reads
+    unsigned long long* counter;  // entries in the list (device)
+};
+template <bool DEFER> __device__ __forceinline__ uint64_t sg_work_count(uint64_t n, const SGWork& W) { return DEFER ? n : (uint64_t)*W.counter; }
+// Index of a new entry for every thread that wants one, ~0 for the others: ONE global atomic per block and call (a quarter
+// of a million warps bumping the same counter cost more than the kernel around them).  Every thread of the block must call.
+__device__ __forceinline__ unsigned long long sg_block_reserve(bool want, unsigned long long* counter) {
+    __shared__ uint32_t s_count;
+    __shared__ unsigned long long s_base;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t m = __ballot_sync(0xffffffffu, want);
+    uint32_t wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&s_count, (uint32_t)__popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_count) s_base = atomicAdd(counter, (unsigned long long)s_count);
+    __syncthreads();
+    return want ? s_base + wbase + __popc(m & ((1u << lane) - 1u)) : ~0ull;
+}
+__device__ __forceinline__ void sg_work_push(const SGWork& W, bool put_off, uint32_t oid) {
+    const unsigned long long at = sg_block_reserve(put_off, W.counter);
+    if (put_off) W.list[at] = oid;
+}
+
 template <class KT> __device__ __forceinline__ KT sg_oriented(const SGView& V, uint32_t g) {
     const uint32_t l = gid_loc(g);
     const KT key = reinterpret_cast<const KT*>(V.p[gid_rank(g)].keys)[l >> 1];
     return (l & 1u) ? revcomp(key, V.k) : key;
 }
 
-// rows must sit on the rank that owns their minimiser bin, or neighbours would look for them elsewhere
-template <class KT> __global__ void sg_check_owner_kernel(const __grid_constant__ SGView V, uint64_t n_rows, unsigned long long* dstat) {
-    const KT* keys = reinterpret_cast<const KT*>(V.p[V.me].keys);
+// Per row, once: the minima of the m-mer hashes inside the first / the last k-1 bases of the canonical k-mer with their bins
+// (the reverse strand sees the same two swapped: m-mer hashes are strand symmetric).  A neighbour's minimiser -- hence its bin
+// and owner -- is then min(one new m-mer, one of the two).  The row's own bin must belong to this rank, or neighbours would
+// look for it elsewhere (checked); its presence bit is set in that bin's region.
+template <class KT>
+__global__ void sg_row_minima_kernel(const KT* __restrict__ keys, uint64_t n_rows, int k, int m, uint32_t B, uint32_t bin_lo, uint32_t bin_hi, int rb_shift,
+                                     uint4* __restrict__ rmin, uint32_t* filter, unsigned long long* dstat) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+        const KT key = keys[r];
         uint32_t a, b;
-        kmer_minima<KT>(keys[r], V.k, V.m, a, b);
+        kmer_minima<KT>(key, k, m, a, b);
+        rmin[r] = make_uint4(a, b, bin_of_minimizer(a, B), bin_of_minimizer(b, B));
         uint32_t h = a < b ? a : b;
-        if (V.m == V.k) h = mm_hash_m((uint32_t)keys[r], V.m);  // one m-mer, in neither the prefix nor the suffix part
-        if ((int)(bin_of_minimizer(h, V.B) / V.bps) != V.me) atomicExch(&dstat[DS_GRAPH_ERR], 3ull);
+        if (m == k) h = mm_hash_m((uint32_t)key, m);  // one m-mer, in neither the prefix nor the suffix part
+        const uint32_t bin = bin_of_minimizer(h, B);
+        if (bin < bin_lo || bin >= bin_hi) atomicExch(&dstat[DS_GRAPH_ERR], 3ull);
+        const uint64_t bit = ((uint64_t)bin << rb_shift) + ((key_hash(key) >> 13) & ((1ull << rb_shift) - 1ull));
+        atomicOr(&filter[bit >> 5], 1u << (bit & 31u));
     }
 }
 
 // ---- K5: A7, A8, links (rules: rfx_core.h; the single-GPU kernels of rfx_graph.cu with peer-aware probes) ----------------
-template <class KT> __global__ void sg_right_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, unsigned long long* dstat) {
+template <class KT, bool DEFER>
+__global__ void __launch_bounds__(256, 8) sg_right_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const KT* keys = reinterpret_cast<const KT*>(Me.keys);
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t row = (uint32_t)(oid >> 1);
-        const KT key = keys[row];
-        const KT rc = revcomp(key, V.k);
-        if ((oid & 1u) && rc == key) { Me.alive[oid] = 0; Me.rflag[oid] = 0; continue; }  // palindrome: one node, not two
-        const KT X = (oid & 1u) ? rc : key;
-        const KT prefix = X >> 2;
-        const uint32_t myb = (uint32_t)X & 3u;
-        uint32_t pre_min, suf_min;
-        kmer_minima<KT>(X, V.k, V.m, pre_min, suf_min);
-        uint32_t cnt[4];
-        bool dup[4];
-#pragma unroll
-        for (uint32_t b = 0; b < 4; b++) {
-            if (b == myb) { cnt[b] = Me.counts[row]; dup[b] = (rc == key); }
+    uint32_t n_remote = 0;
+    const uint64_t count = sg_work_count<DEFER>(n, W);
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
+        const uint64_t i = i0 + threadIdx.x;
+        bool deferred = false;
+        uint32_t oid = 0;
+        if (i < count) {
+            oid = DEFER ? (uint32_t)i : W.list[i];
+            const uint32_t row = oid >> 1;
+            const KT key = keys[row];
+            const KT rc = revcomp(key, V.k);
+            if ((oid & 1u) && rc == key) { Me.alive[oid] = 0; Me.rflag[oid] = 0; }  // palindrome: one node, not two
             else {
-                const KT Z = (prefix << 2) | (KT)b;
-                const uint32_t hl = last_mm_of<KT>(prefix, b, V.m);
-                uint32_t cz = 0;
-                const uint32_t g = sg_find<KT>(V, Z, hl < pre_min ? hl : pre_min, &cz, dstat);
-                cnt[b] = g == NONE32 ? 0u : cz;
-                dup[b] = (Z == revcomp(Z, V.k));
+                const KT X = (oid & 1u) ? rc : key;
+                const KT prefix = X >> 2;
+                const uint32_t myb = (uint32_t)X & 3u;
+                const uint4 mm = rmin[row];
+                const uint32_t pre_min = (oid & 1u) ? mm.y : mm.x, pre_bin = (oid & 1u) ? mm.w : mm.z;
+                uint32_t cnt[4];
+                bool dup[4];
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b++) {
+                    if (b == myb) { cnt[b] = Me.counts[row]; dup[b] = (rc == key); }
+                    else {
+                        const KT Z = (prefix << 2) | (KT)b;
+                        const uint32_t hl = last_mm_of<KT>(prefix, b, V.m);
+                        uint32_t cz = 0;
+                        const uint32_t g = sg_find<KT, DEFER>(V, Z, hl, pre_min, pre_bin, &cz, n_remote, deferred);
+                        cnt[b] = g == NONE32 ? 0u : cz;
+                        dup[b] = (Z == revcomp(Z, V.k));
+                    }
+                }
+                if (!deferred) {
+                    const ForkResult res = right_fork(cnt, dup, E, V.k - 1);
+                    Me.alive[oid] = (uint8_t)(((res.winner == (int)myb) ? 1 : 0) | (res.flag < 0 ? 4 : 0));
+                    Me.rflag[oid] = res.flag;
+                }
             }
         }
-        const ForkResult res = right_fork(cnt, dup, E, V.k - 1);
-        Me.alive[oid] = (uint8_t)(((res.winner == (int)myb) ? 1 : 0) | (res.flag < 0 ? 4 : 0));
-        Me.rflag[oid] = res.flag;
+        if (DEFER) sg_work_push(W, deferred, oid);
     }
+    sg_flush_remote(n_remote, dstat);
 }
 
-template <class KT> __global__ void sg_left_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, unsigned long long* dstat) {
+template <class KT, bool DEFER>
+__global__ void __launch_bounds__(256, 8) sg_left_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const int top = 2 * (V.k - 1);
     const KT sufmask = mask_bases<KT>(V.k - 1);
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
-        Me.lflag[oid] = 0;
-        if (!(Me.alive[oid] & 1)) continue;
-        const KT X = sg_oriented<KT>(V, gid_make(V.me, (uint32_t)oid));
-        const KT suffix = X & sufmask;
-        const uint32_t mya = (uint32_t)(X >> top) & 3u;
-        uint32_t pre_min, suf_min;
-        kmer_minima<KT>(X, V.k, V.m, pre_min, suf_min);
-        uint32_t cnt[4];
+    uint32_t n_remote = 0;
+    const uint64_t count = sg_work_count<DEFER>(n, W);
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
+        const uint64_t i = i0 + threadIdx.x;
+        bool deferred = false;
+        uint32_t oid = 0;
+        if (i < count) {
+            oid = DEFER ? (uint32_t)i : W.list[i];
+            if (DEFER) Me.lflag[oid] = 0;
+            if (Me.alive[oid] & 1) {
+                const KT X = sg_oriented<KT>(V, gid_make(V.me, oid));
+                const KT suffix = X & sufmask;
+                const uint32_t mya = (uint32_t)(X >> top) & 3u;
+                const uint4 mm = rmin[oid >> 1];
+                const uint32_t suf_min = (oid & 1u) ? mm.x : mm.y, suf_bin = (oid & 1u) ? mm.z : mm.w;
+                uint32_t cnt[4];
 #pragma unroll
-        for (uint32_t a = 0; a < 4; a++) {
-            if (a == mya) cnt[a] = Me.counts[oid >> 1];
-            else {
-                uint32_t cz = 0;
-                const uint32_t hf = first_mm_of<KT>(suffix, a, V.k, V.m);
-                const uint32_t g = sg_find<KT>(V, ((KT)a << top) | suffix, hf < suf_min ? hf : suf_min, &cz, dstat);
-                cnt[a] = (g != NONE32 && (V.p[gid_rank(g)].alive[gid_loc(g)] & 1)) ? cz : 0u;
+                for (uint32_t a = 0; a < 4; a++) {
+                    if (a == mya) cnt[a] = Me.counts[oid >> 1];
+                    else {
+                        uint32_t cz = 0;
+                        const uint32_t hf = first_mm_of<KT>(suffix, a, V.k, V.m);
+                        const uint32_t g = sg_find<KT, DEFER>(V, ((KT)a << top) | suffix, hf, suf_min, suf_bin, &cz, n_remote, deferred);
+                        cnt[a] = (g != NONE32 && (V.p[gid_rank(g)].alive[gid_loc(g)] & 1)) ? cz : 0u;
+                    }
+                }
+                if (!deferred) {
+                    const ForkResult res = left_fork(cnt, E, V.k - 1);
+                    if (res.winner == (int)mya) { Me.alive[oid] = (uint8_t)((Me.alive[oid] & 4) | 3 | (res.flag < 0 ? 8 : 0)); Me.lflag[oid] = res.flag; }
+                }
             }
         }
-        const ForkResult res = left_fork(cnt, E, V.k - 1);
-        if (res.winner == (int)mya) { Me.alive[oid] = (uint8_t)((Me.alive[oid] & 4) | 3 | (res.flag < 0 ? 8 : 0)); Me.lflag[oid] = res.flag; }
+        if (DEFER) sg_work_push(W, deferred, oid);
     }
+    sg_flush_remote(n_remote, dstat);
 }
 
-// Raw links over every junction (which of them hold is decided by the budget walks, as on one GPU).  The successor's
-// pred[] may be in a peer's memory: one remote atomic per junction that crosses ranks.
-template <class KT> __global__ void sg_link_kernel(const __grid_constant__ SGView V, uint64_t n, unsigned long long* dstat) {
+// Raw links over every junction (which of them hold is decided by the budget walks, as on one GPU).  A successor on another
+// rank: its index, its alive byte (which carries the sign of the left flag), and one store into the owner's pred[] that nobody waits for.
+template <class KT, bool DEFER>
+__global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__ SGView V, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const KT sufmask = mask_bases<KT>(V.k - 1);
-    for (uint64_t oid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; oid < n; oid += (uint64_t)gridDim.x * blockDim.x) {
-        Me.eff_l[oid] = Me.lflag[oid];
-        Me.eff_r[oid] = Me.rflag[oid];
-        if (!(Me.alive[oid] & 2)) continue;
-        const uint32_t self = gid_make(V.me, (uint32_t)oid);
-        const KT X = sg_oriented<KT>(V, self);
-        const KT suffix = X & sufmask;
-        uint32_t pre_min, suf_min;
-        kmer_minima<KT>(X, V.k, V.m, pre_min, suf_min);
-        uint32_t next = NONE32;
-        int n_cand = 0;
+    uint32_t n_remote = 0;
+    const uint64_t count = sg_work_count<DEFER>(n, W);
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
+        const uint64_t i = i0 + threadIdx.x;
+        bool deferred = false;
+        uint32_t oid = 0;
+        if (i < count) {
+            oid = DEFER ? (uint32_t)i : W.list[i];
+            const int32_t my_l = Me.lflag[oid], my_r = Me.rflag[oid];
+            if (DEFER) { Me.eff_l[oid] = my_l; Me.eff_r[oid] = my_r; }
+            if (Me.alive[oid] & 2) {
+                const uint32_t self = gid_make(V.me, oid);
+                const KT X = sg_oriented<KT>(V, self);
+                const KT suffix = X & sufmask;
+                const uint4 mm = rmin[oid >> 1];
+                const uint32_t suf_min = (oid & 1u) ? mm.x : mm.y, suf_bin = (oid & 1u) ? mm.z : mm.w;
+                uint32_t next = NONE32;
+                bool next_l_neg = false;
+                int n_cand = 0;
 #pragma unroll
-        for (uint32_t b = 0; b < 4; b++) {
-            uint32_t cz;
-            const uint32_t hl = last_mm_of<KT>(suffix, b, V.m);
-            const uint32_t g = sg_find<KT>(V, (suffix << 2) | (KT)b, hl < suf_min ? hl : suf_min, &cz, dstat);
-            if (g != NONE32 && (V.p[gid_rank(g)].alive[gid_loc(g)] & 2)) { next = g; n_cand++; }
-        }
-        if (n_cand > 1) { atomicExch(&dstat[DS_GRAPH_ERR], 1ull); continue; }
-        if (Me.lflag[oid] >= 0 || Me.rflag[oid] >= 0) atomicAdd(&dstat[DS_FLAGGED], 1ull);
-        if (next != NONE32) {
-            const bool joins = junction_joins(Me.rflag[oid], V.p[gid_rank(next)].lflag[gid_loc(next)]);
-            if (!joins) atomicAdd(&dstat[DS_BUDGET], 1ull);
-            if (next == self) {
-                if (joins) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
-            } else {
-                Me.succ[oid] = next;
-                if (atomicExch(&V.p[gid_rank(next)].pred[gid_loc(next)], self) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+                for (uint32_t b = 0; b < 4; b++) {
+                    uint32_t cz;
+                    const uint32_t hl = last_mm_of<KT>(suffix, b, V.m);
+                    const uint32_t g = sg_find<KT, DEFER>(V, (suffix << 2) | (KT)b, hl, suf_min, suf_bin, &cz, n_remote, deferred);
+                    if (g != NONE32) {
+                        const uint8_t al = V.p[gid_rank(g)].alive[gid_loc(g)];  // bit 3: the sign of its left flag, all a junction test needs
+                        if (al & 2) { next = g; next_l_neg = (al & 8) != 0; n_cand++; }
+                    }
+                }
+                if (!deferred) {
+                    if (n_cand > 1) atomicExch(&dstat[DS_GRAPH_ERR], 1ull);
+                    else {
+                        if (my_l >= 0 || my_r >= 0) atomicAdd(&dstat[DS_FLAGGED], 1ull);
+                        if (next != NONE32) {
+                            const bool joins = (my_r < 0) == next_l_neg;  // junction_joins on the signs
+                            if (!joins) atomicAdd(&dstat[DS_BUDGET], 1ull);
+                            if (next == self) {
+                                if (joins) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
+                            } else {
+                                Me.succ[oid] = next;
+                                if (gid_rank(next) == V.me) {
+                                    if (atomicExch(&Me.pred[gid_loc(next)], self) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+                                } else {
+                                    V.p[gid_rank(next)].pred[gid_loc(next)] = self;  // the left filter left at most one predecessor: nobody else writes here
+                                }
+                            }
+                        }
+                    }
+                }
             }
         }
+        if (DEFER) sg_work_push(W, deferred, oid);
     }
+    sg_flush_remote(n_remote, dstat);
 }
 
 // ---- budget walks across ranks (rfx_graph.cu: budget_walk_kernel, every array read through its owner) ----------------------
@@ -298,24 +414,27 @@ __device__ __forceinline__ bool sg_l2_sample(uint32_t l1_gid) { return (fmix32(l
 
 __global__ void sg_select_kernel(const __grid_constant__ SGView V, uint64_t n, uint32_t* __restrict__ spl_node, uint32_t* __restrict__ l2_l1, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t id = NONE32;
-        if (Me.alive[x] & 2) {
-            const uint32_t p = Me.pred[x];
-            if (p == NONE32 || gid_rank(p) != V.me || sg_l1_sample((uint32_t)x)) {
-                id = (uint32_t)atomicAdd(&dstat[DS_NSPL], 1ull);
-                spl_node[id] = (uint32_t)x;
-                uint32_t j = NONE32;
-                if (p == NONE32 || sg_l2_sample(gid_make(V.me, id))) {
-                    j = (uint32_t)atomicAdd(&dstat[DS_NL2], 1ull);
-                    l2_l1[j] = id;
-                    Me.l2_node[j] = (uint32_t)x;
-                    Me.l2_up[0][j] = ad_pack(gid_make(V.me, j), 0u);  // a non-head is overwritten by the level-2 walk that reaches it
-                }
-                Me.l2_of[id] = j;
-            }
+    for (uint64_t x0 = (uint64_t)blockIdx.x * blockDim.x; x0 < n; x0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count
+        const uint64_t x = x0 + threadIdx.x;
+        uint32_t p = 0;
+        bool s1 = false;
+        if (x < n && (Me.alive[x] & 2)) {
+            p = Me.pred[x];
+            s1 = p == NONE32 || gid_rank(p) != V.me || sg_l1_sample((uint32_t)x);
         }
-        Me.spl_id[x] = id;
+        const uint32_t id = (uint32_t)sg_block_reserve(s1, &dstat[DS_NSPL]);
+        const bool s2 = s1 && (p == NONE32 || sg_l2_sample(gid_make(V.me, id)));
+        const uint32_t j = (uint32_t)sg_block_reserve(s2, &dstat[DS_NL2]);
+        if (s1) {
+            spl_node[id] = (uint32_t)x;
+            if (s2) {
+                l2_l1[j] = id;
+                Me.l2_node[j] = (uint32_t)x;
+                Me.l2_up[0][j] = ad_pack(gid_make(V.me, j), 0u);  // a non-head is overwritten by the level-2 walk that reaches it
+            }
+            Me.l2_of[id] = j;  // NONE32 unless level 2
+        }
+        if (x < n) Me.spl_id[x] = s1 ? id : NONE32;
     }
 }
 // level-1 walk: purely local; the segment ends in front of the next level-1 splitter (on this rank or the first node on another)
@@ -472,6 +591,35 @@ __global__ void sg_gather_kernel(const __grid_constant__ SGView V, uint64_t n, c
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
+// RFX_SHARD_PROF=1: event marks between the phases of rfx_assemble_sharded, printed by rank 0 when the call returns
+struct SGProf {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back({name, e});
+    }
+    void report(int rank) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        std::string line = "rfx_assemble_sharded rank " + std::to_string(rank) + " [ms]:";
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            char buf[96];
+            snprintf(buf, sizeof(buf), " %s %.3f", marks[i].first, ms);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+
 // publish the arena offsets of this rank's graph buffers + values; rebuild the view of everybody's buffers
 static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_NHOST], int n_dev, const int* dev_slots, unsigned long long* all) {
     GShard* gs = c->gshard;
@@ -483,13 +631,16 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
     for (int i = 0; i < GP_NPTR; i++) mine[i] = off_of(ptrs[i]);
     mine[GP_NROWS] = c->n_rows;
     mine[GP_HTCAP] = c->ht_cap;
-    mine[GP_BLOOMMASK] = c->g_bloom_mask;
+    mine[GP_BLOOMMASK] = 0;
     for (int i = 0; i < GP_NHOST; i++) mine[GP_HOST + i] = host_vals ? host_vals[i] : 0ull;
     // device values: gathered into a staging block right behind the host values by one small copy each
     for (int i = 0; i < GP_NDEV; i++) mine[GP_DEV + i] = 0ull;
     RFX_TRY(shard_exchange(c, PUB_GRAPH, GP_END, mine, all, n_dev, dev_slots, PUB_GRAPH + GP_DEV));
     V.me = c->sh_rank; V.world = c->sh_world; V.k = c->k; V.m = c->m;
     V.B = c->n_bins; V.bps = c->n_bins / (uint32_t)c->sh_world;
+    V.filter = c->g_bloom.as<uint32_t>();
+    V.rb_shift = gs->rb_shift;
+    V.inv_bps = V.bps > 1 ? ~0ull / V.bps + 1ull : 0ull;
     for (int r = 0; r < RFX_MAX_RANKS; r++) {
         SGPeer& P = V.p[r];
         memset(&P, 0, sizeof(P));
@@ -497,15 +648,13 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
         const unsigned long long* v = all + (size_t)r * RFX_PUB_SLOTS + PUB_GRAPH;
         uint8_t* base = c->peer_base[r];
         auto at = [&](int slot) -> uint8_t* { return v[slot] == ~0ull ? nullptr : base + v[slot]; };
-        P.keys = at(GP_KEYS); P.counts = (const uint32_t*)at(GP_COUNTS); P.ht = (const uint32_t*)at(GP_HT); P.bloom = (const uint32_t*)at(GP_BLOOM);
+        P.keys = at(GP_KEYS); P.counts = (const uint32_t*)at(GP_COUNTS); P.ht = (const uint32_t*)at(GP_HT); P.filter = (const uint32_t*)at(GP_BLOOM);
         P.alive = at(GP_ALIVE); P.lflag = (int32_t*)at(GP_LFLAG); P.rflag = (int32_t*)at(GP_RFLAG); P.eff_l = (int32_t*)at(GP_EFFL); P.eff_r = (int32_t*)at(GP_EFFR);
         P.succ = (uint32_t*)at(GP_SUCC); P.pred = (uint32_t*)at(GP_PRED); P.spl_id = (uint32_t*)at(GP_SPLID);
         P.l1_nl = (uint64_t*)at(GP_L1NL); P.l1_loc = (uint64_t*)at(GP_L1LOC); P.l2_of = (uint32_t*)at(GP_L2OF);
         P.l2_up[0] = (uint64_t*)at(GP_L2UP0); P.l2_up[1] = (uint64_t*)at(GP_L2UP1); P.l2_node = (uint32_t*)at(GP_L2NODE); P.l2_fin = (uint64_t*)at(GP_L2FIN);
         P.chain_len = (uint32_t*)at(GP_CHAINLEN); P.tail_rf = (int32_t*)at(GP_TAILRF); P.ctg_idx = (uint32_t*)at(GP_CTGIDX); P.ctg_off = (uint64_t*)at(GP_CTGOFF);
         P.ctg_bases = (char*)at(GP_CTGBASES);
-        if (gs->bloom_local[r]) P.bloom = gs->bloom_local[r];
-        P.bloom_mask = v[GP_BLOOMMASK];
         P.ht_cap = (uint32_t)v[GP_HTCAP];
     }
     return RFX_OK;
@@ -566,8 +715,11 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     c->have_sorted = false; c->have_contigs = false;
     c->ms_comm = 0;
     gs->fell_back = 0;
-    for (int r = 0; r < RFX_MAX_RANKS; r++) gs->bloom_local[r] = nullptr;
 
+    SGProf prof;
+    prof.on = getenv("RFX_SHARD_PROF") != nullptr && c->sh_rank == 0;
+    prof.st = st;
+    prof.mark("start");
     // ---- K5 ----
     stage_begin(c);
     RFX_TRY(devbuf_reserve(c, c->rflag, nn * sizeof(int32_t)));
@@ -584,6 +736,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->chain_len, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_idx, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, gs->tail_rf, nn * sizeof(int32_t)));
+    RFX_TRY(devbuf_reserve(c, gs->rmin, (n_rows + 1) * sizeof(uint4)));
     RFX_TRY(devbuf_reserve(c, gs->l1_nl, nn * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, gs->l1_loc, nn * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, gs->l1_fin, nn * sizeof(uint64_t)));
@@ -595,19 +748,30 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, gs->l2_fin, nn * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_off, sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_bases, 16));
-    // the own index: one region, load factor <= 1/4, presence bits in front of it (>= 16 per row)
-    uint64_t bits = 1024;
-    while (bits < 16 * n_rows) bits <<= 1;
+    // the own index: one region, load factor <= 1/4.  Presence bits: a region per minimiser bin of ALL ranks (SGView), the
+    // region size from the global row count rfx_count_sharded left behind, so that every rank computes the same
+    const uint32_t B = c->n_bins, bps = B / (uint32_t)world;
+    {
+        const uint64_t per_bin = (c->sh_rows_global + B - 1) / B;
+        int sh = 6;
+        while (sh < 24 && (1ull << sh) < 16 * per_bin) sh++;
+        gs->rb_shift = sh;
+    }
+    const uint64_t filter_bytes = ((uint64_t)B << gs->rb_shift) / 8, slice_bytes = ((uint64_t)bps << gs->rb_shift) / 8;
     const uint64_t slots = 4 * n_rows + 2;
     RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
-    RFX_TRY(devbuf_reserve(c, c->g_bloom, bits / 8));
-    c->ht_cap = slots; c->g_bins = 1; c->g_m = c->m; c->g_bloom_mask = bits - 1;
+    RFX_TRY(devbuf_reserve(c, c->g_bloom, filter_bytes + 64));
+    RFX_TRY(devbuf_reserve(c, gs->work, nn * sizeof(uint32_t)));
+    c->ht_cap = slots; c->g_bins = 1; c->g_m = c->m; c->g_bloom_mask = 0;
     RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
-    RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.p, 0, bits / 8, st));
+    RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.as<uint8_t>() + (size_t)c->sh_rank * slice_bytes, 0, slice_bytes, st));
     if (n_rows) {
         Graph<KT> G = make_graph<KT>(c);
+        G.bloom_mask = 0;
         ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G, nullptr);
-        c->launches++;
+        sg_row_minima_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(c->keys.as<KT>(), n_rows, c->k, c->m, B, (uint32_t)c->sh_rank * bps, (uint32_t)(c->sh_rank + 1) * bps,
+                                                                gs->rb_shift, gs->rmin.as<uint4>(), c->g_bloom.as<uint32_t>(), dstat);
+        c->launches += 2;
     }
     cudaMemsetAsync(c->succ.p, 0xff, nn * sizeof(uint32_t), st);
     cudaMemsetAsync(c->pred.p, 0xff, nn * sizeof(uint32_t), st);
@@ -617,35 +781,52 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     cudaMemsetAsync(gs->l1_loc.p, 0xff, nn * sizeof(uint64_t), st);
     cudaMemsetAsync(c->alive.p, 0, nn + 8, st);
 
+    prof.mark("memsets+index");
     SGView V;
     RFX_TRY(sg_publish(c, V, nullptr, 0, nullptr, all));  // [barrier] everybody's index and presence bits are complete
+    prof.mark("publish1");
     gs->n_rows_global = sg_sum(all, world, GP_NROWS);
-    {   // presence bits of the peers -> local copies
-        uint64_t total = 0;
-        for (int r = 0; r < world; r++) if (r != c->sh_rank) total += (V.p[r].bloom_mask + 1) / 8;
-        RFX_TRY(devbuf_reserve(c, gs->bloom_all, total + 256));
-        uint64_t pos = 0;
-        for (int r = 0; r < world; r++) {
-            if (r == c->sh_rank) continue;
-            const uint64_t nb = (V.p[r].bloom_mask + 1) / 8;
-            RFX_CUDA(c, cudaMemcpyAsync(gs->bloom_all.as<uint8_t>() + pos, V.p[r].bloom, nb, cudaMemcpyDefault, st));
-            gs->bloom_local[r] = reinterpret_cast<const uint32_t*>(gs->bloom_all.as<uint8_t>() + pos);
-            V.p[r].bloom = gs->bloom_local[r];
-            pos += nb;
-        }
+    // presence bits of the peers' bins -> the same place in the local array
+    for (int r = 0; r < world; r++) {
+        if (r == c->sh_rank || !slice_bytes) continue;
+        RFX_CUDA(c, cudaMemcpyAsync(c->g_bloom.as<uint8_t>() + (size_t)r * slice_bytes, reinterpret_cast<const uint8_t*>(V.p[r].filter) + (size_t)r * slice_bytes, slice_bytes,
+                                    cudaMemcpyDefault, st));
     }
+    prof.mark("filter_copy");
     const int E = c->prm.min_error_coverage;
-    if (n_rows) sg_check_owner_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(V, n_rows, dstat);
-    if (n) sg_right_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, E, n, dstat);
+    const uint4* rmin = gs->rmin.as<uint4>();
+    // every K5 kernel in two passes: the nodes that need a peer's index are listed by the first and done by the second
+    const unsigned g2 = sm_count() * 8u;
+    SGWork W[3];
+    for (int i = 0; i < 3; i++) W[i] = SGWork{gs->work.as<uint32_t>(), dstat + DS_WORK + i};
+    if (n) {
+        sg_right_filter_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
+        prof.mark("right");
+        if (world > 1) sg_right_filter_kernel<KT, false><<<g2, 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
+        prof.mark("right2");
+    }
     RFX_TRY(shard_barrier(c));
-    if (n) sg_left_filter_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, E, n, dstat);
+    prof.mark("bar");
+    if (n) {
+        sg_left_filter_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
+        prof.mark("left");
+        if (world > 1) sg_left_filter_kernel<KT, false><<<g2, 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
+        prof.mark("left2");
+    }
     RFX_TRY(shard_barrier(c));
-    if (n) sg_link_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, n, dstat);
-    c->launches += 4;
+    prof.mark("bar");
+    if (n) {
+        sg_link_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, n, rmin, W[2], dstat);
+        prof.mark("link");
+        if (world > 1) sg_link_kernel<KT, false><<<g2, 256, 0, st>>>(V, n, rmin, W[2], dstat);
+        prof.mark("link2");
+    }
+    c->launches += 7;
     {
         const int slots_dev[3] = {DS_FLAGGED, DS_GRAPH_ERR, DS_REMOTE};
         RFX_TRY(sg_publish(c, V, nullptr, 3, slots_dev, all));  // [barrier] every pred[] has its remote writes
     }
+    prof.mark("publish2");
     const unsigned long long flagged = sg_sum(all, world, GP_DEV + 0), gerr = sg_sum(all, world, GP_DEV + 1);
     gs->n_remote = all[(size_t)c->sh_rank * RFX_PUB_SLOTS + PUB_GRAPH + GP_DEV + 2];
     if (gerr) return ctx_fail(c, RFX_E_GRAPH, "sharded fork filters: a (k-1)-mer with degree > 1, or a row on a rank that does not own its minimiser bin (codes add up to %llu)", gerr);
@@ -664,6 +845,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(shard_barrier(c));
     RFX_TRY(shard_check(c, "sharded fork filters"));
     c->ms[3] += stage_end(c);
+    prof.mark("budget+bar+sync");
     stage_begin(c);
     if (n) sg_select_kernel<<<grid_n(n), 256, 0, st>>>(V, n, c->spl_node.as<uint32_t>(), gs->l2_l1.as<uint32_t>(), dstat);
     c->launches++;
@@ -671,6 +853,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
         const int slots_dev[2] = {DS_NSPL, DS_NL2};
         RFX_TRY(sg_publish(c, V, nullptr, 2, slots_dev, all));  // [barrier] spl_id / l2_of of every rank are final
     }
+    prof.mark("select+publish3");
     const uint64_t m1 = all[(size_t)c->sh_rank * RFX_PUB_SLOTS + PUB_GRAPH + GP_DEV + 0];
     const uint64_t m2 = all[(size_t)c->sh_rank * RFX_PUB_SLOTS + PUB_GRAPH + GP_DEV + 1];
     const uint64_t m2_all = sg_sum(all, world, GP_DEV + 1);
@@ -679,13 +862,17 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     while ((1ull << rounds) < m2_all + 1) rounds++;
     rounds += 1;
     if (m1) sg_l1_walk_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, c->spl_node.as<uint32_t>(), c->loc.as<uint64_t>());
+    prof.mark("l1_walk");
     RFX_TRY(shard_barrier(c));
+    prof.mark("bar");
     if (m2) {
         uint64_t g2 = (m2 + 63) / 64;
         if (g2 > sm_count() * 32u) g2 = sm_count() * 32u;
         sg_l2_walk_kernel<<<(unsigned)g2, 64, 0, st>>>(V, m2, gs->l2_l1.as<uint32_t>());
     }
+    prof.mark("l2_walk");
     RFX_TRY(shard_barrier(c));
+    prof.mark("bar");
     c->launches += 2;
     int cur = 0;
     for (int r = 0; r < rounds; r++) {
@@ -694,8 +881,10 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
         c->launches++;
         cur ^= 1;
     }
+    prof.mark("l2_jump_rounds");
     if (m2) sg_l2_fin_kernel<<<grid_n(m2), 256, 0, st>>>(V, m2, cur, dstat);
     RFX_TRY(shard_barrier(c));
+    prof.mark("l2_fin+bar");
     if (m1) sg_l1_fin_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, gs->l1_fin.as<uint64_t>(), dstat);
     if (n) sg_node_fin_kernel<<<grid_n(n), 256, 0, st>>>(V, n, c->loc.as<uint64_t>(), gs->l1_fin.as<uint64_t>(), c->ad[0].as<uint64_t>(), dstat);
     c->launches += 3;
@@ -703,6 +892,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
         const int slots_dev[5] = {DS_SG_CYCLE, DS_BUDGET, DS_ABSORBED, DS_CYCLES, DS_XBAR_ERR};
         RFX_TRY(sg_publish(c, V, nullptr, 5, slots_dev, all));  // [barrier] every head knows its chain's length and right flag
     }
+    prof.mark("l1_fin+node_fin+publish4");
     c->ms[4] += stage_end(c);
     const unsigned long long any_cycle = sg_sum(all, world, GP_DEV + 0);
     c->n_budget = all[(size_t)c->sh_rank * RFX_PUB_SLOTS + PUB_GRAPH + GP_DEV + 1];
@@ -739,6 +929,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "sharded contig scan failed: %s", cudaGetErrorString(e));
     }
+    prof.mark("contig_scan");
     RFX_TRY(devbuf_reserve(c, c->ctg_off, (tot.a + 1) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_left, (tot.a + 1) * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_right, (tot.a + 1) * sizeof(int32_t)));
@@ -759,12 +950,15 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     gs->n_contigs_global = sg_sum(all, world, GP_HOST + 0);
     gs->n_bases_global = sg_sum(all, world, GP_HOST + 1);
     gs->n_oriented_global = sg_sum(all, world, GP_HOST + 2);
+    prof.mark("scan_apply+publish5");
     if (m1) sg_l1_dst_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, gs->l1_fin.as<uint64_t>(), gs->l1_dst.as<unsigned long long>());
     if (n) sg_gather_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, n, c->loc.as<uint64_t>(), gs->l1_dst.as<unsigned long long>());
     c->launches += 2;
     RFX_TRY(shard_barrier(c));  // every base of the own contigs has arrived
+    prof.mark("l1_dst+gather+bar");
     RFX_TRY(shard_check(c, "sharded assembly"));
     c->ms[5] += stage_end(c);
+    prof.report(c->sh_rank);
     c->have_contigs = true;
     return RFX_OK;
 }
