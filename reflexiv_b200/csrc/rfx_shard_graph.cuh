@@ -13,8 +13,13 @@
 //              asking node knows the neighbour's minimiser -- and owner -- after hashing ONE more m-mer.
 //   probes     every rank holds a copy of every rank's presence bits (16 bits per row, pulled once per run: 2 B per
 //              row instead of the 12 B per row of the table).  Three of four probes ask for a k-mer that does not
-//              exist and end there; about 90 % of the rest stay on the rank (same minimiser); what is left walks the
-//              owner's index, keys and counts in place over NVLink (counted: rfx_shard_stats_t.n_remote_probes).
+//              exist and end there; about 90 % of the rest stay on the rank (same minimiser).  What is left is ASKED of
+//              the owner: the first pass of a K5 kernel writes a 16-byte request into the owner's inbox (a posted
+//              store over NVLink), the owner looks the k-mer up in its own index and stores the answer (count, node,
+//              alive byte) into the asker's answer box, a second pass finishes the nodes that were waiting.  One
+//              request / response exchange per filter pass, no round trip ever waits on the link (random reads of a
+//              peer's index from inside the kernels were measured first: 8.5 G/s per GPU between 2 GPUs, 1.3 G/s with
+//              8 GPUs all asking at once -- the link pass alone took 2.7 ms; profiles/).
 //   chains     level-1 splitters = heads, a 1-in-64 sample and every node whose predecessor lives on another rank, so a
 //              level-1 segment never leaves its GPU and the walk that stamps it is purely local.  Level-2 splitters = heads
 //              and 1 in 8 of the level-1 splitters; they walk the level-1 list (one 8-byte peer read and one 8-byte peer
@@ -59,6 +64,9 @@ struct SGPeer {
     uint32_t* ctg_idx;
     uint64_t* ctg_off;
     char* ctg_bases;
+    uint8_t* inbox;          // requests of every rank to this one: channel r at r * chan_cap (SGReq<KT>)
+    uint4* respbox;          // answers of every rank to this one: channel q at q * chan_cap
+    unsigned long long* req_cnt;  // [3 stages][RFX_MAX_RANKS]: requests this rank sent to every rank
     uint32_t ht_cap, pad;
 };
 struct SGView {
@@ -73,70 +81,130 @@ struct SGView {
     const uint32_t* filter;
     int rb_shift;
     uint64_t inv_bps;  // ceil(2^64 / bps): bin -> owner without a division
+    uint64_t chan_cap; // requests one rank may send to one rank per stage
     __device__ __forceinline__ int owner_of_bin(uint32_t bin) const { return bps == 1u ? (int)bin : (int)__umul64hi((uint64_t)bin, inv_bps); }
 };
 
 // slots of the published block (ShardCtl::pub, from PUB_GRAPH on): arena offsets first, then values
 enum {
     GP_KEYS, GP_COUNTS, GP_HT, GP_BLOOM, GP_ALIVE, GP_LFLAG, GP_RFLAG, GP_EFFL, GP_EFFR, GP_SUCC, GP_PRED, GP_SPLID, GP_L1NL, GP_L1LOC, GP_L2OF, GP_L2UP0,
-    GP_L2UP1, GP_L2NODE, GP_L2FIN, GP_CHAINLEN, GP_TAILRF, GP_CTGIDX, GP_CTGOFF, GP_CTGBASES, GP_NPTR,
+    GP_L2UP1, GP_L2NODE, GP_L2FIN, GP_CHAINLEN, GP_TAILRF, GP_CTGIDX, GP_CTGOFF, GP_CTGBASES, GP_INBOX, GP_RESPBOX, GP_REQCNT, GP_NPTR,
     GP_NROWS = GP_NPTR, GP_HTCAP, GP_BLOOMMASK, GP_HOST,  // GP_HOST: 6 host values, then up to 6 device values
     GP_NHOST = 6, GP_DEV = GP_HOST + GP_NHOST, GP_NDEV = 6, GP_END = GP_DEV + GP_NDEV
 };
 static_assert(PUB_GRAPH + GP_END <= RFX_PUB_SLOTS, "published block too small");
 
 struct GShard {
-    DevBuf rmin, work, l1_nl, l1_loc, l1_fin, l1_dst, l2_of, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
+    DevBuf rmin, work, pend_ref, inbox, respbox, req_cnt, l1_nl, l1_loc, l1_fin, l1_dst, l2_of, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
     uint64_t n_remote = 0, n_l1 = 0, n_l2 = 0, n_rows_global = 0, n_oriented_global = 0, n_contigs_global = 0, n_bases_global = 0;
+    uint64_t chan_cap = 0;
     int fell_back = 0, rb_shift = 6;
 };
 
 // ---- neighbour lookup ------------------------------------------------------------------------------------------------
-// gid of the oriented k-mer Z (minimiser hash hmin), NONE32 if its canonical form is in no rank's table.
-// DEFER: the first pass of a K5 kernel does not walk a peer's index -- a warp with one such lane would stall all its lanes
-// for three trips over NVLink -- but sets `deferred`; the node goes onto a work list and a second, small launch in which EVERY
-// lane is a remote probe takes care of the list (measured at 2 GPUs: link pass 1.32 -> see profiles/).
-template <class KT, bool DEFER>
-__device__ __forceinline__ uint32_t sg_find(const SGView& V, KT Z, uint32_t h_new, uint32_t h_side, uint32_t bin_side, uint32_t* cnt, uint32_t& n_remote, bool& deferred) {
+struct SGProbe {
+    uint32_t gid;    // oriented node (NONE32: no such k-mer)
+    uint32_t count;
+    uint32_t alive;  // its alive byte (when asked for)
+};
+// a request to the owner of a k-mer / its answer
+template <class KT> struct alignas(16) SGReq {
+    KT key;        // canonical form
+    uint32_t oid;  // asking node (local id on the sender) | bit 31: the asked orientation IS the canonical form
+    uint32_t pad;
+};
+static_assert(sizeof(SGReq<uint64_t>) == 16 && sizeof(SGReq<u128>) == 32, "requests are 16 / 32 bytes");
+constexpr uint32_t SG_REF_MASK = 0x1fffffffu;
+constexpr uint32_t SG_REF_ASK = 0x80000000u;  // | owner: a candidate that still has to be asked for (only inside pass 1)
+__device__ int getenv_debug = 0;
+
+// row of a canonical k-mer in THIS rank's index, NONE32 if absent
+template <class KT> __device__ __forceinline__ uint32_t sg_lookup_own(const SGPeer& Me, KT canon, uint64_t kh) {
+    const KT* keys = reinterpret_cast<const KT*>(Me.keys);
+    const uint32_t cap = Me.ht_cap;
+    uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(kh >> 20) * cap) >> 32);
+    while (true) {
+        const uint32_t v = Me.ht[slot];
+        if (v == NONE32) return NONE32;
+        if (keys[v] == canon) return v;
+        slot = slot + 1 == cap ? 0u : slot + 1;
+    }
+}
+// The oriented k-mer Z = the (k-1)-mer it shares with the asking node (minimum h_side over its m-mers, bin bin_side) plus
+// one new m-mer (hash h_new).
+//   PASS 1  a candidate in this rank's bins is looked up.  One in a peer's bins that passes the presence bits is marked
+//           (ref = SG_REF_ASK | owner); sg_finish_pass1 turns the marks of a block into requests in the owners' inboxes and
+//           ref = owner << 29 | position, which says where the answer will be.  The node has to wait.
+//   PASS 2  (nodes that waited) a candidate with a ref takes the owner's answer, the others are looked up again.
+template <class KT, int PASS, bool WANT_ALIVE>
+__device__ __forceinline__ SGProbe sg_probe(const SGView& V, KT Z, uint32_t h_new, uint32_t h_side, uint32_t bin_side, uint32_t oid, int stage, uint32_t& ref,
+                                            unsigned long long* dstat) {
+    SGProbe out{NONE32, 0u, 0u};
+    if (PASS == 2 && ref != NONE32) {
+        const uint4 a = V.p[V.me].respbox[(uint64_t)(ref >> 29) * V.chan_cap + (ref & SG_REF_MASK)];
+        if (getenv_debug && (ref & SG_REF_MASK) < 2) printf("answer: rank %d stage %d ref %08x: count %u node %08x alive %u\n", V.me, stage, ref, a.x, a.y, a.z);
+        out.gid = a.y == NONE32 ? NONE32 : gid_make((int)(ref >> 29), a.y);
+        out.count = a.x; out.alive = a.z;
+        return out;
+    }
     const KT zc = revcomp(Z, V.k);
     const bool fwd = !(zc < Z);
     const KT canon = fwd ? Z : zc;
-    // Z = the shared (k-1)-mer (minimum h_side over its m-mers, bin bin_side) plus one new m-mer (hash h_new)
     const uint32_t bin = h_new < h_side ? bin_of_minimizer(h_new, V.B) : bin_side;
     const uint64_t kh = key_hash(canon);
     const uint64_t bit = ((uint64_t)bin << V.rb_shift) + ((kh >> 13) & ((1ull << V.rb_shift) - 1ull));
-    if (!((V.filter[bit >> 5] >> (bit & 31u)) & 1u)) return NONE32;
+    if (!((V.filter[bit >> 5] >> (bit & 31u)) & 1u)) return out;
     const int r = V.owner_of_bin(bin);
     if (r != V.me) {
-        if (DEFER) { deferred = true; return NONE32; }
-        n_remote++;
+        if (PASS == 1) ref = SG_REF_ASK | (uint32_t)r;  // asked of rank r once the block has reserved its channel positions (sg_finish_pass1)
+        return out;  // (PASS 2: not reached -- such a candidate has a ref)
     }
-    const SGPeer& P = V.p[r];
-    const KT* keys = reinterpret_cast<const KT*>(P.keys);
-    const uint32_t cap = P.ht_cap;
-    uint32_t slot = (uint32_t)(((uint64_t)(uint32_t)(kh >> 20) * cap) >> 32);
-    uint32_t v;
-    while (true) {
-        v = P.ht[slot];
-        if (v == NONE32) return NONE32;
-        if (keys[v] == canon) break;
-        slot = slot + 1 == cap ? 0u : slot + 1;
-    }
-    *cnt = P.counts[v];
-    return gid_make(r, 2u * v + (fwd ? 0u : 1u));
+    const SGPeer& Me = V.p[V.me];
+    const uint32_t v = sg_lookup_own<KT>(Me, canon, kh);
+    if (v == NONE32) return out;
+    const uint32_t y = 2u * v + (fwd ? 0u : 1u);
+    out.gid = gid_make(V.me, y);
+    out.count = Me.counts[v];
+    if (WANT_ALIVE) out.alive = Me.alive[y];
+    return out;
 }
-// neighbour probes answered from a peer's index: one atomic per warp, at the end of the kernel
-__device__ __forceinline__ void sg_flush_remote(uint32_t n_remote, unsigned long long* dstat) {
+// The owner's side: every request of every peer is looked up in the own index, the answer goes into the asker's answer box.
+// LINK: a surviving node that is asked for by its predecessor notes that predecessor (the asker links to it in its second pass).
+template <class KT, bool LINK>
+__global__ void __launch_bounds__(256) sg_serve_kernel(const __grid_constant__ SGView V, int stage, unsigned long long* dstat) {
+    const SGPeer& Me = V.p[V.me];
+    unsigned long long served = 0;
+    for (int q = 1; q < V.world; q++) {
+        const int r = (V.me + q) % V.world;  // sender
+        const unsigned long long cnt_raw = *reinterpret_cast<const volatile unsigned long long*>(&V.p[r].req_cnt[stage * RFX_MAX_RANKS + V.me]);
+        const uint64_t cnt = cnt_raw < V.chan_cap ? cnt_raw : V.chan_cap;
+        if (getenv_debug && blockIdx.x == 0 && threadIdx.x == 0) printf("serve: rank %d stage %d sender %d: %llu requests (cap %llu)\n", V.me, stage, r, cnt_raw, (unsigned long long)V.chan_cap);
+        const SGReq<KT>* in = reinterpret_cast<const SGReq<KT>*>(Me.inbox) + (uint64_t)r * V.chan_cap;
+        uint4* out = V.p[r].respbox + (uint64_t)V.me * V.chan_cap;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
+            const SGReq<KT> rq = in[i];
+            const uint32_t v = sg_lookup_own<KT>(Me, rq.key, key_hash(rq.key));
+            uint4 a = make_uint4(0u, NONE32, 0u, 0u);
+            if (v != NONE32) {
+                const uint32_t y = 2u * v + ((rq.oid & 0x80000000u) ? 0u : 1u);
+                a.x = Me.counts[v]; a.y = y; a.z = Me.alive[y];
+                if (LINK && (a.z & 2)) Me.pred[y] = gid_make(r, rq.oid & SG_REF_MASK);  // the left filter left at most one predecessor
+            }
+            out[i] = a;  // posted store into the asker's memory
+            served++;
+        }
+    }
     __syncwarp();
-    const uint32_t t = __reduce_add_sync(0xffffffffu, n_remote);
-    if ((threadIdx.x & 31) == 0 && t) atomicAdd(&dstat[DS_REMOTE], (unsigned long long)t);
+    served = __reduce_add_sync(0xffffffffu, (uint32_t)served);
+    if ((threadIdx.x & 31) == 0 && served) atomicAdd(&dstat[DS_REMOTE], served);
 }
-// the two passes of a K5 kernel: pass 1 (DEFER) runs over the own nodes and lists the ones it puts off, pass 2 runs over that list
+// the two passes of a K5 kernel: pass 1 runs over the own nodes and lists the ones that wait for answers, pass 2 runs over that list
 struct SGWork {
-    uint32_t* list;               // pass 1 appends, pass 2 reads
+    uint32_t* list;               // waiting nodes (pass 1 appends, pass 2 reads)
+    uint4* refs;                  // per waiting node: where the answers for its four candidates are (NONE32: not asked)
     unsigned long long* counter;  // entries in the list (device)
 };
-template <bool DEFER> __device__ __forceinline__ uint64_t sg_work_count(uint64_t n, const SGWork& W) { return DEFER ? n : (uint64_t)*W.counter; }
+template <int PASS> __device__ __forceinline__ uint64_t sg_work_count(uint64_t n, const SGWork& W) { return PASS == 1 ? n : (uint64_t)*W.counter; }
 // Index of a new entry for every thread that wants one, ~0 for the others: ONE global atomic per block and call (a quarter
 // of a million warps bumping the same counter cost more than the kernel around them).  Every thread of the block must call.
 __device__ __forceinline__ unsigned long long sg_block_reserve(bool want, unsigned long long* counter) {
@@ -154,9 +222,60 @@ __device__ __forceinline__ unsigned long long sg_block_reserve(bool want, unsign
     __syncthreads();
     return want ? s_base + wbase + __popc(m & ((1u << lane) - 1u)) : ~0ull;
 }
-__device__ __forceinline__ void sg_work_push(const SGWork& W, bool put_off, uint32_t oid) {
-    const unsigned long long at = sg_block_reserve(put_off, W.counter);
-    if (put_off) W.list[at] = oid;
+// End of a pass-1 iteration, called by every thread of the block: the marked candidates become requests (positions in the
+// channels reserved per block: one global atomic per owner and block, the lanes rank themselves in shared memory) and the
+// nodes that wait go onto the work list with the places of their answers.  zfun(b) rebuilds candidate b of this thread's node.
+template <class KT, class ZFun>
+__device__ __forceinline__ void sg_finish_pass1(const SGView& V, const SGWork& W, int stage, uint32_t oid, uint32_t (&ref)[4], ZFun zfun, unsigned long long* dstat) {
+    __shared__ uint32_t s_req[RFX_MAX_RANKS], s_wait;
+    __shared__ unsigned long long s_rbase[RFX_MAX_RANKS], s_wbase;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (threadIdx.x < RFX_MAX_RANKS) s_req[threadIdx.x] = 0;
+    if (threadIdx.x == RFX_MAX_RANKS) s_wait = 0;
+    __syncthreads();
+    uint32_t lpos[4];
+    bool waits = false;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        lpos[b] = 0;
+        if (ref[b] != NONE32) { waits = true; lpos[b] = atomicAdd(&s_req[ref[b] & 7u], 1u); }
+    }
+    const uint32_t wm = __ballot_sync(0xffffffffu, waits);
+    uint32_t wbase = 0;
+    if (lane == 0 && wm) wbase = atomicAdd(&s_wait, (uint32_t)__popc(wm));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x < RFX_MAX_RANKS && s_req[threadIdx.x])
+        s_rbase[threadIdx.x] = atomicAdd(&V.p[V.me].req_cnt[stage * RFX_MAX_RANKS + threadIdx.x], (unsigned long long)s_req[threadIdx.x]);
+    if (threadIdx.x == RFX_MAX_RANKS && s_wait) s_wbase = atomicAdd(W.counter, (unsigned long long)s_wait);
+    __syncthreads();
+    if (!waits) return;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        if (ref[b] == NONE32) continue;
+        const uint32_t r = ref[b] & 7u;
+        const unsigned long long i = s_rbase[r] + lpos[b];
+        if (i < V.chan_cap) {
+            const KT Z = zfun((uint32_t)b);
+            const KT zc = revcomp(Z, V.k);
+            const bool fwd = !(zc < Z);
+            SGReq<KT> q;
+            q.key = fwd ? Z : zc; q.oid = oid | (fwd ? 0x80000000u : 0u); q.pad = 0;
+            reinterpret_cast<SGReq<KT>*>(V.p[r].inbox)[(uint64_t)V.me * V.chan_cap + i] = q;  // posted store into the owner's memory
+            ref[b] = (r << 29) | (uint32_t)i;
+        } else {
+            atomicExch(&dstat[DS_GRAPH_ERR], 4ull);
+            ref[b] = NONE32;
+        }
+    }
+    const unsigned long long at = s_wbase + wbase + __popc(wm & ((1u << lane) - 1u));
+    W.list[at] = oid;
+    W.refs[at] = make_uint4(ref[0], ref[1], ref[2], ref[3]);
+}
+__device__ __forceinline__ void sg_work_pop(const SGWork& W, uint64_t i, uint32_t& oid, uint32_t (&ref)[4]) {
+    oid = W.list[i];
+    const uint4 r = W.refs[i];
+    ref[0] = r.x; ref[1] = r.y; ref[2] = r.z; ref[3] = r.w;
 }
 
 template <class KT> __device__ __forceinline__ KT sg_oriented(const SGView& V, uint32_t g) {
@@ -186,26 +305,26 @@ __global__ void sg_row_minima_kernel(const KT* __restrict__ keys, uint64_t n_row
     }
 }
 
-// ---- K5: A7, A8, links (rules: rfx_core.h; the single-GPU kernels of rfx_graph.cu with peer-aware probes) ----------------
-template <class KT, bool DEFER>
+// ---- K5: A7, A8, links (rules: rfx_core.h; the single-GPU kernels of rfx_graph.cu, neighbours in a peer's bins asked by message) ----
+template <class KT, int PASS>
 __global__ void __launch_bounds__(256, 8) sg_right_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const KT* keys = reinterpret_cast<const KT*>(Me.keys);
-    uint32_t n_remote = 0;
-    const uint64_t count = sg_work_count<DEFER>(n, W);
+    const uint64_t count = sg_work_count<PASS>(n, W);
     for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
         const uint64_t i = i0 + threadIdx.x;
-        bool deferred = false;
+        uint32_t ref[4] = {NONE32, NONE32, NONE32, NONE32};
         uint32_t oid = 0;
+        KT prefix = 0;
         if (i < count) {
-            oid = DEFER ? (uint32_t)i : W.list[i];
+            if (PASS == 1) oid = (uint32_t)i; else sg_work_pop(W, i, oid, ref);
             const uint32_t row = oid >> 1;
             const KT key = keys[row];
             const KT rc = revcomp(key, V.k);
             if ((oid & 1u) && rc == key) { Me.alive[oid] = 0; Me.rflag[oid] = 0; }  // palindrome: one node, not two
             else {
                 const KT X = (oid & 1u) ? rc : key;
-                const KT prefix = X >> 2;
+                prefix = X >> 2;
                 const uint32_t myb = (uint32_t)X & 3u;
                 const uint4 mm = rmin[row];
                 const uint32_t pre_min = (oid & 1u) ? mm.y : mm.x, pre_bin = (oid & 1u) ? mm.w : mm.z;
@@ -216,42 +335,38 @@ __global__ void __launch_bounds__(256, 8) sg_right_filter_kernel(const __grid_co
                     if (b == myb) { cnt[b] = Me.counts[row]; dup[b] = (rc == key); }
                     else {
                         const KT Z = (prefix << 2) | (KT)b;
-                        const uint32_t hl = last_mm_of<KT>(prefix, b, V.m);
-                        uint32_t cz = 0;
-                        const uint32_t g = sg_find<KT, DEFER>(V, Z, hl, pre_min, pre_bin, &cz, n_remote, deferred);
-                        cnt[b] = g == NONE32 ? 0u : cz;
+                        const SGProbe pr = sg_probe<KT, PASS, false>(V, Z, last_mm_of<KT>(prefix, b, V.m), pre_min, pre_bin, oid, 0, ref[b], dstat);
+                        cnt[b] = pr.gid == NONE32 ? 0u : pr.count;
                         dup[b] = (Z == revcomp(Z, V.k));
                     }
                 }
-                if (!deferred) {
+                if (PASS == 2 || (ref[0] & ref[1] & ref[2] & ref[3]) == NONE32) {
                     const ForkResult res = right_fork(cnt, dup, E, V.k - 1);
                     Me.alive[oid] = (uint8_t)(((res.winner == (int)myb) ? 1 : 0) | (res.flag < 0 ? 4 : 0));
                     Me.rflag[oid] = res.flag;
                 }
             }
         }
-        if (DEFER) sg_work_push(W, deferred, oid);
+        if (PASS == 1) sg_finish_pass1<KT>(V, W, 0, oid, ref, [&](uint32_t b) { return (KT)((prefix << 2) | (KT)b); }, dstat);
     }
-    sg_flush_remote(n_remote, dstat);
 }
 
-template <class KT, bool DEFER>
+template <class KT, int PASS>
 __global__ void __launch_bounds__(256, 8) sg_left_filter_kernel(const __grid_constant__ SGView V, int E, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const int top = 2 * (V.k - 1);
     const KT sufmask = mask_bases<KT>(V.k - 1);
-    uint32_t n_remote = 0;
-    const uint64_t count = sg_work_count<DEFER>(n, W);
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
+    const uint64_t count = sg_work_count<PASS>(n, W);
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = i0 + threadIdx.x;
-        bool deferred = false;
+        uint32_t ref[4] = {NONE32, NONE32, NONE32, NONE32};
         uint32_t oid = 0;
+        KT suffix = 0;
         if (i < count) {
-            oid = DEFER ? (uint32_t)i : W.list[i];
-            if (DEFER) Me.lflag[oid] = 0;
+            if (PASS == 1) { oid = (uint32_t)i; Me.lflag[oid] = 0; } else sg_work_pop(W, i, oid, ref);
             if (Me.alive[oid] & 1) {
                 const KT X = sg_oriented<KT>(V, gid_make(V.me, oid));
-                const KT suffix = X & sufmask;
+                suffix = X & sufmask;
                 const uint32_t mya = (uint32_t)(X >> top) & 3u;
                 const uint4 mm = rmin[oid >> 1];
                 const uint32_t suf_min = (oid & 1u) ? mm.x : mm.y, suf_bin = (oid & 1u) ? mm.z : mm.w;
@@ -260,43 +375,41 @@ __global__ void __launch_bounds__(256, 8) sg_left_filter_kernel(const __grid_con
                 for (uint32_t a = 0; a < 4; a++) {
                     if (a == mya) cnt[a] = Me.counts[oid >> 1];
                     else {
-                        uint32_t cz = 0;
-                        const uint32_t hf = first_mm_of<KT>(suffix, a, V.k, V.m);
-                        const uint32_t g = sg_find<KT, DEFER>(V, ((KT)a << top) | suffix, hf, suf_min, suf_bin, &cz, n_remote, deferred);
-                        cnt[a] = (g != NONE32 && (V.p[gid_rank(g)].alive[gid_loc(g)] & 1)) ? cz : 0u;
+                        const SGProbe pr = sg_probe<KT, PASS, true>(V, ((KT)a << top) | suffix, first_mm_of<KT>(suffix, a, V.k, V.m), suf_min, suf_bin, oid, 1, ref[a], dstat);
+                        cnt[a] = (pr.gid != NONE32 && (pr.alive & 1)) ? pr.count : 0u;
                     }
                 }
-                if (!deferred) {
+                if (PASS == 2 || (ref[0] & ref[1] & ref[2] & ref[3]) == NONE32) {
                     const ForkResult res = left_fork(cnt, E, V.k - 1);
                     if (res.winner == (int)mya) { Me.alive[oid] = (uint8_t)((Me.alive[oid] & 4) | 3 | (res.flag < 0 ? 8 : 0)); Me.lflag[oid] = res.flag; }
                 }
             }
         }
-        if (DEFER) sg_work_push(W, deferred, oid);
+        if (PASS == 1) sg_finish_pass1<KT>(V, W, 1, oid, ref, [&](uint32_t a) { return (KT)(((KT)a << top) | suffix); }, dstat);
     }
-    sg_flush_remote(n_remote, dstat);
 }
 
-// Raw links over every junction (which of them hold is decided by the budget walks, as on one GPU).  A successor on another
-// rank: its index, its alive byte (which carries the sign of the left flag), and one store into the owner's pred[] that nobody waits for.
-template <class KT, bool DEFER>
+// Raw links over every junction (which of them hold is decided by the budget walks, as on one GPU).  A successor in a peer's
+// bins: the owner, asked for it, notes this node as its predecessor while it answers (sg_serve_kernel<LINK>); the alive byte in
+// the answer carries the sign of the successor's left flag, which is all the junction test needs.
+template <class KT, int PASS>
 __global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__ SGView V, uint64_t n, const uint4* __restrict__ rmin, SGWork W, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     const KT sufmask = mask_bases<KT>(V.k - 1);
-    uint32_t n_remote = 0;
-    const uint64_t count = sg_work_count<DEFER>(n, W);
-    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count (sg_work_push)
+    const uint64_t count = sg_work_count<PASS>(n, W);
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x; i0 < count; i0 += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t i = i0 + threadIdx.x;
-        bool deferred = false;
+        uint32_t ref[4] = {NONE32, NONE32, NONE32, NONE32};
         uint32_t oid = 0;
+        KT suffix = 0;
         if (i < count) {
-            oid = DEFER ? (uint32_t)i : W.list[i];
+            if (PASS == 1) oid = (uint32_t)i; else sg_work_pop(W, i, oid, ref);
             const int32_t my_l = Me.lflag[oid], my_r = Me.rflag[oid];
-            if (DEFER) { Me.eff_l[oid] = my_l; Me.eff_r[oid] = my_r; }
+            if (PASS == 1) { Me.eff_l[oid] = my_l; Me.eff_r[oid] = my_r; }
             if (Me.alive[oid] & 2) {
                 const uint32_t self = gid_make(V.me, oid);
                 const KT X = sg_oriented<KT>(V, self);
-                const KT suffix = X & sufmask;
+                suffix = X & sufmask;
                 const uint4 mm = rmin[oid >> 1];
                 const uint32_t suf_min = (oid & 1u) ? mm.x : mm.y, suf_bin = (oid & 1u) ? mm.z : mm.w;
                 uint32_t next = NONE32;
@@ -304,15 +417,10 @@ __global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__
                 int n_cand = 0;
 #pragma unroll
                 for (uint32_t b = 0; b < 4; b++) {
-                    uint32_t cz;
-                    const uint32_t hl = last_mm_of<KT>(suffix, b, V.m);
-                    const uint32_t g = sg_find<KT, DEFER>(V, (suffix << 2) | (KT)b, hl, suf_min, suf_bin, &cz, n_remote, deferred);
-                    if (g != NONE32) {
-                        const uint8_t al = V.p[gid_rank(g)].alive[gid_loc(g)];  // bit 3: the sign of its left flag, all a junction test needs
-                        if (al & 2) { next = g; next_l_neg = (al & 8) != 0; n_cand++; }
-                    }
+                    const SGProbe pr = sg_probe<KT, PASS, true>(V, (suffix << 2) | (KT)b, last_mm_of<KT>(suffix, b, V.m), suf_min, suf_bin, oid, 2, ref[b], dstat);
+                    if (pr.gid != NONE32 && (pr.alive & 2)) { next = pr.gid; next_l_neg = (pr.alive & 8) != 0; n_cand++; }
                 }
-                if (!deferred) {
+                if (PASS == 2 || (ref[0] & ref[1] & ref[2] & ref[3]) == NONE32) {
                     if (n_cand > 1) atomicExch(&dstat[DS_GRAPH_ERR], 1ull);
                     else {
                         if (my_l >= 0 || my_r >= 0) atomicAdd(&dstat[DS_FLAGGED], 1ull);
@@ -324,9 +432,11 @@ __global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__
                             } else {
                                 Me.succ[oid] = next;
                                 if (gid_rank(next) == V.me) {
-                                    if (atomicExch(&Me.pred[gid_loc(next)], self) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
-                                } else {
-                                    V.p[gid_rank(next)].pred[gid_loc(next)] = self;  // the left filter left at most one predecessor: nobody else writes here
+                                    const uint32_t old = atomicExch(&Me.pred[gid_loc(next)], self);
+                                    if (old != NONE32) {
+                                        atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
+                                        if (getenv_debug) printf("rank %d pass %d: node %u -> %u already has pred %08x (refs %08x %08x %08x %08x)\n", V.me, PASS, oid, gid_loc(next), old, ref[0], ref[1], ref[2], ref[3]);
+                                    }
                                 }
                             }
                         }
@@ -334,9 +444,8 @@ __global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__
                 }
             }
         }
-        if (DEFER) sg_work_push(W, deferred, oid);
+        if (PASS == 1) sg_finish_pass1<KT>(V, W, 2, oid, ref, [&](uint32_t b) { return (KT)((suffix << 2) | (KT)b); }, dstat);
     }
-    sg_flush_remote(n_remote, dstat);
 }
 
 // ---- budget walks across ranks (rfx_graph.cu: budget_walk_kernel, every array read through its owner) ----------------------
@@ -627,7 +736,7 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
     auto off_of = [&](const void* p) -> unsigned long long { return p ? (unsigned long long)((const uint8_t*)p - c->arena) : ~0ull; };
     const void* ptrs[GP_NPTR] = {c->keys.p, c->counts.p, c->ht.p, c->g_bloom.p, c->alive.p, c->lflag.p, c->rflag.p, c->eff_l.p, c->eff_r.p, c->succ.p, c->pred.p, c->spl_id.p,
                                  gs->l1_nl.p, gs->l1_loc.p, gs->l2_of.p, gs->l2_up[0].p, gs->l2_up[1].p, gs->l2_node.p, gs->l2_fin.p, c->chain_len.p, gs->tail_rf.p,
-                                 c->ctg_idx.p, c->ctg_off.p, c->ctg_bases.p};
+                                 c->ctg_idx.p, c->ctg_off.p, c->ctg_bases.p, gs->inbox.p, gs->respbox.p, gs->req_cnt.p};
     for (int i = 0; i < GP_NPTR; i++) mine[i] = off_of(ptrs[i]);
     mine[GP_NROWS] = c->n_rows;
     mine[GP_HTCAP] = c->ht_cap;
@@ -641,6 +750,7 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
     V.filter = c->g_bloom.as<uint32_t>();
     V.rb_shift = gs->rb_shift;
     V.inv_bps = V.bps > 1 ? ~0ull / V.bps + 1ull : 0ull;
+    V.chan_cap = gs->chan_cap;
     for (int r = 0; r < RFX_MAX_RANKS; r++) {
         SGPeer& P = V.p[r];
         memset(&P, 0, sizeof(P));
@@ -655,6 +765,7 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
         P.l2_up[0] = (uint64_t*)at(GP_L2UP0); P.l2_up[1] = (uint64_t*)at(GP_L2UP1); P.l2_node = (uint32_t*)at(GP_L2NODE); P.l2_fin = (uint64_t*)at(GP_L2FIN);
         P.chain_len = (uint32_t*)at(GP_CHAINLEN); P.tail_rf = (int32_t*)at(GP_TAILRF); P.ctg_idx = (uint32_t*)at(GP_CTGIDX); P.ctg_off = (uint64_t*)at(GP_CTGOFF);
         P.ctg_bases = (char*)at(GP_CTGBASES);
+        P.inbox = at(GP_INBOX); P.respbox = (uint4*)at(GP_RESPBOX); P.req_cnt = (unsigned long long*)at(GP_REQCNT);
         P.ht_cap = (uint32_t)v[GP_HTCAP];
     }
     return RFX_OK;
@@ -762,6 +873,13 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->g_bloom, filter_bytes + 64));
     RFX_TRY(devbuf_reserve(c, gs->work, nn * sizeof(uint32_t)));
+    RFX_TRY(devbuf_reserve(c, gs->pend_ref, nn * sizeof(uint4)));
+    // request / answer channels: one per (sender, receiver) pair, reused by the three K5 stages
+    gs->chan_cap = world > 1 ? c->sh_rows_global / (uint64_t)world + 65536 : 1;  // the same on every rank: a channel is addressed from both ends
+    RFX_TRY(devbuf_reserve(c, gs->inbox, (size_t)world * gs->chan_cap * sizeof(SGReq<KT>)));
+    RFX_TRY(devbuf_reserve(c, gs->respbox, (size_t)world * gs->chan_cap * sizeof(uint4)));
+    RFX_TRY(devbuf_reserve(c, gs->req_cnt, 3 * RFX_MAX_RANKS * sizeof(unsigned long long)));
+    RFX_CUDA(c, cudaMemsetAsync(gs->req_cnt.p, 0, 3 * RFX_MAX_RANKS * sizeof(unsigned long long), st));
     c->ht_cap = slots; c->g_bins = 1; c->g_m = c->m; c->g_bloom_mask = 0;
     RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.as<uint8_t>() + (size_t)c->sh_rank * slice_bytes, 0, slice_bytes, st));
@@ -795,33 +913,41 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     prof.mark("filter_copy");
     const int E = c->prm.min_error_coverage;
     const uint4* rmin = gs->rmin.as<uint4>();
-    // every K5 kernel in two passes: the nodes that need a peer's index are listed by the first and done by the second
+    // every K5 stage: pass 1 over the own nodes (requests out), [barrier], the owners answer, [barrier], pass 2 over the nodes that waited
     const unsigned g2 = sm_count() * 8u;
     SGWork W[3];
-    for (int i = 0; i < 3; i++) W[i] = SGWork{gs->work.as<uint32_t>(), dstat + DS_WORK + i};
-    if (n) {
-        sg_right_filter_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
-        prof.mark("right");
-        if (world > 1) sg_right_filter_kernel<KT, false><<<g2, 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
+    for (int i = 0; i < 3; i++) W[i] = SGWork{gs->work.as<uint32_t>(), gs->pend_ref.as<uint4>(), dstat + DS_WORK + i};
+    if (n) sg_right_filter_kernel<KT, 1><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
+    prof.mark("right");
+    if (world > 1) {
+        RFX_TRY(shard_barrier(c));
+        sg_serve_kernel<KT, false><<<g2, 256, 0, st>>>(V, 0, dstat);
+        RFX_TRY(shard_barrier(c));
+        prof.mark("right_serve");
+        if (n) sg_right_filter_kernel<KT, 2><<<g2, 256, 0, st>>>(V, E, n, rmin, W[0], dstat);
         prof.mark("right2");
     }
-    RFX_TRY(shard_barrier(c));
-    prof.mark("bar");
-    if (n) {
-        sg_left_filter_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
-        prof.mark("left");
-        if (world > 1) sg_left_filter_kernel<KT, false><<<g2, 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
+    if (n) sg_left_filter_kernel<KT, 1><<<grid_n(n), 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
+    prof.mark("left");
+    if (world > 1) {
+        RFX_TRY(shard_barrier(c));
+        sg_serve_kernel<KT, false><<<g2, 256, 0, st>>>(V, 1, dstat);
+        RFX_TRY(shard_barrier(c));
+        prof.mark("left_serve");
+        if (n) sg_left_filter_kernel<KT, 2><<<g2, 256, 0, st>>>(V, E, n, rmin, W[1], dstat);
         prof.mark("left2");
     }
-    RFX_TRY(shard_barrier(c));
-    prof.mark("bar");
-    if (n) {
-        sg_link_kernel<KT, true><<<grid_n(n), 256, 0, st>>>(V, n, rmin, W[2], dstat);
-        prof.mark("link");
-        if (world > 1) sg_link_kernel<KT, false><<<g2, 256, 0, st>>>(V, n, rmin, W[2], dstat);
+    if (n) sg_link_kernel<KT, 1><<<grid_n(n), 256, 0, st>>>(V, n, rmin, W[2], dstat);
+    prof.mark("link");
+    if (world > 1) {
+        RFX_TRY(shard_barrier(c));
+        sg_serve_kernel<KT, true><<<g2, 256, 0, st>>>(V, 2, dstat);
+        RFX_TRY(shard_barrier(c));
+        prof.mark("link_serve");
+        if (n) sg_link_kernel<KT, 2><<<g2, 256, 0, st>>>(V, n, rmin, W[2], dstat);
         prof.mark("link2");
     }
-    c->launches += 7;
+    c->launches += 9;
     {
         const int slots_dev[3] = {DS_FLAGGED, DS_GRAPH_ERR, DS_REMOTE};
         RFX_TRY(sg_publish(c, V, nullptr, 3, slots_dev, all));  // [barrier] every pred[] has its remote writes
@@ -829,7 +955,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     prof.mark("publish2");
     const unsigned long long flagged = sg_sum(all, world, GP_DEV + 0), gerr = sg_sum(all, world, GP_DEV + 1);
     gs->n_remote = all[(size_t)c->sh_rank * RFX_PUB_SLOTS + PUB_GRAPH + GP_DEV + 2];
-    if (gerr) return ctx_fail(c, RFX_E_GRAPH, "sharded fork filters: a (k-1)-mer with degree > 1, or a row on a rank that does not own its minimiser bin (codes add up to %llu)", gerr);
+    if (gerr) return ctx_fail(c, RFX_E_GRAPH, "sharded fork filters: a (k-1)-mer with degree > 1 (codes 1, 2), a row on a rank that does not own its minimiser bin (3) or a request channel that overflowed (4); codes add up to %llu", gerr);
     if (flagged) {
         if (n) {
             sg_budget_walk_kernel<KT, 0><<<grid_n(n), 256, 0, st>>>(V, n, c->k - 1, dstat);
