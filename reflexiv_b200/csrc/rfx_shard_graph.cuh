@@ -52,10 +52,10 @@ struct SGPeer {
     const uint32_t* filter; // that rank's presence bits in ITS memory (only used to pull its slice)
     uint8_t* alive;
     int32_t *lflag, *rflag, *eff_l, *eff_r;
-    uint32_t *succ, *pred, *spl_id;
-    uint64_t* l1_nl;   // per level-1 splitter: next level-1 splitter (gid form: rank, index) | nodes of the segment << 32
-    uint64_t* l1_loc;  // per level-1 splitter: (level-2 splitter that walked over it, nodes in front of it)
-    uint32_t* l2_of;   // per level-1 splitter: its level-2 index or NONE
+    uint32_t *succ, *pred;
+    uint32_t* nxt_l1;  // per node whose successor lives on another rank: that successor's level-1 splitter (written by its owner)
+    ulonglong2* l1_ent;  // per level-1 splitter: x = next level-1 splitter (gid form: rank, index) | nodes of the segment << 32, y = its level-2 index or NONE
+    uint64_t* l1_loc;    // per level-1 splitter: (level-2 splitter that walked over it, nodes in front of it)
     uint64_t* l2_up[2];
     uint32_t* l2_node;
     uint64_t* l2_fin;  // per level-2 splitter: (head node, nodes in front of it)
@@ -73,13 +73,13 @@ struct SGView {
     SGPeer p[RFX_MAX_RANKS];
     int me, world, k, m;
     uint32_t B, bps;
-    // Presence bits of ALL ranks' rows, one region of 2^rb_shift bits per minimiser bin (>= 16 bits per row on average), the
+    // Presence bits of ALL ranks' rows, one region of `rb` bits per minimiser bin (16 bits per row on average), the
     // whole array replicated on every rank (a rank fills the regions of its own bins, the others pull them: 2 B per row).
     // A node's neighbours mostly share its minimiser -- its bin -- and rows sit in the table grouped by bin, so the probes of
     // neighbouring threads fall into the same few hundred bytes; the array is streamed through once instead of being hit at
     // random (at 8 GPUs it is 8 x the size of one rank's rows and no longer fits the L2).
     const uint32_t* filter;
-    int rb_shift;
+    uint32_t rb;       // bits per region (a multiple of 64)
     uint64_t inv_bps;  // ceil(2^64 / bps): bin -> owner without a division
     uint64_t chan_cap; // requests one rank may send to one rank per stage
     __device__ __forceinline__ int owner_of_bin(uint32_t bin) const { return bps == 1u ? (int)bin : (int)__umul64hi((uint64_t)bin, inv_bps); }
@@ -87,7 +87,7 @@ struct SGView {
 
 // slots of the published block (ShardCtl::pub, from PUB_GRAPH on): arena offsets first, then values
 enum {
-    GP_KEYS, GP_COUNTS, GP_HT, GP_BLOOM, GP_ALIVE, GP_LFLAG, GP_RFLAG, GP_EFFL, GP_EFFR, GP_SUCC, GP_PRED, GP_SPLID, GP_L1NL, GP_L1LOC, GP_L2OF, GP_L2UP0,
+    GP_KEYS, GP_COUNTS, GP_HT, GP_BLOOM, GP_ALIVE, GP_LFLAG, GP_RFLAG, GP_EFFL, GP_EFFR, GP_SUCC, GP_PRED, GP_NXTL1, GP_L1ENT, GP_L1LOC, GP_L2UP0,
     GP_L2UP1, GP_L2NODE, GP_L2FIN, GP_CHAINLEN, GP_TAILRF, GP_CTGIDX, GP_CTGOFF, GP_CTGBASES, GP_INBOX, GP_RESPBOX, GP_REQCNT, GP_NPTR,
     GP_NROWS = GP_NPTR, GP_HTCAP, GP_BLOOMMASK, GP_HOST,  // GP_HOST: 6 host values, then up to 6 device values
     GP_NHOST = 6, GP_DEV = GP_HOST + GP_NHOST, GP_NDEV = 6, GP_END = GP_DEV + GP_NDEV
@@ -95,10 +95,11 @@ enum {
 static_assert(PUB_GRAPH + GP_END <= RFX_PUB_SLOTS, "published block too small");
 
 struct GShard {
-    DevBuf rmin, work, pend_ref, inbox, respbox, req_cnt, l1_nl, l1_loc, l1_fin, l1_dst, l2_of, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
+    DevBuf rmin, work, pend_ref, inbox, respbox, req_cnt, nxt_l1, l1_ent, l1_loc, l1_fin, l1_dst, l2_l1, l2_node, l2_up[2], l2_fin, tail_rf, pubsrc, all_keys, all_counts;
     uint64_t n_remote = 0, n_l1 = 0, n_l2 = 0, n_rows_global = 0, n_oriented_global = 0, n_contigs_global = 0, n_bases_global = 0;
     uint64_t chan_cap = 0;
-    int fell_back = 0, rb_shift = 6;
+    int fell_back = 0;
+    uint32_t rb = 64;
 };
 
 // ---- neighbour lookup ------------------------------------------------------------------------------------------------
@@ -116,7 +117,6 @@ template <class KT> struct alignas(16) SGReq {
 static_assert(sizeof(SGReq<uint64_t>) == 16 && sizeof(SGReq<u128>) == 32, "requests are 16 / 32 bytes");
 constexpr uint32_t SG_REF_MASK = 0x1fffffffu;
 constexpr uint32_t SG_REF_ASK = 0x80000000u;  // | owner: a candidate that still has to be asked for (only inside pass 1)
-__device__ int getenv_debug = 0;
 
 // row of a canonical k-mer in THIS rank's index, NONE32 if absent
 template <class KT> __device__ __forceinline__ uint32_t sg_lookup_own(const SGPeer& Me, KT canon, uint64_t kh) {
@@ -142,7 +142,7 @@ __device__ __forceinline__ SGProbe sg_probe(const SGView& V, KT Z, uint32_t h_ne
     SGProbe out{NONE32, 0u, 0u};
     if (PASS == 2 && ref != NONE32) {
         const uint4 a = V.p[V.me].respbox[(uint64_t)(ref >> 29) * V.chan_cap + (ref & SG_REF_MASK)];
-        if (getenv_debug && (ref & SG_REF_MASK) < 2) printf("answer: rank %d stage %d ref %08x: count %u node %08x alive %u\n", V.me, stage, ref, a.x, a.y, a.z);
+
         out.gid = a.y == NONE32 ? NONE32 : gid_make((int)(ref >> 29), a.y);
         out.count = a.x; out.alive = a.z;
         return out;
@@ -152,7 +152,7 @@ __device__ __forceinline__ SGProbe sg_probe(const SGView& V, KT Z, uint32_t h_ne
     const KT canon = fwd ? Z : zc;
     const uint32_t bin = h_new < h_side ? bin_of_minimizer(h_new, V.B) : bin_side;
     const uint64_t kh = key_hash(canon);
-    const uint64_t bit = ((uint64_t)bin << V.rb_shift) + ((kh >> 13) & ((1ull << V.rb_shift) - 1ull));
+    const uint64_t bit = (uint64_t)bin * V.rb + (((uint64_t)(uint32_t)kh * V.rb) >> 32);
     if (!((V.filter[bit >> 5] >> (bit & 31u)) & 1u)) return out;
     const int r = V.owner_of_bin(bin);
     if (r != V.me) {
@@ -178,7 +178,6 @@ __global__ void __launch_bounds__(256) sg_serve_kernel(const __grid_constant__ S
         const int r = (V.me + q) % V.world;  // sender
         const unsigned long long cnt_raw = *reinterpret_cast<const volatile unsigned long long*>(&V.p[r].req_cnt[stage * RFX_MAX_RANKS + V.me]);
         const uint64_t cnt = cnt_raw < V.chan_cap ? cnt_raw : V.chan_cap;
-        if (getenv_debug && blockIdx.x == 0 && threadIdx.x == 0) printf("serve: rank %d stage %d sender %d: %llu requests (cap %llu)\n", V.me, stage, r, cnt_raw, (unsigned long long)V.chan_cap);
         const SGReq<KT>* in = reinterpret_cast<const SGReq<KT>*>(Me.inbox) + (uint64_t)r * V.chan_cap;
         uint4* out = V.p[r].respbox + (uint64_t)V.me * V.chan_cap;
         for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -289,7 +288,7 @@ template <class KT> __device__ __forceinline__ KT sg_oriented(const SGView& V, u
 // and owner -- is then min(one new m-mer, one of the two).  The row's own bin must belong to this rank, or neighbours would
 // look for it elsewhere (checked); its presence bit is set in that bin's region.
 template <class KT>
-__global__ void sg_row_minima_kernel(const KT* __restrict__ keys, uint64_t n_rows, int k, int m, uint32_t B, uint32_t bin_lo, uint32_t bin_hi, int rb_shift,
+__global__ void sg_row_minima_kernel(const KT* __restrict__ keys, uint64_t n_rows, int k, int m, uint32_t B, uint32_t bin_lo, uint32_t bin_hi, uint32_t rb,
                                      uint4* __restrict__ rmin, uint32_t* filter, unsigned long long* dstat) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
         const KT key = keys[r];
@@ -300,7 +299,7 @@ __global__ void sg_row_minima_kernel(const KT* __restrict__ keys, uint64_t n_row
         if (m == k) h = mm_hash_m((uint32_t)key, m);  // one m-mer, in neither the prefix nor the suffix part
         const uint32_t bin = bin_of_minimizer(h, B);
         if (bin < bin_lo || bin >= bin_hi) atomicExch(&dstat[DS_GRAPH_ERR], 3ull);
-        const uint64_t bit = ((uint64_t)bin << rb_shift) + ((key_hash(key) >> 13) & ((1ull << rb_shift) - 1ull));
+        const uint64_t bit = (uint64_t)bin * rb + (((uint64_t)(uint32_t)key_hash(key) * rb) >> 32);
         atomicOr(&filter[bit >> 5], 1u << (bit & 31u));
     }
 }
@@ -431,13 +430,7 @@ __global__ void __launch_bounds__(256, 8) sg_link_kernel(const __grid_constant__
                                 if (joins) atomicAdd(&dstat[DS_CYCLES], 1ull);  // 1-cycle: a record never merges with itself
                             } else {
                                 Me.succ[oid] = next;
-                                if (gid_rank(next) == V.me) {
-                                    const uint32_t old = atomicExch(&Me.pred[gid_loc(next)], self);
-                                    if (old != NONE32) {
-                                        atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
-                                        if (getenv_debug) printf("rank %d pass %d: node %u -> %u already has pred %08x (refs %08x %08x %08x %08x)\n", V.me, PASS, oid, gid_loc(next), old, ref[0], ref[1], ref[2], ref[3]);
-                                    }
-                                }
+                                if (gid_rank(next) == V.me && atomicExch(&Me.pred[gid_loc(next)], self) != NONE32) atomicExch(&dstat[DS_GRAPH_ERR], 2ull);
                             }
                         }
                     }
@@ -521,7 +514,8 @@ __global__ void sg_junction_finalize_kernel(const __grid_constant__ SGView V, ui
 __device__ __forceinline__ bool sg_l1_sample(uint32_t x) { return (fmix32(x ^ 0xa5a5a5a5u) & 63u) == 0u; }
 __device__ __forceinline__ bool sg_l2_sample(uint32_t l1_gid) { return (fmix32(l1_gid ^ 0x3c6ef372u) & 7u) == 0u; }
 
-__global__ void sg_select_kernel(const __grid_constant__ SGView V, uint64_t n, uint32_t* __restrict__ spl_node, uint32_t* __restrict__ l2_l1, unsigned long long* dstat) {
+__global__ void sg_select_kernel(const __grid_constant__ SGView V, uint64_t n, uint32_t* __restrict__ spl_id, uint32_t* __restrict__ spl_node, uint32_t* __restrict__ l2_l1,
+                                 unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     for (uint64_t x0 = (uint64_t)blockIdx.x * blockDim.x; x0 < n; x0 += (uint64_t)gridDim.x * blockDim.x) {  // block-uniform trip count
         const uint64_t x = x0 + threadIdx.x;
@@ -541,48 +535,52 @@ __global__ void sg_select_kernel(const __grid_constant__ SGView V, uint64_t n, u
                 Me.l2_node[j] = (uint32_t)x;
                 Me.l2_up[0][j] = ad_pack(gid_make(V.me, j), 0u);  // a non-head is overwritten by the level-2 walk that reaches it
             }
-            Me.l2_of[id] = j;  // NONE32 unless level 2
+            Me.l1_ent[id].y = (unsigned long long)j;  // NONE32 unless level 2
+            // the predecessor lives on another rank: tell it where its segment ends (a posted store; its walk never has to ask)
+            if (p != NONE32 && gid_rank(p) != V.me) V.p[gid_rank(p)].nxt_l1[gid_loc(p)] = gid_make(V.me, id);
         }
-        if (x < n) Me.spl_id[x] = s1 ? id : NONE32;
+        if (x < n) spl_id[x] = s1 ? id : NONE32;
     }
 }
 // level-1 walk: purely local; the segment ends in front of the next level-1 splitter (on this rank or the first node on another)
-__global__ void sg_l1_walk_kernel(const __grid_constant__ SGView V, uint64_t m1, const uint32_t* __restrict__ spl_node, uint64_t* __restrict__ loc) {
+__global__ void sg_l1_walk_kernel(const __grid_constant__ SGView V, uint64_t m1, const uint32_t* __restrict__ spl_id, const uint32_t* __restrict__ spl_node, uint64_t* __restrict__ loc) {
     const SGPeer& Me = V.p[V.me];
     for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m1; id += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t x = spl_node[id];
+        uint32_t x = spl_node[id];
         uint32_t off = 0, next = NONE32;
         loc[x] = ad_pack((uint32_t)id, 0u);
         uint32_t y = Me.succ[x];
         while (y != NONE32) {
-            if (gid_rank(y) != V.me) { next = gid_make(gid_rank(y), V.p[gid_rank(y)].spl_id[gid_loc(y)]); break; }
+            if (gid_rank(y) != V.me) { next = Me.nxt_l1[x]; break; }  // left here by the successor's owner (sg_select_kernel)
             const uint32_t yl = gid_loc(y);
-            const uint32_t s = Me.spl_id[yl];
+            const uint32_t s = spl_id[yl];
             if (s != NONE32) { next = gid_make(V.me, s); break; }
             off++;
             loc[yl] = ad_pack((uint32_t)id, off);
+            x = yl;
             y = Me.succ[yl];
         }
-        Me.l1_nl[id] = ad_pack(next, off + 1u);
+        Me.l1_ent[id].x = ad_pack(next, off + 1u);
     }
 }
 // level-2 walk over the level-1 list: stamps (owner, nodes in front) on every level-1 splitter it passes, ends at the next level-2 splitter
 __global__ void sg_l2_walk_kernel(const __grid_constant__ SGView V, uint64_t m2, const uint32_t* __restrict__ l2_l1) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m2; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t self = gid_make(V.me, (uint32_t)j);
-        uint32_t a = gid_make(V.me, l2_l1[j]);
+        const uint32_t a = l2_l1[j];
         uint32_t dist = 0;
-        V.p[V.me].l1_loc[gid_loc(a)] = ad_pack(self, 0u);
-        while (true) {
-            const uint64_t nl = V.p[gid_rank(a)].l1_nl[gid_loc(a)];
+        V.p[V.me].l1_loc[a] = ad_pack(self, 0u);
+        unsigned long long nl = V.p[V.me].l1_ent[a].x;
+        while (true) {  // one 16-byte read and one 8-byte store per hop, most of them in a peer's memory
             const uint32_t nx = (uint32_t)nl;
             dist += (uint32_t)(nl >> 32);
             if (nx == NONE32) break;
             const SGPeer& Q = V.p[gid_rank(nx)];
-            const uint32_t t = Q.l2_of[gid_loc(nx)];
+            const ulonglong2 e = Q.l1_ent[gid_loc(nx)];
+            const uint32_t t = (uint32_t)e.y;
             if (t != NONE32) { Q.l2_up[0][t] = ad_pack(self, dist); break; }
             Q.l1_loc[gid_loc(nx)] = ad_pack(self, dist);
-            a = nx;
+            nl = e.x;
         }
     }
 }
@@ -682,8 +680,9 @@ __global__ void sg_l1_dst_kernel(const __grid_constant__ SGView V, uint64_t m1, 
         l1_dst[i] = d;
     }
 }
+// one thread per node: its base goes to where its segment starts + its offset (a one-byte store, often into a peer's memory)
 template <class KT>
-__global__ void sg_gather_kernel(const __grid_constant__ SGView V, uint64_t n, const uint64_t* __restrict__ loc, const unsigned long long* __restrict__ l1_dst) {
+__global__ void sg_gather_nodes_kernel(const __grid_constant__ SGView V, uint64_t n, const uint64_t* __restrict__ loc, const unsigned long long* __restrict__ l1_dst) {
     const SGPeer& Me = V.p[V.me];
     for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (uint64_t)gridDim.x * blockDim.x) {
         if (!(Me.alive[x] & 2)) continue;
@@ -696,6 +695,38 @@ __global__ void sg_gather_kernel(const __grid_constant__ SGView V, uint64_t n, c
         *dst = "ACGT"[(uint32_t)X & 3u];
         if (Me.pred[x] == NONE32)  // head: its contig lives on this rank; the first k-1 bases come from it as well
             for (int j = 0; j < V.k - 1; j++) dst[j - (V.k - 1)] = "ACGT"[(uint32_t)(X >> (2 * (V.k - 1 - j))) & 3u];
+    }
+}
+// One thread per level-1 segment: the bases of its nodes (the head's segment: the first k-1 bases of the contig as well) are
+// packed into 8-byte words and OR-ed into the owner's buffer (zeroed by the owner; words are shared with the neighbouring
+// segments, which other ranks write): about one posted atomic per 8 bases instead of one store per base -- on this
+// workload all ranks write into the buffers of the two ranks that own the two strands of the chromosome.
+template <class KT>
+__global__ void sg_gather_kernel(const __grid_constant__ SGView V, uint64_t m1, const uint32_t* __restrict__ spl_node, const unsigned long long* __restrict__ l1_dst) {
+    const SGPeer& Me = V.p[V.me];
+    for (uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; id < m1; id += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long addr = l1_dst[id];
+        if (!addr) continue;
+        uint32_t x = spl_node[id];
+        const uint32_t len = (uint32_t)(Me.l1_ent[id].x >> 32);
+        unsigned long long word = 0;
+        auto put = [&](uint32_t code) {
+            word |= (unsigned long long)(uint8_t)"ACGT"[code] << (8u * (uint32_t)(addr & 7ull));
+            addr++;
+            if (!(addr & 7ull)) { atomicOr(reinterpret_cast<unsigned long long*>(addr - 8ull), word); word = 0; }
+        };
+        KT X = sg_oriented<KT>(V, gid_make(V.me, x));
+        if (Me.pred[x] == NONE32) {  // head
+            addr -= (unsigned long long)(V.k - 1);
+            for (int j = 0; j < V.k - 1; j++) put((uint32_t)(X >> (2 * (V.k - 1 - j))) & 3u);
+        }
+        for (uint32_t t = 0;;) {
+            put((uint32_t)X & 3u);
+            if (++t == len) break;
+            x = gid_loc(Me.succ[x]);  // the segment stays on this rank
+            X = sg_oriented<KT>(V, gid_make(V.me, x));
+        }
+        if (addr & 7ull) atomicOr(reinterpret_cast<unsigned long long*>(addr & ~7ull), word);
     }
 }
 
@@ -734,8 +765,8 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
     GShard* gs = c->gshard;
     unsigned long long mine[GP_END];
     auto off_of = [&](const void* p) -> unsigned long long { return p ? (unsigned long long)((const uint8_t*)p - c->arena) : ~0ull; };
-    const void* ptrs[GP_NPTR] = {c->keys.p, c->counts.p, c->ht.p, c->g_bloom.p, c->alive.p, c->lflag.p, c->rflag.p, c->eff_l.p, c->eff_r.p, c->succ.p, c->pred.p, c->spl_id.p,
-                                 gs->l1_nl.p, gs->l1_loc.p, gs->l2_of.p, gs->l2_up[0].p, gs->l2_up[1].p, gs->l2_node.p, gs->l2_fin.p, c->chain_len.p, gs->tail_rf.p,
+    const void* ptrs[GP_NPTR] = {c->keys.p, c->counts.p, c->ht.p, c->g_bloom.p, c->alive.p, c->lflag.p, c->rflag.p, c->eff_l.p, c->eff_r.p, c->succ.p, c->pred.p, gs->nxt_l1.p,
+                                 gs->l1_ent.p, gs->l1_loc.p, gs->l2_up[0].p, gs->l2_up[1].p, gs->l2_node.p, gs->l2_fin.p, c->chain_len.p, gs->tail_rf.p,
                                  c->ctg_idx.p, c->ctg_off.p, c->ctg_bases.p, gs->inbox.p, gs->respbox.p, gs->req_cnt.p};
     for (int i = 0; i < GP_NPTR; i++) mine[i] = off_of(ptrs[i]);
     mine[GP_NROWS] = c->n_rows;
@@ -748,7 +779,7 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
     V.me = c->sh_rank; V.world = c->sh_world; V.k = c->k; V.m = c->m;
     V.B = c->n_bins; V.bps = c->n_bins / (uint32_t)c->sh_world;
     V.filter = c->g_bloom.as<uint32_t>();
-    V.rb_shift = gs->rb_shift;
+    V.rb = gs->rb;
     V.inv_bps = V.bps > 1 ? ~0ull / V.bps + 1ull : 0ull;
     V.chan_cap = gs->chan_cap;
     for (int r = 0; r < RFX_MAX_RANKS; r++) {
@@ -760,8 +791,8 @@ static int sg_publish(Ctx* c, SGView& V, const unsigned long long host_vals[GP_N
         auto at = [&](int slot) -> uint8_t* { return v[slot] == ~0ull ? nullptr : base + v[slot]; };
         P.keys = at(GP_KEYS); P.counts = (const uint32_t*)at(GP_COUNTS); P.ht = (const uint32_t*)at(GP_HT); P.filter = (const uint32_t*)at(GP_BLOOM);
         P.alive = at(GP_ALIVE); P.lflag = (int32_t*)at(GP_LFLAG); P.rflag = (int32_t*)at(GP_RFLAG); P.eff_l = (int32_t*)at(GP_EFFL); P.eff_r = (int32_t*)at(GP_EFFR);
-        P.succ = (uint32_t*)at(GP_SUCC); P.pred = (uint32_t*)at(GP_PRED); P.spl_id = (uint32_t*)at(GP_SPLID);
-        P.l1_nl = (uint64_t*)at(GP_L1NL); P.l1_loc = (uint64_t*)at(GP_L1LOC); P.l2_of = (uint32_t*)at(GP_L2OF);
+        P.succ = (uint32_t*)at(GP_SUCC); P.pred = (uint32_t*)at(GP_PRED); P.nxt_l1 = (uint32_t*)at(GP_NXTL1);
+        P.l1_ent = (ulonglong2*)at(GP_L1ENT); P.l1_loc = (uint64_t*)at(GP_L1LOC);
         P.l2_up[0] = (uint64_t*)at(GP_L2UP0); P.l2_up[1] = (uint64_t*)at(GP_L2UP1); P.l2_node = (uint32_t*)at(GP_L2NODE); P.l2_fin = (uint64_t*)at(GP_L2FIN);
         P.chain_len = (uint32_t*)at(GP_CHAINLEN); P.tail_rf = (int32_t*)at(GP_TAILRF); P.ctg_idx = (uint32_t*)at(GP_CTGIDX); P.ctg_off = (uint64_t*)at(GP_CTGOFF);
         P.ctg_bases = (char*)at(GP_CTGBASES);
@@ -848,11 +879,11 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->ctg_idx, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, gs->tail_rf, nn * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, gs->rmin, (n_rows + 1) * sizeof(uint4)));
-    RFX_TRY(devbuf_reserve(c, gs->l1_nl, nn * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, gs->l1_ent, nn * sizeof(ulonglong2)));
+    RFX_TRY(devbuf_reserve(c, gs->nxt_l1, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, gs->l1_loc, nn * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, gs->l1_fin, nn * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, gs->l1_dst, nn * sizeof(uint64_t)));
-    RFX_TRY(devbuf_reserve(c, gs->l2_of, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, gs->l2_l1, nn * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, gs->l2_node, nn * sizeof(uint32_t)));
     for (int i = 0; i < 2; i++) RFX_TRY(devbuf_reserve(c, gs->l2_up[i], nn * sizeof(uint64_t)));
@@ -864,11 +895,12 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     const uint32_t B = c->n_bins, bps = B / (uint32_t)world;
     {
         const uint64_t per_bin = (c->sh_rows_global + B - 1) / B;
-        int sh = 6;
-        while (sh < 24 && (1ull << sh) < 16 * per_bin) sh++;
-        gs->rb_shift = sh;
+        uint64_t rb = (16 * per_bin + 63) / 64 * 64;
+        if (rb < 64) rb = 64;
+        if (rb > (1u << 24)) rb = 1u << 24;
+        gs->rb = (uint32_t)rb;
     }
-    const uint64_t filter_bytes = ((uint64_t)B << gs->rb_shift) / 8, slice_bytes = ((uint64_t)bps << gs->rb_shift) / 8;
+    const uint64_t filter_bytes = (uint64_t)B * gs->rb / 8, slice_bytes = (uint64_t)bps * gs->rb / 8;
     const uint64_t slots = 4 * n_rows + 2;
     RFX_TRY(devbuf_reserve(c, c->ht, slots * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->g_bloom, filter_bytes + 64));
@@ -879,17 +911,39 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, gs->inbox, (size_t)world * gs->chan_cap * sizeof(SGReq<KT>)));
     RFX_TRY(devbuf_reserve(c, gs->respbox, (size_t)world * gs->chan_cap * sizeof(uint4)));
     RFX_TRY(devbuf_reserve(c, gs->req_cnt, 3 * RFX_MAX_RANKS * sizeof(unsigned long long)));
-    RFX_CUDA(c, cudaMemsetAsync(gs->req_cnt.p, 0, 3 * RFX_MAX_RANKS * sizeof(unsigned long long), st));
     c->ht_cap = slots; c->g_bins = 1; c->g_m = c->m; c->g_bloom_mask = 0;
-    RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
+
+    // everything is allocated: tell the others where (nothing behind these addresses is valid yet)
+    SGView V;
+    RFX_TRY(sg_publish(c, V, nullptr, 0, nullptr, all));
+    gs->n_rows_global = sg_sum(all, world, GP_NROWS);
+    prof.mark("reserve+publish1");
+    // own presence bits (+ the per-row minima) first: the peers pull them while this rank builds its index
+    RFX_CUDA(c, cudaMemsetAsync(gs->req_cnt.p, 0, 3 * RFX_MAX_RANKS * sizeof(unsigned long long), st));
     RFX_CUDA(c, cudaMemsetAsync(c->g_bloom.as<uint8_t>() + (size_t)c->sh_rank * slice_bytes, 0, slice_bytes, st));
+    if (n_rows) {
+        sg_row_minima_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(c->keys.as<KT>(), n_rows, c->k, c->m, B, (uint32_t)c->sh_rank * bps, (uint32_t)(c->sh_rank + 1) * bps,
+                                                                gs->rb, gs->rmin.as<uint4>(), c->g_bloom.as<uint32_t>(), dstat);
+        c->launches++;
+    }
+    if (world > 1) {
+        RFX_TRY(shard_barrier(c));  // every rank's presence bits are complete
+        RFX_CUDA(c, cudaEventRecord(c->copy_done[0], st));
+        RFX_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_done[0], 0));
+        for (int q = 1; q < world && slice_bytes; q++) {  // every rank starts with another peer
+            const int r = (c->sh_rank + q) % world;
+            RFX_CUDA(c, cudaMemcpyAsync(c->g_bloom.as<uint8_t>() + (size_t)r * slice_bytes, reinterpret_cast<const uint8_t*>(V.p[r].filter) + (size_t)r * slice_bytes, slice_bytes,
+                                        cudaMemcpyDefault, c->copy_stream));
+        }
+        RFX_CUDA(c, cudaEventRecord(c->copy_done[1], c->copy_stream));
+    }
+    prof.mark("filter_bits");
+    RFX_CUDA(c, cudaMemsetAsync(c->ht.p, 0xff, slots * sizeof(uint32_t), st));
     if (n_rows) {
         Graph<KT> G = make_graph<KT>(c);
         G.bloom_mask = 0;
         ht_build_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(G, nullptr);
-        sg_row_minima_kernel<KT><<<grid_n(n_rows), 256, 0, st>>>(c->keys.as<KT>(), n_rows, c->k, c->m, B, (uint32_t)c->sh_rank * bps, (uint32_t)(c->sh_rank + 1) * bps,
-                                                                gs->rb_shift, gs->rmin.as<uint4>(), c->g_bloom.as<uint32_t>(), dstat);
-        c->launches += 2;
+        c->launches++;
     }
     cudaMemsetAsync(c->succ.p, 0xff, nn * sizeof(uint32_t), st);
     cudaMemsetAsync(c->pred.p, 0xff, nn * sizeof(uint32_t), st);
@@ -898,19 +952,10 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     cudaMemsetAsync(c->loc.p, 0xff, nn * sizeof(uint64_t), st);
     cudaMemsetAsync(gs->l1_loc.p, 0xff, nn * sizeof(uint64_t), st);
     cudaMemsetAsync(c->alive.p, 0, nn + 8, st);
-
     prof.mark("memsets+index");
-    SGView V;
-    RFX_TRY(sg_publish(c, V, nullptr, 0, nullptr, all));  // [barrier] everybody's index and presence bits are complete
-    prof.mark("publish1");
-    gs->n_rows_global = sg_sum(all, world, GP_NROWS);
-    // presence bits of the peers' bins -> the same place in the local array
-    for (int r = 0; r < world; r++) {
-        if (r == c->sh_rank || !slice_bytes) continue;
-        RFX_CUDA(c, cudaMemcpyAsync(c->g_bloom.as<uint8_t>() + (size_t)r * slice_bytes, reinterpret_cast<const uint8_t*>(V.p[r].filter) + (size_t)r * slice_bytes, slice_bytes,
-                                    cudaMemcpyDefault, st));
-    }
-    prof.mark("filter_copy");
+    if (world > 1) RFX_CUDA(c, cudaStreamWaitEvent(st, c->copy_done[1], 0));  // the peers' presence bits have arrived
+    prof.mark("filter_wait");
+    // (the peers' indexes are first touched by the answering kernels, behind the barrier that follows the first pass)
     const int E = c->prm.min_error_coverage;
     const uint4* rmin = gs->rmin.as<uint4>();
     // every K5 stage: pass 1 over the own nodes (requests out), [barrier], the owners answer, [barrier], pass 2 over the nodes that waited
@@ -973,7 +1018,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     c->ms[3] += stage_end(c);
     prof.mark("budget+bar+sync");
     stage_begin(c);
-    if (n) sg_select_kernel<<<grid_n(n), 256, 0, st>>>(V, n, c->spl_node.as<uint32_t>(), gs->l2_l1.as<uint32_t>(), dstat);
+    if (n) sg_select_kernel<<<grid_n(n), 256, 0, st>>>(V, n, c->spl_id.as<uint32_t>(), c->spl_node.as<uint32_t>(), gs->l2_l1.as<uint32_t>(), dstat);
     c->launches++;
     {
         const int slots_dev[2] = {DS_NSPL, DS_NL2};
@@ -987,7 +1032,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     int rounds = 1;
     while ((1ull << rounds) < m2_all + 1) rounds++;
     rounds += 1;
-    if (m1) sg_l1_walk_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, c->spl_node.as<uint32_t>(), c->loc.as<uint64_t>());
+    if (m1) sg_l1_walk_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, c->spl_id.as<uint32_t>(), c->spl_node.as<uint32_t>(), c->loc.as<uint64_t>());
     prof.mark("l1_walk");
     RFX_TRY(shard_barrier(c));
     prof.mark("bar");
@@ -1060,6 +1105,7 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->ctg_left, (tot.a + 1) * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_right, (tot.a + 1) * sizeof(int32_t)));
     RFX_TRY(devbuf_reserve(c, c->ctg_bases, tot.b + 16));
+    RFX_CUDA(c, cudaMemsetAsync(c->ctg_bases.p, 0, tot.b + 16, st));  // the bases arrive as OR-ed words (sg_gather_kernel)
     if (n) {
         SContigOut out{c->eff_l.as<int32_t>(), gs->tail_rf.as<int32_t>(), c->ctg_idx.as<uint32_t>(), c->ctg_off.as<uint64_t>(), c->ctg_left.as<int32_t>(), c->ctg_right.as<int32_t>()};
         scan_apply(plan, in, out, OpAddU64x3{}, U64x3{0, 0, 0}, st);
@@ -1078,7 +1124,12 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     gs->n_oriented_global = sg_sum(all, world, GP_HOST + 2);
     prof.mark("scan_apply+publish5");
     if (m1) sg_l1_dst_kernel<<<grid_n(m1), 256, 0, st>>>(V, m1, gs->l1_fin.as<uint64_t>(), gs->l1_dst.as<unsigned long long>());
-    if (n) sg_gather_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, n, c->loc.as<uint64_t>(), gs->l1_dst.as<unsigned long long>());
+    {
+        const char* gv = getenv("RFX_GATHER");  // "nodes" / "segments": measured both ways (profiles/)
+        const bool by_segment = gv ? !strcmp(gv, "segments") : world > 2;
+        if (by_segment) { if (m1) sg_gather_kernel<KT><<<grid_n(m1), 128, 0, st>>>(V, m1, c->spl_node.as<uint32_t>(), gs->l1_dst.as<unsigned long long>()); }
+        else if (n) sg_gather_nodes_kernel<KT><<<grid_n(n), 256, 0, st>>>(V, n, c->loc.as<uint64_t>(), gs->l1_dst.as<unsigned long long>());
+    }
     c->launches += 2;
     RFX_TRY(shard_barrier(c));  // every base of the own contigs has arrived
     prof.mark("l1_dst+gather+bar");
