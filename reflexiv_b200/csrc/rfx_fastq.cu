@@ -146,6 +146,34 @@ __global__ void fq_state_update_kernel(const uint32_t* total_fn, unsigned long l
     *state = (*total_fn >> (3u * (uint32_t)*state)) & 7u;
 }
 
+// The common case of the state machine above: a chunk whose lines are whole 4-line records (header '@', sequence not '@',
+// two lines taken blindly), starting at whatever phase the carried lineMark says.  Then "which lines are reads" is i mod 4
+// and the scan of transition functions (two passes over the per-line arrays) is not needed.  The check is exact: any
+// line that breaks the layout sends the chunk down the general path.
+__global__ void fq_regular_check_kernel(const uint8_t* __restrict__ line_at, unsigned long long* dstat) {
+    const uint64_t n_lines = dstat[DS_FQ_NLINES];
+    const uint32_t s0 = (uint32_t)dstat[DS_FQ_STATE];
+    const uint32_t hdr = (s0 == 0u || s0 == 4u) ? 0u : (s0 == 1u ? 3u : (s0 == 2u ? 2u : 1u)), seq = (hdr + 1u) & 3u;
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t ph = (uint32_t)i & 3u;
+        const uint8_t at = line_at[i];
+        bad |= (ph == hdr && !at) || (ph == seq && at);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(&dstat[DS_FQ_IRREGULAR], 1ull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dstat[DS_FQ_SEQPOS] = seq;
+        // lineMark after the last line: header -> 1, sequence -> 2, then 3, 4
+        const uint32_t last = n_lines ? ((uint32_t)(n_lines - 1) + 4u - hdr) & 3u : 0u;
+        dstat[DS_FQ_NEXT] = n_lines ? last + 1u : s0;
+    }
+}
+__global__ void fq_regular_lines_kernel(Lines L, uint64_t n_known, uint32_t seq_pos, uint32_t* __restrict__ seq_eff, int k, int fc, int ec, unsigned long long* dstat) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.n_lines; i += (uint64_t)gridDim.x * blockDim.x)
+        seq_eff[i] = (((uint32_t)i & 3u) == seq_pos && i + 2 < n_known) ? effective_read_len((int64_t)L.len(i), k, fc, ec) : NOT_A_READ;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dstat[DS_FQ_STATE] = dstat[DS_FQ_NEXT];
+}
+
 __device__ __forceinline__ bool is_atcgn(uint8_t a) { return a == 'A' || a == 'T' || a == 'C' || a == 'G' || a == 'N'; }
 
 __global__ void flag_lines_kernel(Lines L, int mode, uint32_t* seq_eff, int k, int fc, int ec) {
@@ -214,51 +242,79 @@ __global__ void __launch_bounds__(256) read_totals_kernel(const uint32_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// warp-cooperative 2-bit encoder: a lane turns 4 ASCII bases into one byte with SIMD-in-register
-// compares, 8 lanes assemble a 64-bit word with xor shuffles, a warp writes 4 words per step.
+// warp-cooperative 2-bit encoder.  Half a warp owns one read: lane l loads the l-th 16-byte ALIGNED chunk of the text the
+// read lies in (one 128-bit load per lane, 16 bytes in flight per thread instead of 4), takes the four words of its
+// neighbour's chunk by shuffle and cuts its own 16 bases out of the eight words at the read's byte offset (word rotation
+// by selects, then funnel shifts).  Four SIMD-in-register compares turn 4 ASCII bases into one byte; two lanes make one
+// 64-bit word.  A round covers 224 bases (14 producing lanes + 1 that only feeds its neighbour).
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t encode4(uint32_t w) {  // 4 ASCII bases (first in the low byte) -> 8 bits, first base in bits 7..6
+    const uint32_t mA = __vcmpeq4(w, 0x41414141u), mC = __vcmpeq4(w, 0x43434343u), mG = __vcmpeq4(w, 0x47474747u);
+    const uint32_t codes = (~(mA | mC) & 0x02020202u) | (~(mA | mG) & 0x01010101u);
+    return (codes * 0x40100401u) >> 24;
+}
+struct EncRead {
+    uint32_t elen;
+    uintptr_t a0;   // address of the first base
+    uint64_t* dst;  // first packed word
+};
+__device__ __forceinline__ EncRead enc_read(const uint8_t* text, const uint64_t* rd_src, const uint32_t* rd_len, const uint64_t* rd_woff, uint64_t r, uint64_t n_new,
+                                            uint64_t read_base, uint64_t* packed) {
+    EncRead e{0u, (uintptr_t)text, packed};
+    if (r < n_new) {
+        e.elen = rd_len[read_base + r];
+        e.a0 = (uintptr_t)(text + rd_src[r]);
+        e.dst = packed + rd_woff[read_base + r];
+    }
+    return e;
+}
+__device__ __forceinline__ uint4 enc_load(const EncRead& e, int l, uint32_t round) {
+    const uintptr_t addr = (e.a0 & ~(uintptr_t)15) + 16u * (uintptr_t)((uint32_t)l + 14u * round);
+    return (l < 15 && addr < e.a0 + e.elen) ? *reinterpret_cast<const uint4*>(addr) : make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void enc_round(const EncRead& e, uint4 w, int l, uint32_t round) {
+    const uint32_t mis = (uint32_t)(e.a0 & 15), s = mis >> 2, sh = (mis & 3u) * 8u;
+    uint32_t W[8] = {w.x, w.y, w.z, w.w, 0u, 0u, 0u, 0u};
+    W[4] = __shfl_down_sync(0xffffffffu, w.x, 1, 16);
+    W[5] = __shfl_down_sync(0xffffffffu, w.y, 1, 16);
+    W[6] = __shfl_down_sync(0xffffffffu, w.z, 1, 16);
+    W[7] = __shfl_down_sync(0xffffffffu, w.w, 1, 16);
+    if (s & 1u) {  // W[t] <- W[t + s], t = 0..4
+#pragma unroll
+        for (int t = 0; t < 7; t++) W[t] = W[t + 1];
+    }
+    if (s & 2u) {
+#pragma unroll
+        for (int t = 0; t < 5; t++) W[t] = W[t + 2];
+    }
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) bits |= encode4(__funnelshift_r(W[j], W[j + 1], sh)) << (24 - 8 * j);
+    const uint32_t b0 = 16u * ((uint32_t)l + 14u * round);  // first base of this lane's window
+    const uint32_t nv = b0 < e.elen ? min(16u, e.elen - b0) : 0u;
+    bits = nv == 0u ? 0u : (bits & (0xffffffffu << (2u * (16u - nv))));  // clear the bases past the end of the read
+    const uint32_t partner = __shfl_down_sync(0xffffffffu, bits, 1, 16);
+    if (!(l & 1) && l < 14 && b0 < e.elen) e.dst[b0 >> 5] = ((uint64_t)bits << 32) | partner;
+}
 __global__ void __launch_bounds__(256) encode_reads_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ rd_src,
                                                             const uint32_t* __restrict__ rd_len, const uint64_t* __restrict__ rd_woff,
                                                             uint64_t n_new, uint64_t read_base, uint64_t* __restrict__ packed) {
-    // four reads per warp: an 8-lane group owns one read and produces one 64-bit word (8 lanes x 4 bases) per step
-    const int lane = threadIdx.x & 31, q = lane & 7, grp = lane >> 3;
+    const int lane = threadIdx.x & 31, l = lane & 15, half = lane >> 4;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    // four reads per warp and step, two per half: both table entries, then both text chunks are in flight before either is used
     for (uint64_t r0 = warp0 * 4; r0 < n_new; r0 += n_warps * 4) {
-        const uint64_t r = r0 + grp;
-        uint32_t elen = 0;
-        uint64_t src = 0;
-        uint64_t* dst = packed;
-        if (r < n_new) {
-            elen = rd_len[read_base + r];
-            src = rd_src[r];
-            dst = packed + rd_woff[read_base + r];
-        }
-        const uint32_t n_words = (elen + 31u) >> 5;
-        uint32_t max_words = n_words;  // warp-uniform trip count: the shuffles below need every lane
-        max_words = max(max_words, __shfl_xor_sync(0xffffffffu, max_words, 8));
-        max_words = max(max_words, __shfl_xor_sync(0xffffffffu, max_words, 16));
-        for (uint32_t wi = 0; wi < max_words; wi++) {
-            const uint32_t b0 = wi * 32u + 4u * (uint32_t)q;
-            uint32_t cb = 0;
-            if (b0 < elen) {
-                const uint32_t nvalid = min(4u, elen - b0);
-                const uintptr_t a = (uintptr_t)(text + src + b0);
-                const uint32_t* p32 = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-                const uint32_t mis = (uint32_t)(a & 3);
-                const uint32_t lo = p32[0];
-                const uint32_t hi = (mis + nvalid > 4u) ? p32[1] : 0u;
-                const uint32_t w = __funnelshift_r(lo, hi, mis * 8u);  // bytes a..a+3, first base in the low byte
-                const uint32_t mA = __vcmpeq4(w, 0x41414141u), mC = __vcmpeq4(w, 0x43434343u), mG = __vcmpeq4(w, 0x47474747u);
-                const uint32_t codes = (~(mA | mC) & 0x02020202u) | (~(mA | mG) & 0x01010101u);
-                cb = (codes * 0x40100401u) >> 24;            // first base -> bits 7..6
-                cb &= (0xff00u >> (2u * nvalid)) & 0xffu;    // clear the bases past the end of the read
-            }
-            uint64_t word = (uint64_t)cb << (56 - 8 * q);
-            word |= __shfl_xor_sync(0xffffffffu, word, 1);
-            word |= __shfl_xor_sync(0xffffffffu, word, 2);
-            word |= __shfl_xor_sync(0xffffffffu, word, 4);
-            if (q == 0 && wi < n_words) dst[wi] = word;
+        const EncRead A = enc_read(text, rd_src, rd_len, rd_woff, r0 + half, n_new, read_base, packed);
+        const EncRead B = enc_read(text, rd_src, rd_len, rd_woff, r0 + 2 + half, n_new, read_base, packed);
+        const uint4 wa = enc_load(A, l, 0), wb = enc_load(B, l, 0);
+        uint32_t rounds = (max(A.elen, B.elen) + 223u) / 224u;
+        rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, 16));  // warp-uniform trip count: the shuffles need every lane
+        enc_round(A, wa, l, 0);
+        enc_round(B, wb, l, 0);
+        for (uint32_t round = 1; round < rounds; round++) {  // reads longer than 224 bases
+            const uint4 xa = enc_load(A, l, round), xb = enc_load(B, l, round);
+            enc_round(A, xa, l, round);
+            enc_round(B, xb, l, round);
         }
     }
 }
@@ -347,18 +403,29 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     uint64_t* ls = c->line_start.as<uint64_t>();
     uint8_t* lat = c->line_at.as<uint8_t>();
     scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, d_text, ls, lat}, OpAddU64{}, (uint64_t)0, st);
-    finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, lat, c->dstat.as<uint64_t>() + DS_NSLOTS - 1);
+    finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, lat, c->dstat.as<uint64_t>() + DS_FQ_NLINES);
     c->launches += 2;
-    uint64_t n_lines = 0;
-    RFX_CUDA(c, cudaMemcpyAsync(&n_lines, c->dstat.as<uint64_t>() + DS_NSLOTS - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    const bool try_regular = c->prm.fastq_mode == RFX_FASTQ_RUN && !getenv("RFX_FASTQ_GENERAL");  // (tests force the general path)
+    if (try_regular) {
+        RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_FQ_IRREGULAR, 0, sizeof(uint64_t), st));
+        fq_regular_check_kernel<<<sm_count() * 8, 256, 0, st>>>(lat, c->dstat.as<unsigned long long>());
+        c->launches++;
+    }
+    uint64_t fq[4] = {0, 0, 0, 0};  // lines, irregular?, position of the sequence lines, lineMark behind the chunk
+    RFX_CUDA(c, cudaMemcpyAsync(fq, c->dstat.as<uint64_t>() + DS_FQ_NLINES, (try_regular ? 4 : 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     RFX_CUDA(c, cudaStreamSynchronize(st));
+    const uint64_t n_lines = fq[0];
     if (n_lines == 0) { c->ms[0] += stage_end(c); return RFX_OK; }
 
     // 2. which lines are reads
     Lines L{d_text, ls, n_lines, 1u};
     RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
     const uint32_t* flags = c->seq_flag.as<uint32_t>();
-    if (c->prm.fastq_mode == RFX_FASTQ_RUN) {
+    if (try_regular && !fq[1]) {
+        fq_regular_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2], c->seq_flag.as<uint32_t>(), c->k,
+                                                                       c->prm.front_clip, c->prm.end_clip, c->dstat.as<unsigned long long>());
+        c->launches++;
+    } else if (c->prm.fastq_mode == RFX_FASTQ_RUN) {
         ScanPlan<uint32_t> fs;
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
         fs.bind(n_lines, c->scan_ws.as<uint32_t>());

@@ -220,7 +220,11 @@ enum {
     DS_REMOTE = 33,       // neighbour probes answered from a peer's index
     DS_SG_CYCLE = 34,
     DS_WORK = 35,         // 3 slots: nodes the first pass of a sharded K5 kernel put off (their probe goes to a peer)     // a closed path was seen
-    DS_NSLOTS = 40
+    DS_FQ_NLINES = 39,    // 4 slots read back together by rfx_fastq.cu: lines of the chunk, violations of the regular 4-line layout,
+    DS_FQ_IRREGULAR = 40, //   position (mod 4) of the sequence lines, lineMark behind the chunk if the layout is regular
+    DS_FQ_SEQPOS = 41,
+    DS_FQ_NEXT = 42,
+    DS_NSLOTS = 48
 };
 
 static const uint32_t NONE32 = 0xffffffffu;

@@ -108,6 +108,24 @@ def test_chunked_upload_carries_the_fastq_state(R, orc, hooks, example_text, mon
     assert g_ints == ints and np.array_equal(g_counts, counts)
 
 
+def test_regular_layout_shortcut_and_general_state_machine_agree(R, orc, hooks, example_text, monkeypatch):
+    """K1 takes a shortcut when a chunk is made of whole 4-line records (reads = every fourth line, at the phase the carried
+    lineMark gives) and runs the scan of transition functions otherwise.  Same read table either way, with chunk cuts at
+    every phase; a single stray line flips the chunk to the general path without changing the answer."""
+    stray = example_text[:50_000] + b"stray line\n" + example_text[50_000:]
+    for txt in (example_text, stray):
+        s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
+        want = np.where(l.astype(np.int64) - 31 > 1, l, 0).astype(np.uint32)
+        for chunk in ("", "2777", "50021"):
+            for general in ("", "1"):
+                monkeypatch.setenv("RFX_FASTQ_CHUNK_BYTES", chunk) if chunk else monkeypatch.delenv("RFX_FASTQ_CHUNK_BYTES", raising=False)
+                monkeypatch.setenv("RFX_FASTQ_GENERAL", general) if general else monkeypatch.delenv("RFX_FASTQ_GENERAL", raising=False)
+                with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1)) as ctx:
+                    ctx.push_fastq(txt)
+                    g_len, _, _ = hooks.reads(ctx)
+                assert np.array_equal(g_len, want), (len(txt), chunk, general)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # K2: super-k-mer records
 # ---------------------------------------------------------------------------------------------------------
@@ -212,6 +230,62 @@ def test_bin_overflow_splitting_is_exact(R, orc):
         g_ints, g_counts = _sorted_table(R, ctx, 61)
     assert st["n_bin_splits"] > 0
     assert g_ints == ints and np.array_equal(g_counts, counts)
+
+
+def test_repeated_runs_are_bit_identical(R, orc, monkeypatch):
+    """compute-sanitizer is closed on the GPU pool (profiles/r2_sanitizer.txt); a race in the counting kernel's shared-memory
+    machinery or in the request / answer exchange of the sharded graph stages would show as a run that differs.  Twenty runs
+    of a split-forcing input on one context, twenty sharded runs of two ranks on one device: one digest each."""
+    import hashlib
+    from reflexiv_b200 import sharded
+    from reflexiv_b200.pipeline import keys_to_int
+    txt = bytes(make_reads(23, 60_000, 4000, read_len=150, err=0.01, frag=400))
+    ref = orc.run_pipeline(txt, k=31, cover=1, min_contig=100)
+    want_rows = len(ref["counts"]["counts"])
+    want_contigs = sorted(ref["asm"]["contigs"])
+
+    def digest(tables, contigs):
+        rows = sorted(kv for keys, cnt in tables for kv in zip(keys_to_int(keys, 31), cnt.tolist()))
+        return hashlib.sha256(repr((rows, sorted(contigs))).encode()).hexdigest(), len(rows)
+
+    monkeypatch.setenv("RFX_COUNT_VARIANT", "small")
+    seen = set()
+    with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1, minContig=100), bin_target_kmers=200_000) as ctx:
+        for _ in range(20):
+            ctx.reset()
+            ctx.push_fastq(txt)
+            st = ctx.count()
+            assert st["n_bin_splits"] > 0
+            tab = ctx.counts()
+            ctx.assemble()
+            d, n = digest([tab], [s for s, _, _ in ctx.contigs()])
+            assert n == want_rows
+            seen.add(d)
+    assert len(seen) == 1
+    monkeypatch.delenv("RFX_COUNT_VARIANT")
+    cut = txt.find(b"\n@r", len(txt) // 2) + 1
+    parts = [txt[:cut], txt[cut:]]
+    ctxs = [R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=1, minContig=100)) for _ in range(2)]
+    try:
+        grp = sharded.LocalRanks(ctxs, arena_bytes=1 << 30)
+        for _ in range(20):
+            out = [None, None]
+
+            def body(r, c):
+                c.reset()
+                c.push_fastq(parts[r])
+                c.count_sharded()
+                tab = c.counts()
+                c.assemble_sharded()
+                out[r] = (tab, [s for s, _, _ in c.contigs()])
+            grp.run(body)
+            d, n = digest([o[0] for o in out], [s for o in out for s in o[1]])
+            assert n == want_rows and sorted(s for o in out for s in o[1]) == want_contigs
+            seen.add(d)
+    finally:
+        for c in ctxs:
+            c.close()
+    assert len(seen) == 1  # ... and the sharded runs give the very digest of the single-context runs
 
 
 @pytest.mark.parametrize("k", [31, 61])

@@ -1,6 +1,7 @@
-"""Large-input checks: size-independent properties only, the oracle is too slow here.  RFX_SCALE_TEST=<million reads>
-sets the size: the default `pytest -m gpu` run uses 4 (1.3 GB of text, a few seconds); 16 crosses 4 GiB of text and
-tens of millions of lines; RFX_SCALE_TEST=0 skips."""
+"""BASELINE-size inputs.  (1) Size-independent properties on RFX_SCALE_TEST=<million reads> (default 4: 1.3 GB of text, a few
+seconds; 16 crosses 4 GiB of text and tens of millions of lines).  (2) The oracle itself, on all host threads, at the full
+size of configs[1] and on a scaled configs[3]: count table, fork-filter survivors, contigs and flags bit for bit.
+RFX_SCALE_TEST=0 skips the file."""
 import os
 
 import numpy as np
@@ -53,3 +54,73 @@ def test_large_input_properties(orc):
         c = min(v, rc)
         i = np.searchsorted(keys, np.uint64(c))
         assert i < len(keys) and int(keys[i]) == c
+
+
+def _sorted_table(keys, cnt, k):
+    """(keys as (hi, lo) uint64 columns of the right-aligned 2k-bit value, counts) sorted by key.  The C ABI hands out the
+    reference's key layout: one word for k <= 31, else (leading bases, last k % 32 bases) -- pipeline.keys_to_int."""
+    k2 = keys.reshape(len(cnt), -1)
+    if k <= 31:
+        hi, lo = np.zeros(len(cnt), np.uint64), k2[:, 0]
+    else:
+        sh = np.uint64(2 * (k % 32))
+        hi = k2[:, 0] >> (np.uint64(64) - sh)
+        lo = (k2[:, 0] << sh) | k2[:, 1]
+    order = np.lexsort((lo, hi))
+    return hi[order], lo[order], cnt[order]
+
+
+def _full_size_against_oracle(orc, txt, k, cover, min_contig):
+    """The library against the oracle on a BASELINE-size input: the whole count table row by row, the fork-filter survivors
+    with both flags, the contigs with their header flags, the statistics.  The oracle runs on all host threads."""
+    import reflexiv_b200 as R
+    threads = os.cpu_count() or 1
+    orc.set_threads(threads)
+    try:
+        starts, lens = orc.fastq_reads(txt, orc.FASTQ_RUN)
+        c = orc.count_kmers(txt, starts, lens, k, 0, 0, cover, 10_000_000, threads)
+        f = orc.fork_filter(c["keys_hi"], c["keys_lo"], c["counts"], k, 8)
+        a = orc.assemble(f["keys_hi"], f["keys_lo"], f["left"], f["right"], k, min_contig, orc.ASM_CANONICAL)
+    finally:
+        orc.set_threads(1)
+    with R.ReflexivContext(R.DefaultParam(kmerSize=k, minKmerCoverage=cover, minContig=min_contig)) as ctx:
+        ctx.push_fastq(txt)
+        st = ctx.count()
+        hi, lo, cnt = _sorted_table(*ctx.counts(), k)
+        assert st["n_instances"] == c["n_instances"] and st["n_rows"] == len(c["counts"])
+        assert np.array_equal(hi, c["keys_hi"]) and np.array_equal(lo, c["keys_lo"]) and np.array_equal(cnt, c["counts"])
+        st = ctx.assemble()
+        ohi, olo, ole, ori = ctx.oriented()
+        order = np.lexsort((olo, ohi))
+        assert np.array_equal(ohi[order], f["keys_hi"]) and np.array_equal(olo[order], f["keys_lo"])
+        assert np.array_equal(ole[order], f["left"]) and np.array_equal(ori[order], f["right"])
+        got = sorted((s, l, r) for s, l, r in ctx.contigs())
+    exp = sorted(zip(a["contigs"], a["left"].tolist(), a["right"].tolist()))
+    assert len(got) == len(exp)
+    assert got == exp
+    assert (st["n_budget_junctions"], st["n_budget_admissible"], st["n_cycles"]) == (a["n_budget_junctions"], a["n_budget_admissible"], a["n_cycles"])
+    return st, a
+
+
+@pytest.mark.skipif(MREADS <= 0, reason="RFX_SCALE_TEST=0")
+def test_config2_in_full_against_the_oracle(orc):
+    """BASELINE configs[1] at its full size: 4.6 Mbp genome, 3 066 668 x 150 bp reads at 100x, k = 31, cover 2 -- the input of
+    the bench -- bit for bit against the oracle (about 10 s of host time on 16 threads)."""
+    import bench
+    wl = bench.Workload(2, 1)
+    txt = wl.text(0)
+    st, a = _full_size_against_oracle(orc, txt, 31, 2, 500)
+    assert st["n_rows"] > 4_590_000 and st["n_contigs"] == 2 and a["n_budget_junctions"] == 0
+
+
+@pytest.mark.skipif(MREADS <= 0, reason="RFX_SCALE_TEST=0")
+def test_config4_scaled_against_the_oracle(orc):
+    """BASELINE configs[3] (k = 61, 1 % substitution errors, cover 2, 30x) on a 5 Mbp genome instead of 100 Mbp: two-word keys,
+    noisy reads (most distinct k-mers are singletons that the coverage filter drops), real forks where errors collide."""
+    from workload import synth
+    G = 5_000_000
+    g = synth.genome(G, 4242)
+    g[1_000_000:1_003_000] = g[3_000_000:3_003_000]  # a 3 kb repeat: fork winners and budget junctions at this size as well
+    txt = synth.fastq(g, synth.n_pairs_for(G, 30.0, 150), read_len=150, frag_len=400, error_rate=0.01)
+    st, a = _full_size_against_oracle(orc, txt, 61, 2, 500)
+    assert st["n_rows"] > 4_000_000 and st["n_contigs"] >= 2
