@@ -243,10 +243,11 @@ __global__ void __launch_bounds__(PART_THREADS)
 // The m-mers of a read are taken in blocks of W = K - M + 1 (van Herk / Gil-Werman): 32 bases starting at the block
 // are funnelled into one 64-bit window, so every base, shift and mask inside the fully unrolled block is an
 // immediate; the block's W hashes stay in registers until its suffix minima are formed at the block end, and the
-// minimum of a k-mer's window is min(prefix minimum of this block, suffix minimum of the previous block).  A warp takes
-// this path when its 32 reads have the same length (one position schedule for all lanes, no per-base predicates);
-// any other warp marks its reads SCAN_TODO and the general kernel above picks them up.  Results are bit-identical
-// to bin_scan_read() (rfx_core.h).
+// minimum of a k-mer's window is min(prefix minimum of this block, suffix minimum of the previous block).  The 32 reads
+// of a warp share one position schedule, the one of the LONGEST of them: a shorter read (quality-trimmed data) walks along
+// to the end -- its window loads are clamped to its own words -- and simply stops queueing minimiser changes behind its
+// last k-mer, so ragged warps stay on this path at the price of the padding (reads of 100..150 bases: 17 %).  Only reads
+// beyond 60 000 bases go to the general kernel above (SCAN_TODO).  Results are bit-identical to bin_scan_read() (rfx_core.h).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int FAST_Q = 40;  // queued minimiser changes per read between two drains (a block adds at most W)
 
@@ -254,6 +255,7 @@ template <int M, int W> struct FastScan {
     uint32_t mfl, mr;        // rolling m-mer: forward left-aligned in the top 2M bits, reverse complement right-aligned
     uint32_t sfx[W + 1];     // suffix minima of the previous block, sfx[W] = +inf
     uint32_t prev_h, qn;
+    uint32_t nk;             // k-mers of THIS lane's read: changes at or behind it are not queued
     uint32_t* qh;            // [FAST_Q][PART_THREADS] lane-interleaved
     uint16_t* qp;
 
@@ -276,7 +278,7 @@ template <int M, int W> struct FastScan {
             if (MODE != 0 || p == W - 1) {
                 uint32_t hmin = pre;
                 if (p != W - 1) hmin = sfx[p + 1] < hmin ? sfx[p + 1] : hmin;
-                if (MODE == 0 || hmin != prev_h) {  // minimiser changed (or first k-mer): remember where, decide later
+                if ((MODE == 0 || hmin != prev_h) && i0 + (uint32_t)p < nk) {  // minimiser changed (or first k-mer): remember where, decide later
                     prev_h = hmin;
                     qh[qn * PART_THREADS] = hmin;
                     qp[qn * PART_THREADS] = (uint16_t)(i0 + (uint32_t)p);
@@ -305,10 +307,16 @@ __global__ void __launch_bounds__(PART_THREADS, 7)  // 72 registers: seven block
         const bool valid = r < n_reads;
         if (!__any_sync(0xffffffffu, valid)) continue;  // (valid lanes are a prefix of the warp: lane 0 is one of them)
         const uint32_t len = valid ? rd_len[r] : 0u;
-        const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
-        if (!__all_sync(0xffffffffu, !valid || len == len0) || len0 < (uint32_t)K || len0 > 60000u) {
+        uint32_t len0 = len;  // the longest read of the warp sets the schedule
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) len0 = max(len0, __shfl_xor_sync(0xffffffffu, len0, d));
+        if (len0 > 60000u) {
             if (valid) rd_runs[r] = SCAN_TODO;
             if ((threadIdx.x & 31) == 0) atomicExch(&dstat[DS_SCAN_TODO], 1ull);
+            continue;
+        }
+        if (len0 < (uint32_t)K) {  // no k-mer in any of the 32 reads
+            if (valid) rd_runs[r] = 0u;
             continue;
         }
         // the lanes behind the last read walk lane 0's read along (same schedule, nothing emitted)
@@ -318,7 +326,10 @@ __global__ void __launch_bounds__(PART_THREADS, 7)  // 72 registers: seven block
         RunState rst{0u, 0u, false};
         FastScan<M, W> S;
         S.mfl = 0; S.mr = 0; S.prev_h = 0; S.qn = 0;
+        S.nk = len >= (uint32_t)K ? len - (uint32_t)K + 1u : 0u;
         S.qh = s_qh + threadIdx.x; S.qp = s_qp + threadIdx.x;
+        const uint64_t last_pos = (uint64_t)len;  // window loads never leave the read's own words (+ the one behind them)
+        auto window = [&](uint64_t pos) { return packed_window(rd, pos < last_pos ? pos : last_pos); };
 #pragma unroll
         for (int t = 0; t <= W; t++) S.sfx[t] = 0xffffffffu;
         // the whole warp drains its queues together: bin lookup, run cutting and record emission run with most lanes busy
@@ -349,12 +360,12 @@ __global__ void __launch_bounds__(PART_THREADS, 7)  // 72 registers: seven block
         const uint32_t n_full = n_mmers / (uint32_t)W, rem = n_mmers % (uint32_t)W;
         // the 64-bit base window of block b + 1 is requested before block b is worked on: its latency (the first touch of
         // a read's words misses L1) hides behind ~500 instructions instead of stalling the warp at every block start
-        uint64_t win = packed_window(rd, (uint64_t)(M - 1));
-        uint64_t win_next = (n_full > 1 || rem) ? packed_window(rd, (uint64_t)(M - 1) + (uint64_t)W) : 0ull;
+        uint64_t win = window((uint64_t)(M - 1));
+        uint64_t win_next = (n_full > 1 || rem) ? window((uint64_t)(M - 1) + (uint64_t)W) : 0ull;
         S.template block<0>(win, 0u - (uint32_t)(W - 1), W);
         for (uint32_t b = 1; b < n_full; b++) {
             win = win_next;
-            if (b + 1 < n_full || rem) win_next = packed_window(rd, (uint64_t)(M - 1) + (uint64_t)(b + 1) * W);
+            if (b + 1 < n_full || rem) win_next = window((uint64_t)(M - 1) + (uint64_t)(b + 1) * W);
             S.template block<1>(win, b * W - (uint32_t)(W - 1), W);
             if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
         }
@@ -362,7 +373,7 @@ __global__ void __launch_bounds__(PART_THREADS, 7)  // 72 registers: seven block
             if (__any_sync(0xffffffffu, S.qn > (uint32_t)(FAST_Q - W))) drain(false, 0u);
             S.template block<2>(win_next, n_full * W - (uint32_t)(W - 1), (int)rem);
         }
-        drain(true, len0 - (uint32_t)K + 1u);
+        drain(true, S.nk);
         if (!valid) continue;
         if (Factory::kNeedsRuns) {
             const bool spill = em.n > em.stored;
