@@ -97,7 +97,27 @@ struct InputFile {
     }
 };
 
+// Hadoop's LineRecordReader (the reference's text source) ends a line at "\n", "\r\n" and at a lone "\r".  The library
+// takes "\n" and "\r\n"; a file with classic-Mac line ends would silently parse as one long line, so it is refused.
+// Looked for in the first 64 KB (a line-end convention holds for a whole file).
+static bool has_lone_cr(const char* d, size_t n) {
+    if (n > 65536) n = 65536;
+    for (size_t i = 0; i + 1 < n; i++)
+        if (d[i] == '\r' && d[i + 1] != '\n') return true;
+    return false;
+}
+static bool load_file_raw(InputFile& f);
 static bool load_file(InputFile& f) {
+    if (!load_file_raw(f)) return false;
+    const char* d = f.map ? f.map : f.data.data();
+    const size_t n = f.map ? f.map_len : f.data.size();
+    if (n && has_lone_cr(d, n)) {
+        fprintf(stderr, "%s: lone '\\r' line ends (classic Mac text) are not supported; convert with tr '\\r' '\\n'\n", f.path.c_str());
+        return false;
+    }
+    return true;
+}
+static bool load_file_raw(InputFile& f) {
     if (ends_with(f.path, ".4mc")) {
         fprintf(stderr, "%s: 4mc input needs hadoop-4mc; decompress first or use gzip / plain text\n", f.path.c_str());
         return false;

@@ -384,9 +384,15 @@ def _read_one(path: str) -> bytes:
         raise RfxError(_lib.RFX_E_UNSUPPORTED, f"{path}: 4mc input needs hadoop-4mc; decompress first or use gzip/plain text")
     if path.endswith(".gz"):
         with gzip.open(path, "rb") as f:
-            return f.read()
-    with open(path, "rb") as f:
-        return f.read()
+            data = f.read()
+    else:
+        with open(path, "rb") as f:
+            data = f.read()
+    # Hadoop's LineRecordReader also ends a line at a lone "\r"; the library takes "\n" and "\r\n" only (csrc/reflexiv_main.cpp)
+    head = data[:65536]
+    if any(head[i:i + 1] == b"\r" and head[i + 1:i + 2] != b"\n" for i in range(len(head) - 1) if head[i] == 13):
+        raise RfxError(_lib.RFX_E_UNSUPPORTED, f"{path}: lone '\\r' line ends (classic Mac text) are not supported; convert with tr '\\r' '\\n'")
+    return data
 
 
 def parse_count_csv(text: bytes, k: int) -> Tuple[np.ndarray, np.ndarray]:

@@ -109,6 +109,13 @@ def test_python_mirror_reads_the_same_way(example_text, tmp_path):
     assert read_input_text(str(ind / "part*")) == example_text
     with pytest.raises(FileNotFoundError):
         read_input_text(str(tmp_path / "none*"))
+    # classic-Mac line ends would parse as one long line (Hadoop's reader splits at a lone "\\r"): refused, "\\r\\n" is fine
+    (tmp_path / "mac.fq").write_bytes(example_text[:5000].replace(b"\n", b"\r"))
+    (tmp_path / "dos.fq").write_bytes(example_text[:5000].replace(b"\n", b"\r\n"))
+    from reflexiv_b200 import RfxError
+    with pytest.raises(RfxError):
+        read_input_text(str(tmp_path / "mac.fq"))
+    assert read_input_text(str(tmp_path / "dos.fq")).count(b"\r\n") == example_text[:5000].count(b"\n")
 
 
 def test_count_table_parser(harness, tmp_path):

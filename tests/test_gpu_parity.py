@@ -108,6 +108,21 @@ def test_chunked_upload_carries_the_fastq_state(R, orc, hooks, example_text, mon
     assert g_ints == ints and np.array_equal(g_counts, counts)
 
 
+def test_dos_line_ends(R, example_text, golden):
+    """"\\r\\n" line ends give the table of the Unix file (K1 strips the "\\r" like Hadoop's LineRecordReader), in both FASTQ modes."""
+    dos = example_text.replace(b"\n", b"\r\n")
+    for counter_mode in (False, True):
+        rows = []
+        for txt in (example_text, dos):
+            with R.ReflexivContext(_param(R, kmerSize=31, minKmerCoverage=2), counter_mode=counter_mode) as ctx:
+                ctx.push_fastq(txt)
+                ctx.count()
+                rows.append(sorted(ctx.counts_csv().decode().splitlines()))
+        assert rows[0] == rows[1]
+        if not counter_mode:
+            assert hashlib.sha256(("\n".join(rows[1]) + "\n").encode()).hexdigest() == golden["oracle"]["count_ge2"]["sha256_sorted_csv"]
+
+
 def test_regular_layout_shortcut_and_general_state_machine_agree(R, orc, hooks, example_text, monkeypatch):
     """K1 takes a shortcut when a chunk is made of whole 4-line records (reads = every fourth line, at the phase the carried
     lineMark gives) and runs the scan of transition functions otherwise.  Same read table either way, with chunk cuts at
