@@ -214,7 +214,10 @@ int rfx_load_counts_device(rfx_ctx* ctx, const void* d_keys, const uint32_t* d_c
  *   every rank:  rfx_shard_init -> rfx_shard_export -> [caller gathers the world * RFX_SHARD_HANDLE_BYTES bytes] ->
  *                rfx_shard_connect -> { rfx_reset, rfx_push_fastq*, rfx_count_sharded, rfx_assemble_sharded, results }*
  * rfx_count_sharded / rfx_assemble_sharded are collective: every rank must call them (from its own host thread or
- * process); they meet in cross-GPU barriers and fail with RFX_E_STATE if a peer never arrives.
+ * process); they meet in cross-GPU barriers and fail with RFX_E_STATE if a peer never arrives.  Ranks that share a device
+ * inside one process meet on the host instead and need CUDA_MODULE_LOADING=EAGER in the environment (no kernel may be
+ * loaded lazily while a peer on the same device waits).  rfx_assemble_sharded needs the table rfx_count_sharded left (rows
+ * sharded by minimiser bin); a table loaded with rfx_load_counts is assembled with rfx_assemble.
  * On return from rfx_count_sharded the context holds its shard of the global table (the rows whose minimiser bin it
  * owns; rfx_counts_* work on it); after rfx_assemble_sharded it holds the contigs whose first k-mer it owns
  * (rfx_contigs_* work on them): the union over the ranks is the result of the single-GPU calls. */
@@ -226,7 +229,7 @@ typedef struct {
     uint64_t n_instances_global;  /* k-mer instances extracted by all ranks */
     uint64_t n_shard_instances;   /* ... that fell into this rank's bins */
     uint64_t n_rows_global, n_oriented_global, n_contigs_global, n_contig_bases_global;
-    uint64_t n_remote_probes;     /* neighbour probes answered from a peer's index */
+    uint64_t n_remote_probes;     /* neighbour requests of peers this rank answered from its index (last rfx_assemble_sharded) */
     uint64_t n_l1_splitters, n_l2_splitters;
     float ms_comm;                /* barriers + value exchanges of the last sharded calls */
     int32_t fell_back;            /* last rfx_assemble_sharded met a closed path: rank 0 assembled the whole table */
