@@ -609,6 +609,158 @@ __global__ void __launch_bounds__(NT + 32, PER_SM) count_bins_kernel(CountArgs A
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The measured alternative (north_star: "hash table or radix / sort + run-length, picked by measurement"): count a bin by
+// SORTING.  One CTA per bin ticket: the k-mers of the bin's super-k-mer records are expanded into shared memory (one
+// shared-memory atomic per record claims its range), sorted by a bitonic network, and equal neighbours are run-length counted;
+// rows inside the coverage bounds go out through one global atomic per warp.  No table, no probing, no tag collisions, no
+// splitting: a bin with more k-mers than the array holds is done in P passes over its records, pass p keeping the k-mers of
+// hash class p (class sizes are measured first, P doubles until every class fits).  Work per bin is O(T log^2 T) whatever
+// the data look like -- against the hash kernel's O(T) on clean reads (where equal super-k-mers collapse before a k-mer is
+// touched) and its probing / splitting cost on noisy ones, where every second instance is a k-mer of its own.
+// ---------------------------------------------------------------------------------------------------------------------------
+template <bool WIDE, int CAPS, int NT>
+__global__ void __launch_bounds__(NT) sort_bins_kernel(CountArgs A) {
+    using KT = typename std::conditional<WIDE, u128, uint64_t>::type;
+    constexpr int RECW = WIDE ? 4 : 2;
+    constexpr int MAXP = 64;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KT* skey = reinterpret_cast<KT*>(smem_raw);  // [CAPS]
+    __shared__ uint32_t s_fill, s_total, s_bin, s_hist[MAXP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = A.k;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long t = atomicAdd(&A.dstat[DS_TICKET], 1ull);
+            s_bin = t < (unsigned long long)A.n_tickets ? (uint32_t)t * A.bin_stride : BIN_END;
+            s_total = 0;
+        }
+        __syncthreads();
+        const uint32_t bin = s_bin;
+        if (bin == BIN_END) break;
+        // k-mer instances of the bin
+        uint32_t mine = 0;
+        for (int sg = 0; sg < A.n_seg; sg++) {
+            const SegExt e = A.ext[(size_t)sg * A.n_bins + bin];
+            const uint64_t* rec = reinterpret_cast<const uint64_t*>(e.addr);
+            for (uint32_t i = tid; i < e.cnt; i += NT) mine += (uint32_t)(rec[(size_t)i * RECW] >> 48);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+        if (lane == 0 && mine) atomicAdd(&s_total, mine);
+        __syncthreads();
+        const uint32_t T = s_total;
+        if (T == 0) continue;
+        if (tid == 0) atomicAdd(&A.dstat[DS_INSTANCES], (unsigned long long)T);
+        // passes: one if everything fits, else hash classes whose sizes are measured before anything is written
+        uint32_t P = 1;
+        if (T > (uint32_t)CAPS) {
+            P = 2;
+            while ((uint64_t)P * (uint64_t)(CAPS * 3 / 4) < (uint64_t)T && P < (uint32_t)MAXP) P <<= 1;
+            while (true) {
+                __syncthreads();
+                if (tid < MAXP) s_hist[tid] = 0;
+                __syncthreads();
+                for (int sg = 0; sg < A.n_seg; sg++) {
+                    const SegExt e = A.ext[(size_t)sg * A.n_bins + bin];
+                    const uint64_t* rec = reinterpret_cast<const uint64_t*>(e.addr);
+                    for (uint32_t i = tid; i < e.cnt; i += NT)
+                        rec_foreach_kmer<KT, RECW>(rec + (size_t)i * RECW, k, [&](KT key) { atomicAdd(&s_hist[(uint32_t)(key_hash(key) >> 40) & (P - 1u)], 1u); });
+                }
+                __syncthreads();
+                bool fits = true;
+                for (uint32_t q = 0; q < P; q++) fits = fits && s_hist[q] <= (uint32_t)CAPS;
+                if (fits) break;
+                if (P >= (uint32_t)MAXP) { if (tid == 0) atomicExch(&A.dstat[DS_OVERFLOW], 2ull); break; }  // (one k-mer more than CAPS times in a class of 1/64: not with real data)
+                P <<= 1;
+            }
+            if (tid == 0) atomicAdd(&A.dstat[DS_SPLITS], 1ull);
+        }
+        for (uint32_t p = 0; p < P; p++) {
+            __syncthreads();
+            if (tid == 0) s_fill = 0;
+            __syncthreads();
+            for (int sg = 0; sg < A.n_seg; sg++) {
+                const SegExt e = A.ext[(size_t)sg * A.n_bins + bin];
+                const uint64_t* rec = reinterpret_cast<const uint64_t*>(e.addr);
+                for (uint32_t i = tid; i < e.cnt; i += NT) {
+                    const uint64_t* r = rec + (size_t)i * RECW;
+                    if (P == 1) {
+                        uint32_t at = atomicAdd(&s_fill, (uint32_t)(r[0] >> 48));
+                        rec_foreach_kmer<KT, RECW>(r, k, [&](KT key) { if (at < (uint32_t)CAPS) skey[at] = key; at++; });
+                    } else {
+                        rec_foreach_kmer<KT, RECW>(r, k, [&](KT key) {
+                            if (((uint32_t)(key_hash(key) >> 40) & (P - 1u)) == p) {
+                                const uint32_t at = atomicAdd(&s_fill, 1u);
+                                if (at < (uint32_t)CAPS) skey[at] = key;
+                            }
+                        });
+                    }
+                }
+            }
+            __syncthreads();
+            const uint32_t n = s_fill < (uint32_t)CAPS ? s_fill : (uint32_t)CAPS;
+            if (n == 0) continue;
+            uint32_t N2 = 32;
+            while (N2 < n) N2 <<= 1;
+            for (uint32_t i = n + tid; i < N2; i += NT) skey[i] = ~(KT)0;  // no k-mer has all bits set (k <= 63)
+            __syncthreads();
+            // bitonic network, ascending
+            for (uint32_t k2 = 2; k2 <= N2; k2 <<= 1) {
+                for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                    for (uint32_t t = tid; t < (N2 >> 1); t += NT) {
+                        const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), ixj = i | j;
+                        const KT a = skey[i], b = skey[ixj];
+                        if ((a > b) == ((i & k2) == 0u)) { skey[i] = b; skey[ixj] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            // run lengths, coverage filter, rows out
+            uint32_t nd = 0;
+            for (uint32_t i0 = (uint32_t)warp * 32u; i0 < n; i0 += NT) {
+                const uint32_t i = i0 + lane;
+                bool keep = false;
+                uint32_t c = 0;
+                KT key = 0;
+                if (i < n) {
+                    key = skey[i];
+                    if (i == 0 || skey[i - 1] != key) {
+                        c = 1;
+                        while (i + c < n && skey[i + c] == key) c++;
+                        nd++;
+                        keep = c >= A.min_count && c <= A.max_count;
+                    }
+                }
+                const uint32_t ball = __ballot_sync(0xffffffffu, keep);
+                if (ball) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&A.dstat[DS_OUT_CURSOR], (unsigned long long)__popc(ball));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (keep) {
+                        const unsigned long long o = base + (uint32_t)__popc(ball & ((1u << lane) - 1u));
+                        if (o < A.out_cap) { reinterpret_cast<KT*>(A.out_keys)[o] = key; A.out_counts[o] = c; }
+                        else atomicExch(&A.dstat[DS_OVERFLOW], 1ull);
+                    }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, d);
+            if (lane == 0 && nd) atomicAdd(&A.dstat[DS_DISTINCT], (unsigned long long)nd);
+        }
+    }
+}
+template <bool WIDE, int CAPS, int NT> static cudaError_t launch_sort_count(const CountArgs& A, cudaStream_t st) {
+    const size_t smem = (size_t)CAPS * (WIDE ? 16 : 8);
+    cudaError_t e = cudaFuncSetAttribute(sort_bins_kernel<WIDE, CAPS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = sm_count() * 3u;  // 64 KB of keys per CTA
+    if (grid > A.n_tickets) grid = A.n_tickets;
+    sort_bins_kernel<WIDE, CAPS, NT><<<grid, NT, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
 // (segment, bin) -> extent, for every layout the records may be in (rfx_internal.h: ExtSrc)
 __global__ void build_ext_kernel(ExtSrcs S, int n_seg, uint32_t n_bins, int recw, SegExt* __restrict__ ext) {
     const uint64_t total = (uint64_t)n_seg * n_bins;
@@ -738,39 +890,46 @@ int stage_count_segments(Ctx* c, const ExtSrcs& S, int n_seg, uint32_t n_bins, b
     if (any) {
         cudaEventRecord(c->evk[4], st);
         cudaError_t le;
-        const char* variant = getenv("RFX_COUNT_VARIANT");  // "small" / "large": skip the pilot and force a geometry (tests, tuning)
+        const char* variant = getenv("RFX_COUNT_VARIANT");  // skip the pilot and force a kernel (tests, tuning)
         std::string vs = variant ? variant : "";
-        if (!c->wide) {
-            if (vs.empty() && c->count_geometry && c->count_geometry_bins == n_bins) {
-                // same context, same bin count as the run the pilot looked at (a driver pushing batch after batch of one
-                // data set): keep its choice; a run that splits more than 1 % of its bins drops it again (below)
-                vs = c->count_geometry == 1 ? "small" : "large";
-            } else if (vs.empty()) {
-                // Pilot: count ~300 evenly spaced bins with the large table, write nothing, and look at how many distinct
-                // k-mers a bin holds.  Clean high-coverage reads (tens per bin) run fastest on the small table at 3 CTAs / SM;
-                // noisy reads (every fourth instance a singleton) need the large one or most bins would be split.
-                CountArgs P = A;
-                P.n_tickets = n_bins < 296u ? n_bins : 296u;
-                P.bin_stride = n_bins / P.n_tickets;
-                P.dry = 1;
-                le = launch_count<false, 4096, 1024, 384, 2>(P, st);
-                if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count pilot launch failed: %s", cudaGetErrorString(le));
-                uint64_t ph[DS_NSLOTS];
-                RFX_CUDA(c, cudaMemcpyAsync(ph, c->dstat.p, sizeof(ph), cudaMemcpyDeviceToHost, st));
-                RFX_CUDA(c, cudaStreamSynchronize(st));
-                RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
-                c->launches++;
-                const uint64_t per_bin = ph[DS_DISTINCT] / P.n_tickets;
-                vs = (per_bin <= 600 && ph[DS_SPLITS] == 0) ? "small" : "large";
-                c->count_geometry = vs == "small" ? 1 : 2;
-                c->count_geometry_bins = n_bins;
-            }
-            if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
-            else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
-            else return ctx_fail(c, RFX_E_INVALID, "RFX_COUNT_VARIANT must be small or large");
-        } else {
-            le = launch_count<true, 2048, 256, 192, 3>(A, st);
+        // Which kernel: "small" / "large" (hash tables of 2048 / 4096 slots, k <= 31), "hash" (k > 31), "sort" (sort_bins_kernel).
+        // Unless forced, k <= 31 runs a pilot: ~300 evenly spaced bins are counted by the hash kernel without writing anything,
+        // and the distinct k-mers per bin pick the table geometry.  The sort kernel is the measured alternative and LOSES in
+        // every regime tried (one B200, profiles/r2_count_hash_vs_sort.md: clean configs[1] 36.9 ms against 1.2; k = 61 with
+        // 1 % errors, where every second instance is a k-mer of its own, 24.4 ms against 9.6), so it is only taken when asked
+        // for: RFX_COUNT_VARIANT=sort, or RFX_SORT_RATIO=<x> (the pilot then picks it where distinct / instances > x).
+        // The choice is kept per context while the bin count stays the same (a driver pushing batch after batch of one data
+        // set) and dropped when a run splits more than 1 % of its bins.
+        const char* rs = getenv("RFX_SORT_RATIO");
+        if (vs.empty() && c->count_geometry && c->count_geometry_bins == n_bins) {
+            vs = c->count_geometry == 1 ? "small" : c->count_geometry == 2 ? "large" : c->count_geometry == 3 ? "hash" : "sort";
+        } else if (vs.empty() && c->wide && !rs) {
+            vs = "hash";
+        } else if (vs.empty()) {
+            CountArgs P = A;
+            P.n_tickets = n_bins < 296u ? n_bins : 296u;
+            P.bin_stride = n_bins / P.n_tickets;
+            P.dry = 1;
+            le = c->wide ? launch_count<true, 2048, 256, 192, 3>(P, st) : launch_count<false, 4096, 1024, 384, 2>(P, st);
+            if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count pilot launch failed: %s", cudaGetErrorString(le));
+            uint64_t ph[DS_NSLOTS];
+            RFX_CUDA(c, cudaMemcpyAsync(ph, c->dstat.p, sizeof(ph), cudaMemcpyDeviceToHost, st));
+            RFX_CUDA(c, cudaStreamSynchronize(st));
+            RFX_CUDA(c, cudaMemsetAsync(c->dstat.p, 0, DS_NSLOTS * sizeof(uint64_t), st));
+            c->launches++;
+            const uint64_t per_bin = ph[DS_DISTINCT] / P.n_tickets;
+            const double ratio = ph[DS_INSTANCES] ? (double)ph[DS_DISTINCT] / (double)ph[DS_INSTANCES] : 0.0;
+            if (rs && ratio > atof(rs)) vs = "sort";
+            else if (c->wide) vs = "hash";
+            else vs = (per_bin <= 600 && ph[DS_SPLITS] == 0) ? "small" : "large";
+            c->count_geometry = vs == "small" ? 1 : vs == "large" ? 2 : vs == "hash" ? 3 : 4;
+            c->count_geometry_bins = n_bins;
         }
+        if (vs == "sort") le = c->wide ? launch_sort_count<true, 4096, 256>(A, st) : launch_sort_count<false, 8192, 256>(A, st);
+        else if (c->wide) le = launch_count<true, 2048, 256, 192, 3>(A, st);
+        else if (vs == "small") le = launch_count<false, 2048, 1024, 384, 3>(A, st);
+        else if (vs == "large") le = launch_count<false, 4096, 1024, 384, 2>(A, st);
+        else return ctx_fail(c, RFX_E_INVALID, "RFX_COUNT_VARIANT must be small, large, hash or sort");
         if (le != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "count kernel launch failed: %s", cudaGetErrorString(le));
         cudaEventRecord(c->evk[5], st);
         c->launches++;

@@ -198,6 +198,43 @@ def test_counts_match_oracle_all_k(R, orc, example_text, k):
     assert np.array_equal(g_counts, counts)
 
 
+@pytest.mark.parametrize("k,cover,bin_target", [(5, 1, 0), (21, 1, 0), (31, 2, 0), (33, 1, 0), (61, 2, 0), (63, 1, 0), (31, 1, 60_000), (61, 1, 30_000)])
+def test_sort_based_counting_kernel_matches_oracle(R, orc, example_text, monkeypatch, k, cover, bin_target):
+    """The measured alternative of the hash kernel (sort_bins_kernel: expand, bitonic sort, run-length count), forced here;
+    bins far larger than its shared-memory array go through hash-class passes (bin_target)."""
+    monkeypatch.setenv("RFX_COUNT_VARIANT", "sort")
+    noisy = bytes(make_reads(31, 50_000, 5000, read_len=150, err=0.01, frag=400))
+    for txt in (example_text, noisy):
+        s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
+        c = orc.count_kmers(txt, s, l, k, 0, 0, cover, 10_000_000, 1)
+        ints = [(int(h) << 64) | int(lo) for h, lo in zip(c["keys_hi"], c["keys_lo"])]
+        with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=cover), bin_target_kmers=bin_target) as ctx:
+            ctx.push_fastq(txt)
+            st = ctx.count()
+            g_ints, g_counts = _sorted_table(R, ctx, k)
+        assert st["n_instances"] == c["n_instances"] and st["n_distinct"] == c["n_distinct"]
+        assert g_ints == ints and np.array_equal(g_counts, c["counts"])
+        assert st["n_bin_splits"] > 0 or not bin_target
+
+
+def test_pilot_can_route_noisy_bins_to_the_sort_kernel(R, orc, monkeypatch):
+    """RFX_SORT_RATIO=<x>: the pilot (~300 bins counted without writing) sends a run to the sort kernel when more than x of its
+    k-mer instances are k-mers of their own.  Off by default -- the sort kernel lost every measurement -- but the route is
+    kept and must give the oracle's table; clean reads stay on the hash kernel under the same setting."""
+    monkeypatch.setenv("RFX_SORT_RATIO", "0.35")
+    clean = bytes(make_reads(41, 60_000, 6000, read_len=150, err=0.0, frag=400))
+    noisy = bytes(make_reads(42, 60_000, 6000, read_len=150, err=0.012, frag=400))
+    for txt, k in ((clean, 31), (noisy, 61), (noisy, 31)):
+        s, l = orc.fastq_reads(txt, orc.FASTQ_RUN)
+        c = orc.count_kmers(txt, s, l, k, 0, 0, 1, 10_000_000, 1)
+        ints = [(int(h) << 64) | int(lo) for h, lo in zip(c["keys_hi"], c["keys_lo"])]
+        with R.ReflexivContext(_param(R, kmerSize=k, minKmerCoverage=1)) as ctx:
+            ctx.push_fastq(txt)
+            ctx.count()
+            g_ints, g_counts = _sorted_table(R, ctx, k)
+        assert g_ints == ints and np.array_equal(g_counts, c["counts"])
+
+
 @pytest.mark.parametrize("k,m", [(31, 15), (31, 9), (27, 15), (61, 16)])
 def test_counts_do_not_depend_on_the_minimiser_length(R, orc, example_text, k, m):
     """m = 15 is what inputs with more than 2^16 bins use (register-resident scan, single-pass slab partition)."""
