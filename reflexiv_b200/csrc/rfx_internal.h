@@ -170,6 +170,7 @@ struct Ctx {
     uint8_t* peer_base[RFX_MAX_RANKS] = {nullptr};  // arena of every rank as seen from this device (own: arena)
     bool peer_ipc[RFX_MAX_RANKS] = {false};         // opened through cudaIpcOpenMemHandle
     unsigned long long sh_epoch = 0;                // barriers passed
+    unsigned long long sh_epoch2 = 0;               // in-kernel barriers passed (ShardCtl::flags2)
     unsigned long long sh_exchanges = 0;            // value exchanges made (parity picks the published block)
     unsigned long long* d_pub = nullptr;            // device staging: everybody's published block, gathered by one kernel
     unsigned long long* h_pub = nullptr;            // pinned: own published values + everybody's after an exchange

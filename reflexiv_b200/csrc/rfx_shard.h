@@ -10,6 +10,7 @@ namespace rfx {
 struct ShardCtl {
     unsigned long long flags[RFX_MAX_RANKS];
     unsigned long long pub[2][RFX_PUB_SLOTS];
+    unsigned long long flags2[RFX_MAX_RANKS];  // barriers taken INSIDE a kernel (the fused pointer-jumping rounds), own epoch counter
 };
 
 // what rfx_shard_export hands out (RFX_SHARD_HANDLE_BYTES = 128)

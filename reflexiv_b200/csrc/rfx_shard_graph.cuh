@@ -595,6 +595,45 @@ __global__ void sg_l2_jump_kernel(const __grid_constant__ SGView V, uint64_t m2,
         Me.l2_up[in ^ 1][j] = ad_pack((uint32_t)up, (uint32_t)(mine >> 32) + (uint32_t)(up >> 32));
     }
 }
+// Measured alternative (RFX_JUMP_FUSED=1; slower, see the call site): all rounds in ONE cooperative launch per rank (ranks on
+// different devices only): between two rounds a grid-wide barrier, a cross-GPU barrier taken by block 0 (every rank writes the
+// round's epoch into every rank's flags2[] and waits for its own to fill up) and another grid-wide barrier.
+// The (ancestor, distance) words change under the kernel's feet by design, so they are read around the L1.
+__global__ void __launch_bounds__(256) sg_l2_jump_all_kernel(const __grid_constant__ SGView V, PeerBases P, uint64_t m2, int rounds, unsigned long long epoch0,
+                                                             unsigned long long* dstat) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const SGPeer& Me = V.p[V.me];
+    int cur = 0;
+    for (int r = 0; r < rounds; r++) {
+        for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m2; j += (uint64_t)gridDim.x * blockDim.x) {
+            const uint64_t mine = *reinterpret_cast<const volatile uint64_t*>(&Me.l2_up[cur][j]);
+            const uint32_t a = (uint32_t)mine;
+            uint64_t out = mine;
+            if (a != gid_make(V.me, (uint32_t)j)) {
+                const uint64_t up = *reinterpret_cast<const volatile uint64_t*>(&V.p[gid_rank(a)].l2_up[cur][gid_loc(a)]);
+                out = ad_pack((uint32_t)up, (uint32_t)(mine >> 32) + (uint32_t)(up >> 32));
+            }
+            Me.l2_up[cur ^ 1][j] = out;
+        }
+        __threadfence_system();
+        grid.sync();
+        if (blockIdx.x == 0 && (int)threadIdx.x < P.n) {
+            const unsigned long long epoch = epoch0 + (unsigned long long)r + 1ull;
+            const int q = threadIdx.x;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(&reinterpret_cast<ShardCtl*>(P.base[q])->flags2[P.me]) = epoch;
+            const volatile unsigned long long* mine = &reinterpret_cast<ShardCtl*>(P.base[P.me])->flags2[q];
+            const long long t0 = clock64();
+            while (*mine < epoch) {
+                if (clock64() - t0 > 40000000000ll) { dstat[DS_XBAR_ERR] = 1ull; break; }
+                __nanosleep(100);
+            }
+            __threadfence_system();
+        }
+        grid.sync();
+        cur ^= 1;
+    }
+}
 __global__ void sg_l2_fin_kernel(const __grid_constant__ SGView V, uint64_t m2, int res, unsigned long long* dstat) {
     const SGPeer& Me = V.p[V.me];
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < m2; j += (uint64_t)gridDim.x * blockDim.x) {
@@ -1046,11 +1085,30 @@ template <class KT> static int sharded_graph_impl(Ctx* c) {
     prof.mark("bar");
     c->launches += 2;
     int cur = 0;
-    for (int r = 0; r < rounds; r++) {
-        if (m2) sg_l2_jump_kernel<<<grid_n(m2), 256, 0, st>>>(V, m2, cur);
-        RFX_TRY(shard_barrier(c));
+    if (world > 1 && !c->hbar && getenv("RFX_JUMP_FUSED")) {
+        // measured alternative, off by default: every round inside one cooperative launch (sg_l2_jump_all_kernel).  At 2 GPUs
+        // 0.61 ms against 0.31 ms for one small kernel + one barrier kernel per round: two grid-wide barriers per round cost more
+        // than the two launches they replace.
+        PeerBases PB = peer_bases(c);
+        uint64_t m2v = m2;
+        int rv = rounds;
+        unsigned long long e0 = c->sh_epoch2;
+        unsigned long long* ds = dstat;
+        unsigned blocks = (unsigned)((m2 + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        if (blocks > sm_count()) blocks = sm_count();
+        void* args[] = {(void*)&V, (void*)&PB, (void*)&m2v, (void*)&rv, (void*)&e0, (void*)&ds};
+        RFX_CUDA(c, cudaLaunchCooperativeKernel((void*)sg_l2_jump_all_kernel, dim3(blocks), dim3(256), args, 0, st));
+        c->sh_epoch2 += (unsigned long long)rounds;
         c->launches++;
-        cur ^= 1;
+        cur = rounds & 1;  // (the last round ends behind a cross-GPU barrier: every rank's result is complete and visible)
+    } else {
+        for (int r = 0; r < rounds; r++) {
+            if (m2) sg_l2_jump_kernel<<<grid_n(m2), 256, 0, st>>>(V, m2, cur);
+            RFX_TRY(shard_barrier(c));
+            c->launches++;
+            cur ^= 1;
+        }
     }
     prof.mark("l2_jump_rounds");
     if (m2) sg_l2_fin_kernel<<<grid_n(m2), 256, 0, st>>>(V, m2, cur, dstat);

@@ -214,7 +214,8 @@ def test_sort_based_counting_kernel_matches_oracle(R, orc, example_text, monkeyp
             g_ints, g_counts = _sorted_table(R, ctx, k)
         assert st["n_instances"] == c["n_instances"] and st["n_distinct"] == c["n_distinct"]
         assert g_ints == ints and np.array_equal(g_counts, c["counts"])
-        assert st["n_bin_splits"] > 0 or not bin_target
+        if bin_target and txt is noisy:  # (the example is too small to overfill the 64 bins a run has at least)
+            assert st["n_bin_splits"] > 0
 
 
 def test_pilot_can_route_noisy_bins_to_the_sort_kernel(R, orc, monkeypatch):
