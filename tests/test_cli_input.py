@@ -29,6 +29,22 @@ int main(int argc, char** argv) {
         }
         return 0;
     }
+    if (argc > 1 && !strcmp(argv[1], "cuts")) {     // cuts <file> <n>: where run_sharded cuts a FASTQ text into n runs of whole records
+        std::string text;
+        FILE* f = fopen(argv[2], "rb");
+        char buf[1 << 16]; size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+        fclose(f);
+        const int n = atoi(argv[3]);
+        size_t prev = 0;
+        for (int r = 1; r < n; r++) {
+            size_t want = text.size() / n * r;
+            if (want < prev) want = prev;
+            prev = record_start_near(text.data(), text.size(), want);
+            printf("%%zu\n", prev);
+        }
+        return 0;
+    }
     std::string all; size_t calls = 0;
     const size_t fail_at = argc > 2 ? (size_t)atoi(argv[2]) : (size_t)-1;
     bool ok = stream_inputs(argv[1], [&](const char* d, size_t n) { all.append(d, n); return calls++ != fail_at; });
@@ -179,3 +195,39 @@ def test_python_count_table_parser_row_forms():
         with pytest.raises(ValueError):
             parse_count_csv(bad, 31)
     assert parse_count_csv(b"\n\n", 31)[1].size == 0
+
+
+def test_multi_rank_input_cuts_fall_on_record_starts(harness, example_text, tmp_path):
+    """`reflexiv run --gpus N` gives rank r the r-th run of every file; a run must start on a record's header line -- also when
+    quality lines begin with '@' -- or the ranks would read other reads than one rank does."""
+    from oracle import orc
+    lines = example_text.split(b"\n")
+    # make every 7th quality line start with '@' and every 11th with '+'
+    for j, i in enumerate(range(3, len(lines) - 1, 4)):
+        if j % 7 == 0:
+            lines[i] = b"@" + lines[i][1:]
+        elif j % 11 == 0:
+            lines[i] = b"+" + lines[i][1:]
+    txt = b"\n".join(lines)
+    p = tmp_path / "tricky.fq"
+    p.write_bytes(txt)
+    s_all, l_all = orc.fastq_reads(txt, orc.FASTQ_RUN)
+    for n in (2, 3, 8):
+        cuts = [int(x) for x in subprocess.run([harness, "cuts", str(p), str(n)], capture_output=True, text=True, check=True).stdout.split()]
+        assert len(cuts) == n - 1 and cuts == sorted(cuts)
+        bounds = [0] + cuts + [len(txt)]
+        total = 0
+        for a, b in zip(bounds, bounds[1:]):
+            assert a == b or txt[a:a + 1] == b"@"
+            s, l = orc.fastq_reads(txt[a:b], orc.FASTQ_RUN)
+            total += len(s)
+        assert total == len(s_all)       # the runs hold exactly the reads of the whole file
+
+
+def test_lone_cr_files_are_refused_by_the_driver(harness, example_text, tmp_path):
+    (tmp_path / "mac.fq").write_bytes(example_text[:4000].replace(b"\n", b"\r"))
+    r = subprocess.run([harness, str(tmp_path / "mac.fq")], capture_output=True)
+    assert r.returncode != 0 and b"lone" in r.stderr
+    (tmp_path / "dos.fq").write_bytes(example_text[:4000].replace(b"\n", b"\r\n"))
+    r = subprocess.run([harness, str(tmp_path / "dos.fq")], capture_output=True)
+    assert r.returncode == 0 and r.stdout.count(b"\r\n") == example_text[:4000].count(b"\n")
