@@ -66,6 +66,13 @@ public final class ReflexivCuda implements AutoCloseable {
     private static final MethodHandle CONTIGS_COPY = h("rfx_contigs_copy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle SORT_KMERS = h("rfx_sort_kmers", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT));
     private static final MethodHandle SORTED_CSV = h("rfx_sorted_csv", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    // multi-GPU over peer memory (include/reflexiv_cuda.h: rfx_shard_*): one ReflexivCuda per GPU, collective calls from one thread each
+    private static final MethodHandle SHARD_INIT = h("rfx_shard_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, JAVA_LONG));
+    private static final MethodHandle SHARD_EXPORT = h("rfx_shard_export", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SHARD_CONNECT = h("rfx_shard_connect", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT));
+    private static final MethodHandle COUNT_SHARDED = h("rfx_count_sharded", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle ASSEMBLE_SHARDED = h("rfx_assemble_sharded", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    public static final int SHARD_HANDLE_BYTES = 128;
 
     /** One contig as the reference's DSKmerToContig sees it: bases plus the two end flags of the header. */
     public record Contig(String bases, int left, int right) {}
@@ -117,6 +124,29 @@ public final class ReflexivCuda implements AutoCloseable {
 
     /** fork filters + reflexible extension to the fixed point (ReflexivDSMain.java:221-338) */
     public void assemble() { call(() -> (int) ASSEMBLE.invoke(ctx)); }
+
+    /**
+     * Ranks of one JVM: {@code ranks[r]} was created on device r.  Puts every rank's buffers into an arena, hands every rank the
+     * handles of all ranks; afterwards {@link #countSharded()} / {@link #assembleSharded()} are collective calls, one thread per rank
+     * (an ExecutorService with ranks.length threads), and {@link #countsCsv()} / {@link #contigs()} return what the rank owns.
+     */
+    public static void connect(ReflexivCuda[] ranks, long arenaBytes) {
+        try (Arena a = Arena.ofConfined()) {
+            MemorySegment handles = a.allocate((long) ranks.length * SHARD_HANDLE_BYTES);
+            for (int r = 0; r < ranks.length; r++) {
+                final int rank = r;
+                ranks[r].call(() -> (int) SHARD_INIT.invoke(ranks[rank].ctx, rank, ranks.length, arenaBytes));
+                ranks[r].call(() -> (int) SHARD_EXPORT.invoke(ranks[rank].ctx, handles.asSlice((long) rank * SHARD_HANDLE_BYTES, SHARD_HANDLE_BYTES)));
+            }
+            for (ReflexivCuda k : ranks) k.call(() -> (int) SHARD_CONNECT.invoke(k.ctx, handles, ranks.length));
+        }
+    }
+
+    /** collective: every rank calls it from its own thread */
+    public void countSharded() { call(() -> (int) COUNT_SHARDED.invoke(ctx)); }
+
+    /** collective: every rank calls it from its own thread */
+    public void assembleSharded() { call(() -> (int) ASSEMBLE_SHARDED.invoke(ctx)); }
 
     /** The rows of Count_<k>: `KMER,count\n`, formatted on the device. */
     public byte[] countsCsv() { return csv(COUNTS_CSV); }
