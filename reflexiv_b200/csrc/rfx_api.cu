@@ -266,6 +266,20 @@ const char* rfx_last_error(const rfx_ctx* c) { return c ? c->err.c_str() : g_cre
 
 int rfx_reset(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
+    if (c->arena) {
+        // Sharded runs: buffers are bump-allocated in the peer-visible arena and nothing of a finished run is needed any more
+        // (every sharded call ends behind a cross-rank barrier, so no peer still reads them): hand the whole arena back, the
+        // next run lays its buffers out afresh.  Without this a context that is fed data sets of growing size would creep
+        // through its arena, since an outgrown block is only given up, never reused.
+        cudaSetDevice(c->prm.device);
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        DevBuf keep = c->dstat;
+        c->dstat = DevBuf();
+        free_all_buffers(c);
+        c->dstat = keep;
+        shard_graph_reset(c);
+        c->arena_used = c->arena_base;
+    }
     c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
     c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0; c->sp_active = false;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;

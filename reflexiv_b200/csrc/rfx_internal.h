@@ -166,7 +166,7 @@ struct Ctx {
     // ONE cudaMalloc'ed arena that the other ranks map (CUDA IPC between processes, plain pointers inside a process) ----
     int sh_rank = -1, sh_world = 0;
     uint8_t* arena = nullptr;
-    uint64_t arena_bytes = 0, arena_used = 0;
+    uint64_t arena_bytes = 0, arena_used = 0, arena_base = 0;  // arena_base: behind the control block and the published-value staging
     uint8_t* peer_base[RFX_MAX_RANKS] = {nullptr};  // arena of every rank as seen from this device (own: arena)
     bool peer_ipc[RFX_MAX_RANKS] = {false};         // opened through cudaIpcOpenMemHandle
     unsigned long long sh_epoch = 0;                // barriers passed

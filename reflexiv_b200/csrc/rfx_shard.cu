@@ -281,6 +281,7 @@ int rfx_shard_init(rfx_ctx* c, int32_t rank, int32_t world, uint64_t arena_bytes
     c->arena_used = (sizeof(ShardCtl) + 255) & ~(size_t)255;
     c->d_pub = reinterpret_cast<unsigned long long*>(c->arena + c->arena_used);  // staging of everybody's published block
     c->arena_used += ((size_t)RFX_MAX_RANKS * RFX_PUB_SLOTS * sizeof(unsigned long long) + 255) & ~(size_t)255;
+    c->arena_base = c->arena_used;
     c->sh_rank = rank; c->sh_world = world; c->sh_epoch = 0; c->sh_epoch2 = 0; c->sh_exchanges = 0;
     for (int r = 0; r < RFX_MAX_RANKS; r++) { c->peer_base[r] = nullptr; c->peer_ipc[r] = false; }
     return RFX_OK;

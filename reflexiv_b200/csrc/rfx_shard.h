@@ -45,6 +45,7 @@ int shard_check(Ctx* c, const char* what);       // synchronise the stream, repo
 int shard_exchange(Ctx* c, int first, int n, const unsigned long long* mine, unsigned long long* all /* [RFX_MAX_RANKS * RFX_PUB_SLOTS] */, int n_dev = 0,
                    const int* dev_slots = nullptr, int dev_first = 0);
 void shard_graph_release(Ctx* c);
+void shard_graph_reset(Ctx* c);  // forget the graph stages' arena buffers (rfx_reset)
 void shard_graph_stats(Ctx* c, rfx_shard_stats_t* out);
 void free_all_buffers(Ctx* c);
 

@@ -1206,6 +1206,10 @@ int stage_assemble_sharded(Ctx* c) {
     return c->wide ? sharded_graph_impl<u128>(c) : sharded_graph_impl<uint64_t>(c);
 }
 
+void shard_graph_reset(Ctx* c) {
+    if (c->gshard) *c->gshard = GShard();  // (all of its buffers live in the arena: nothing to free)
+}
+
 void shard_graph_release(Ctx* c) {
     delete c->gshard;
     c->gshard = nullptr;
