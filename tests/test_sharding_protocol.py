@@ -1,4 +1,6 @@
-"""A CPU model of the sharded fork filters DESIGN.md section 8 (item 1) plans for the next round -- NOT product code.
+"""A CPU model of the sharded fork filters -- NOT product code.  It was written in round 1 as the plan; the protocol it models
+is what csrc/rfx_shard_graph.cuh now implements on the GPUs (presence bits replicated, neighbours in a peer's bins asked by
+request / answer), and the model stays as the host-side check of the rules and of the traffic estimate.
 
 Every rank owns the rows whose canonical minimiser falls into its bins (the partition the counting stage already
 produces) and keeps an index over those rows only; the presence-bit filter (16 bits per row) is the one replicated
