@@ -131,6 +131,8 @@ class Workload:
              f"cover {c['cover']}, " + ("full run path (FASTQ text -> counts -> fork filters -> contigs)" if c["mode"] == "run" else "counter path (FASTQ text -> filtered count table)"))
         if c["error"]:
             s += f", {c['error'] * 100:g} % substitution errors"
+        if c.get("variant_error"):
+            s += " [variant: error rate overridden]"
         if self.scale != 1.0 and self.cfg_id != 2:
             s += f" [SCALED to {self.scale:g} of the configuration's size]"
         if self.read_len_min:
@@ -301,6 +303,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the single-GPU cross-check after the timed region")
     ap.add_argument("--files", action="store_true", help="N = 1: also time the `reflexiv` command line end to end through files (plain and gzip input, output tree written)")
     ap.add_argument("--trim-to", type=int, default=0, help="variant: reads quality-trimmed to a random length in [trim-to, 150]")
+    ap.add_argument("--error-rate", type=float, default=None, help="variant: override the configuration's per-base substitution rate")
     ap.add_argument("--minimizer", type=int, default=0)
     ap.add_argument("--bin-target", type=int, default=0)
     args = ap.parse_args()
@@ -335,6 +338,9 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     wl = Workload(args.config, world, args.scale, args.trim_to)
+    if args.error_rate is not None:
+        wl.cfg["variant_error"] = wl.cfg["error"] != args.error_rate
+        wl.cfg["error"] = args.error_rate
     cfg, kk, mode = wl.cfg, wl.k, wl.cfg["mode"]
     txt = wl.text(rank)
     n_reads = 2 * wl.pairs[rank]

@@ -951,7 +951,10 @@ int stage_count_segments(Ctx* c, const ExtSrcs& S, int n_seg, uint32_t n_bins, b
     c->n_rows = h[DS_OUT_CURSOR];
     c->n_distinct = h[DS_DISTINCT];
     c->n_bin_splits = h[DS_SPLITS];
-    if (c->n_bin_splits * 100 > n_bins) c->count_geometry = 0;  // the remembered geometry no longer fits the data: pilot again next time
+    if (c->n_bin_splits * 100 > n_bins) {
+        c->count_geometry = 0;  // the remembered geometry no longer fits the data: pilot again next time
+        if (c->bin_shrink < 4) c->bin_shrink *= 2;  // ... and smaller bins (rfx_partition.cu: choose_bin_count)
+    }
     c->n_shard_instances = h[DS_INSTANCES];
     if (!check_instances) {}  // a shard counts the instances of ITS bins, not those of the reads this rank scanned
     else if (c->n_instances == 0) c->n_instances = h[DS_INSTANCES];

@@ -129,6 +129,8 @@ struct Ctx {
     uint64_t table_cap = 0, n_rows = 0, n_distinct = 0, n_bin_splits = 0, n_shard_instances = 0;
     int count_geometry = 0;           // 0: unknown (run the pilot), 1: small table, 2: large table -- survives rfx_reset
     uint32_t count_geometry_bins = 0; // bin count of the run the pilot looked at
+    uint32_t bin_shrink = 1;          // 1, 2, 4: bins this much smaller than the default (a run that had to split > 1 % of its bins asks the next
+                                      // run on this context for smaller ones: noisy reads) -- survives rfx_reset, not used by sharded runs
     bool have_counts = false;
 
     // ---- de Bruijn graph over oriented k-mers (id = 2*row + strand) ----

@@ -505,6 +505,11 @@ __global__ void set_last_offset_kernel(uint64_t* off, uint64_t n_bins, const uin
 // shared-memory table even when every fourth (k = 31) or second (k = 61) instance is a sequencing-error singleton.
 uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards) {
     uint64_t target = c->prm.bin_target_kmers > 0 ? (uint64_t)c->prm.bin_target_kmers : (c->wide ? 2048 : 6144);
+    // Noisy reads fill a bin with k-mers of their own (1 % errors at k = 31: every fourth instance): the shared-memory table
+    // overflows and the bin is re-run in sub-classes.  Measured (one B200, gpurun_out/r2_n_*.json, r2_w_*.json): k = 31 with 1 % errors
+    // counts in 3.4 ms with bins of 3072 instances against 6.1 ms with 6144; k = 61: 7.4 against 9.6 ms; clean reads prefer the
+    // large bins (k = 61: 3.0 against 3.5 ms).  So a context whose last run split more than 1 % of its bins halves them.
+    if (c->prm.bin_target_kmers <= 0 && c->sh_world == 0 && n_shards == 1) target /= c->bin_shrink;
     uint64_t nb = (instances + target - 1) / target;
     if (nb < 64) nb = 64;
     if (nb > (1u << 24)) nb = 1u << 24;
