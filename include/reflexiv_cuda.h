@@ -169,6 +169,36 @@ int rfx_sorted_copy(rfx_ctx* ctx, uint64_t* keys_hi, uint64_t* keys_lo, int32_t*
 /* the CSV text of Count_<k>_sorted/part-*.csv, formatted on the device; out == NULL: size query */
 int rfx_sorted_csv(rfx_ctx* ctx, char* out, uint64_t cap, uint64_t* n_bytes);
 
+/* ---- -stitch: low-coverage read rescue --------------------------------------------
+ * Replaces the `if (param.stitch)` branch of ReflexivDSMain.assemblyFromKmer() (pipeline/ReflexivDSMain.java:585-672):
+ * DSLowCoverageSubKmerExtraction (:1211-1268) + SubKmerProbRowToHash (:109-118) + the broadcast, the second pass over the
+ * FASTQ with DSLowCoverageReadDetection (:1448-1612), DSFilterRepeatLowCoverageFragment (:922-1010), the union and the second
+ * extension loop (:640-670).  k <= 31 (that class is the k <= 31 assembler), one GPU.
+ *   rfx_load_counts | rfx_count  ->  rfx_stitch_begin  ->  rfx_push_fastq* (any number of calls)  ->  rfx_stitch_finish
+ * rfx_stitch_begin runs the assembly itself (as rfx_assemble, but every record of the extension is kept whatever its
+ * length: the -mincontig rule applies to the stitched set, as in the reference where DSKmerToContig runs last) and puts
+ * the (k-1)-mers of the contig ends that are clean and covered at most 4 times into a probe table.  While the stage is
+ * open, rfx_push_fastq / rfx_push_fastq_device / rfx_push_reads do not store reads: every sequence line of the `run`
+ * FASTQ filter (unclipped, as the reference reads units[1]) is scanned on both strands for a "left extendable" probe
+ * followed by a "right extendable" probe of another contig, and the piece between them is kept as a fragment.
+ * rfx_stitch_finish keeps one fragment per contig end, joins contig + fragment + contig chains and REPLACES the contigs
+ * that rfx_contigs_size / rfx_contigs_copy return.  The order-dependent choices of the reference (probe collisions, which
+ * fragment of a run stays, rings) are fixed as DESIGN.md section 2 lists them. */
+typedef struct {
+    uint64_t n_probes;      /* keys in the probe table */
+    uint64_t n_reads;       /* sequence lines scanned */
+    uint64_t n_fragments;   /* fragments cut from reads (both strands) */
+    uint64_t n_after_pass1; /* ... one per contig end they leave (DSFilterRepeatLowCoverageFragment) */
+    uint64_t n_joined;      /* ... that also won the contig they end on */
+    uint64_t n_stitched;    /* records made of more than one piece */
+    uint64_t n_rings;       /* closed chains, opened at their smallest first k-mer */
+    float ms_stitch;        /* probe table + finish (the read scan is part of ms_parse) */
+    float reserved;
+} rfx_stitch_stats_t;
+int rfx_stitch_begin(rfx_ctx* ctx);
+int rfx_stitch_finish(rfx_ctx* ctx);
+int rfx_stitch_stats(rfx_ctx* ctx, rfx_stitch_stats_t* out);
+
 int rfx_stats(rfx_ctx* ctx, rfx_stats_t* out);
 
 /* ---- sharded counting (one context per GPU; the caller moves records between GPUs) ------------

@@ -61,6 +61,9 @@ def lib():
         L.orc_assemble.restype = C.c_int
         L.orc_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.POINTER(_Contigs)]
+        L.orc_stitch.restype = C.c_int
+        L.orc_stitch.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_int, C.c_int, C.POINTER(_Contigs), C.c_void_p]
         L.orc_contigs_free.argtypes = [C.POINTER(_Contigs)]
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
@@ -180,6 +183,43 @@ def assemble(keys_hi, keys_lo, left, right, k: int, min_contig: int = 500, mode:
                right=np.ctypeslib.as_array(c.right, shape=(n,)).copy() if n else np.empty(0, np.int32),
                n_passes=c.n_passes, n_budget_junctions=c.n_budget_junctions,
                n_budget_admissible=c.n_budget_admissible, n_cycles=c.n_cycles)
+    lib().orc_contigs_free(C.byref(c))
+    return out
+
+
+def _contigs_out(c: _Contigs) -> dict:
+    n = c.n_contigs
+    offs = np.ctypeslib.as_array(c.offsets, shape=(n + 1,)).copy()
+    blob = C.string_at(c.bases, int(offs[-1])) if n else b""
+    return dict(contigs=[blob[int(offs[i]):int(offs[i + 1])].decode() for i in range(n)],
+                left=np.ctypeslib.as_array(c.left, shape=(n,)).copy() if n else np.empty(0, np.int32),
+                right=np.ctypeslib.as_array(c.right, shape=(n,)).copy() if n else np.empty(0, np.int32))
+
+
+STITCH_STATS = ("probes", "fragments", "after_pass1", "joined_both_sides", "stitched_records", "rings")
+
+
+def stitch(contigs, left, right, txt, k: int, min_contig: int = 500):
+    """SURVEY 8f-4 (`-stitch`, ReflexivDSMain.java:585-672): `contigs` are ALL records of the extension (assemble with
+    min_contig=0) with their flags; `txt` is the FASTQ text, read through the `run` filter.  Returns dict(contigs, left,
+    right, stats)."""
+    a = _as_bytes_array(txt)
+    starts, lens = fastq_reads(a, FASTQ_RUN)
+    blob = "".join(contigs).encode()
+    offs = np.zeros(len(contigs) + 1, dtype=np.uint64)
+    if contigs:
+        offs[1:] = np.cumsum([len(c) for c in contigs])
+    le = np.ascontiguousarray(left, dtype=np.int32)
+    ri = np.ascontiguousarray(right, dtype=np.int32)
+    bb = np.frombuffer(blob + b"\0", dtype=np.uint8)
+    stats = np.zeros(6, dtype=np.int64)
+    c = _Contigs()
+    rc = lib().orc_stitch(len(contigs), offs.ctypes.data, bb.ctypes.data, le.ctypes.data, ri.ctypes.data, a.ctypes.data,
+                          starts.ctypes.data, lens.ctypes.data, len(starts), k, min_contig, C.byref(c), stats.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"orc_stitch: k = {k} is outside ReflexivDSMain's range ({rc})")
+    out = _contigs_out(c)
+    out["stats"] = dict(zip(STITCH_STATS, stats.tolist()))
     lib().orc_contigs_free(C.byref(c))
     return out
 

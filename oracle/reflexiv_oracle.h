@@ -87,6 +87,16 @@ int orc_assemble(const uint64_t *o_hi, const uint64_t *o_lo, const int32_t *o_le
                  int64_t n, int k, int min_contig, int mode, int min_iter, int max_iter, orc_contigs *out);
 void orc_contigs_free(orc_contigs *c);
 
+/* -stitch low-coverage read rescue ------------------------------ */
+/* pipeline/ReflexivDSMain.java:585-672 with DSLowCoverageSubKmerExtraction (:1211-1268), DSLowCoverageReadDetection
+ * (:1448-1612) and DSFilterRepeatLowCoverageFragment (:922-1010); k <= 31 (returns -1 otherwise).  PARITY UNPINNED, see
+ * stitch_oracle.c.  Input: ALL contig records of the extension (assemble with min_contig 0) and the reads the `run`
+ * FASTQ filter keeps (orc_fastq_reads, UNclipped).  Output: the contig set after stitching, filtered like A10.
+ * stats[6]: probes, fragments cut, after pass 1, joined on both sides, stitched records, rings. */
+int orc_stitch(int64_t n_contigs, const uint64_t *offsets, const char *bases, const int32_t *left, const int32_t *right,
+               const char *txt, const uint64_t *starts, const uint32_t *lens, int64_t n_reads,
+               int k, int min_contig, orc_contigs *out, int64_t *stats);
+
 void orc_free(void *p);
 
 /* Host threads for the sort-based stages (fork filters, ORC_ASM_REFSIM passes): T-thread sorts and one scan task per

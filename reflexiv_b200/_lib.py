@@ -49,6 +49,14 @@ class RfxShardStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class RfxStitchStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_probes", "n_reads", "n_fragments", "n_after_pass1", "n_joined", "n_stitched", "n_rings")] + [
+        ("ms_stitch", C.c_float), ("reserved", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
 # every symbol include/reflexiv_cuda.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -75,6 +83,9 @@ SYMBOLS = {
     "rfx_sorted_size": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rfx_sorted_copy": (C.c_int, [_P, _P, _P, _P, _P]),
     "rfx_sorted_csv": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "rfx_stitch_begin": (C.c_int, [_P]),
+    "rfx_stitch_finish": (C.c_int, [_P]),
+    "rfx_stitch_stats": (C.c_int, [_P, C.POINTER(RfxStitchStats)]),
     "rfx_stats": (C.c_int, [_P, C.POINTER(RfxStats)]),
     "rfx_partition": (C.c_int, [_P, C.c_int32, C.c_uint32]),
     "rfx_choose_bins": (C.c_uint32, [_P, C.c_uint64, C.c_int32]),

@@ -44,6 +44,7 @@ static const char* HELP =
     "usage: reflexiv <run|counter|sort> [--spark-options ignored] -fastq <glob> -outfile <dir> [-kmer 31] [-cover 2]\n"
     "       [-maxcov 10000000] [-error 8] [-clipf N] [-clipe N] [-mincontig 500] [-miniter 15] [-maxiter 150]\n"
     "       [-partition N] [-partitionredu 200] [-kmerc <Count_k csv glob>] [-infmt fmt] [-bubble] [-gzip] [-cache]\n"
+    "       [-stitch]  (with -kmerc AND -fastq: low-coverage reads bridge contig ends, ReflexivDSMain.java:585-672)\n"
     "       sort: -kmerc <Count_k csv glob> -outfile <dir> -kmer k [-maxcov N] [-error 8] [-klist 23,31,...] [-accurate]\n"
     "             writes <dir>/Count_<k>_sorted (rows KMER,1|left|right)\n";
 
@@ -541,7 +542,10 @@ int main(int argc, char** argv) {
     if (v.count("bubble")) p.bubble = 0;
     const bool gz = v.count("gzip") > 0;
     const std::string infmt = v.count("infmt") ? v["infmt"] : "4mc";
-    const bool from_kmer = !counter && v.count("kmerc") && (sorter || !v.count("fastq"));
+    // -kmerc wins over -fastq (Pipelines.java:83-84: inputKmerPath != null -> assemblyFromKmer()); with both, the FASTQ is
+    // only read by the -stitch branch (Parameter.java:571-575, ReflexivDSMain.java:599)
+    const bool from_kmer = !counter && v.count("kmerc");
+    const bool stitch = from_kmer && !sorter && v.count("stitch");
     if (sorter && !from_kmer) { fputs(HELP, stdout); return 0; }
     if (!v.count("fastq") && !from_kmer) { fputs(HELP, stdout); return 0; }  // Parameter.java:565-568
     // -klist / -accurate: Parameter.java:362-387, 417-420 (read by the sorted stage only)
@@ -619,7 +623,25 @@ int main(int argc, char** argv) {
         clear_dir(target);
         if (!write_csv_part(c, sorter, target, 0, gz)) return fail(c, sorter ? "rfx_sorted_csv" : "rfx_counts_csv");
     } else {
-        if (rfx_assemble(c) != RFX_OK) return fail(c, "rfx_assemble");
+        if (stitch) {
+            // ReflexivDSMain.java:585-672: probes from the contig ends, the reads scanned for fragments, contigs joined
+            if (!v.count("fastq")) { fprintf(stderr, "reflexiv: -stitch reads the FASTQ a second time (ReflexivDSMain.java:599): give -fastq\n"); rfx_destroy(c); return 1; }
+            if (rfx_stitch_begin(c) != RFX_OK) return fail(c, "rfx_stitch_begin");
+            bool push_ok = true;
+            const bool read_ok = stream_inputs(v["fastq"], [&](const char* data, size_t n) {
+                push_ok = rfx_push_fastq(c, reinterpret_cast<const uint8_t*>(data), n) == RFX_OK;
+                return push_ok;
+            });
+            if (!push_ok) return fail(c, "rfx_push_fastq");
+            if (!read_ok) { rfx_destroy(c); return 1; }
+            if (rfx_stitch_finish(c) != RFX_OK) return fail(c, "rfx_stitch_finish");
+            rfx_stitch_stats_t ss;
+            rfx_stitch_stats(c, &ss);
+            char m2[256];
+            snprintf(m2, sizeof(m2), "stitch: %llu probes, %llu reads scanned, %llu fragments, %llu kept, %llu records stitched", (unsigned long long)ss.n_probes,
+                     (unsigned long long)ss.n_reads, (unsigned long long)ss.n_fragments, (unsigned long long)ss.n_after_pass1, (unsigned long long)ss.n_stitched);
+            info(m2);
+        } else if (rfx_assemble(c) != RFX_OK) return fail(c, "rfx_assemble");
         mkdir(target.c_str(), 0755);
         if (!write_contig_part(c, target, 0, 0, gz && from_kmer, nullptr)) return fail(c, "rfx_contigs_copy");
     }

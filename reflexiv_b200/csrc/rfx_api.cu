@@ -83,7 +83,9 @@ void free_all_buffers(Ctx* c) {
     DevBuf* all[] = {&c->text, &c->line_start, &c->line_at, &c->seq_flag, &c->scan_ws, &c->rd_len, &c->rd_woff, &c->packed, &c->bin_off, &c->bin_cursor,
                      &c->records, &c->keys, &c->counts, &c->dstat, &c->ht, &c->rflag, &c->lflag, &c->alive, &c->succ, &c->pred, &c->ad[0],
                      &c->ad[1], &c->rd_src, &c->spl_id, &c->spl_node, &c->loc, &c->sp_ad[0], &c->sp_ad[1], &c->cmin[0], &c->cmin[1], &c->chain_len, &c->tail_of, &c->ctg_idx, &c->ctg_off,
-                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom, &c->srt_left, &c->srt_right, &c->eff_l, &c->eff_r, &c->seg_ext};
+                     &c->ctg_left, &c->ctg_right, &c->ctg_bases, &c->rx_records, &c->run_desc, &c->rd_runs, &c->seg_off, &c->seg_base, &c->ovf_rec, &c->ovf_bin, &c->g_rowbin, &c->g_binrows, &c->g_hoff, &c->g_bloom, &c->srt_left, &c->srt_right, &c->eff_l, &c->eff_r, &c->seg_ext,
+                     &c->st_keys, &c->st_vals, &c->st_firstk, &c->st_ctr, &c->st_len, &c->st_woff, &c->st_hits, &c->st_frags, &c->st_codes, &c->st_nxt, &c->st_prv,
+                     &c->st_role, &c->st_outlen, &c->st_outright, &c->st_slot};
     for (DevBuf* b : all) devbuf_free(*b);
 }
 
@@ -283,7 +285,7 @@ int rfx_reset(rfx_ctx* c) {
     c->n_reads = c->n_words = c->n_bases = c->n_instances = 0;
     c->n_records = 0; c->n_bins = 0; c->have_records = false; c->slab_cap = 0; c->n_ovf = 0; c->sp_active = false;
     c->n_rows = c->n_distinct = c->n_bin_splits = 0; c->have_counts = false;
-    c->have_contigs = false; c->have_sorted = false;
+    c->have_contigs = false; c->have_sorted = false; c->st_active = false;
     c->rx_bytes = 0; c->shard_id = -1; c->n_seg = 0;
     for (float& m : c->ms) m = 0;
     return RFX_OK;
@@ -292,6 +294,7 @@ int rfx_reset(rfx_ctx* c) {
 int rfx_push_fastq_device(rfx_ctx* c, const uint8_t* d_buf, size_t len) {
     if (!c || (!d_buf && len)) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    if (c->st_active) return stage_parse_fastq(c, d_buf, len, true, false);  // reads of the stitch stage: scanned, nothing is kept
     c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; c->sp_active = false;
     return stage_parse_fastq(c, d_buf, len, true, false);
 }
@@ -303,7 +306,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     if (!c || (!buf && len)) return RFX_E_INVALID;
     if (len == 0) return RFX_OK;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false;
+    if (!c->st_active) { c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; }
     RFX_TRY(devbuf_reserve(c, c->text, len + 128));
     uint8_t* d_text = c->text.as<uint8_t>();
     // chunk boundaries: just behind a newline; the last chunk keeps at least two lines
@@ -332,7 +335,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
     // first chunk scaled to the whole text, every chunk's reads scanned while the next chunk is still on the bus.
     // (A later rfx_partition -- sharded runs -- or another push simply discards that work.)
     const char* sp_env = getenv("RFX_STREAM_PARTITION");
-    bool stream_part = n_chunks >= 2 && c->n_reads == 0 && !(sp_env && !strcmp(sp_env, "0"));
+    bool stream_part = n_chunks >= 2 && c->n_reads == 0 && !c->st_active && !(sp_env && !strcmp(sp_env, "0"));
     c->sp_active = false;
     // every error path waits for the copy stream: the next chunk's upload may still be reading the caller's buffer,
     // and the header promises that host buffers are not touched after the call returns
@@ -366,7 +369,7 @@ int rfx_push_fastq(rfx_ctx* c, const uint8_t* buf, size_t len) {
 int rfx_push_reads(rfx_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint64_t n_reads) {
     if (!c || !offsets || (!bases && n_reads && offsets[n_reads])) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
-    c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; c->sp_active = false;
+    if (!c->st_active) { c->have_records = false; c->have_counts = false; c->have_contigs = false; c->have_sorted = false; c->sp_active = false; }
     return stage_push_reads(c, bases, offsets, n_reads);
 }
 
@@ -612,6 +615,32 @@ int rfx_sorted_csv(rfx_ctx* c, char* out, uint64_t cap, uint64_t* n_bytes) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     devbuf_free(txt);
     if (e != cudaSuccess) return ctx_fail(c, RFX_E_CUDA, "rfx_sorted_csv: %s", cudaGetErrorString(e));
+    return RFX_OK;
+}
+
+int rfx_stitch_begin(rfx_ctx* c) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    return stage_stitch_begin(c);
+}
+
+int rfx_stitch_finish(rfx_ctx* c) {
+    if (!c) return RFX_E_INVALID;
+    cudaSetDevice(c->prm.device);
+    return stage_stitch_finish(c);
+}
+
+int rfx_stitch_stats(rfx_ctx* c, rfx_stitch_stats_t* out) {
+    if (!c || !out) return RFX_E_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->n_probes = c->st_stat[0];
+    out->n_reads = c->st_reads;
+    out->n_fragments = c->st_stat[1];
+    out->n_after_pass1 = c->st_stat[2];
+    out->n_joined = c->st_stat[3];
+    out->n_stitched = c->st_stat[4];
+    out->n_rings = c->st_stat[5];
+    out->ms_stitch = c->ms_stitch;
     return RFX_OK;
 }
 

@@ -330,6 +330,10 @@ static unsigned grid_for(uint64_t n, int block, unsigned cap = 0) {
     return (unsigned)(g > cap ? cap : g);
 }
 
+static inline int parse_k(const Ctx* c) { return c->st_active ? c->k - 1 : c->k; }
+static inline int parse_fc(const Ctx* c) { return c->st_active ? 0 : c->prm.front_clip; }
+static inline int parse_ec(const Ctx* c) { return c->st_active ? 0 : c->prm.end_clip; }
+
 // Builds the read table for `n_lines` lines and appends the packed reads to the context.
 static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* seq_flag) {
     cudaStream_t st = c->stream;
@@ -337,7 +341,9 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* 
     ScanPlan<uint64_t> plan;
     RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(L.n_lines) * sizeof(uint64_t)));
     plan.bind(L.n_lines, c->scan_ws.as<uint64_t>());
-    ReadIn in{L, seq_flag, c->k, c->prm.front_clip, c->prm.end_clip};
+    // While the stitch stage is open (rfx_stitch.cu) the reads are the UNclipped sequence lines of DSLowCoverageReadDetection
+    // (ReflexivDSMain.java:1467-1475: read = units[1], skipped when readLength - (k-1) <= 1) and are scanned, not stored.
+    ReadIn in{L, seq_flag, parse_k(c), parse_fc(c), parse_ec(c)};
     scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
     c->launches += 2 * plan.levels;
     uint64_t tot = 0;
@@ -347,6 +353,14 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* 
     if (n_new == 0) return RFX_OK;
     DevBuf& rd_src = c->rd_src;
     RFX_TRY(devbuf_reserve(c, rd_src, n_new * sizeof(uint64_t)));
+    if (c->st_active) {
+        RFX_TRY(devbuf_reserve(c, c->st_len, n_new * sizeof(uint32_t)));
+        RFX_TRY(devbuf_reserve(c, c->st_woff, n_new * sizeof(uint64_t)));
+        ReadOut out{in, 0, 0, rd_src.as<uint64_t>(), c->st_len.as<uint32_t>(), c->st_woff.as<uint64_t>()};
+        scan_apply(plan, in, out, OpAddU64{}, (uint64_t)0, st);
+        c->launches += 1;
+        return stitch_scan_reads(c, d_text, rd_src.as<uint64_t>(), c->st_len.as<uint32_t>(), n_new);
+    }
     int rc = RFX_OK;
     do {
         if ((rc = devbuf_reserve(c, c->rd_len, (c->n_reads + n_new) * sizeof(uint32_t), true)) != RFX_OK) break;
@@ -405,7 +419,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, d_text, ls, lat}, OpAddU64{}, (uint64_t)0, st);
     finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, lat, c->dstat.as<uint64_t>() + DS_FQ_NLINES);
     c->launches += 2;
-    const bool try_regular = c->prm.fastq_mode == RFX_FASTQ_RUN && !getenv("RFX_FASTQ_GENERAL");  // (tests force the general path)
+    const int fmode = c->st_active ? RFX_FASTQ_RUN : c->prm.fastq_mode;  // the stitch stage always reads units (ReflexivDSMain.java:601-606)
+    const bool try_regular = fmode == RFX_FASTQ_RUN && !getenv("RFX_FASTQ_GENERAL");  // (tests force the general path)
     if (try_regular) {
         RFX_CUDA(c, cudaMemsetAsync(c->dstat.as<uint64_t>() + DS_FQ_IRREGULAR, 0, sizeof(uint64_t), st));
         fq_regular_check_kernel<<<sm_count() * 8, 256, 0, st>>>(lat, c->dstat.as<unsigned long long>());
@@ -422,20 +437,20 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
     const uint32_t* flags = c->seq_flag.as<uint32_t>();
     if (try_regular && !fq[1]) {
-        fq_regular_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2], c->seq_flag.as<uint32_t>(), c->k,
-                                                                       c->prm.front_clip, c->prm.end_clip, c->dstat.as<unsigned long long>());
+        fq_regular_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2], c->seq_flag.as<uint32_t>(), parse_k(c),
+                                                                       parse_fc(c), parse_ec(c), c->dstat.as<unsigned long long>());
         c->launches++;
-    } else if (c->prm.fastq_mode == RFX_FASTQ_RUN) {
+    } else if (fmode == RFX_FASTQ_RUN) {
         ScanPlan<uint32_t> fs;
         RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint32_t>::workspace_elems(n_lines) * sizeof(uint32_t)));
         fs.bind(n_lines, c->scan_ws.as<uint32_t>());
         scan_prepare(fs, LineFnIn{lat}, OpCompose{}, FN_IDENT, st);
-        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines + (more_follows ? 2u : 0u), c->seq_flag.as<uint32_t>(), fq_state, L, c->k, c->prm.front_clip, c->prm.end_clip},
+        scan_apply(fs, LineFnIn{lat}, LineFnOut{n_lines + (more_follows ? 2u : 0u), c->seq_flag.as<uint32_t>(), fq_state, L, parse_k(c), parse_fc(c), parse_ec(c)},
                    OpCompose{}, FN_IDENT, st);
         fq_state_update_kernel<<<1, 1, 0, st>>>(fs.total, fq_state);
         c->launches += 2 * fs.levels + 1;
-    } else if (c->prm.fastq_mode == RFX_FASTQ_COUNTER) {
-        flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint32_t>(), c->k, c->prm.front_clip, c->prm.end_clip);
+    } else if (fmode == RFX_FASTQ_COUNTER) {
+        flag_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, RFX_FASTQ_COUNTER, c->seq_flag.as<uint32_t>(), parse_k(c), parse_fc(c), parse_ec(c));
         c->launches += 1;
     } else {
         flags = nullptr;

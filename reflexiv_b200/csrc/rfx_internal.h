@@ -164,6 +164,19 @@ struct Ctx {
     uint64_t n_sorted = 0;
     bool have_sorted = false;
 
+    // ---- -stitch (rfx_stitch.cu): contig-end probes, fragments cut from the reads, chains over contigs ----
+    bool st_active = false;      // between rfx_stitch_begin and rfx_stitch_finish: pushed reads are scanned, not stored
+    DevBuf st_keys, st_vals;     // u64 / u32 [st_cap] open-addressing probe table: (k-1)-mer -> contig << 1 | direction
+    DevBuf st_firstk;            // u64[n_contigs] first k-mer of every contig (orders probes and opens rings)
+    DevBuf st_ctr;               // u64[8] device counters
+    DevBuf st_len, st_woff;      // read table of the chunk being scanned (scratch)
+    DevBuf st_hits;              // fragments found in the chunk being scanned
+    DevBuf st_frags, st_codes;   // all fragments so far: descriptors + 2-bit codes, one per byte
+    DevBuf st_nxt, st_prv, st_role, st_outlen, st_outright, st_slot;
+    uint64_t st_cap = 0, st_nfrag = 0, st_ncodes = 0, st_reads = 0;
+    uint64_t st_stat[6] = {0, 0, 0, 0, 0, 0};  // probes, fragments, after pass 1, joined on both sides, stitched records, rings
+    float ms_stitch = 0;
+
     // ---- sharded runs over peer memory (rfx_shard.cu): one context per GPU, every device buffer of the context lives in
     // ONE cudaMalloc'ed arena that the other ranks map (CUDA IPC between processes, plain pointers inside a process) ----
     int sh_rank = -1, sh_world = 0;
@@ -259,6 +272,9 @@ int stage_count(Ctx* c);
 int stage_count_segments(Ctx* c, const ExtSrcs& S, int n_seg, uint32_t n_bins, bool check_instances);
 int stage_graph(Ctx* c);
 int stage_sorted(Ctx* c, int min_error_coverage, double min_repeat_fold, int max_kmer_size);
+int stage_stitch_begin(Ctx* c);
+int stitch_scan_reads(Ctx* c, const uint8_t* d_text, const uint64_t* rd_src, const uint32_t* rd_len, uint64_t n_reads);
+int stage_stitch_finish(Ctx* c);
 uint32_t choose_bin_count(const Ctx* c, uint64_t instances, int n_shards);
 int stage_count_sharded(Ctx* c);
 int stage_assemble_sharded(Ctx* c);

@@ -139,6 +139,23 @@ class ReflexivContext:
         self._check(self.L.rfx_assemble(self._ctx), self._ctx)
         return self.stats()
 
+    # ---- -stitch (ReflexivDSMain.java:585-672) ----
+    def stitch_begin(self):
+        """Assembles (every record kept) and builds the probe table of the low-coverage contig ends; until stitch_finish()
+        the push_* calls scan reads for fragments instead of storing them."""
+        self._check(self.L.rfx_stitch_begin(self._ctx), self._ctx)
+        return self.stitch_stats()
+
+    def stitch_finish(self):
+        """Joins contig + fragment + contig chains; contigs() then returns the stitched set."""
+        self._check(self.L.rfx_stitch_finish(self._ctx), self._ctx)
+        return self.stitch_stats()
+
+    def stitch_stats(self) -> dict:
+        st = _lib.RfxStitchStats()
+        self._check(self.L.rfx_stitch_stats(self._ctx, C.byref(st)), self._ctx)
+        return st.as_dict()
+
     def contigs(self):
         """[(sequence, left_flag, right_flag)], both strands of every contig, order unspecified."""
         n, tot = C.c_uint64(), C.c_uint64()
@@ -491,7 +508,18 @@ class Pipelines:
                 if not n_files:
                     ctx.push_fastq(b"")
                 ctx.count()
-            st = ctx.assemble()
+            if from_kmer and p.stitch:
+                # ReflexivDSMain.java:585-672: the FASTQ is read a second time, by the stitch branch only (Parameter.java:571-575)
+                if p.inputFqPath is None:
+                    raise ValueError("-stitch reads the FASTQ (ReflexivDSMain.java:599): give -fastq next to -kmerc")
+                ctx.stitch_begin()
+                for chunk in iter_input_files(p.inputFqPath):
+                    ctx.push_fastq(chunk)
+                stitch = ctx.stitch_finish()
+                st = ctx.stats()
+                st["stitch"] = stitch
+            else:
+                st = ctx.assemble()
             contigs = ctx.contigs()
         os.makedirs(out_dir)
         data = "".join(format_contig(s, l, r, i) + "\n" for i, (s, l, r) in enumerate(contigs)).encode()
