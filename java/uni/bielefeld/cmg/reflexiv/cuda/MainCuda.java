@@ -77,7 +77,11 @@ public final class MainCuda {
         try (ReflexivCuda gpu = new ReflexivCuda(p, false, device)) {
             if (fromKmer) loadCountTable(gpu, p, p.minKmerCoverage);
             else { pushInputs(gpu, p.inputFqPath); gpu.count(); }
-            gpu.assemble();
+            if (fromKmer && p.stitch) {                     // ReflexivDSMain.java:585-672: the FASTQ is read a second time
+                gpu.stitchBegin();
+                pushInputs(gpu, p.inputFqPath);
+                gpu.stitchFinish();
+            } else gpu.assemble();
             StringBuilder sb = new StringBuilder();
             ReflexivCuda.Contig[] contigs = gpu.contigs();
             for (int i = 0; i < contigs.length; i++) {      // DSKmerToContig + changeLine + TagRowContigID, ReflexivDSMain.java:743-794, 717-725

@@ -64,6 +64,8 @@ public final class ReflexivCuda implements AutoCloseable {
     private static final MethodHandle ASSEMBLE = h("rfx_assemble", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle CONTIGS_SIZE = h("rfx_contigs_size", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle CONTIGS_COPY = h("rfx_contigs_copy", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle STITCH_BEGIN = h("rfx_stitch_begin", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle STITCH_FINISH = h("rfx_stitch_finish", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle SORT_KMERS = h("rfx_sort_kmers", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_DOUBLE, JAVA_INT));
     private static final MethodHandle SORTED_CSV = h("rfx_sorted_csv", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     // multi-GPU over peer memory (include/reflexiv_cuda.h: rfx_shard_*): one ReflexivCuda per GPU, collective calls from one thread each
@@ -124,6 +126,15 @@ public final class ReflexivCuda implements AutoCloseable {
 
     /** fork filters + reflexible extension to the fixed point (ReflexivDSMain.java:221-338) */
     public void assemble() { call(() -> (int) ASSEMBLE.invoke(ctx)); }
+
+    /**
+     * -stitch (ReflexivDSMain.java:585-672): assembles with every record kept and builds the probe table of the thinly covered contig
+     * ends; until {@link #stitchFinish()} every pushFastq scans reads for bridging fragments instead of storing them.
+     */
+    public void stitchBegin() { call(() -> (int) STITCH_BEGIN.invoke(ctx)); }
+
+    /** Joins contig + fragment + contig chains; {@link #contigs()} then returns the stitched set. */
+    public void stitchFinish() { call(() -> (int) STITCH_FINISH.invoke(ctx)); }
 
     /**
      * Ranks of one JVM: {@code ranks[r]} was created on device r.  Puts every rank's buffers into an arena, hands every rank the
