@@ -52,6 +52,14 @@ def random_scenarios(n):
         yield k, gap_scenario(100 + s, glen, 90, gaps, circular=bool(s % 2), err=0.01 if s % 3 == 0 else 0.0)[1]
 
 
+def natural_scenario(glen, coverage, seed=7, err=0.0):
+    """Uniformly sampled paired reads at LOW coverage: the k-mer coverage drops below -cover here and there, which is what
+    the stitch branch is for."""
+    from workload import synth
+    g = synth.genome(glen, seed=seed)
+    return bytes(synth.fastq(g, synth.n_pairs_for(glen, coverage, 150), read_len=150, frag_len=400, error_rate=err))
+
+
 def assembled(txt, k, cover=3):
     asm = orc.run_pipeline(txt, k=k, cover=cover, min_contig=0)["asm"]
     return asm["contigs"], asm["left"].tolist(), asm["right"].tolist()
@@ -282,6 +290,21 @@ def test_stitch_kernels_on_the_host_match_the_oracle():
     assert rings > 0
 
 
+def test_stitch_on_thinly_covered_reads_oracle_and_host_kernels():
+    txt = natural_scenario(300_000, 8)
+    contigs, left, right = assembled(txt, 31)
+    want = orc.stitch(contigs, left, right, txt, 31, min_contig=0)
+    st = want["stats"]
+    assert len(contigs) > 500 and st["stitched_records"] > 100 and len(want["contigs"]) < 0.6 * len(contigs)
+    assert max(len(c) for c in want["contigs"]) > 2 * max(len(c) for c in contigs)
+    got = emu_stitch(contigs, left, right, txt, 31, 0, chunk=5000, cap0=64)
+    assert triples(got) == triples(want) and got["stats"] == list(st.values())
+    from workload import synth
+    G = synth.genome(300_000, seed=7).tobytes().decode()
+    for c in want["contigs"]:  # error-free reads: whatever was stitched is still a piece of the genome
+        assert c in G or orc.revcomp_str(c) in G
+
+
 def test_stitch_is_outside_the_k_range_of_the_class():
     with pytest.raises(ValueError):
         orc.stitch(["A" * 100], [-2], [-2], fq(["A" * 80]), 33)
@@ -324,6 +347,20 @@ def test_stitch_matches_oracle_on_gap_scenarios(monkeypatch):
         stitched += want["stats"]["stitched_records"]
         rings += want["stats"]["rings"]
     assert stitched > 10 and rings > 0
+
+
+@pytest.mark.gpu
+def test_stitch_on_thinly_covered_reads(monkeypatch):
+    for glen, cov, err in ((1_000_000, 8, 0.0), (400_000, 10, 0.005)):
+        txt = natural_scenario(glen, cov, err=err)
+        contigs, left, right = assembled(txt, 31)
+        want = orc.stitch(contigs, left, right, txt, 31, min_contig=200)
+        monkeypatch.setenv("RFX_FASTQ_CHUNK_BYTES", str(8 << 20))
+        got, st = _gpu_stitch(txt, 31, min_contig=200)
+        monkeypatch.delenv("RFX_FASTQ_CHUNK_BYTES", raising=False)
+        assert got == triples(want)
+        assert [st["n_probes"], st["n_fragments"], st["n_after_pass1"], st["n_joined"], st["n_stitched"], st["n_rings"]] == list(want["stats"].values())
+        assert st["n_stitched"] > 100
 
 
 @pytest.mark.gpu
