@@ -167,6 +167,7 @@ struct Ctx {
     // ---- -stitch (rfx_stitch.cu): contig-end probes, fragments cut from the reads, chains over contigs ----
     bool st_active = false;      // between rfx_stitch_begin and rfx_stitch_finish: pushed reads are scanned, not stored
     DevBuf st_keys, st_vals;     // u64 / u32 [st_cap] open-addressing probe table: (k-1)-mer -> contig << 1 | direction
+    DevBuf st_bloom;             // u32[2^19 / 32] Bloom filter over the probe keys (64 KB: answers from the L1)
     DevBuf st_firstk;            // u64[n_contigs] first k-mer of every contig (orders probes and opens rings)
     DevBuf st_ctr;               // u64[8] device counters
     DevBuf st_len, st_woff;      // read table of the chunk being scanned (scratch)

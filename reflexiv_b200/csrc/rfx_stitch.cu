@@ -57,6 +57,8 @@ int stage_stitch_begin(Ctx* c) {
     RFX_TRY(devbuf_reserve(c, c->st_vals, cap * sizeof(uint32_t)));
     RFX_TRY(devbuf_reserve(c, c->st_firstk, (n + 1) * sizeof(uint64_t)));
     RFX_TRY(devbuf_reserve(c, c->st_ctr, SC_N * sizeof(uint64_t)));
+    RFX_TRY(devbuf_reserve(c, c->st_bloom, ST_BLOOM_BITS / 8));
+    RFX_CUDA(c, cudaMemsetAsync(c->st_bloom.p, 0, ST_BLOOM_BITS / 8, st));
     c->st_cap = cap;
     RFX_CUDA(c, cudaMemsetAsync(c->st_keys.p, 0xff, cap * sizeof(uint64_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->st_vals.p, 0xff, cap * sizeof(uint32_t), st));
@@ -65,7 +67,7 @@ int stage_stitch_begin(Ctx* c) {
     if (n) {
         probe_first_kernel<<<grid_for_n(n), 256, 0, st>>>(c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>(), n, c->k, c->st_firstk.as<uint64_t>());
         probe_insert_kernel<<<grid_for_n(n), 256, 0, st>>>(c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>(), c->ctg_left.as<int32_t>(), c->ctg_right.as<int32_t>(), n,
-                                                          c->k, c->st_firstk.as<uint64_t>(), c->st_keys.as<uint64_t>(), c->st_vals.as<uint32_t>(), cap - 1, ctr + SC_PUT);
+                                                          c->k, c->st_firstk.as<uint64_t>(), c->st_keys.as<uint64_t>(), c->st_vals.as<uint32_t>(), cap - 1, c->st_bloom.as<uint32_t>(), ctr + SC_PUT);
         count_keys_kernel<<<grid_for_n(cap), 256, 0, st>>>(c->st_keys.as<uint64_t>(), cap, ctr + SC_KEYS);
         c->launches += 3;
     }
@@ -91,8 +93,8 @@ int stitch_scan_reads(Ctx* c, const uint8_t* d_text, const uint64_t* rd_src, con
     uint64_t h[2];
     for (int attempt = 0;; attempt++) {
         RFX_CUDA(c, cudaMemsetAsync(ctr, 0, 2 * sizeof(uint64_t), st));
-        stitch_scan_kernel<<<grid_for_n(2 * n_reads), 256, 0, st>>>(d_text, rd_src, rd_len, n_reads, c->k, c->st_keys.as<uint64_t>(), c->st_vals.as<uint32_t>(), c->st_cap - 1,
-                                                                  c->st_hits.as<Hit>(), hit_cap, ctr);
+        stitch_scan_kernel<<<grid_for_n(n_reads), 256, 0, st>>>(d_text, rd_src, rd_len, n_reads, c->k, c->st_keys.as<uint64_t>(), c->st_vals.as<uint32_t>(), c->st_cap - 1,
+                                                                  c->st_bloom.as<uint32_t>(), c->st_hits.as<Hit>(), hit_cap, ctr);
         c->launches++;
         RFX_CUDA(c, cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
         RFX_CUDA(c, cudaStreamSynchronize(st));

@@ -40,6 +40,16 @@ __device__ __forceinline__ uint64_t st_hash(uint64_t x) {
     return x;
 }
 
+// A Bloom filter over the probe keys (64 KB, two bits per key) in front of the table: almost every (k-1)-mer of a read is no
+// contig end, and the filter answers that from the L1 where the table itself only fits the L2.
+constexpr uint32_t ST_BLOOM_BITS = 1u << 19;
+__device__ __forceinline__ void bloom_set(uint32_t* bloom, uint64_t key) {
+    const uint32_t x = (uint32_t)key ^ (uint32_t)(key >> 31);
+    const uint32_t a = (x * 0x9E3779B1u) >> 13, b = (x * 0x85EBCA6Bu) >> 13;  // 19 bits each (ST_BLOOM_BITS), as bloom_maybe below
+    atomicOr(&bloom[a >> 5], 1u << (a & 31));
+    atomicOr(&bloom[b >> 5], 1u << (b & 31));
+}
+
 // ---- S1: probes ---------------------------------------------------------------------------------
 __global__ void probe_first_kernel(const uint64_t* __restrict__ off, const char* __restrict__ bases, uint64_t n, int k, uint64_t* __restrict__ firstk) {
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
@@ -58,7 +68,8 @@ __device__ __forceinline__ bool probe_after(uint32_t a, uint32_t b, const uint64
     if (fa != fb) return fa > fb;
     return (a & 1u) < (b & 1u);
 }
-__device__ void probe_insert(uint64_t key, uint32_t val, uint64_t* keys, uint32_t* vals, uint64_t mask, const uint64_t* firstk) {
+__device__ void probe_insert(uint64_t key, uint32_t val, uint64_t* keys, uint32_t* vals, uint64_t mask, const uint64_t* firstk, uint32_t* bloom) {
+    bloom_set(bloom, key);
     uint64_t s = st_hash(key) & mask;
     for (;;) {
         const unsigned long long prev = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)ST_EMPTY, (unsigned long long)key);
@@ -75,7 +86,7 @@ __device__ void probe_insert(uint64_t key, uint32_t val, uint64_t* keys, uint32_
 }
 __global__ void probe_insert_kernel(const uint64_t* __restrict__ off, const char* __restrict__ bases, const int32_t* __restrict__ cl,
                                     const int32_t* __restrict__ cr, uint64_t n, int k, const uint64_t* __restrict__ firstk, uint64_t* keys,
-                                    uint32_t* vals, uint64_t mask, unsigned long long* n_probes) {
+                                    uint32_t* vals, uint64_t mask, uint32_t* bloom, unsigned long long* n_probes) {
     const int sk = k - 1;
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t len = off[c + 1] - off[c];
@@ -87,8 +98,8 @@ __global__ void probe_insert_kernel(const uint64_t* __restrict__ off, const char
             a = (a << 2) | nv((uint8_t)bases[off[c] + j]);
             b = (b << 2) | nv((uint8_t)bases[off[c + 1] - sk + j]);
         }
-        if (l) probe_insert(a, (uint32_t)(c << 1) | 1u, keys, vals, mask, firstk);
-        if (r) probe_insert(b, (uint32_t)(c << 1), keys, vals, mask, firstk);
+        if (l) probe_insert(a, (uint32_t)(c << 1) | 1u, keys, vals, mask, firstk, bloom);
+        if (r) probe_insert(b, (uint32_t)(c << 1), keys, vals, mask, firstk, bloom);
         atomicAdd(n_probes, (unsigned long long)l + (unsigned long long)r);
     }
 }
@@ -98,8 +109,8 @@ __global__ void count_keys_kernel(const uint64_t* __restrict__ keys, uint64_t ca
     if (m) atomicAdd(n, m);
 }
 
-__device__ __forceinline__ uint32_t probe_lookup(uint64_t key, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask) {
-    uint64_t s = st_hash(key) & mask;
+__device__ __forceinline__ uint32_t probe_lookup_h(uint64_t key, uint64_t h, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask) {
+    uint64_t s = h & mask;
     for (;;) {
         const uint64_t kk = __ldg(&keys[s]);
         if (kk == key) return __ldg(&vals[s]);
@@ -108,40 +119,109 @@ __device__ __forceinline__ uint32_t probe_lookup(uint64_t key, const uint64_t* _
     }
 }
 
+__device__ __forceinline__ uint32_t probe_lookup(uint64_t key, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask) {
+    return probe_lookup_h(key, st_hash(key), keys, vals, mask);
+}
+
+// Both codes of a text byte in one table entry: bits 0-1 nucleotideValue(c) (the forward strand), bits 2-3
+// nucleotideValue(complementary(c)) (the reverse-complement STRING of the reference: lower case folded, U = T, anything else 'N' -> 3).
+__device__ const uint8_t ST_CODES[256] = {
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 12, 15, 9, 15, 15, 15, 6, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 3, 3, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 11, 15, 15, 15, 7, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 3, 3, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+};
+
+// the window hash of the Bloom filter: cheap, because nearly every window of a read ends here
+__device__ __forceinline__ uint32_t bloom_fold(uint64_t w) { return (uint32_t)w ^ (uint32_t)(w >> 31); }
+__device__ __forceinline__ bool bloom_maybe(const uint32_t* __restrict__ bloom, uint64_t w) {
+    const uint32_t x = bloom_fold(w);
+    const uint32_t a = (x * 0x9E3779B1u) >> 13;
+    if (!((__ldg(&bloom[a >> 5]) >> (a & 31)) & 1u)) return false;
+    const uint32_t b = (x * 0x85EBCA6Bu) >> 13;
+    return (__ldg(&bloom[b >> 5]) >> (b & 31)) & 1u;
+}
+
 // ---- S2: reads ----------------------------------------------------------------------------------
-// One thread per (read, strand); the two strands of a read sit in neighbouring lanes and walk the same bytes from both ends.
-// left = the FIRST direction-0 hit (its contig is remembered), right = the LAST direction-1 hit of another contig (:1497-1531).
+// One thread per read walks the text ONCE, in aligned 4-byte words, and rolls two windows: the (k-1)-mer of the forward strand
+// and the (k-1)-mer the reverse-complement string shows at the mirrored position (window ending at i  <->  window ending at
+// L + k - 3 - i of the other strand).  DSLowCoverageReadDetection scans each strand front to back and keeps the FIRST direction-0
+// hit (its contig is remembered) and the LAST direction-1 hit of another contig (:1497-1531); that is: left = the smallest hit
+// position of direction 0, right = the largest direction-1 position behind it whose contig differs from left's -- a rule without
+// an order, so the reverse strand can be collected back to front: the last direction-0 hit met is its `left`, and of the
+// direction-1 hits only the first met and the first met of another contig can be its `right`.
 __global__ void __launch_bounds__(256) stitch_scan_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ rd_src, const uint32_t* __restrict__ rd_len,
                                                           uint64_t n_reads, int k, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask,
-                                                          Hit* hits, uint64_t hit_cap, unsigned long long* ctr /* [0] hits, [1] codes */) {
+                                                          const uint32_t* __restrict__ bloom, Hit* hits, uint64_t hit_cap, unsigned long long* ctr /* [0] hits, [1] codes */) {
     const int sk = k - 1;
     const uint64_t kmask = (1ull << (2 * sk)) - 1;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n_reads; t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = t >> 1;
-        const uint32_t strand = (uint32_t)t & 1u;
+    const int top = 2 * (sk - 1);
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t L = rd_len[r];  // 0 when readLength - (k-1) <= 1 (:1473)
         if (L == 0) continue;
-        const uint8_t* rd = text + rd_src[r];
-        uint32_t probed = NONE32;
-        int left = -1, right = -1;
-        uint64_t w = 0;
-        for (uint32_t i = 0; i < L; i++) {
-            const uint32_t code = strand ? nv(complementary(__ldg(&rd[L - 1 - i]))) : nv(__ldg(&rd[i]));
-            w = ((w << 2) | code) & kmask;
-            if ((int)i < sk - 1) continue;
-            const uint32_t v = probe_lookup(w, keys, vals, mask);
-            if (v == NONE32) continue;
-            if (!(v & 1u)) {
-                if (left < 0) { probed = v >> 1; left = (int)i; }
-            } else if (probed != (v >> 1)) {
-                right = (int)i;
+        const uint64_t src = rd_src[r];
+        const uintptr_t a0 = (uintptr_t)(text + src), a1 = a0 + L;
+        // forward strand
+        uint32_t f_probed = NONE32;
+        int f_left = -1, f_right = -1;
+        // reverse strand, positions in ITS coordinates
+        uint32_t r_lctg = NONE32, ra_ctg = NONE32, rb_ctg = NONE32;
+        int r_left = -1, ra_pos = -1, rb_pos = -1;
+        uint64_t wf = 0, wr = 0;
+        int i = 0;
+        for (uintptr_t wa = a0 & ~(uintptr_t)3; wa < a1; wa += 4) {
+            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(wa));  // (inside the text buffer: it is read in whole 64-byte chunks)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uintptr_t a = wa + b;
+                if (a < a0 || a >= a1) continue;
+                const uint32_t cc = ST_CODES[(word >> (8 * b)) & 0xffu];
+                wf = ((wf << 2) | (cc & 3u)) & kmask;
+                wr = (wr >> 2) | ((uint64_t)(cc >> 2) << top);
+                if (i >= sk - 1) {
+                    if (bloom_maybe(bloom, wf)) {
+                        const uint32_t v = probe_lookup(wf, keys, vals, mask);
+                        if (v != NONE32) {
+                            if (!(v & 1u)) {
+                                if (f_left < 0) { f_probed = v >> 1; f_left = i; }
+                            } else if (f_probed != (v >> 1)) {
+                                f_right = i;
+                            }
+                        }
+                    }
+                    if (bloom_maybe(bloom, wr)) {
+                        const uint32_t v = probe_lookup(wr, keys, vals, mask);
+                        if (v != NONE32) {
+                            const int ip = (int)L + sk - 2 - i;  // where the reverse strand shows this window
+                            if (!(v & 1u)) { r_left = ip; r_lctg = v >> 1; }
+                            else if (ra_pos < 0) { ra_pos = ip; ra_ctg = v >> 1; }
+                            else if (rb_pos < 0 && (v >> 1) != ra_ctg) { rb_pos = ip; rb_ctg = v >> 1; }
+                        }
+                    }
+                }
+                i++;
             }
         }
-        if (left >= 0 && right >= 0 && left < right) {
-            const uint32_t start = (uint32_t)(left - sk + 1), len = (uint32_t)right + 1u - start;
+        int r_right = -1;
+        if (r_left >= 0) {
+            if (ra_pos >= 0 && ra_ctg != r_lctg) r_right = ra_pos;
+            else if (rb_pos >= 0 && rb_ctg != r_lctg) r_right = rb_pos;
+        }
+        if (f_left >= 0 && f_right >= 0 && f_left < f_right) {
+            const uint32_t start = (uint32_t)(f_left - sk + 1), len = (uint32_t)f_right + 1u - start;
             const unsigned long long idx = atomicAdd(&ctr[0], 1ull);
             const unsigned long long o = atomicAdd(&ctr[1], (unsigned long long)len);
-            if (idx < hit_cap) hits[idx] = Hit{rd_src[r], o, L, start, len, 0u, 0u, strand};
+            if (idx < hit_cap) hits[idx] = Hit{src, o, L, start, len, 0u, 0u, 0u};
+        }
+        if (r_left >= 0 && r_right >= 0 && r_left < r_right) {
+            const uint32_t start = (uint32_t)(r_left - sk + 1), len = (uint32_t)r_right + 1u - start;
+            const unsigned long long idx = atomicAdd(&ctr[0], 1ull);
+            const unsigned long long o = atomicAdd(&ctr[1], (unsigned long long)len);
+            if (idx < hit_cap) hits[idx] = Hit{src, o, L, start, len, 0u, 0u, 1u};
         }
     }
 }

@@ -19,6 +19,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long cmp, unsigned long long v) { unsigned long long o = *p; if (o == cmp) *p = v; return o; }
 static inline uint32_t atomicCAS(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
 static inline void __syncwarp() {}
 namespace rfx {
 struct U64x3 { uint64_t a, b, c; };
@@ -59,11 +60,17 @@ int emu_stitch(uint64_t n, const uint64_t* off, const char* bases, const int32_t
     uint64_t cap = 1024;
     while (cap < 4 * n + 16) cap <<= 1;
     std::vector<uint64_t> keys(cap, ~0ull), firstk(n + 1, 0);
-    std::vector<uint32_t> vals(cap, NONE32);
+    std::vector<uint32_t> vals(cap, NONE32), bloom(ST_BLOOM_BITS / 32, 0);
+    // the scan reads the text in aligned 4-byte words: give it the slack the device buffer has
+    uint64_t text_len = 0;
+    for (uint64_t r = 0; r < n_reads; r++) if (starts[r] + lens[r] > text_len) text_len = starts[r] + lens[r];
+    std::vector<uint8_t> padded(text_len + 16, 0);
+    if (text_len) memcpy(padded.data() + 8, text, text_len);
+    text = padded.data() + 8;
     unsigned long long ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (n) {
         launch(G, B, [&] { probe_first_kernel(off, bases, n, k, firstk.data()); });
-        launch(G, B, [&] { probe_insert_kernel(off, bases, cl, cr, n, k, firstk.data(), keys.data(), vals.data(), cap - 1, &ctr[2]); });
+        launch(G, B, [&] { probe_insert_kernel(off, bases, cl, cr, n, k, firstk.data(), keys.data(), vals.data(), cap - 1, bloom.data(), &ctr[2]); });
         launch(G, B, [&] { count_keys_kernel(keys.data(), cap, &ctr[3]); });
     }
     out->stats[0] = ctr[3];
@@ -78,7 +85,7 @@ int emu_stitch(uint64_t n, const uint64_t* off, const char* bases, const int32_t
         const uint64_t nr = n_reads - r0 < chunk_reads ? n_reads - r0 : chunk_reads;
         for (int attempt = 0;; attempt++) {
             ctr[0] = ctr[1] = 0;
-            launch(G, B, [&] { stitch_scan_kernel(text, starts + r0, elen.data() + r0, nr, k, keys.data(), vals.data(), cap - 1, hits.data(), hits.size(), ctr); });
+            launch(G, B, [&] { stitch_scan_kernel(text, starts + r0, elen.data() + r0, nr, k, keys.data(), vals.data(), cap - 1, bloom.data(), hits.data(), hits.size(), ctr); });
             if (ctr[0] <= hits.size()) break;
             if (attempt) return -2;
             hits.resize(ctr[0]);

@@ -220,6 +220,14 @@ def hand_cases():
                                                                   orc.revcomp_str(A1[-45:]) .join(["", ""]) ])
     # reads too short to be looked at (readLength - (k-1) <= 1) and exactly long enough
     cases["short reads"] = (k, [A1, B], [-2, -2], [-2, -2], [A1[-20:] + B[:1], A1[-20:] + B[:2], (A1[-20:] + B[:20])])
+    # several probes in one read: the first left-extendable hit and the LAST right-extendable hit of another contig count
+    cases["many probes"] = (k, [A1, A2, B, Cc], [-2, -2, -2, -2], [-2, -2, -2, -2],
+                            [A1[-30:] + "AC" + B[:25] + "GT" + A2[-25:] + "T" + Cc[:30], B[:25] + "GT" + A1[-30:] + "AC" + A1[:30] + "G" + Cc[:30] + A1[:25],
+                             A1[-30:] + "AC" + A1[:30] + "G" + A1[:25]])
+    # every case again with its reads handed over as the other strand: the same fragments must be found back to front
+    for name, (kk, ctg, le, ri, reads) in list(cases.items()):
+        if all(set(r) <= set("ACGT") for r in reads):
+            cases[name + " (reads as the other strand)"] = (kk, ctg, le, ri, [orc.revcomp_str(r) for r in reads])
     return cases
 
 
@@ -303,6 +311,27 @@ def test_stitch_on_thinly_covered_reads_oracle_and_host_kernels():
     G = synth.genome(300_000, seed=7).tobytes().decode()
     for c in want["contigs"]:  # error-free reads: whatever was stitched is still a piece of the genome
         assert c in G or orc.revcomp_str(c) in G
+
+
+def test_stitch_dense_probes_three_way():
+    """Tiny k: nearly every window of a read is some contig end, so the first-left / last-right-of-another-contig rule, probe
+    collisions and reads full of N are exercised on every read; oracle == literal transcription == kernels on the host."""
+    frags = 0
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        k = int(rng.choice([4, 5, 6, 7]))
+        nc = int(rng.integers(3, 14))
+        contigs = ["".join(rng.choice(list("ACGT"), int(rng.integers(61, 90)))) for _ in range(nc)]
+        left = [int(rng.choice([-1, -2, -5, -6, 3])) for _ in range(nc)]
+        right = [int(rng.choice([-1, -3, -5, -7, 2])) for _ in range(nc)]
+        reads = ["".join(rng.choice(list("ACGTN" if seed % 4 == 0 else "ACGT"), int(rng.integers(k - 1, 60)))) for _ in range(40)]
+        txt = fq(reads)
+        want = orc.stitch(contigs, left, right, txt, k, 0)
+        got = emu_stitch(contigs, left, right, txt, k, 0, chunk=9, cap0=2)
+        assert triples(want) == triples(got) == py_stitch(contigs, left, right, reads_of(txt), k, 0), seed
+        assert got["stats"] == list(want["stats"].values())
+        frags += want["stats"]["fragments"]
+    assert frags > 300
 
 
 def test_stitch_is_outside_the_k_range_of_the_class():
