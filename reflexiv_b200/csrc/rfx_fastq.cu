@@ -46,6 +46,73 @@ __device__ __forceinline__ uint64_t newline_mask64(const TextView& tv, uint64_t 
     return mask;
 }
 
+// The same chunk as two masks: the newlines, and those of them behind which an '@' follows (the first byte of the next line).
+// Pass 1 of the newline scan stores both (16 bytes per 64 bytes of text), so that pass 2 never reads the text again.
+__device__ __forceinline__ void chunk_masks(const TextView& tv, uint64_t chunk, uint64_t& nl_out, uint64_t& nl_at_out) {
+    const uint4* p = reinterpret_cast<const uint4*>(tv.aligned + chunk * 64);
+    uint64_t nl = 0, at = 0;
+#pragma unroll
+    for (int part = 0; part < 4; part++) {
+        const uint4 v = p[part];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t m16 = 0, a16 = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au), ea = __vcmpeq4(w[q], 0x40404040u);
+            m16 |= ((((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);
+            a16 |= ((((ea & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);
+        }
+        nl |= (uint64_t)m16 << (16 * part);
+        at |= (uint64_t)a16 << (16 * part);
+    }
+    const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
+    uint64_t valid = ~0ull;
+    if (p0 < 0) valid &= ~0ull << (uint32_t)(-p0);
+    const int64_t over = p0 + 64 - (int64_t)tv.len;
+    if (over > 0) valid &= over >= 64 ? 0ull : (~0ull >> (uint32_t)over);
+    nl &= valid;
+    at &= valid;
+    // the byte behind bit 63 is byte 0 of the next chunk
+    uint64_t next_at = 0;
+    if (p0 + 64 < (int64_t)tv.len && (nl >> 63)) next_at = tv.aligned[(chunk + 1) * 64] == '@' ? 1ull : 0ull;
+    nl_out = nl;
+    nl_at_out = nl & ((at >> 1) | (next_at << 63));
+}
+struct NewlineMaskIn {  // pass 1: counts the newlines of a chunk and leaves its masks behind
+    TextView tv;
+    ulonglong2* masks;
+    __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const {
+        uint64_t nl, nl_at;
+        chunk_masks(tv, chunk, nl, nl_at);
+        masks[chunk] = make_ulonglong2(nl, nl_at);
+        return __popcll(nl);
+    }
+};
+struct MaskCountIn {  // pass 2
+    const ulonglong2* masks;
+    __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const { return __popcll(masks[chunk].x); }
+};
+struct MaskOut {
+    TextView tv;
+    const ulonglong2* masks;
+    uint64_t* line_start;
+    uint8_t* line_at;
+    __device__ __forceinline__ void operator()(uint64_t chunk, uint64_t excl, uint64_t v) const {
+        if (!v) return;
+        const ulonglong2 m = masks[chunk];
+        uint64_t mask = m.x;
+        const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;
+        uint64_t idx = excl + 1;
+        while (mask) {
+            const int j = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            line_start[idx] = (uint64_t)(p0 + j) + 1;  // the line after this newline starts here
+            line_at[idx] = (uint8_t)((m.y >> j) & 1ull);
+            idx++;
+        }
+    }
+};
+
 struct NewlineIn {
     TextView tv;
     __device__ __forceinline__ uint64_t operator()(uint64_t chunk) const { return __popcll(newline_mask64(tv, chunk)); }
@@ -407,6 +474,12 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     ScanPlan<uint64_t> nl;
     RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n_chunks) * sizeof(uint64_t)));
     nl.bind(n_chunks, c->scan_ws.as<uint64_t>());
+    // pass 1 leaves the newline / '@' masks of every chunk behind (a quarter of the text), pass 2 works from them
+    const bool use_masks = !getenv("RFX_NEWLINE_REREAD");  // (measured alternative: pass 2 reads the text again)
+    if (use_masks) {
+        RFX_TRY(devbuf_reserve(c, c->nl_masks, (n_chunks + 1) * sizeof(ulonglong2)));
+        scan_prepare(nl, NewlineMaskIn{tv, c->nl_masks.as<ulonglong2>()}, OpAddU64{}, (uint64_t)0, st);
+    } else
     scan_prepare(nl, NewlineIn{tv}, OpAddU64{}, (uint64_t)0, st);
     c->launches += 2 * nl.levels;
     uint64_t n_newlines = 0;
@@ -416,7 +489,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     RFX_TRY(devbuf_reserve(c, c->line_at, n_newlines + 2));
     uint64_t* ls = c->line_start.as<uint64_t>();
     uint8_t* lat = c->line_at.as<uint8_t>();
-    scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, d_text, ls, lat}, OpAddU64{}, (uint64_t)0, st);
+    if (use_masks) scan_apply(nl, MaskCountIn{c->nl_masks.as<ulonglong2>()}, MaskOut{tv, c->nl_masks.as<ulonglong2>(), ls, lat}, OpAddU64{}, (uint64_t)0, st);
+    else scan_apply(nl, NewlineIn{tv}, NewlineOut{tv, d_text, ls, lat}, OpAddU64{}, (uint64_t)0, st);
     finish_lines_kernel<<<1, 1, 0, st>>>(d_text, len, nl.total, ls, lat, c->dstat.as<uint64_t>() + DS_FQ_NLINES);
     c->launches += 2;
     const int fmode = c->st_active ? RFX_FASTQ_RUN : c->prm.fastq_mode;  // the stitch stage always reads units (ReflexivDSMain.java:601-606)

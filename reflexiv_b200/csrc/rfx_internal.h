@@ -82,6 +82,7 @@ struct Ctx {
     DevBuf text;        // staging for host FASTQ text
     DevBuf line_start;  // u64[n_lines + 1]
     DevBuf line_at;     // u8[n_lines + 1] line starts with '@'
+    DevBuf nl_masks;    // ulonglong2[n_chunks] newline mask + newline-followed-by-'@' mask of every 64-byte chunk of the text
     DevBuf seq_flag;    // u32[n_lines]  NOT_A_READ, or the effective length of the read on that line
     DevBuf scan_ws;     // scan workspace
     DevBuf rd_src;      // u64[new reads] text offset of each read of the current push (scratch)
