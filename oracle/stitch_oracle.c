@@ -40,6 +40,10 @@
  *     Other records that happen to share a junction (k-1)-mer are left alone.  A closed ring of contigs and fragments is
  *     opened in front of the contig with the smallest first k-mer and keeps the closing fragment at its end (a record
  *     never meets itself).
+ * NOT REPRODUCED: reflexivKmerExtractionFromLowCoverageFragment (DSMain:1541-1562) builds a fragment whose extension is a multiple
+ *     of 31 bases long with an empty first block that lacks the length marker (firstBlock = 0: the marker line only fires at
+ *     i - subKmerSize == firstBlock - 1), so the reference's own length arithmetic is off by one base on that record.  Here such
+ *     a fragment is an ordinary one.
  */
 #define _GNU_SOURCE
 #include <stdlib.h>
