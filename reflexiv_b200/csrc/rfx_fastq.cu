@@ -11,73 +11,10 @@
 #include "rfx_internal.h"
 #include "rfx_scan.cuh"
 
+#include "rfx_newline.cuh"
+
 namespace rfx {
 
-// ------------------------------------------------------------------------------------------
-// newline scan: element = one 64-byte aligned chunk of the text
-// ------------------------------------------------------------------------------------------
-struct TextView {
-    const uint8_t* aligned;  // text pointer rounded down to 64 bytes
-    uint32_t delta;          // text - aligned
-    uint64_t len;
-};
-
-// newline positions of one 64-byte aligned chunk as a 64-bit mask
-__device__ __forceinline__ uint64_t newline_mask64(const TextView& tv, uint64_t chunk) {
-    const uint4* p = reinterpret_cast<const uint4*>(tv.aligned + chunk * 64);
-    uint64_t mask = 0;
-#pragma unroll
-    for (int part = 0; part < 4; part++) {
-        const uint4 v = p[part];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t m16 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au);                          // 0xff in every byte that is '\n'
-            m16 |= ((((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);  // movemask: one bit per byte
-        }
-        mask |= (uint64_t)m16 << (16 * part);
-    }
-    // drop bytes outside [0, len)
-    const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
-    if (p0 < 0) mask &= ~0ull << (uint32_t)(-p0);
-    const int64_t over = p0 + 64 - (int64_t)tv.len;
-    if (over > 0) mask &= over >= 64 ? 0ull : (~0ull >> (uint32_t)over);
-    return mask;
-}
-
-// The same chunk as two masks: the newlines, and those of them behind which an '@' follows (the first byte of the next line).
-// Pass 1 of the newline scan stores both (16 bytes per 64 bytes of text), so that pass 2 never reads the text again.
-__device__ __forceinline__ void chunk_masks(const TextView& tv, uint64_t chunk, uint64_t& nl_out, uint64_t& nl_at_out) {
-    const uint4* p = reinterpret_cast<const uint4*>(tv.aligned + chunk * 64);
-    uint64_t nl = 0, at = 0;
-#pragma unroll
-    for (int part = 0; part < 4; part++) {
-        const uint4 v = p[part];
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t m16 = 0, a16 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t eq = __vcmpeq4(w[q], 0x0a0a0a0au), ea = __vcmpeq4(w[q], 0x40404040u);
-            m16 |= ((((eq & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);
-            a16 |= ((((ea & 0x80808080u) >> 7) * 0x00204081u >> 21) & 0xfu) << (4 * q);
-        }
-        nl |= (uint64_t)m16 << (16 * part);
-        at |= (uint64_t)a16 << (16 * part);
-    }
-    const int64_t p0 = (int64_t)(chunk * 64) - (int64_t)tv.delta;  // text position of byte 0 of the chunk
-    uint64_t valid = ~0ull;
-    if (p0 < 0) valid &= ~0ull << (uint32_t)(-p0);
-    const int64_t over = p0 + 64 - (int64_t)tv.len;
-    if (over > 0) valid &= over >= 64 ? 0ull : (~0ull >> (uint32_t)over);
-    nl &= valid;
-    at &= valid;
-    // the byte behind bit 63 is byte 0 of the next chunk
-    uint64_t next_at = 0;
-    if (p0 + 64 < (int64_t)tv.len && (nl >> 63)) next_at = tv.aligned[(chunk + 1) * 64] == '@' ? 1ull : 0ull;
-    nl_out = nl;
-    nl_at_out = nl & ((at >> 1) | (next_at << 63));
-}
 struct NewlineMaskIn {  // pass 1: counts the newlines of a chunk and leaves its masks behind
     TextView tv;
     ulonglong2* masks;

@@ -296,3 +296,20 @@ def test_fork_filters_fuzz_on_dense_random_tables(orc, hostemu, k):
             ref = orc.sorted_rows(cnt["keys_hi"], cnt["keys_lo"], cnt["counts"], k, E, fold, kmax)
             hi, lo, le, ri = _emu_sorted(hostemu, cnt, k, E, fold, kmax + 3)
             assert np.array_equal(lo, ref["keys_lo"]) and np.array_equal(le, ref["left"]) and np.array_equal(ri, ref["right"]), (k, trial, E, fold)
+
+
+def test_newline_masks_equal_a_bytewise_scan():
+    """K1, rfx_newline.cuh: the per-chunk newline mask and the newline-followed-by-'@' mask (what pass 2 of the line scan works
+    from instead of the text) against a byte-by-byte scan: random texts, every alignment, garbage in front and behind."""
+    import ctypes as C
+    import os
+    import subprocess
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemu")
+    subprocess.run(["make", "-s", "-C", d], check=True)
+    E = C.CDLL(os.path.join(d, "libnewlineemu.so"))
+    E.emu_newline_masks.restype = C.c_int64
+    E.emu_newline_masks.argtypes = [C.c_uint32, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
+    lines = C.c_int64()
+    assert E.emu_newline_masks(3, 30000, 700, C.byref(lines)) == 0
+    assert lines.value > 1_000_000
+    assert E.emu_newline_masks(4, 2000, 5, C.byref(lines)) == 0  # texts shorter than a chunk, empty texts
