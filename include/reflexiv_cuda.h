@@ -182,7 +182,8 @@ int rfx_sorted_csv(rfx_ctx* ctx, char* out, uint64_t cap, uint64_t* n_bytes);
  * FASTQ filter (unclipped, as the reference reads units[1]) is scanned on both strands for a "left extendable" probe
  * followed by a "right extendable" probe of another contig, and the piece between them is kept as a fragment.
  * rfx_stitch_finish keeps one fragment per contig end, joins contig + fragment + contig chains and REPLACES the contigs
- * that rfx_contigs_size / rfx_contigs_copy return.  The order-dependent choices of the reference (probe collisions, which
+ * that rfx_contigs_size / rfx_contigs_copy return.  rfx_reset, rfx_count, rfx_load_counts*, rfx_assemble and rfx_sort_kmers
+ * abandon an open stage (its fragments refer to the contigs it was opened on).  The order-dependent choices of the reference (probe collisions, which
  * fragment of a run stays, rings) are fixed as DESIGN.md section 2 lists them. */
 typedef struct {
     uint64_t n_probes;      /* keys in the probe table */

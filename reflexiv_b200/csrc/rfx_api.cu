@@ -388,6 +388,7 @@ uint32_t rfx_choose_bins(rfx_ctx* c, uint64_t global_instances, int32_t n_shards
 int rfx_count(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    c->st_active = false;  // an open stitch stage is abandoned: its fragments refer to the contigs it was opened on
     if (c->shard_id >= 0 && c->n_seg > 0) RFX_TRY(stage_adopt_segments(c));
     else if (c->shard_id >= 0) RFX_TRY(stage_rebin(c));
     else if (!c->have_records) {
@@ -439,6 +440,7 @@ int rfx_counts_copy(rfx_ctx* c, uint64_t* keys, uint32_t* counts) {
 int rfx_load_counts(rfx_ctx* c, const uint64_t* keys, const uint32_t* counts, uint64_t n_rows) {
     if (!c || (n_rows && (!keys || !counts))) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    c->st_active = false;
     const size_t ksz = c->wide ? sizeof(u128) : sizeof(uint64_t);
     RFX_TRY(devbuf_reserve(c, c->keys, (n_rows + 1) * ksz));
     RFX_TRY(devbuf_reserve(c, c->counts, (n_rows + 1) * sizeof(uint32_t)));
@@ -496,6 +498,7 @@ int rfx_counts_csv(rfx_ctx* c, char* out, uint64_t cap, uint64_t* n_bytes) {
 int rfx_assemble(rfx_ctx* c) {
     if (!c) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    c->st_active = false;  // an open stitch stage is abandoned: its fragments refer to the contigs it was opened on
     return stage_graph(c);
 }
 
@@ -571,6 +574,7 @@ int rfx_oriented_copy(rfx_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, int32_t*
 int rfx_sort_kmers(rfx_ctx* c, int32_t min_error_coverage, double min_repeat_fold, int32_t max_kmer_size) {
     if (!c) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    c->st_active = false;  // an open stitch stage is abandoned: its fragments refer to the contigs it was opened on
     return stage_sorted(c, min_error_coverage, min_repeat_fold, max_kmer_size);
 }
 
@@ -724,6 +728,7 @@ int rfx_counts_device(rfx_ctx* c, const void** d_keys, const uint32_t** d_counts
 int rfx_load_counts_device(rfx_ctx* c, const void* d_keys, const uint32_t* d_counts, uint64_t n_rows, int32_t append) {
     if (!c || (n_rows && (!d_keys || !d_counts))) return RFX_E_INVALID;
     cudaSetDevice(c->prm.device);
+    c->st_active = false;
     const size_t ksz = c->wide ? 16 : 8;
     const uint64_t base = (append && c->have_counts) ? c->n_rows : 0;
     RFX_TRY(devbuf_reserve(c, c->keys, (base + n_rows + 1) * ksz, base > 0));
