@@ -420,6 +420,15 @@ def test_stitch_error_paths():
         with pytest.raises(R.RfxError) as e:
             ctx.stitch_begin()  # no table yet
         assert e.value.code == _lib.RFX_E_STATE
+    with R.ReflexivContext(R.DefaultParam(kmerSize=31, minKmerCoverage=3), device=0) as ctx:
+        ctx.push_fastq(txt)
+        ctx.count()
+        ctx.stitch_begin()
+        ctx.assemble()  # abandons the open stage: its fragments would refer to the contigs it was opened on
+        with pytest.raises(R.RfxError) as e:
+            ctx.stitch_finish()
+        assert e.value.code == _lib.RFX_E_STATE
+        assert len(ctx.contigs()) > 0
     with R.ReflexivContext(R.DefaultParam(kmerSize=41, minKmerCoverage=3), device=0) as ctx:
         ctx.push_fastq(txt)
         ctx.count()
