@@ -204,14 +204,35 @@ struct ReadIn {
     __device__ __forceinline__ uint32_t eff(uint64_t i) const {
         return seq_eff ? seq_eff[i] : effective_read_len((int64_t)L.len(i), k, fc, ec);
     }
+    __device__ __forceinline__ uint64_t src(uint64_t i) const { return L.start[i] + (uint64_t)fc; }
     __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
         const uint32_t e = eff(i);
         if (e == NOT_A_READ) return 0ull;
         return (1ull << 32) | (uint64_t)((e + 31u) >> 5);
     }
 };
-struct ReadOut {
-    ReadIn in;
+// Whole 4-line records (fq_regular_check_kernel said so): element r is the sequence line 4 r + seq_pos -- a quarter of the elements
+// of the scan over lines, and no per-line array of read flags in between.  A unit whose quality line is not among the lines known
+// to exist is no read yet (DSFastqFilterWithQual returns the unit at its fourth line, ReflexivDSMain.java:4056-4059).
+struct RegularReadIn {
+    Lines L;
+    uint64_t n_known;
+    uint32_t seq_pos;
+    int k, fc, ec;
+    __device__ __forceinline__ uint64_t line(uint64_t r) const { return 4 * r + seq_pos; }
+    __device__ __forceinline__ uint32_t eff(uint64_t r) const {
+        const uint64_t i = line(r);
+        return (i < L.n_lines && i + 2 < n_known) ? effective_read_len((int64_t)L.len(i), k, fc, ec) : NOT_A_READ;
+    }
+    __device__ __forceinline__ uint64_t src(uint64_t r) const { return L.start[line(r)] + (uint64_t)fc; }
+    __device__ __forceinline__ uint64_t operator()(uint64_t r) const {
+        const uint32_t e = eff(r);
+        if (e == NOT_A_READ) return 0ull;
+        return (1ull << 32) | (uint64_t)((e + 31u) >> 5);
+    }
+};
+template <class In> struct ReadOutT {
+    In in;
     uint64_t read_base, word_base;
     uint64_t* rd_src;
     uint32_t* rd_len;
@@ -220,7 +241,7 @@ struct ReadOut {
         if (!v) return;
         const uint32_t e = in.eff(i);
         const uint64_t r = excl >> 32;
-        rd_src[r] = in.L.start[i] + (uint64_t)in.fc;
+        rd_src[r] = in.src(i);
         rd_len[read_base + r] = e;
         rd_woff[read_base + r] = word_base + (excl & 0xffffffffull);
     }
@@ -339,15 +360,12 @@ static inline int parse_fc(const Ctx* c) { return c->st_active ? 0 : c->prm.fron
 static inline int parse_ec(const Ctx* c) { return c->st_active ? 0 : c->prm.end_clip; }
 
 // Builds the read table for `n_lines` lines and appends the packed reads to the context.
-static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* seq_flag) {
+template <class In> static int append_reads_from(Ctx* c, const uint8_t* d_text, In in, uint64_t n_elems) {
     cudaStream_t st = c->stream;
-    if (L.n_lines && (L.start == nullptr)) return ctx_fail(c, RFX_E_INVALID, "append_reads: no line table");
+    typedef ReadOutT<In> ReadOut;
     ScanPlan<uint64_t> plan;
-    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(L.n_lines) * sizeof(uint64_t)));
-    plan.bind(L.n_lines, c->scan_ws.as<uint64_t>());
-    // While the stitch stage is open (rfx_stitch.cu) the reads are the UNclipped sequence lines of DSLowCoverageReadDetection
-    // (ReflexivDSMain.java:1467-1475: read = units[1], skipped when readLength - (k-1) <= 1) and are scanned, not stored.
-    ReadIn in{L, seq_flag, parse_k(c), parse_fc(c), parse_ec(c)};
+    RFX_TRY(devbuf_reserve(c, c->scan_ws, ScanPlan<uint64_t>::workspace_elems(n_elems) * sizeof(uint64_t)));
+    plan.bind(n_elems, c->scan_ws.as<uint64_t>());
     scan_prepare(plan, in, OpAddU64{}, (uint64_t)0, st);
     c->launches += 2 * plan.levels;
     uint64_t tot = 0;
@@ -392,6 +410,18 @@ static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* 
     } while (0);
     return rc;
 }
+
+// While the stitch stage is open (rfx_stitch.cu) the reads are the UNclipped sequence lines of DSLowCoverageReadDetection
+// (ReflexivDSMain.java:1467-1475: read = units[1], skipped when readLength - (k-1) <= 1) and are scanned, not stored.
+static int append_reads(Ctx* c, const uint8_t* d_text, Lines L, const uint32_t* seq_flag) {
+    if (L.n_lines && (L.start == nullptr)) return ctx_fail(c, RFX_E_INVALID, "append_reads: no line table");
+    return append_reads_from(c, d_text, ReadIn{L, seq_flag, parse_k(c), parse_fc(c), parse_ec(c)}, L.n_lines);
+}
+static int append_reads_regular(Ctx* c, const uint8_t* d_text, Lines L, uint64_t n_known, uint32_t seq_pos) {
+    const uint64_t n_rec = L.n_lines > seq_pos ? (L.n_lines - seq_pos + 3) / 4 : 0;
+    return append_reads_from(c, d_text, RegularReadIn{L, n_known, seq_pos, parse_k(c), parse_fc(c), parse_ec(c)}, n_rec);
+}
+__global__ void fq_state_next_kernel(unsigned long long* dstat) { dstat[DS_FQ_STATE] = dstat[DS_FQ_NEXT]; }
 
 // One chunk of FASTQ text (whole lines).  `first_chunk` resets the carried lineMark; `more_follows` promises that at
 // least two more lines come after this chunk, so a unit that starts in its last lines is known to complete.
@@ -447,6 +477,13 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
     Lines L{d_text, ls, n_lines, 1u};
     RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
     const uint32_t* flags = c->seq_flag.as<uint32_t>();
+    if (try_regular && !fq[1] && !getenv("RFX_FASTQ_LINE_FLAGS")) {  // (measured alternative: per-line flags + the scan over lines)
+        fq_state_next_kernel<<<1, 1, 0, st>>>(c->dstat.as<unsigned long long>());
+        c->launches++;
+        const int rc = append_reads_regular(c, d_text, L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2]);
+        c->ms[0] += stage_end(c);
+        return rc;
+    }
     if (try_regular && !fq[1]) {
         fq_regular_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2], c->seq_flag.as<uint32_t>(), parse_k(c),
                                                                        parse_fc(c), parse_ec(c), c->dstat.as<unsigned long long>());
