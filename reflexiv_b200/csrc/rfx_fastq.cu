@@ -475,8 +475,6 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
 
     // 2. which lines are reads
     Lines L{d_text, ls, n_lines, 1u};
-    RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
-    const uint32_t* flags = c->seq_flag.as<uint32_t>();
     if (try_regular && !fq[1] && !getenv("RFX_FASTQ_LINE_FLAGS")) {  // (measured alternative: per-line flags + the scan over lines)
         fq_state_next_kernel<<<1, 1, 0, st>>>(c->dstat.as<unsigned long long>());
         c->launches++;
@@ -484,6 +482,8 @@ int stage_parse_fastq(Ctx* c, const uint8_t* d_text, size_t len, bool first_chun
         c->ms[0] += stage_end(c);
         return rc;
     }
+    RFX_TRY(devbuf_reserve(c, c->seq_flag, n_lines * sizeof(uint32_t)));
+    const uint32_t* flags = c->seq_flag.as<uint32_t>();
     if (try_regular && !fq[1]) {
         fq_regular_lines_kernel<<<grid_for(n_lines, 256), 256, 0, st>>>(L, n_lines + (more_follows ? 2u : 0u), (uint32_t)fq[2], c->seq_flag.as<uint32_t>(), parse_k(c),
                                                                        parse_fc(c), parse_ec(c), c->dstat.as<unsigned long long>());
