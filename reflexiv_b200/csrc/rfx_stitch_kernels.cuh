@@ -292,7 +292,8 @@ __global__ void chain_heads_kernel(uint64_t n, const uint32_t* __restrict__ nxt,
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         if (prv[c] != NONE32) continue;
         role[c] = nxt[c] != NONE32 ? 1 : 0;
-        for (uint32_t cur = next_ctg((uint32_t)c, nxt, prv, f); cur != NONE32; cur = next_ctg(cur, nxt, prv, f)) role[cur] = 2;
+        uint64_t steps = 0;  // (every walk below is bounded by the number of contigs: a chain cannot be longer)
+        for (uint32_t cur = next_ctg((uint32_t)c, nxt, prv, f); cur != NONE32 && steps < n; cur = next_ctg(cur, nxt, prv, f), steps++) role[cur] = 2;
     }
 }
 // what no head reached lies on a ring: its member with the smallest first k-mer becomes the head (a record never meets itself)
@@ -301,7 +302,8 @@ __global__ void ring_heads_kernel(uint64_t n, const uint32_t* __restrict__ nxt, 
     for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         if (prv[c] == NONE32 || role[c] == 2) continue;
         bool smallest = true;
-        for (uint32_t cur = next_ctg((uint32_t)c, nxt, prv, f); cur != (uint32_t)c && cur != NONE32; cur = next_ctg(cur, nxt, prv, f))
+        uint64_t steps = 0;
+        for (uint32_t cur = next_ctg((uint32_t)c, nxt, prv, f); cur != (uint32_t)c && cur != NONE32 && steps < n; cur = next_ctg(cur, nxt, prv, f), steps++)
             if (firstk[cur] < firstk[c]) { smallest = false; break; }
         if (smallest) { role[c] = 3; atomicAdd(n_rings, 1ull); }
     }
@@ -319,7 +321,7 @@ __global__ void chain_sizes_kernel(uint64_t n, int k, int min_contig, const uint
             len = off[c + 1] - off[c];
             right = cr[c];
             uint32_t cur = (uint32_t)c;
-            while (nxt[cur] != NONE32) {
+            for (uint64_t steps = 0; nxt[cur] != NONE32 && steps < n; steps++) {
                 const Frag F = f[nxt[cur]];
                 len += F.len - sk;
                 right = -10000000;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(256) chain_gather_kernel(uint64_t n, int k, co
         for (uint64_t j = threadIdx.x; j < l0; j += blockDim.x) dst[j] = bases[off[c] + j];
         dst += l0;
         uint32_t cur = (uint32_t)c;
-        while (nxt[cur] != NONE32) {
+        for (uint64_t steps = 0; nxt[cur] != NONE32 && steps < n; steps++) {
             const Frag F = f[nxt[cur]];
             for (uint64_t j = threadIdx.x; j + sk < F.len; j += blockDim.x) dst[j] = "ACGT"[codes[F.off + sk + j]];
             dst += F.len - sk;
