@@ -173,7 +173,8 @@ int rfx_sorted_csv(rfx_ctx* ctx, char* out, uint64_t cap, uint64_t* n_bytes);
  * Replaces the `if (param.stitch)` branch of ReflexivDSMain.assemblyFromKmer() (pipeline/ReflexivDSMain.java:585-672):
  * DSLowCoverageSubKmerExtraction (:1211-1268) + SubKmerProbRowToHash (:109-118) + the broadcast, the second pass over the
  * FASTQ with DSLowCoverageReadDetection (:1448-1612), DSFilterRepeatLowCoverageFragment (:922-1010), the union and the second
- * extension loop (:640-670).  k <= 31 (that class is the k <= 31 assembler), one GPU.
+ * extension loop (:640-670).  One GPU.  For k > 31 the reference's own branch (ReflexivDSMain64.java:715-790) can never cut a read -- it
+ * looks a Long up in a Hashtable keyed by List<Long> (:1562-1600, :119-131) -- so there the stage returns the plain assembly.
  *   rfx_load_counts | rfx_count  ->  rfx_stitch_begin  ->  rfx_push_fastq* (any number of calls)  ->  rfx_stitch_finish
  * rfx_stitch_begin runs the assembly itself (as rfx_assemble, but every record of the extension is kept whatever its
  * length: the -mincontig rule applies to the stitched set, as in the reference where DSKmerToContig runs last) and puts

@@ -217,7 +217,7 @@ def stitch(contigs, left, right, txt, k: int, min_contig: int = 500):
     rc = lib().orc_stitch(len(contigs), offs.ctypes.data, bb.ctypes.data, le.ctypes.data, ri.ctypes.data, a.ctypes.data,
                           starts.ctypes.data, lens.ctypes.data, len(starts), k, min_contig, C.byref(c), stats.ctypes.data)
     if rc != 0:
-        raise ValueError(f"orc_stitch: k = {k} is outside ReflexivDSMain's range ({rc})")
+        raise ValueError(f"orc_stitch: k = {k} is outside the reference's range ({rc})")
     out = _contigs_out(c)
     out["stats"] = dict(zip(STITCH_STATS, stats.tolist()))
     lib().orc_contigs_free(C.byref(c))

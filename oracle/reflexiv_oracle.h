@@ -89,7 +89,8 @@ void orc_contigs_free(orc_contigs *c);
 
 /* -stitch low-coverage read rescue ------------------------------ */
 /* pipeline/ReflexivDSMain.java:585-672 with DSLowCoverageSubKmerExtraction (:1211-1268), DSLowCoverageReadDetection
- * (:1448-1612) and DSFilterRepeatLowCoverageFragment (:922-1010); k <= 31 (returns -1 otherwise).  PARITY UNPINNED, see
+ * (:1448-1612) and DSFilterRepeatLowCoverageFragment (:922-1010); for k > 31 (ReflexivDSMain64) the reference's probe
+ * lookup can never match and the contigs come back unchanged (stitch_oracle.c).  PARITY UNPINNED, see
  * stitch_oracle.c.  Input: ALL contig records of the extension (assemble with min_contig 0) and the reads the `run`
  * FASTQ filter keeps (orc_fastq_reads, UNclipped).  Output: the contig set after stitching, filtered like A10.
  * stats[6]: probes, fragments cut, after pass 1, joined on both sides, stitched records, rings. */

@@ -152,14 +152,18 @@ int orc_stitch(int64_t n_ctg, const uint64_t *off, const char *bases, const int3
                int k, int min_contig, orc_contigs *out, int64_t *stats) {
     memset(out, 0, sizeof(*out));
     for (int i = 0; i < 6; i++) stats[i] = 0;
-    if (k < 2 || k > 31) return -1; /* ReflexivDSMain is the k <= 31 assembler */
+    if (k < 2 || k > 63) return -1;
+    /* k > 31 is ReflexivDSMain64: its DSLowCoverageReadDetection (DSMain64:1562-1600) looks a Long up in a
+     * Hashtable<List<Long>, Integer> (SubKmerProbRowToHash, DSMain64:119-131); a Long never equals a List, no read is
+     * ever cut, the contigs come out as they went in.  Restated as: no probes. */
+    const int no_probe_can_match = k > 31;
     const int sk = k - 1;
 
     /* ---- S1 ---- */
     probe_t *pr = (probe_t *)malloc((size_t)(2 * n_ctg + 1) * sizeof(probe_t));
     uint64_t *firstk = (uint64_t *)calloc((size_t)n_ctg + 1, sizeof(uint64_t));
     int64_t np = 0;
-    for (int64_t c = 0; c < n_ctg; c++) {
+    for (int64_t c = 0; c < n_ctg && !no_probe_can_match; c++) {
         const char *s = bases + off[c];
         const int64_t len = (int64_t)(off[c + 1] - off[c]);
         if (len >= k) { uint64_t f = 0; for (int j = 0; j < k; j++) f = (f << 2) | nv((unsigned char)s[j]); firstk[c] = f; }

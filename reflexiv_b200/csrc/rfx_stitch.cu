@@ -1,4 +1,5 @@
-// rfx_stitch.cu -- `reflexiv run -stitch`: the low-coverage read rescue of ReflexivDSMain.java:585-672, k <= 31.
+// rfx_stitch.cu -- `reflexiv run -stitch`: the low-coverage read rescue of ReflexivDSMain.java:585-672; for k > 31 the
+// reference's own branch can never cut a read (see stage_stitch_begin) and the stage is the plain assembly.
 //
 //   reference (pipeline/ReflexivDSMain.java)                          here
 //   DSLowCoverageSubKmerExtraction :1211-1268 + collect +            probe_first_kernel / probe_insert_kernel: an open-addressing
@@ -38,8 +39,10 @@ enum { SC_HITS = 0, SC_CODES = 1, SC_PUT = 2, SC_KEYS = 3, SC_PASS1 = 4, SC_BOTH
 }  // namespace
 
 int stage_stitch_begin(Ctx* c) {
-    if (c->k > 31)
-        return ctx_fail(c, RFX_E_UNSUPPORTED, "-stitch with k = %d: the rescue of ReflexivDSMain.java:585-672 belongs to the k <= 31 assembler", c->k);
+    // k > 31 (ReflexivDSMain64.java:715-790): DSLowCoverageReadDetection rolls the read's (k-1)-mer into ONE Long and asks a
+    // Hashtable<List<Long>, Integer> for it (:1562-1600 against SubKmerProbRowToHash :119-131) -- a Long never equals a List, so
+    // no read is ever cut there and the branch leaves the contigs as they are.  Same here: the stage opens with an empty probe table.
+    const bool no_probe_can_match = c->k > 31;
     if (c->arena) return ctx_fail(c, RFX_E_UNSUPPORTED, "-stitch runs on one GPU (assemble the shard tables with rfx_load_counts_device + rfx_assemble first)");
     if (!c->have_counts) return ctx_fail(c, RFX_E_STATE, "rfx_stitch_begin: no count table (call rfx_count or rfx_load_counts first)");
     // every record of the extension takes part, whatever its length (the minContig rule is applied to the stitched set)
@@ -64,7 +67,7 @@ int stage_stitch_begin(Ctx* c) {
     RFX_CUDA(c, cudaMemsetAsync(c->st_vals.p, 0xff, cap * sizeof(uint32_t), st));
     RFX_CUDA(c, cudaMemsetAsync(c->st_ctr.p, 0, SC_N * sizeof(uint64_t), st));
     unsigned long long* ctr = c->st_ctr.as<unsigned long long>();
-    if (n) {
+    if (n && !no_probe_can_match) {
         probe_first_kernel<<<grid_for_n(n), 256, 0, st>>>(c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>(), n, c->k, c->st_firstk.as<uint64_t>());
         probe_insert_kernel<<<grid_for_n(n), 256, 0, st>>>(c->ctg_off.as<uint64_t>(), c->ctg_bases.as<char>(), c->ctg_left.as<int32_t>(), c->ctg_right.as<int32_t>(), n,
                                                           c->k, c->st_firstk.as<uint64_t>(), c->st_keys.as<uint64_t>(), c->st_vals.as<uint32_t>(), cap - 1, c->st_bloom.as<uint32_t>(), ctr + SC_PUT);

@@ -334,9 +334,16 @@ def test_stitch_dense_probes_three_way():
     assert frags > 300
 
 
-def test_stitch_is_outside_the_k_range_of_the_class():
+def test_stitch_for_k_above_31_is_the_plain_assembly():
+    """ReflexivDSMain64's stitch branch asks a Hashtable<List<Long>, Integer> for a Long (DSMain64:1562-1600 against :119-131): no
+    read is ever cut.  The restatement keeps the contigs (the -mincontig rule still applies) and refuses k > 63."""
+    k = 33
+    _, contigs, left, right, txt = _as_fastq_case(hand_cases()["bridge"])
+    res = orc.stitch(contigs, left, right, txt, k, min_contig=0)
+    assert triples(res) == sorted(zip(contigs, left, right)) and res["stats"]["probes"] == 0 and res["stats"]["fragments"] == 0
+    assert [len(c) for c in orc.stitch(contigs, left, right, txt, k, min_contig=100)["contigs"]] == [len(c) for c in contigs if len(c) >= 100]
     with pytest.raises(ValueError):
-        orc.stitch(["A" * 100], [-2], [-2], fq(["A" * 80]), 33)
+        orc.stitch(["A" * 100], [-2], [-2], fq(["A" * 80]), 64)
 
 
 # ---- GPU tests (through the C ABI) ----------------------------------------------------------------------------------------
@@ -429,12 +436,16 @@ def test_stitch_error_paths():
             ctx.stitch_finish()
         assert e.value.code == _lib.RFX_E_STATE
         assert len(ctx.contigs()) > 0
-    with R.ReflexivContext(R.DefaultParam(kmerSize=41, minKmerCoverage=3), device=0) as ctx:
+    # k > 31: the reference's branch can never cut a read (ReflexivDSMain64.java:1562-1600): the stage is the plain assembly
+    with R.ReflexivContext(R.DefaultParam(kmerSize=41, minKmerCoverage=3, minContig=100), device=0) as ctx:
         ctx.push_fastq(txt)
         ctx.count()
-        with pytest.raises(R.RfxError) as e:
-            ctx.stitch_begin()
-        assert e.value.code == _lib.RFX_E_UNSUPPORTED
+        ctx.assemble()
+        plain = sorted(ctx.contigs())
+        assert ctx.stitch_begin()["n_probes"] == 0
+        ctx.push_fastq(txt)
+        st = ctx.stitch_finish()
+        assert sorted(ctx.contigs()) == plain and st["n_fragments"] == 0 and st["n_reads"] > 0 and len(plain) > 0
 
 
 @pytest.mark.gpu
