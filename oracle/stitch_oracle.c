@@ -72,6 +72,7 @@ static int cmp_probe(const void *a, const void *b) {
     const probe_t *x = (const probe_t *)a, *y = (const probe_t *)b;
     if (x->key != y->key) return x->key < y->key ? -1 : 1;
     if (x->first != y->first) return x->first < y->first ? -1 : 1;
+    if (x->ctg != y->ctg) return x->ctg < y->ctg ? -1 : 1; /* (never needed on an assembly: every k-mer starts one contig) */
     /* direction 0 is put after direction 1 of the same contig (DSMain:1231-1264) */
     return (x->dir == 0) - (y->dir == 0);
 }
@@ -235,7 +236,7 @@ int orc_stitch(int64_t n_ctg, const uint64_t *off, const char *bases, const int3
         while (nxt[cur] >= 0 && ATTACHED(nxt[cur]) && steps <= n_ctg) {
             cur = fv.v[nxt[cur]].right_ctg; steps++;
             if (cur == c) { ring = 1; break; }
-            if (firstk[cur] < firstk[best]) best = cur;
+            if (firstk[cur] < firstk[best] || (firstk[cur] == firstk[best] && cur < best)) best = cur;
         }
         if (!ring) continue;
         cur = c;

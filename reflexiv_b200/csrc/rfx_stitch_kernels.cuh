@@ -66,6 +66,7 @@ __global__ void probe_first_kernel(const uint64_t* __restrict__ off, const char*
 __device__ __forceinline__ bool probe_after(uint32_t a, uint32_t b, const uint64_t* firstk) {
     const uint64_t fa = firstk[a >> 1], fb = firstk[b >> 1];
     if (fa != fb) return fa > fb;
+    if ((a >> 1) != (b >> 1)) return (a >> 1) > (b >> 1);  // (two contigs never start with the same k-mer; a total order all the same)
     return (a & 1u) < (b & 1u);
 }
 __device__ void probe_insert(uint64_t key, uint32_t val, uint64_t* keys, uint32_t* vals, uint64_t mask, const uint64_t* firstk, uint32_t* bloom) {
@@ -304,7 +305,7 @@ __global__ void ring_heads_kernel(uint64_t n, const uint32_t* __restrict__ nxt, 
         bool smallest = true;
         uint64_t steps = 0;
         for (uint32_t cur = next_ctg((uint32_t)c, nxt, prv, f); cur != (uint32_t)c && cur != NONE32 && steps < n; cur = next_ctg(cur, nxt, prv, f), steps++)
-            if (firstk[cur] < firstk[c]) { smallest = false; break; }
+            if (firstk[cur] < firstk[c] || (firstk[cur] == firstk[c] && cur < (uint32_t)c)) { smallest = false; break; }
         if (smallest) { role[c] = 3; atomicAdd(n_rings, 1ull); }
     }
 }

@@ -332,6 +332,21 @@ def test_stitch_dense_probes_three_way():
         assert got["stats"] == list(want["stats"].values())
         frags += want["stats"]["fragments"]
     assert frags > 300
+    # contigs that start with the same k-mer (no assembly has them, a random set at k = 4 does): the probe of the later contig
+    # stays and a ring is opened at the earlier one, in all three
+    for seed in (2001, 2139, 2955, 3741):
+        rng = np.random.default_rng(seed)
+        k = int(rng.choice([4, 5, 6, 7, 9]))
+        nc = int(rng.integers(2, 16))
+        contigs = ["".join(rng.choice(list("ACGT"), int(rng.integers(55, 95)))) for _ in range(nc)]
+        left = [int(rng.choice([-1, -2, -5, -6, 3, -10000000])) for _ in range(nc)]
+        right = [int(rng.choice([-1, -3, -5, -7, 2, -10000000])) for _ in range(nc)]
+        reads = ["".join(rng.choice(list("ACGTNacgtu" if seed % 5 == 0 else "ACGT"), int(rng.integers(max(1, k - 2), 70)))) for _ in range(int(rng.integers(5, 60)))]
+        txt = fq(reads)
+        want = orc.stitch(contigs, left, right, txt, k, 0)
+        got = emu_stitch(contigs, left, right, txt, k, 0)
+        assert triples(want) == triples(got) == py_stitch(contigs, left, right, reads_of(txt), k, 0), seed
+        assert got["stats"] == list(want["stats"].values())
 
 
 def test_stitch_for_k_above_31_is_the_plain_assembly():
