@@ -69,15 +69,17 @@ public final class MainCuda {
         }
     }
 
-    /** ReflexivDSMain.assembly() :123-357, or assemblyFromKmer() :362-713 when -kmerc is given without -fastq */
+    /** ReflexivDSMain.assembly() :123-357, or assemblyFromKmer() :362-713 when -kmerc is given (Pipelines.java:83-84; a -fastq next to it
+     *  is only read by the -stitch branch, Parameter.java:571-575) */
     static void run(DefaultParam p, int device) throws IOException {
-        boolean fromKmer = p.inputFqPath == null && p.inputKmerPath != null;
+        boolean fromKmer = p.inputKmerPath != null;
         Path out = fromKmer ? Paths.get(p.outputPath, "Assemble_" + p.kmerSize) : Paths.get(p.outputPath);
         if (Files.exists(out)) throw new IOException("Output directory " + out + " already exists");  // saveAsTextFile refuses
         try (ReflexivCuda gpu = new ReflexivCuda(p, false, device)) {
             if (fromKmer) loadCountTable(gpu, p, p.minKmerCoverage);
             else { pushInputs(gpu, p.inputFqPath); gpu.count(); }
             if (fromKmer && p.stitch) {                     // ReflexivDSMain.java:585-672: the FASTQ is read a second time
+                if (p.inputFqPath == null) throw new IOException("-stitch reads the FASTQ (ReflexivDSMain.java:599): give -fastq next to -kmerc");
                 gpu.stitchBegin();
                 pushInputs(gpu, p.inputFqPath);
                 gpu.stitchFinish();
