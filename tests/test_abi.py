@@ -102,6 +102,10 @@ def test_launcher_and_option_parsing():
     assert (q.kmerListInt, q.minRepeatFold) == ([21, 33], 2.0)
     with pytest.raises(ParseExit):
         Parameter(["-kmerc", "x", "-outfile", "o", "-klist", "21,zz"]).importCommandLine()
+    # -kmerc next to -fastq keeps both: the table is assembled (Pipelines.java:83-84), the FASTQ is only read by -stitch (Parameter.java:571-575)
+    b = Parameter(["-fastq", "y", "-kmerc", "x", "-outfile", "o", "-stitch"]).importCommandLine()
+    assert (b.inputKmerPath, b.inputFqPath, b.stitch) == ("x", "y", True)
+    assert Parameter(["-kmerc", "x", "-outfile", "o"]).importCommandLine().stitch is False
     with pytest.raises(ParseExit):
         ParameterOfCounter(["-fastq", "x", "-outfile", "o", "-mincontig", "5"]).importCommandLine()  # not a counter option
     c = ParameterOfCounter(["-fastq", "x", "-outfile", "o", "-kmer", "61", "-infmt", "line"]).importCommandLine()
